@@ -1,0 +1,195 @@
+"""Pins `oracle/egnn_oracle.py` against fixtures produced by the UNMODIFIED reference
+(tests/golden/make_golden.py) and, when /root/reference is present, against the live reference."""
+import math
+
+import pytest
+import torch
+
+from oracle import egnn_oracle as orc
+from oracle import ref_shim
+from tests.helpers import load_case, noise_dict, rel_err
+
+TOL = 2e-5  # fp32 restatement vs fp32 reference: summation order only
+
+
+def _fwd(case):
+    batch = orc.batch_to_frames(case["batch"])
+    with torch.no_grad():
+        return orc.model_forward(case["params"], batch, case["t"], case["T"])
+
+
+@pytest.mark.parametrize("name", ["fwd_shipped_p80.pt", "fwd_random_p96.pt", "fwd_shipped_p192.pt"])
+def test_forward_matches_reference(name):
+    case = load_case(name)
+    out = _fwd(case)
+    m = case["batch"]["mask"]
+    assert rel_err(orc.frames_to_tensor7(out["frames"])[m], case["out_frames"][m]) < TOL
+    assert rel_err(out["torsions"][m], case["out_torsions"][m]) < TOL
+
+
+def test_layer1_taps_match_reference():
+    case = load_case("fwd_shipped_p80.pt")
+    batch = orc.batch_to_frames(case["batch"])
+    p = case["params"]
+    B, N = batch["mask"].shape
+    h = torch.cat((batch["features"], torch.full((B, N, 1), case["t"] / case["T"])), -1)
+    pocket_h = torch.nn.functional.pad(batch["pocket_features"], (0, 1))
+    idx = torch.arange(16)
+    edge = torch.nn.functional.one_hot(15 + idx[:, None] - idx[None, :], 31)[None].expand(B, -1, -1, -1)
+    with torch.no_grad():
+        fr, tors, o = orc.egnn_layer(p, "gnn1", batch["frames"], batch["torsions"], h, edge, batch["mask"],
+                                     pocket_h, batch["pocket_frames"], batch["pocket_mask"])
+    m = batch["mask"]
+    assert rel_err(orc.frames_to_tensor7(fr)[m], case["l1_frames"][m]) < TOL
+    assert rel_err(tors[m], case["l1_torsions"][m]) < TOL
+    assert rel_err(o[m], case["l1_features"][m]) < TOL
+
+
+@pytest.mark.parametrize("name", ["train_shipped_p80.pt", "train_random_p80.pt"])
+def test_train_step_matches_reference(name):
+    case = load_case(name)
+    p = {k: v.clone().requires_grad_(True) for k, v in case["params"].items()}
+    batch = orc.batch_to_frames(case["batch"])
+    noise = noise_dict(case["noise"])
+    zt = orc.add_noise(batch, noise, case["t"], case["T"])
+    assert rel_err(zt["frames"]["rot_mats"], case["zt_rot_mats"]) < TOL
+    assert rel_err(zt["frames"]["trans"], case["zt_trans"]) < TOL
+    assert rel_err(zt["torsions"], case["zt_torsions"]) < TOL
+    # eigh's sign flips under 1-ulp changes of the matrix, so the recorded quaternions are the sign tape
+    zt["frames"]["quat_hint"] = case["zt_quats"]
+    assert rel_err(orc.frame_quats(zt["frames"]), case["zt_quats"]) < TOL
+    loss, losses, pred = orc.train_step_loss(p, batch, noise, case["t"], case["T"], quat_hint=case["zt_quats"])
+    m = case["batch"]["mask"]
+    assert rel_err(orc.frames_to_tensor7(pred["frames"])[m].detach(), case["pred_frames"][m]) < 5e-5
+    for k, v in case["losses"].items():
+        assert rel_err(losses[k].detach(), v) < 5e-5, k
+    loss.backward()
+    for k, g in case["grads"].items():
+        if g is None:
+            assert p[k].grad is None or float(p[k].grad.abs().max()) == 0.0, k
+        else:
+            assert rel_err(p[k].grad, g) < 1e-4, k
+
+
+def test_reverse_step_matches_reference():
+    case = load_case("reverse_step_p80.pt")
+    batch = orc.batch_to_frames(case["batch"])
+    zt = dict(batch)
+    zt["frames"] = {"quats": case["zt_quats"], "trans": case["zt_trans"]}
+    zt["torsions"] = case["zt_torsions"]
+    pred = {"frames": orc.frames_from_tensor7(case["pred_frames"]), "torsions": case["pred_torsions"]}
+    zs = orc.remove_noise(zt, pred, case["t"], case["t"] - 1, case["T"], noise_dict(case["fresh"]))
+    assert rel_err(zs["frames"]["rot_mats"], case["zs_rot_mats"]) < TOL
+    assert rel_err(zs["frames"]["trans"], case["zs_trans"]) < TOL
+    assert rel_err(zs["torsions"], case["zs_torsions"]) < TOL
+
+
+def _trajectory_inputs(case):
+    batch = orc.batch_to_frames(case["batch"])
+    start = case["start"]
+    batch["frames"] = {"quats": start["q"], "trans": start["x"]}
+    batch["torsions"] = start["tors"]
+    T = case["T"]
+    tape = [noise_dict({"q": case["tape_q"][k], "x": case["tape_x"][k], "tors": case["tape_tors"][k]}) for k in range(T)]
+    return batch, tape, T
+
+
+def test_trajectory_teacher_forced_matches_reference():
+    """Every one of the T reverse steps, each started from the reference's own z_t.
+
+    The sampling map with the shipped weights is chaotic (a 1e-6 A change of the start grows to
+    ~1 A after 100 steps, measured on the oracle AND between oracle and reference), so a free-running
+    100-step comparison cannot hold for any independent fp32 implementation; per-step parity can."""
+    case = load_case("trajectory_T100_p80.pt")
+    batch, tape, T = _trajectory_inputs(case)
+    m = case["batch"]["mask"]
+    worst_x, worst_q, worst_t = 0.0, 0.0, 0.0
+    with torch.no_grad():
+        for k in range(T - 1):
+            t = T - k
+            zt = dict(batch)
+            zt["frames"] = {"quats": case["zt_quats"][k], "trans": case["zt_trans"][k]}
+            zt["torsions"] = case["zt_torsions"][k]
+            pred = orc.model_forward(case["params"], zt, t, T)
+            zs = orc.remove_noise(zt, pred, t, t - 1, T, tape[k], quat_hint=case["zt_quats"][k + 1])
+            worst_x = max(worst_x, float((zs["frames"]["trans"] - case["zt_trans"][k + 1]).norm(dim=-1)[m].max()))
+            worst_q = max(worst_q, float((orc.frame_quats(zs["frames"]) - case["zt_quats"][k + 1])[m].abs().max()))
+            worst_t = max(worst_t, float((zs["torsions"] - case["zt_torsions"][k + 1])[m].abs().max()))
+    assert worst_x < 1e-3 and worst_q < 1e-4 and worst_t < 1e-4, (worst_x, worst_q, worst_t)
+
+
+def test_trajectory_free_running_short_horizon():
+    """Free-running parity over the first 12 steps: per-residue deviation <= 0.05 A (north_star gate)."""
+    case = load_case("trajectory_T100_p80.pt")
+    batch, tape, T = _trajectory_inputs(case)
+    rec = []
+    orc.sample(case["params"], batch, T, noise_tape=tape, quat_tape=case["zt_quats"], record=rec)
+    m = case["batch"]["mask"]
+    for k in range(12):
+        dev = (rec[k]["zt_trans"] - case["zt_trans"][k]).norm(dim=-1)[m]
+        assert float(dev.max()) < 0.05, (k, float(dev.max()))
+
+
+def test_angle_tools_known_answers():
+    case = load_case("angle_tools.pt")
+    assert rel_err(orc.shoemake(case["u"]), case["shoemake"]) < 1e-6
+    assert rel_err(orc.sin_cos_mul(case["sc1"], case["sc2"]), case["multiply"]) < 1e-6
+    assert rel_err(orc.sin_cos_inv(case["sc1"]), case["inverse"]) < 1e-6
+    for amt in (0.3, 0.8):
+        assert rel_err(orc.sin_cos_partial(case["sc1"], amt), case[f"partial_{amt}"]) < 1e-6
+        assert rel_err(orc.quat_partial(case["q"], amt), case[f"partial_rot_{amt}"]) < 1e-6
+    assert rel_err(orc.angle_to_sin_cos(case["angles"]), case["angle_to_sin_cos"]) < 1e-6
+
+
+def test_reference_unit_test_sin_cos_multiplication():
+    """Restates tests/unit/tools/test_angle.py:11-38 of the reference on the oracle's functions."""
+    pi = math.pi
+    angles = torch.tensor([pi, pi / 2, pi / 3, 0.0, -pi / 3, -pi / 2, -pi])
+    n = angles.shape[0]
+    sc = orc.angle_to_sin_cos(angles)
+    prod = orc.sin_cos_mul(sc[:, None, :].expand(-1, n, -1), sc[None, :, :].expand(n, -1, -1))
+    assert torch.all((prod - orc.angle_to_sin_cos(angles[:, None] + angles[None, :])).abs() < 1e-6)
+    back = orc.sin_cos_mul(orc.sin_cos_inv(sc), sc)
+    assert torch.all(back[..., 0] == 0.0) and torch.all(back[..., 1] == 1.0)
+
+
+def test_reference_unit_test_random_quat():
+    """Restates tests/unit/tools/test_angle.py:42-48."""
+    q = orc.shoemake(torch.rand(10, 10, 3))
+    assert torch.all(((q ** 2).sum(-1).sqrt() - 1.0).abs() < 1e-6)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present (GPU box)")
+def test_oracle_against_live_reference():
+    """Fresh seeded inputs through the live reference and the oracle (build container only)."""
+    ref_model, ref_opt, _ = ref_shim.load_reference()
+    from openfold.utils.rigid_utils import Rigid
+    params = orc.random_params(seed=123)
+    model = ref_model.Model(16, 22, 50)
+    model.load_state_dict(params, strict=True)
+    b = orc.synthetic_batch(3, (8, 15), (10, 80), P_pad=80, seed=99)
+    rb = dict(b)
+    rb["frames"] = Rigid.from_tensor_7(b["frames"])
+    rb["pocket_frames"] = Rigid.from_tensor_7(b["pocket_frames"])
+    with torch.no_grad():
+        ref = model(rb, 17)
+        mine = orc.model_forward(params, orc.batch_to_frames(b), 17, 50)
+    m = b["mask"]
+    assert rel_err(orc.frames_to_tensor7(mine["frames"])[m], ref["frames"].to_tensor_7()[m]) < TOL
+    assert rel_err(mine["torsions"][m], ref["torsions"][m]) < TOL
+
+
+def test_optimize_steps_match_reference():
+    """Two genuine reference optimize() calls (Adam, lr 1e-3) replayed on the oracle with the recorded t, noise, signs."""
+    case = load_case("optimize_shipped_p80.pt")
+    p = {k: v.clone().requires_grad_(True) for k, v in case["params"].items()}
+    opt = torch.optim.Adam(list(p.values()), lr=case["lr"])
+    batch = orc.batch_to_frames(case["batch"])
+    for t, noise, hint in zip(case["ts"], case["noises"], case["zt_quats"]):
+        opt.zero_grad()
+        loss, _, _ = orc.train_step_loss(p, batch, noise_dict(noise), t, case["T"], quat_hint=hint)
+        loss.backward()
+        opt.step()
+    for k, v in case["params_after"].items():
+        assert rel_err(p[k].detach(), v) < 1e-4, k
