@@ -1,0 +1,155 @@
+/*
+ * pmhc_b200.h — C ABI of the B200-native denoising hot path of cmbi/pmhc-diffusion-model.
+ *
+ * The reference has no FFI layer: its boundary is the Python surface of
+ * diffusion/model.py and diffusion/optimizer.py.  Each entry point below names the
+ * reference interface (file:line under /root/reference) whose arithmetic it
+ * replaces; pmhc_diffusion_model_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), nothing
+ *     allocates, nothing synchronises, no global mutable state;
+ *   - return value: 0 = ok, < 0 = error (text in pmhc_last_error(), thread-local);
+ *   - sm_100a only: there is no CPU or other-arch fallback.
+ *   - N = 16 padded peptide slots, 22 node features, 7 torsions (sin, cos),
+ *     frames are tensor_7 rows: quaternion (w, x, y, z) then translation (x, y, z).
+ */
+#ifndef PMHC_B200_H
+#define PMHC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMHC_N 16          /* peptide_maxlen, data.py:15 / Model(16, ...) optimize.py:54 */
+#define PMHC_NFEAT 22      /* node_input_size, optimize.py:54 */
+#define PMHC_NTORS 7       /* model.py:32 */
+#define PMHC_HID 64        /* transition / message / feature width, model.py:36, 367-368 */
+#define PMHC_NPARAM 79195  /* total fp32 parameters of Model(16, 22, T) */
+#define PMHC_ROWSTAT 16    /* floats saved per peptide row per layer for the backward pass */
+
+/* One batch of complexes in the dataset's padded layout (data.py:105-117, model.py:384-390). */
+typedef struct {
+    int32_t B;                    /* complexes */
+    int32_t P;                    /* padded pocket slots per complex (data.py:16 pocket_maxlen) */
+    const float *frames;          /* [B,16,7]  peptide frames, used as given (RU:1037 from_tensor_7) */
+    const float *torsions;        /* [B,16,7,2] sin, cos */
+    const float *features;        /* [B,16,22] */
+    const uint8_t *mask;          /* [B,16]  1 = real residue */
+    const float *pocket_frames;   /* [B,P,7] */
+    const float *pocket_features; /* [B,P,22] */
+    const uint8_t *pocket_mask;   /* [B,P] */
+} PmhcBatch;
+
+const char *pmhc_last_error(void);
+
+/* Library / device probe: returns 0 when the current device is sm_100 and the kernels are loadable. */
+int pmhc_check_device(void);
+
+/* Offset (in floats) of state-dict tensor `index` (0..47, state_dict order of model.py:370-371:
+ * gnn1.feature_mlp.0.weight, .0.bias, .2.weight, .2.bias, message_mlp.*, attention_mlp.*, translation_mlp.*,
+ * rotation_mlp.*, torsion_mlp.*, then gnn2.*) inside the flat parameter buffer; -1 if out of range. */
+int64_t pmhc_param_offset(int index);
+int64_t pmhc_param_numel(int index);
+
+/* Bytes of workspace pmhc_model_forward/backward need for a batch shape. */
+size_t pmhc_workspace_bytes(int B, int P);
+
+/* Denoiser forward — replaces Model.forward (diffusion/model.py:377-421) and both EGNNLayer.forward calls
+ * (model.py:83-181): two fused message-passing layers over peptide x (peptide + pocket).
+ *   params      flat fp32 parameter buffer (PMHC_NPARAM floats, pmhc_param_offset layout)
+ *   t_over_T    the time feature t / T (model.py:394)
+ *   out_frames  [B,16,7]   unit quaternion + translation (model.py:181, 418-421)
+ *   out_torsions[B,16,7,2]
+ *   saved       NULL for inference; else pmhc_saved_floats(B, P) floats kept for pmhc_model_backward
+ *               (per-row softmax statistics, per-pair logits, layer-1 outputs)
+ * Padded peptide rows (mask 0) pass their input frame/torsions through (the reference leaves finite
+ * don't-care values there). */
+size_t pmhc_saved_floats(int B, int P);
+int pmhc_model_forward(const float *params, const PmhcBatch *batch_host, float t_over_T,
+                       float *out_frames, float *out_torsions, float *saved,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Denoiser backward — the autograd of the above (what total_loss.mean().backward() does at
+ * optimizer.py:222 for the model part).  Accumulates (+=) into flat_grad (PMHC_NPARAM floats, same
+ * layout as params; gnn2.feature_mlp.* never receives a gradient).
+ *   d_out_frames [B,16,7], d_out_torsions [B,16,7,2]: gradient of the loss w.r.t. the forward outputs. */
+int pmhc_model_backward(const float *params, const PmhcBatch *batch_host, float t_over_T,
+                        const float *saved, const float *d_out_frames, const float *d_out_torsions,
+                        float *flat_grad, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Noise draw — replaces DiffusionModelOptimizer.gen_noise (optimizer.py:93-108) with random_quat /
+ * shoemake_quat (angle.py:59-98) and random_sin_cos (angle.py:33-57): translation 5*N(0,I), uniform
+ * rotation, 7 uniform torsion angles per residue.  Counter-based (Philox4x32-10): residue r of the call
+ * uses counter (first_residue + r, draw), so results do not depend on how residues are split over GPUs.
+ *   noise_frames [n,7], noise_torsions [n,7,2]. */
+int pmhc_gen_noise(uint64_t seed, uint64_t first_residue, int64_t n_residues,
+                   float *noise_frames, float *noise_torsions, void *stream);
+
+/* Noise from caller-supplied randoms (parity mode): normal [n,3] ~ N(0,1), uniform [n,10] ~ U(0,1)
+ * (3 Shoemake coordinates then 7 torsion angles / 2pi) -> same formulas as above. */
+int pmhc_noise_from_randoms(const float *normal, const float *uniform, int64_t n_residues,
+                            float *noise_frames, float *noise_torsions, void *stream);
+
+/* Forward noising — replaces add_noise (optimizer.py:110-138; partial_sin_cos angle.py:165-174,
+ * partial_rot angle.py:177-186, multiply_sin_cos angle.py:139-152, compose_r RU:525-538).
+ * Rotations stay quaternions: q_t = partial_rot(eps_q, beta) * q_0 (Hamilton product), equal to the
+ * reference's compose_r + rot_to_quat up to the eigh sign.  quat_sign_ref (nullable,
+ * [n,4]): if given, q_t is flipped where q_t . ref < 0 (parity mode: the reference's sign tape). */
+int pmhc_add_noise(const float *frames, const float *torsions, const float *noise_frames,
+                   const float *noise_torsions, double beta, int64_t n_residues,
+                   const float *quat_sign_ref, float *out_frames, float *out_torsions, void *stream);
+
+/* Reverse step t -> s — replaces remove_noise (optimizer.py:140-193; inverse_sin_cos angle.py:155-162,
+ * Rotation.invert RU:585-601).  fresh_* is the step's new noise (optimizer.py:151).
+ * beta is the schedule value as the reference's Python float (double): the angle scalings use it rounded to
+ * fp32 (tensor * python-float semantics), the translation coefficients are derived from it in double.
+ * In-place safe (out may alias zt). */
+int pmhc_remove_noise(const float *zt_frames, const float *zt_torsions, const float *pred_frames,
+                      const float *pred_torsions, const float *fresh_frames, const float *fresh_torsions,
+                      double beta_t, double beta_s, int64_t n_residues, const float *quat_sign_ref,
+                      float *out_frames, float *out_torsions, void *stream);
+
+/* Loss forward + gradient — replaces get_loss (optimizer.py:38-79) and its autograd.
+ *   losses [5,B]: total, positions, rotations, torsions, rmsd (optimizer.py:73-79)
+ *   d_pred_frames [B,16,7], d_pred_torsions [B,16,7,2] (nullable): d(grad_scale * sum_b total[b]) / d pred;
+ *   the training step uses grad_scale = 1/B for total_loss.mean() (optimizer.py:222). */
+int pmhc_loss(const float *true_frames, const float *true_torsions, const float *pred_frames,
+              const float *pred_torsions, const uint8_t *mask, const uint8_t *torsions_mask, int B,
+              float grad_scale, float *losses, float *d_pred_frames, float *d_pred_torsions, void *stream);
+
+/* Whole sampling trajectory — replaces DiffusionModelOptimizer.sample (optimizer.py:226-252): T sequential
+ * (denoiser forward, reverse step) pairs on `stream`, updating frames/torsions in place.
+ *   frames [B,16,7], torsions [B,16,7,2]: z_T on entry (test.py:71-74), z_0 on return
+ *   noise_tape (nullable): [T, B*16, 21] = per step fresh noise as tensor_7 + 14 torsion values;
+ *                          NULL -> Philox with (seed, first_complex)
+ *   quat_sign_tape (nullable): [T, B*16, 4] reference quaternions of z after each step (parity mode)
+ *   scratch: 2 * B*16*21 floats for (pred, fresh). */
+int pmhc_sample(const float *params, const PmhcBatch *batch_host, float *frames, float *torsions,
+                int T, double beta_min, double beta_max, uint64_t seed, uint64_t first_complex,
+                const float *noise_tape, const float *quat_sign_tape, float *scratch,
+                void *workspace, size_t workspace_bytes, void *stream);
+
+/* Adam update over the flat buffers — replaces torch.optim.Adam.step (optimizer.py:33, 224), default
+ * betas/eps unless given; `skip` ranges (gnn2.feature_mlp) are left untouched like grad=None params. */
+int pmhc_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, int step, void *stream);
+
+/* Number of kernel launches issued by this library since load (for bench.py's gpu_launches claim). */
+int64_t pmhc_launch_count(void);
+
+/* Measurement hooks (bench.py's roofline leg; no reference counterpart): while enabled, every fused EGNN layer
+ * launch is bracketed by CUDA events on its stream.  pmhc_profile_read waits for them and returns, for slot 0
+ * (forward layer kernels) and slot 1 (backward layer kernels), the summed device time in ms and the launch count,
+ * then clears the record. */
+void pmhc_profile_enable(int on);
+int pmhc_profile_read(double *ms_by_slot, int64_t *launches_by_slot);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMHC_B200_H */

@@ -1,0 +1,144 @@
+// capi.cu — error text, device probe, parameter layout queries and the sampling trajectory driver.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "egnn_common.cuh"
+
+namespace pmhc {
+
+static thread_local char g_error[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+static bool g_profile = false;
+static std::mutex g_profile_mu;
+static std::vector<cudaEvent_t> g_prof_events[PROF_SLOTS];  // begin, end, begin, end, ...
+
+bool profile_enabled() { return g_profile; }
+void profile_mark(int slot, cudaStream_t stream, bool begin) {
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    if ((g_prof_events[slot].size() % 2 == 0) != begin) return;  // keep begin/end paired
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, stream);
+    g_prof_events[slot].push_back(ev);
+}
+
+int launch_remove_noise(const float* zf, const float* zt, const float* pf, const float* pt, const float* xf,
+                        const float* xt, double beta_t, double beta_s, int64_t n, const float* sign_ref, float* of,
+                        float* ot, cudaStream_t stream);
+__global__ void unpack_noise_tape_kernel(const float* __restrict__ tape, int64_t n, float* __restrict__ frames,
+                                         float* __restrict__ tors) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 21) return;
+    int64_t r = idx / 21;
+    int c = (int)(idx - r * 21);
+    if (c < 7) frames[r * 7 + c] = tape[idx];
+    else tors[r * 14 + (c - 7)] = tape[idx];
+}
+
+}  // namespace pmhc
+
+using namespace pmhc;
+
+extern "C" const char* pmhc_last_error(void) { return g_error; }
+
+extern "C" int64_t pmhc_launch_count(void) { return g_launches.load(); }
+
+extern "C" void pmhc_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    g_profile = on != 0;
+}
+
+extern "C" int pmhc_profile_read(double* ms, int64_t* launches) {
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    for (int s = 0; s < PROF_SLOTS; ++s) {
+        double total = 0.0;
+        int64_t n = 0;
+        auto& ev = g_prof_events[s];
+        for (size_t k = 0; k + 1 < ev.size(); k += 2) {
+            cudaEventSynchronize(ev[k + 1]);
+            float t = 0.0f;
+            if (cudaEventElapsedTime(&t, ev[k], ev[k + 1]) == cudaSuccess) {
+                total += t;
+                ++n;
+            }
+        }
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        ev.clear();
+        ms[s] = total;
+        launches[s] = n;
+    }
+    return 0;
+}
+
+extern "C" int pmhc_check_device(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    PMHC_REQUIRE(e == cudaSuccess, "cudaGetDevice: %s", cudaGetErrorString(e));
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    PMHC_REQUIRE(major == 10 && minor == 0, "this library is built for sm_100a only; device is sm_%d%d", major, minor);
+    PMHC_REQUIRE(device_props() == 0, "could not query the device");
+    return 0;
+}
+
+extern "C" int64_t pmhc_param_offset(int index) {
+    if (index < 0 || index >= 2 * PARAMS_PER_LAYER) return -1;
+    return param_offset(index / PARAMS_PER_LAYER, index % PARAMS_PER_LAYER);
+}
+
+extern "C" int64_t pmhc_param_numel(int index) {
+    if (index < 0 || index >= 2 * PARAMS_PER_LAYER) return -1;
+    return param_numel(index / PARAMS_PER_LAYER, index % PARAMS_PER_LAYER);
+}
+
+// DiffusionModelOptimizer.sample (optimizer.py:226-252): t = T..1: z <- remove_noise(z, model(z, t), t, t-1).
+extern "C" int pmhc_sample(const float* params, const PmhcBatch* bt, float* frames, float* torsions, int T,
+                           double beta_min, double beta_max, uint64_t seed, uint64_t first_complex,
+                           const float* noise_tape, const float* quat_sign_tape, float* scratch, void* workspace,
+                           size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PMHC_REQUIRE(bt != nullptr && bt->B > 0 && T > 0, "pmhc_sample: empty batch or T <= 0");
+    PMHC_REQUIRE(scratch != nullptr, "pmhc_sample: scratch is required");
+    const int64_t n = (int64_t)bt->B * kN;
+    float* pred_f = scratch;
+    float* pred_t = pred_f + n * 7;
+    float* fresh_f = pred_t + n * 14;
+    float* fresh_t = fresh_f + n * 7;
+    PmhcBatch step = *bt;
+    step.frames = frames;
+    step.torsions = torsions;
+    for (int t = T; t > 0; --t) {
+        const int k = T - t;
+        int rc = pmhc_model_forward(params, &step, (float)((double)t / (double)T), pred_f, pred_t, nullptr, workspace,
+                                    workspace_bytes, stream);
+        if (rc != 0) return rc;
+        if (noise_tape != nullptr) {
+            unpack_noise_tape_kernel<<<(unsigned)((n * 21 + 255) / 256), 256, 0, stream>>>(noise_tape + (size_t)k * n * 21, n, fresh_f, fresh_t);
+            PMHC_CHECK_LAUNCH("unpack_noise_tape");
+        } else {
+            // one Philox stream per (complex-residue, step): counter = residue index, key mixes seed and step
+            rc = pmhc_gen_noise(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(k + 1), first_complex * kN, n, fresh_f, fresh_t, stream);
+            if (rc != 0) return rc;
+        }
+        // linear_schedule (optimizer.py:20-21) in double, exactly as the reference's Python floats
+        double beta_t = beta_min + (beta_max - beta_min) * ((double)t / (double)T);
+        double beta_s = beta_min + (beta_max - beta_min) * ((double)(t - 1) / (double)T);
+        rc = launch_remove_noise(frames, torsions, pred_f, pred_t, fresh_f, fresh_t, beta_t, beta_s, n,
+                                 quat_sign_tape ? quat_sign_tape + (size_t)k * n * 4 : nullptr, frames, torsions, stream);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}

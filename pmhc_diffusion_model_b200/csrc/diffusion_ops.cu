@@ -1,0 +1,298 @@
+// diffusion_ops.cu — noise draw, forward noising, reverse step, loss (+gradient) and Adam.
+//
+// All HBM-bound, one thread per peptide residue (loss: one half-warp per complex), no shared-memory
+// staging needed: every input element is read once, every output written once.
+#include "common.cuh"
+#include "pmhc_math.cuh"
+
+namespace pmhc {
+
+__device__ __forceinline__ Quat load_quat(const float* p) { return Quat{p[0], p[1], p[2], p[3]}; }
+__device__ __forceinline__ void store_frame(float* p, const Quat& q, float x, float y, float z) {
+    p[0] = q.w; p[1] = q.x; p[2] = q.y; p[3] = q.z; p[4] = x; p[5] = y; p[6] = z;
+}
+__device__ __forceinline__ Quat align_sign(const Quat& q, const float* ref) {
+    if (ref == nullptr) return q;
+    float d = q.w * ref[0] + q.x * ref[1] + q.y * ref[2] + q.z * ref[3];
+    return d < 0.0f ? Quat{-q.w, -q.x, -q.y, -q.z} : q;
+}
+
+// Noise formulas shared by the Philox and the caller-supplied-randoms paths
+// (optimizer.py:97-103, angle.py:33-98): translation 5 * N(0,1), Shoemake rotation, sin/cos of 2*pi*u.
+__device__ __forceinline__ void write_noise(float* fr, float* tors, float n0, float n1, float n2, float u0,
+                                            float u1, float u2, const float* ua) {
+    Quat q = shoemake(u0, u1, u2);
+    store_frame(fr, q, n0 * 5.0f, n1 * 5.0f, n2 * 5.0f);
+#pragma unroll
+    for (int c = 0; c < PMHC_NTORS; ++c) {
+        float a = ua[c] * kTwoPi;
+        tors[2 * c] = sinf(a);
+        tors[2 * c + 1] = cosf(a);
+    }
+}
+
+__global__ void gen_noise_kernel(uint64_t seed, uint64_t first, int64_t n, float* __restrict__ frames,
+                                 float* __restrict__ tors) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint64_t ctr = first + (uint64_t)r;
+    Philox4 a = philox4x32_10(ctr, 0, seed), b = philox4x32_10(ctr, 1, seed);
+    Philox4 c = philox4x32_10(ctr, 2, seed), d = philox4x32_10(ctr, 3, seed);
+    // Box-Muller on (a0,a1) and (a2,a3)
+    float r0 = sqrtf(-2.0f * logf(u32_to_unit(a.v[0]))), r1 = sqrtf(-2.0f * logf(u32_to_unit(a.v[2])));
+    float s0, c0, s1, c1;
+    sincosf(kTwoPi * u32_to_unit(a.v[1]), &s0, &c0);
+    sincosf(kTwoPi * u32_to_unit(a.v[3]), &s1, &c1);
+    float ua[PMHC_NTORS] = {u32_to_unit(b.v[3]), u32_to_unit(c.v[0]), u32_to_unit(c.v[1]), u32_to_unit(c.v[2]),
+                            u32_to_unit(c.v[3]), u32_to_unit(d.v[0]), u32_to_unit(d.v[1])};
+    write_noise(frames + r * 7, tors + r * 14, r0 * c0, r0 * s0, r1 * c1, u32_to_unit(b.v[0]),
+                u32_to_unit(b.v[1]), u32_to_unit(b.v[2]), ua);
+}
+
+__global__ void noise_from_randoms_kernel(const float* __restrict__ normal, const float* __restrict__ uniform,
+                                          int64_t n, float* __restrict__ frames, float* __restrict__ tors) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float* u = uniform + r * 10;
+    float ua[PMHC_NTORS];
+#pragma unroll
+    for (int c = 0; c < PMHC_NTORS; ++c) ua[c] = u[3 + c];
+    write_noise(frames + r * 7, tors + r * 14, normal[r * 3], normal[r * 3 + 1], normal[r * 3 + 2], u[0], u[1], u[2], ua);
+}
+
+// add_noise (optimizer.py:110-138)
+__global__ void add_noise_kernel(const float* __restrict__ frames, const float* __restrict__ tors,
+                                 const float* __restrict__ nframes, const float* __restrict__ ntors, float beta,
+                                 float alpha, float sigma, int64_t n, const float* __restrict__ sign_ref,
+                                 float* __restrict__ oframes, float* __restrict__ otors) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float* f = frames + r * 7;
+    const float* e = nframes + r * 7;
+    Quat q = qunit(qmul(qpartial(load_quat(e), beta), load_quat(f)));
+    q = align_sign(q, sign_ref ? sign_ref + r * 4 : nullptr);
+    store_frame(oframes + r * 7, q, f[4] * alpha + e[4] * sigma, f[5] * alpha + e[5] * sigma, f[6] * alpha + e[6] * sigma);
+#pragma unroll
+    for (int c = 0; c < PMHC_NTORS; ++c) {
+        SinCos eps{ntors[r * 14 + 2 * c], ntors[r * 14 + 2 * c + 1]};
+        SinCos t0{tors[r * 14 + 2 * c], tors[r * 14 + 2 * c + 1]};
+        SinCos o = scmul(scpartial(eps, beta), t0);
+        otors[r * 14 + 2 * c] = o.s;
+        otors[r * 14 + 2 * c + 1] = o.c;
+    }
+}
+
+// remove_noise (optimizer.py:140-193)
+struct ReverseCoef {
+    float beta_t, beta_s, alpha_ts, var_ts, denom, sigma_t2s;
+};
+
+__device__ __forceinline__ void reverse_step_residue(const float* zf, const float* zt, const float* pf, const float* pt,
+                                                     const float* xf, const float* xt, const ReverseCoef& k,
+                                                     const float* sign_ref, float* of, float* ot) {
+    Quat undo = qinv(qpartial(load_quat(pf), k.beta_t));
+    Quat q = qunit(qmul(qpartial(load_quat(xf), k.beta_s), qmul(undo, load_quat(zf))));
+    q = align_sign(q, sign_ref);
+    float px = zf[4] / k.alpha_ts - (pf[4] * k.var_ts) / k.denom + k.sigma_t2s * xf[4];
+    float py = zf[5] / k.alpha_ts - (pf[5] * k.var_ts) / k.denom + k.sigma_t2s * xf[5];
+    float pz = zf[6] / k.alpha_ts - (pf[6] * k.var_ts) / k.denom + k.sigma_t2s * xf[6];
+    float tmp[14];
+#pragma unroll
+    for (int c = 0; c < PMHC_NTORS; ++c) {
+        SinCos z{zt[2 * c], zt[2 * c + 1]}, p{pt[2 * c], pt[2 * c + 1]}, x{xt[2 * c], xt[2 * c + 1]};
+        SinCos o = scmul(scpartial(x, k.beta_s), scmul(scinv(scpartial(p, k.beta_t)), z));
+        tmp[2 * c] = o.s;
+        tmp[2 * c + 1] = o.c;
+    }
+    store_frame(of, q, px, py, pz);
+#pragma unroll
+    for (int c = 0; c < 14; ++c) ot[c] = tmp[c];
+}
+
+__global__ void remove_noise_kernel(const float* zf, const float* zt, const float* __restrict__ pf,
+                                    const float* __restrict__ pt, const float* __restrict__ xf,
+                                    const float* __restrict__ xt, ReverseCoef k, int64_t n,
+                                    const float* __restrict__ sign_ref, float* of, float* ot) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    reverse_step_residue(zf + r * 7, zt + r * 14, pf + r * 7, pt + r * 14, xf + r * 7, xt + r * 14, k,
+                         sign_ref ? sign_ref + r * 4 : nullptr, of + r * 7, ot + r * 14);
+}
+
+// get_loss + gradient (optimizer.py:38-79): one half-warp (16 lanes = 16 residues) per complex.
+__global__ void loss_kernel(const float* __restrict__ tf, const float* __restrict__ tt, const float* __restrict__ pf,
+                            const float* __restrict__ pt, const uint8_t* __restrict__ mask,
+                            const uint8_t* __restrict__ tmask, int B, float gscale, float* __restrict__ losses,
+                            float* __restrict__ dpf, float* __restrict__ dpt) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = gid >> 4, i = gid & 15;
+    bool live = b < B;
+    int64_t r = (int64_t)(live ? b : 0) * 16 + i;
+    float m = live ? (float)mask[r] : 0.0f;
+    const float* a = tf + r * 7;
+    const float* p = pf + r * 7;
+    float dx = a[4] - p[4], dy = a[5] - p[5], dz = a[6] - p[6];
+    float sq = (dx * dx + dy * dy + dz * dz) * m;
+    Quat qa = qnormalize(load_quat(a)), qp_raw = load_quat(p), qp = qnormalize(qp_raw);
+    float rdev = (1.0f - qdot(qa, qp)) * m;
+    float tdev = 0.0f, tcnt = 0.0f;
+    float tm[PMHC_NTORS];
+    SinCos ta[PMHC_NTORS], tp_raw[PMHC_NTORS];
+#pragma unroll
+    for (int c = 0; c < PMHC_NTORS; ++c) {
+        tm[c] = live ? (float)tmask[r * 7 + c] : 0.0f;
+        float as = tt[r * 14 + 2 * c], ac = tt[r * 14 + 2 * c + 1];
+        float an = fmaxf(sqrtf(as * as + ac * ac), kNormEps);
+        ta[c] = SinCos{as / an, ac / an};
+        tp_raw[c] = SinCos{pt[r * 14 + 2 * c], pt[r * 14 + 2 * c + 1]};
+        float pn = fmaxf(sqrtf(tp_raw[c].s * tp_raw[c].s + tp_raw[c].c * tp_raw[c].c), kNormEps);
+        tdev += (1.0f - (ta[c].s * tp_raw[c].s + ta[c].c * tp_raw[c].c) / pn) * tm[c];
+        tcnt += tm[c];
+    }
+    float nres = m;
+    // reduce over the 16 lanes of this complex (xor offsets < 16 stay inside the half-warp)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        rdev += __shfl_xor_sync(0xffffffffu, rdev, o);
+        tdev += __shfl_xor_sync(0xffffffffu, tdev, o);
+        tcnt += __shfl_xor_sync(0xffffffffu, tcnt, o);
+        nres += __shfl_xor_sync(0xffffffffu, nres, o);
+    }
+    if (!live) return;
+    float pos_loss = sq / nres, rot_loss = rdev / nres, tors_loss = tdev / tcnt;
+    if (i == 0) {
+        losses[b] = 0.1f * pos_loss + rot_loss + tors_loss;
+        losses[B + b] = pos_loss;
+        losses[2 * B + b] = rot_loss;
+        losses[3 * B + b] = tors_loss;
+        losses[4 * B + b] = sqrtf(pos_loss);
+    }
+    if (dpf != nullptr) {
+        float* g = dpf + r * 7;
+        float wq = -gscale * m / nres;
+        Quat dq = qnormalize_grad(qp_raw, qscale(qa, wq));
+        float wx = gscale * 0.1f * m * 2.0f / nres;
+        g[0] = dq.w; g[1] = dq.x; g[2] = dq.y; g[3] = dq.z;
+        g[4] = -wx * dx; g[5] = -wx * dy; g[6] = -wx * dz;
+#pragma unroll
+        for (int c = 0; c < PMHC_NTORS; ++c) {
+            float w = -gscale * tm[c] / tcnt;
+            float ps = tp_raw[c].s, pc = tp_raw[c].c;
+            float pn = fmaxf(sqrtf(ps * ps + pc * pc), kNormEps);
+            float us = ps / pn, uc = pc / pn;
+            float gs = w * ta[c].s, gc = w * ta[c].c;
+            float proj = us * gs + uc * gc;
+            dpt[r * 14 + 2 * c] = (gs - us * proj) / pn;
+            dpt[r * 14 + 2 * c + 1] = (gc - uc * proj) / pn;
+        }
+    }
+}
+
+// torch.optim.Adam single-tensor update (no amsgrad, no weight decay) over the flat buffers.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float b1, float b2, float eps, float step_size,
+                            float bc2_sqrt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i];
+    float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+    float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+}
+
+}  // namespace pmhc
+
+using namespace pmhc;
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" int pmhc_gen_noise(uint64_t seed, uint64_t first_residue, int64_t n, float* frames, float* tors, void* stream) {
+    if (n <= 0) return 0;
+    gen_noise_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(seed, first_residue, n, frames, tors);
+    PMHC_CHECK_LAUNCH("pmhc_gen_noise");
+    return 0;
+}
+
+extern "C" int pmhc_noise_from_randoms(const float* normal, const float* uniform, int64_t n, float* frames,
+                                       float* tors, void* stream) {
+    if (n <= 0) return 0;
+    noise_from_randoms_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(normal, uniform, n, frames, tors);
+    PMHC_CHECK_LAUNCH("pmhc_noise_from_randoms");
+    return 0;
+}
+
+extern "C" int pmhc_add_noise(const float* frames, const float* torsions, const float* nframes, const float* ntors,
+                              double beta, int64_t n, const float* sign_ref, float* oframes, float* otors,
+                              void* stream) {
+    if (n <= 0) return 0;
+    PMHC_REQUIRE(beta >= 0.0 && beta <= 1.0, "pmhc_add_noise: beta %f outside [0,1]", beta);
+    float alpha = (float)sqrt(1.0 - beta), sigma = (float)sqrt(beta);
+    add_noise_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(frames, torsions, nframes, ntors, (float)beta, alpha,
+                                                                          sigma, n, sign_ref, oframes, otors);
+    PMHC_CHECK_LAUNCH("pmhc_add_noise");
+    return 0;
+}
+
+namespace pmhc {
+// host-side coefficients of one reverse step, in double like the reference's Python floats
+// (optimizer.py:148-157; sigma_ts^2 = sigma_t^2 - sigma_s^2 * alpha_ts as written)
+ReverseCoef reverse_coef(double beta_t, double beta_s) {
+    double alpha_t = sqrt(1.0 - beta_t), alpha_s = sqrt(1.0 - beta_s);
+    double sigma_t = sqrt(beta_t), sigma_s = sqrt(beta_s);
+    double alpha_ts = alpha_t / alpha_s;
+    double var_ts = sigma_t * sigma_t - sigma_s * sigma_s * alpha_ts;
+    double sigma_ts = sqrt(var_ts);
+    ReverseCoef k;
+    k.beta_t = (float)beta_t;
+    k.beta_s = (float)beta_s;
+    k.alpha_ts = (float)alpha_ts;
+    k.var_ts = (float)var_ts;
+    k.denom = (float)(alpha_ts * sigma_t);
+    k.sigma_t2s = (float)(sigma_ts * sigma_s / sigma_t);
+    return k;
+}
+
+int launch_remove_noise(const float* zf, const float* zt, const float* pf, const float* pt, const float* xf,
+                        const float* xt, double beta_t, double beta_s, int64_t n, const float* sign_ref, float* of,
+                        float* ot, cudaStream_t stream) {
+    PMHC_REQUIRE(beta_t > 0.0 && beta_t < 1.0 && beta_s >= 0.0 && beta_s < beta_t,
+                 "pmhc_remove_noise: need 0 <= beta_s < beta_t < 1 (got %f, %f)", beta_s, beta_t);
+    ReverseCoef k = reverse_coef(beta_t, beta_s);
+    remove_noise_kernel<<<grid_for(n, 128), 128, 0, stream>>>(zf, zt, pf, pt, xf, xt, k, n, sign_ref, of, ot);
+    PMHC_CHECK_LAUNCH("pmhc_remove_noise");
+    return 0;
+}
+}  // namespace pmhc
+
+extern "C" int pmhc_remove_noise(const float* zf, const float* zt, const float* pf, const float* pt, const float* xf,
+                                 const float* xt, double beta_t, double beta_s, int64_t n, const float* sign_ref,
+                                 float* of, float* ot, void* stream) {
+    if (n <= 0) return 0;
+    return launch_remove_noise(zf, zt, pf, pt, xf, xt, beta_t, beta_s, n, sign_ref, of, ot, (cudaStream_t)stream);
+}
+
+extern "C" int pmhc_loss(const float* tf, const float* tt, const float* pf, const float* pt, const uint8_t* mask,
+                         const uint8_t* tmask, int B, float gscale, float* losses, float* dpf, float* dpt,
+                         void* stream) {
+    if (B <= 0) return 0;
+    PMHC_REQUIRE((dpf == nullptr) == (dpt == nullptr), "pmhc_loss: pass both gradient buffers or neither");
+    loss_kernel<<<grid_for((int64_t)B * 16, 128), 128, 0, (cudaStream_t)stream>>>(tf, tt, pf, pt, mask, tmask, B, gscale,
+                                                                                  losses, dpf, dpt);
+    PMHC_CHECK_LAUNCH("pmhc_loss");
+    return 0;
+}
+
+extern "C" int pmhc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                              float eps, int step, void* stream) {
+    if (n <= 0) return 0;
+    PMHC_REQUIRE(step >= 1, "pmhc_adam_step: step counts from 1");
+    double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+    adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, b1, b2, eps, (float)(lr / bc1),
+                                                                   (float)sqrt(bc2));
+    PMHC_CHECK_LAUNCH("pmhc_adam_step");
+    return 0;
+}

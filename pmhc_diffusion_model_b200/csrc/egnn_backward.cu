@@ -1,0 +1,951 @@
+// egnn_backward.cu — fused EGNN layer backward: weight gradients of every MLP of the layer and (layer 2) the
+// gradients w.r.t. the layer's input frames / torsions / node features.  This is the autograd of
+// EGNNLayer.forward (diffusion/model.py:83-333) that `total_loss.mean().backward()` (optimizer.py:222) runs
+// as ~700 ATen backward ops in the reference.
+//
+// Same persistent one-CTA-per-SM structure as the forward.  One thread owns one (i, j) pair per pass of 128
+// pairs: it recomputes the pair's forward (message, head hidden layers) in registers from the staged weights,
+// back-propagates through the heads / softmax / quaternion sandwich in registers, and leaves its activation
+// and gradient columns in two shared [64][128] tiles; after each head the CTA turns those tiles into the
+// weight-gradient outer products (a 64x64x128 register-tiled GEMM per matrix) accumulated in a per-CTA
+// partial buffer, so no gradient needs an atomic on global memory and the result is run-to-run deterministic.
+// Softmax statistics and logits saved by the forward make the per-pair backward single-pass.
+#include "egnn_common.cuh"
+
+namespace pmhc {
+
+constexpr int kLdc = 132;                     // column-tile row stride (floats): 16-byte aligned rows
+constexpr int kTileFloats = 5 * kHid * kHid;  // tile-owner-layout partials of the five 64x64 matrices
+enum { T_W2 = 0, T_ATT = 1, T_ROT = 2, T_TOR = 3, T_TRN = 4 };
+enum { HD_ATT = 0, HD_ROT = 1, HD_TOR = 2, HD_TRN = 3 };
+
+struct BwdArgs {
+    LayerArgs a;                // the forward's inputs of this layer (outputs unused)
+    const float* rowstat;       // [B,16,16] saved by the forward
+    const float* logits;        // [B,16,Kpad] saved by the forward
+    const float* msum;          // layer 1: [B,16,64] saved unmasked message sums
+    const float* feat_post;     // layer 1: [B,16,64] relu(o1) (for the relu mask)
+    const float* d_frames_out;  // [B,16,7]   dL / d (unit quaternion, translation) of this layer's output
+    const float* d_tors_out;    // [B,16,14]
+    const float* d_feat_out;    // layer 1: [B,16,64] dL / d relu(o1)
+    float* d_frames_in;         // layer 2: [B,16,7]  dL / d layer inputs
+    float* d_tors_in;           // layer 2: [B,16,14]
+    float* d_feat_in;           // layer 2: [B,16,64]
+    float* partial;             // [gridDim][kTileFloats + layer params] per-CTA gradient partial sums
+    float* dajt_ws;             // [gridDim][64][Kpad] per-CTA scratch: dL / d A_j^T
+    int partial_stride;
+};
+
+struct BwdMap {
+    SmemMap f;  // the fields setup_complex() uses (Scr, Ai, Tt, Msum, H, Tors, Q, X, Ints) and the packs
+    int W2, Wh, BufA, BufB, Dout, Ex;
+    int dAi, dAjPep, dWe, dTt, dMsum, RowG, dQ, dX, dTors, grads_end;
+    int total_floats;
+};
+
+__host__ __device__ inline BwdMap make_bwd_map(int Kpad) {
+    BwdMap m;
+    int o = 0;
+    m.W2 = o;       o += kHid * kHid;        // message_mlp.2.weight as stored: [n][k]
+    m.Wh = o;       o += 4 * kHid * kHid;    // head first layers, message columns only: [head][n][k]
+    m.f.W2T = m.f.WhT = m.f.We = -1;
+    m.f.PkAtt = o;  o += 4 * kHid;
+    m.f.PkRotQ = o; o += 4 * kHid;
+    m.f.PkRot2 = o; o += 4 * kHid;
+    m.f.PkMisc = o; o += 4 * kHid;
+    m.f.PkTor2 = o; o += 8 * kHid;
+    m.f.Scal = o;   o += 16;
+    m.BufA = o;     o += kHid * kLdc;
+    m.BufB = o;     o += kHid * kLdc;
+    m.f.Scr = m.BufA;                         // setup_complex stages pocket features in BufA..BufB
+    m.f.Out = -1;
+    m.Dout = o;     o += 8 * kLdc;
+    m.Ex = o;       o += 6 * kLdc;
+    m.f.Ai = o;     o += kN * kLdN;
+    o = (o + 3) & ~3;
+    m.f.Tt = o;     o += kN * kHid;
+    m.f.Msum = o;   o += kN * kHid;
+    m.f.H = o;      o += kN * kLdN;
+    o = (o + 3) & ~3;
+    m.f.Tors = o;   o += kN * 2 * PMHC_NTORS;
+    m.dAi = o;      o += kN * kLdN;
+    m.dAjPep = o;   o += kN * kLdN;
+    m.dWe = o;      o += kEdge * kLdN;
+    m.dTt = o;      o += kN * kHid;
+    m.dMsum = o;    o += kN * kHid;
+    m.RowG = o;     o += kN * 16;
+    m.dQ = o;       o += kN * 4;
+    m.dX = o;       o += kN * 3;
+    m.dTors = o;    o += kN * 14;
+    m.grads_end = o;
+    o = (o + 3) & ~3;
+    m.f.Q = o;      o += Kpad * 4;
+    m.f.X = o;      o += Kpad * 3;
+    o = (o + 3) & ~3;
+    m.f.Ints = o;   o += Kpad + 64;
+    m.total_floats = o;
+    m.f.total_floats = o;
+    return m;
+}
+
+template <int LAYER>
+__device__ inline void stage_layer_weights_bwd(float* S, const BwdMap& M, const float* __restrict__ params) {
+    constexpr int L = LAYER;
+    const int tid = threadIdx.x;
+    const float* msg2 = params + param_offset(L, MSG2_W);
+    const float* att0 = params + param_offset(L, ATT0_W);
+    const float* rot0 = params + param_offset(L, ROT0_W);
+    const float* tor0 = params + param_offset(L, TOR0_W);
+    const float* trn0 = params + param_offset(L, TRN0_W);
+    for (int idx = tid; idx < kHid * kHid; idx += kThreads) {
+        S[M.W2 + idx] = msg2[idx];
+        S[M.Wh + HD_TRN * 4096 + idx] = trn0[idx];
+    }
+    for (int idx = tid; idx < kHid * 66; idx += kThreads) {
+        int n = idx / 66, k = idx - n * 66;
+        float v = att0[idx];
+        if (k < 64) S[M.Wh + HD_ATT * 4096 + n * 64 + k] = v;
+        else S[M.f.PkAtt + 4 * n + (k - 64)] = v;
+    }
+    for (int idx = tid; idx < kHid * 68; idx += kThreads) {
+        int n = idx / 68, k = idx - n * 68;
+        float v = rot0[idx];
+        if (k < 64) S[M.Wh + HD_ROT * 4096 + n * 64 + k] = v;
+        else S[M.f.PkRotQ + 4 * n + (k - 64)] = v;
+    }
+    for (int idx = tid; idx < kHid * 78; idx += kThreads) {
+        int n = idx / 78, k = idx - n * 78;
+        if (k < 64) S[M.Wh + HD_TOR * 4096 + n * 64 + k] = tor0[idx];
+    }
+    for (int n = tid; n < kHid; n += kThreads) {
+        S[M.f.PkAtt + 4 * n + 2] = params[param_offset(L, ATT0_B) + n];
+        S[M.f.PkAtt + 4 * n + 3] = params[param_offset(L, ATT2_W) + n];
+        S[M.f.PkMisc + 4 * n + 0] = params[param_offset(L, TRN0_B) + n];
+        S[M.f.PkMisc + 4 * n + 1] = params[param_offset(L, TRN2_W) + n];
+        S[M.f.PkMisc + 4 * n + 2] = params[param_offset(L, ROT0_B) + n];
+        S[M.f.PkMisc + 4 * n + 3] = params[param_offset(L, MSG2_B) + n];
+        S[M.f.PkTor2 + 8 * n + 7] = 0.0f;
+    }
+    for (int idx = tid; idx < 4 * kHid; idx += kThreads) {
+        int c = idx >> 6, n = idx & 63;
+        S[M.f.PkRot2 + 4 * n + c] = params[param_offset(L, ROT2_W) + idx];
+    }
+    for (int idx = tid; idx < PMHC_NTORS * kHid; idx += kThreads) {
+        int c = idx >> 6, n = idx & 63;
+        S[M.f.PkTor2 + 8 * n + c] = params[param_offset(L, TOR2_W) + idx];
+    }
+    if (tid == 0) {
+        S[M.f.Scal + SC_ATT2B] = params[param_offset(L, ATT2_B)];
+        S[M.f.Scal + SC_TRN2B] = params[param_offset(L, TRN2_B)];
+        for (int c = 0; c < 4; ++c) S[M.f.Scal + SC_ROT2B + c] = params[param_offset(L, ROT2_B) + c];
+        for (int c = 0; c < PMHC_NTORS; ++c) S[M.f.Scal + SC_TOR2B + c] = params[param_offset(L, TOR2_B) + c];
+    }
+}
+
+// sum_k wrow[k] * v[k], wrow a warp-uniform shared row; four independent chains
+__device__ __forceinline__ float dot64(const float* __restrict__ wrow, const float (&v)[kHid]) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow);
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+    for (int k4 = 0; k4 < kHid / 4; ++k4) {
+        float4 w = w4[k4];
+        s0 = fmaf(w.x, v[4 * k4 + 0], s0);
+        s1 = fmaf(w.y, v[4 * k4 + 1], s1);
+        s2 = fmaf(w.z, v[4 * k4 + 2], s2);
+        s3 = fmaf(w.w, v[4 * k4 + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+// acc[k] += wrow[k] * a
+__device__ __forceinline__ void axpy64(float (&acc)[kHid], const float* __restrict__ wrow, float a) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+    for (int k4 = 0; k4 < kHid / 4; ++k4) {
+        float4 w = w4[k4];
+        acc[4 * k4 + 0] = fmaf(w.x, a, acc[4 * k4 + 0]);
+        acc[4 * k4 + 1] = fmaf(w.y, a, acc[4 * k4 + 1]);
+        acc[4 * k4 + 2] = fmaf(w.z, a, acc[4 * k4 + 2]);
+        acc[4 * k4 + 3] = fmaf(w.w, a, acc[4 * k4 + 3]);
+    }
+}
+
+// tile[n][k] += sum_p bufN[n][p] * bufK[k][p] over the 128 columns of the pass: register-tiled 64x64x128 GEMM.
+// Thread t owns k in {t&15 + 16a}, n in {t>>4 + 8b}; its 32 sums live contiguously in the tile-owner layout.
+__device__ __forceinline__ void coop_outer(const float* __restrict__ bufN, const float* __restrict__ bufK,
+                                           float* __restrict__ tile) {
+    const int tid = threadIdx.x, kk = tid & 15, nn = tid >> 4;
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0f;
+#pragma unroll 2
+    for (int p4 = 0; p4 < 32; ++p4) {
+        float4 kv[4], nv[8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) kv[a] = *reinterpret_cast<const float4*>(bufK + (kk + 16 * a) * kLdc + 4 * p4);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) nv[b] = *reinterpret_cast<const float4*>(bufN + (nn + 8 * b) * kLdc + 4 * p4);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                acc[a][b] = fmaf(kv[a].x, nv[b].x, acc[a][b]);
+                acc[a][b] = fmaf(kv[a].y, nv[b].y, acc[a][b]);
+                acc[a][b] = fmaf(kv[a].z, nv[b].z, acc[a][b]);
+                acc[a][b] = fmaf(kv[a].w, nv[b].w, acc[a][b]);
+            }
+    }
+    float4* dst = reinterpret_cast<float4*>(tile + tid * 32);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 v = dst[a * 2 + h];
+            v.x += acc[a][4 * h + 0];
+            v.y += acc[a][4 * h + 1];
+            v.z += acc[a][4 * h + 2];
+            v.w += acc[a][4 * h + 3];
+            dst[a * 2 + h] = v;
+        }
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+// second-layer weights of a head: dWo[c][n] += sum_p dout[c][p] * hid[n][p], dbo[c] += sum_p dout[c][p]
+__device__ __forceinline__ void coop_dwo(const float* __restrict__ hid, const float* __restrict__ dout, int C,
+                                         float* __restrict__ dwo, float* __restrict__ dbo) {
+    for (int idx = threadIdx.x; idx < C * kHid + C; idx += kThreads) {
+        float sum = 0.0f;
+        if (idx < C * kHid) {
+            int c = idx >> 6, n = idx & 63;
+            for (int p4 = 0; p4 < 32; ++p4)
+                sum += dot4(*reinterpret_cast<const float4*>(hid + n * kLdc + 4 * p4),
+                            *reinterpret_cast<const float4*>(dout + c * kLdc + 4 * p4));
+            dwo[idx] += sum;
+        } else {
+            int c = idx - C * kHid;
+            for (int p4 = 0; p4 < 32; ++p4) {
+                float4 v = *reinterpret_cast<const float4*>(dout + c * kLdc + 4 * p4);
+                sum += (v.x + v.y) + (v.z + v.w);
+            }
+            dbo[c] += sum;
+        }
+    }
+}
+
+// first-layer bias and "extra input" weights of a head: db[n] += sum_p dpre[n][p]; dwx[n*ldx + e] += sum_p dpre[n][p] * ex[e][p]
+__device__ __forceinline__ void coop_bias_extras(const float* __restrict__ dpre, const float* __restrict__ ex, int nEx,
+                                                 float* __restrict__ db, float* __restrict__ dwx, int ldx) {
+    const int n = threadIdx.x;
+    if (n >= kHid) return;
+    float sb = 0.0f, se[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int p4 = 0; p4 < 32; ++p4) {
+        float4 v = *reinterpret_cast<const float4*>(dpre + n * kLdc + 4 * p4);
+        sb += (v.x + v.y) + (v.z + v.w);
+        for (int e = 0; e < nEx; ++e) se[e] += dot4(v, *reinterpret_cast<const float4*>(ex + e * kLdc + 4 * p4));
+    }
+    db[n] += sb;
+    for (int e = 0; e < nEx; ++e) dwx[n * ldx + e] += se[e];
+}
+
+// dst[row(rl)][n] += sum over the pass's pairs of row rl of buf[n][col]
+__device__ __forceinline__ void accumulate_rows(const float* __restrict__ buf, float* __restrict__ dst, int ld,
+                                                const int* I, int L, int Wr, int pass_base, int npass) {
+    for (int idx = threadIdx.x; idx < L * kHid; idx += kThreads) {
+        int rl = idx >> 6, n = idx & 63;
+        int lo = max(rl * Wr, pass_base), hi = min((rl + 1) * Wr, pass_base + npass);
+        if (hi <= lo) continue;
+        float sum = 0.0f;
+        for (int gp = lo; gp < hi; ++gp) sum += buf[n * kLdc + (gp - pass_base)];
+        dst[I[IN_ROWS + rl] * ld + n] += sum;
+    }
+}
+
+__device__ __forceinline__ void atomic_add_quat(float* p, const Quat& q) {
+    atomicAdd(p + 0, q.w); atomicAdd(p + 1, q.x); atomicAdd(p + 2, q.y); atomicAdd(p + 3, q.z);
+}
+
+template <int LAYER>
+__device__ __forceinline__ void compute_m1(float (&m1)[kHid], const float* S, const BwdMap& M, const float* __restrict__ params,
+                                           const float* __restrict__ ajt, int Kpad, int i, int j) {
+    constexpr int H = layer_H(LAYER);
+    constexpr int ld1 = 2 * H + kEdge;
+    const float* ai = S + M.f.Ai + i * kLdN;
+    const bool pep = (j >= 0 && j < kN);
+    const float* we = params + param_offset(LAYER, MSG0_W) + 2 * H + (pep ? (kN - 1 + i - j) : 0);
+#pragma unroll 8
+    for (int k = 0; k < kHid; ++k) {
+        float v = ai[k];
+        if (j >= 0) v += __ldcg(ajt + k * Kpad + j);
+        if (pep) v += __ldg(we + k * ld1);
+        m1[k] = fmaxf(v, 0.0f);
+    }
+}
+
+// One pass of up to 128 pairs.  HEADS = attention-carrying pairs (all four heads); otherwise message-only
+// pairs of layer 1 whose only gradient source is the unmasked message sum (model.py:151).
+template <int LAYER, bool HEADS>
+__device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdArgs& g, const PairRef pr, float mult,
+                                          int b, const float* __restrict__ ajt, float* __restrict__ dajt,
+                                          float* __restrict__ tiles, float* __restrict__ direct, const int* I,
+                                          int L, int Wr, int pass_base, int npass, int n_pocket_cols, int pocket_e0) {
+    constexpr bool IN_GRADS = (LAYER == 1);
+    const LayerArgs& a = g.a;
+    const int tid = threadIdx.x;
+    const int i = pr.i, j = pr.j;
+    const bool act = pr.active;
+    const bool pep = (j >= 0 && j < kN);
+    float* bufA = S + M.BufA;
+    float* bufB = S + M.BufB;
+    float* sDout = S + M.Dout;
+    float* sEx = S + M.Ex;
+    const int Kpad = a.Kpad;
+    // offsets of this layer's tensors inside `direct` (relative to the layer's first parameter)
+    constexpr int base = param_offset(LAYER, 0);
+    float dm[kHid];
+
+    {   // ---- recompute the message: m1 (registers) -> m (BufA column) ----
+        float m1[kHid];
+        compute_m1<LAYER>(m1, S, M, a.params, ajt, Kpad, i, j);
+        if (HEADS) {
+#pragma unroll 2
+            for (int n = 0; n < kHid; ++n)
+                bufA[n * kLdc + tid] = S[M.f.PkMisc + 4 * n + 3] + dot64(S + M.W2 + n * kHid, m1);
+        }
+    }
+
+    if (HEADS) {
+        float m[kHid];
+#pragma unroll
+        for (int k = 0; k < kHid; ++k) m[k] = bufA[k * kLdc + tid];
+#pragma unroll
+        for (int k = 0; k < kHid; ++k) dm[k] = 0.0f;
+
+        const float* rg = S + M.RowG + i * 16;
+        const float lse = rg[15], c_i = rg[14];
+        const float logit = g.logits[((size_t)b * kN + i) * Kpad + j];
+        const float w = act ? expf(logit - lse) : 0.0f;
+        const float* pqi = S + M.f.Q + i * 4;
+        const float* pqj = S + M.f.Q + j * 4;
+        const Quat qi{pqi[0], pqi[1], pqi[2], pqi[3]}, qj{pqj[0], pqj[1], pqj[2], pqj[3]};
+        const float rx = S[M.f.X + i * 3] - S[M.f.X + j * 3], ry = S[M.f.X + i * 3 + 1] - S[M.f.X + j * 3 + 1],
+                    rz = S[M.f.X + i * 3 + 2] - S[M.f.X + j * 3 + 2];
+        float dLdw = 0.0f;
+
+        // ================= rotation head (model.py:283-296) =================
+        {
+            const Quat qinvj = qinv(qj);
+            const Quat v = qmul(qi, qj);
+            const Quat lq = qmul(qinvj, v);
+            float pre[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pre[c] = S[M.f.Scal + SC_ROT2B + c];
+#pragma unroll 2
+            for (int n = 0; n < kHid; ++n) {
+                const float4 wq = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n);
+                float s = S[M.f.PkMisc + 4 * n + 2] + wq.x * lq.w + wq.y * lq.x + wq.z * lq.y + wq.w * lq.z;
+                s += dot64(S + M.Wh + HD_ROT * 4096 + n * kHid, m);
+                const float h = fmaxf(s, 0.0f);
+                bufB[n * kLdc + tid] = h;
+                const float4 w2 = *reinterpret_cast<const float4*>(S + M.f.PkRot2 + 4 * n);
+                pre[0] = fmaf(w2.x, h, pre[0]); pre[1] = fmaf(w2.y, h, pre[1]);
+                pre[2] = fmaf(w2.z, h, pre[2]); pre[3] = fmaf(w2.w, h, pre[3]);
+            }
+            const Quat dl{sigmoidf(pre[0]), sigmoidf(pre[1]), sigmoidf(pre[2]), sigmoidf(pre[3])};
+            const Quat u = qmul(dl, qinvj);
+            const Quat dg = qmul(qj, u);
+            const Quat dG{rg[0], rg[1], rg[2], rg[3]};
+            dLdw += qdot(dG, dg);
+            const Quat ddg = qscale(dG, w);
+            const Quat du = qmul_grad_b(qj, ddg);         // dg = qj * u
+            const Quat ddl = qmul_grad_a(du, qinvj);      // u = dl * qinvj
+            float dp2[4] = {ddl.w * dl.w * (1.0f - dl.w), ddl.x * dl.x * (1.0f - dl.x), ddl.y * dl.y * (1.0f - dl.y),
+                            ddl.z * dl.z * (1.0f - dl.z)};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sDout[c * kLdc + tid] = dp2[c];
+            sEx[0 * kLdc + tid] = lq.w; sEx[1 * kLdc + tid] = lq.x; sEx[2 * kLdc + tid] = lq.y; sEx[3 * kLdc + tid] = lq.z;
+            __syncthreads();
+            coop_dwo(bufB, sDout, 4, direct + (param_offset(LAYER, ROT2_W) - base), direct + (param_offset(LAYER, ROT2_B) - base));
+            __syncthreads();
+            float dlq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 2
+            for (int n = 0; n < kHid; ++n) {
+                const float h = bufB[n * kLdc + tid];
+                const float4 w2 = *reinterpret_cast<const float4*>(S + M.f.PkRot2 + 4 * n);
+                float dp = w2.x * dp2[0] + w2.y * dp2[1] + w2.z * dp2[2] + w2.w * dp2[3];
+                dp = h > 0.0f ? dp : 0.0f;
+                bufB[n * kLdc + tid] = dp;
+                axpy64(dm, S + M.Wh + HD_ROT * 4096 + n * kHid, dp);
+                const float4 wq = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n);
+                dlq[0] = fmaf(wq.x, dp, dlq[0]); dlq[1] = fmaf(wq.y, dp, dlq[1]);
+                dlq[2] = fmaf(wq.z, dp, dlq[2]); dlq[3] = fmaf(wq.w, dp, dlq[3]);
+            }
+            if (IN_GRADS && act) {
+                const Quat dlqq{dlq[0], dlq[1], dlq[2], dlq[3]};
+                Quat dqinv = qmul_grad_a(dlqq, v);             // lq = qinvj * v
+                const Quat dv = qmul_grad_b(qinvj, dlqq);
+                Quat dqi = qmul_grad_a(dv, qj);                // v = qi * qj
+                Quat dqj = qmul_grad_b(qi, dv);
+                dqj = qadd(dqj, qmul_grad_a(ddg, u));          // dg = qj * u
+                dqinv = qadd(dqinv, qmul_grad_b(dl, du));      // u = dl * qinvj
+                dqj = qadd(dqj, qinv_grad(qj, dqinv));
+                atomic_add_quat(S + M.dQ + i * 4, dqi);
+                if (pep) atomic_add_quat(S + M.dQ + j * 4, dqj);
+            }
+            __syncthreads();
+            coop_outer(bufB, bufA, tiles + T_ROT * 4096);
+            coop_bias_extras(bufB, sEx, 4, direct + (param_offset(LAYER, ROT0_B) - base),
+                             direct + (param_offset(LAYER, ROT0_W) - base) + 64, 68);
+            __syncthreads();
+        }
+
+        // ================= torsion head (model.py:257-263) =================
+        {
+            float da[PMHC_NTORS];
+#pragma unroll
+            for (int c = 0; c < PMHC_NTORS; ++c) da[c] = S[M.f.Scal + SC_TOR2B + c];
+#pragma unroll 2
+            for (int n = 0; n < kHid; ++n) {
+                float s = S[M.f.Tt + i * kHid + n] + dot64(S + M.Wh + HD_TOR * 4096 + n * kHid, m);
+                const float h = fmaxf(s, 0.0f);
+                bufB[n * kLdc + tid] = h;
+                const float4 w0 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n);
+                const float4 w1 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n + 4);
+                da[0] = fmaf(w0.x, h, da[0]); da[1] = fmaf(w0.y, h, da[1]); da[2] = fmaf(w0.z, h, da[2]);
+                da[3] = fmaf(w0.w, h, da[3]); da[4] = fmaf(w1.x, h, da[4]); da[5] = fmaf(w1.y, h, da[5]);
+                da[6] = fmaf(w1.z, h, da[6]);
+            }
+            float dda[PMHC_NTORS];
+#pragma unroll
+            for (int c = 0; c < PMHC_NTORS; ++c) {
+                dLdw = fmaf(rg[4 + c], da[c], dLdw);
+                dda[c] = w * rg[4 + c];
+                sDout[c * kLdc + tid] = dda[c];
+            }
+            __syncthreads();
+            coop_dwo(bufB, sDout, PMHC_NTORS, direct + (param_offset(LAYER, TOR2_W) - base), direct + (param_offset(LAYER, TOR2_B) - base));
+            __syncthreads();
+#pragma unroll 2
+            for (int n = 0; n < kHid; ++n) {
+                const float h = bufB[n * kLdc + tid];
+                const float4 w0 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n);
+                const float4 w1 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n + 4);
+                float dp = w0.x * dda[0] + w0.y * dda[1] + w0.z * dda[2] + w0.w * dda[3] + w1.x * dda[4] + w1.y * dda[5] + w1.z * dda[6];
+                dp = h > 0.0f ? dp : 0.0f;
+                bufB[n * kLdc + tid] = dp;
+                axpy64(dm, S + M.Wh + HD_TOR * 4096 + n * kHid, dp);
+            }
+            __syncthreads();
+            coop_outer(bufB, bufA, tiles + T_TOR * 4096);
+            accumulate_rows(bufB, S + M.dTt, kHid, I, L, Wr, pass_base, npass);
+            __syncthreads();
+        }
+
+        // ================= translation head (model.py:325-331) =================
+        {
+            float sc = S[M.f.Scal + SC_TRN2B];
+#pragma unroll 2
+            for (int n = 0; n < kHid; ++n) {
+                float s = S[M.f.PkMisc + 4 * n + 0] + dot64(S + M.Wh + HD_TRN * 4096 + n * kHid, m);
+                const float h = fmaxf(s, 0.0f);
+                bufB[n * kLdc + tid] = h;
+                sc = fmaf(S[M.f.PkMisc + 4 * n + 1], h, sc);
+            }
+            const float dXr = rg[11] * rx + rg[12] * ry + rg[13] * rz;
+            dLdw = fmaf(sc, dXr, dLdw);
+            const float ds = w * dXr;
+            sDout[tid] = ds;
+            if (IN_GRADS && act) {
+                const float f = w * sc;
+                atomicAdd(S + M.dX + i * 3 + 0, f * rg[11]); atomicAdd(S + M.dX + i * 3 + 1, f * rg[12]); atomicAdd(S + M.dX + i * 3 + 2, f * rg[13]);
+                if (pep) {
+                    atomicAdd(S + M.dX + j * 3 + 0, -f * rg[11]); atomicAdd(S + M.dX + j * 3 + 1, -f * rg[12]); atomicAdd(S + M.dX + j * 3 + 2, -f * rg[13]);
+                }
+            }
+            __syncthreads();
+            coop_dwo(bufB, sDout, 1, direct + (param_offset(LAYER, TRN2_W) - base), direct + (param_offset(LAYER, TRN2_B) - base));
+            __syncthreads();
+#pragma unroll 2
+            for (int n = 0; n < kHid; ++n) {
+                const float h = bufB[n * kLdc + tid];
+                const float dp = h > 0.0f ? S[M.f.PkMisc + 4 * n + 1] * ds : 0.0f;
+                bufB[n * kLdc + tid] = dp;
+                axpy64(dm, S + M.Wh + HD_TRN * 4096 + n * kHid, dp);
+            }
+            __syncthreads();
+            coop_outer(bufB, bufA, tiles + T_TRN * 4096);
+            coop_bias_extras(bufB, sEx, 0, direct + (param_offset(LAYER, TRN0_B) - base), nullptr, 0);
+            __syncthreads();
+        }
+
+        // ================= attention head (model.py:238-243) =================
+        {
+            const float d2 = rx * rx + ry * ry + rz * rz;
+            const float dotq = qdot(qi, qj);
+            const float qd = dotq * dotq;
+#pragma unroll 2
+            for (int n = 0; n < kHid; ++n) {
+                const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
+                float s = fmaf(pk.y, qd, fmaf(pk.x, -d2, pk.z)) + dot64(S + M.Wh + HD_ATT * 4096 + n * kHid, m);
+                bufB[n * kLdc + tid] = fmaxf(s, 0.0f);
+            }
+            const float dlogit = w * (dLdw - c_i);   // softmax backward with the saved row statistics
+            sDout[tid] = dlogit;
+            sEx[0 * kLdc + tid] = -d2;
+            sEx[1 * kLdc + tid] = qd;
+            __syncthreads();
+            coop_dwo(bufB, sDout, 1, direct + (param_offset(LAYER, ATT2_W) - base), direct + (param_offset(LAYER, ATT2_B) - base));
+            __syncthreads();
+            float gd = 0.0f, gq = 0.0f;
+#pragma unroll 2
+            for (int n = 0; n < kHid; ++n) {
+                const float h = bufB[n * kLdc + tid];
+                const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
+                const float dp = h > 0.0f ? pk.w * dlogit : 0.0f;
+                bufB[n * kLdc + tid] = dp;
+                axpy64(dm, S + M.Wh + HD_ATT * 4096 + n * kHid, dp);
+                gd = fmaf(pk.x, dp, gd);
+                gq = fmaf(pk.y, dp, gq);
+            }
+            if (IN_GRADS && act) {
+                const float f = -gd * 2.0f;                 // d(-d2) = gd
+                atomicAdd(S + M.dX + i * 3 + 0, f * rx); atomicAdd(S + M.dX + i * 3 + 1, f * ry); atomicAdd(S + M.dX + i * 3 + 2, f * rz);
+                const float fq = gq * 2.0f * dotq;
+                atomic_add_quat(S + M.dQ + i * 4, qscale(qj, fq));
+                if (pep) {
+                    atomicAdd(S + M.dX + j * 3 + 0, -f * rx); atomicAdd(S + M.dX + j * 3 + 1, -f * ry); atomicAdd(S + M.dX + j * 3 + 2, -f * rz);
+                    atomic_add_quat(S + M.dQ + j * 4, qscale(qi, fq));
+                }
+            }
+            __syncthreads();
+            coop_outer(bufB, bufA, tiles + T_ATT * 4096);
+            coop_bias_extras(bufB, sEx, 2, direct + (param_offset(LAYER, ATT0_B) - base),
+                             direct + (param_offset(LAYER, ATT0_W) - base) + 64, 66);
+            __syncthreads();
+        }
+        if (LAYER == 0) {
+#pragma unroll
+            for (int k = 0; k < kHid; ++k) dm[k] += S[M.dMsum + i * kHid + k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kHid; ++k) dm[k] = mult * S[M.dMsum + i * kHid + k];
+    }
+
+    // ---- message MLP backward: dW2 += dm (x) m1, dm1 = relu'(.) W2^T dm, then the per-node reductions ----
+#pragma unroll
+    for (int k = 0; k < kHid; ++k) bufB[k * kLdc + tid] = act ? dm[k] : 0.0f;
+    float dm1[kHid];
+    {
+        float m1[kHid];
+        compute_m1<LAYER>(m1, S, M, a.params, ajt, Kpad, i, j);
+#pragma unroll
+        for (int k = 0; k < kHid; ++k) bufA[k * kLdc + tid] = m1[k];
+    }
+#pragma unroll
+    for (int k = 0; k < kHid; ++k) dm1[k] = 0.0f;
+#pragma unroll 2
+    for (int n = 0; n < kHid; ++n) axpy64(dm1, S + M.W2 + n * kHid, bufB[n * kLdc + tid]);
+#pragma unroll
+    for (int k = 0; k < kHid; ++k) dm1[k] = bufA[k * kLdc + tid] > 0.0f ? dm1[k] : 0.0f;
+    __syncthreads();
+    coop_outer(bufB, bufA, tiles + T_W2 * 4096);
+    coop_bias_extras(bufB, sEx, 0, direct + (param_offset(LAYER, MSG2_B) - base), nullptr, 0);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kHid; ++k) bufB[k * kLdc + tid] = dm1[k];
+    if (act && pep) {
+        float* dj = S + M.dAjPep + j * kLdN;
+        float* de = S + M.dWe + (kN - 1 + i - j) * kLdN;
+#pragma unroll 8
+        for (int k = 0; k < kHid; ++k) {
+            atomicAdd(dj + k, dm1[k]);
+            atomicAdd(de + k, dm1[k]);
+        }
+    } else if (act && !HEADS && j >= kN) {
+        // masked pocket slot with non-zero features (rare): straight to the A_j^T gradient scratch
+        for (int k = 0; k < kHid; ++k) atomicAdd(dajt + k * Kpad + j, dm1[k]);
+    }
+    __syncthreads();
+    accumulate_rows(bufB, S + M.dAi, kLdN, I, L, Wr, pass_base, npass);
+    if (HEADS) {
+        // dA_j^T[k][j] += sum over rows of dm1 for the valid pocket columns of this pass
+        const int rl_lo = pass_base / Wr, rl_hi = (pass_base + npass - 1) / Wr;
+        for (int idx = tid; idx < n_pocket_cols * kHid; idx += kThreads) {
+            int k = idx / n_pocket_cols, ep = idx - k * n_pocket_cols;
+            float sum = 0.0f;
+            for (int rl = rl_lo; rl <= rl_hi; ++rl) {
+                int col = rl * Wr + pocket_e0 + ep - pass_base;
+                if (col >= 0 && col < npass) sum += bufB[k * kLdc + col];
+            }
+            dajt[k * Kpad + I[IN_POCKET + ep]] += sum;
+        }
+    }
+    __syncthreads();
+}
+
+template <int LAYER>
+__global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArgs g) {
+    extern __shared__ __align__(16) float S[];
+    const LayerArgs& a = g.a;
+    const BwdMap M = make_bwd_map(a.Kpad);
+    constexpr bool IN_GRADS = (LAYER == 1);
+    constexpr int H = layer_H(LAYER);
+    constexpr int ld1 = 2 * H + kEdge;
+    constexpr int base = param_offset(LAYER, 0);
+    constexpr int layer_numel = param_offset(LAYER + 1, 0) - base;
+    const int tid = threadIdx.x;
+    const int Kpad = a.Kpad, P = a.P;
+    int* I = reinterpret_cast<int*>(S + M.f.Ints);
+    float* ajt = a.ajt_ws + (size_t)blockIdx.x * kHid * Kpad;
+    float* dajt = g.dajt_ws + (size_t)blockIdx.x * kHid * Kpad;
+    float* tiles = g.partial + (size_t)blockIdx.x * g.partial_stride;
+    float* direct = tiles + kTileFloats;
+
+    for (int idx = tid; idx < kTileFloats + layer_numel; idx += kThreads) tiles[idx] = 0.0f;
+    stage_layer_weights_bwd<LAYER>(S, M, a.params);
+    __syncthreads();
+
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const ComplexInfo ci = setup_complex<LAYER>(S, M.f, a, b, ajt);
+        const int L = ci.L;
+        const int W = (L - 1) + ci.nv;
+        for (int idx = tid; idx < M.grads_end - M.dAi; idx += kThreads) S[M.dAi + idx] = 0.0f;
+        for (int idx = tid; idx < kHid * Kpad; idx += kThreads) dajt[idx] = 0.0f;
+        if (LAYER == 0)
+            for (int idx = tid; idx < kN * kHid; idx += kThreads) S[M.f.Msum + idx] = g.msum[(size_t)b * kN * kHid + idx];
+        __syncthreads();
+
+        // ---------------- row level: output normalisation, q' = g * q_i, torsion rotation, x' = x + Xa ----------------
+        if (tid < L) {
+            const int i = I[IN_ROWS + tid];
+            const size_t node = (size_t)b * kN + i;
+            const float* rs = g.rowstat + node * PMHC_ROWSTAT;
+            const float* dof = g.d_frames_out + node * 7;
+            const float* dot_ = g.d_tors_out + node * 14;
+            const Quat G{rs[1], rs[2], rs[3], rs[4]};
+            const Quat qi{S[M.f.Q + i * 4], S[M.f.Q + i * 4 + 1], S[M.f.Q + i * 4 + 2], S[M.f.Q + i * 4 + 3]};
+            const bool hasnb = W > 0;
+            const Quat gq = hasnb ? qnormalize(G) : Quat{1.0f, 0.0f, 0.0f, 0.0f};
+            const Quat qp = qmul(gq, qi);
+            const Quat dqp = qnormalize_grad(qp, Quat{dof[0], dof[1], dof[2], dof[3]});
+            const Quat dgq = qmul_grad_a(dqp, qi);
+            const Quat dG = hasnb ? qnormalize_grad(G, dgq) : Quat{0.0f, 0.0f, 0.0f, 0.0f};
+            float* rg = S + M.RowG + i * 16;
+            rg[0] = dG.w; rg[1] = dG.x; rg[2] = dG.y; rg[3] = dG.z;
+            float cacc = qdot(dG, G);
+            if (IN_GRADS) {
+                const Quat dqi = qmul_grad_b(gq, dqp);
+                S[M.dQ + i * 4 + 0] += dqi.w; S[M.dQ + i * 4 + 1] += dqi.x; S[M.dQ + i * 4 + 2] += dqi.y; S[M.dQ + i * 4 + 3] += dqi.z;
+            }
+            for (int c = 0; c < PMHC_NTORS; ++c) {
+                float sn, cs;
+                sincosf(rs[5 + c], &sn, &cs);
+                const float ts = S[M.f.Tors + i * 14 + 2 * c], tc = S[M.f.Tors + i * 14 + 2 * c + 1];
+                const float ds_ = dot_[2 * c], dc_ = dot_[2 * c + 1];
+                const float dS = ds_ * tc - dc_ * ts, dC = ds_ * ts + dc_ * tc;
+                const float dDa = dS * cs - dC * sn;
+                rg[4 + c] = dDa;
+                cacc = fmaf(dDa, rs[5 + c], cacc);
+                if (IN_GRADS) {
+                    S[M.dTors + i * 14 + 2 * c] += ds_ * cs - dc_ * sn;
+                    S[M.dTors + i * 14 + 2 * c + 1] += ds_ * sn + dc_ * cs;
+                }
+            }
+            for (int c = 0; c < 3; ++c) {
+                rg[11 + c] = dof[4 + c];
+                cacc = fmaf(dof[4 + c], rs[12 + c], cacc);
+                if (IN_GRADS) S[M.dX + i * 3 + c] += dof[4 + c];
+            }
+            rg[14] = cacc;
+            rg[15] = rs[0];
+        }
+
+        // ---------------- layer 1: node feature MLP backward (model.py:151, :407) -> dMsum ----------------
+        if (LAYER == 0) {
+            const float* f0w = a.params + param_offset(0, FEAT0_W);
+            const float* f0b = a.params + param_offset(0, FEAT0_B);
+            const float* f2w = a.params + param_offset(0, FEAT2_W);
+            constexpr int ldf = kH1 + kHid;
+            float* hid = S + M.BufA;                 // [16][65] relu(feature_mlp.0(...))
+            float* dO = S + M.BufA + kN * kLdN;      // [16][65] dL/do (after the relu mask)
+            float* dhid = S + M.BufB;                // [16][65]
+            for (int idx = tid; idx < L * kHid; idx += kThreads) {
+                int r = idx >> 6, n = idx & 63;
+                int i = I[IN_ROWS + r];
+                const float* w = f0w + n * ldf;
+                const float* h = S + M.f.H + i * kLdN;
+                const float* ms = S + M.f.Msum + i * kHid;
+                float acc = f0b[n];
+                for (int c = 0; c < kH1; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
+                for (int c = 0; c < kHid; ++c) acc = fmaf(__ldg(w + kH1 + c), ms[c], acc);
+                hid[r * kLdN + n] = fmaxf(acc, 0.0f);
+                const size_t node = (size_t)b * kN + i;
+                dO[r * kLdN + n] = g.feat_post[node * kHid + n] > 0.0f ? g.d_feat_out[node * kHid + n] : 0.0f;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < L * kHid; idx += kThreads) {
+                int r = idx >> 6, n = idx & 63;
+                float acc = 0.0f;
+                for (int n2 = 0; n2 < kHid; ++n2) acc = fmaf(__ldg(f2w + n2 * kHid + n), dO[r * kLdN + n2], acc);
+                dhid[r * kLdN + n] = hid[r * kLdN + n] > 0.0f ? acc : 0.0f;
+            }
+            // feature_mlp.2: dW[n2][n] += sum_r dO[r][n2] hid[r][n]; db[n2] += sum_r dO[r][n2]
+            for (int idx = tid; idx < kHid * kHid + kHid; idx += kThreads) {
+                float acc = 0.0f;
+                if (idx < kHid * kHid) {
+                    int n2 = idx >> 6, n = idx & 63;
+                    for (int r = 0; r < L; ++r) acc = fmaf(dO[r * kLdN + n2], hid[r * kLdN + n], acc);
+                    direct[(param_offset(0, FEAT2_W) - base) + idx] += acc;
+                } else {
+                    int n2 = idx - kHid * kHid;
+                    for (int r = 0; r < L; ++r) acc += dO[r * kLdN + n2];
+                    direct[(param_offset(0, FEAT2_B) - base) + n2] += acc;
+                }
+            }
+            __syncthreads();
+            // feature_mlp.0: dW[n][c] += sum_r dhid[r][n] cat(h, msum)[r][c]; db[n] += sum_r dhid[r][n]
+            for (int idx = tid; idx < kHid * ldf + kHid; idx += kThreads) {
+                float acc = 0.0f;
+                if (idx < kHid * ldf) {
+                    int n = idx / ldf, c = idx - n * ldf;
+                    for (int r = 0; r < L; ++r) {
+                        int i = I[IN_ROWS + r];
+                        float x = c < kH1 ? S[M.f.H + i * kLdN + c] : S[M.f.Msum + i * kHid + (c - kH1)];
+                        acc = fmaf(dhid[r * kLdN + n], x, acc);
+                    }
+                    direct[(param_offset(0, FEAT0_W) - base) + idx] += acc;
+                } else {
+                    int n = idx - kHid * ldf;
+                    for (int r = 0; r < L; ++r) acc += dhid[r * kLdN + n];
+                    direct[(param_offset(0, FEAT0_B) - base) + n] += acc;
+                }
+            }
+            for (int idx = tid; idx < L * kHid; idx += kThreads) {
+                int r = idx >> 6, k = idx & 63;
+                float acc = 0.0f;
+                for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(f0w + n * ldf + kH1 + k), dhid[r * kLdN + n], acc);
+                S[M.dMsum + I[IN_ROWS + r] * kHid + k] = acc;
+            }
+        }
+        __syncthreads();
+
+        // ---------------- attention-carrying pairs ----------------
+        const int total = L > 0 ? L * W : 0;
+        for (int pass_base = 0; pass_base < total; pass_base += kThreads) {
+            const int npass = min(kThreads, total - pass_base);
+            const bool act = tid < npass;
+            const PairRef pr = decode_full_pair(I, act ? pass_base + tid : pass_base, W, L, 0, act);
+            pair_pass<LAYER, true>(S, M, g, pr, 1.0f, b, ajt, dajt, tiles, direct, I, L, W, pass_base, npass, ci.nv, L - 1);
+        }
+        // ---------------- layer 1: message-only pairs (self, masked peptide / pocket slots) ----------------
+        if (LAYER == 0 && L > 0) {
+            const int npx = kN - L;
+            const int W2 = 1 + npx + ci.nx + (ci.c0 > 0 ? 1 : 0);
+            const int total2 = L * W2;
+            for (int pass_base = 0; pass_base < total2; pass_base += kThreads) {
+                const int npass = min(kThreads, total2 - pass_base);
+                const bool act = tid < npass;
+                const int gp = act ? pass_base + tid : pass_base;
+                const int rl = gp / W2, e = gp - rl * W2;
+                PairRef pr;
+                pr.i = I[IN_ROWS + rl];
+                pr.active = act;
+                float mult = 1.0f;
+                if (e == 0) pr.j = pr.i;
+                else if (e <= npx) pr.j = I[IN_PEPX + e - 1];
+                else if (e <= npx + ci.nx) pr.j = I[IN_POCKET + Kpad - 1 - (e - npx - 1)];
+                else { pr.j = -1; mult = (float)ci.c0; }
+                pair_pass<LAYER, false>(S, M, g, pr, mult, b, ajt, dajt, tiles, direct, I, L, W2, pass_base, npass, 0, 0);
+            }
+        }
+        __syncthreads();
+
+        // ---------------- node level: message_mlp.0, torsion_mlp.0[:, 64:78] and biases; input gradients ----------------
+        {
+            float* dW1 = direct + (param_offset(LAYER, MSG0_W) - base);
+            for (int idx = tid; idx < kHid * ld1; idx += kThreads) {
+                int k = idx / ld1, c = idx - k * ld1;
+                float acc = 0.0f;
+                if (c < H) {
+                    for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dAi + i * kLdN + k], S[M.f.H + i * kLdN + c], acc);
+                } else if (c < 2 * H) {
+                    int cc = c - H;
+                    for (int j = 0; j < kN; ++j) acc = fmaf(S[M.dAjPep + j * kLdN + k], S[M.f.H + j * kLdN + cc], acc);
+                    if (cc < PMHC_NFEAT) {
+                        const float* pf = a.pocket_feat + (size_t)b * P * PMHC_NFEAT + cc;
+                        const float* dj = dajt + k * Kpad + kN;
+                        for (int p = 0; p < P; ++p) acc = fmaf(__ldcg(dj + p), __ldg(pf + p * PMHC_NFEAT), acc);
+                    }
+                } else {
+                    acc = S[M.dWe + (c - 2 * H) * kLdN + k];
+                }
+                dW1[idx] += acc;
+            }
+            for (int k = tid; k < kHid; k += kThreads) {
+                float acc = 0.0f, acct = 0.0f;
+                for (int i = 0; i < kN; ++i) {
+                    acc += S[M.dAi + i * kLdN + k];
+                    acct += S[M.dTt + i * kHid + k];
+                }
+                direct[(param_offset(LAYER, MSG0_B) - base) + k] += acc;
+                direct[(param_offset(LAYER, TOR0_B) - base) + k] += acct;
+            }
+            for (int idx = tid; idx < kHid * 14; idx += kThreads) {
+                int n = idx / 14, c = idx - n * 14;
+                float acc = 0.0f;
+                for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dTt + i * kHid + n], S[M.f.Tors + i * 14 + c], acc);
+                direct[(param_offset(LAYER, TOR0_W) - base) + n * 78 + 64 + c] += acc;
+            }
+            if (IN_GRADS) {
+                const float* tor0 = a.params + param_offset(LAYER, TOR0_W);
+                const float* msg0 = a.params + param_offset(LAYER, MSG0_W);
+                for (int idx = tid; idx < kN * 7; idx += kThreads) {
+                    int i = idx / 7, c = idx - i * 7;
+                    g.d_frames_in[((size_t)b * kN + i) * 7 + c] = c < 4 ? S[M.dQ + i * 4 + c] : S[M.dX + i * 3 + (c - 4)];
+                }
+                for (int idx = tid; idx < kN * 14; idx += kThreads) {
+                    int i = idx / 14, c = idx - i * 14;
+                    float acc = S[M.dTors + idx];
+                    for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(tor0 + n * 78 + 64 + c), S[M.dTt + i * kHid + n], acc);
+                    g.d_tors_in[(size_t)b * kN * 14 + idx] = acc;
+                }
+                for (int idx = tid; idx < kN * kHid; idx += kThreads) {
+                    int i = idx >> 6, c = idx & 63;
+                    float acc = 0.0f;
+                    for (int k = 0; k < kHid; ++k) {
+                        acc = fmaf(S[M.dAi + i * kLdN + k], __ldg(msg0 + k * ld1 + c), acc);
+                        acc = fmaf(S[M.dAjPep + i * kLdN + k], __ldg(msg0 + k * ld1 + H + c), acc);
+                    }
+                    g.d_feat_in[(size_t)b * kN * kHid + idx] = acc;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---------------- fold the tile-owner partials into the parameter layout of this CTA's `direct` region ----------------
+    __syncthreads();
+    for (int idx = tid; idx < kTileFloats; idx += kThreads) {
+        int T = idx >> 12, r = idx & 4095;
+        int t = r >> 5, e = r & 31;
+        int k = (t & 15) + 16 * (e >> 3), n = (t >> 4) + 8 * (e & 7);
+        int off, ld;
+        switch (T) {
+            case T_W2: off = param_offset(LAYER, MSG2_W); ld = 64; break;
+            case T_ATT: off = param_offset(LAYER, ATT0_W); ld = 66; break;
+            case T_ROT: off = param_offset(LAYER, ROT0_W); ld = 68; break;
+            case T_TOR: off = param_offset(LAYER, TOR0_W); ld = 78; break;
+            default: off = param_offset(LAYER, TRN0_W); ld = 64; break;
+        }
+        direct[(off - base) + n * ld + k] += tiles[idx];
+    }
+}
+
+// grad[p] += sum over CTAs of direct[cta][p]
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int stride, int n_cta, int numel,
+                                       float* __restrict__ grad) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= numel) return;
+    float acc = 0.0f;
+    for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * stride + kTileFloats + p];
+    grad[p] += acc;
+}
+
+struct BwdWorkspace {
+    float *ajt, *dajt, *partial, *d_frames1, *d_tors1, *d_feat1;
+    int partial_stride;
+    size_t bytes;
+};
+
+BwdWorkspace carve_bwd_workspace(void* wsbase, size_t fwd_bytes, int B, int P) {
+    BwdWorkspace w;
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    float* p = (float*)wsbase;
+    size_t o = 0;
+    w.ajt = p;  // shared with the forward's scratch (first region of the forward workspace)
+    o = (fwd_bytes + 15) / 16 * 4;
+    w.dajt = p + o;      o += (size_t)sms * kHid * pad_k(P);
+    constexpr int max_layer = param_offset(1, 0) > (PMHC_NPARAM - param_offset(1, 0)) ? param_offset(1, 0) : (PMHC_NPARAM - param_offset(1, 0));
+    w.partial_stride = ((kTileFloats + max_layer + 3) / 4) * 4;
+    w.partial = p + o;   o += (size_t)sms * w.partial_stride;
+    w.d_frames1 = p + o; o += (size_t)B * kN * 7;
+    w.d_tors1 = p + o;   o += (size_t)B * kN * 14;
+    w.d_feat1 = p + o;   o += (size_t)B * kN * kHid;
+    w.bytes = o * sizeof(float);
+    return w;
+}
+
+template <int LAYER>
+int launch_layer_backward(const BwdArgs& g, int n_cta, float* grad, cudaStream_t stream) {
+    static bool configured = false;
+    int max_smem = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const BwdMap M = make_bwd_map(g.a.Kpad);
+    size_t smem = (size_t)M.total_floats * sizeof(float);
+    PMHC_REQUIRE((int)smem <= max_smem, "EGNN backward needs %zu B of shared memory (P=%d), device allows %d", smem, g.a.P, max_smem);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(egnn_layer_backward_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(backward): %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    if (profile_enabled()) profile_mark(PROF_BWD, stream, true);
+    egnn_layer_backward_kernel<LAYER><<<n_cta, kThreads, smem, stream>>>(g);
+    if (profile_enabled()) profile_mark(PROF_BWD, stream, false);
+    PMHC_CHECK_LAUNCH("egnn_layer_backward");
+    constexpr int base = param_offset(LAYER, 0);
+    constexpr int numel = param_offset(LAYER + 1, 0) - base;
+    reduce_partials_kernel<<<(numel + 255) / 256, 256, 0, stream>>>(g.partial, g.partial_stride, n_cta, numel, grad + base);
+    PMHC_CHECK_LAUNCH("reduce_partials");
+    return 0;
+}
+
+size_t forward_workspace_bytes(int B, int P);
+
+}  // namespace pmhc
+
+using namespace pmhc;
+
+extern "C" size_t pmhc_workspace_bytes(int B, int P) {
+    return carve_bwd_workspace(nullptr, forward_workspace_bytes(B, P), B, P).bytes;
+}
+
+extern "C" int pmhc_model_backward(const float* params, const PmhcBatch* bt, float t_over_T, const float* saved,
+                                   const float* d_out_frames, const float* d_out_torsions, float* flat_grad,
+                                   void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PMHC_REQUIRE(device_props() == 0, "no CUDA device");
+    PMHC_REQUIRE(bt != nullptr && bt->B > 0, "pmhc_model_backward: empty batch");
+    PMHC_REQUIRE(bt->P >= 1 && bt->P <= kMaxP, "pmhc_model_backward: pocket_maxlen %d outside [1, %d]", bt->P, kMaxP);
+    PMHC_REQUIRE(saved != nullptr, "pmhc_model_backward: the forward must have been run with a `saved` buffer");
+    const size_t fwd_bytes = forward_workspace_bytes(bt->B, bt->P);
+    BwdWorkspace w = carve_bwd_workspace(workspace, fwd_bytes, bt->B, bt->P);
+    PMHC_REQUIRE(workspace != nullptr && workspace_bytes >= w.bytes, "pmhc_model_backward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    SavedMap sv = carve_saved(const_cast<float*>(saved), bt->B, bt->P);
+    const int n_cta = bt->B < num_sms() ? bt->B : num_sms();
+
+    BwdArgs g{};
+    g.a.params = params;
+    g.a.B = bt->B; g.a.P = bt->P; g.a.Kpad = pad_k(bt->P);
+    g.a.t_over_T = t_over_T;
+    g.a.mask = bt->mask;
+    g.a.pocket_frames = bt->pocket_frames; g.a.pocket_feat = bt->pocket_features; g.a.pocket_mask = bt->pocket_mask;
+    g.a.ajt_ws = w.ajt;
+    g.partial = w.partial; g.partial_stride = w.partial_stride; g.dajt_ws = w.dajt;
+
+    // layer 2 (its inputs are layer 1's outputs)
+    g.a.frames_in = sv.frames1; g.a.tors_in = sv.tors1; g.a.feat_in = sv.feat1;
+    g.rowstat = sv.rowstat2; g.logits = sv.logits2; g.msum = nullptr; g.feat_post = nullptr;
+    g.d_frames_out = d_out_frames; g.d_tors_out = d_out_torsions; g.d_feat_out = nullptr;
+    g.d_frames_in = w.d_frames1; g.d_tors_in = w.d_tors1; g.d_feat_in = w.d_feat1;
+    int rc = launch_layer_backward<1>(g, n_cta, flat_grad, stream);
+    if (rc != 0) return rc;
+    // layer 1
+    g.a.frames_in = bt->frames; g.a.tors_in = bt->torsions; g.a.feat_in = bt->features;
+    g.rowstat = sv.rowstat1; g.logits = sv.logits1; g.msum = sv.msum1; g.feat_post = sv.feat1;
+    g.d_frames_out = w.d_frames1; g.d_tors_out = w.d_tors1; g.d_feat_out = w.d_feat1;
+    g.d_frames_in = nullptr; g.d_tors_in = nullptr; g.d_feat_in = nullptr;
+    return launch_layer_backward<0>(g, n_cta, flat_grad, stream);
+}

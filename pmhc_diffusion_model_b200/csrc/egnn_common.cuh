@@ -1,0 +1,350 @@
+// egnn_common.cuh — shared-memory layout, weight staging and per-complex setup used by the fused
+// EGNN layer forward and backward kernels.
+//
+// Factorisation used everywhere (derived from the reference's definitions, model.py:183-333):
+//   message_mlp.0(cat(h_i, h_j, e_ij)) = A_i[i] + A_j[j] + W_e[:, rel(i,j)] * [j is peptide]   (bias folded in A_i)
+//   attention_mlp.0(cat(m, -d2, qdot2)) = W_m m - w_d d2 + w_q qdot2 + b
+//   rotation_mlp.0(cat(m, local_q))     = W_m m + W_q local_q + b
+//   torsion_mlp.0(cat(m, tors_i))       = W_m m + T_t[i]          (T_t = W_t tors_i + b, per node)
+//   translation_mlp.0(m)                = W_m m + b
+// so per pair the dense work is 64x64 (message layer 2) and 64x256 (the four head hidden layers share m).
+#pragma once
+
+#include "common.cuh"
+#include "pmhc_math.cuh"
+
+namespace pmhc {
+
+constexpr int kThreads = 128;        // one CTA = 4 warps, one CTA per SM (shared memory bound)
+constexpr int kPassPairs = 256;      // pairs per full pass (2 per thread)
+constexpr int kScrLd = kPassPairs + 1;  // odd row stride -> conflict-free column access
+constexpr int kCapPairs = 512;       // pairs whose head outputs are buffered before the row softmax
+constexpr int kOutPerPair = 15;      // logit, global delta quat (4), delta angles (7), scale * (x_i - x_j) (3)
+constexpr int kLdN = kHid + 1;       // padded stride of per-node rows (A_i, W_e) -> conflict-free
+constexpr int kMaxP = 480;           // largest pocket_maxlen the shared-memory budget allows
+
+struct LayerArgs {
+    const float* params;         // flat parameter buffer
+    int B, P, Kpad;              // complexes, pocket slots, padded neighbour count (multiple of 32)
+    float t_over_T;
+    const float* frames_in;      // [B,16,7]
+    const float* tors_in;        // [B,16,14]
+    const float* feat_in;        // layer 1: [B,16,22] features; layer 2: [B,16,64] relu(o1)
+    const uint8_t* mask;         // [B,16]
+    const float* pocket_frames;  // [B,P,7]
+    const float* pocket_feat;    // [B,P,22]
+    const uint8_t* pocket_mask;  // [B,P]
+    float* frames_out;           // [B,16,7]
+    float* tors_out;             // [B,16,14]
+    float* feat_out;             // layer 1 only: [B,16,64] relu(o1)
+    float* msum_out;             // layer 1, training only: [B,16,64] unmasked message sums
+    float* rowstat;              // training only: [B,16,16] lse, G(4), dA(7), Xa(3), pad
+    float* logit_out;            // training only: [B,16,Kpad] attention logits by neighbour slot
+    float* ajt_ws;               // [gridDim.x][64][Kpad] per-CTA scratch for the neighbour projections A_j^T
+};
+
+// pointers into the caller's `saved` buffer (pmhc_saved_floats)
+struct SavedMap {
+    float *rowstat1, *rowstat2, *frames1, *tors1, *feat1, *msum1, *logits1, *logits2;
+};
+SavedMap carve_saved(float* saved, int B, int P);
+int pad_k(int P);
+int device_props();
+int num_sms();
+
+// ---- shared memory map (float offsets); K-dependent arrays last ----
+struct SmemMap {
+    int W2T, WhT, We, PkAtt, PkRotQ, PkRot2, PkMisc, PkTor2, Scal;
+    int Scr, Out, Ai, Tt, Msum, H, Tors, Q, X, Ints, total_floats;
+};
+
+__host__ __device__ inline SmemMap make_smem_map(int Kpad) {
+    SmemMap m;
+    int o = 0;
+    m.W2T = o;  o += kHid * kHid;
+    m.WhT = o;  o += kHid * 4 * kHid;
+    m.We = o;   o += kEdge * kLdN + 1;   // +1 keeps the next array 16-byte aligned (31*65 = 2015)
+    // per-hidden-unit parameter packs, one float4 (or two) per unit n so the head epilogues need one 128-bit
+    // shared load per unit: PkAtt = {w_d, w_q, b_att, att2}, PkRotQ = W_q[n, 0:4], PkRot2 = rot2[0:4, n],
+    // PkMisc = {b_trn, trn2, b_rot, b2}, PkTor2 = {tor2[0:7, n], 0}
+    m.PkAtt = o;  o += 4 * kHid;
+    m.PkRotQ = o; o += 4 * kHid;
+    m.PkRot2 = o; o += 4 * kHid;
+    m.PkMisc = o; o += 4 * kHid;
+    m.PkTor2 = o; o += 8 * kHid;
+    m.Scal = o;   o += 16;
+    m.Scr = o;  o += kHid * kScrLd + 3;  // 64*257 = 16448 (+3 -> multiple of 4... keep alignment below)
+    o = (o + 3) & ~3;
+    m.Out = o;  o += kCapPairs * kOutPerPair;
+    m.Ai = o;   o += kN * kLdN;
+    o = (o + 3) & ~3;
+    m.Tt = o;   o += kN * kHid;
+    m.Msum = o; o += kN * kHid;
+    m.H = o;    o += kN * kLdN;
+    o = (o + 3) & ~3;
+    m.Tors = o; o += kN * 2 * PMHC_NTORS;
+    m.Q = o;    o += Kpad * 4;
+    m.X = o;    o += Kpad * 3;
+    o = (o + 3) & ~3;
+    m.Ints = o; o += Kpad + 64;          // neighbour lists and row lists (int32)
+    m.total_floats = o;
+    return m;
+}
+
+// scalar slots inside Scal
+enum { SC_ATT2B = 0, SC_TRN2B = 1, SC_ROT2B = 2 /*..5*/, SC_TOR2B = 6 /*..12*/ };
+
+// int slots (relative to Ints): [0,16) real rows; [16,32) masked peptide slots; [32, 32+Kpad) pocket lists:
+// valid pocket slots packed from the front, masked-with-nonzero-features packed from the back.
+enum { IN_ROWS = 0, IN_PEPX = 16, IN_POCKET = 32 };
+
+struct ComplexInfo {
+    int L;    // real peptide rows
+    int nv;   // valid pocket slots
+    int nx;   // masked pocket slots with non-zero features (need their own message in layer 1)
+    int c0;   // masked pocket slots with all-zero features (one shared message, multiplicity c0)
+};
+
+// Copy one layer's weights into shared memory in the k-major layouts the pair loops read.
+template <int LAYER>
+__device__ inline void stage_layer_weights(float* S, const SmemMap& M, const float* __restrict__ params) {
+    constexpr int L = LAYER;
+    constexpr int H = layer_H(L);
+    const int tid = threadIdx.x;
+    const float* msg0 = params + param_offset(L, MSG0_W);
+    const float* msg2 = params + param_offset(L, MSG2_W);
+    const float* att0 = params + param_offset(L, ATT0_W);
+    const float* rot0 = params + param_offset(L, ROT0_W);
+    const float* tor0 = params + param_offset(L, TOR0_W);
+    const float* trn0 = params + param_offset(L, TRN0_W);
+    constexpr int ld1 = 2 * H + kEdge;
+    // global reads are coalesced along the weight rows (k fastest); shared writes are transposed
+    for (int idx = tid; idx < kHid * kHid; idx += kThreads) {
+        int n = idx >> 6, k = idx & 63;
+        S[M.W2T + k * kHid + n] = msg2[idx];
+        S[M.WhT + k * 256 + 192 + n] = trn0[idx];
+    }
+    for (int idx = tid; idx < kHid * 66; idx += kThreads) {
+        int n = idx / 66, k = idx - n * 66;
+        float v = att0[idx];
+        if (k < 64) S[M.WhT + k * 256 + n] = v;
+        else S[M.PkAtt + 4 * n + (k - 64)] = v;       // w_d, w_q
+    }
+    for (int idx = tid; idx < kHid * 68; idx += kThreads) {
+        int n = idx / 68, k = idx - n * 68;
+        float v = rot0[idx];
+        if (k < 64) S[M.WhT + k * 256 + 64 + n] = v;
+        else S[M.PkRotQ + 4 * n + (k - 64)] = v;
+    }
+    for (int idx = tid; idx < kHid * 78; idx += kThreads) {
+        int n = idx / 78, k = idx - n * 78;
+        if (k < 64) S[M.WhT + k * 256 + 128 + n] = tor0[idx];
+    }
+    for (int idx = tid; idx < kHid * kEdge; idx += kThreads) {
+        int k = idx / kEdge, r = idx - k * kEdge;
+        S[M.We + r * kLdN + k] = msg0[k * ld1 + 2 * H + r];
+    }
+    for (int n = tid; n < kHid; n += kThreads) {
+        S[M.PkAtt + 4 * n + 2] = params[param_offset(L, ATT0_B) + n];
+        S[M.PkAtt + 4 * n + 3] = params[param_offset(L, ATT2_W) + n];
+        S[M.PkMisc + 4 * n + 0] = params[param_offset(L, TRN0_B) + n];
+        S[M.PkMisc + 4 * n + 1] = params[param_offset(L, TRN2_W) + n];
+        S[M.PkMisc + 4 * n + 2] = params[param_offset(L, ROT0_B) + n];
+        S[M.PkMisc + 4 * n + 3] = params[param_offset(L, MSG2_B) + n];
+        S[M.PkTor2 + 8 * n + 7] = 0.0f;
+    }
+    for (int idx = tid; idx < 4 * kHid; idx += kThreads) {
+        int c = idx >> 6, n = idx & 63;
+        S[M.PkRot2 + 4 * n + c] = params[param_offset(L, ROT2_W) + idx];
+    }
+    for (int idx = tid; idx < PMHC_NTORS * kHid; idx += kThreads) {
+        int c = idx >> 6, n = idx & 63;
+        S[M.PkTor2 + 8 * n + c] = params[param_offset(L, TOR2_W) + idx];
+    }
+    if (tid == 0) {
+        S[M.Scal + SC_ATT2B] = params[param_offset(L, ATT2_B)];
+        S[M.Scal + SC_TRN2B] = params[param_offset(L, TRN2_B)];
+        for (int c = 0; c < 4; ++c) S[M.Scal + SC_ROT2B + c] = params[param_offset(L, ROT2_B) + c];
+        for (int c = 0; c < PMHC_NTORS; ++c) S[M.Scal + SC_TOR2B + c] = params[param_offset(L, TOR2_B) + c];
+    }
+}
+
+// Per-complex setup: frames, torsions, node features, row / neighbour lists, and the per-node projections
+// A_i (shared), A_j^T (global scratch, [64][Kpad]) and T_t (shared).  Ends with a __syncthreads().
+template <int LAYER>
+__device__ inline ComplexInfo setup_complex(float* S, const SmemMap& M, const LayerArgs& a, int b, float* ajt) {
+    constexpr int L = LAYER;
+    constexpr int H = layer_H(L);
+    constexpr int ld1 = 2 * H + kEdge;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = a.P, K = kN + P, Kpad = a.Kpad;
+    int* I = reinterpret_cast<int*>(S + M.Ints);
+    float* feat_stage = S + M.Scr;  // pocket features staged here: [P][23] (scr is free during setup)
+    constexpr int FS = 23;
+
+    // -- geometry of all K slots --
+    for (int idx = tid; idx < K * 7; idx += kThreads) {
+        int j = idx / 7, c = idx - j * 7;
+        float v = (j < kN) ? a.frames_in[((size_t)b * kN + j) * 7 + c] : a.pocket_frames[((size_t)b * P + (j - kN)) * 7 + c];
+        if (c < 4) S[M.Q + j * 4 + c] = v;
+        else S[M.X + j * 3 + (c - 4)] = v;
+    }
+    for (int idx = tid; idx < kN * 14; idx += kThreads) S[M.Tors + idx] = a.tors_in[(size_t)b * kN * 14 + idx];
+    // -- node features: layer 1 = (22 features, t/T); layer 2 = 64 learned features --
+    for (int idx = tid; idx < kN * kHid; idx += kThreads) {
+        int i = idx >> 6, c = idx & 63;
+        float v;
+        if (L == 0) v = (c < PMHC_NFEAT) ? a.feat_in[((size_t)b * kN + i) * PMHC_NFEAT + c] : (c == PMHC_NFEAT ? a.t_over_T : 0.0f);
+        else v = a.feat_in[((size_t)b * kN + i) * kHid + c];
+        S[M.H + i * kLdN + c] = v;
+    }
+    for (int idx = tid; idx < P * PMHC_NFEAT; idx += kThreads) {
+        int j = idx / PMHC_NFEAT, c = idx - j * PMHC_NFEAT;
+        feat_stage[j * FS + c] = a.pocket_feat[(size_t)b * P * PMHC_NFEAT + idx];
+    }
+    __syncthreads();
+
+    // -- lists (warp 0): real rows, masked peptide slots, valid pocket slots, masked non-zero pocket slots --
+    if (warp == 0) {
+        bool real = lane < kN && a.mask[(size_t)b * kN + lane] != 0;
+        unsigned bal = __ballot_sync(0xffffffffu, real);
+        int pos = __popc(bal & ((1u << lane) - 1u));
+        int Lr = __popc(bal);
+        if (lane < kN) {
+            if (real) I[IN_ROWS + pos] = lane;
+            else I[IN_PEPX + (lane - pos)] = lane;
+        }
+        int nv = 0, nx = 0, c0 = 0;
+        for (int base = 0; base < P; base += 32) {
+            int j = base + lane;
+            bool in = j < P;
+            bool valid = in && a.pocket_mask[(size_t)b * P + j] != 0;
+            bool nonzero = false;
+            if (in && !valid) {
+                for (int c = 0; c < PMHC_NFEAT; ++c) nonzero |= (feat_stage[j * FS + c] != 0.0f);
+            }
+            unsigned bv = __ballot_sync(0xffffffffu, valid);
+            unsigned bx = __ballot_sync(0xffffffffu, in && !valid && nonzero);
+            unsigned bz = __ballot_sync(0xffffffffu, in && !valid && !nonzero);
+            if (valid) I[IN_POCKET + nv + __popc(bv & ((1u << lane) - 1u))] = kN + j;
+            if (in && !valid && nonzero) I[IN_POCKET + Kpad - 1 - (nx + __popc(bx & ((1u << lane) - 1u)))] = kN + j;
+            nv += __popc(bv);
+            nx += __popc(bx);
+            c0 += __popc(bz);
+        }
+        if (lane == 0) {
+            I[IN_POCKET + Kpad + 0] = Lr;
+            I[IN_POCKET + Kpad + 1] = nv;
+            I[IN_POCKET + Kpad + 2] = nx;
+            I[IN_POCKET + Kpad + 3] = c0;
+        }
+    }
+
+    // -- per-node projections --
+    const float* msg0 = a.params + param_offset(L, MSG0_W);
+    const float* msg0b = a.params + param_offset(L, MSG0_B);
+    const float* tor0 = a.params + param_offset(L, TOR0_W);
+    const float* tor0b = a.params + param_offset(L, TOR0_B);
+    // A_i[i][k] = b1[k] + W1[k, 0:H] h_i   (all 16 slots; padded rows are never read as i)
+    for (int idx = tid; idx < kN * kHid; idx += kThreads) {
+        int k = idx >> 4, i = idx & 15;
+        const float* w = msg0 + k * ld1;
+        const float* h = S + M.H + i * kLdN;
+        float acc = msg0b[k];
+#pragma unroll 4
+        for (int c = 0; c < H; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
+        S[M.Ai + i * kLdN + k] = acc;
+    }
+    // A_j^T[k][j]: peptide slots use h (H wide), pocket slots the 22 staged features (time / padding columns are 0)
+    for (int idx = tid; idx < kHid * Kpad; idx += kThreads) {
+        int k = idx / Kpad, j = idx - k * Kpad;
+        float acc = 0.0f;
+        if (j < kN) {
+            const float* w = msg0 + k * ld1 + H;
+            const float* h = S + M.H + j * kLdN;
+#pragma unroll 4
+            for (int c = 0; c < H; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
+        } else if (j < K) {
+            const float* w = msg0 + k * ld1 + H;
+            const float* h = feat_stage + (j - kN) * FS;
+#pragma unroll 2
+            for (int c = 0; c < PMHC_NFEAT; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
+        }
+        ajt[idx] = acc;
+    }
+    // T_t[i][n] = b[n] + W_t[n, 64:78] tors_i
+    for (int idx = tid; idx < kN * kHid; idx += kThreads) {
+        int i = idx >> 6, n = idx & 63;
+        const float* w = tor0 + n * 78 + 64;
+        const float* t = S + M.Tors + i * 14;
+        float acc = tor0b[n];
+#pragma unroll
+        for (int c = 0; c < 14; ++c) acc = fmaf(__ldg(w + c), t[c], acc);
+        S[M.Tt + idx] = acc;
+    }
+    for (int idx = tid; idx < kN * kHid; idx += kThreads) S[M.Msum + idx] = 0.0f;
+    __syncthreads();
+    ComplexInfo ci;
+    ci.L = I[IN_POCKET + Kpad + 0];
+    ci.nv = I[IN_POCKET + Kpad + 1];
+    ci.nx = I[IN_POCKET + Kpad + 2];
+    ci.c0 = I[IN_POCKET + Kpad + 3];
+    return ci;
+}
+
+// acc[u][n] += sum_k WT[k*ldw + n] * scr[k*kScrLd + col[u]]  for k in [0,64), n in [0,64).
+// Weight reads are warp-uniform 128-bit loads (one shared-memory wavefront feeds 4*PPT FMAs per lane).
+template <int PPT>
+__device__ __forceinline__ void gemv64(float (&acc)[PPT][kHid], const float* __restrict__ WT, int ldw,
+                                       const float* __restrict__ scr, const int (&col)[PPT]) {
+#pragma unroll 2
+    for (int k = 0; k < kHid; ++k) {
+        float av[PPT];
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) av[u] = scr[k * kScrLd + col[u]];
+        const float4* w4 = reinterpret_cast<const float4*>(WT + k * ldw);
+#pragma unroll
+        for (int n4 = 0; n4 < kHid / 4; ++n4) {
+            float4 w = w4[n4];
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) {
+                acc[u][4 * n4 + 0] = fmaf(w.x, av[u], acc[u][4 * n4 + 0]);
+                acc[u][4 * n4 + 1] = fmaf(w.y, av[u], acc[u][4 * n4 + 1]);
+                acc[u][4 * n4 + 2] = fmaf(w.z, av[u], acc[u][4 * n4 + 2]);
+                acc[u][4 * n4 + 3] = fmaf(w.w, av[u], acc[u][4 * n4 + 3]);
+            }
+        }
+    }
+}
+
+// Decoded pair of one thread slot.
+struct PairRef {
+    int i;       // peptide row (slot index)
+    int j;       // neighbour slot: < 16 peptide, >= 16 pocket (16 + pocket slot); -1 = shared zero-feature pocket message
+    bool active;
+};
+
+// Full (attention-carrying) pairs of row i: the L-1 other real peptide residues, then the nv valid pocket slots.
+__device__ __forceinline__ PairRef decode_full_pair(const int* I, int gp, int W, int L, int row0, bool active) {
+    PairRef p;
+    int rl = gp / W, e = gp - rl * W;
+    int r = row0 + rl;
+    p.i = I[IN_ROWS + r];
+    if (e < L - 1) p.j = I[IN_ROWS + (e < r ? e : e + 1)];
+    else p.j = I[IN_POCKET + (e - (L - 1))];
+    p.active = active;
+    return p;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace pmhc

@@ -1,0 +1,510 @@
+// egnn_forward.cu — fused EGNN layer forward (replaces EGNNLayer.forward, diffusion/model.py:83-333, and the
+// glue of Model.forward, model.py:377-421).
+//
+// One persistent CTA per SM loops over complexes.  Per complex: frames / features / per-node projections are
+// staged in shared memory once; every (peptide row i, neighbour j) pair is owned by one thread slot which
+// carries it through message MLP -> four head MLPs -> quaternion sandwich entirely in registers, reading the
+// layer's weights as warp-uniform 128-bit shared-memory loads; per-pair head outputs go to a shared buffer and
+// one warp per row does the masked softmax and the attention-weighted frame / torsion / translation updates.
+// Nothing of size [B, N, K, *] ever touches HBM (the reference materialises ~15 such tensors per layer).
+#include "egnn_common.cuh"
+
+namespace pmhc {
+
+// Compiler-only fence: keeps ptxas from hoisting all 64 units' shared loads of an unrolled head epilogue
+// ahead of the FMAs (which spilled the 2 x 64 accumulators); placed every 8 units.
+#define PMHC_SCHED_FENCE(n) do { if (((n) & 7) == 7) asm volatile("" ::: "memory"); } while (0)
+
+// message MLP for the thread's PPT pairs: scr[:, col] <- m = W2 relu(A_i + A_j + W_e) + b2  (model.py:183-226)
+template <int PPT>
+__device__ __forceinline__ void message_stage(float* S, const SmemMap& M, const float* __restrict__ ajt, int Kpad,
+                                              const PairRef (&pr)[PPT], const int (&col)[PPT]) {
+    float* scr = S + M.Scr;
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        const int i = pr[u].i, j = pr[u].j;
+        const float* ai = S + M.Ai + i * kLdN;
+        const bool pep = (j >= 0 && j < kN);
+        const float* we = S + M.We + (pep ? (kN - 1 + i - j) : 0) * kLdN;
+#pragma unroll 8
+        for (int k = 0; k < kHid; ++k) {
+            float v = ai[k];
+            if (j >= 0) v += __ldcg(ajt + k * Kpad + j);
+            if (pep) v += we[k];
+            scr[k * kScrLd + col[u]] = fmaxf(v, 0.0f);
+        }
+    }
+    float acc[PPT][kHid];
+#pragma unroll
+    for (int u = 0; u < PPT; ++u)
+#pragma unroll
+        for (int n = 0; n < kHid; ++n) acc[u][n] = S[M.PkMisc + 4 * n + 3];
+    gemv64<PPT>(acc, S + M.W2T, kHid, scr, col);
+#pragma unroll
+    for (int u = 0; u < PPT; ++u)
+#pragma unroll
+        for (int n = 0; n < kHid; ++n) scr[n * kScrLd + col[u]] = acc[u][n];
+}
+
+// the four heads of one pair; writes kOutPerPair floats  (model.py:228-333)
+template <int PPT>
+__device__ __forceinline__ void heads_stage(float* S, const SmemMap& M, const PairRef (&pr)[PPT], const int (&col)[PPT],
+                                            const int (&oslot)[PPT], float* __restrict__ logit_save, int Kpad) {
+    const float* scr = S + M.Scr;
+    float acc[PPT][kHid];
+    // ---- attention logit (model.py:238-242) ----
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        const float* qi = S + M.Q + pr[u].i * 4;
+        const float* qj = S + M.Q + pr[u].j * 4;
+        const float* xi = S + M.X + pr[u].i * 3;
+        const float* xj = S + M.X + pr[u].j * 3;
+        float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+        float d2 = dx * dx + dy * dy + dz * dz;
+        float dot = qi[0] * qj[0] + qi[1] * qj[1] + qi[2] * qj[2] + qi[3] * qj[3];
+        float qd = dot * dot;
+#pragma unroll
+        for (int n = 0; n < kHid; ++n) {
+            const float4 pk = *reinterpret_cast<const float4*>(S + M.PkAtt + 4 * n);
+            acc[u][n] = fmaf(pk.y, qd, fmaf(pk.x, -d2, pk.z));
+            PMHC_SCHED_FENCE(n);
+        }
+    }
+    gemv64<PPT>(acc, S + M.WhT, 256, scr, col);
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        float logit = S[M.Scal + SC_ATT2B];
+#pragma unroll
+        for (int n = 0; n < kHid; ++n) logit = fmaf(S[M.PkAtt + 4 * n + 3], fmaxf(acc[u][n], 0.0f), logit);
+        if (pr[u].active) {
+            S[M.Out + oslot[u] * kOutPerPair] = logit;
+            if (logit_save != nullptr) logit_save[pr[u].i * Kpad + pr[u].j] = logit;
+        }
+    }
+    // ---- rotation: local frame -> MLP -> sigmoid -> back to the global frame (model.py:283-296) ----
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        const float* a = S + M.Q + pr[u].i * 4;
+        const float* b = S + M.Q + pr[u].j * 4;
+        Quat qi{a[0], a[1], a[2], a[3]}, qj{b[0], b[1], b[2], b[3]};
+        Quat lq = qmul(qinv(qj), qmul(qi, qj));
+#pragma unroll
+        for (int n = 0; n < kHid; ++n) {
+            const float4 wq = *reinterpret_cast<const float4*>(S + M.PkRotQ + 4 * n);
+            float v = S[M.PkMisc + 4 * n + 2];
+            v = fmaf(wq.x, lq.w, v);
+            v = fmaf(wq.y, lq.x, v);
+            v = fmaf(wq.z, lq.y, v);
+            v = fmaf(wq.w, lq.z, v);
+            acc[u][n] = v;
+            PMHC_SCHED_FENCE(n);
+        }
+    }
+    gemv64<PPT>(acc, S + M.WhT + 64, 256, scr, col);
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        float pre[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pre[c] = S[M.Scal + SC_ROT2B + c];
+#pragma unroll
+        for (int n = 0; n < kHid; ++n) {
+            float h = fmaxf(acc[u][n], 0.0f);
+            const float4 w = *reinterpret_cast<const float4*>(S + M.PkRot2 + 4 * n);
+            pre[0] = fmaf(w.x, h, pre[0]);
+            pre[1] = fmaf(w.y, h, pre[1]);
+            pre[2] = fmaf(w.z, h, pre[2]);
+            pre[3] = fmaf(w.w, h, pre[3]);
+            PMHC_SCHED_FENCE(n);
+        }
+        const float* b = S + M.Q + pr[u].j * 4;
+        Quat qj{b[0], b[1], b[2], b[3]};
+        Quat dl{sigmoidf(pre[0]), sigmoidf(pre[1]), sigmoidf(pre[2]), sigmoidf(pre[3])};  // never normalised (T5)
+        Quat dg = qmul(qj, qmul(dl, qinv(qj)));
+        if (pr[u].active) {
+            float* o = S + M.Out + oslot[u] * kOutPerPair + 1;
+            o[0] = dg.w; o[1] = dg.x; o[2] = dg.y; o[3] = dg.z;
+        }
+    }
+    // ---- torsion angle increments (model.py:257-260) ----
+#pragma unroll
+    for (int u = 0; u < PPT; ++u)
+#pragma unroll
+        for (int n = 0; n < kHid; ++n) acc[u][n] = S[M.Tt + pr[u].i * kHid + n];
+    gemv64<PPT>(acc, S + M.WhT + 128, 256, scr, col);
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        float da[PMHC_NTORS];
+#pragma unroll
+        for (int c = 0; c < PMHC_NTORS; ++c) da[c] = S[M.Scal + SC_TOR2B + c];
+#pragma unroll
+        for (int n = 0; n < kHid; ++n) {
+            float h = fmaxf(acc[u][n], 0.0f);
+            const float4 w0 = *reinterpret_cast<const float4*>(S + M.PkTor2 + 8 * n);
+            const float4 w1 = *reinterpret_cast<const float4*>(S + M.PkTor2 + 8 * n + 4);
+            da[0] = fmaf(w0.x, h, da[0]);
+            da[1] = fmaf(w0.y, h, da[1]);
+            da[2] = fmaf(w0.z, h, da[2]);
+            da[3] = fmaf(w0.w, h, da[3]);
+            da[4] = fmaf(w1.x, h, da[4]);
+            da[5] = fmaf(w1.y, h, da[5]);
+            da[6] = fmaf(w1.z, h, da[6]);
+            PMHC_SCHED_FENCE(n);
+        }
+        if (pr[u].active) {
+            float* o = S + M.Out + oslot[u] * kOutPerPair + 5;
+#pragma unroll
+            for (int c = 0; c < PMHC_NTORS; ++c) o[c] = da[c];
+        }
+    }
+    // ---- translation scale (model.py:325-331) ----
+#pragma unroll
+    for (int u = 0; u < PPT; ++u)
+#pragma unroll
+        for (int n = 0; n < kHid; ++n) acc[u][n] = S[M.PkMisc + 4 * n + 0];
+    gemv64<PPT>(acc, S + M.WhT + 192, 256, scr, col);
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        float s = S[M.Scal + SC_TRN2B];
+#pragma unroll
+        for (int n = 0; n < kHid; ++n) s = fmaf(S[M.PkMisc + 4 * n + 1], fmaxf(acc[u][n], 0.0f), s);
+        if (pr[u].active) {
+            const float* xi = S + M.X + pr[u].i * 3;
+            const float* xj = S + M.X + pr[u].j * 3;
+            float* o = S + M.Out + oslot[u] * kOutPerPair + 12;
+            o[0] = s * (xi[0] - xj[0]);
+            o[1] = s * (xi[1] - xj[1]);
+            o[2] = s * (xi[2] - xj[2]);
+        }
+    }
+}
+
+// Adds this pass's messages into the per-row unmasked sums (model.py:151, trap T3).  `mult_last` is the
+// multiplicity of the last pair of every row (the shared zero-feature pocket message), 1 otherwise.
+__device__ __forceinline__ void accumulate_msum(float* S, const SmemMap& M, const int* I, int row0, int nrows, int W,
+                                                int pass_base, int npass, int mult_last_e, float mult_last) {
+    const float* scr = S + M.Scr;
+    for (int idx = threadIdx.x; idx < nrows * kHid; idx += kThreads) {
+        int rl = idx >> 6, n = idx & 63;
+        int lo = max(rl * W, pass_base), hi = min((rl + 1) * W, pass_base + npass);
+        float sum = 0.0f;
+        for (int gp = lo; gp < hi; ++gp) {
+            float v = scr[n * kScrLd + (gp - pass_base)];
+            if (gp - rl * W == mult_last_e) v *= mult_last;
+            sum += v;
+        }
+        if (hi > lo) S[M.Msum + I[IN_ROWS + row0 + rl] * kHid + n] += sum;
+    }
+}
+
+template <int LAYER>
+__global__ void __launch_bounds__(kThreads, 1) egnn_layer_forward_kernel(LayerArgs a) {
+    extern __shared__ __align__(16) float S[];
+    const SmemMap M = make_smem_map(a.Kpad);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* I = reinterpret_cast<int*>(S + M.Ints);
+    float* ajt = a.ajt_ws + (size_t)blockIdx.x * kHid * a.Kpad;
+
+    stage_layer_weights<LAYER>(S, M, a.params);
+    __syncthreads();
+
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const ComplexInfo ci = setup_complex<LAYER>(S, M, a, b, ajt);
+        const int L = ci.L;
+        const int W = (L - 1) + ci.nv;  // attention-carrying neighbours of every real row
+        float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
+
+        // padded rows: pass the inputs through (finite don't-care values)
+        for (int idx = tid; idx < (kN - L) * 21; idx += kThreads) {
+            int s = idx / 21, c = idx - s * 21;
+            int i = I[IN_PEPX + s];
+            if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = a.frames_in[((size_t)b * kN + i) * 7 + c];
+            else a.tors_out[((size_t)b * kN + i) * 14 + (c - 7)] = a.tors_in[((size_t)b * kN + i) * 14 + (c - 7)];
+        }
+
+        // ---------------- attention-carrying pairs, in groups of whole rows ----------------
+        const int rows_per_group = W > 0 ? max(1, kCapPairs / W) : kN;
+        for (int row0 = 0; row0 < L; row0 += rows_per_group) {  // (L == 0: nothing to do)
+            const int nrows = min(rows_per_group, L - row0);
+            const int gpairs = nrows * W;
+            for (int pass_base = 0; pass_base < gpairs;) {
+                const int remaining = gpairs - pass_base;
+                int npass;
+                if (remaining > kThreads) {
+                    npass = min(remaining, kPassPairs);
+                    PairRef pr[2];
+                    int col[2], oslot[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        col[u] = u * kThreads + tid;
+                        bool act = col[u] < npass;
+                        int gp = act ? pass_base + col[u] : pass_base;
+                        pr[u] = decode_full_pair(I, gp, W, L, row0, act);
+                        oslot[u] = gp;
+                    }
+                    message_stage<2>(S, M, ajt, a.Kpad, pr, col);
+                    heads_stage<2>(S, M, pr, col, oslot, lsave, a.Kpad);
+                } else {
+                    npass = remaining;
+                    PairRef pr[1];
+                    int col[1] = {tid}, oslot[1];
+                    bool act = tid < npass;
+                    int gp = act ? pass_base + tid : pass_base;
+                    pr[0] = decode_full_pair(I, gp, W, L, row0, act);
+                    oslot[0] = gp;
+                    message_stage<1>(S, M, ajt, a.Kpad, pr, col);
+                    heads_stage<1>(S, M, pr, col, oslot, lsave, a.Kpad);
+                }
+                if (LAYER == 0) {
+                    __syncthreads();
+                    accumulate_msum(S, M, I, row0, nrows, W, pass_base, npass, -1, 1.0f);
+                    __syncthreads();
+                }
+                pass_base += npass;
+            }
+            __syncthreads();
+
+            // ---------------- per-row softmax + weighted updates (one warp per row) ----------------
+            for (int rl = warp; rl < nrows; rl += kThreads / 32) {
+                const int i = I[IN_ROWS + row0 + rl];
+                const float* out = S + M.Out + (size_t)rl * W * kOutPerPair;
+                float mx = -INFINITY;
+                for (int e = lane; e < W; e += 32) mx = fmaxf(mx, out[e * kOutPerPair]);
+                mx = warp_max(mx);
+                float se = 0.0f, ws[14];
+#pragma unroll
+                for (int c = 0; c < 14; ++c) ws[c] = 0.0f;
+                for (int e = lane; e < W; e += 32) {
+                    const float* o = out + e * kOutPerPair;
+                    float p = expf(o[0] - mx);
+                    se += p;
+#pragma unroll
+                    for (int c = 0; c < 14; ++c) ws[c] = fmaf(p, o[1 + c], ws[c]);
+                }
+                se = warp_sum(se);
+#pragma unroll
+                for (int c = 0; c < 14; ++c) ws[c] = warp_sum(ws[c]);
+                const float inv = W > 0 ? 1.0f / se : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 14; ++c) ws[c] *= inv;
+                const size_t node = (size_t)b * kN + i;
+                if (lane == 0) {
+                    const float* qi = S + M.Q + i * 4;
+                    const float* xi = S + M.X + i * 3;
+                    Quat G{ws[0], ws[1], ws[2], ws[3]};
+                    Quat g = W > 0 ? qnormalize(G) : Quat{1.0f, 0.0f, 0.0f, 0.0f};  // model.py:301-306
+                    Quat q = qunit(qmul(g, Quat{qi[0], qi[1], qi[2], qi[3]}));       // model.py:310, :181
+                    float* fo = a.frames_out + node * 7;
+                    fo[0] = q.w; fo[1] = q.x; fo[2] = q.y; fo[3] = q.z;
+                    fo[4] = xi[0] + ws[11]; fo[5] = xi[1] + ws[12]; fo[6] = xi[2] + ws[13];
+                    if (a.rowstat != nullptr) {
+                        float* rs = a.rowstat + node * PMHC_ROWSTAT;
+                        rs[0] = W > 0 ? mx + logf(se) : 0.0f;
+#pragma unroll
+                        for (int c = 0; c < 14; ++c) rs[1 + c] = ws[c];
+                        rs[15] = 0.0f;
+                    }
+                }
+                if (lane < PMHC_NTORS) {
+                    // torsions' = (sin dA, cos dA) (x) torsions (model.py:263-269)
+                    float da = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < PMHC_NTORS; ++c) da = (lane == c) ? ws[4 + c] : da;
+                    float sn, cs;
+                    sincosf(da, &sn, &cs);
+                    const float* t = S + M.Tors + i * 14 + 2 * lane;
+                    SinCos o = scmul(SinCos{sn, cs}, SinCos{t[0], t[1]});
+                    a.tors_out[node * 14 + 2 * lane] = o.s;
+                    a.tors_out[node * 14 + 2 * lane + 1] = o.c;
+                }
+            }
+            __syncthreads();
+        }
+
+        if (LAYER == 0) {
+            // ---------------- message-only pairs: self, masked peptide slots, masked pocket slots ----------------
+            const int npx = kN - L;                          // masked peptide slots
+            const int W2 = 1 + npx + ci.nx + (ci.c0 > 0 ? 1 : 0);
+            const int total = L * W2;
+            for (int pass_base = 0; pass_base < total; pass_base += kThreads) {
+                const int npass = min(kThreads, total - pass_base);
+                PairRef pr[1];
+                int col[1] = {tid};
+                bool act = tid < npass;
+                int gp = act ? pass_base + tid : pass_base;
+                int rl = gp / W2, e = gp - rl * W2;
+                pr[0].i = I[IN_ROWS + rl];
+                pr[0].active = act;
+                if (e == 0) pr[0].j = pr[0].i;
+                else if (e <= npx) pr[0].j = I[IN_PEPX + e - 1];
+                else if (e <= npx + ci.nx) pr[0].j = I[IN_POCKET + a.Kpad - 1 - (e - npx - 1)];
+                else pr[0].j = -1;
+                message_stage<1>(S, M, ajt, a.Kpad, pr, col);
+                __syncthreads();
+                accumulate_msum(S, M, I, 0, L, W2, pass_base, npass, ci.c0 > 0 ? W2 - 1 : -1, (float)ci.c0);
+                __syncthreads();
+            }
+
+            // ---------------- node feature update: relu(feature_mlp(cat(h_i, sum_j m_ij))) (model.py:151, :407) ----------------
+            const float* f0w = a.params + param_offset(0, FEAT0_W);
+            const float* f0b = a.params + param_offset(0, FEAT0_B);
+            const float* f2w = a.params + param_offset(0, FEAT2_W);
+            const float* f2b = a.params + param_offset(0, FEAT2_B);
+            constexpr int ldf = kH1 + kHid;
+            float* hid = S + M.Scr;  // [16][65]
+            for (int idx = tid; idx < L * kHid; idx += kThreads) {
+                int r = idx >> 6, n = idx & 63;
+                int i = I[IN_ROWS + r];
+                const float* w = f0w + n * ldf;
+                const float* h = S + M.H + i * kLdN;
+                const float* ms = S + M.Msum + i * kHid;
+                float acc = f0b[n];
+                for (int c = 0; c < kH1; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
+                for (int c = 0; c < kHid; ++c) acc = fmaf(__ldg(w + kH1 + c), ms[c], acc);
+                hid[r * kLdN + n] = fmaxf(acc, 0.0f);
+                if (a.msum_out != nullptr) a.msum_out[((size_t)b * kN + i) * kHid + n] = ms[n];
+            }
+            __syncthreads();
+            for (int idx = tid; idx < kN * kHid; idx += kThreads) {
+                int s = idx >> 6, n = idx & 63;
+                float v = 0.0f;
+                int i;
+                if (s < L) {
+                    i = I[IN_ROWS + s];
+                    const float* w = f2w + n * kHid;
+                    float acc = f2b[n];
+                    for (int c = 0; c < kHid; ++c) acc = fmaf(__ldg(w + c), hid[s * kLdN + c], acc);
+                    v = fmaxf(acc, 0.0f);
+                } else {
+                    i = I[IN_PEPX + s - L];
+                    if (a.msum_out != nullptr) a.msum_out[((size_t)b * kN + i) * kHid + n] = 0.0f;
+                }
+                a.feat_out[((size_t)b * kN + i) * kHid + n] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pmhc
+
+using namespace pmhc;
+
+namespace pmhc {
+
+static int g_num_sms = 0;
+static int g_max_smem = 0;
+
+int device_props() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    return g_num_sms > 0 ? 0 : -1;
+}
+int num_sms() { return g_num_sms; }
+int pad_k(int P) { return ((kN + P + 31) / 32) * 32; }
+
+// workspace layout: [ajt scratch: num_sms * 64 * Kpad] [frames1: B*16*7] [tors1: B*16*14] [feat1: B*16*64]
+struct Workspace {
+    float *ajt, *frames1, *tors1, *feat1;
+    size_t bytes;
+};
+Workspace carve_workspace(void* base, int B, int P) {
+    Workspace w;
+    size_t o = 0;
+    float* p = (float*)base;
+    size_t n_ajt = (size_t)(g_num_sms > 0 ? g_num_sms : 148) * kHid * pad_k(P);
+    w.ajt = p + o;     o += n_ajt;
+    w.frames1 = p + o; o += (size_t)B * kN * 7;
+    w.tors1 = p + o;   o += (size_t)B * kN * 14;
+    w.feat1 = p + o;   o += (size_t)B * kN * kHid;
+    w.bytes = o * sizeof(float);
+    return w;
+}
+
+template <int LAYER>
+int launch_layer_forward(const LayerArgs& a, cudaStream_t stream) {
+    static bool configured = false;
+    const SmemMap M = make_smem_map(a.Kpad);
+    size_t smem = (size_t)M.total_floats * sizeof(float);
+    PMHC_REQUIRE((int)smem <= g_max_smem, "EGNN layer needs %zu B of shared memory (P=%d), device allows %d", smem, a.P, g_max_smem);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(egnn_layer_forward_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
+        PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(forward): %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    int grid = a.B < g_num_sms ? a.B : g_num_sms;
+    if (profile_enabled()) profile_mark(PROF_FWD, stream, true);
+    egnn_layer_forward_kernel<LAYER><<<grid, kThreads, smem, stream>>>(a);
+    if (profile_enabled()) profile_mark(PROF_FWD, stream, false);
+    PMHC_CHECK_LAUNCH("egnn_layer_forward");
+    return 0;
+}
+
+}  // namespace pmhc
+
+namespace pmhc {
+size_t forward_workspace_bytes(int B, int P) {
+    device_props();
+    return carve_workspace(nullptr, B, P).bytes;
+}
+}  // namespace pmhc
+
+// saved-for-backward layout (floats): rowstat1 [B,16,16] | rowstat2 [B,16,16] | frames1 [B,16,7] | tors1 [B,16,14]
+// | feat1 [B,16,64] | msum1 [B,16,64] | logits1 [B,16,Kpad] | logits2 [B,16,Kpad]
+extern "C" size_t pmhc_saved_floats(int B, int P) {
+    return (size_t)B * kN * (2 * PMHC_ROWSTAT + 7 + 14 + kHid + kHid + 2 * pad_k(P));
+}
+
+namespace pmhc {
+SavedMap carve_saved(float* saved, int B, int P) {
+    SavedMap s;
+    const size_t BN = (size_t)B * kN;
+    s.rowstat1 = saved;
+    s.rowstat2 = s.rowstat1 + BN * PMHC_ROWSTAT;
+    s.frames1 = s.rowstat2 + BN * PMHC_ROWSTAT;
+    s.tors1 = s.frames1 + BN * 7;
+    s.feat1 = s.tors1 + BN * 14;
+    s.msum1 = s.feat1 + BN * kHid;
+    s.logits1 = s.msum1 + BN * kHid;
+    s.logits2 = s.logits1 + BN * pad_k(P);
+    return s;
+}
+}  // namespace pmhc
+
+extern "C" int pmhc_model_forward(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames,
+                                  float* out_torsions, float* saved, void* workspace, size_t workspace_bytes,
+                                  void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PMHC_REQUIRE(device_props() == 0, "no CUDA device");
+    PMHC_REQUIRE(bt != nullptr && bt->B > 0, "pmhc_model_forward: empty batch");
+    PMHC_REQUIRE(bt->P >= 1 && bt->P <= kMaxP, "pmhc_model_forward: pocket_maxlen %d outside [1, %d]", bt->P, kMaxP);
+    Workspace w = carve_workspace(workspace, bt->B, bt->P);
+    PMHC_REQUIRE(workspace != nullptr && workspace_bytes >= w.bytes, "pmhc_model_forward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    SavedMap sv{};
+    if (saved != nullptr) sv = carve_saved(saved, bt->B, bt->P);
+    float* rowstat1 = sv.rowstat1;
+    float* rowstat2 = sv.rowstat2;
+    float* frames1 = saved ? sv.frames1 : w.frames1;
+    float* tors1 = saved ? sv.tors1 : w.tors1;
+    float* feat1 = saved ? sv.feat1 : w.feat1;
+    float* msum1 = sv.msum1;
+
+    LayerArgs a;
+    a.params = params;
+    a.B = bt->B; a.P = bt->P; a.Kpad = pad_k(bt->P);
+    a.t_over_T = t_over_T;
+    a.frames_in = bt->frames; a.tors_in = bt->torsions; a.feat_in = bt->features; a.mask = bt->mask;
+    a.pocket_frames = bt->pocket_frames; a.pocket_feat = bt->pocket_features; a.pocket_mask = bt->pocket_mask;
+    a.frames_out = frames1; a.tors_out = tors1; a.feat_out = feat1; a.msum_out = msum1; a.rowstat = rowstat1;
+    a.logit_out = sv.logits1;
+    a.ajt_ws = w.ajt;
+    int rc = launch_layer_forward<0>(a, stream);
+    if (rc != 0) return rc;
+    a.frames_in = frames1; a.tors_in = tors1; a.feat_in = feat1;
+    a.frames_out = out_frames; a.tors_out = out_torsions; a.feat_out = nullptr; a.msum_out = nullptr; a.rowstat = rowstat2;
+    a.logit_out = sv.logits2;
+    return launch_layer_forward<1>(a, stream);
+}

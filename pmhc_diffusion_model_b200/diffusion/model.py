@@ -1,0 +1,194 @@
+"""Denoiser `Model` — drop-in for diffusion/model.py:336-421 of the reference, computed by the fused
+sm_100a EGNN kernels (csrc/egnn_forward.cu, csrc/egnn_backward.cu) through the C ABI.
+
+The module keeps the reference's constructor, attributes (`max_len`, `T`, `gnn1`, `gnn2`) and its 48
+state-dict keys/shapes (`model.pth` loads with strict=True), but `forward` launches two fused layer
+kernels instead of ~350 broadcast ATen ops.  Parameters live in ONE flat fp32 buffer (each
+`nn.Parameter` is a view into it) so the kernels read weights, and write weight gradients, through a
+single pointer — the same buffer a data-parallel all-reduce sends.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Union
+
+import torch
+
+from .. import _lib
+from ..rigid import Rigid, Rotation
+
+_TRANSITION = 64  # model.py:36
+_N_TORSIONS = 7   # model.py:32
+
+
+def _mlp(n_in: int, n_out: int, sigmoid: bool = False, flatten: bool = False) -> torch.nn.Sequential:
+    """Linear -> ReLU -> Linear with the reference's submodule indices (0, 2) so state-dict keys agree."""
+    mods = [torch.nn.Linear(n_in, _TRANSITION), torch.nn.ReLU(), torch.nn.Linear(_TRANSITION, n_out)]
+    if sigmoid:
+        mods.append(torch.nn.Sigmoid())      # rotation_mlp.3, parameter-free (model.py:73)
+    if flatten:
+        mods.append(torch.nn.Flatten(-2, -1))  # attention_mlp.3, parameter-free (model.py:58)
+    return torch.nn.Sequential(*mods)
+
+
+class EGNNLayer(torch.nn.Module):
+    """Parameter container of one message-passing layer (model.py:14-81).
+
+    The arithmetic of the reference's `EGNNLayer.forward` (model.py:83-333) lives in the fused CUDA layer
+    kernel; this class only owns the weights, in the reference's registration order.
+    """
+
+    def __init__(self, node_input_size: int, edge_input_size: int, node_output_size: int, message_size: int):
+        super().__init__()
+        t2 = 2 * _N_TORSIONS
+        self.feature_mlp = _mlp(node_input_size + message_size, node_output_size)
+        self.message_mlp = _mlp(2 * node_input_size + edge_input_size, message_size)
+        self.attention_mlp = _mlp(message_size + 2, 1, flatten=True)
+        self.translation_mlp = _mlp(message_size, 1)
+        self.rotation_mlp = _mlp(message_size + 4, 4, sigmoid=True)
+        self.torsion_mlp = _mlp(message_size + t2, _N_TORSIONS)
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError("EGNNLayer has no standalone forward here: both layers run inside Model.forward's fused kernels")
+
+
+def _as_tensor7(frames: Union[Rigid, torch.Tensor]) -> torch.Tensor:
+    if isinstance(frames, torch.Tensor):
+        return frames
+    return frames.to_tensor_7()
+
+
+class _DenoiserFn(torch.autograd.Function):
+    """Autograd bridge: forward = pmhc_model_forward, backward = pmhc_model_backward (weight gradients only;
+    the reference never differentiates w.r.t. the noised inputs, optimizer.py:205-222)."""
+
+    @staticmethod
+    def forward(ctx, model, t_over_T, frames7, torsions, features, mask, pocket7, pocket_features, pocket_mask, *params):
+        lib = _lib.load()
+        desc, keep = _lib.make_batch(frames7, torsions, features, mask, pocket7, pocket_features, pocket_mask)
+        dev = keep[0].device
+        flat = model._flat_params()
+        B, P = desc.B, desc.P
+        out_frames = torch.empty(B, _lib.N, 7, device=dev, dtype=torch.float32)
+        out_tors = torch.empty(B, _lib.N, _lib.NTORS, 2, device=dev, dtype=torch.float32)
+        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        saved = torch.empty(lib.pmhc_saved_floats(B, P), device=dev, dtype=torch.float32) if need_grad else None
+        ws_bytes = lib.pmhc_workspace_bytes(B, P)
+        ws = _lib.workspace(dev, ws_bytes)
+        with torch.cuda.device(dev):
+            _lib.check(lib.pmhc_model_forward(flat.data_ptr(), ctypes.byref(desc), t_over_T, out_frames.data_ptr(),
+                                              out_tors.data_ptr(), _lib.ptr(saved), ws.data_ptr(), ws_bytes,
+                                              _lib.stream_ptr(dev)), "pmhc_model_forward")
+        ctx.model, ctx.t_over_T, ctx.keep, ctx.saved_buf = model, t_over_T, keep, saved
+        ctx.flat_version = model._flat_generation
+        ctx.mark_non_differentiable()
+        return out_frames, out_tors
+
+    @staticmethod
+    def backward(ctx, d_frames, d_tors):
+        lib = _lib.load()
+        model = ctx.model
+        if ctx.saved_buf is None:
+            raise RuntimeError("backward through a forward that ran without gradient tracking")
+        keep = ctx.keep
+        dev = keep[0].device
+        desc = _lib.PmhcBatch(keep[0].shape[0], keep[4].shape[1], *[t.data_ptr() for t in keep])
+        flat = model._flat_params()
+        grad = torch.zeros_like(flat)
+        B = desc.B
+        d_frames = _lib.f32c(d_frames) if d_frames is not None else torch.zeros(B, _lib.N, 7, device=dev)
+        d_tors = _lib.f32c(d_tors) if d_tors is not None else torch.zeros(B, _lib.N, _lib.NTORS, 2, device=dev)
+        ws_bytes = lib.pmhc_workspace_bytes(B, desc.P)
+        ws = _lib.workspace(dev, ws_bytes)
+        with torch.cuda.device(dev):
+            _lib.check(lib.pmhc_model_backward(flat.data_ptr(), ctypes.byref(desc), ctx.t_over_T, ctx.saved_buf.data_ptr(),
+                                               d_frames.data_ptr(), d_tors.data_ptr(), grad.data_ptr(), ws.data_ptr(),
+                                               ws_bytes, _lib.stream_ptr(dev)), "pmhc_model_backward")
+        grads = model._split_flat(grad)
+        return (None,) * 9 + tuple(grads)
+
+
+class Model(torch.nn.Module):
+    def __init__(self, max_len: int, node_input_size: int, T: int):
+        """
+        Args (as model.py:337-343):
+            max_len: max expected input length of peptide sequence
+            node_input_size: expected dimension for node features
+            T: expected max number of time steps
+        """
+        super().__init__()
+        if max_len != _lib.N or node_input_size != _lib.NFEAT:
+            raise NotImplementedError(
+                f"the fused kernels are specialised for Model({_lib.N}, {_lib.NFEAT}, T) — the only configuration the "
+                f"reference's entry points construct (optimize.py:54, test.py:46); got Model({max_len}, {node_input_size}, T)")
+        self.max_len = max_len
+        self.relposenc_depth = max_len * 2 - 1
+        H = node_input_size + 1           # features + time (model.py:362)
+        E = self.relposenc_depth          # one-hot relative position (model.py:365)
+        I = 64
+        M = 64
+        self.gnn1 = EGNNLayer(H, E, I, M)
+        self.gnn2 = EGNNLayer(I, E, 1, M)
+        self.act = torch.nn.ReLU()
+        self.T = T
+        self._flat = None
+        self._flat_generation = 0
+        self._flatten()
+
+    # ---- flat parameter buffer -------------------------------------------------------------------------
+    def _flatten(self) -> None:
+        """(Re)build the flat fp32 buffer and make every parameter a view into it (state_dict order)."""
+        params = list(self.parameters())
+        if sum(p.numel() for p in params) != _lib.NPARAM:
+            raise RuntimeError("unexpected parameter count")
+        dev = params[0].device
+        flat = torch.empty(_lib.NPARAM, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.detach().reshape(-1).to(torch.float32))
+                p.data = flat[off:off + n].view(p.shape)
+                off += n
+        self._flat = flat
+        self._flat_generation += 1
+
+    def _flat_params(self) -> torch.Tensor:
+        """The flat buffer, re-built if some parameter no longer aliases it (e.g. after .to() / .cuda())."""
+        off = 0
+        base = self._flat.data_ptr()
+        for p in self.parameters():
+            if p.data_ptr() != base + 4 * off or p.dtype != torch.float32 or p.device != self._flat.device:
+                self._flatten()
+                break
+            off += p.numel()
+        return self._flat
+
+    def _split_flat(self, flat_grad: torch.Tensor):
+        """Views of a flat gradient per parameter; None for gnn2.feature_mlp (never used, model.py:415, T6)."""
+        out, off = [], 0
+        for name, p in self.named_parameters():
+            n = p.numel()
+            out.append(None if name.startswith("gnn2.feature_mlp") else flat_grad[off:off + n].view(p.shape))
+            off += n
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._flatten()
+        return out
+
+    # ---- forward -----------------------------------------------------------------------------------------
+    def forward(self, batch: Dict[str, Union[torch.Tensor, Rigid]], t: int) -> Dict[str, Union[Rigid, torch.Tensor]]:
+        """Same contract as model.py:377-421: reads frames/torsions/features/mask/pocket_* from `batch`
+        (frames as `Rigid` or tensor_7), returns {"frames": Rigid (unit quaternions), "torsions": [B,16,7,2]}."""
+        frames7 = _as_tensor7(batch["frames"])
+        pocket7 = _as_tensor7(batch["pocket_frames"])
+        params = tuple(self.parameters())
+        out_frames, out_tors = _DenoiserFn.apply(
+            self, float(t) / float(self.T), frames7, batch["torsions"], batch["features"], batch["mask"],
+            pocket7, batch["pocket_features"], batch["pocket_mask"], *params)
+        return {
+            "frames": Rigid(Rotation(quats=out_frames[..., :4], normalize_quats=False), out_frames[..., 4:]),
+            "torsions": out_tors,
+        }

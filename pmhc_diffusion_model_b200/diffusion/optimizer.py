@@ -1,0 +1,286 @@
+"""`DiffusionModelOptimizer` — drop-in for diffusion/optimizer.py:27-252 of the reference.
+
+Same constructor, attributes and method names; every method runs fused sm_100a kernels through the C ABI
+(csrc/diffusion_ops.cu, csrc/egnn_*.cu).  Rotations never leave quaternion form: where the reference goes
+through rotation matrices and `torch.linalg.eigh` (compose_r + rot_to_quat) the kernels
+compose Hamilton products, which is the same rotation up to the eigenvector's arbitrary sign.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+import random
+from math import sqrt
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+
+from .. import _lib
+from ..rigid import Rigid, Rotation
+from .tools.metrics import MetricsRecord
+
+_log = logging.getLogger(__name__)
+
+LOSS_KEYS = ("total loss", "positions loss", "rotations loss", "torsions loss", "rmsd")  # optimizer.py:73-79
+
+
+def linear_schedule(t: int, T: int, beta_min: float, beta_max: float) -> float:
+    """optimizer.py:20-21."""
+    return beta_min + (beta_max - beta_min) * (float(t) / T)
+
+
+def _frames7(x: Union[Rigid, torch.Tensor]) -> torch.Tensor:
+    return x if isinstance(x, torch.Tensor) else x.to_tensor_7()
+
+
+def _rigid(t7: torch.Tensor) -> Rigid:
+    return Rigid(Rotation(quats=t7[..., :4], normalize_quats=False), t7[..., 4:])
+
+
+def _next_noise_key() -> int:
+    """64-bit Philox key for one noise draw, taken from torch's default CPU generator: `torch.manual_seed` makes
+    runs repeatable exactly as it does for the reference's torch.randn / torch.rand draws (no GPU sync involved)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+class _LossFn(torch.autograd.Function):
+    """get_loss with a fused gradient: one kernel computes the five per-complex losses [5, B] and d total / d pred."""
+
+    @staticmethod
+    def forward(ctx, true_f, true_t, pred_f, pred_t, mask_u8, tmask_u8):
+        lib = _lib.load()
+        dev = pred_f.device
+        B = pred_f.shape[0]
+        losses = torch.empty(5, B, device=dev, dtype=torch.float32)
+        need = pred_f.requires_grad or pred_t.requires_grad
+        d_f = torch.empty_like(pred_f) if need else None
+        d_t = torch.empty_like(pred_t) if need else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.pmhc_loss(true_f.data_ptr(), true_t.data_ptr(), pred_f.data_ptr(), pred_t.data_ptr(),
+                                     mask_u8.data_ptr(), tmask_u8.data_ptr(), B, 1.0, losses.data_ptr(),
+                                     _lib.ptr(d_f), _lib.ptr(d_t), _lib.stream_ptr(dev)), "pmhc_loss")
+        ctx.need = need
+        if need:
+            ctx.save_for_backward(d_f, d_t)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.need:
+            return (None,) * 6
+        d_f, d_t = ctx.saved_tensors
+        g0 = g[0].to(torch.float32)  # only 'total loss' is differentiable; the other rows are diagnostics
+        return None, None, d_f * g0[:, None, None], d_t * g0[:, None, None, None], None, None
+
+
+class DiffusionModelOptimizer:
+
+    def __init__(self, noise_step_count: int, model: torch.nn.Module, lr: float):
+        self.noise_step_count = noise_step_count
+        self.model = model
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr)  # optimizer.py:33
+        self.beta_min = 0.0
+        self.beta_max = 0.8
+        # parity hooks (tests only): reference z_t quaternions to align the q / -q sign with
+        self.quat_sign_ref: Optional[torch.Tensor] = None
+        # sharded sampling: a fixed (seed, index of this shard's first complex) makes the Philox noise of every
+        # complex independent of how the complexes are split over GPUs
+        self.sample_seed: Optional[int] = None
+        self.sample_first_complex: int = 0
+
+    # ---- loss ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def get_loss(
+        noise_true: Dict[str, Union[Rigid, torch.Tensor]],
+        noise_pred: Dict[str, Union[Rigid, torch.Tensor]],
+        residues_mask: torch.Tensor,
+        torsions_mask: torch.Tensor,
+    ) -> Dict[str, torch.Tensor]:
+        """optimizer.py:38-79: 0.1 * masked translation MSE + masked (1 - q.q') + masked (1 - t.t')."""
+        true_f = _lib.f32c(_frames7(noise_true["frames"]))
+        pred_f = _lib.f32c(_frames7(noise_pred["frames"]))
+        true_t = _lib.f32c(noise_true["torsions"])
+        pred_t = _lib.f32c(noise_pred["torsions"])
+        _lib.require_cuda(true_f, pred_f, true_t, pred_t, residues_mask, torsions_mask)
+        losses = _LossFn.apply(true_f.detach(), true_t.detach(), pred_f, pred_t, _lib.u8c(residues_mask), _lib.u8c(torsions_mask))
+        out = {LOSS_KEYS[0]: losses[0]}
+        out.update({k: losses[i].detach() for i, k in enumerate(LOSS_KEYS) if i > 0})
+        return out
+
+    # ---- schedule -----------------------------------------------------------------------------------------
+    def get_beta_alpha_sigma(self, noise_step: int) -> Tuple[float, float, float]:
+        """optimizer.py:81-91."""
+        beta = linear_schedule(noise_step, self.noise_step_count, self.beta_min, self.beta_max)
+        return (beta, sqrt(1.0 - beta), sqrt(beta))
+
+    # ---- noise --------------------------------------------------------------------------------------------
+    @staticmethod
+    def gen_noise(shape: Union[List[int], Tuple[int]], device: torch.device) -> Dict[str, Union[Rigid, torch.Tensor]]:
+        """optimizer.py:93-108: translation 5*N(0,I), uniform rotation (Shoemake), 7 uniform torsion angles.
+        Philox counter stream instead of torch's generator (statistically identical, not bitwise)."""
+        lib = _lib.load()
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("gen_noise runs on the GPU only (no CPU fallback)")
+        shape = list(shape)
+        n = 1
+        for s in shape:
+            n *= int(s)
+        frames = torch.empty(shape + [7], device=device, dtype=torch.float32)
+        tors = torch.empty(shape + [_lib.NTORS, 2], device=device, dtype=torch.float32)
+        with torch.cuda.device(device):
+            _lib.check(lib.pmhc_gen_noise(_next_noise_key(), 0, n, frames.data_ptr(), tors.data_ptr(), _lib.stream_ptr(device)), "pmhc_gen_noise")
+        return {"frames": _rigid(frames), "torsions": tors}
+
+    @staticmethod
+    def noise_from_randoms(normal: torch.Tensor, uniform: torch.Tensor) -> Dict[str, Union[Rigid, torch.Tensor]]:
+        """Same formulas as gen_noise from caller-supplied randoms: normal [*,3] ~ N(0,1), uniform [*,10] ~ U(0,1)."""
+        lib = _lib.load()
+        normal, uniform = _lib.f32c(normal), _lib.f32c(uniform)
+        dev = _lib.require_cuda(normal, uniform)
+        shape = list(normal.shape[:-1])
+        n = normal.numel() // 3
+        frames = torch.empty(shape + [7], device=dev, dtype=torch.float32)
+        tors = torch.empty(shape + [_lib.NTORS, 2], device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.pmhc_noise_from_randoms(normal.data_ptr(), uniform.data_ptr(), n, frames.data_ptr(), tors.data_ptr(),
+                                                   _lib.stream_ptr(dev)), "pmhc_noise_from_randoms")
+        return {"frames": _rigid(frames), "torsions": tors}
+
+    def add_noise(self, signal: Dict, noise: Dict, t: int) -> Dict:
+        """optimizer.py:110-138.  All other keys of `signal` pass through untouched (:135)."""
+        lib = _lib.load()
+        beta, _, _ = self.get_beta_alpha_sigma(t)
+        f0, t0 = _lib.f32c(_frames7(signal["frames"])), _lib.f32c(signal["torsions"])
+        fe, te = _lib.f32c(_frames7(noise["frames"])), _lib.f32c(noise["torsions"])
+        dev = _lib.require_cuda(f0, t0, fe, te)
+        out_f, out_t = torch.empty_like(f0), torch.empty_like(t0)
+        ref = _lib.f32c(self.quat_sign_ref) if self.quat_sign_ref is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.pmhc_add_noise(f0.data_ptr(), t0.data_ptr(), fe.data_ptr(), te.data_ptr(), beta, f0.numel() // 7,
+                                          _lib.ptr(ref), out_f.data_ptr(), out_t.data_ptr(), _lib.stream_ptr(dev)), "pmhc_add_noise")
+        result = {k: signal[k] for k in signal}
+        result["frames"] = _rigid(out_f)
+        result["torsions"] = out_t
+        return result
+
+    def remove_noise(self, noised_signal: Dict, predicted_noise: Dict, t: int, s: int,
+                     random_noise: Optional[Dict] = None) -> Dict:
+        """optimizer.py:140-193; draws the step's fresh noise itself (:151) unless `random_noise` is given."""
+        lib = _lib.load()
+        beta_t, _, _ = self.get_beta_alpha_sigma(t)
+        beta_s, _, _ = self.get_beta_alpha_sigma(s)
+        zf, zt = _lib.f32c(_frames7(noised_signal["frames"])), _lib.f32c(noised_signal["torsions"])
+        pf, pt = _lib.f32c(_frames7(predicted_noise["frames"])), _lib.f32c(predicted_noise["torsions"])
+        dev = _lib.require_cuda(zf, zt, pf, pt)
+        if random_noise is None:
+            random_noise = DiffusionModelOptimizer.gen_noise(zf.shape[:-1], dev)
+        xf, xt = _lib.f32c(_frames7(random_noise["frames"])), _lib.f32c(random_noise["torsions"])
+        out_f, out_t = torch.empty_like(zf), torch.empty_like(zt)
+        ref = _lib.f32c(self.quat_sign_ref) if self.quat_sign_ref is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.pmhc_remove_noise(zf.data_ptr(), zt.data_ptr(), pf.data_ptr(), pt.data_ptr(), xf.data_ptr(), xt.data_ptr(),
+                                             beta_t, beta_s, zf.numel() // 7, _lib.ptr(ref), out_f.data_ptr(), out_t.data_ptr(),
+                                             _lib.stream_ptr(dev)), "pmhc_remove_noise")
+        result = {k: noised_signal[k] for k in noised_signal}
+        result["frames"] = _rigid(out_f)
+        result["torsions"] = out_t
+        return result
+
+    # ---- training step --------------------------------------------------------------------------------------
+    def optimize(self, batch: Dict[str, Union[Rigid, torch.Tensor]], metrics: Optional[MetricsRecord] = None,
+                 t: Optional[int] = None, noise: Optional[Dict] = None):
+        """One training step (optimizer.py:195-224): draw t and noise, noise the batch, predict, loss, backward,
+        Adam.  `t` / `noise` may be pinned by the caller (parity tests, data-parallel ranks sharing one t).
+        Six fused launches + Adam; no autograd graph is built."""
+        lib = _lib.load()
+        if t is None:
+            t = random.randint(0, self.noise_step_count - 1)  # optimizer.py:197
+        self.optimizer.zero_grad()
+
+        # in-place conversion of the caller's batch, as optimizer.py:201-202
+        batch["frames"] = Rigid.from_tensor_7(_frames7(batch["frames"]))
+        batch["pocket_frames"] = Rigid.from_tensor_7(_frames7(batch["pocket_frames"]))
+
+        model = self.model
+        frames7 = _lib.f32c(batch["frames"].to_tensor_7())
+        dev = frames7.device
+        if noise is None:
+            noise = self.gen_noise(frames7.shape[:-1], dev)
+        zt = self.add_noise(batch, noise, t)
+
+        desc, keep = _lib.make_batch(zt["frames"].to_tensor_7(), zt["torsions"], batch["features"], batch["mask"],
+                                     batch["pocket_frames"].to_tensor_7(), batch["pocket_features"], batch["pocket_mask"])
+        B, P = desc.B, desc.P
+        flat = model._flat_params()
+        pred_f = torch.empty(B, _lib.N, 7, device=dev, dtype=torch.float32)
+        pred_t = torch.empty(B, _lib.N, _lib.NTORS, 2, device=dev, dtype=torch.float32)
+        saved = torch.empty(lib.pmhc_saved_floats(B, P), device=dev, dtype=torch.float32)
+        ws_bytes = lib.pmhc_workspace_bytes(B, P)
+        ws = _lib.workspace(dev, ws_bytes)
+        t_over_T = float(t) / float(model.T)
+        true_f, true_t = _lib.f32c(_frames7(noise["frames"])), _lib.f32c(noise["torsions"])
+        losses = torch.empty(5, B, device=dev, dtype=torch.float32)
+        d_f, d_t = torch.empty_like(pred_f), torch.empty_like(pred_t)
+        grad = torch.zeros_like(flat)
+        stream = _lib.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.pmhc_model_forward(flat.data_ptr(), ctypes.byref(desc), t_over_T, pred_f.data_ptr(), pred_t.data_ptr(),
+                                              saved.data_ptr(), ws.data_ptr(), ws_bytes, stream), "pmhc_model_forward")
+            # total_loss.mean().backward() (optimizer.py:222): gradient scale 1/B
+            _lib.check(lib.pmhc_loss(true_f.data_ptr(), true_t.data_ptr(), pred_f.data_ptr(), pred_t.data_ptr(),
+                                     _lib.u8c(batch["mask"]).data_ptr(), _lib.u8c(batch["torsions_mask"]).data_ptr(), B,
+                                     1.0 / B, losses.data_ptr(), d_f.data_ptr(), d_t.data_ptr(), stream), "pmhc_loss")
+            _lib.check(lib.pmhc_model_backward(flat.data_ptr(), ctypes.byref(desc), t_over_T, saved.data_ptr(), d_f.data_ptr(),
+                                               d_t.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes, stream), "pmhc_model_backward")
+
+        loss_dict = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
+        if metrics is not None:
+            metrics.add_batch(loss_dict)
+        self.last_losses = loss_dict
+        self._nan_flag = losses[0].isnan().any()  # checked lazily: see check_nan()
+
+        for p, g in zip(model.parameters(), model._split_flat(grad)):
+            p.grad = g
+        self.grad_hook(grad)
+        self.optimizer.step()
+
+    def grad_hook(self, flat_grad: torch.Tensor) -> None:
+        """Called with the flat gradient before the Adam step; data-parallel wrappers all-reduce here."""
+
+    def check_nan(self) -> None:
+        """The reference raises RuntimeError("NaN loss") inside optimize() (optimizer.py:217-218) at the price of a
+        host sync per step; here the flag stays on the device until asked for."""
+        if getattr(self, "_nan_flag", None) is not None and bool(self._nan_flag):
+            raise RuntimeError("NaN loss")
+
+    # ---- sampling -------------------------------------------------------------------------------------------
+    def sample(self, batch: Dict[str, Union[torch.Tensor, Rigid]], noise_tape: Optional[torch.Tensor] = None,
+               quat_sign_tape: Optional[torch.Tensor] = None) -> Dict:
+        """optimizer.py:226-252: T sequential reverse steps, all enqueued by one pmhc_sample call.
+        noise_tape [T, B, 16, 21] (tensor_7 + 14 torsion values) and quat_sign_tape [T, B, 16, 4] are parity hooks."""
+        lib = _lib.load()
+        batch["pocket_frames"] = Rigid.from_tensor_7(_frames7(batch["pocket_frames"]))
+        batch["frames"] = Rigid.from_tensor_7(_frames7(batch["frames"]))
+        frames = _lib.f32c(batch["frames"].to_tensor_7()).clone()
+        tors = _lib.f32c(batch["torsions"]).clone()
+        desc, keep = _lib.make_batch(frames, tors, batch["features"], batch["mask"], batch["pocket_frames"].to_tensor_7(),
+                                     batch["pocket_features"], batch["pocket_mask"])
+        dev = frames.device
+        B, P = desc.B, desc.P
+        T = self.noise_step_count
+        scratch = torch.empty(2 * B * _lib.N * 21, device=dev, dtype=torch.float32)
+        ws_bytes = lib.pmhc_workspace_bytes(B, P)
+        ws = _lib.workspace(dev, ws_bytes)
+        tape = _lib.f32c(noise_tape) if noise_tape is not None else None
+        sign = _lib.f32c(quat_sign_tape) if quat_sign_tape is not None else None
+        flat = self.model._flat_params()
+        seed = self.sample_seed if self.sample_seed is not None else _next_noise_key()
+        with torch.cuda.device(dev):
+            _lib.check(lib.pmhc_sample(flat.data_ptr(), ctypes.byref(desc), frames.data_ptr(), tors.data_ptr(), T,
+                                       self.beta_min, self.beta_max, seed, self.sample_first_complex, _lib.ptr(tape), _lib.ptr(sign),
+                                       scratch.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(dev)), "pmhc_sample")
+        result = {k: batch[k] for k in batch}
+        result["frames"] = _rigid(frames)
+        result["torsions"] = tors
+        return result
