@@ -80,7 +80,11 @@ int pmhc_model_forward(const float *params, const PmhcBatch *batch_host, float t
  *   d_out_frames [B,16,7], d_out_torsions [B,16,7,2]: gradient of the loss w.r.t. the forward outputs. */
 int pmhc_model_backward(const float *params, const PmhcBatch *batch_host, float t_over_T,
                         const float *saved, const float *d_out_frames, const float *d_out_torsions,
-                        float *flat_grad, void *workspace, size_t workspace_bytes, void *stream);
+                        float *flat_grad, void *workspace, size_t workspace_bytes, void *stream,
+                        void *layer2_done_event);
+/* layer2_done_event (nullable cudaEvent_t): recorded on `stream` as soon as the gnn2.* half of flat_grad is final
+ * (the gnn1.* half follows), so a data-parallel caller can start all-reducing it on a second stream while the
+ * layer-1 backward kernel is still running. */
 
 /* Noise draw — replaces DiffusionModelOptimizer.gen_noise (optimizer.py:93-108) with random_quat /
  * shoemake_quat (angle.py:59-98) and random_sin_cos (angle.py:33-57): translation 5*N(0,I), uniform

@@ -63,7 +63,7 @@ def load() -> ctypes.CDLL:
     lib.pmhc_model_forward.restype = c_int
     lib.pmhc_model_forward.argtypes = [vp, POINTER(PmhcBatch), f32, vp, vp, vp, vp, c_size_t, vp]
     lib.pmhc_model_backward.restype = c_int
-    lib.pmhc_model_backward.argtypes = [vp, POINTER(PmhcBatch), f32, vp, vp, vp, vp, vp, c_size_t, vp]
+    lib.pmhc_model_backward.argtypes = [vp, POINTER(PmhcBatch), f32, vp, vp, vp, vp, vp, c_size_t, vp, vp]
     lib.pmhc_gen_noise.restype = c_int
     lib.pmhc_gen_noise.argtypes = [u64, u64, i64, vp, vp, vp]
     lib.pmhc_noise_from_randoms.restype = c_int

@@ -923,7 +923,7 @@ extern "C" size_t pmhc_workspace_bytes(int B, int P) {
 
 extern "C" int pmhc_model_backward(const float* params, const PmhcBatch* bt, float t_over_T, const float* saved,
                                    const float* d_out_frames, const float* d_out_torsions, float* flat_grad,
-                                   void* workspace, size_t workspace_bytes, void* stream_) {
+                                   void* workspace, size_t workspace_bytes, void* stream_, void* layer2_done_event) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PMHC_REQUIRE(device_props() == 0, "no CUDA device");
     PMHC_REQUIRE(bt != nullptr && bt->B > 0, "pmhc_model_backward: empty batch");
@@ -951,6 +951,7 @@ extern "C" int pmhc_model_backward(const float* params, const PmhcBatch* bt, flo
     g.d_frames_in = w.d_frames1; g.d_tors_in = w.d_tors1; g.d_feat_in = w.d_feat1;
     int rc = launch_layer_backward<1>(g, n_cta, flat_grad, stream);
     if (rc != 0) return rc;
+    if (layer2_done_event != nullptr) cudaEventRecord((cudaEvent_t)layer2_done_event, stream);
     // layer 1
     g.a.frames_in = bt->frames; g.a.tors_in = bt->torsions; g.a.feat_in = bt->features;
     g.rowstat = sv.rowstat1; g.logits = sv.logits1; g.msum = sv.msum1; g.feat_post = sv.feat1;

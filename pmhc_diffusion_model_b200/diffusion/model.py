@@ -102,7 +102,7 @@ class _DenoiserFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.pmhc_model_backward(flat.data_ptr(), ctypes.byref(desc), ctx.t_over_T, ctx.saved_buf.data_ptr(),
                                                d_frames.data_ptr(), d_tors.data_ptr(), grad.data_ptr(), ws.data_ptr(),
-                                               ws_bytes, _lib.stream_ptr(dev)), "pmhc_model_backward")
+                                               ws_bytes, _lib.stream_ptr(dev), None), "pmhc_model_backward")
         grads = model._split_flat(grad)
         return (None,) * 9 + tuple(grads)
 

@@ -232,7 +232,8 @@ class DiffusionModelOptimizer:
                                      _lib.u8c(batch["mask"]).data_ptr(), _lib.u8c(batch["torsions_mask"]).data_ptr(), B,
                                      1.0 / B, losses.data_ptr(), d_f.data_ptr(), d_t.data_ptr(), stream), "pmhc_loss")
             _lib.check(lib.pmhc_model_backward(flat.data_ptr(), ctypes.byref(desc), t_over_T, saved.data_ptr(), d_f.data_ptr(),
-                                               d_t.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes, stream), "pmhc_model_backward")
+                                               d_t.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes, stream,
+                                               self.layer2_event_handle()), "pmhc_model_backward")
 
         loss_dict = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
         if metrics is not None:
@@ -247,6 +248,10 @@ class DiffusionModelOptimizer:
 
     def grad_hook(self, flat_grad: torch.Tensor) -> None:
         """Called with the flat gradient before the Adam step; data-parallel wrappers all-reduce here."""
+
+    def layer2_event_handle(self):
+        """cudaEvent_t (or None) the backward records once the gnn2.* gradients are final; see diffusion/parallel.py."""
+        return None
 
     def check_nan(self) -> None:
         """The reference raises RuntimeError("NaN loss") inside optimize() (optimizer.py:217-218) at the price of a
