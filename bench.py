@@ -284,21 +284,16 @@ def main():
         tmodel = tmodel.to(dev)
         tdm = DiffusionModelOptimizer(T_TRAIN, tmodel, 1e-3)
         tb = {k: v.to(dev) for k, v in synthetic(TRAIN_B, seed=5000 + rank).items()}
-        if world > 1:
-            def allreduce(gflat):
-                gflat.div_(world)
-                dist.all_reduce(gflat)
-            tdm.grad_hook = allreduce
-        import random
-        random.seed(0)                          # same t on every rank
+        from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer
+        trainer = DataParallelTrainer(tdm, seed=0)   # N = 1: plain optimize(); N > 1: shared t + overlapped NCCL all-reduce
         for _ in range(W):
-            tdm.optimize(dict(tb), None)
+            trainer.optimize(dict(tb), None)
         barrier()
         n_train = 20
         e0.record()
         for _ in range(n_train):
             flush.zero_()
-            tdm.optimize(dict(tb), None)
+            trainer.optimize(dict(tb), None)
         e1.record()
         barrier()
         tms = max_over_ranks(e0.elapsed_time(e1))

@@ -70,7 +70,7 @@ def install() -> None:
             _stub("Bio.PDB." + leaf, **{cls: type(cls, (), {})})
 
     if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.append(REFERENCE_ROOT)  # appended, not prepended: the reference has its own `tests` package
 
 
 def load_reference():
