@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--complexes", type=int, default=N_COMPLEX, help="complexes per GPU per step")
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+                    help="arithmetic of the denoiser's two dense contractions in the sampling legs (see include/pmhc_b200.h)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -209,6 +211,7 @@ def main():
     model = Model(16, 22, T_STEPS)
     model.load_state_dict(params, strict=True)
     model = model.to(dev)
+    model.precision = args.precision
     dm = DiffusionModelOptimizer(T_STEPS, model, 0.0)
     dm.sample_seed = 2024
     dm.sample_first_complex = rank * B        # Philox stream per global complex index: result independent of N

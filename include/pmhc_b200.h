@@ -32,6 +32,12 @@ extern "C" {
 #define PMHC_NPARAM 79195  /* total fp32 parameters of Model(16, 22, T) */
 #define PMHC_ROWSTAT 16    /* floats saved per peptide row per layer for the backward pass */
 
+/* Arithmetic of the two dense per-pair contractions of the denoiser (message_mlp.2 and the four head hidden layers):
+ *   FP32: fp32 FFMA, the exact-parity mode (<= 1e-4 vs the reference);
+ *   BF16: tcgen05 tensor cores, bf16 operands, fp32 accumulation in TMEM (<= 1e-2); everything else stays fp32. */
+#define PMHC_PRECISION_FP32 0
+#define PMHC_PRECISION_BF16 1
+
 /* One batch of complexes in the dataset's padded layout (data.py:105-117, model.py:384-390). */
 typedef struct {
     int32_t B;                    /* complexes */
@@ -73,6 +79,10 @@ size_t pmhc_saved_floats(int B, int P);
 int pmhc_model_forward(const float *params, const PmhcBatch *batch_host, float t_over_T,
                        float *out_frames, float *out_torsions, float *saved,
                        void *workspace, size_t workspace_bytes, void *stream);
+/* Same with an explicit PMHC_PRECISION_* mode (pmhc_model_forward == PMHC_PRECISION_FP32). */
+int pmhc_model_forward_ex(const float *params, const PmhcBatch *batch_host, float t_over_T,
+                          float *out_frames, float *out_torsions, float *saved,
+                          void *workspace, size_t workspace_bytes, void *stream, int precision);
 
 /* Denoiser backward — the autograd of the above (what total_loss.mean().backward() does at
  * optimizer.py:222 for the model part).  Accumulates (+=) into flat_grad (PMHC_NPARAM floats, same
@@ -136,7 +146,7 @@ int pmhc_loss(const float *true_frames, const float *true_torsions, const float 
 int pmhc_sample(const float *params, const PmhcBatch *batch_host, float *frames, float *torsions,
                 int T, double beta_min, double beta_max, uint64_t seed, uint64_t first_complex,
                 const float *noise_tape, const float *quat_sign_tape, float *scratch,
-                void *workspace, size_t workspace_bytes, void *stream);
+                void *workspace, size_t workspace_bytes, void *stream, int precision);
 
 /* Adam update over the flat buffers — replaces torch.optim.Adam.step (optimizer.py:33, 224), default
  * betas/eps unless given; `skip` ranges (gnn2.feature_mlp) are left untouched like grad=None params. */

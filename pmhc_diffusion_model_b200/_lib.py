@@ -17,10 +17,11 @@ NTORS = 7       # PMHC_NTORS
 HID = 64        # PMHC_HID
 NPARAM = 79195  # PMHC_NPARAM
 ROWSTAT = 16    # PMHC_ROWSTAT
+PRECISIONS = {"fp32": 0, "bf16": 1}  # PMHC_PRECISION_*
 
 EXPORTS = (
     "pmhc_last_error", "pmhc_check_device", "pmhc_param_offset", "pmhc_param_numel", "pmhc_workspace_bytes",
-    "pmhc_saved_floats", "pmhc_model_forward", "pmhc_model_backward", "pmhc_gen_noise", "pmhc_noise_from_randoms",
+    "pmhc_saved_floats", "pmhc_model_forward", "pmhc_model_forward_ex", "pmhc_model_backward", "pmhc_gen_noise", "pmhc_noise_from_randoms",
     "pmhc_add_noise", "pmhc_remove_noise", "pmhc_loss", "pmhc_sample", "pmhc_adam_step", "pmhc_launch_count",
     "pmhc_profile_enable", "pmhc_profile_read",
 )
@@ -62,6 +63,8 @@ def load() -> ctypes.CDLL:
     lib.pmhc_saved_floats.argtypes = [c_int, c_int]
     lib.pmhc_model_forward.restype = c_int
     lib.pmhc_model_forward.argtypes = [vp, POINTER(PmhcBatch), f32, vp, vp, vp, vp, c_size_t, vp]
+    lib.pmhc_model_forward_ex.restype = c_int
+    lib.pmhc_model_forward_ex.argtypes = [vp, POINTER(PmhcBatch), f32, vp, vp, vp, vp, c_size_t, vp, c_int]
     lib.pmhc_model_backward.restype = c_int
     lib.pmhc_model_backward.argtypes = [vp, POINTER(PmhcBatch), f32, vp, vp, vp, vp, vp, c_size_t, vp, vp]
     lib.pmhc_gen_noise.restype = c_int
@@ -75,7 +78,7 @@ def load() -> ctypes.CDLL:
     lib.pmhc_loss.restype = c_int
     lib.pmhc_loss.argtypes = [vp, vp, vp, vp, vp, vp, c_int, f32, vp, vp, vp, vp]
     lib.pmhc_sample.restype = c_int
-    lib.pmhc_sample.argtypes = [vp, POINTER(PmhcBatch), vp, vp, c_int, c_double, c_double, u64, u64, vp, vp, vp, vp, c_size_t, vp]
+    lib.pmhc_sample.argtypes = [vp, POINTER(PmhcBatch), vp, vp, c_int, c_double, c_double, u64, u64, vp, vp, vp, vp, c_size_t, vp, c_int]
     lib.pmhc_adam_step.restype = c_int
     lib.pmhc_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, c_int, vp]
     lib.pmhc_launch_count.restype = i64

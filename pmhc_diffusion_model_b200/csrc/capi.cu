@@ -108,7 +108,7 @@ extern "C" int64_t pmhc_param_numel(int index) {
 extern "C" int pmhc_sample(const float* params, const PmhcBatch* bt, float* frames, float* torsions, int T,
                            double beta_min, double beta_max, uint64_t seed, uint64_t first_complex,
                            const float* noise_tape, const float* quat_sign_tape, float* scratch, void* workspace,
-                           size_t workspace_bytes, void* stream_) {
+                           size_t workspace_bytes, void* stream_, int precision) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PMHC_REQUIRE(bt != nullptr && bt->B > 0 && T > 0, "pmhc_sample: empty batch or T <= 0");
     PMHC_REQUIRE(scratch != nullptr, "pmhc_sample: scratch is required");
@@ -122,8 +122,8 @@ extern "C" int pmhc_sample(const float* params, const PmhcBatch* bt, float* fram
     step.torsions = torsions;
     for (int t = T; t > 0; --t) {
         const int k = T - t;
-        int rc = pmhc_model_forward(params, &step, (float)((double)t / (double)T), pred_f, pred_t, nullptr, workspace,
-                                    workspace_bytes, stream);
+        int rc = pmhc_model_forward_ex(params, &step, (float)((double)t / (double)T), pred_f, pred_t, nullptr, workspace,
+                                       workspace_bytes, stream, precision);
         if (rc != 0) return rc;
         if (noise_tape != nullptr) {
             unpack_noise_tape_kernel<<<(unsigned)((n * 21 + 255) / 256), 256, 0, stream>>>(noise_tape + (size_t)k * n * 21, n, fresh_f, fresh_t);

@@ -381,4 +381,96 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+
+// Per-row masked softmax over the buffered head outputs and the attention-weighted frame / torsion / translation
+// updates (model.py:243, 263-269, 300-310, 331; output quaternion normalised, model.py:181).  One warp per row.
+__device__ inline void finalize_rows(float* S, const SmemMap& M, const LayerArgs& a, const int* I, int b, int row0,
+                                     int nrows, int W) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int rl = warp; rl < nrows; rl += nwarps) {
+        const int i = I[IN_ROWS + row0 + rl];
+        const float* out = S + M.Out + (size_t)rl * W * kOutPerPair;
+        float mx = -INFINITY;
+        for (int e = lane; e < W; e += 32) mx = fmaxf(mx, out[e * kOutPerPair]);
+        mx = warp_max(mx);
+        float se = 0.0f, ws[14];
+#pragma unroll
+        for (int c = 0; c < 14; ++c) ws[c] = 0.0f;
+        for (int e = lane; e < W; e += 32) {
+            const float* o = out + e * kOutPerPair;
+            float p = expf(o[0] - mx);
+            se += p;
+#pragma unroll
+            for (int c = 0; c < 14; ++c) ws[c] = fmaf(p, o[1 + c], ws[c]);
+        }
+        se = warp_sum(se);
+#pragma unroll
+        for (int c = 0; c < 14; ++c) ws[c] = warp_sum(ws[c]);
+        const float inv = W > 0 ? 1.0f / se : 0.0f;
+#pragma unroll
+        for (int c = 0; c < 14; ++c) ws[c] *= inv;
+        const size_t node = (size_t)b * kN + i;
+        if (lane == 0) {
+            const float* qi = S + M.Q + i * 4;
+            const float* xi = S + M.X + i * 3;
+            Quat G{ws[0], ws[1], ws[2], ws[3]};
+            Quat g = W > 0 ? qnormalize(G) : Quat{1.0f, 0.0f, 0.0f, 0.0f};  // model.py:301-306
+            Quat q = qunit(qmul(g, Quat{qi[0], qi[1], qi[2], qi[3]}));       // model.py:310, :181
+            float* fo = a.frames_out + node * 7;
+            fo[0] = q.w; fo[1] = q.x; fo[2] = q.y; fo[3] = q.z;
+            fo[4] = xi[0] + ws[11]; fo[5] = xi[1] + ws[12]; fo[6] = xi[2] + ws[13];
+            if (a.rowstat != nullptr) {
+                float* rs = a.rowstat + node * PMHC_ROWSTAT;
+                rs[0] = W > 0 ? mx + logf(se) : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 14; ++c) rs[1 + c] = ws[c];
+                rs[15] = 0.0f;
+            }
+        }
+        if (lane < PMHC_NTORS) {
+            // torsions' = (sin dA, cos dA) (x) torsions (model.py:263-269)
+            float da = 0.0f;
+#pragma unroll
+            for (int c = 0; c < PMHC_NTORS; ++c) da = (lane == c) ? ws[4 + c] : da;
+            float sn, cs;
+            sincosf(da, &sn, &cs);
+            const float* t = S + M.Tors + i * 14 + 2 * lane;
+            SinCos o = scmul(SinCos{sn, cs}, SinCos{t[0], t[1]});
+            a.tors_out[node * 14 + 2 * lane] = o.s;
+            a.tors_out[node * 14 + 2 * lane + 1] = o.c;
+        }
+    }
+}
+
+
+// The per-hidden-unit parameter packs and scalars only (see SmemMap), for kernels that stage the big matrices
+// in their own format.
+template <int LAYER>
+__device__ inline void stage_packs(float* S, const SmemMap& M, const float* __restrict__ params) {
+    constexpr int L = LAYER;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const float* att0 = params + param_offset(L, ATT0_W);
+    const float* rot0 = params + param_offset(L, ROT0_W);
+    for (int n = tid; n < kHid; n += nthr) {
+        S[M.PkAtt + 4 * n + 0] = att0[n * 66 + 64];
+        S[M.PkAtt + 4 * n + 1] = att0[n * 66 + 65];
+        S[M.PkAtt + 4 * n + 2] = params[param_offset(L, ATT0_B) + n];
+        S[M.PkAtt + 4 * n + 3] = params[param_offset(L, ATT2_W) + n];
+        for (int c = 0; c < 4; ++c) S[M.PkRotQ + 4 * n + c] = rot0[n * 68 + 64 + c];
+        for (int c = 0; c < 4; ++c) S[M.PkRot2 + 4 * n + c] = params[param_offset(L, ROT2_W) + c * kHid + n];
+        S[M.PkMisc + 4 * n + 0] = params[param_offset(L, TRN0_B) + n];
+        S[M.PkMisc + 4 * n + 1] = params[param_offset(L, TRN2_W) + n];
+        S[M.PkMisc + 4 * n + 2] = params[param_offset(L, ROT0_B) + n];
+        S[M.PkMisc + 4 * n + 3] = params[param_offset(L, MSG2_B) + n];
+        for (int c = 0; c < PMHC_NTORS; ++c) S[M.PkTor2 + 8 * n + c] = params[param_offset(L, TOR2_W) + c * kHid + n];
+        S[M.PkTor2 + 8 * n + 7] = 0.0f;
+    }
+    if (tid == 0) {
+        S[M.Scal + SC_ATT2B] = params[param_offset(L, ATT2_B)];
+        S[M.Scal + SC_TRN2B] = params[param_offset(L, TRN2_B)];
+        for (int c = 0; c < 4; ++c) S[M.Scal + SC_ROT2B + c] = params[param_offset(L, ROT2_B) + c];
+        for (int c = 0; c < PMHC_NTORS; ++c) S[M.Scal + SC_TOR2B + c] = params[param_offset(L, TOR2_B) + c];
+    }
+}
+
 }  // namespace pmhc

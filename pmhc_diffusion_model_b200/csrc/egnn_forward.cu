@@ -257,60 +257,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) egnn_layer_forward_kernel(Laye
             }
             __syncthreads();
 
-            // ---------------- per-row softmax + weighted updates (one warp per row) ----------------
-            for (int rl = warp; rl < nrows; rl += kFwdThreads / 32) {
-                const int i = I[IN_ROWS + row0 + rl];
-                const float* out = S + M.Out + (size_t)rl * W * kOutPerPair;
-                float mx = -INFINITY;
-                for (int e = lane; e < W; e += 32) mx = fmaxf(mx, out[e * kOutPerPair]);
-                mx = warp_max(mx);
-                float se = 0.0f, ws[14];
-#pragma unroll
-                for (int c = 0; c < 14; ++c) ws[c] = 0.0f;
-                for (int e = lane; e < W; e += 32) {
-                    const float* o = out + e * kOutPerPair;
-                    float p = expf(o[0] - mx);
-                    se += p;
-#pragma unroll
-                    for (int c = 0; c < 14; ++c) ws[c] = fmaf(p, o[1 + c], ws[c]);
-                }
-                se = warp_sum(se);
-#pragma unroll
-                for (int c = 0; c < 14; ++c) ws[c] = warp_sum(ws[c]);
-                const float inv = W > 0 ? 1.0f / se : 0.0f;
-#pragma unroll
-                for (int c = 0; c < 14; ++c) ws[c] *= inv;
-                const size_t node = (size_t)b * kN + i;
-                if (lane == 0) {
-                    const float* qi = S + M.Q + i * 4;
-                    const float* xi = S + M.X + i * 3;
-                    Quat G{ws[0], ws[1], ws[2], ws[3]};
-                    Quat g = W > 0 ? qnormalize(G) : Quat{1.0f, 0.0f, 0.0f, 0.0f};  // model.py:301-306
-                    Quat q = qunit(qmul(g, Quat{qi[0], qi[1], qi[2], qi[3]}));       // model.py:310, :181
-                    float* fo = a.frames_out + node * 7;
-                    fo[0] = q.w; fo[1] = q.x; fo[2] = q.y; fo[3] = q.z;
-                    fo[4] = xi[0] + ws[11]; fo[5] = xi[1] + ws[12]; fo[6] = xi[2] + ws[13];
-                    if (a.rowstat != nullptr) {
-                        float* rs = a.rowstat + node * PMHC_ROWSTAT;
-                        rs[0] = W > 0 ? mx + logf(se) : 0.0f;
-#pragma unroll
-                        for (int c = 0; c < 14; ++c) rs[1 + c] = ws[c];
-                        rs[15] = 0.0f;
-                    }
-                }
-                if (lane < PMHC_NTORS) {
-                    // torsions' = (sin dA, cos dA) (x) torsions (model.py:263-269)
-                    float da = 0.0f;
-#pragma unroll
-                    for (int c = 0; c < PMHC_NTORS; ++c) da = (lane == c) ? ws[4 + c] : da;
-                    float sn, cs;
-                    sincosf(da, &sn, &cs);
-                    const float* t = S + M.Tors + i * 14 + 2 * lane;
-                    SinCos o = scmul(SinCos{sn, cs}, SinCos{t[0], t[1]});
-                    a.tors_out[node * 14 + 2 * lane] = o.s;
-                    a.tors_out[node * 14 + 2 * lane + 1] = o.c;
-                }
-            }
+            finalize_rows(S, M, a, I, b, row0, nrows, W);
             __syncthreads();
         }
 
@@ -478,10 +425,23 @@ SavedMap carve_saved(float* saved, int B, int P) {
 }
 }  // namespace pmhc
 
+namespace pmhc {
+int launch_layer_forward_tc_layer(int layer, const LayerArgs& a, cudaStream_t stream);
+}
+
 extern "C" int pmhc_model_forward(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames,
                                   float* out_torsions, float* saved, void* workspace, size_t workspace_bytes,
                                   void* stream_) {
+    return pmhc_model_forward_ex(params, bt, t_over_T, out_frames, out_torsions, saved, workspace, workspace_bytes,
+                                 stream_, PMHC_PRECISION_FP32);
+}
+
+extern "C" int pmhc_model_forward_ex(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames,
+                                     float* out_torsions, float* saved, void* workspace, size_t workspace_bytes,
+                                     void* stream_, int precision) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    PMHC_REQUIRE(precision == PMHC_PRECISION_FP32 || precision == PMHC_PRECISION_BF16, "unknown precision mode %d", precision);
+    const bool use_tc = precision == PMHC_PRECISION_BF16;
     PMHC_REQUIRE(device_props() == 0, "no CUDA device");
     PMHC_REQUIRE(bt != nullptr && bt->B > 0, "pmhc_model_forward: empty batch");
     PMHC_REQUIRE(bt->P >= 1 && bt->P <= kMaxP, "pmhc_model_forward: pocket_maxlen %d outside [1, %d]", bt->P, kMaxP);
@@ -505,10 +465,10 @@ extern "C" int pmhc_model_forward(const float* params, const PmhcBatch* bt, floa
     a.frames_out = frames1; a.tors_out = tors1; a.feat_out = feat1; a.msum_out = msum1; a.rowstat = rowstat1;
     a.logit_out = sv.logits1;
     a.ajt_ws = w.ajt;
-    int rc = launch_layer_forward<0>(a, stream);
+    int rc = use_tc ? launch_layer_forward_tc_layer(0, a, stream) : launch_layer_forward<0>(a, stream);
     if (rc != 0) return rc;
     a.frames_in = frames1; a.tors_in = tors1; a.feat_in = feat1;
     a.frames_out = out_frames; a.tors_out = out_torsions; a.feat_out = nullptr; a.msum_out = nullptr; a.rowstat = rowstat2;
     a.logit_out = sv.logits2;
-    return launch_layer_forward<1>(a, stream);
+    return use_tc ? launch_layer_forward_tc_layer(1, a, stream) : launch_layer_forward<1>(a, stream);
 }

@@ -76,9 +76,9 @@ class _DenoiserFn(torch.autograd.Function):
         ws_bytes = lib.pmhc_workspace_bytes(B, P)
         ws = _lib.workspace(dev, ws_bytes)
         with torch.cuda.device(dev):
-            _lib.check(lib.pmhc_model_forward(flat.data_ptr(), ctypes.byref(desc), t_over_T, out_frames.data_ptr(),
-                                              out_tors.data_ptr(), _lib.ptr(saved), ws.data_ptr(), ws_bytes,
-                                              _lib.stream_ptr(dev)), "pmhc_model_forward")
+            _lib.check(lib.pmhc_model_forward_ex(flat.data_ptr(), ctypes.byref(desc), t_over_T, out_frames.data_ptr(),
+                                                 out_tors.data_ptr(), _lib.ptr(saved), ws.data_ptr(), ws_bytes,
+                                                 _lib.stream_ptr(dev), model.precision_code()), "pmhc_model_forward")
         ctx.model, ctx.t_over_T, ctx.keep, ctx.saved_buf = model, t_over_T, keep, saved
         ctx.flat_version = model._flat_generation
         return out_frames, out_tors
@@ -130,6 +130,9 @@ class Model(torch.nn.Module):
         self.gnn2 = EGNNLayer(I, E, 1, M)
         self.act = torch.nn.ReLU()
         self.T = T
+        # arithmetic of the two dense per-pair contractions: "fp32" (FFMA, <= 1e-4 parity) or "bf16" (tcgen05 tensor
+        # cores, bf16 operands / fp32 accumulate, <= 1e-2); everything else is fp32 in both modes
+        self.precision = "fp32"
         self._flat = None
         self._flat_generation = 0
         self._flatten()
@@ -176,6 +179,12 @@ class Model(torch.nn.Module):
         out = super()._apply(fn, *args, **kwargs)
         self._flatten()
         return out
+
+    def precision_code(self) -> int:
+        try:
+            return _lib.PRECISIONS[self.precision]
+        except KeyError:
+            raise ValueError(f"Model.precision must be one of {sorted(_lib.PRECISIONS)}, got {self.precision!r}") from None
 
     # ---- forward -----------------------------------------------------------------------------------------
     def forward(self, batch: Dict[str, Union[torch.Tensor, Rigid]], t: int) -> Dict[str, Union[Rigid, torch.Tensor]]:

@@ -225,8 +225,9 @@ class DiffusionModelOptimizer:
         grad = torch.zeros_like(flat)
         stream = _lib.stream_ptr(dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.pmhc_model_forward(flat.data_ptr(), ctypes.byref(desc), t_over_T, pred_f.data_ptr(), pred_t.data_ptr(),
-                                              saved.data_ptr(), ws.data_ptr(), ws_bytes, stream), "pmhc_model_forward")
+            _lib.check(lib.pmhc_model_forward_ex(flat.data_ptr(), ctypes.byref(desc), t_over_T, pred_f.data_ptr(), pred_t.data_ptr(),
+                                                 saved.data_ptr(), ws.data_ptr(), ws_bytes, stream, model.precision_code()),
+                       "pmhc_model_forward")
             # total_loss.mean().backward() (optimizer.py:222): gradient scale 1/B
             _lib.check(lib.pmhc_loss(true_f.data_ptr(), true_t.data_ptr(), pred_f.data_ptr(), pred_t.data_ptr(),
                                      _lib.u8c(batch["mask"]).data_ptr(), _lib.u8c(batch["torsions_mask"]).data_ptr(), B,
@@ -284,7 +285,8 @@ class DiffusionModelOptimizer:
         with torch.cuda.device(dev):
             _lib.check(lib.pmhc_sample(flat.data_ptr(), ctypes.byref(desc), frames.data_ptr(), tors.data_ptr(), T,
                                        self.beta_min, self.beta_max, seed, self.sample_first_complex, _lib.ptr(tape), _lib.ptr(sign),
-                                       scratch.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(dev)), "pmhc_sample")
+                                       scratch.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(dev),
+                                       self.model.precision_code()), "pmhc_sample")
         result = {k: batch[k] for k in batch}
         result["frames"] = _rigid(frames)
         result["torsions"] = tors

@@ -479,3 +479,77 @@ def test_sample_equals_stepwise_api_and_shards_bitwise(api):
     hi = dm.sample({k: v[5:] for k, v in gb.items()}, noise_tape=tape[:, 5:].contiguous())
     assert torch.equal(full["frames"].to_tensor_7(), torch.cat((lo["frames"].to_tensor_7(), hi["frames"].to_tensor_7())))
     assert torch.equal(full["torsions"], torch.cat((lo["torsions"], hi["torsions"])))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# bf16 tensor-core mode (tcgen05): the two dense contractions in bf16, everything else fp32; gate 1e-2
+# ------------------------------------------------------------------------------------------------------------
+
+TOL_BF16 = 1e-2
+
+
+@pytest.mark.parametrize("B,L,Pn,P_pad,seed", [
+    (4, (8, 12), (50, 70), 80, 61),
+    (5, (1, 16), (0, 40), 40, 62),       # ragged, empty pockets, partial tiles
+    (2, (8, 15), (300, 400), 400, 63),   # rows longer than one 128-pair tile
+    (150, 9, 60, 80, 64),                # more complexes than SMs
+])
+def test_bf16_forward_matches_oracle(api, B, L, Pn, P_pad, seed):
+    batch = orc.synthetic_batch(B, L, Pn, P_pad=P_pad, seed=seed)
+    params = orc.random_params(seed=seed)
+    model = make_model(api, params, 100)
+    model.precision = "bf16"
+    with torch.no_grad():
+        out = model(gpu_batch(batch), 42)
+        ref = orc.model_forward(params, orc.batch_to_frames(batch), 42, 100)
+        model.precision = "fp32"
+        out32 = model(gpu_batch(batch), 42)
+    m = batch["mask"]
+    sel = m & ((m.sum(-1, keepdim=True) - 1 + batch["pocket_mask"].sum(-1, keepdim=True)) > 0)
+    ef = rel_err(out["frames"].to_tensor_7().cpu()[sel], orc.frames_to_tensor7(ref["frames"])[sel])
+    et = rel_err(out["torsions"].cpu()[sel], ref["torsions"][sel])
+    assert ef < TOL_BF16 and et < TOL_BF16, (ef, et)
+    assert torch.isfinite(out["frames"].to_tensor_7()).all() and torch.isfinite(out["torsions"]).all()
+    # the mode must actually differ from the fp32 path (it rounds operands to bf16) yet stay close to it
+    d = (out["frames"].to_tensor_7() - out32["frames"].to_tensor_7()).abs().max()
+    assert 0.0 < float(d) < 0.5
+
+
+def test_bf16_forward_dirty_padding_and_unordered_masks(api):
+    g = torch.Generator().manual_seed(15)
+    batch = orc.synthetic_batch(6, 11, 55, P_pad=80, seed=71)
+    perm_p = torch.randperm(80, generator=g)
+    for k in ("pocket_frames", "pocket_features", "pocket_mask"):
+        batch[k] = batch[k][:, perm_p]
+    batch["pocket_features"][:, ::9] += torch.rand(6, 9, 22, generator=g)
+    params = orc.random_params(seed=18)
+    model = make_model(api, params, 100)
+    model.precision = "bf16"
+    with torch.no_grad():
+        out = model(gpu_batch(batch), 9)
+        ref = orc.model_forward(params, orc.batch_to_frames(batch), 9, 100)
+    m = batch["mask"]
+    assert rel_err(out["frames"].to_tensor_7().cpu()[m], orc.frames_to_tensor7(ref["frames"])[m]) < TOL_BF16
+    assert rel_err(out["torsions"].cpu()[m], ref["torsions"][m]) < TOL_BF16
+
+
+def test_bf16_sample_runs_and_is_shard_invariant(api):
+    T, B = 20, 10
+    batch = orc.synthetic_batch(B, 9, 60, P_pad=80, seed=81)
+    model = make_model(api, orc.random_params(seed=5), T)
+    model.precision = "bf16"
+    g = torch.Generator().manual_seed(9)
+    start = orc.gen_noise([B, 16], g)
+    gb = gpu_batch(batch)
+    gb["frames"] = torch.cat((start["frames"]["quats"], start["frames"]["trans"]), -1).to(DEV)
+    gb["torsions"] = start["torsions"].to(DEV)
+    dm = api.DMO(T, model, 0.0)
+    dm.sample_seed = 77
+    full = dm.sample(dict(gb))
+    dm.sample_first_complex = 0
+    lo = dm.sample({k: v[:4] for k, v in gb.items()})
+    dm.sample_first_complex = 4
+    hi = dm.sample({k: v[4:] for k, v in gb.items()})
+    f = full["frames"].to_tensor_7()
+    assert torch.isfinite(f).all()
+    assert torch.equal(f, torch.cat((lo["frames"].to_tensor_7(), hi["frames"].to_tensor_7())))
