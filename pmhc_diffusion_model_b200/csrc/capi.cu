@@ -34,6 +34,9 @@ void profile_mark(int slot, cudaStream_t stream, bool begin) {
     g_prof_events[slot].push_back(ev);
 }
 
+int model_forward_impl(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames, float* out_torsions,
+                       float* saved, void* workspace, size_t workspace_bytes, cudaStream_t stream, int precision,
+                       bool reuse_pocket_cache);
 int launch_remove_noise(const float* zf, const float* zt, const float* pf, const float* pt, const float* xf,
                         const float* xt, double beta_t, double beta_s, int64_t n, const float* sign_ref, float* of,
                         float* ot, cudaStream_t stream);
@@ -122,8 +125,9 @@ extern "C" int pmhc_sample(const float* params, const PmhcBatch* bt, float* fram
     step.torsions = torsions;
     for (int t = T; t > 0; --t) {
         const int k = T - t;
-        int rc = pmhc_model_forward_ex(params, &step, (float)((double)t / (double)T), pred_f, pred_t, nullptr, workspace,
-                                       workspace_bytes, stream, precision);
+        // the pocket side of the first-layer projections is identical for all T steps: computed at the first step only
+        int rc = model_forward_impl(params, &step, (float)((double)t / (double)T), pred_f, pred_t, nullptr, workspace,
+                                    workspace_bytes, stream, precision, /*reuse_pocket_cache=*/t != T);
         if (rc != 0) return rc;
         if (noise_tape != nullptr) {
             unpack_noise_tape_kernel<<<(unsigned)((n * 21 + 255) / 256), 256, 0, stream>>>(noise_tape + (size_t)k * n * 21, n, fresh_f, fresh_t);

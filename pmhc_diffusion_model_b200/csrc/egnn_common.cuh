@@ -42,6 +42,9 @@ struct LayerArgs {
     float* rowstat;              // training only: [B,16,16] lse, G(4), dA(7), Xa(3), pad
     float* logit_out;            // training only: [B,16,Kpad] attention logits by neighbour slot
     float* ajt_ws;               // [gridDim.x][64][Kpad] per-CTA scratch for the neighbour projections A_j^T
+    // step-invariant pocket data precomputed by pocket_projection_kernel (tensor-core path; null otherwise):
+    float* ajt_cache;            // [B][2][64][Kpad] A_j^T per complex and layer; pocket columns 16.. are pre-filled
+    const uint8_t* pocket_cls;   // [B][P] 0 = valid, 1 = masked with all-zero features, 2 = masked with non-zero features
 };
 
 // pointers into the caller's `saved` buffer (pmhc_saved_floats)
@@ -442,6 +445,98 @@ __device__ inline void finalize_rows(float* S, const SmemMap& M, const LayerArgs
     }
 }
 
+
+// Per-complex setup when the pocket projections are cached (pocket_projection_kernel): only the peptide side is
+// recomputed — geometry, torsions, node features, lists from the cached slot classes, A_i / A_j for the 16 peptide
+// slots from the RESIDENT first-layer weights (wq: [64][2H+1], torx: [64][15]) and T_t.  `ajt` is this complex's
+// [64][Kpad] block of the cache; its peptide columns 0..15 are rewritten here.  Ends with a __syncthreads().
+template <int LAYER>
+__device__ inline ComplexInfo setup_complex_cached(float* S, const SmemMap& M, const float* wq, const float* torx,
+                                                   const LayerArgs& a, int b, float* ajt) {
+    constexpr int L = LAYER;
+    constexpr int H = layer_H(L);
+    constexpr int LDQ = 2 * H + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = a.P, K = kN + P, Kpad = a.Kpad;
+    int* I = reinterpret_cast<int*>(S + M.Ints);
+    const float* msg0b = a.params + param_offset(L, MSG0_B);
+
+    for (int idx = tid; idx < K * 7; idx += blockDim.x) {
+        int j = idx / 7, c = idx - j * 7;
+        float v = (j < kN) ? a.frames_in[((size_t)b * kN + j) * 7 + c] : a.pocket_frames[((size_t)b * P + (j - kN)) * 7 + c];
+        if (c < 4) S[M.Q + j * 4 + c] = v;
+        else S[M.X + j * 3 + (c - 4)] = v;
+    }
+    for (int idx = tid; idx < kN * 14; idx += blockDim.x) S[M.Tors + idx] = a.tors_in[(size_t)b * kN * 14 + idx];
+    for (int idx = tid; idx < kN * kHid; idx += blockDim.x) {
+        int i = idx >> 6, c = idx & 63;
+        float v;
+        if (L == 0) v = (c < PMHC_NFEAT) ? a.feat_in[((size_t)b * kN + i) * PMHC_NFEAT + c] : (c == PMHC_NFEAT ? a.t_over_T : 0.0f);
+        else v = a.feat_in[((size_t)b * kN + i) * kHid + c];
+        S[M.H + i * kLdN + c] = v;
+    }
+    for (int idx = tid; idx < kN * kHid; idx += blockDim.x) S[M.Msum + idx] = 0.0f;
+    if (warp == 0) {
+        bool real = lane < kN && a.mask[(size_t)b * kN + lane] != 0;
+        unsigned bal = __ballot_sync(0xffffffffu, real);
+        int pos = __popc(bal & ((1u << lane) - 1u));
+        int Lr = __popc(bal);
+        if (lane < kN) {
+            if (real) I[IN_ROWS + pos] = lane;
+            else I[IN_PEPX + (lane - pos)] = lane;
+        }
+        int nv = 0, nx = 0, c0 = 0;
+        for (int base = 0; base < P; base += 32) {
+            int j = base + lane;
+            int cls = j < P ? (int)a.pocket_cls[(size_t)b * P + j] : 3;
+            unsigned bv = __ballot_sync(0xffffffffu, cls == 0);
+            unsigned bx = __ballot_sync(0xffffffffu, cls == 2);
+            unsigned bz = __ballot_sync(0xffffffffu, cls == 1);
+            if (cls == 0) I[IN_POCKET + nv + __popc(bv & ((1u << lane) - 1u))] = kN + j;
+            if (cls == 2) I[IN_POCKET + Kpad - 1 - (nx + __popc(bx & ((1u << lane) - 1u)))] = kN + j;
+            nv += __popc(bv);
+            nx += __popc(bx);
+            c0 += __popc(bz);
+        }
+        if (lane == 0) {
+            I[IN_POCKET + Kpad + 0] = Lr;
+            I[IN_POCKET + Kpad + 1] = nv;
+            I[IN_POCKET + Kpad + 2] = nx;
+            I[IN_POCKET + Kpad + 3] = c0;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kN * kHid; idx += blockDim.x) {
+        int k = idx >> 4, i = idx & 15;
+        const float* w = wq + k * LDQ;
+        const float* h = S + M.H + i * kLdN;
+        float ai = msg0b[k], aj = 0.0f;
+#pragma unroll 8
+        for (int c = 0; c < H; ++c) {
+            float hv = h[c];
+            ai = fmaf(w[c], hv, ai);
+            aj = fmaf(w[H + c], hv, aj);
+        }
+        S[M.Ai + i * kLdN + k] = ai;
+        ajt[k * Kpad + i] = aj;
+    }
+    for (int idx = tid; idx < kN * kHid; idx += blockDim.x) {
+        int i = idx >> 6, n = idx & 63;
+        const float* w = torx + n * 15;
+        const float* t = S + M.Tors + i * 14;
+        float acc = w[14];
+#pragma unroll
+        for (int c = 0; c < 14; ++c) acc = fmaf(w[c], t[c], acc);
+        S[M.Tt + idx] = acc;
+    }
+    __syncthreads();
+    ComplexInfo ci;
+    ci.L = I[IN_POCKET + Kpad + 0];
+    ci.nv = I[IN_POCKET + Kpad + 1];
+    ci.nx = I[IN_POCKET + Kpad + 2];
+    ci.c0 = I[IN_POCKET + Kpad + 3];
+    return ci;
+}
 
 // The per-hidden-unit parameter packs and scalars only (see SmemMap), for kernels that stage the big matrices
 // in their own format.

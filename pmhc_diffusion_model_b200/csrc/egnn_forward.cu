@@ -359,7 +359,8 @@ int pad_k(int P) { return ((kN + P + 31) / 32) * 32; }
 
 // workspace layout: [ajt scratch: num_sms * 64 * Kpad] [frames1: B*16*7] [tors1: B*16*14] [feat1: B*16*64]
 struct Workspace {
-    float *ajt, *frames1, *tors1, *feat1;
+    float *ajt, *frames1, *tors1, *feat1, *ajt_cache;
+    uint8_t* pocket_cls;
     size_t bytes;
 };
 Workspace carve_workspace(void* base, int B, int P) {
@@ -371,6 +372,8 @@ Workspace carve_workspace(void* base, int B, int P) {
     w.frames1 = p + o; o += (size_t)B * kN * 7;
     w.tors1 = p + o;   o += (size_t)B * kN * 14;
     w.feat1 = p + o;   o += (size_t)B * kN * kHid;
+    w.ajt_cache = p + o; o += (size_t)B * 2 * kHid * pad_k(P);
+    w.pocket_cls = reinterpret_cast<uint8_t*>(p + o); o += ((size_t)B * P + 3) / 4;
     w.bytes = o * sizeof(float);
     return w;
 }
@@ -427,6 +430,10 @@ SavedMap carve_saved(float* saved, int B, int P) {
 
 namespace pmhc {
 int launch_layer_forward_tc_layer(int layer, const LayerArgs& a, cudaStream_t stream);
+int launch_pocket_projection(const LayerArgs& a, cudaStream_t stream);
+int model_forward_impl(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames, float* out_torsions,
+                       float* saved, void* workspace, size_t workspace_bytes, cudaStream_t stream, int precision,
+                       bool reuse_pocket_cache);
 }
 
 extern "C" int pmhc_model_forward(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames,
@@ -439,7 +446,15 @@ extern "C" int pmhc_model_forward(const float* params, const PmhcBatch* bt, floa
 extern "C" int pmhc_model_forward_ex(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames,
                                      float* out_torsions, float* saved, void* workspace, size_t workspace_bytes,
                                      void* stream_, int precision) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+    return model_forward_impl(params, bt, t_over_T, out_frames, out_torsions, saved, workspace, workspace_bytes,
+                              (cudaStream_t)stream_, precision, false);
+}
+
+// reuse_pocket_cache: the pocket projection cache in `workspace` is still valid (same batch, same weights) — the
+// sampling trajectory sets it from its second step on.
+int pmhc::model_forward_impl(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames,
+                             float* out_torsions, float* saved, void* workspace, size_t workspace_bytes,
+                             cudaStream_t stream, int precision, bool reuse_pocket_cache) {
     PMHC_REQUIRE(precision == PMHC_PRECISION_FP32 || precision == PMHC_PRECISION_BF16, "unknown precision mode %d", precision);
     const bool use_tc = precision == PMHC_PRECISION_BF16;
     PMHC_REQUIRE(device_props() == 0, "no CUDA device");
@@ -465,6 +480,12 @@ extern "C" int pmhc_model_forward_ex(const float* params, const PmhcBatch* bt, f
     a.frames_out = frames1; a.tors_out = tors1; a.feat_out = feat1; a.msum_out = msum1; a.rowstat = rowstat1;
     a.logit_out = sv.logits1;
     a.ajt_ws = w.ajt;
+    a.ajt_cache = use_tc ? w.ajt_cache : nullptr;
+    a.pocket_cls = use_tc ? w.pocket_cls : nullptr;
+    if (use_tc && !reuse_pocket_cache) {
+        int rcp = launch_pocket_projection(a, stream);
+        if (rcp != 0) return rcp;
+    }
     int rc = use_tc ? launch_layer_forward_tc_layer(0, a, stream) : launch_layer_forward<0>(a, stream);
     if (rc != 0) return rc;
     a.frames_in = frames1; a.tors_in = tors1; a.feat_in = feat1;

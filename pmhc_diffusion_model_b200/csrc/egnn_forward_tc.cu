@@ -27,11 +27,12 @@ constexpr int kTmemCols = 512;    // D1: 0..63, D2: 64..319
 struct TcMap {
     SmemMap f;           // float-offset fields used by setup_complex / finalize_rows / packs
     int W2b, Whb, A1b, A2b;   // BYTE offsets of the bf16 SW128 tiles (1024-B aligned)
+    int Wq, TorX;        // float offsets: resident message_mlp.0[:, 0:2H] as [64][2H+1] and torsion_mlp.0[:, 64:78]+bias as [64][15]
     int Bar, TmemPtr;    // float offsets of the mbarrier (2 floats) and the TMEM base address
     int total_bytes;
 };
 
-__host__ __device__ inline TcMap make_tc_map(int Kpad) {
+__host__ __device__ inline TcMap make_tc_map(int Kpad, int layer) {
     TcMap m;
     m.W2b = 0;
     m.Whb = m.W2b + 64 * 128;
@@ -59,6 +60,9 @@ __host__ __device__ inline TcMap make_tc_map(int Kpad) {
     m.f.X = o;      o += Kpad * 3;
     o = (o + 3) & ~3;
     m.f.Ints = o;   o += Kpad + 64;
+    o = (o + 3) & ~3;
+    m.Wq = o;       o += kHid * (2 * layer_H(layer) + 1);
+    m.TorX = o;     o += kHid * 15;
     o = (o + 3) & ~3;
     m.Bar = o;      o += 4;
     m.TmemPtr = o;  o += 4;
@@ -94,6 +98,17 @@ __device__ inline void stage_weights_tc(uint8_t* smem, const TcMap& M, const flo
         int k = idx / kEdge, r = idx - k * kEdge;
         S[M.f.We + r * kLdN + k] = msg0[k * ld1 + 2 * H + r];
     }
+    constexpr int LDQ = 2 * H + 1;
+    for (int idx = tid; idx < kHid * 2 * H; idx += kTcThreads) {
+        int k = idx / (2 * H), c = idx - k * (2 * H);
+        S[M.Wq + k * LDQ + c] = msg0[k * ld1 + c];
+    }
+    const float* tor0 = params + param_offset(L, TOR0_W);
+    for (int idx = tid; idx < kHid * 14; idx += kTcThreads) {
+        int n = idx / 14, c = idx - n * 14;
+        S[M.TorX + n * 15 + c] = tor0[n * 78 + 64 + c];
+    }
+    for (int n = tid; n < kHid; n += kTcThreads) S[M.TorX + n * 15 + 14] = params[param_offset(L, TOR0_B) + n];
     stage_packs<LAYER>(S, M.f, params);
 }
 
@@ -242,8 +257,8 @@ __device__ __forceinline__ void run_tile(uint8_t* smem, const TcMap& M, const La
         const float dq = qdot(qi, qj);
         const float qd = dq * dq;
         float logit = S[M.f.Scal + SC_ATT2B];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {  // rolled: keeps the epilogue inside the instruction cache
             tc::tmem_ld32(ctx.tmem + lane_base + 64 + 32 * half, v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -258,8 +273,8 @@ __device__ __forceinline__ void run_tile(uint8_t* smem, const TcMap& M, const La
         float pre[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) pre[c] = S[M.f.Scal + SC_ROT2B + c];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {  // rolled: keeps the epilogue inside the instruction cache
             tc::tmem_ld32(ctx.tmem + lane_base + 64 + 64 + 32 * half, v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -285,8 +300,8 @@ __device__ __forceinline__ void run_tile(uint8_t* smem, const TcMap& M, const La
         float da[PMHC_NTORS];
 #pragma unroll
         for (int c = 0; c < PMHC_NTORS; ++c) da[c] = S[M.f.Scal + SC_TOR2B + c];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {  // rolled: keeps the epilogue inside the instruction cache
             tc::tmem_ld32(ctx.tmem + lane_base + 64 + 128 + 32 * half, v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -301,8 +316,8 @@ __device__ __forceinline__ void run_tile(uint8_t* smem, const TcMap& M, const La
         }
         // translation scale (model.py:325-331)
         float sc = S[M.f.Scal + SC_TRN2B];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {  // rolled: keeps the epilogue inside the instruction cache
             tc::tmem_ld32(ctx.tmem + lane_base + 64 + 192 + 32 * half, v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -325,10 +340,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) egnn_layer_forward_tc_kernel(La
     // SWIZZLE_128B operand tiles need a 1024-byte aligned base in the shared window: round up (1 KB slack is allocated)
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     float* S = reinterpret_cast<float*>(smem);
-    const TcMap M = make_tc_map(a.Kpad);
+    const TcMap M = make_tc_map(a.Kpad, LAYER);
     const int tid = threadIdx.x, warp = tid >> 5;
     int* I = reinterpret_cast<int*>(S + M.f.Ints);
-    float* ajt = a.ajt_ws + (size_t)blockIdx.x * kHid * a.Kpad;
     uint64_t* bar = reinterpret_cast<uint64_t*>(S + M.Bar);
 
     if (warp == 0) tc::tmem_alloc(reinterpret_cast<uint32_t*>(S + M.TmemPtr), kTmemCols);
@@ -346,7 +360,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) egnn_layer_forward_tc_kernel(La
     ctx.phase = 0;
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-        const ComplexInfo ci = setup_complex<LAYER>(S, M.f, a, b, ajt);
+        float* ajt = a.ajt_cache + ((size_t)b * 2 + LAYER) * kHid * a.Kpad;
+        const ComplexInfo ci = setup_complex_cached<LAYER>(S, M.f, S + M.Wq, S + M.TorX, a, b, ajt);
         const int L = ci.L;
         const int W = (L - 1) + ci.nv;
         float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
@@ -453,11 +468,10 @@ int launch_layer_forward_tc(const LayerArgs& a, cudaStream_t stream) {
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const TcMap M = make_tc_map(a.Kpad);
+    const TcMap M = make_tc_map(a.Kpad, LAYER);
     const size_t smem = (size_t)M.total_bytes + 1024;   // slack so the tile base can be rounded up to 1024 B
     PMHC_REQUIRE((int)smem <= max_smem, "EGNN tensor-core layer needs %zu B of shared memory (P=%d), device allows %d", smem, a.P, max_smem);
-    // the staging area of setup_complex (A1 | A2 | Out) must hold the pocket features and first-layer weights
-    PMHC_REQUIRE(a.P * 23 + 1472 + 4 <= 2 * kTileRows * 32 + kCapPairs * kOutPerPair, "pocket_maxlen %d too large for the tensor-core layer", a.P);
+    PMHC_REQUIRE(a.ajt_cache != nullptr && a.pocket_cls != nullptr, "tensor-core layer needs the pocket projection cache");
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(egnn_layer_forward_tc_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(forward_tc): %s", cudaGetErrorString(e));
@@ -468,6 +482,78 @@ int launch_layer_forward_tc(const LayerArgs& a, cudaStream_t stream) {
     egnn_layer_forward_tc_kernel<LAYER><<<grid, kTcThreads, smem, stream>>>(a);
     if (profile_enabled()) profile_mark(PROF_FWD, stream, false);
     PMHC_CHECK_LAUNCH("egnn_layer_forward_tc");
+    return 0;
+}
+
+// Step-invariant pocket side of message_mlp.0 for both layers (model.py:401, 411-412: pocket nodes carry no time
+// feature and layer 2 sees the same 22 features zero-padded), computed once per batch / sampling trajectory:
+//   ajt_cache[b][l][k][16 + p] = W1_l[k, H_l : H_l + 22] . pocket_features[b][p]      (zero beyond P)
+//   cls[b][p] = 0 valid, 1 masked + all-zero features (shares one message), 2 masked + non-zero features
+__global__ void pocket_projection_kernel(const float* __restrict__ params, const float* __restrict__ pocket_feat,
+                                         const uint8_t* __restrict__ pocket_mask, int P, int Kpad,
+                                         float* __restrict__ ajt_cache, uint8_t* __restrict__ cls) {
+    extern __shared__ __align__(16) float sp[];
+    const int b = blockIdx.x, layer = blockIdx.y, tid = threadIdx.x;
+    const int H = layer == 0 ? kH1 : kH2, ld1 = 2 * H + kEdge;
+    constexpr int FS = 23;
+    float* feat = sp;
+    float* w = sp + ((P * FS + 3) & ~3);
+    const float* msg0 = params + (layer == 0 ? param_offset(0, MSG0_W) : param_offset(1, MSG0_W));
+    for (int idx = tid; idx < P * PMHC_NFEAT; idx += blockDim.x) {
+        int j = idx / PMHC_NFEAT, c = idx - j * PMHC_NFEAT;
+        feat[j * FS + c] = pocket_feat[(size_t)b * P * PMHC_NFEAT + idx];
+    }
+    for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += blockDim.x) {
+        int k = idx / PMHC_NFEAT, c = idx - k * PMHC_NFEAT;
+        w[k * FS + c] = msg0[k * ld1 + H + c];
+    }
+    __syncthreads();
+    float* out = ajt_cache + ((size_t)b * 2 + layer) * kHid * Kpad;
+    const int ncol = Kpad - kN;
+    for (int idx = tid; idx < (kHid / 4) * ncol; idx += blockDim.x) {
+        int kq = idx / ncol, pj = idx - kq * ncol;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        if (pj < P) {
+            const float* h = feat + pj * FS;
+            const float* ww = w + (4 * kq) * FS;
+#pragma unroll
+            for (int c = 0; c < PMHC_NFEAT; ++c) {
+                float hv = h[c];
+                a0 = fmaf(ww[c], hv, a0);
+                a1 = fmaf(ww[FS + c], hv, a1);
+                a2 = fmaf(ww[2 * FS + c], hv, a2);
+                a3 = fmaf(ww[3 * FS + c], hv, a3);
+            }
+        }
+        out[(4 * kq + 0) * Kpad + kN + pj] = a0;
+        out[(4 * kq + 1) * Kpad + kN + pj] = a1;
+        out[(4 * kq + 2) * Kpad + kN + pj] = a2;
+        out[(4 * kq + 3) * Kpad + kN + pj] = a3;
+    }
+    if (layer == 0) {
+        for (int j = tid; j < P; j += blockDim.x) {
+            uint8_t c = 0;
+            if (pocket_mask[(size_t)b * P + j] == 0) {
+                bool nz = false;
+                for (int q = 0; q < PMHC_NFEAT; ++q) nz |= (feat[j * FS + q] != 0.0f);
+                c = nz ? 2 : 1;
+            }
+            cls[(size_t)b * P + j] = c;
+        }
+    }
+}
+
+int launch_pocket_projection(const LayerArgs& a, cudaStream_t stream) {
+    const size_t smem = (size_t)(((a.P * 23 + 3) & ~3) + kHid * 23) * sizeof(float);
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pocket_projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(pocket_projection): %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    pocket_projection_kernel<<<dim3(a.B, 2), 128, smem, stream>>>(a.params, a.pocket_feat, a.pocket_mask, a.P, a.Kpad, a.ajt_cache,
+                                                                 const_cast<uint8_t*>(a.pocket_cls));
+    PMHC_CHECK_LAUNCH("pocket_projection");
     return 0;
 }
 

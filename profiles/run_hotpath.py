@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Short driver for ncu captures: a few denoiser forwards (and optionally training steps) at the bench shapes.
 
-    python profiles/run_hotpath.py [forward|train] [B]
+    python profiles/run_hotpath.py [forward|train] [B] [fp32|bf16]
 """
 import os
 import sys
@@ -17,10 +17,12 @@ from pmhc_diffusion_model_b200.diffusion.optimizer import DiffusionModelOptimize
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "forward"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+precision = sys.argv[3] if len(sys.argv) > 3 else "fp32"
 dev = torch.device("cuda:0")
 model = Model(16, 22, 100)
 model.load_state_dict(orc.random_params(seed=0), strict=True)
 model = model.to(dev)
+model.precision = precision
 batch = {k: v.to(dev) for k, v in orc.synthetic_batch(B, 9, 60, P_pad=80, seed=1).items()}
 if mode == "forward":
     with torch.no_grad():
