@@ -431,6 +431,7 @@ SavedMap carve_saved(float* saved, int B, int P) {
 namespace pmhc {
 int launch_layer_forward_tc_layer(int layer, const LayerArgs& a, cudaStream_t stream);
 int launch_pocket_projection(const LayerArgs& a, cudaStream_t stream);
+
 int model_forward_impl(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames, float* out_torsions,
                        float* saved, void* workspace, size_t workspace_bytes, cudaStream_t stream, int precision,
                        bool reuse_pocket_cache);
