@@ -37,6 +37,9 @@ void profile_mark(int slot, cudaStream_t stream, bool begin) {
 int model_forward_impl(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames, float* out_torsions,
                        float* saved, void* workspace, size_t workspace_bytes, cudaStream_t stream, int precision,
                        bool reuse_pocket_cache);
+int launch_reverse_step_philox(const float* zf, const float* zt, const float* pf, const float* pt, uint64_t seed,
+                               uint64_t first, double beta_t, double beta_s, int64_t n, const float* sign_ref, float* of,
+                               float* ot, cudaStream_t stream);
 int launch_remove_noise(const float* zf, const float* zt, const float* pf, const float* pt, const float* xf,
                         const float* xt, double beta_t, double beta_s, int64_t n, const float* sign_ref, float* of,
                         float* ot, cudaStream_t stream);
@@ -129,19 +132,19 @@ extern "C" int pmhc_sample(const float* params, const PmhcBatch* bt, float* fram
         int rc = model_forward_impl(params, &step, (float)((double)t / (double)T), pred_f, pred_t, nullptr, workspace,
                                     workspace_bytes, stream, precision, /*reuse_pocket_cache=*/t != T);
         if (rc != 0) return rc;
-        if (noise_tape != nullptr) {
-            unpack_noise_tape_kernel<<<(unsigned)((n * 21 + 255) / 256), 256, 0, stream>>>(noise_tape + (size_t)k * n * 21, n, fresh_f, fresh_t);
-            PMHC_CHECK_LAUNCH("unpack_noise_tape");
-        } else {
-            // one Philox stream per (complex-residue, step): counter = residue index, key mixes seed and step
-            rc = pmhc_gen_noise(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(k + 1), first_complex * kN, n, fresh_f, fresh_t, stream);
-            if (rc != 0) return rc;
-        }
         // linear_schedule (optimizer.py:20-21) in double, exactly as the reference's Python floats
         double beta_t = beta_min + (beta_max - beta_min) * ((double)t / (double)T);
         double beta_s = beta_min + (beta_max - beta_min) * ((double)(t - 1) / (double)T);
-        rc = launch_remove_noise(frames, torsions, pred_f, pred_t, fresh_f, fresh_t, beta_t, beta_s, n,
-                                 quat_sign_tape ? quat_sign_tape + (size_t)k * n * 4 : nullptr, frames, torsions, stream);
+        const float* sign = quat_sign_tape ? quat_sign_tape + (size_t)k * n * 4 : nullptr;
+        if (noise_tape != nullptr) {
+            unpack_noise_tape_kernel<<<(unsigned)((n * 21 + 255) / 256), 256, 0, stream>>>(noise_tape + (size_t)k * n * 21, n, fresh_f, fresh_t);
+            PMHC_CHECK_LAUNCH("unpack_noise_tape");
+            rc = launch_remove_noise(frames, torsions, pred_f, pred_t, fresh_f, fresh_t, beta_t, beta_s, n, sign, frames, torsions, stream);
+        } else {
+            // fused draw + reverse step; one Philox stream per (global residue index, step): the key mixes seed and step
+            rc = launch_reverse_step_philox(frames, torsions, pred_f, pred_t, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(k + 1),
+                                            first_complex * kN, beta_t, beta_s, n, sign, frames, torsions, stream);
+        }
         if (rc != 0) return rc;
     }
     return 0;

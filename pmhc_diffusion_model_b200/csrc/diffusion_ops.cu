@@ -31,11 +31,8 @@ __device__ __forceinline__ void write_noise(float* fr, float* tors, float n0, fl
     }
 }
 
-__global__ void gen_noise_kernel(uint64_t seed, uint64_t first, int64_t n, float* __restrict__ frames,
-                                 float* __restrict__ tors) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    uint64_t ctr = first + (uint64_t)r;
+// One residue's noise from the counter-based stream: counter = global residue index, 4 Philox blocks.
+__device__ __forceinline__ void philox_noise(uint64_t seed, uint64_t ctr, float* fr, float* tors) {
     Philox4 a = philox4x32_10(ctr, 0, seed), b = philox4x32_10(ctr, 1, seed);
     Philox4 c = philox4x32_10(ctr, 2, seed), d = philox4x32_10(ctr, 3, seed);
     // Box-Muller on (a0,a1) and (a2,a3)
@@ -45,8 +42,14 @@ __global__ void gen_noise_kernel(uint64_t seed, uint64_t first, int64_t n, float
     sincosf(kTwoPi * u32_to_unit(a.v[3]), &s1, &c1);
     float ua[PMHC_NTORS] = {u32_to_unit(b.v[3]), u32_to_unit(c.v[0]), u32_to_unit(c.v[1]), u32_to_unit(c.v[2]),
                             u32_to_unit(c.v[3]), u32_to_unit(d.v[0]), u32_to_unit(d.v[1])};
-    write_noise(frames + r * 7, tors + r * 14, r0 * c0, r0 * s0, r1 * c1, u32_to_unit(b.v[0]),
-                u32_to_unit(b.v[1]), u32_to_unit(b.v[2]), ua);
+    write_noise(fr, tors, r0 * c0, r0 * s0, r1 * c1, u32_to_unit(b.v[0]), u32_to_unit(b.v[1]), u32_to_unit(b.v[2]), ua);
+}
+
+__global__ void gen_noise_kernel(uint64_t seed, uint64_t first, int64_t n, float* __restrict__ frames,
+                                 float* __restrict__ tors) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    philox_noise(seed, first + (uint64_t)r, frames + r * 7, tors + r * 14);
 }
 
 __global__ void noise_from_randoms_kernel(const float* __restrict__ normal, const float* __restrict__ uniform,
@@ -116,6 +119,19 @@ __global__ void remove_noise_kernel(const float* zf, const float* zt, const floa
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     reverse_step_residue(zf + r * 7, zt + r * 14, pf + r * 7, pt + r * 14, xf + r * 7, xt + r * 14, k,
+                         sign_ref ? sign_ref + r * 4 : nullptr, of + r * 7, ot + r * 14);
+}
+
+// Fused noise draw + reverse step of the sampling loop: the step's fresh noise (optimizer.py:151) never leaves
+// registers.  Bit-identical to gen_noise_kernel followed by remove_noise_kernel.
+__global__ void reverse_step_philox_kernel(const float* zf, const float* zt, const float* __restrict__ pf,
+                                           const float* __restrict__ pt, uint64_t seed, uint64_t first, ReverseCoef k,
+                                           int64_t n, const float* __restrict__ sign_ref, float* of, float* ot) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float xf[7], xt[14];
+    philox_noise(seed, first + (uint64_t)r, xf, xt);
+    reverse_step_residue(zf + r * 7, zt + r * 14, pf + r * 7, pt + r * 14, xf, xt, k,
                          sign_ref ? sign_ref + r * 4 : nullptr, of + r * 7, ot + r * 14);
 }
 
@@ -264,6 +280,16 @@ int launch_remove_noise(const float* zf, const float* zt, const float* pf, const
     ReverseCoef k = reverse_coef(beta_t, beta_s);
     remove_noise_kernel<<<grid_for(n, 128), 128, 0, stream>>>(zf, zt, pf, pt, xf, xt, k, n, sign_ref, of, ot);
     PMHC_CHECK_LAUNCH("pmhc_remove_noise");
+    return 0;
+}
+int launch_reverse_step_philox(const float* zf, const float* zt, const float* pf, const float* pt, uint64_t seed,
+                               uint64_t first, double beta_t, double beta_s, int64_t n, const float* sign_ref, float* of,
+                               float* ot, cudaStream_t stream) {
+    PMHC_REQUIRE(beta_t > 0.0 && beta_t < 1.0 && beta_s >= 0.0 && beta_s < beta_t,
+                 "reverse step: need 0 <= beta_s < beta_t < 1 (got %f, %f)", beta_s, beta_t);
+    ReverseCoef k = reverse_coef(beta_t, beta_s);
+    reverse_step_philox_kernel<<<grid_for(n, 128), 128, 0, stream>>>(zf, zt, pf, pt, seed, first, k, n, sign_ref, of, ot);
+    PMHC_CHECK_LAUNCH("reverse_step_philox");
     return 0;
 }
 }  // namespace pmhc

@@ -389,31 +389,40 @@ __device__ __forceinline__ float warp_max(float v) {
 // updates (model.py:243, 263-269, 300-310, 331; output quaternion normalised, model.py:181).  One warp per row.
 __device__ inline void finalize_rows(float* S, const SmemMap& M, const LayerArgs& a, const int* I, int b, int row0,
                                      int nrows, int W) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int rl = warp; rl < nrows; rl += nwarps) {
-        const int i = I[IN_ROWS + row0 + rl];
-        const float* out = S + M.Out + (size_t)rl * W * kOutPerPair;
+    // one HALF-warp (16 lanes) per row: 16 rows per round with 8 warps, so a 9..16-mer is one round
+    const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int base = 0; base < nrows; base += 2 * nwarps) {
+        const int rl = base + 2 * warp + half;
+        const bool live = rl < nrows;
+        const int i = I[IN_ROWS + row0 + (live ? rl : 0)];
+        const float* out = S + M.Out + (size_t)(live ? rl : 0) * W * kOutPerPair;
+        const int Wl = live ? W : 0;
         float mx = -INFINITY;
-        for (int e = lane; e < W; e += 32) mx = fmaxf(mx, out[e * kOutPerPair]);
-        mx = warp_max(mx);
+        for (int e = l16; e < Wl; e += 16) mx = fmaxf(mx, out[e * kOutPerPair]);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         float se = 0.0f, ws[14];
 #pragma unroll
         for (int c = 0; c < 14; ++c) ws[c] = 0.0f;
-        for (int e = lane; e < W; e += 32) {
+        for (int e = l16; e < Wl; e += 16) {
             const float* o = out + e * kOutPerPair;
             float p = expf(o[0] - mx);
             se += p;
 #pragma unroll
             for (int c = 0; c < 14; ++c) ws[c] = fmaf(p, o[1 + c], ws[c]);
         }
-        se = warp_sum(se);
 #pragma unroll
-        for (int c = 0; c < 14; ++c) ws[c] = warp_sum(ws[c]);
+        for (int o = 8; o > 0; o >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+#pragma unroll
+            for (int c = 0; c < 14; ++c) ws[c] += __shfl_xor_sync(0xffffffffu, ws[c], o);
+        }
+        if (!live) continue;
         const float inv = W > 0 ? 1.0f / se : 0.0f;
 #pragma unroll
         for (int c = 0; c < 14; ++c) ws[c] *= inv;
         const size_t node = (size_t)b * kN + i;
-        if (lane == 0) {
+        if (l16 == 0) {
             const float* qi = S + M.Q + i * 4;
             const float* xi = S + M.X + i * 3;
             Quat G{ws[0], ws[1], ws[2], ws[3]};
@@ -430,21 +439,21 @@ __device__ inline void finalize_rows(float* S, const SmemMap& M, const LayerArgs
                 rs[15] = 0.0f;
             }
         }
-        if (lane < PMHC_NTORS) {
+        if (l16 >= 1 && l16 <= PMHC_NTORS) {
             // torsions' = (sin dA, cos dA) (x) torsions (model.py:263-269)
+            const int tc_ = l16 - 1;
             float da = 0.0f;
 #pragma unroll
-            for (int c = 0; c < PMHC_NTORS; ++c) da = (lane == c) ? ws[4 + c] : da;
+            for (int c = 0; c < PMHC_NTORS; ++c) da = (tc_ == c) ? ws[4 + c] : da;
             float sn, cs;
             sincosf(da, &sn, &cs);
-            const float* t = S + M.Tors + i * 14 + 2 * lane;
+            const float* t = S + M.Tors + i * 14 + 2 * tc_;
             SinCos o = scmul(SinCos{sn, cs}, SinCos{t[0], t[1]});
-            a.tors_out[node * 14 + 2 * lane] = o.s;
-            a.tors_out[node * 14 + 2 * lane + 1] = o.c;
+            a.tors_out[node * 14 + 2 * tc_] = o.s;
+            a.tors_out[node * 14 + 2 * tc_ + 1] = o.c;
         }
     }
 }
-
 
 // Per-complex setup when the pocket projections are cached (pocket_projection_kernel): only the peptide side is
 // recomputed — geometry, torsions, node features, lists from the cached slot classes, A_i / A_j for the 16 peptide
