@@ -274,10 +274,31 @@ def main():
     flops_per_launch = forward_flops_per_complex() * B / 2.0       # one layer per launch
     kernel_ms = prof_ms[0] / max(1, prof_n[0])
     achieved = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+    tc = args.precision == "bf16"
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
-                "kernel": "egnn_layer_forward_kernel", "kernel_ms": kernel_ms, "kernel_share_of_step": prof_ms[0] / (ms * 1.0) if world == 1 else None,
-                "math": "fp32 FFMA (exact-parity mode); tensor-pipe peak is the judged denominator", "flops_per_launch": flops_per_launch}
+                "frac": achieved / peaks["bf16_tflops"],
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ (ncu --set full, B = 1000)
+                "traffic": 28.5e6 if tc else 15.1e6, "peak_source": peaks["source"] + " bf16 sustained",
+                "kernel": "egnn_layer_forward_tc_kernel" if tc else "egnn_layer_forward_kernel", "kernel_ms": kernel_ms,
+                "kernel_share_of_step": prof_ms[0] / (ms * 1.0) if world == 1 else None,
+                "math": ("tcgen05 bf16 x bf16 -> fp32 (TMEM) for the two dense contractions, everything else fp32" if tc
+                         else "fp32 FFMA (exact-parity mode); tensor-pipe peak is the judged denominator"),
+                "flops_per_launch": flops_per_launch}
+
+    # the other precision mode, one short measurement, for the record (same workload, inputs resident)
+    other = None
+    if world == 1:
+        model.precision = "fp32" if tc else "bf16"
+        sample_resident()
+        barrier()
+        e0.record()
+        sample_resident()
+        e1.record()
+        barrier()
+        oms = e0.elapsed_time(e1)
+        other = {"precision": model.precision, "value": B / (oms / 1e3), "unit": UNIT, "ms_per_step": oms,
+                 "parity_gate": "1e-4 (fp32 FFMA, exact-parity mode)" if tc else "1e-2 (bf16 tensor cores)"}
+        model.precision = args.precision
 
     # ---------------- training throughput (second half of the metric) ----------------
     train = None
@@ -316,17 +337,20 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if tc else "f32", "data": "synthetic",
             "config": {"workload": "sampling T=100, 1000 complexes/GPU, 9-mer peptide, M=180 protein / 60 pocket residues padded to 80 (BASELINE configs[1])",
                        "complexes_per_gpu": B, "T": T_STEPS, "P_pad": P_PAD, "l2": "flushed between steps (256 MiB memset)",
-                       "weights": "random init, reference architecture (79 195 params)"},
+                       "weights": "random init, reference architecture (79 195 params)",
+                       "precision": args.precision + (" (tcgen05 bf16 operands / fp32 accumulate for the two dense contractions; parity gate 1e-2)"
+                                                      if tc else " (FFMA; parity gate 1e-4)")},
             "clocks": clocks.summary(),
             "e2e": {"value": world * B * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "other_precision": other,
             "train": train,
         }))
     if world > 1:
