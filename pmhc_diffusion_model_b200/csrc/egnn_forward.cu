@@ -359,10 +359,11 @@ int pad_k(int P) { return ((kN + P + 31) / 32) * 32; }
 
 // workspace layout: [ajt scratch: num_sms * 64 * Kpad] [frames1: B*16*7] [tors1: B*16*14] [feat1: B*16*64]
 struct Workspace {
-    float *ajt, *frames1, *tors1, *feat1, *ajt_cache;
-    uint8_t* pocket_cls;
+    float *ajt, *frames1, *tors1, *feat1;
+    void* tc2;          // buffers of the tensor-core path (carve_tc2)
     size_t bytes;
 };
+size_t tc2_workspace_bytes(int B, int P);
 Workspace carve_workspace(void* base, int B, int P) {
     Workspace w;
     size_t o = 0;
@@ -372,8 +373,8 @@ Workspace carve_workspace(void* base, int B, int P) {
     w.frames1 = p + o; o += (size_t)B * kN * 7;
     w.tors1 = p + o;   o += (size_t)B * kN * 14;
     w.feat1 = p + o;   o += (size_t)B * kN * kHid;
-    w.ajt_cache = p + o; o += (size_t)B * 2 * kHid * pad_k(P);
-    w.pocket_cls = reinterpret_cast<uint8_t*>(p + o); o += ((size_t)B * P + 3) / 4;
+    o = (o + 63) & ~(size_t)63;   // 256-byte aligned
+    w.tc2 = p + o;     o += (tc2_workspace_bytes(B, P) + 3) / 4;
     w.bytes = o * sizeof(float);
     return w;
 }
@@ -429,8 +430,9 @@ SavedMap carve_saved(float* saved, int B, int P) {
 }  // namespace pmhc
 
 namespace pmhc {
-int launch_layer_forward_tc_layer(int layer, const LayerArgs& a, cudaStream_t stream);
-int launch_pocket_projection(const LayerArgs& a, cudaStream_t stream);
+int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float* frames1, float* tors1, float* out_frames,
+                float* out_torsions, float* feat1_out, float* msum_out, float* rowstat1, float* rowstat2, float* logits1,
+                float* logits2, void* tc2_ws, cudaStream_t stream, bool reuse_pocket_cache);
 
 int model_forward_impl(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames, float* out_torsions,
                        float* saved, void* workspace, size_t workspace_bytes, cudaStream_t stream, int precision,
@@ -472,6 +474,10 @@ int pmhc::model_forward_impl(const float* params, const PmhcBatch* bt, float t_o
     float* feat1 = saved ? sv.feat1 : w.feat1;
     float* msum1 = sv.msum1;
 
+    if (use_tc)
+        return forward_tc2(params, bt, t_over_T, frames1, tors1, out_frames, out_torsions, saved ? feat1 : nullptr, msum1,
+                           rowstat1, rowstat2, sv.logits1, sv.logits2, w.tc2, stream, reuse_pocket_cache);
+
     LayerArgs a;
     a.params = params;
     a.B = bt->B; a.P = bt->P; a.Kpad = pad_k(bt->P);
@@ -481,16 +487,12 @@ int pmhc::model_forward_impl(const float* params, const PmhcBatch* bt, float t_o
     a.frames_out = frames1; a.tors_out = tors1; a.feat_out = feat1; a.msum_out = msum1; a.rowstat = rowstat1;
     a.logit_out = sv.logits1;
     a.ajt_ws = w.ajt;
-    a.ajt_cache = use_tc ? w.ajt_cache : nullptr;
-    a.pocket_cls = use_tc ? w.pocket_cls : nullptr;
-    if (use_tc && !reuse_pocket_cache) {
-        int rcp = launch_pocket_projection(a, stream);
-        if (rcp != 0) return rcp;
-    }
-    int rc = use_tc ? launch_layer_forward_tc_layer(0, a, stream) : launch_layer_forward<0>(a, stream);
+    a.ajt_cache = nullptr;
+    a.pocket_cls = nullptr;
+    int rc = launch_layer_forward<0>(a, stream);
     if (rc != 0) return rc;
     a.frames_in = frames1; a.tors_in = tors1; a.feat_in = feat1;
     a.frames_out = out_frames; a.tors_out = out_torsions; a.feat_out = nullptr; a.msum_out = nullptr; a.rowstat = rowstat2;
     a.logit_out = sv.logits2;
-    return use_tc ? launch_layer_forward_tc_layer(1, a, stream) : launch_layer_forward<1>(a, stream);
+    return launch_layer_forward<1>(a, stream);
 }
