@@ -43,19 +43,20 @@ constexpr int TM_XB = 40;                     // extras of the (torsion, transla
 constexpr int TM_D3 = 48;                     // second-layer outputs, 16 columns
 constexpr int TM_D2 = 64;                     // D2 [64,192) -> A3 in place [64,128)
 constexpr int TM_SUM = 192;                   // layer 1: message column sums, 32 columns
+constexpr int TM_A1 = 224;                    // layer 2: the pair tile m1 as an A operand, 32 columns
 
 struct PairArgs {
-    const float* params;
     int B, P, Kpad;
-    float t_over_T;
     const float* frames_in;          // [B,16,7]
     const float* tors_in;            // [B,16,14]
     const uint8_t* mask;             // [B,16]
     const float* pocket_frames;      // [B,P,7]
-    const uint8_t* pocket_cls;       // [B,P]
+    const uint8_t* pocket_cls;       // [B,cls_stride]
     const __nv_bfloat16* pk_cache;   // [B,2,P,64] pocket rows of A_j per layer
-    const float* pep1;               // layer 1: [B,16,128] static (A_i + b1 | A_j) without the time term
-    const __nv_bfloat16* aij2;       // layer 2: [B,16,128] (A_i + b1 | A_j)
+    const __nv_bfloat16* aij;        // [B,16,128] (A_i + b1 | A_j) of this layer's peptide nodes
+    const uint8_t* wimage;           // this layer's operand tiles in their shared-memory layout (weight_image_kernel)
+    int cls_stride;                  // row stride of pocket_cls (P rounded up to 16)
+    long long* dbg;                  // development: per-phase clock64 stamps of engine 0 / CTA 0 (nullable)
     float* frames_out;               // [B,16,7]
     float* tors_out;                 // [B,16,14]
     float* ssum_out;                 // layer 1: [B,16,64] sum_j m1_ij (before message_mlp.2), zero for padded rows
@@ -67,11 +68,11 @@ struct PairArgs {
 
 struct Map {
     int W2b, Whb, W3b, Wxb, Web, Misc, Bar, TmemPtr, cta_bytes;       // CTA-shared, byte offsets
-    int A1, Sel, AjS, Out, Ai, Q, X, Tors, TorsB, Ints, eng_bytes;    // per engine, byte offsets from the engine base
+    int A1, Sel, AjS, Out, Ai, Q, X, Tors, TorsB, Ints, Cls, eng_bytes;   // per engine, byte offsets from the engine base
     int total_bytes;
 };
-// Misc floats: [0,16) second-layer biases in D3 order; [16,144) layer-1 time weights (A_i part | A_j part)
-constexpr int MISC_B2ND = 0, MISC_TIME = 16, MISC_FLOATS = 144;
+// Misc floats: [0,16) second-layer biases in D3 order
+constexpr int MISC_B2ND = 0, MISC_FLOATS = 16;
 
 __host__ __device__ inline Map make_map(int Kpad, int cap_pairs, int aj_rows) {
     Map m;
@@ -82,7 +83,7 @@ __host__ __device__ inline Map make_map(int Kpad, int cap_pairs, int aj_rows) {
     m.Wxb = o; o += 256 * 32;
     m.Web = o; o += 32 * 128;
     m.Misc = o; o += MISC_FLOATS * 4;
-    m.Bar = o; o += 32;
+    m.Bar = o; o += 32;   // [0, Bar) is the weight image
     m.TmemPtr = o; o += 32;
     o = (o + 1023) & ~1023;
     m.cta_bytes = o;
@@ -97,6 +98,7 @@ __host__ __device__ inline Map make_map(int Kpad, int cap_pairs, int aj_rows) {
     m.Tors = e; e += kN * 14 * 4;
     m.TorsB = e; e += kN * 32;
     m.Ints = e; e += (Kpad + 64) * 4;
+    m.Cls = e; e += Kpad + 32;            // [0,16) peptide mask, [16, ...) pocket slot classes
     e = (e + 1023) & ~1023;
     m.eng_bytes = e;
     m.total_bytes = m.cta_bytes + kEngines * m.eng_bytes;
@@ -104,14 +106,13 @@ __host__ __device__ inline Map make_map(int Kpad, int cap_pairs, int aj_rows) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// weight staging (once per CTA)
+// operand tiles of one layer, in the shared-memory layout of the pair kernel (Map offsets [0, Bar))
 // ---------------------------------------------------------------------------------------------------------------
 template <int LAYER>
-__device__ inline void stage_weights(uint8_t* smem, const Map& M, const float* __restrict__ params) {
+__device__ inline void build_weight_image(uint8_t* smem, const Map& M, const float* __restrict__ params, int tid, int kThreads) {
     constexpr int L = LAYER;
     constexpr int H = layer_H(L);
     constexpr int ld1 = 2 * H + kEdge;
-    const int tid = threadIdx.x;
     const float* msg0 = params + param_offset(L, MSG0_W);
     const float* msg2 = params + param_offset(L, MSG2_W);
     const float* msg2b = params + param_offset(L, MSG2_B);
@@ -150,9 +151,8 @@ __device__ inline void stage_weights(uint8_t* smem, const Map& M, const float* _
                             __float2bfloat16_rn(n == 0 ? v - tc::bf16_round(v) : 0.0f);
         }
     }
-    {   // extras operand, one row per hidden unit of the four heads (no-swizzle K-major core matrices, K = 16)
-        const int row = tid;   // kThreads == 256 rows
-        const int h = row >> 6, n = row & 63;
+    for (int row = tid; row < 256; row += kThreads) {   // extras operand, one row per hidden unit of the four heads
+        const int h = row >> 6, n = row & 63;            // (no-swizzle K-major core matrices, K = 16)
         float bias = headb[h][n];
         const float* w = head[h] + n * ldh[h];
         for (int k = 0; k < 64; ++k) bias = fmaf(w[k], msg2b[k], bias);   // message bias folded in: W_h b2
@@ -198,10 +198,12 @@ __device__ inline void stage_weights(uint8_t* smem, const Map& M, const float* _
         else if (tid == 12) v = params[param_offset(L, TRN2_B)];
         misc[MISC_B2ND + tid] = v;
     }
-    if (LAYER == 0 && tid < 128) {
-        const int k = tid & 63;
-        misc[MISC_TIME + tid] = msg0[k * ld1 + (tid < 64 ? PMHC_NFEAT : H + PMHC_NFEAT)];
-    }
+}
+
+template <int LAYER>
+__global__ void __launch_bounds__(256) weight_image_kernel(const float* __restrict__ params, uint8_t* __restrict__ image) {
+    const Map M = make_map(32, 256, kN);
+    build_weight_image<LAYER>(image, M, params, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -217,6 +219,15 @@ struct Engine {
     uint32_t lane_base; // (32 * warp-in-engine) << 16
     uint64_t* bar;      // MMA completion mbarrier
     uint32_t phase;
+    uint32_t smem_u, es_u;   // shared-window addresses of the CTA block and the engine block
+
+    // value the compiler cannot see through: keeps the operand descriptors from being hoisted out of the issue
+    // branch into ~40 long-lived registers (they are recomputed by the one issuing lane, a handful of integer ops)
+    static __device__ __forceinline__ uint32_t opaque(uint32_t x) {
+        uint32_t r;
+        asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(x));
+        return r;
+    }
 
     __device__ __forceinline__ void sync() const { tc::named_bar_sync(1 + eng, kEngThreads); }
     __device__ __forceinline__ void wait_mma() {
@@ -242,11 +253,6 @@ struct Engine {
         }
     }
     __device__ __forceinline__ const int* ints() const { return reinterpret_cast<const int*>(es + M.Ints); }
-};
-
-struct PairGeo {        // kept in registers from the extras stage to the output stage
-    Quat qj, qinvj;
-    float rx, ry, rz;
 };
 
 // m1 row of this thread's pair -> A1 tile
@@ -277,14 +283,27 @@ __device__ __forceinline__ void stage_a1(const Engine& E, const PairRef& pr, int
             bj[c].z = tc::add_bf16x2(bj[c].z, w.z); bj[c].w = tc::add_bf16x2(bj[c].w, w.w);
         }
     }
-    uint8_t* row = E.es + E.M.A1 + (r >> 3) * 1024 + (r & 7) * 128;
+    if (LAYER == 1) {
+        uint32_t m1[32];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint4 av = ai[c];
-        uint4 v;
-        v.x = tc::add_relu_bf16x2(av.x, bj[c].x); v.y = tc::add_relu_bf16x2(av.y, bj[c].y);
-        v.z = tc::add_relu_bf16x2(av.z, bj[c].z); v.w = tc::add_relu_bf16x2(av.w, bj[c].w);
-        *reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4)) = v;
+        for (int c = 0; c < 8; ++c) {
+            const uint4 av = ai[c];
+            m1[4 * c] = tc::add_relu_bf16x2(av.x, bj[c].x); m1[4 * c + 1] = tc::add_relu_bf16x2(av.y, bj[c].y);
+            m1[4 * c + 2] = tc::add_relu_bf16x2(av.z, bj[c].z); m1[4 * c + 3] = tc::add_relu_bf16x2(av.w, bj[c].w);
+        }
+        tc::tmem_st32(E.tmem + E.lane_base + TM_A1, m1);
+        tc::tmem_wait_st();
+    } else {
+        uint8_t* row = E.es + E.M.A1 + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 av = ai[c];
+            uint4 v;
+            v.x = tc::add_relu_bf16x2(av.x, bj[c].x); v.y = tc::add_relu_bf16x2(av.y, bj[c].y);
+            v.z = tc::add_relu_bf16x2(av.z, bj[c].z); v.w = tc::add_relu_bf16x2(av.w, bj[c].w);
+            *reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4)) = v;
+        }
+        tc::fence_proxy_async_smem();
     }
 }
 
@@ -301,35 +320,45 @@ __device__ __forceinline__ void zero_sel(const Engine& E) {
     s[E.et + kEngThreads] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-__device__ __forceinline__ void issue_mma1(const Engine& E, bool with_sum, bool with_d1, bool sum_accumulate) {
+template <int LAYER>
+__device__ __forceinline__ void issue_mma1(const Engine& E, bool with_d1, bool sum_accumulate) {
     E.issue([&] {
-        const uint32_t a1 = tc::smem_u32(E.es + E.M.A1);
-        if (with_d1) {
-            const uint64_t da = tc::smem_desc_sw128(a1);
-            const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(E.smem + E.M.W2b));
+        const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
+        if (LAYER == 1) {
+            // layer 2: the pair tile lives in tensor memory (no message sums needed, no proxy fence)
+            const uint64_t db = tc::smem_desc_sw128(cta + E.M.W2b);
             constexpr uint32_t id = tc::idesc_bf16_f32(128, 64);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) tc::mma_bf16(E.tmem + TM_A2, da + 2 * s, db + 2 * s, id, s > 0);
-        }
-        if (with_sum) {
-            // A = the pair tile read MN-major: M = 2 atoms of 64 features (pairs 0..63 | 64..127), K = 64 pairs
-            const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(E.es + E.M.Sel));
+            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_A2, tm + TM_A1 + 8 * s, db + 2 * s, id, s > 0);
+        } else {
+            const uint32_t a1 = Engine::opaque(E.es_u) + E.M.A1;
+            if (with_d1) {
+                const uint64_t da = tc::smem_desc_sw128(a1);
+                const uint64_t db = tc::smem_desc_sw128(cta + E.M.W2b);
+                constexpr uint32_t id = tc::idesc_bf16_f32(128, 64);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) tc::mma_bf16(tm + TM_A2, da + 2 * s, db + 2 * s, id, s > 0);
+            }
+            // message column sums: A = the pair tile read MN-major (M = 2 atoms of 64 features for pairs 0..63 | 64..127,
+            // K = 64 pairs), B = the selector
+            const uint64_t db = tc::smem_desc_sw128(a1 - E.M.A1 + E.M.Sel);
             constexpr uint32_t id = tc::idesc_bf16_f32_major(128, 32, 1, 0);
 #pragma unroll
             for (int s = 0; s < 4; ++s)
-                tc::mma_bf16(E.tmem + TM_SUM, tc::smem_desc(a1 + s * 2048, 8192, 1024, 2), db + 2 * s, id, (s > 0 || sum_accumulate) ? 1u : 0u);
+                tc::mma_bf16(tm + TM_SUM, tc::smem_desc(a1 + s * 2048, 8192, 1024, 2), db + 2 * s, id, (s > 0 || sum_accumulate) ? 1u : 0u);
         }
     });
 }
 // D2 = [A2 | extras of this half] . W_half^T   (half 0: attention + rotation rows, half 1: torsion + translation)
 __device__ __forceinline__ void issue_mma2(const Engine& E, int half) {
     E.issue([&] {
-        const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(E.smem + E.M.Whb + half * 128 * 128));
-        const uint64_t dx = tc::smem_desc(tc::smem_u32(E.smem + E.M.Wxb + half * 128 * 32), 128, 256, 0);
+        const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
+        const uint64_t db = tc::smem_desc_sw128(cta + E.M.Whb + half * 128 * 128);
+        const uint64_t dx = tc::smem_desc(cta + E.M.Wxb + half * 128 * 32, 128, 256, 0);
         constexpr uint32_t id = tc::idesc_bf16_f32(128, 128);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(E.tmem + TM_D2, E.tmem + TM_A2 + 8 * s, db + 2 * s, id, s > 0);
-        tc::mma_bf16_ts(E.tmem + TM_D2, E.tmem + (half == 0 ? TM_XA : TM_XB), dx, id, 1);
+        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D2, tm + TM_A2 + 8 * s, db + 2 * s, id, s > 0);
+        tc::mma_bf16_ts(tm + TM_D2, tm + (half == 0 ? TM_XA : TM_XB), dx, id, 1);
     });
 }
 // D3 (+)= A3 . W3^T.  Half 0: A3 = [att hi | att lo | rot] (96 columns) -> att hi.W hi + att lo.W hi + att hi.W lo + rot;
@@ -337,38 +366,35 @@ __device__ __forceinline__ void issue_mma2(const Engine& E, int half) {
 __device__ __forceinline__ void issue_mma3(const Engine& E, int half) {
     E.issue([&] {
         constexpr uint32_t id = tc::idesc_bf16_f32(128, 16);
-        const uint32_t w3 = tc::smem_u32(E.smem + E.M.W3b);
+        const uint32_t w3 = Engine::opaque(E.smem_u) + E.M.W3b, tm = Engine::opaque(E.tmem);
         if (half == 0) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(E.tmem + TM_D3, E.tmem + TM_D2 + 8 * s, tc::smem_desc_sw128(w3) + 2 * s, id, s > 0);
+            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + TM_D2 + 8 * s, tc::smem_desc_sw128(w3) + 2 * s, id, s > 0);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(E.tmem + TM_D3, E.tmem + TM_D2 + 32 + 8 * s, tc::smem_desc_sw128(w3) + 2 * s, id, 1);
+            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + TM_D2 + 32 + 8 * s, tc::smem_desc_sw128(w3) + 2 * s, id, 1);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(E.tmem + TM_D3, E.tmem + TM_D2 + 8 * s, tc::smem_desc_sw128(w3 + 4 * 2048) + 2 * s, id, 1);
+            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + TM_D2 + 8 * s, tc::smem_desc_sw128(w3 + 4 * 2048) + 2 * s, id, 1);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(E.tmem + TM_D3, E.tmem + TM_D2 + 64 + 8 * s, tc::smem_desc_sw128(w3 + 2048) + 2 * s, id, 1);
+            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + TM_D2 + 64 + 8 * s, tc::smem_desc_sw128(w3 + 2048) + 2 * s, id, 1);
         } else {
 #pragma unroll
             for (int s = 0; s < 8; ++s)
-                tc::mma_bf16_ts(E.tmem + TM_D3, E.tmem + TM_D2 + 8 * s, tc::smem_desc_sw128(w3 + (2 + (s >> 2)) * 2048) + 2 * (s & 3), id, 1);
+                tc::mma_bf16_ts(tm + TM_D3, tm + TM_D2 + 8 * s, tc::smem_desc_sw128(w3 + (2 + (s >> 2)) * 2048) + 2 * (s & 3), id, 1);
         }
     });
 }
 
-// extras of the (attention, rotation) half for this pair + the geometry the output stage needs again
-__device__ __forceinline__ void pair_extras(const Engine& E, const PairRef& pr, uint32_t (&xa)[8], PairGeo& g) {
+// extras of the (attention, rotation) half for this pair
+__device__ __forceinline__ void pair_extras(const Engine& E, const PairRef& pr, uint32_t (&xa)[8]) {
     const float4* Q = reinterpret_cast<const float4*>(E.es + E.M.Q);
     const float4* X = reinterpret_cast<const float4*>(E.es + E.M.X);
-    const int j = pr.j < 0 ? pr.i : pr.j;
-    const float4 qi4 = Q[pr.i], qj4 = Q[j], xi = X[pr.i], xj = X[j];
-    const Quat qi{qi4.x, qi4.y, qi4.z, qi4.w};
-    g.qj = Quat{qj4.x, qj4.y, qj4.z, qj4.w};
-    g.rx = xi.x - xj.x; g.ry = xi.y - xj.y; g.rz = xi.z - xj.z;
-    const float nd2 = -(g.rx * g.rx + g.ry * g.ry + g.rz * g.rz);   // attention input -d2 (model.py:238)
-    const float dq = qdot(qi, g.qj);
+    const float4 qi4 = Q[pr.i], qj4 = Q[pr.j], xi = X[pr.i], xj = X[pr.j];
+    const Quat qi{qi4.x, qi4.y, qi4.z, qi4.w}, qj{qj4.x, qj4.y, qj4.z, qj4.w};
+    const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+    const float nd2 = -(rx * rx + ry * ry + rz * rz);               // attention input -d2 (model.py:238)
+    const float dq = qdot(qi, qj);
     const float qd = dq * dq;                                       // (q_i . q_j)^2 (model.py:239)
-    g.qinvj = qinv(g.qj);
-    const Quat lq = qmul(g.qinvj, qmul(qi, g.qj));                   // local quaternion (model.py:283-287)
+    const Quat lq = qmul(qinv(qj), qmul(qi, qj));                   // local quaternion (model.py:283-287)
     const float dh = tc::bf16_round(nd2), qh = tc::bf16_round(qd);
     xa[0] = tc::pack_bf16x2(dh, nd2 - dh);
     xa[1] = tc::pack_bf16x2(dh, qh);
@@ -418,11 +444,12 @@ __device__ __forceinline__ void epilogue2(const Engine& E) {
             uint32_t pl[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
+                // hi = relu(x) truncated to bf16 (a byte permute), lo = bf16(relu(x) - hi): ~16 mantissa bits together
                 const uint32_t* v = c < 16 ? v0 : v1;
                 const float x0 = fmaxf(__uint_as_float(v[2 * (c & 15)]), 0.0f), x1 = fmaxf(__uint_as_float(v[2 * (c & 15) + 1]), 0.0f);
-                const float h0 = tc::bf16_round(x0), h1 = tc::bf16_round(x1);
-                pk[c] = tc::pack_bf16x2(h0, h1);
-                pl[c] = tc::pack_bf16x2(x0 - h0, x1 - h1);
+                const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
+                pk[c] = __byte_perm(u0, u1, 0x7632);
+                pl[c] = tc::pack_bf16x2(x0 - __uint_as_float(u0 & 0xFFFF0000u), x1 - __uint_as_float(u1 & 0xFFFF0000u));
             }
             tc::tmem_st32(E.tmem + E.lane_base + TM_D2, pk);
             tc::tmem_st32(E.tmem + E.lane_base + TM_D2 + 32, pl);
@@ -438,22 +465,30 @@ __device__ __forceinline__ void epilogue2(const Engine& E) {
 }
 
 // D3 -> per-pair outputs: logit, global delta quaternion, delta angles, scale * (x_i - x_j)   (model.py:243-331)
-__device__ __forceinline__ void epilogue3(const Engine& E, const PairRef& pr, const PairGeo& g, int slot, float* __restrict__ lsave) {
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ void epilogue3(const Engine& E, const PairRef& pr, int slot, float* __restrict__ lsave) {
     float o[16];
     tc::tmem_ld16(E.tmem + E.lane_base + TM_D3, o);
-    const float* b2nd = reinterpret_cast<const float*>(E.smem + E.M.Misc) + MISC_B2ND;
-#pragma unroll
-    for (int c = 0; c < 13; ++c) o[c] += b2nd[c];
-    const Quat dl{sigmoidf(o[1]), sigmoidf(o[2]), sigmoidf(o[3]), sigmoidf(o[4])};   // never normalised (T5)
-    const Quat dg = qmul(g.qj, qmul(dl, g.qinvj));
+    const float4* b2nd = reinterpret_cast<const float4*>(E.smem + E.M.Misc) + MISC_B2ND / 4;
+    const float4 b0 = b2nd[0], b1 = b2nd[1], b2 = b2nd[2], b3 = b2nd[3];
+    const float4* Q = reinterpret_cast<const float4*>(E.es + E.M.Q);
+    const float4* X = reinterpret_cast<const float4*>(E.es + E.M.X);
+    const float4 qj4 = Q[pr.j], xi = X[pr.i], xj = X[pr.j];
+    const Quat qj{qj4.x, qj4.y, qj4.z, qj4.w};
+    const float in2 = __fdividef(1.0f, qdot(qj, qj));
+    const Quat qinvj{qj.w * in2, -qj.x * in2, -qj.y * in2, -qj.z * in2};
+    const Quat dl{fast_sigmoid(o[1] + b0.y), fast_sigmoid(o[2] + b0.z), fast_sigmoid(o[3] + b0.w), fast_sigmoid(o[4] + b1.x)};   // never normalised (T5)
+    const Quat dg = qmul(qj, qmul(dl, qinvj));
+    const float sc = o[12] + b3.x;
     if (pr.active) {
         float* out = reinterpret_cast<float*>(E.es + E.M.Out) + slot * kOutPerPair;
-        out[0] = o[0];
+        const float logit = o[0] + b0.x;
+        out[0] = logit;
         out[1] = dg.w; out[2] = dg.x; out[3] = dg.y; out[4] = dg.z;
-#pragma unroll
-        for (int c = 0; c < PMHC_NTORS; ++c) out[5 + c] = o[5 + c];
-        out[12] = o[12] * g.rx; out[13] = o[12] * g.ry; out[14] = o[12] * g.rz;
-        if (lsave != nullptr) lsave[pr.i * E.a.Kpad + pr.j] = o[0];
+        out[5] = o[5] + b1.y; out[6] = o[6] + b1.z; out[7] = o[7] + b1.w;
+        out[8] = o[8] + b2.x; out[9] = o[9] + b2.y; out[10] = o[10] + b2.z; out[11] = o[11] + b2.w;
+        out[12] = sc * (xi.x - xj.x); out[13] = sc * (xi.y - xj.y); out[14] = sc * (xi.z - xj.z);
+        if (lsave != nullptr) lsave[pr.i * E.a.Kpad + pr.j] = logit;
     }
 }
 
@@ -528,35 +563,51 @@ __device__ inline void finalize_rows_engine(const Engine& E, int b, int row0, in
     }
 }
 
-// per-complex setup of one engine: geometry, torsions, lists, the 16 peptide rows of A_i / A_j and (when they fit)
-// the pocket rows of A_j.  Ends with an engine barrier.
-template <int LAYER>
-__device__ inline ComplexInfo setup_engine(const Engine& E, int b) {
+// per-complex setup of one engine.  Every global read is a cp.async issued up front (one memory round trip per complex
+// instead of one per array); then the lists and the torsion extras rows are derived from the shared copies.
+__device__ inline ComplexInfo setup_engine(const Engine& E, int b, bool layer1) {
     const PairArgs& a = E.a;
     const Map& M = E.M;
     const int et = E.et, lane = et & 31;
     const int P = a.P, K = kN + P, Kpad = a.Kpad;
     int* I = reinterpret_cast<int*>(E.es + M.Ints);
-    float4* Q = reinterpret_cast<float4*>(E.es + M.Q);
-    float4* X = reinterpret_cast<float4*>(E.es + M.X);
-    for (int j = et; j < K; j += kEngThreads) {
-        const float* f = (j < kN) ? a.frames_in + ((size_t)b * kN + j) * 7 : a.pocket_frames + ((size_t)b * P + (j - kN)) * 7;
-        Q[j] = make_float4(f[0], f[1], f[2], f[3]);
-        X[j] = make_float4(f[4], f[5], f[6], 0.0f);
-    }
+    float* Q = reinterpret_cast<float*>(E.es + M.Q);
+    float* X = reinterpret_cast<float*>(E.es + M.X);
     float* Tors = reinterpret_cast<float*>(E.es + M.Tors);
-    for (int idx = et; idx < kN * 14; idx += kEngThreads) Tors[idx] = a.tors_in[(size_t)b * kN * 14 + idx];
+    uint8_t* Cls = E.es + M.Cls;
+    for (int idx = et; idx < K * 7; idx += kEngThreads) {
+        const int j = idx / 7, c = idx - j * 7;
+        const float* f = (j < kN) ? a.frames_in + ((size_t)b * kN + j) * 7 + c : a.pocket_frames + ((size_t)b * P + (j - kN)) * 7 + c;
+        tc::cp_async_4(c < 4 ? Q + 4 * j + c : X + 4 * j + (c - 4), f);
+    }
+    for (int idx = et; idx < kN * 14 / 4; idx += kEngThreads) tc::cp_async_16(Tors + 4 * idx, a.tors_in + (size_t)b * kN * 14 + 4 * idx);
+    if (et == 0) tc::cp_async_16(Cls, a.mask + (size_t)b * kN);
+    for (int idx = et; idx < a.cls_stride / 16; idx += kEngThreads) tc::cp_async_16(Cls + 16 + 16 * idx, a.pocket_cls + (size_t)b * a.cls_stride + 16 * idx);
+    {   // peptide rows of A_i (row-major) and A_j (chunk-swizzled like the pocket rows)
+        uint4* ai = reinterpret_cast<uint4*>(E.es + M.Ai);
+        uint4* aj = reinterpret_cast<uint4*>(E.es + M.AjS);
+        const uint4* src = reinterpret_cast<const uint4*>(a.aij + (size_t)b * kN * 128);
+        for (int idx = et; idx < kN * 16; idx += kEngThreads) {
+            const int i = idx >> 4, ch = idx & 15;
+            tc::cp_async_16(ch < 8 ? ai + i * 8 + ch : aj + i * 8 + ((ch - 8) ^ (i & 7)), src + idx);
+        }
+        if (a.aj_rows > kN) {
+            const uint4* ps = reinterpret_cast<const uint4*>(a.pk_cache + ((size_t)b * 2 + (layer1 ? 0 : 1)) * P * kHid);
+            for (int idx = et; idx < P * 8; idx += kEngThreads) {
+                const int j = kN + (idx >> 3), c = idx & 7;
+                tc::cp_async_16(aj + j * 8 + (c ^ (j & 7)), ps + idx);
+            }
+        }
+    }
+    if (layer1) zero_sel(E);
+    tc::cp_async_wait_all();
+    E.sync();
     {   // torsion extras rows: 14 bf16 (sin, cos) + (1, 1) for the biases
         const int i = et >> 3, w = et & 7;
-        uint32_t v = 0x3F803F80u;
-        if (w < 7) {
-            const float* t = a.tors_in + ((size_t)b * kN + i) * 14 + 2 * w;
-            v = tc::pack_bf16x2(t[0], t[1]);
-        }
-        reinterpret_cast<uint32_t*>(E.es + M.TorsB)[et] = v;
+        reinterpret_cast<uint32_t*>(E.es + M.TorsB)[et] = w < 7 ? tc::pack_bf16x2(Tors[i * 14 + 2 * w], Tors[i * 14 + 2 * w + 1]) : 0x3F803F80u;
     }
     if ((et >> 5) == 0) {
-        const bool real = lane < kN && a.mask[(size_t)b * kN + lane] != 0;
+        const bool real = lane < kN && Cls[lane] != 0;
         const unsigned bal = __ballot_sync(0xffffffffu, real);
         const int pos = __popc(bal & ((1u << lane) - 1u));
         const int Lr = __popc(bal);
@@ -567,7 +618,7 @@ __device__ inline ComplexInfo setup_engine(const Engine& E, int b) {
         int nv = 0, nx = 0, c0 = 0;
         for (int base = 0; base < P; base += 32) {
             const int j = base + lane;
-            const int cls = j < P ? (int)a.pocket_cls[(size_t)b * P + j] : 3;
+            const int cls = j < P ? (int)Cls[16 + j] : 3;
             const unsigned bv = __ballot_sync(0xffffffffu, cls == 0);
             const unsigned bx = __ballot_sync(0xffffffffu, cls == 2);
             const unsigned bz = __ballot_sync(0xffffffffu, cls == 1);
@@ -584,45 +635,6 @@ __device__ inline ComplexInfo setup_engine(const Engine& E, int b) {
             I[IN_POCKET + Kpad + 3] = c0;
         }
     }
-    {   // peptide rows of A_i (row-major) and A_j (chunk-swizzled like the pocket rows): thread = (node, 16 values)
-        const int i = et >> 3, qd = et & 7;
-        uint32_t pk[8];
-        if (LAYER == 0) {
-            const float4* src = reinterpret_cast<const float4*>(a.pep1 + ((size_t)b * kN + i) * 128 + 16 * qd);
-            const float* tw = reinterpret_cast<const float*>(E.smem + M.Misc) + MISC_TIME + 16 * qd;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float4 v = __ldg(src + c);
-                pk[2 * c] = tc::pack_bf16x2(fmaf(a.t_over_T, tw[4 * c], v.x), fmaf(a.t_over_T, tw[4 * c + 1], v.y));
-                pk[2 * c + 1] = tc::pack_bf16x2(fmaf(a.t_over_T, tw[4 * c + 2], v.z), fmaf(a.t_over_T, tw[4 * c + 3], v.w));
-            }
-        } else {
-            const uint4* src = reinterpret_cast<const uint4*>(a.aij2 + ((size_t)b * kN + i) * 128 + 16 * qd);
-            const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
-            pk[0] = v0.x; pk[1] = v0.y; pk[2] = v0.z; pk[3] = v0.w;
-            pk[4] = v1.x; pk[5] = v1.y; pk[6] = v1.z; pk[7] = v1.w;
-        }
-        const uint4 c0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), c1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        if (qd < 4) {
-            uint4* dst = reinterpret_cast<uint4*>(E.es + M.Ai) + i * 8;
-            dst[2 * qd] = c0;
-            dst[2 * qd + 1] = c1;
-        } else {
-            uint4* dst = reinterpret_cast<uint4*>(E.es + M.AjS) + i * 8;
-            const int ch = 2 * (qd - 4);
-            dst[ch ^ (i & 7)] = c0;
-            dst[(ch + 1) ^ (i & 7)] = c1;
-        }
-    }
-    if (a.aj_rows > kN) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.pk_cache + ((size_t)b * 2 + LAYER) * P * kHid);
-        uint4* dst = reinterpret_cast<uint4*>(E.es + M.AjS);
-        for (int idx = et; idx < P * 8; idx += kEngThreads) {
-            const int j = kN + (idx >> 3), c = idx & 7;
-            dst[j * 8 + (c ^ (j & 7))] = __ldg(src + idx);
-        }
-    }
-    if (LAYER == 0) zero_sel(E);
     E.sync();
     ComplexInfo ci;
     ci.L = I[IN_POCKET + Kpad + 0];
@@ -647,7 +659,11 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
         tc::mbar_init(bars + 1, 1);
         tc::mbar_fence_init();
     }
-    stage_weights<LAYER>(smem, M, a.params);
+    {   // the layer's operand tiles, prepared by weight_image_kernel: one coalesced copy
+        const uint4* src = reinterpret_cast<const uint4*>(a.wimage);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (int idx = tid; idx < M.Bar / 16; idx += kThreads) dst[idx] = __ldg(src + idx);
+    }
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
     __syncthreads();
@@ -655,11 +671,18 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + M.TmemPtr);
 
     Engine E{smem, smem + M.cta_bytes + eng * M.eng_bytes, M, a, eng, et, tmem_base + (uint32_t)(eng * kEngCols),
-             (uint32_t)(((et >> 5) & 3) * 32) << 16, bars + eng, 0u};
+             (uint32_t)(((et >> 5) & 3) * 32) << 16, bars + eng, 0u, tc::smem_u32(smem),
+             tc::smem_u32(smem + M.cta_bytes + eng * M.eng_bytes)};
     const int* I = E.ints();
+    int ts_n = 0;
+    const bool ts_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+#define PMHC_TS() do { if (ts_on && ts_n < 120) a.dbg[ts_n++] = clock64(); } while (0)
+    PMHC_TS();
 
     for (int b = blockIdx.x * kEngines + eng; b < a.B; b += gridDim.x * kEngines) {
-        const ComplexInfo ci = setup_engine<LAYER>(E, b);
+        PMHC_TS();
+        const ComplexInfo ci = setup_engine(E, b, LAYER == 0);
+        PMHC_TS();
         const int L = ci.L;
         const int W = (L - 1) + ci.nv;
         float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
@@ -676,42 +699,79 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
             const int nrows = min(rows_per_group, L - row0);
             const int gpairs = nrows * W;
             const int ntiles = (gpairs + kTile - 1) / kTile;
-            for (int t = 0; t < ntiles; ++t) {
-                const int gp = t * kTile + et;
-                const bool act = gp < gpairs;
-                const PairRef pr = decode_full_pair(I, act ? gp : t * kTile, W, L, row0, act);
-                stage_a1<LAYER>(E, pr, b);
+            // The A1 tile of tile t + 1 is staged while the tensor core runs the first head contraction of tile t.
+            // (row, entry) of this thread's pair advance by 128 pairs per tile without a division
+            const int adv_q = W > 0 ? kTile / W : 0, adv_r = W > 0 ? kTile - adv_q * W : 0;
+            int cur_rl = W > 0 ? et / W : 0, cur_e = W > 0 ? et - cur_rl * W : 0;
+            auto decode = [&](int t) {
+                PairRef p;
+                p.active = t * kTile + et < gpairs;
+                const int rl = p.active ? cur_rl : 0, e = p.active ? cur_e : 0;
+                const int r = row0 + rl;
+                p.i = I[IN_ROWS + r];
+                p.j = e < L - 1 ? I[IN_ROWS + (e < r ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
+                cur_rl += adv_q;
+                cur_e += adv_r;
+                if (cur_e >= W) { cur_e -= W; ++cur_rl; }
+                return p;
+            };
+            PairRef pr = decode(0);
+            if (ntiles > 0) {
                 if (LAYER == 0) write_sel(E, pr, 1.0f);
-                tc::fence_proxy_async_smem();
+                stage_a1<LAYER>(E, pr, b);
+            }
+            for (int t = 0; t < ntiles; ++t) {
+                PMHC_TS();   // 0
                 tc::fence_before_thread_sync();
                 E.sync();
-                issue_mma1(E, LAYER == 0, true, sum_started);
+                PMHC_TS();   // 1 synced
+                issue_mma1<LAYER>(E, true, sum_started);
                 sum_started = true;
+                PMHC_TS();   // 2 issued
                 uint32_t xa[8];
-                PairGeo g;
-                pair_extras(E, pr, xa, g);
+                pair_extras(E, pr, xa);
+                PMHC_TS();   // 3 extras
                 E.wait_mma();
+                PMHC_TS();   // 4 mma1 done
                 if (LAYER == 0) zero_sel(E);
                 epilogue1(E, pr, xa);
+                PMHC_TS();   // 5 ep1
                 E.publish_tmem();
                 issue_mma2(E, 0);
+                PMHC_TS();   // 6 published + issued
+                PairRef nxt = pr;
+                if (t + 1 < ntiles) {
+                    nxt = decode(t + 1);
+                    if (LAYER == 0) write_sel(E, nxt, 1.0f);
+                    stage_a1<LAYER>(E, nxt, b);
+                }
+                PMHC_TS();   // 7 next tile staged
                 E.wait_mma();
+                PMHC_TS();   // 8 mma2a done
                 epilogue2<0>(E);
+                PMHC_TS();   // 9 ep2a
                 E.publish_tmem();
                 issue_mma3(E, 0);
                 E.wait_mma();          // A3 of the first half has been consumed: its columns may be overwritten
+                PMHC_TS();   // 10 mma3a done
                 issue_mma2(E, 1);
                 E.wait_mma();
+                PMHC_TS();   // 11 mma2b done
                 epilogue2<1>(E);
+                PMHC_TS();   // 12 ep2b
                 E.publish_tmem();
                 issue_mma3(E, 1);
                 E.wait_mma();
-                epilogue3(E, pr, g, gp, lsave);
-                tc::fence_before_thread_sync();
+                PMHC_TS();   // 13 mma3b done
+                epilogue3(E, pr, t * kTile + et, lsave);
+                PMHC_TS();   // 14 ep3
+                pr = nxt;
             }
             E.sync();
+            PMHC_TS();
             finalize_rows_engine(E, b, row0, nrows, W);
             E.sync();
+            PMHC_TS();
         }
 
         if (LAYER == 0) {
@@ -738,12 +798,11 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
                     const int which = e - (npx + ci.nx + 1);
                     mult = (float)(which == 0 ? min(ci.c0, 256) : ci.c0 - 256);
                 }
-                stage_a1<LAYER>(E, pr, b);
                 write_sel(E, pr, mult);
-                tc::fence_proxy_async_smem();
+                stage_a1<LAYER>(E, pr, b);
                 tc::fence_before_thread_sync();
                 E.sync();
-                issue_mma1(E, true, false, sum_started);
+                issue_mma1<LAYER>(E, false, sum_started);
                 sum_started = true;
                 E.wait_mma();
                 zero_sel(E);
@@ -760,13 +819,16 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
             E.sync();
             for (int idx = et; idx < kN * kHid; idx += kEngThreads) {
                 const int i = idx >> 6;
-                const bool real = a.mask[(size_t)b * kN + i] != 0;
+                const bool real = (E.es + M.Cls)[i] != 0;
                 a.ssum_out[(size_t)b * kN * kHid + idx] = (real && L > 0) ? scr[idx] + scr[kN * kHid + idx] : 0.0f;
             }
         }
         E.sync();
     }
 
+    PMHC_TS();
+    if (ts_on) a.dbg[127] = ts_n;
+#undef PMHC_TS
     tc::fence_before_thread_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
@@ -782,8 +844,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) node_pre_kernel(const float* __restrict__ params, const float* __restrict__ feat,
                                                        const float* __restrict__ pocket_feat, const uint8_t* __restrict__ pocket_mask,
-                                                       int P, __nv_bfloat16* __restrict__ pk_cache, uint8_t* __restrict__ cls,
-                                                       float* __restrict__ pep1) {
+                                                       int P, int cls_stride, __nv_bfloat16* __restrict__ pk_cache,
+                                                       uint8_t* __restrict__ cls, float* __restrict__ pep1) {
     extern __shared__ __align__(16) float sp[];
     const int b = blockIdx.x, tid = threadIdx.x;
     constexpr int FS = 23;
@@ -836,7 +898,7 @@ __global__ void __launch_bounds__(128) node_pre_kernel(const float* __restrict__
             for (int q = 0; q < PMHC_NFEAT; ++q) nz |= (pf[j * FS + q] != 0.0f);
             c = nz ? 2 : 1;
         }
-        cls[(size_t)b * P + j] = c;
+        cls[(size_t)b * cls_stride + j] = c;
     }
     for (int idx = tid; idx < kN * 128; idx += blockDim.x) {
         const int i = idx >> 7, k = idx & 127;
@@ -845,6 +907,28 @@ __global__ void __launch_bounds__(128) node_pre_kernel(const float* __restrict__
         for (int c = 0; c < PMHC_NFEAT; ++c) acc = fmaf(wp[k * FS + c], nf[i * FS + c], acc);
         pep1[(size_t)b * kN * 128 + idx] = acc;
     }
+}
+
+// Layer 1's peptide projections at time t: aij1 = bf16(pep1 + (t/T) * time column of message_mlp.0) (model.py:394).
+__global__ void __launch_bounds__(256) pep_time_kernel(const float* __restrict__ params, const float* __restrict__ pep1, float t_over_T,
+                                                       int64_t n_nodes, __nv_bfloat16* __restrict__ aij1) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (node, 8 outputs)
+    if (idx >= n_nodes * 16) return;
+    const int k0 = (int)(idx & 15) * 8;
+    constexpr int ld1 = 2 * kH1 + kEdge;
+    const float* msg0 = params + param_offset(0, MSG0_W);
+    const float4* src = reinterpret_cast<const float4*>(pep1 + idx * 8);
+    const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+    float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u;
+        v[u] = fmaf(t_over_T, __ldg(msg0 + (k & 63) * ld1 + (k < 64 ? PMHC_NFEAT : kH1 + PMHC_NFEAT)), v[u]);
+    }
+    uint4 o;
+    o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
+    o.z = tc::pack_bf16x2(v[4], v[5]); o.w = tc::pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(aij1 + idx * 8) = o;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1047,12 +1131,17 @@ __global__ void __launch_bounds__(128, 1) node_mid_kernel(NodeMidArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+long long* g_tc2_dbg = nullptr;   // development hook (pmhc_debug_set_stamps)
+
 struct Tc2Workspace {
     __nv_bfloat16* pk_cache;   // [B,2,P,64]
     float* pep1;               // [B,16,128]
     float* ssum;               // [B,16,64]
+    __nv_bfloat16* aij1;       // [B,16,128]
     __nv_bfloat16* aij2;       // [B,16,128]
-    uint8_t* cls;              // [B,P]
+    uint8_t* cls;              // [B,cls_stride]
+    uint8_t* wimage;           // [2][image_bytes]
+    int cls_stride, image_bytes;
     size_t bytes;
 };
 Tc2Workspace carve_tc2(void* base, int B, int P) {
@@ -1060,11 +1149,15 @@ Tc2Workspace carve_tc2(void* base, int B, int P) {
     uint8_t* p = (uint8_t*)base;
     size_t o = 0;
     auto take = [&](size_t n) { size_t at = o; o += (n + 255) & ~(size_t)255; return p + at; };
+    w.cls_stride = (P + 15) & ~15;
+    w.image_bytes = tc2::make_map(32, 256, kN).Bar;
     w.pk_cache = (__nv_bfloat16*)take((size_t)B * 2 * P * kHid * 2);
     w.pep1 = (float*)take((size_t)B * kN * 128 * 4);
     w.ssum = (float*)take((size_t)B * kN * kHid * 4);
+    w.aij1 = (__nv_bfloat16*)take((size_t)B * kN * 128 * 2);
     w.aij2 = (__nv_bfloat16*)take((size_t)B * kN * 128 * 2);
-    w.cls = (uint8_t*)take((size_t)B * P);
+    w.cls = (uint8_t*)take((size_t)B * w.cls_stride);
+    w.wimage = (uint8_t*)take((size_t)2 * w.image_bytes);
     w.bytes = o;
     return w;
 }
@@ -1113,6 +1206,11 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
     const int B = bt->B, P = bt->P;
     Tc2Workspace w = carve_tc2(tc2_ws, B, P);
     if (!reuse_pocket_cache) {
+        // step-invariant: operand tiles of both layers, pocket projections, static peptide projections
+        tc2::weight_image_kernel<0><<<8, 256, 0, stream>>>(params, w.wimage);
+        PMHC_CHECK_LAUNCH("weight_image");
+        tc2::weight_image_kernel<1><<<8, 256, 0, stream>>>(params, w.wimage + w.image_bytes);
+        PMHC_CHECK_LAUNCH("weight_image");
         const size_t smem = (size_t)(((P * 23 + 3) & ~3) + 2 * kHid * 23 + kN * 23 + 1 + 128 * 23) * sizeof(float);
         static bool configured = false;
         if (!configured) {
@@ -1120,16 +1218,21 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
             PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(node_pre): %s", cudaGetErrorString(e));
             configured = true;
         }
-        tc2::node_pre_kernel<<<B, 128, smem, stream>>>(params, bt->features, bt->pocket_features, bt->pocket_mask, P, w.pk_cache, w.cls, w.pep1);
+        tc2::node_pre_kernel<<<B, 128, smem, stream>>>(params, bt->features, bt->pocket_features, bt->pocket_mask, P, w.cls_stride,
+                                                       w.pk_cache, w.cls, w.pep1);
         PMHC_CHECK_LAUNCH("node_pre");
     }
+    {
+        const int64_t n_items = (int64_t)B * kN * 16;
+        tc2::pep_time_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, stream>>>(params, w.pep1, t_over_T, (int64_t)B * kN, w.aij1);
+        PMHC_CHECK_LAUNCH("pep_time");
+    }
     tc2::PairArgs a{};
-    a.params = params;
     a.B = B; a.P = P; a.Kpad = pad_k(P);
-    a.t_over_T = t_over_T;
     a.frames_in = bt->frames; a.tors_in = bt->torsions; a.mask = bt->mask;
-    a.pocket_frames = bt->pocket_frames; a.pocket_cls = w.cls; a.pk_cache = w.pk_cache;
-    a.pep1 = w.pep1; a.aij2 = w.aij2;
+    a.pocket_frames = bt->pocket_frames; a.pocket_cls = w.cls; a.cls_stride = w.cls_stride; a.pk_cache = w.pk_cache;
+    a.aij = w.aij1; a.wimage = w.wimage;
+    a.dbg = g_tc2_dbg;
     a.frames_out = frames1; a.tors_out = tors1; a.ssum_out = w.ssum;
     a.rowstat = rowstat1; a.logit_out = logits1;
     int rc = launch_pair<0>(a, stream);
@@ -1147,9 +1250,14 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
         PMHC_CHECK_LAUNCH("node_mid");
     }
     a.frames_in = frames1; a.tors_in = tors1;
+    a.aij = w.aij2; a.wimage = w.wimage + w.image_bytes;
+    a.dbg = g_tc2_dbg ? g_tc2_dbg + 128 : nullptr;
     a.frames_out = out_frames; a.tors_out = out_torsions; a.ssum_out = nullptr;
     a.rowstat = rowstat2; a.logit_out = logits2;
     return launch_pair<1>(a, stream);
 }
 
 }  // namespace pmhc
+
+// development hook: device buffer of 256 int64 receiving clock64 stamps of CTA 0 / thread 0 (layer 1: [0,128), layer 2: [128,256))
+extern "C" void pmhc_debug_set_stamps(long long* dev_buf) { pmhc::g_tc2_dbg = dev_buf; }

@@ -224,5 +224,15 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // named barrier over `count` threads (count a multiple of 32); id 0 is __syncthreads
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+
+// ---- cp.async (LDGSTS): global -> shared without a register round trip; all copies of a thread are in flight together ----
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 }  // namespace tc
 }  // namespace pmhc
