@@ -32,18 +32,22 @@ namespace pmhc {
 namespace tc2 {
 
 constexpr int kEngines = 2;
-constexpr int kEngThreads = 128;
-constexpr int kThreads = kEngines * kEngThreads;
+constexpr int kEngThreads = 128;                 // compute threads of one engine (one per pair row / TMEM lane)
+constexpr int kComputeThreads = kEngines * kEngThreads;
+constexpr int kThreads = kComputeThreads + 128;  // + one warpgroup: warp 8 / 9 issue the MMAs of engine 0 / 1, two warps idle
+constexpr int kRegsCompute = 232, kRegsIssue = 40;   // setmaxnreg budgets (256 * 232 + 128 * 40 <= 64 K registers)
 constexpr int kTile = 128;
 constexpr int kEngCols = 256;                 // TMEM columns per engine
 // TMEM columns of one engine, relative to its base
 constexpr int TM_A2 = 0;                      // D1 [0,64) -> A2 = bf16 message, 32 columns
-constexpr int TM_XA = 32;                     // extras of the (attention, rotation) half, 8 columns = 16 bf16
-constexpr int TM_XB = 40;                     // extras of the (torsion, translation) half
+constexpr int TM_XA = 32;                     // extras of the attention / rotation heads, 8 columns = 16 bf16
+constexpr int TM_XB = 40;                     // extras of the torsion / translation heads
 constexpr int TM_D3 = 48;                     // second-layer outputs, 16 columns
-constexpr int TM_D2 = 64;                     // D2 [64,192) -> A3 in place [64,128)
-constexpr int TM_SUM = 192;                   // layer 1: message column sums, 32 columns
-constexpr int TM_A1 = 224;                    // layer 2: the pair tile m1 as an A operand, 32 columns
+constexpr int TM_X = 64;                      // head buffers: hidden pre-activations D2 (64 columns), then the
+constexpr int TM_Y = 128;                     //   second-layer operand A3 in place; X: attention then translation,
+constexpr int TM_Z = 192;                     //   Y: rotation, Z: torsion (layer 1: also the per-tile message column sums)
+// mbarriers of one engine
+constexpr int BM = 0, BX = 1, BY = 2, BZ = 3;
 
 struct PairArgs {
     int B, P, Kpad;
@@ -83,7 +87,7 @@ __host__ __device__ inline Map make_map(int Kpad, int cap_pairs, int aj_rows) {
     m.Wxb = o; o += 256 * 32;
     m.Web = o; o += 32 * 128;
     m.Misc = o; o += MISC_FLOATS * 4;
-    m.Bar = o; o += 32;   // [0, Bar) is the weight image
+    m.Bar = o; o += 64;   // [0, Bar) is the weight image; 4 mbarriers per engine
     m.TmemPtr = o; o += 32;
     o = (o + 1023) & ~1023;
     m.cta_bytes = o;
@@ -186,7 +190,8 @@ __device__ inline void build_weight_image(uint8_t* smem, const Map& M, const flo
     }
     for (int idx = tid; idx < kEdge * 32; idx += kThreads) {         // edge one-hot columns of message_mlp.0
         int r = idx >> 5, k = (idx & 31) * 2;
-        *reinterpret_cast<uint32_t*>(smem + M.Web + r * 128 + k * 2) =
+        // 16-byte chunks of a row are XOR-swizzled by the row: neighbouring relative positions read different banks
+        *reinterpret_cast<uint32_t*>(smem + M.Web + r * 128 + ((((k >> 3) ^ r) & 7) << 4) + (k & 7) * 2) =
             tc::pack_bf16x2(msg0[k * ld1 + 2 * H + r], msg0[(k + 1) * ld1 + 2 * H + r]);
     }
     float* misc = reinterpret_cast<float*>(smem + M.Misc);
@@ -217,8 +222,8 @@ struct Engine {
     int eng, et;        // engine index, thread within the engine (= pair row = TMEM lane)
     uint32_t tmem;      // engine's TMEM base (column offset applied)
     uint32_t lane_base; // (32 * warp-in-engine) << 16
-    uint64_t* bar;      // MMA completion mbarrier
-    uint32_t phase;
+    uint64_t* bar;      // this engine's four MMA completion mbarriers (BM, BX, BY, BZ)
+    uint32_t phase;     // bit k: parity of the next completion of barrier k
     uint32_t smem_u, es_u;   // shared-window addresses of the CTA block and the engine block
 
     // value the compiler cannot see through: keeps the operand descriptors from being hoisted out of the issue
@@ -229,34 +234,42 @@ struct Engine {
         return r;
     }
 
-    __device__ __forceinline__ void sync() const { tc::named_bar_sync(1 + eng, kEngThreads); }
-    __device__ __forceinline__ void wait_mma() {
-        tc::mbar_wait(bar, phase);
-        phase ^= 1;
+    // named barriers of the engine: two alternating request barriers (compute threads arrive, the issuing warp syncs),
+    // one among the compute threads, one among all 160 threads
+    uint32_t req;       // requests made (compute threads) / served (issuing warp) so far
+    __device__ __forceinline__ int bar_id(int k) const { return 1 + 4 * eng + k; }
+    __device__ __forceinline__ void sync() const { tc::named_bar_sync(bar_id(2), kEngThreads); }
+    __device__ __forceinline__ void sync_all() const { tc::named_bar_sync(bar_id(3), kEngThreads + 32); }
+    // every compute thread waits for every committed completion exactly once, in the same order
+    __device__ __forceinline__ void wait(int k) {
+        tc::mbar_wait(bar + k, (phase >> k) & 1u);
+        phase ^= 1u << k;
         tc::fence_after_thread_sync();
     }
-    // publish this thread's TMEM / shared-memory writes, then rendezvous with the engine
-    __device__ __forceinline__ void publish_tmem() const {
+    // compute thread: my TMEM / shared-memory operand writes are done -> ask the issuing warp for the next MMA batch.
+    // Between two requests every compute thread waits for a completion caused by the earlier one, so a thread is never
+    // more than one request ahead and two alternating barriers suffice.
+    __device__ __forceinline__ void request() {
         tc::tmem_wait_st();
         tc::fence_before_thread_sync();
-        sync();
+        asm volatile("bar.arrive %0, %1;" ::"r"(bar_id((int)(req & 1u))), "r"(kEngThreads + 32) : "memory");
+        ++req;
     }
+    // issuing warp: wait for the request, then one elected lane issues f (which commits to the barriers it wants)
     template <class F>
-    __device__ __forceinline__ void issue(F&& f) const {
-        if ((et >> 5) == 0) {
-            if (tc::elect_one()) {
-                tc::fence_after_thread_sync();
-                f();
-                tc::mma_commit(bar);
-            }
-            __syncwarp();
-        }
+    __device__ __forceinline__ void serve(F&& f) {
+        tc::named_bar_sync(bar_id((int)(req & 1u)), kEngThreads + 32);
+        ++req;
+        tc::fence_after_thread_sync();
+        if (tc::elect_one()) f();
+        __syncwarp();
     }
+    __device__ __forceinline__ void commit(int k) const { tc::mma_commit(bar + k); }
     __device__ __forceinline__ const int* ints() const { return reinterpret_cast<const int*>(es + M.Ints); }
 };
 
 // m1 row of this thread's pair -> A1 tile
-template <int LAYER>
+template <int LAYER, bool FENCE = true>
 __device__ __forceinline__ void stage_a1(const Engine& E, const PairRef& pr, int b) {
     const int r = E.et, i = pr.i, j = pr.j;
     const bool pep = (j >= 0 && j < kN);
@@ -275,113 +288,88 @@ __device__ __forceinline__ void stage_a1(const Engine& E, const PairRef& pr, int
         for (int c = 0; c < 8; ++c) bj[c] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (pep) {
-        const uint4* we = reinterpret_cast<const uint4*>(E.smem + E.M.Web) + (kN - 1 + i - j) * 8;
+        const int rel = kN - 1 + i - j;
+        const uint4* we = reinterpret_cast<const uint4*>(E.smem + E.M.Web) + rel * 8;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint4 w = we[c];
+            const uint4 w = we[c ^ (rel & 7)];
             bj[c].x = tc::add_bf16x2(bj[c].x, w.x); bj[c].y = tc::add_bf16x2(bj[c].y, w.y);
             bj[c].z = tc::add_bf16x2(bj[c].z, w.z); bj[c].w = tc::add_bf16x2(bj[c].w, w.w);
         }
     }
-    if (LAYER == 1) {
-        uint32_t m1[32];
+    uint8_t* row = E.es + E.M.A1 + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 av = ai[c];
-            m1[4 * c] = tc::add_relu_bf16x2(av.x, bj[c].x); m1[4 * c + 1] = tc::add_relu_bf16x2(av.y, bj[c].y);
-            m1[4 * c + 2] = tc::add_relu_bf16x2(av.z, bj[c].z); m1[4 * c + 3] = tc::add_relu_bf16x2(av.w, bj[c].w);
-        }
-        tc::tmem_st32(E.tmem + E.lane_base + TM_A1, m1);
-        tc::tmem_wait_st();
-    } else {
-        uint8_t* row = E.es + E.M.A1 + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 av = ai[c];
-            uint4 v;
-            v.x = tc::add_relu_bf16x2(av.x, bj[c].x); v.y = tc::add_relu_bf16x2(av.y, bj[c].y);
-            v.z = tc::add_relu_bf16x2(av.z, bj[c].z); v.w = tc::add_relu_bf16x2(av.w, bj[c].w);
-            *reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4)) = v;
-        }
-        tc::fence_proxy_async_smem();
+    for (int c = 0; c < 8; ++c) {
+        const uint4 av = ai[c];
+        uint4 v;
+        v.x = tc::add_relu_bf16x2(av.x, bj[c].x); v.y = tc::add_relu_bf16x2(av.y, bj[c].y);
+        v.z = tc::add_relu_bf16x2(av.z, bj[c].z); v.w = tc::add_relu_bf16x2(av.w, bj[c].w);
+        *reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4)) = v;
     }
+    if (FENCE) tc::fence_proxy_async_smem();
 }
 
-// layer 1: this pair's entry of the column-sum selector (Sel[16 * (r / 64) + i][r % 64] = multiplicity)
+// layer 1: this pair's entry of the column-sum selector (Sel[16 * (r / 64) + i][r % 64] = multiplicity).  A thread only
+// ever touches column r % 64 of row block r / 64, so writing and clearing need no synchronisation between threads.
 __device__ __forceinline__ void write_sel(const Engine& E, const PairRef& pr, float mult) {
     if (pr.active) {
         const int r = E.et;
         *reinterpret_cast<__nv_bfloat16*>(E.es + E.M.Sel + tc::sw128_offset(16 * (r >> 6) + pr.i, r & 63)) = __float2bfloat16_rn(mult);
     }
 }
+__device__ __forceinline__ void clear_sel(const Engine& E, const PairRef& pr) { write_sel(E, pr, 0.0f); }
 __device__ __forceinline__ void zero_sel(const Engine& E) {
     uint4* s = reinterpret_cast<uint4*>(E.es + E.M.Sel);
     s[E.et] = make_uint4(0u, 0u, 0u, 0u);
     s[E.et + kEngThreads] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// D1 = m1 . W2^T  (+ layer 1: the tile's message column sums into buffer Z), completion -> BM
 template <int LAYER>
-__device__ __forceinline__ void issue_mma1(const Engine& E, bool with_d1, bool sum_accumulate) {
-    E.issue([&] {
-        const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
-        if (LAYER == 1) {
-            // layer 2: the pair tile lives in tensor memory (no message sums needed, no proxy fence)
-            const uint64_t db = tc::smem_desc_sw128(cta + E.M.W2b);
-            constexpr uint32_t id = tc::idesc_bf16_f32(128, 64);
+__device__ __forceinline__ void mma_first(const Engine& E, bool with_d1) {
+    const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
+    const uint32_t a1 = Engine::opaque(E.es_u) + E.M.A1;
+    if (with_d1) {
+        const uint64_t da = tc::smem_desc_sw128(a1);
+        const uint64_t db = tc::smem_desc_sw128(cta + E.M.W2b);
+        constexpr uint32_t id = tc::idesc_bf16_f32(128, 64);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_A2, tm + TM_A1 + 8 * s, db + 2 * s, id, s > 0);
-        } else {
-            const uint32_t a1 = Engine::opaque(E.es_u) + E.M.A1;
-            if (with_d1) {
-                const uint64_t da = tc::smem_desc_sw128(a1);
-                const uint64_t db = tc::smem_desc_sw128(cta + E.M.W2b);
-                constexpr uint32_t id = tc::idesc_bf16_f32(128, 64);
+        for (int s = 0; s < 4; ++s) tc::mma_bf16(tm + TM_A2, da + 2 * s, db + 2 * s, id, s > 0);
+    }
+    if (LAYER == 0) {
+        // message column sums: A = the pair tile read MN-major (M = 2 atoms of 64 features for pairs 0..63 | 64..127,
+        // K = 64 pairs), B = the selector
+        const uint64_t db = tc::smem_desc_sw128(a1 - E.M.A1 + E.M.Sel);
+        constexpr uint32_t id = tc::idesc_bf16_f32_major(128, 32, 1, 0);
 #pragma unroll
-                for (int s = 0; s < 4; ++s) tc::mma_bf16(tm + TM_A2, da + 2 * s, db + 2 * s, id, s > 0);
-            }
-            // message column sums: A = the pair tile read MN-major (M = 2 atoms of 64 features for pairs 0..63 | 64..127,
-            // K = 64 pairs), B = the selector
-            const uint64_t db = tc::smem_desc_sw128(a1 - E.M.A1 + E.M.Sel);
-            constexpr uint32_t id = tc::idesc_bf16_f32_major(128, 32, 1, 0);
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                tc::mma_bf16(tm + TM_SUM, tc::smem_desc(a1 + s * 2048, 8192, 1024, 2), db + 2 * s, id, (s > 0 || sum_accumulate) ? 1u : 0u);
-        }
-    });
+        for (int s = 0; s < 4; ++s) tc::mma_bf16(tm + TM_Z, tc::smem_desc(a1 + s * 2048, 8192, 1024, 2), db + 2 * s, id, s > 0);
+    }
+    E.commit(BM);
 }
-// D2 = [A2 | extras of this half] . W_half^T   (half 0: attention + rotation rows, half 1: torsion + translation)
-__device__ __forceinline__ void issue_mma2(const Engine& E, int half) {
-    E.issue([&] {
-        const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
-        const uint64_t db = tc::smem_desc_sw128(cta + E.M.Whb + half * 128 * 128);
-        const uint64_t dx = tc::smem_desc(cta + E.M.Wxb + half * 128 * 32, 128, 256, 0);
-        constexpr uint32_t id = tc::idesc_bf16_f32(128, 128);
+// hidden pre-activations of head h: D2 = [A2 | extras] . W_h^T  (h: 0 attention, 1 rotation, 2 torsion, 3 translation)
+__device__ __forceinline__ void mma_head(const Engine& E, uint32_t cta, uint32_t tm, int h, int dst) {
+    const uint64_t db = tc::smem_desc_sw128(cta + E.M.Whb + h * 64 * 128);
+    const uint64_t dx = tc::smem_desc(cta + E.M.Wxb + h * 64 * 32, 128, 256, 0);
+    constexpr uint32_t id = tc::idesc_bf16_f32(128, 64);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D2, tm + TM_A2 + 8 * s, db + 2 * s, id, s > 0);
-        tc::mma_bf16_ts(tm + TM_D2, tm + (half == 0 ? TM_XA : TM_XB), dx, id, 1);
-    });
+    for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + dst, tm + TM_A2 + 8 * s, db + 2 * s, id, s > 0);
+    tc::mma_bf16_ts(tm + dst, tm + (h < 2 ? TM_XA : TM_XB), dx, id, 1);
 }
-// D3 (+)= A3 . W3^T.  Half 0: A3 = [att hi | att lo | rot] (96 columns) -> att hi.W hi + att lo.W hi + att hi.W lo + rot;
-// half 1: A3 = [tor | trn] (64 columns)
-__device__ __forceinline__ void issue_mma3(const Engine& E, int half) {
-    E.issue([&] {
-        constexpr uint32_t id = tc::idesc_bf16_f32(128, 16);
-        const uint32_t w3 = Engine::opaque(E.smem_u) + E.M.W3b, tm = Engine::opaque(E.tmem);
-        if (half == 0) {
+// second layer of head h on its packed hidden units: D3 (+)= A3 . W3_h^T  (W3 blocks: 0 att hi, 1 rot, 2 tor, 3 trn, 4 att lo)
+__device__ __forceinline__ void mma_second(const Engine& E, uint32_t cta, uint32_t tm, int h, int src) {
+    constexpr uint32_t id = tc::idesc_bf16_f32(128, 16);
+    const uint32_t w3 = cta + E.M.W3b;
+    if (h == 0) {   // attention: hi.W hi + lo.W hi + hi.W lo
 #pragma unroll
-            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + TM_D2 + 8 * s, tc::smem_desc_sw128(w3) + 2 * s, id, s > 0);
+        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + src + 8 * s, tc::smem_desc_sw128(w3) + 2 * s, id, s > 0);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + TM_D2 + 32 + 8 * s, tc::smem_desc_sw128(w3) + 2 * s, id, 1);
+        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + src + 32 + 8 * s, tc::smem_desc_sw128(w3) + 2 * s, id, 1);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + TM_D2 + 8 * s, tc::smem_desc_sw128(w3 + 4 * 2048) + 2 * s, id, 1);
+        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + src + 8 * s, tc::smem_desc_sw128(w3 + 4 * 2048) + 2 * s, id, 1);
+    } else {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + TM_D2 + 64 + 8 * s, tc::smem_desc_sw128(w3 + 2048) + 2 * s, id, 1);
-        } else {
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                tc::mma_bf16_ts(tm + TM_D3, tm + TM_D2 + 8 * s, tc::smem_desc_sw128(w3 + (2 + (s >> 2)) * 2048) + 2 * (s & 3), id, 1);
-        }
-    });
+        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + src + 8 * s, tc::smem_desc_sw128(w3 + h * 2048) + 2 * s, id, 1);
+    }
 }
 
 // extras of the (attention, rotation) half for this pair
@@ -394,7 +382,8 @@ __device__ __forceinline__ void pair_extras(const Engine& E, const PairRef& pr, 
     const float nd2 = -(rx * rx + ry * ry + rz * rz);               // attention input -d2 (model.py:238)
     const float dq = qdot(qi, qj);
     const float qd = dq * dq;                                       // (q_i . q_j)^2 (model.py:239)
-    const Quat lq = qmul(qinv(qj), qmul(qi, qj));                   // local quaternion (model.py:283-287)
+    const float in2 = __fdividef(1.0f, qdot(qj, qj));
+    const Quat lq = qmul(Quat{qj.w * in2, -qj.x * in2, -qj.y * in2, -qj.z * in2}, qmul(qi, qj));   // local quaternion (model.py:283-287)
     const float dh = tc::bf16_round(nd2), qh = tc::bf16_round(qd);
     xa[0] = tc::pack_bf16x2(dh, nd2 - dh);
     xa[1] = tc::pack_bf16x2(dh, qh);
@@ -429,39 +418,38 @@ __device__ __forceinline__ void epilogue1(const Engine& E, const PairRef& pr, co
     tc::tmem_st16(E.tmem + E.lane_base + TM_XA, xs);
 }
 
-// D2 (128 columns) -> relu -> packed bf16x2 in place.  Half 0: attention units as hi + lo (64 columns) then rotation
-// (32 columns); half 1: torsion, translation (64 columns).  Every store lands on columns this thread has already read.
-template <int HALF>
-__device__ __forceinline__ void epilogue2(const Engine& E) {
+// hidden units of one head (64 columns) -> relu -> packed bf16x2 in place (32 columns)
+__device__ __forceinline__ void epilogue2(const Engine& E, int buf) {
+    uint32_t v0[32], v1[32];
+    tc::tmem_ld32_nowait(E.tmem + E.lane_base + buf, v0);
+    tc::tmem_ld32_nowait(E.tmem + E.lane_base + buf + 32, v1);
+    tc::tmem_wait_ld();
+    uint32_t pk[32];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        uint32_t v0[32], v1[32];
-        tc::tmem_ld32_nowait(E.tmem + E.lane_base + TM_D2 + 64 * q, v0);
-        tc::tmem_ld32_nowait(E.tmem + E.lane_base + TM_D2 + 64 * q + 32, v1);
-        tc::tmem_wait_ld();
-        uint32_t pk[32];
-        if (HALF == 0 && q == 0) {
-            uint32_t pl[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                // hi = relu(x) truncated to bf16 (a byte permute), lo = bf16(relu(x) - hi): ~16 mantissa bits together
-                const uint32_t* v = c < 16 ? v0 : v1;
-                const float x0 = fmaxf(__uint_as_float(v[2 * (c & 15)]), 0.0f), x1 = fmaxf(__uint_as_float(v[2 * (c & 15) + 1]), 0.0f);
-                const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
-                pk[c] = __byte_perm(u0, u1, 0x7632);
-                pl[c] = tc::pack_bf16x2(x0 - __uint_as_float(u0 & 0xFFFF0000u), x1 - __uint_as_float(u1 & 0xFFFF0000u));
-            }
-            tc::tmem_st32(E.tmem + E.lane_base + TM_D2, pk);
-            tc::tmem_st32(E.tmem + E.lane_base + TM_D2 + 32, pl);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                pk[c] = tc::pack_bf16x2_relu(__uint_as_float(v0[2 * c]), __uint_as_float(v0[2 * c + 1]));
-                pk[16 + c] = tc::pack_bf16x2_relu(__uint_as_float(v1[2 * c]), __uint_as_float(v1[2 * c + 1]));
-            }
-            tc::tmem_st32(E.tmem + E.lane_base + TM_D2 + (HALF == 0 ? 64 : 32 * q), pk);
-        }
+    for (int c = 0; c < 16; ++c) {
+        pk[c] = tc::pack_bf16x2_relu(__uint_as_float(v0[2 * c]), __uint_as_float(v0[2 * c + 1]));
+        pk[16 + c] = tc::pack_bf16x2_relu(__uint_as_float(v1[2 * c]), __uint_as_float(v1[2 * c + 1]));
     }
+    tc::tmem_st32(E.tmem + E.lane_base + buf, pk);
+}
+// attention head: its hidden units see -d2 and reach 1e2..1e3, so they go to the second layer as hi + lo
+// (hi = relu(x) truncated to bf16 by a byte permute, lo = bf16(relu(x) - hi): ~16 mantissa bits): 64 columns in place
+__device__ __forceinline__ void epilogue2_att(const Engine& E, int buf) {
+    uint32_t v0[32], v1[32];
+    tc::tmem_ld32_nowait(E.tmem + E.lane_base + buf, v0);
+    tc::tmem_ld32_nowait(E.tmem + E.lane_base + buf + 32, v1);
+    tc::tmem_wait_ld();
+    uint32_t pk[32], pl[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const uint32_t* v = c < 16 ? v0 : v1;
+        const float x0 = fmaxf(__uint_as_float(v[2 * (c & 15)]), 0.0f), x1 = fmaxf(__uint_as_float(v[2 * (c & 15) + 1]), 0.0f);
+        const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
+        pk[c] = __byte_perm(u0, u1, 0x7632);
+        pl[c] = tc::pack_bf16x2(x0 - __uint_as_float(u0 & 0xFFFF0000u), x1 - __uint_as_float(u1 & 0xFFFF0000u));
+    }
+    tc::tmem_st32(E.tmem + E.lane_base + buf, pk);
+    tc::tmem_st32(E.tmem + E.lane_base + buf + 32, pl);
 }
 
 // D3 -> per-pair outputs: logit, global delta quaternion, delta angles, scale * (x_i - x_j)   (model.py:243-331)
@@ -635,7 +623,7 @@ __device__ inline ComplexInfo setup_engine(const Engine& E, int b, bool layer1) 
             I[IN_POCKET + Kpad + 3] = c0;
         }
     }
-    E.sync();
+    E.sync_all();   // + the issuing warp, which reads the lists' counts
     ComplexInfo ci;
     ci.L = I[IN_POCKET + Kpad + 0];
     ci.nv = I[IN_POCKET + Kpad + 1];
@@ -644,19 +632,34 @@ __device__ inline ComplexInfo setup_engine(const Engine& E, int b, bool layer1) 
     return ci;
 }
 
+// tiles and message-only tiles of one complex, identically derived by the compute threads and the issuing warp
+struct ComplexPlan {
+    int L, W, rows_per_group, msg_w, msg_tiles;
+};
+__device__ __forceinline__ ComplexPlan plan_complex(const ComplexInfo& ci, int cap_pairs, bool layer1) {
+    ComplexPlan p;
+    p.L = ci.L;
+    p.W = (ci.L - 1) + ci.nv;
+    p.rows_per_group = p.W > 0 ? max(1, cap_pairs / p.W) : kN;
+    // message-only pairs (model.py:151 sums over ALL K slots): self, masked peptide slots, masked pocket slots with their
+    // own features, and one shared message for the c0 zero-feature masked pocket slots (multiplicity <= 256 stays exact in bf16)
+    const int nshared = ci.c0 > 256 ? 2 : (ci.c0 > 0 ? 1 : 0);
+    p.msg_w = 1 + (kN - ci.L) + ci.nx + nshared;
+    p.msg_tiles = layer1 ? (ci.L * p.msg_w + kTile - 1) / kTile : 0;
+    return p;
+}
+
 template <int LAYER>
 __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const Map M = make_map(a.Kpad, a.cap_pairs, a.aj_rows);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int eng = tid >> 7, et = tid & 127;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + M.Bar);
 
     if (warp == 0) tc::tmem_alloc(reinterpret_cast<uint32_t*>(smem + M.TmemPtr), 512);
     if (tid == 32) {
-        tc::mbar_init(bars + 0, 1);
-        tc::mbar_init(bars + 1, 1);
+        for (int k = 0; k < 4 * kEngines; ++k) tc::mbar_init(bars + k, 1);
         tc::mbar_fence_init();
     }
     {   // the layer's operand tiles, prepared by weight_image_kernel: one coalesced copy
@@ -670,165 +673,241 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
     tc::fence_after_thread_sync();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + M.TmemPtr);
 
-    Engine E{smem, smem + M.cta_bytes + eng * M.eng_bytes, M, a, eng, et, tmem_base + (uint32_t)(eng * kEngCols),
-             (uint32_t)(((et >> 5) & 3) * 32) << 16, bars + eng, 0u, tc::smem_u32(smem),
-             tc::smem_u32(smem + M.cta_bytes + eng * M.eng_bytes)};
-    const int* I = E.ints();
-    int ts_n = 0;
-    const bool ts_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    if (tid >= kComputeThreads) {
+        // =============================== MMA issue: warp 8 -> engine 0, warp 9 -> engine 1 ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
+        const int eng = warp - kComputeThreads / 32;
+        if (eng < kEngines) {
+            Engine E{smem, smem + M.cta_bytes + eng * M.eng_bytes, M, a, eng, kEngThreads, tmem_base + (uint32_t)(eng * kEngCols), 0u,
+                     bars + 4 * eng, 0u, tc::smem_u32(smem), tc::smem_u32(smem + M.cta_bytes + eng * M.eng_bytes), 0u};
+            const int* I = E.ints();
+            for (int b = blockIdx.x * kEngines + eng; b < a.B; b += gridDim.x * kEngines) {
+                E.sync_all();   // the compute threads have set the complex up
+                ComplexInfo ci;
+                ci.L = I[IN_POCKET + a.Kpad + 0];
+                ci.nv = I[IN_POCKET + a.Kpad + 1];
+                ci.nx = I[IN_POCKET + a.Kpad + 2];
+                ci.c0 = I[IN_POCKET + a.Kpad + 3];
+                const ComplexPlan cp = plan_complex(ci, a.cap_pairs, LAYER == 0);
+                for (int row0 = 0; row0 < cp.L; row0 += cp.rows_per_group) {
+                    const int ntiles = (min(cp.rows_per_group, cp.L - row0) * cp.W + kTile - 1) / kTile;
+                    for (int t = 0; t < ntiles; ++t) {
+                        E.serve([&] { mma_first<LAYER>(E, true); });
+                        E.serve([&] {
+                            const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
+                            mma_head(E, cta, tm, 0, TM_X); E.commit(BX);
+                            mma_head(E, cta, tm, 1, TM_Y); E.commit(BY);
+                            mma_head(E, cta, tm, 2, TM_Z); E.commit(BZ);
+                        });
+                        E.serve([&] {
+                            const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
+                            mma_second(E, cta, tm, 0, TM_X); E.commit(BX);
+                        });
+                        E.serve([&] {   // the compute threads have seen the attention second layer complete: X is free
+                            const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
+                            mma_second(E, cta, tm, 1, TM_Y);
+                            mma_head(E, cta, tm, 3, TM_X); E.commit(BX);
+                        });
+                        E.serve([&] {
+                            const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
+                            mma_second(E, cta, tm, 2, TM_Z); E.commit(BZ);
+                        });
+                        E.serve([&] {
+                            const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
+                            mma_second(E, cta, tm, 3, TM_X); E.commit(BM);
+                        });
+                    }
+                }
+                for (int t = 0; t < cp.msg_tiles; ++t) E.serve([&] { mma_first<LAYER>(E, false); });
+            }
+        }
+    } else {
+        // ======================================= compute: one thread per pair row =======================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
+        const int eng = tid >> 7, et = tid & 127;
+        Engine E{smem, smem + M.cta_bytes + eng * M.eng_bytes, M, a, eng, et, tmem_base + (uint32_t)(eng * kEngCols),
+                 (uint32_t)(((et >> 5) & 3) * 32) << 16, bars + 4 * eng, 0u, tc::smem_u32(smem),
+                 tc::smem_u32(smem + M.cta_bytes + eng * M.eng_bytes), 0u};
+        const int* I = E.ints();
+        int ts_n = 0;
+        const bool ts_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
 #define PMHC_TS() do { if (ts_on && ts_n < 120) a.dbg[ts_n++] = clock64(); } while (0)
-    PMHC_TS();
-
-    for (int b = blockIdx.x * kEngines + eng; b < a.B; b += gridDim.x * kEngines) {
         PMHC_TS();
-        const ComplexInfo ci = setup_engine(E, b, LAYER == 0);
-        PMHC_TS();
-        const int L = ci.L;
-        const int W = (L - 1) + ci.nv;
-        float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
-        for (int idx = et; idx < (kN - L) * 21; idx += kEngThreads) {   // padded rows: pass-through (T4)
-            const int s = idx / 21, c = idx - s * 21;
-            const int i = I[IN_PEPX + s];
-            if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = a.frames_in[((size_t)b * kN + i) * 7 + c];
-            else a.tors_out[((size_t)b * kN + i) * 14 + (c - 7)] = a.tors_in[((size_t)b * kN + i) * 14 + (c - 7)];
-        }
-        bool sum_started = false;
 
-        const int rows_per_group = W > 0 ? max(1, a.cap_pairs / W) : kN;
-        for (int row0 = 0; row0 < L; row0 += rows_per_group) {
-            const int nrows = min(rows_per_group, L - row0);
-            const int gpairs = nrows * W;
-            const int ntiles = (gpairs + kTile - 1) / kTile;
-            // The A1 tile of tile t + 1 is staged while the tensor core runs the first head contraction of tile t.
-            // (row, entry) of this thread's pair advance by 128 pairs per tile without a division
-            const int adv_q = W > 0 ? kTile / W : 0, adv_r = W > 0 ? kTile - adv_q * W : 0;
-            int cur_rl = W > 0 ? et / W : 0, cur_e = W > 0 ? et - cur_rl * W : 0;
-            auto decode = [&](int t) {
-                PairRef p;
-                p.active = t * kTile + et < gpairs;
-                const int rl = p.active ? cur_rl : 0, e = p.active ? cur_e : 0;
-                const int r = row0 + rl;
-                p.i = I[IN_ROWS + r];
-                p.j = e < L - 1 ? I[IN_ROWS + (e < r ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
-                cur_rl += adv_q;
-                cur_e += adv_r;
-                if (cur_e >= W) { cur_e -= W; ++cur_rl; }
-                return p;
-            };
-            PairRef pr = decode(0);
-            if (ntiles > 0) {
-                if (LAYER == 0) write_sel(E, pr, 1.0f);
-                stage_a1<LAYER>(E, pr, b);
-            }
-            for (int t = 0; t < ntiles; ++t) {
-                PMHC_TS();   // 0
-                tc::fence_before_thread_sync();
-                E.sync();
-                PMHC_TS();   // 1 synced
-                issue_mma1<LAYER>(E, true, sum_started);
-                sum_started = true;
-                PMHC_TS();   // 2 issued
-                uint32_t xa[8];
-                pair_extras(E, pr, xa);
-                PMHC_TS();   // 3 extras
-                E.wait_mma();
-                PMHC_TS();   // 4 mma1 done
-                if (LAYER == 0) zero_sel(E);
-                epilogue1(E, pr, xa);
-                PMHC_TS();   // 5 ep1
-                E.publish_tmem();
-                issue_mma2(E, 0);
-                PMHC_TS();   // 6 published + issued
-                PairRef nxt = pr;
-                if (t + 1 < ntiles) {
-                    nxt = decode(t + 1);
-                    if (LAYER == 0) write_sel(E, nxt, 1.0f);
-                    stage_a1<LAYER>(E, nxt, b);
-                }
-                PMHC_TS();   // 7 next tile staged
-                E.wait_mma();
-                PMHC_TS();   // 8 mma2a done
-                epilogue2<0>(E);
-                PMHC_TS();   // 9 ep2a
-                E.publish_tmem();
-                issue_mma3(E, 0);
-                E.wait_mma();          // A3 of the first half has been consumed: its columns may be overwritten
-                PMHC_TS();   // 10 mma3a done
-                issue_mma2(E, 1);
-                E.wait_mma();
-                PMHC_TS();   // 11 mma2b done
-                epilogue2<1>(E);
-                PMHC_TS();   // 12 ep2b
-                E.publish_tmem();
-                issue_mma3(E, 1);
-                E.wait_mma();
-                PMHC_TS();   // 13 mma3b done
-                epilogue3(E, pr, t * kTile + et, lsave);
-                PMHC_TS();   // 14 ep3
-                pr = nxt;
-            }
-            E.sync();
+        for (int b = blockIdx.x * kEngines + eng; b < a.B; b += gridDim.x * kEngines) {
             PMHC_TS();
-            finalize_rows_engine(E, b, row0, nrows, W);
-            E.sync();
+            const ComplexInfo ci = setup_engine(E, b, LAYER == 0);
             PMHC_TS();
-        }
-
-        if (LAYER == 0) {
-            // message-only pairs (model.py:151 sums over ALL K slots): self, masked peptide slots, masked pocket slots
-            // with their own features, and one shared message for the c0 zero-feature masked pocket slots
-            const int npx = kN - L;
-            const int nshared = ci.c0 > 256 ? 2 : (ci.c0 > 0 ? 1 : 0);   // multiplicities stay exact in bf16 (<= 256)
-            const int W2 = 1 + npx + ci.nx + nshared;
-            const int total = L * W2;
-            for (int tile_base = 0; tile_base < total; tile_base += kTile) {
-                const int gp0 = tile_base + et;
-                const bool act = gp0 < total;
-                const int gp = act ? gp0 : tile_base;
-                const int rl = gp / W2, e = gp - rl * W2;
-                PairRef pr;
-                pr.i = I[IN_ROWS + rl];
-                pr.active = act;
-                float mult = 1.0f;
-                if (e == 0) pr.j = pr.i;
-                else if (e <= npx) pr.j = I[IN_PEPX + e - 1];
-                else if (e <= npx + ci.nx) pr.j = I[IN_POCKET + a.Kpad - 1 - (e - npx - 1)];
-                else {
-                    pr.j = -1;
-                    const int which = e - (npx + ci.nx + 1);
-                    mult = (float)(which == 0 ? min(ci.c0, 256) : ci.c0 - 256);
-                }
-                write_sel(E, pr, mult);
-                stage_a1<LAYER>(E, pr, b);
-                tc::fence_before_thread_sync();
-                E.sync();
-                issue_mma1<LAYER>(E, false, sum_started);
-                sum_started = true;
-                E.wait_mma();
-                zero_sel(E);
+            const ComplexPlan cp = plan_complex(ci, a.cap_pairs, LAYER == 0);
+            const int L = cp.L, W = cp.W;
+            float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
+            for (int idx = et; idx < (kN - L) * 21; idx += kEngThreads) {   // padded rows: pass-through (T4)
+                const int s = idx / 21, c = idx - s * 21;
+                const int i = I[IN_PEPX + s];
+                if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = a.frames_in[((size_t)b * kN + i) * 7 + c];
+                else a.tors_out[((size_t)b * kN + i) * 14 + (c - 7)] = a.tors_in[((size_t)b * kN + i) * 14 + (c - 7)];
             }
-            // Dsum[64 h + f][16 h' + i]: the blocks h' == h hold sum over the tile halves; add the two halves
-            float* scr = reinterpret_cast<float*>(E.es + M.Out);
-            if (L > 0) {
-                float s[16];
-                tc::tmem_ld16(E.tmem + E.lane_base + TM_SUM + 16 * (et >> 6), s);
+            // layer 1: this thread's share of the message column sums, sum_j m1_ij: thread 64 h + f holds feature f of
+            // rows i = 0..15 summed over the tile halves h (the tensor core delivers them per tile in buffer Z)
+            float ssum[kN];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) scr[((et >> 6) * 16 + i) * 64 + (et & 63)] = s[i];
+            for (int i = 0; i < kN; ++i) ssum[i] = 0.0f;
+            auto add_tile_sums = [&] {
+                float v[16];
+                tc::tmem_ld16(E.tmem + E.lane_base + TM_Z + 16 * (et >> 6), v);
+#pragma unroll
+                for (int i = 0; i < kN; ++i) ssum[i] += v[i];
+            };
+
+            for (int row0 = 0; row0 < L; row0 += cp.rows_per_group) {
+                const int nrows = min(cp.rows_per_group, L - row0);
+                const int gpairs = nrows * W;
+                const int ntiles = (gpairs + kTile - 1) / kTile;
+                // Pair order inside a row group: the pocket neighbours of all its rows first, then the peptide neighbours
+                // (they need the relative-position term, a divergent extra step: keeping them together confines it to a few
+                // warps).  The output slot stays row-major, rl * W + e.  (row, entry) of this thread's pocket pair advance by
+                // 128 pairs per tile without a division.
+                const int nvp = W - (L - 1), npocket = nrows * nvp;
+                const int adv_q = nvp > 0 ? kTile / nvp : 0, adv_r = nvp > 0 ? kTile - adv_q * nvp : 0;
+                int cur_rl = nvp > 0 ? et / nvp : 0, cur_e = nvp > 0 ? et - cur_rl * nvp : 0;
+                int slot = 0, nslot = 0;
+                auto decode = [&](int t) {
+                    PairRef p;
+                    const int gp = t * kTile + et;
+                    p.active = gp < gpairs;
+                    int rl = 0, e = 0;
+                    if (gp < npocket) {
+                        rl = cur_rl;
+                        e = (L - 1) + cur_e;
+                        cur_rl += adv_q;
+                        cur_e += adv_r;
+                        if (cur_e >= nvp) { cur_e -= nvp; ++cur_rl; }
+                    } else if (p.active) {
+                        const int g2 = gp - npocket;
+                        rl = g2 / (L - 1);
+                        e = g2 - rl * (L - 1);
+                    } else if (nvp == 0) {
+                        e = 0;   // no pocket: pair (row0, first peptide neighbour) stands in for the idle lanes
+                    } else {
+                        e = L - 1;
+                    }
+                    const int r = row0 + rl;
+                    p.i = I[IN_ROWS + r];
+                    p.j = e < L - 1 ? I[IN_ROWS + (e < r ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
+                    nslot = rl * W + e;
+                    return p;
+                };
+                PairRef pr = decode(0);
+                slot = nslot;
+                if (ntiles > 0) {
+                    if (LAYER == 0) write_sel(E, pr, 1.0f);
+                    stage_a1<LAYER>(E, pr, b);
+                }
+                // One tile = a chain of small MMAs issued by the engine's issuing warp on request.  The four heads go through
+                // three 64-column TMEM buffers (X, Y, Z), so the tensor core has the next head's contraction in flight while
+                // these threads convert the previous one; the pair tile of tile t + 1 is staged under the head contractions.
+                for (int t = 0; t < ntiles; ++t) {
+                    PMHC_TS();   // 0
+                    E.request();           // message layer 2 (+ layer 1: message column sums)
+                    uint32_t xa[8];
+                    pair_extras(E, pr, xa);
+                    PMHC_TS();   // 1 extras
+                    E.wait(BM);
+                    PMHC_TS();   // 2 D1 ready
+                    if (LAYER == 0) {
+                        clear_sel(E, pr);
+                        add_tile_sums();
+                    }
+                    epilogue1(E, pr, xa);
+                    E.request();           // attention -> X, rotation -> Y, torsion -> Z
+                    PMHC_TS();   // 3 ep1
+                    PairRef nxt = pr;
+                    if (t + 1 < ntiles) {
+                        nxt = decode(t + 1);
+                        PMHC_TS();   // decode
+                        if (LAYER == 0) write_sel(E, nxt, 1.0f);
+                        stage_a1<LAYER, false>(E, nxt, b);
+                        PMHC_TS();   // stores issued
+                        tc::fence_proxy_async_smem();
+                    } else { PMHC_TS(); PMHC_TS(); }
+                    PMHC_TS();   // 4 next tile staged
+                    E.wait(BX);
+                    PMHC_TS();   // 5 attention hidden ready
+                    epilogue2_att(E, TM_X);
+                    E.request();           // attention second layer
+                    PMHC_TS();   // 6
+                    E.wait(BY);
+                    PMHC_TS();   // 7 rotation hidden ready
+                    epilogue2(E, TM_Y);
+                    E.wait(BX);            // attention second layer done: X is free
+                    E.request();           // rotation second layer, translation -> X
+                    PMHC_TS();   // 8
+                    E.wait(BZ);
+                    PMHC_TS();   // 9 torsion hidden ready
+                    epilogue2(E, TM_Z);
+                    E.wait(BX);            // translation hidden ready
+                    E.request();           // torsion second layer
+                    PMHC_TS();   // 10
+                    epilogue2(E, TM_X);
+                    E.wait(BZ);
+                    E.request();           // translation second layer
+                    PMHC_TS();   // 11
+                    E.wait(BM);
+                    PMHC_TS();   // 12 second layers done
+                    epilogue3(E, pr, slot, lsave);
+                    PMHC_TS();   // 13
+                    pr = nxt;
+                    slot = nslot;
+                }
+                E.sync();
+                finalize_rows_engine(E, b, row0, nrows, W);
+                E.sync();
             }
-            tc::fence_before_thread_sync();
+
+            if (LAYER == 0) {
+                const int npx = kN - L, W2 = cp.msg_w, total = L * W2;
+                for (int tile_base = 0; tile_base < total; tile_base += kTile) {
+                    const int gp0 = tile_base + et;
+                    const bool act = gp0 < total;
+                    const int gp = act ? gp0 : tile_base;
+                    const int rl = gp / W2, e = gp - rl * W2;
+                    PairRef pr;
+                    pr.i = I[IN_ROWS + rl];
+                    pr.active = act;
+                    float mult = 1.0f;
+                    if (e == 0) pr.j = pr.i;
+                    else if (e <= npx) pr.j = I[IN_PEPX + e - 1];
+                    else if (e <= npx + ci.nx) pr.j = I[IN_POCKET + a.Kpad - 1 - (e - npx - 1)];
+                    else {
+                        pr.j = -1;
+                        const int which = e - (npx + ci.nx + 1);
+                        mult = (float)(which == 0 ? min(ci.c0, 256) : ci.c0 - 256);
+                    }
+                    write_sel(E, pr, mult);
+                    stage_a1<LAYER>(E, pr, b);
+                    E.request();
+                    E.wait(BM);
+                    clear_sel(E, pr);
+                    add_tile_sums();
+                }
+                // thread 64 h + f holds the sums of tile half h: add the two halves through shared memory
+                float* scr = reinterpret_cast<float*>(E.es + M.Out);
+#pragma unroll
+                for (int i = 0; i < kN; ++i) scr[((et >> 6) * kN + i) * 64 + (et & 63)] = ssum[i];
+                E.sync();
+                for (int idx = et; idx < kN * kHid; idx += kEngThreads) {
+                    const int i = idx >> 6;
+                    const bool real = (E.es + M.Cls)[i] != 0;
+                    a.ssum_out[(size_t)b * kN * kHid + idx] = real ? scr[idx] + scr[kN * kHid + idx] : 0.0f;
+                }
+            }
             E.sync();
-            for (int idx = et; idx < kN * kHid; idx += kEngThreads) {
-                const int i = idx >> 6;
-                const bool real = (E.es + M.Cls)[i] != 0;
-                a.ssum_out[(size_t)b * kN * kHid + idx] = (real && L > 0) ? scr[idx] + scr[kN * kHid + idx] : 0.0f;
-            }
         }
-        E.sync();
+        PMHC_TS();
+        if (ts_on) a.dbg[127] = ts_n;
+#undef PMHC_TS
     }
 
-    PMHC_TS();
-    if (ts_on) a.dbg[127] = ts_n;
-#undef PMHC_TS
     tc::fence_before_thread_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, 512);

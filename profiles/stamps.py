@@ -24,7 +24,9 @@ with torch.no_grad():
     torch.cuda.synchronize()
     lib.pmhc_debug_set_stamps(ctypes.c_void_p(0))
 st = buf.cpu().tolist()
-names = ["sync", "issue1", "extras", "wait1", "ep1", "pub+iss2a", "stage_next", "wait2a", "ep2a", "mma3a", "mma2b", "ep2b", "mma3b", "ep3"]
+names = ["req+extras", "waitM", "sums+ep1+req", "decode", "stage_ldst", "stage_fence", "waitX", "ep2att+req", "waitY", "ep2rot+waitX+req", "waitZ", "ep2tor+waitX+req",
+         "ep2trn+waitZ+req", "waitM", "ep3"]
+NS = len(names) + 1
 for layer in (0, 1):
     s = st[128 * layer:128 * layer + 128]
     n = s[127]
@@ -34,9 +36,9 @@ for layer in (0, 1):
     # tiles: groups of 15 stamps starting at index 3
     i = 3
     tile = 0
-    while i + 14 < n and tile < 6:
-        d = [s[i + k + 1] - s[i + k] for k in range(14)]
-        print(f"  tile {tile}: total {s[i + 14] - s[i]:6d} | " + " ".join(f"{nm}={v}" for nm, v in zip(names, d)))
-        i += 15
+    while i + NS - 1 < n and tile < 5:
+        d = [s[i + k + 1] - s[i + k] for k in range(NS - 1)]
+        print(f"  tile {tile}: total {s[i + NS - 1] - s[i]:6d} | " + " ".join(f"{nm}={v}" for nm, v in zip(names, d)))
+        i += NS
         tile += 1
     print("  remaining stamps deltas:", [s[k + 1] - s[k] for k in range(i - 1, min(n - 1, i + 12))])
