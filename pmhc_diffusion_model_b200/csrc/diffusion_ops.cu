@@ -31,18 +31,35 @@ __device__ __forceinline__ void write_noise(float* fr, float* tors, float n0, fl
     }
 }
 
-// One residue's noise from the counter-based stream: counter = global residue index, 4 Philox blocks.
-__device__ __forceinline__ void philox_noise(uint64_t seed, uint64_t ctr, float* fr, float* tors) {
+// One residue's noise from the counter-based stream: counter = global residue index, 4 Philox blocks (a: the three
+// normals, b: Shoemake coordinates + torsion 0, c: torsions 1..4, d: torsions 5, 6).  Split by output part so that the
+// per-residue kernels and the 8-lanes-per-residue fused reverse step run the very same arithmetic.
+__device__ __forceinline__ void philox_frame_noise(uint64_t seed, uint64_t ctr, float* fr) {
     Philox4 a = philox4x32_10(ctr, 0, seed), b = philox4x32_10(ctr, 1, seed);
-    Philox4 c = philox4x32_10(ctr, 2, seed), d = philox4x32_10(ctr, 3, seed);
     // Box-Muller on (a0,a1) and (a2,a3)
     float r0 = sqrtf(-2.0f * logf(u32_to_unit(a.v[0]))), r1 = sqrtf(-2.0f * logf(u32_to_unit(a.v[2])));
     float s0, c0, s1, c1;
     sincosf(kTwoPi * u32_to_unit(a.v[1]), &s0, &c0);
     sincosf(kTwoPi * u32_to_unit(a.v[3]), &s1, &c1);
-    float ua[PMHC_NTORS] = {u32_to_unit(b.v[3]), u32_to_unit(c.v[0]), u32_to_unit(c.v[1]), u32_to_unit(c.v[2]),
-                            u32_to_unit(c.v[3]), u32_to_unit(d.v[0]), u32_to_unit(d.v[1])};
-    write_noise(fr, tors, r0 * c0, r0 * s0, r1 * c1, u32_to_unit(b.v[0]), u32_to_unit(b.v[1]), u32_to_unit(b.v[2]), ua);
+    Quat q = shoemake(u32_to_unit(b.v[0]), u32_to_unit(b.v[1]), u32_to_unit(b.v[2]));
+    store_frame(fr, q, (r0 * c0) * 5.0f, (r0 * s0) * 5.0f, (r1 * c1) * 5.0f);
+}
+__device__ __forceinline__ SinCos philox_torsion_noise(uint64_t seed, uint64_t ctr, int c) {
+    uint32_t u;
+    if (c == 0) u = philox4x32_10(ctr, 1, seed).v[3];
+    else if (c <= 4) u = philox4x32_10(ctr, 2, seed).v[c - 1];
+    else u = philox4x32_10(ctr, 3, seed).v[c - 5];
+    float a = u32_to_unit(u) * kTwoPi;
+    return SinCos{sinf(a), cosf(a)};
+}
+__device__ __forceinline__ void philox_noise(uint64_t seed, uint64_t ctr, float* fr, float* tors) {
+    philox_frame_noise(seed, ctr, fr);
+#pragma unroll
+    for (int c = 0; c < PMHC_NTORS; ++c) {
+        SinCos t = philox_torsion_noise(seed, ctr, c);
+        tors[2 * c] = t.s;
+        tors[2 * c + 1] = t.c;
+    }
 }
 
 __global__ void gen_noise_kernel(uint64_t seed, uint64_t first, int64_t n, float* __restrict__ frames,
@@ -90,24 +107,31 @@ struct ReverseCoef {
     float beta_t, beta_s, alpha_ts, var_ts, denom, sigma_t2s;
 };
 
-__device__ __forceinline__ void reverse_step_residue(const float* zf, const float* zt, const float* pf, const float* pt,
-                                                     const float* xf, const float* xt, const ReverseCoef& k,
-                                                     const float* sign_ref, float* of, float* ot) {
+__device__ __forceinline__ void reverse_step_frame(const float* zf, const float* pf, const float* xf, const ReverseCoef& k,
+                                                   const float* sign_ref, float* of) {
     Quat undo = qinv(qpartial(load_quat(pf), k.beta_t));
     Quat q = qunit(qmul(qpartial(load_quat(xf), k.beta_s), qmul(undo, load_quat(zf))));
     q = align_sign(q, sign_ref);
     float px = zf[4] / k.alpha_ts - (pf[4] * k.var_ts) / k.denom + k.sigma_t2s * xf[4];
     float py = zf[5] / k.alpha_ts - (pf[5] * k.var_ts) / k.denom + k.sigma_t2s * xf[5];
     float pz = zf[6] / k.alpha_ts - (pf[6] * k.var_ts) / k.denom + k.sigma_t2s * xf[6];
+    store_frame(of, q, px, py, pz);
+}
+__device__ __forceinline__ SinCos reverse_step_torsion(const SinCos& z, const SinCos& p, const SinCos& x, const ReverseCoef& k) {
+    return scmul(scpartial(x, k.beta_s), scmul(scinv(scpartial(p, k.beta_t)), z));
+}
+__device__ __forceinline__ void reverse_step_residue(const float* zf, const float* zt, const float* pf, const float* pt,
+                                                     const float* xf, const float* xt, const ReverseCoef& k,
+                                                     const float* sign_ref, float* of, float* ot) {
     float tmp[14];
 #pragma unroll
     for (int c = 0; c < PMHC_NTORS; ++c) {
-        SinCos z{zt[2 * c], zt[2 * c + 1]}, p{pt[2 * c], pt[2 * c + 1]}, x{xt[2 * c], xt[2 * c + 1]};
-        SinCos o = scmul(scpartial(x, k.beta_s), scmul(scinv(scpartial(p, k.beta_t)), z));
+        SinCos o = reverse_step_torsion(SinCos{zt[2 * c], zt[2 * c + 1]}, SinCos{pt[2 * c], pt[2 * c + 1]},
+                                        SinCos{xt[2 * c], xt[2 * c + 1]}, k);
         tmp[2 * c] = o.s;
         tmp[2 * c + 1] = o.c;
     }
-    store_frame(of, q, px, py, pz);
+    reverse_step_frame(zf, pf, xf, k, sign_ref, of);
 #pragma unroll
     for (int c = 0; c < 14; ++c) ot[c] = tmp[c];
 }
@@ -123,16 +147,28 @@ __global__ void remove_noise_kernel(const float* zf, const float* zt, const floa
 }
 
 // Fused noise draw + reverse step of the sampling loop: the step's fresh noise (optimizer.py:151) never leaves
-// registers.  Bit-identical to gen_noise_kernel followed by remove_noise_kernel.
-__global__ void reverse_step_philox_kernel(const float* zf, const float* zt, const float* __restrict__ pf,
-                                           const float* __restrict__ pt, uint64_t seed, uint64_t first, ReverseCoef k,
-                                           int64_t n, const float* __restrict__ sign_ref, float* of, float* ot) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// registers.  Eight lanes per residue (lane 0: the frame, lanes 1..7: one torsion each) so the long scalar chains
+// (Philox, acos, sincos) of a residue run side by side.  Bit-identical to gen_noise_kernel followed by remove_noise_kernel.
+__global__ void __launch_bounds__(128) reverse_step_philox_kernel(const float* zf, const float* zt, const float* __restrict__ pf,
+                                                                  const float* __restrict__ pt, uint64_t seed, uint64_t first, ReverseCoef k,
+                                                                  int64_t n, const float* __restrict__ sign_ref, float* of, float* ot) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = gid >> 3;
+    const int l = (int)(gid & 7);
     if (r >= n) return;
-    float xf[7], xt[14];
-    philox_noise(seed, first + (uint64_t)r, xf, xt);
-    reverse_step_residue(zf + r * 7, zt + r * 14, pf + r * 7, pt + r * 14, xf, xt, k,
-                         sign_ref ? sign_ref + r * 4 : nullptr, of + r * 7, ot + r * 14);
+    const uint64_t ctr = first + (uint64_t)r;
+    if (l == 0) {
+        float xf[7];
+        philox_frame_noise(seed, ctr, xf);
+        reverse_step_frame(zf + r * 7, pf + r * 7, xf, k, sign_ref ? sign_ref + r * 4 : nullptr, of + r * 7);
+    } else {
+        const int c = l - 1;
+        const SinCos x = philox_torsion_noise(seed, ctr, c);
+        const SinCos o = reverse_step_torsion(SinCos{zt[r * 14 + 2 * c], zt[r * 14 + 2 * c + 1]},
+                                              SinCos{pt[r * 14 + 2 * c], pt[r * 14 + 2 * c + 1]}, x, k);
+        ot[r * 14 + 2 * c] = o.s;
+        ot[r * 14 + 2 * c + 1] = o.c;
+    }
 }
 
 // get_loss + gradient (optimizer.py:38-79): one half-warp (16 lanes = 16 residues) per complex.
@@ -288,7 +324,7 @@ int launch_reverse_step_philox(const float* zf, const float* zt, const float* pf
     PMHC_REQUIRE(beta_t > 0.0 && beta_t < 1.0 && beta_s >= 0.0 && beta_s < beta_t,
                  "reverse step: need 0 <= beta_s < beta_t < 1 (got %f, %f)", beta_s, beta_t);
     ReverseCoef k = reverse_coef(beta_t, beta_s);
-    reverse_step_philox_kernel<<<grid_for(n, 128), 128, 0, stream>>>(zf, zt, pf, pt, seed, first, k, n, sign_ref, of, ot);
+    reverse_step_philox_kernel<<<grid_for(n * 8, 128), 128, 0, stream>>>(zf, zt, pf, pt, seed, first, k, n, sign_ref, of, ot);
     PMHC_CHECK_LAUNCH("reverse_step_philox");
     return 0;
 }

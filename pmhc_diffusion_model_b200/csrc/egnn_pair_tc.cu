@@ -51,13 +51,14 @@ constexpr int BM = 0, BX = 1, BY = 2, BZ = 3;
 
 struct PairArgs {
     int B, P, Kpad;
+    float t_over_T;
     const float* frames_in;          // [B,16,7]
     const float* tors_in;            // [B,16,14]
     const uint8_t* mask;             // [B,16]
     const float* pocket_frames;      // [B,P,7]
     const uint8_t* pocket_cls;       // [B,cls_stride]
     const __nv_bfloat16* pk_cache;   // [B,2,P,64] pocket rows of A_j per layer
-    const __nv_bfloat16* aij;        // [B,16,128] (A_i + b1 | A_j) of this layer's peptide nodes
+    const __nv_bfloat16* aij;        // [B,16,128] (A_i + b1 | A_j) of this layer's peptide nodes (layer 1: without the time term)
     const uint8_t* wimage;           // this layer's operand tiles in their shared-memory layout (weight_image_kernel)
     int cls_stride;                  // row stride of pocket_cls (P rounded up to 16)
     long long* dbg;                  // development: per-phase clock64 stamps of engine 0 / CTA 0 (nullable)
@@ -75,8 +76,9 @@ struct Map {
     int A1, Sel, AjS, Out, Ai, Q, X, Tors, TorsB, Ints, Cls, eng_bytes;   // per engine, byte offsets from the engine base
     int total_bytes;
 };
-// Misc floats: [0,16) second-layer biases in D3 order
-constexpr int MISC_B2ND = 0, MISC_FLOATS = 16;
+// Misc words: [0,16) second-layer biases (fp32) in D3 order; [16,80) layer 1: time column of message_mlp.0 as bf16x2
+// (A_i part | A_j part)
+constexpr int MISC_B2ND = 0, MISC_TIME = 16, MISC_FLOATS = 80;
 
 __host__ __device__ inline Map make_map(int Kpad, int cap_pairs, int aj_rows) {
     Map m;
@@ -202,6 +204,12 @@ __device__ inline void build_weight_image(uint8_t* smem, const Map& M, const flo
         else if (tid <= 11) v = params[param_offset(L, TOR2_B) + tid - 5];
         else if (tid == 12) v = params[param_offset(L, TRN2_B)];
         misc[MISC_B2ND + tid] = v;
+    }
+    if (LAYER == 0) {
+        for (int w = tid; w < 64; w += kThreads) {
+            const int k = 2 * (w & 31), col = w < 32 ? PMHC_NFEAT : H + PMHC_NFEAT;
+            reinterpret_cast<uint32_t*>(misc)[MISC_TIME + w] = tc::pack_bf16x2(msg0[k * ld1 + col], msg0[(k + 1) * ld1 + col]);
+        }
     }
 }
 
@@ -590,6 +598,22 @@ __device__ inline ComplexInfo setup_engine(const Engine& E, int b, bool layer1) 
     if (layer1) zero_sel(E);
     tc::cp_async_wait_all();
     E.sync();
+    if (layer1) {
+        // time feature (model.py:394): A_i += (t/T) w_ti, A_j += (t/T) w_tj on the 16 peptide rows, packed bf16x2 FMAs
+        const uint32_t* tw = reinterpret_cast<const uint32_t*>(E.smem + M.Misc) + MISC_TIME;
+        const uint32_t t2 = tc::pack_bf16x2(a.t_over_T, a.t_over_T);
+        uint4* ai = reinterpret_cast<uint4*>(E.es + M.Ai);
+        uint4* aj = reinterpret_cast<uint4*>(E.es + M.AjS);
+        for (int idx = et; idx < kN * 16; idx += kEngThreads) {
+            const int i = idx >> 4, ch = idx & 15;
+            uint4* p = ch < 8 ? ai + i * 8 + ch : aj + i * 8 + ((ch - 8) ^ (i & 7));
+            const uint32_t* w = tw + 4 * ch;
+            uint4 v = *p;
+            v.x = tc::fma_bf16x2(w[0], t2, v.x); v.y = tc::fma_bf16x2(w[1], t2, v.y);
+            v.z = tc::fma_bf16x2(w[2], t2, v.z); v.w = tc::fma_bf16x2(w[3], t2, v.w);
+            *p = v;
+        }
+    }
     {   // torsion extras rows: 14 bf16 (sin, cos) + (1, 1) for the biases
         const int i = et >> 3, w = et & 7;
         reinterpret_cast<uint32_t*>(E.es + M.TorsB)[et] = w < 7 ? tc::pack_bf16x2(Tors[i * 14 + 2 * w], Tors[i * 14 + 2 * w + 1]) : 0x3F803F80u;
@@ -918,13 +942,13 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
 // 411-412: pocket nodes carry no time feature; layer 2 sees the pocket's 22 features zero-padded to 64):
 //   pk_cache[b][l][p][k] = bf16( W1_l[k, H_l : H_l + 22] . pocket_features[b][p] )
 //   cls[b][p]            = 0 valid, 1 masked + all-zero features (one shared message), 2 masked + non-zero features
-//   pep1[b][i][0:64]     = b1 + W1_0[k, 0:22] . features[b][i]       (A_i of layer 1 without the time term)
-//   pep1[b][i][64:128]   =      W1_0[k, 23:45] . features[b][i]      (A_j)
+//   aij1[b][i][0:64]     = bf16( b1 + W1_0[k, 0:22] . features[b][i] )   (A_i of layer 1 without the time term, which the
+//   aij1[b][i][64:128]   = bf16(      W1_0[k, 23:45] . features[b][i] )   pair kernel adds per step)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) node_pre_kernel(const float* __restrict__ params, const float* __restrict__ feat,
                                                        const float* __restrict__ pocket_feat, const uint8_t* __restrict__ pocket_mask,
                                                        int P, int cls_stride, __nv_bfloat16* __restrict__ pk_cache,
-                                                       uint8_t* __restrict__ cls, float* __restrict__ pep1) {
+                                                       uint8_t* __restrict__ cls, __nv_bfloat16* __restrict__ aij1) {
     extern __shared__ __align__(16) float sp[];
     const int b = blockIdx.x, tid = threadIdx.x;
     constexpr int FS = 23;
@@ -979,35 +1003,17 @@ __global__ void __launch_bounds__(128) node_pre_kernel(const float* __restrict__
         }
         cls[(size_t)b * cls_stride + j] = c;
     }
-    for (int idx = tid; idx < kN * 128; idx += blockDim.x) {
-        const int i = idx >> 7, k = idx & 127;
-        float acc = k < 64 ? params[param_offset(0, MSG0_B) + k] : 0.0f;
+    for (int idx = tid; idx < kN * 64; idx += blockDim.x) {
+        const int i = idx >> 6, k = 2 * (idx & 63);
+        float acc[2];
 #pragma unroll
-        for (int c = 0; c < PMHC_NFEAT; ++c) acc = fmaf(wp[k * FS + c], nf[i * FS + c], acc);
-        pep1[(size_t)b * kN * 128 + idx] = acc;
-    }
-}
-
-// Layer 1's peptide projections at time t: aij1 = bf16(pep1 + (t/T) * time column of message_mlp.0) (model.py:394).
-__global__ void __launch_bounds__(256) pep_time_kernel(const float* __restrict__ params, const float* __restrict__ pep1, float t_over_T,
-                                                       int64_t n_nodes, __nv_bfloat16* __restrict__ aij1) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (node, 8 outputs)
-    if (idx >= n_nodes * 16) return;
-    const int k0 = (int)(idx & 15) * 8;
-    constexpr int ld1 = 2 * kH1 + kEdge;
-    const float* msg0 = params + param_offset(0, MSG0_W);
-    const float4* src = reinterpret_cast<const float4*>(pep1 + idx * 8);
-    const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
-    float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        for (int u = 0; u < 2; ++u) {
+            acc[u] = k + u < 64 ? params[param_offset(0, MSG0_B) + k + u] : 0.0f;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int k = k0 + u;
-        v[u] = fmaf(t_over_T, __ldg(msg0 + (k & 63) * ld1 + (k < 64 ? PMHC_NFEAT : kH1 + PMHC_NFEAT)), v[u]);
+            for (int c = 0; c < PMHC_NFEAT; ++c) acc[u] = fmaf(wp[(k + u) * FS + c], nf[i * FS + c], acc[u]);
+        }
+        reinterpret_cast<uint32_t*>(aij1)[(size_t)b * kN * 64 + idx] = tc::pack_bf16x2(acc[0], acc[1]);
     }
-    uint4 o;
-    o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
-    o.z = tc::pack_bf16x2(v[4], v[5]); o.w = tc::pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(aij1 + idx * 8) = o;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1019,7 +1025,7 @@ __global__ void __launch_bounds__(256) pep_time_kernel(const float* __restrict__
 //   [A_i | A_j] = o1 . [W1_i ; W1_j]^T (+ b1)      (layer 2's message_mlp.0 peptide blocks) -> bf16
 // ---------------------------------------------------------------------------------------------------------------
 struct NodeMidArgs {
-    const float* params;
+    const uint8_t* image;     // node_mid_image_kernel's output
     int B, P;
     float t_over_T;
     const float* ssum;        // [B,16,64]
@@ -1032,23 +1038,16 @@ struct NodeMidArgs {
 constexpr int NM_W2 = 0, NM_WF0 = 8192, NM_WF2 = 24576, NM_W1 = 32768, NM_BIAS = 49152, NM_BAR = 50432, NM_TPTR = 50448,
               NM_BYTES = 50464 + 1024;
 
-__global__ void __launch_bounds__(128, 1) node_mid_kernel(NodeMidArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + NM_BAR);
+// operand tiles + biases of node_mid_kernel in its shared-memory layout ([0, NM_BAR)), built once per batch / trajectory
+__global__ void __launch_bounds__(256) node_mid_image_kernel(const float* __restrict__ params, int P, uint8_t* __restrict__ smem) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     float* bias = reinterpret_cast<float*>(smem + NM_BIAS);   // [0,64) b2 * (16 + P) | f0b | f2b | b1(layer 2) | 64 zeros
-    if (warp == 0) tc::tmem_alloc(reinterpret_cast<uint32_t*>(smem + NM_TPTR), 512);
-    if (tid == 32) {
-        tc::mbar_init(bar, 1);
-        tc::mbar_fence_init();
-    }
-    const float* msg2 = a.params + param_offset(0, MSG2_W);
-    const float* f0w = a.params + param_offset(0, FEAT0_W);   // [64][23 + 64]: columns 0..22 node features (+time), 23.. message sum
-    const float* f2w = a.params + param_offset(0, FEAT2_W);
-    const float* w1 = a.params + param_offset(1, MSG0_W);     // [64][2*64 + 31]
+    const float* msg2 = params + param_offset(0, MSG2_W);
+    const float* f0w = params + param_offset(0, FEAT0_W);   // [64][23 + 64]: columns 0..22 node features (+time), 23.. message sum
+    const float* f2w = params + param_offset(0, FEAT2_W);
+    const float* w1 = params + param_offset(1, MSG0_W);     // [64][2*64 + 31]
     constexpr int ldf = kH1 + kHid, ld1 = 2 * kH2 + kEdge;
-    for (int idx = tid; idx < 64 * 32; idx += 128) {
+    for (int idx = tid; idx < 64 * 32; idx += nthr) {
         const int n = idx >> 5, k = (idx & 31) * 2;
         *reinterpret_cast<uint32_t*>(smem + NM_W2 + tc::sw128_offset(n, k)) = tc::pack_bf16x2(msg2[n * 64 + k], msg2[n * 64 + k + 1]);
         *reinterpret_cast<uint32_t*>(smem + NM_WF2 + tc::sw128_offset(n, k)) = tc::pack_bf16x2(f2w[n * 64 + k], f2w[n * 64 + k + 1]);
@@ -1061,17 +1060,35 @@ __global__ void __launch_bounds__(128, 1) node_mid_kernel(NodeMidArgs a) {
         else if (k == PMHC_NFEAT) v0 = v1 = f0w[n * ldf + PMHC_NFEAT];                   // columns 22, 23: t/T hi, t/T lo
         *reinterpret_cast<uint32_t*>(smem + NM_WF0 + 8192 + tc::sw128_offset(n, k)) = tc::pack_bf16x2(v0, v1);
     }
-    for (int idx = tid; idx < 128 * 32; idx += 128) {
+    for (int idx = tid; idx < 128 * 32; idx += nthr) {
         const int n = idx >> 5, k = (idx & 31) * 2;
         const float* src = w1 + (n & 63) * ld1 + (n < 64 ? 0 : kH2) + k;
         *reinterpret_cast<uint32_t*>(smem + NM_W1 + tc::sw128_offset(n, k)) = tc::pack_bf16x2(src[0], src[1]);
     }
     if (tid < 64) {
-        bias[tid] = a.params[param_offset(0, MSG2_B) + tid] * (float)(kN + a.P);
-        bias[64 + tid] = a.params[param_offset(0, FEAT0_B) + tid];
-        bias[128 + tid] = a.params[param_offset(0, FEAT2_B) + tid];
-        bias[192 + tid] = a.params[param_offset(1, MSG0_B) + tid];
+        bias[tid] = params[param_offset(0, MSG2_B) + tid] * (float)(kN + P);
+        bias[64 + tid] = params[param_offset(0, FEAT0_B) + tid];
+        bias[128 + tid] = params[param_offset(0, FEAT2_B) + tid];
+        bias[192 + tid] = params[param_offset(1, MSG0_B) + tid];
         bias[256 + tid] = 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(128, 1) node_mid_kernel(NodeMidArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + NM_BAR);
+    const float* bias = reinterpret_cast<const float*>(smem + NM_BIAS);
+    if (warp == 0) tc::tmem_alloc(reinterpret_cast<uint32_t*>(smem + NM_TPTR), 512);
+    if (tid == 32) {
+        tc::mbar_init(bar, 1);
+        tc::mbar_fence_init();
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.image);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (int idx = tid; idx < NM_BAR / 16; idx += 128) dst[idx] = __ldg(src + idx);
     }
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
@@ -1214,12 +1231,12 @@ long long* g_tc2_dbg = nullptr;   // development hook (pmhc_debug_set_stamps)
 
 struct Tc2Workspace {
     __nv_bfloat16* pk_cache;   // [B,2,P,64]
-    float* pep1;               // [B,16,128]
     float* ssum;               // [B,16,64]
     __nv_bfloat16* aij1;       // [B,16,128]
     __nv_bfloat16* aij2;       // [B,16,128]
     uint8_t* cls;              // [B,cls_stride]
     uint8_t* wimage;           // [2][image_bytes]
+    uint8_t* nm_image;         // node_mid operand tiles
     int cls_stride, image_bytes;
     size_t bytes;
 };
@@ -1231,12 +1248,12 @@ Tc2Workspace carve_tc2(void* base, int B, int P) {
     w.cls_stride = (P + 15) & ~15;
     w.image_bytes = tc2::make_map(32, 256, kN).Bar;
     w.pk_cache = (__nv_bfloat16*)take((size_t)B * 2 * P * kHid * 2);
-    w.pep1 = (float*)take((size_t)B * kN * 128 * 4);
     w.ssum = (float*)take((size_t)B * kN * kHid * 4);
     w.aij1 = (__nv_bfloat16*)take((size_t)B * kN * 128 * 2);
     w.aij2 = (__nv_bfloat16*)take((size_t)B * kN * 128 * 2);
     w.cls = (uint8_t*)take((size_t)B * w.cls_stride);
     w.wimage = (uint8_t*)take((size_t)2 * w.image_bytes);
+    w.nm_image = (uint8_t*)take((size_t)tc2::NM_BAR);
     w.bytes = o;
     return w;
 }
@@ -1290,6 +1307,8 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
         PMHC_CHECK_LAUNCH("weight_image");
         tc2::weight_image_kernel<1><<<8, 256, 0, stream>>>(params, w.wimage + w.image_bytes);
         PMHC_CHECK_LAUNCH("weight_image");
+        tc2::node_mid_image_kernel<<<8, 256, 0, stream>>>(params, P, w.nm_image);
+        PMHC_CHECK_LAUNCH("node_mid_image");
         const size_t smem = (size_t)(((P * 23 + 3) & ~3) + 2 * kHid * 23 + kN * 23 + 1 + 128 * 23) * sizeof(float);
         static bool configured = false;
         if (!configured) {
@@ -1298,16 +1317,12 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
             configured = true;
         }
         tc2::node_pre_kernel<<<B, 128, smem, stream>>>(params, bt->features, bt->pocket_features, bt->pocket_mask, P, w.cls_stride,
-                                                       w.pk_cache, w.cls, w.pep1);
+                                                       w.pk_cache, w.cls, w.aij1);
         PMHC_CHECK_LAUNCH("node_pre");
-    }
-    {
-        const int64_t n_items = (int64_t)B * kN * 16;
-        tc2::pep_time_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, stream>>>(params, w.pep1, t_over_T, (int64_t)B * kN, w.aij1);
-        PMHC_CHECK_LAUNCH("pep_time");
     }
     tc2::PairArgs a{};
     a.B = B; a.P = P; a.Kpad = pad_k(P);
+    a.t_over_T = t_over_T;
     a.frames_in = bt->frames; a.tors_in = bt->torsions; a.mask = bt->mask;
     a.pocket_frames = bt->pocket_frames; a.pocket_cls = w.cls; a.cls_stride = w.cls_stride; a.pk_cache = w.pk_cache;
     a.aij = w.aij1; a.wimage = w.wimage;
@@ -1323,7 +1338,7 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
             PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(node_mid): %s", cudaGetErrorString(e));
             configured = true;
         }
-        tc2::NodeMidArgs n{params, B, P, t_over_T, w.ssum, bt->features, bt->mask, w.aij2, feat1_out, msum_out};
+        tc2::NodeMidArgs n{w.nm_image, B, P, t_over_T, w.ssum, bt->features, bt->mask, w.aij2, feat1_out, msum_out};
         const int grid = (B * kN + 127) / 128;
         tc2::node_mid_kernel<<<grid, 128, tc2::NM_BYTES, stream>>>(n);
         PMHC_CHECK_LAUNCH("node_mid");
