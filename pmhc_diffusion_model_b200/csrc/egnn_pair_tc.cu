@@ -71,6 +71,39 @@ struct PairArgs {
     int aj_rows;                     // rows of A_j kept in shared memory: 16 (peptide only) or 16 + P
 };
 
+// Work of one engine.  Complexes are dealt round-robin over the E = 2 * gridDim.x engines; when the last round is only
+// partly filled (rem < E complexes left), each of its complexes is split by peptide rows into `parts` pieces handled by
+// different engines, so the tail of the launch costs a fraction of a complex instead of a whole one.  Engine slots are
+// ordered "first engine of every CTA, then the second", so a thin tail spreads over the SMs.
+constexpr int kMaxParts = 4;
+struct Work {
+    int b, part, parts;
+};
+__device__ __forceinline__ bool get_work(int k, int cta, int eng, int ctas, int B, Work& w) {
+    const int E = ctas * kEngines;
+    const int full = B / E, rem = B - full * E;
+    if (k < full) {
+        w.b = k * E + cta * kEngines + eng;
+        w.part = 0;
+        w.parts = 1;
+        return true;
+    }
+    if (k > full || rem == 0) return false;
+    int S = E / rem;
+    S = S > kMaxParts ? kMaxParts : S;
+    const int slot = eng * ctas + cta;
+    if (slot >= rem * S) return false;
+    w.b = full * E + slot / S;
+    w.part = slot - (slot / S) * S;
+    w.parts = S;
+    return true;
+}
+// real peptide rows [beg, end) of a part
+__device__ __forceinline__ void part_rows(const Work& w, int L, int& beg, int& end) {
+    beg = (L * w.part) / w.parts;
+    end = (L * (w.part + 1)) / w.parts;
+}
+
 struct Map {
     int W2b, Whb, W3b, Wxb, Web, Misc, Bar, TmemPtr, cta_bytes;       // CTA-shared, byte offsets
     int A1, Sel, AjS, Out, Ai, Q, X, Tors, TorsB, Ints, Cls, eng_bytes;   // per engine, byte offsets from the engine base
@@ -705,7 +738,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
             Engine E{smem, smem + M.cta_bytes + eng * M.eng_bytes, M, a, eng, kEngThreads, tmem_base + (uint32_t)(eng * kEngCols), 0u,
                      bars + 4 * eng, 0u, tc::smem_u32(smem), tc::smem_u32(smem + M.cta_bytes + eng * M.eng_bytes), 0u};
             const int* I = E.ints();
-            for (int b = blockIdx.x * kEngines + eng; b < a.B; b += gridDim.x * kEngines) {
+            Work wk;
+            for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.B, wk); ++k) {
                 E.sync_all();   // the compute threads have set the complex up
                 ComplexInfo ci;
                 ci.L = I[IN_POCKET + a.Kpad + 0];
@@ -713,8 +747,10 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
                 ci.nx = I[IN_POCKET + a.Kpad + 2];
                 ci.c0 = I[IN_POCKET + a.Kpad + 3];
                 const ComplexPlan cp = plan_complex(ci, a.cap_pairs, LAYER == 0);
-                for (int row0 = 0; row0 < cp.L; row0 += cp.rows_per_group) {
-                    const int ntiles = (min(cp.rows_per_group, cp.L - row0) * cp.W + kTile - 1) / kTile;
+                int rbeg, rend;
+                part_rows(wk, cp.L, rbeg, rend);
+                for (int row0 = rbeg; row0 < rend; row0 += cp.rows_per_group) {
+                    const int ntiles = (min(cp.rows_per_group, rend - row0) * cp.W + kTile - 1) / kTile;
                     for (int t = 0; t < ntiles; ++t) {
                         E.serve([&] { mma_first<LAYER>(E, true); });
                         E.serve([&] {
@@ -742,7 +778,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
                         });
                     }
                 }
-                for (int t = 0; t < cp.msg_tiles; ++t) E.serve([&] { mma_first<LAYER>(E, false); });
+                const int msg_tiles = LAYER == 0 ? ((rend - rbeg) * cp.msg_w + kTile - 1) / kTile : 0;
+                for (int t = 0; t < msg_tiles; ++t) E.serve([&] { mma_first<LAYER>(E, false); });
             }
         }
     } else {
@@ -758,18 +795,24 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
 #define PMHC_TS() do { if (ts_on && ts_n < 120) a.dbg[ts_n++] = clock64(); } while (0)
         PMHC_TS();
 
-        for (int b = blockIdx.x * kEngines + eng; b < a.B; b += gridDim.x * kEngines) {
+        Work wk;
+        for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.B, wk); ++k) {
+            const int b = wk.b;
             PMHC_TS();
             const ComplexInfo ci = setup_engine(E, b, LAYER == 0);
             PMHC_TS();
             const ComplexPlan cp = plan_complex(ci, a.cap_pairs, LAYER == 0);
             const int L = cp.L, W = cp.W;
+            int rbeg, rend;
+            part_rows(wk, L, rbeg, rend);
             float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
-            for (int idx = et; idx < (kN - L) * 21; idx += kEngThreads) {   // padded rows: pass-through (T4)
-                const int s = idx / 21, c = idx - s * 21;
-                const int i = I[IN_PEPX + s];
-                if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = a.frames_in[((size_t)b * kN + i) * 7 + c];
-                else a.tors_out[((size_t)b * kN + i) * 14 + (c - 7)] = a.tors_in[((size_t)b * kN + i) * 14 + (c - 7)];
+            if (wk.part == 0) {   // padded rows: pass-through (T4)
+                for (int idx = et; idx < (kN - L) * 21; idx += kEngThreads) {
+                    const int s = idx / 21, c = idx - s * 21;
+                    const int i = I[IN_PEPX + s];
+                    if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = a.frames_in[((size_t)b * kN + i) * 7 + c];
+                    else a.tors_out[((size_t)b * kN + i) * 14 + (c - 7)] = a.tors_in[((size_t)b * kN + i) * 14 + (c - 7)];
+                }
             }
             // layer 1: this thread's share of the message column sums, sum_j m1_ij: thread 64 h + f holds feature f of
             // rows i = 0..15 summed over the tile halves h (the tensor core delivers them per tile in buffer Z)
@@ -783,8 +826,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
                 for (int i = 0; i < kN; ++i) ssum[i] += v[i];
             };
 
-            for (int row0 = 0; row0 < L; row0 += cp.rows_per_group) {
-                const int nrows = min(cp.rows_per_group, L - row0);
+            for (int row0 = rbeg; row0 < rend; row0 += cp.rows_per_group) {
+                const int nrows = min(cp.rows_per_group, rend - row0);
                 const int gpairs = nrows * W;
                 const int ntiles = (gpairs + kTile - 1) / kTile;
                 // Pair order inside a row group: the pocket neighbours of all its rows first, then the peptide neighbours
@@ -889,14 +932,14 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
             }
 
             if (LAYER == 0) {
-                const int npx = kN - L, W2 = cp.msg_w, total = L * W2;
+                const int npx = kN - L, W2 = cp.msg_w, total = (rend - rbeg) * W2;
                 for (int tile_base = 0; tile_base < total; tile_base += kTile) {
                     const int gp0 = tile_base + et;
                     const bool act = gp0 < total;
                     const int gp = act ? gp0 : tile_base;
                     const int rl = gp / W2, e = gp - rl * W2;
                     PairRef pr;
-                    pr.i = I[IN_ROWS + rl];
+                    pr.i = I[IN_ROWS + rbeg + rl];
                     pr.active = act;
                     float mult = 1.0f;
                     if (e == 0) pr.j = pr.i;
@@ -919,11 +962,14 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
 #pragma unroll
                 for (int i = 0; i < kN; ++i) scr[((et >> 6) * kN + i) * 64 + (et & 63)] = ssum[i];
                 E.sync();
-                for (int idx = et; idx < kN * kHid; idx += kEngThreads) {
-                    const int i = idx >> 6;
-                    const bool real = (E.es + M.Cls)[i] != 0;
-                    a.ssum_out[(size_t)b * kN * kHid + idx] = real ? scr[idx] + scr[kN * kHid + idx] : 0.0f;
+                // this part's real rows; part 0 also zeroes the padded rows
+                for (int idx = et; idx < (rend - rbeg) * kHid; idx += kEngThreads) {
+                    const int o = I[IN_ROWS + rbeg + (idx >> 6)] * kHid + (idx & 63);
+                    a.ssum_out[(size_t)b * kN * kHid + o] = scr[o] + scr[kN * kHid + o];
                 }
+                if (wk.part == 0)
+                    for (int idx = et; idx < npx * kHid; idx += kEngThreads)
+                        a.ssum_out[(size_t)b * kN * kHid + I[IN_PEPX + (idx >> 6)] * kHid + (idx & 63)] = 0.0f;
             }
             E.sync();
         }

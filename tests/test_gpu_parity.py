@@ -553,3 +553,29 @@ def test_bf16_sample_runs_and_is_shard_invariant(api):
     f = full["frames"].to_tensor_7()
     assert torch.isfinite(f).all()
     assert torch.equal(f, torch.cat((lo["frames"].to_tensor_7(), hi["frames"].to_tensor_7())))
+
+
+def test_bf16_forward_full_rounds_equal_split_tail(api):
+    """The pair kernel deals whole complexes round-robin over its 2 x #SM engines and splits the complexes of a partly
+    filled last round by peptide rows (egnn_pair_tc.cu: get_work).  B = 700 runs two full rounds + a split tail; the
+    same complexes in chunks of 7 run split only.  A row's result must not depend on which way it was scheduled."""
+    B = 700
+    batch = orc.synthetic_batch(B, (8, 13), (40, 60), P_pad=80, seed=91)
+    model = make_model(api, orc.random_params(seed=12), 100)
+    model.precision = "bf16"
+    gb = gpu_batch(batch)
+    with torch.no_grad():
+        full = model(dict(gb), 33)
+        parts = [model({k: v[s:s + 7] for k, v in gb.items()}, 33) for s in (0, 294, 693)]
+    f, t = full["frames"].to_tensor_7(), full["torsions"]
+    assert torch.isfinite(f).all() and torch.isfinite(t).all()
+    for s, p in zip((0, 294, 693), parts):
+        assert torch.equal(f[s:s + 7], p["frames"].to_tensor_7())
+        assert torch.equal(t[s:s + 7], p["torsions"])
+    # ... and the fp32 path agrees within the bf16 gate on all of them (oracle parity of that path is tested above)
+    model.precision = "fp32"
+    with torch.no_grad():
+        ref = model(dict(gb), 33)
+    m = batch["mask"].to(DEV)
+    assert rel_err(f[m], ref["frames"].to_tensor_7()[m]) < TOL_BF16
+    assert rel_err(t[m], ref["torsions"][m]) < TOL_BF16
