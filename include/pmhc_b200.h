@@ -153,6 +153,24 @@ int pmhc_sample(const float *params, const PmhcBatch *batch_host, float *frames,
 int pmhc_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n,
                    float lr, float beta1, float beta2, float eps, int step, void *stream);
 
+/* Loader side — replaces the per-entry Rigid.from_tensor_4x4(...).to_tensor_7() of MhcpDataset.get_entry
+ * (diffusion/data.py:107, :115; RU:1004-1034 + rot_to_quat RU:184-216): n homogeneous 4x4 matrices (row-major,
+ * rotation in [0:3,0:3], translation in [0:3,3]) -> tensor_7 rows.  The quaternion is unit with w >= 0; the reference's
+ * eigh-based rot_to_quat returns the same quaternion up to sign. */
+int pmhc_frames4x4_to_tensor7(const float *frames4x4, int64_t n, float *out7, void *stream);
+
+/* Writer side — the coordinate arithmetic of tools/pdb.py::save (pdb.py:67-174): torsion_angles_to_frames and
+ * frames_and_literature_positions_to_atom14_pos (openfold.utils.feats), backbone N / CA / C / CB from the normalised
+ * frame, backbone O from the next residue's N (pdb.py:139-151), terminal O and OXT from the psi frame (pdb.py:153-174).
+ *   frames [B,16,7], torsions [B,16,7,2], aatype [B,16] int64, mask [B,16]
+ *   default_frames [21,8,4,4], group_idx [21,14] int32, lit_positions [21,14,3], atom_mask [21,14] u8:
+ *       openfold.np.residue_constants.restype_rigid_group_default_frame / restype_atom14_to_rigid_group /
+ *       restype_atom14_rigid_group_positions / restype_atom14_mask (pdb.py:47-66)
+ *   positions [B,16,15,3]: atom14 order, slot 14 = OXT;  exists [B,16,15] (0 on padded residues). */
+int pmhc_atom14(const float *frames, const float *torsions, const int64_t *aatype, const uint8_t *mask, int B,
+                const float *default_frames, const int32_t *group_idx, const float *lit_positions,
+                const uint8_t *atom_mask, float *positions, uint8_t *exists, void *stream);
+
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches claim). */
 int64_t pmhc_launch_count(void);
 
