@@ -130,6 +130,48 @@ def cpu_trajectory_rate(params, threads, B=CPU_SAMPLE_B, T=T_STEPS, repeats=1):
     return B / best, best
 
 
+def io_leg(dev, dm, n=256):
+    """HDF5 -> GPU-resident batches -> (sampled frames) -> PDB files on n synthetic complexes: rates of the rows around the
+    hot path.  The reference's per-entry loader (file re-open + CPU eigh per entry, data.py:38, :107) and BioPython writer
+    cannot run on this box (no h5py / BioPython), so only this repo's side is timed."""
+    import shutil
+    import tempfile
+    from pmhc_diffusion_model_b200.diffusion.data import MhcpDataset, write_synthetic_hdf5
+    from pmhc_diffusion_model_b200.diffusion.tools import pdb as pdbio
+    tmp = tempfile.mkdtemp(prefix="pmhc_io_")
+    try:
+        path = os.path.join(tmp, "synthetic.hdf5")
+        write_synthetic_hdf5(path, n, peptide_len=PEPTIDE_LEN, protein_len=180, pocket_n=POCKET_N, seed=3)
+        t0 = time.perf_counter()
+        ds = MhcpDataset(path, dev)
+        ds.load_all()
+        parse_s = time.perf_counter() - t0
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            batch = ds.device_batch(slice(0, n), dev)
+        torch.cuda.synchronize(dev)
+        batch_s = (time.perf_counter() - t0) / 10
+        batch.update(ds.get_protein_positions(batch["name"][0]))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pdbio.peptide_atoms(batch)
+        e0.record()
+        for _ in range(20):
+            pdbio.peptide_atoms(batch)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        atom_us = e0.elapsed_time(e1) * 1e3 / 20
+        t0 = time.perf_counter()
+        pdbio.save_batch(batch, batch["name"][0], os.path.join(tmp, "out"))
+        write_s = time.perf_counter() - t0
+        return {"complexes": n, "hdf5_parse_complexes_per_s": n / parse_s, "device_batch_complexes_per_s": n / batch_s,
+                "atom14_kernel_us": atom_us, "pdb_files_per_s": n / write_s,
+                "note": "HDF5 subset parsed in Python (no h5py in the image); device_batch = pinned slices -> H2D -> 4x4 to tensor_7 kernel; "
+                        "PDB = one atom14 launch + text formatting of peptide (chain P) and 180-residue protein (chain M)"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (it has no GPU path),
     restated in oracle/ (the reference itself cannot travel to the GPU box), all host threads."""
@@ -169,6 +211,7 @@ def main():
     ap.add_argument("--complexes", type=int, default=N_COMPLEX, help="complexes per GPU per step")
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-io", action="store_true", help="skip the HDF5 loader / PDB writer leg")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="arithmetic of the denoiser's two dense contractions in the sampling legs (see include/pmhc_b200.h)")
     args = ap.parse_args()
@@ -278,10 +321,10 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ (ncu --set full, B = 1000)
-                "traffic": 28.5e6 if tc else 15.1e6, "peak_source": peaks["source"] + " bf16 sustained",
-                "kernel": "egnn_layer_forward_tc_kernel" if tc else "egnn_layer_forward_kernel", "kernel_ms": kernel_ms,
+                "traffic": 18.2e6 if tc else 15.1e6, "peak_source": peaks["source"] + " bf16 sustained",
+                "kernel": "egnn_pair_tc_kernel" if tc else "egnn_layer_forward_kernel", "kernel_ms": kernel_ms,
                 "kernel_share_of_step": prof_ms[0] / (ms * 1.0) if world == 1 else None,
-                "math": ("tcgen05 bf16 x bf16 -> fp32 (TMEM) for the two dense contractions, everything else fp32" if tc
+                "math": ("tcgen05 bf16 x bf16 -> fp32 (TMEM) for every per-pair contraction, geometry / softmax / updates fp32" if tc
                          else "fp32 FFMA (exact-parity mode); tensor-pipe peak is the judged denominator"),
                 "flops_per_launch": flops_per_launch}
 
@@ -310,21 +353,36 @@ def main():
         tb = {k: v.to(dev) for k, v in synthetic(TRAIN_B, seed=5000 + rank).items()}
         from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer
         trainer = DataParallelTrainer(tdm, seed=0)   # N = 1: plain optimize(); N > 1: shared t + overlapped NCCL all-reduce
-        for _ in range(W):
-            trainer.optimize(dict(tb), None)
-        barrier()
         n_train = 20
-        e0.record()
-        for _ in range(n_train):
-            flush.zero_()
-            trainer.optimize(dict(tb), None)
-        e1.record()
-        barrier()
-        tms = max_over_ranks(e0.elapsed_time(e1))
-        tdm.check_nan()
+
+        def time_training():
+            for _ in range(W):
+                trainer.optimize(dict(tb), None)
+            barrier()
+            e0.record()
+            for _ in range(n_train):
+                flush.zero_()
+                trainer.optimize(dict(tb), None)
+            e1.record()
+            barrier()
+            t = max_over_ranks(e0.elapsed_time(e1))
+            tdm.check_nan()
+            return t
+
+        tms = time_training()
+        tmodel.precision = "bf16"       # tensor-core forward (saves the softmax statistics), fp32 backward
+        tms_bf16 = time_training()
+        tmodel.precision = "fp32"
         train = {"metric": "train complexes/s", "value": world * TRAIN_B * n_train / (tms / 1e3), "unit": UNIT,
                  "ms_per_step": tms / n_train, "global_batch": world * TRAIN_B, "steps": n_train,
-                 "config": "B=256/GPU, 9-mer, pocket 60/80, fp32, noise+forward+loss+backward+Adam per step"}
+                 "config": "B=256/GPU, 9-mer, pocket 60/80, fp32, noise+forward+loss+backward+Adam per step",
+                 "bf16_forward": {"value": world * TRAIN_B * n_train / (tms_bf16 / 1e3), "ms_per_step": tms_bf16 / n_train,
+                                  "config": "same step with the tensor-core (bf16 operand) forward, fp32 backward"}}
+
+    # ---------------- loader / writer rows, rank 0 at N = 1 ----------------
+    io = None
+    if rank == 0 and world == 1 and not args.no_io:
+        io = io_leg(dev, dm)
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
@@ -352,6 +410,7 @@ def main():
             "cpu_baseline": cpu,
             "other_precision": other,
             "train": train,
+            "io": io,
         }))
     if world > 1:
         dist.destroy_process_group()

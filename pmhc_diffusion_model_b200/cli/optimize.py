@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Training entry point — same arguments and outputs as the reference's optimize.py (optimize.py:24-82):
+
+    python -m pmhc_diffusion_model_b200.cli.optimize train_set.hdf5 100 model.pth [-T 1000] [-b 64] [--lr 0.001]
+
+writes `<output_model>` (state dict, the reference's 48 keys) every 100 batches and per epoch, and one CSV row of mean
+losses per epoch to `<output_model stem>.csv`.  Differences that do not change results: batches come GPU-resident from
+`MhcpDataset.batches()` (`--num-workers` is accepted and ignored: there are no loader processes), the NaN check is read
+once per epoch instead of once per step (`DiffusionModelOptimizer.check_nan`), `--precision bf16` selects the tensor-core
+forward.  Runs on one GPU; under torchrun each rank trains on its shard of every batch with an NCCL gradient all-reduce.
+"""
+import logging
+import os
+import sys
+from argparse import ArgumentParser
+
+import torch
+
+_log = logging.getLogger(__name__)
+
+arg_parser = ArgumentParser()
+arg_parser.add_argument("train_hdf5", help="train data")
+arg_parser.add_argument("epoch_count", type=int, help="number of epochs over the data")
+arg_parser.add_argument("output_model", help="output model parameters file")
+arg_parser.add_argument("--debug", "-d", action="store_const", const=True, default=False, help="run in debug mode")
+arg_parser.add_argument("-T", type=int, help="number of noise steps", default=1000)
+arg_parser.add_argument("--batch-size", "-b", type=int, help="data batch size", default=64)
+arg_parser.add_argument("--num-workers", "-w", type=int, help="accepted for compatibility; batches are built on the GPU", default=4)
+arg_parser.add_argument("--lr", type=float, help="learning rate", default=0.001)
+arg_parser.add_argument("--precision", choices=["fp32", "bf16"], default="fp32", help="arithmetic of the denoiser forward")
+arg_parser.add_argument("--seed", type=int, default=None, help="seed of the batch order, noise steps and noise")
+
+
+def main(argv=None) -> None:
+    args = arg_parser.parse_args(argv)
+    logging.basicConfig(stream=sys.stdout, level=logging.DEBUG if args.debug else logging.INFO)
+    if not torch.cuda.is_available():
+        raise SystemExit("pmhc_diffusion_model_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+
+    import torch.distributed as dist
+    from pmhc_diffusion_model_b200.diffusion.data import MhcpDataset
+    from pmhc_diffusion_model_b200.diffusion.model import Model
+    from pmhc_diffusion_model_b200.diffusion.optimizer import DiffusionModelOptimizer
+    from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer
+    from pmhc_diffusion_model_b200.diffusion.tools.metrics import MetricsRecord
+
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    model = Model(16, 22, args.T).to(device=device)
+    if os.path.isfile(args.output_model):
+        model.load_state_dict(torch.load(args.output_model, map_location=device), strict=True)
+    model.precision = args.precision
+    dm = DiffusionModelOptimizer(args.T, model, args.lr)
+    trainer = DataParallelTrainer(dm, seed=args.seed if args.seed is not None else 0)
+
+    train_dataset = MhcpDataset(args.train_hdf5, device)
+    order = torch.Generator().manual_seed(args.seed if args.seed is not None else torch.seed() % (1 << 31))
+    metrics_path = args.output_model.replace(".pth", ".csv")
+    for epoch_index in range(args.epoch_count):
+        _log.debug(f"starting epoch {epoch_index}")
+        metrics = MetricsRecord()
+        for i, batch in enumerate(train_dataset.batches(args.batch_size, device, shuffle=True, generator=order)):
+            if world > 1:      # every rank draws the same order and takes its slice of the batch
+                batch = {k: (v[rank::world] if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+            trainer.optimize(batch, metrics)
+            if rank == 0 and i > 0 and i % 100 == 0:
+                torch.save(model.state_dict(), args.output_model)
+                _log.debug(f"saved {args.output_model}")
+        dm.check_nan()
+        if rank == 0:
+            torch.save(model.state_dict(), args.output_model)
+            _log.debug(f"saved {args.output_model}")
+            metrics.save(metrics_path, epoch_index)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

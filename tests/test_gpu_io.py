@@ -172,3 +172,24 @@ def test_sampling_flow_from_hdf5_to_pdb(io, tmp_path):
         atoms = parse_atoms(p)
         assert sum(a[0] == "P" for a in atoms) > 40 and sum(a[0] == "M" for a in atoms) > 200
         assert all(numpy.isfinite(a[4]).all() for a in atoms)
+
+
+def test_cli_entry_points_keep_the_reference_interface(io, tmp_path):
+    """optimize.py / test.py flags and outputs (optimize.py:24-82, test.py:20-84): <model>.pth with the reference's 48
+    state-dict keys, <model>.csv with one row per epoch, <hdf5 stem>-sampled/<name>.pdb."""
+    import csv
+    from pmhc_diffusion_model_b200.cli import optimize as cli_optimize
+    from pmhc_diffusion_model_b200.cli import test as cli_test
+    train = str(tmp_path / "train_set.hdf5")
+    names = io.data.write_synthetic_hdf5(train, 12, peptide_len=(8, 11), protein_len=50, pocket_n=25, seed=21)
+    model_path = str(tmp_path / "model.pth")
+    cli_optimize.main([train, "2", model_path, "-T", "20", "-b", "5", "--seed", "1"])
+    state = torch.load(model_path, map_location="cpu")
+    assert len(state) == 48 and "gnn1.message_mlp.0.weight" in state and all(torch.isfinite(v).all() for v in state.values())
+    rows = list(csv.reader(open(str(tmp_path / "model.csv"))))
+    assert rows[0] == ["epoch", "total loss", "positions loss", "rotations loss", "torsions loss", "rmsd"]
+    assert [r[0] for r in rows[1:]] == ["0", "1"] and all(float(x) == float(x) for r in rows[1:] for x in r[1:])
+    cli_test.main([model_path, train, "-T", "5", "-b", "7", "--precision", "bf16", "--seed", "3"])
+    out = tmp_path / "train_set-sampled"
+    assert sorted(os.listdir(out)) == sorted(n + ".pdb" for n in names)
+    assert all(len(parse_atoms(str(out / f))) > 300 for f in os.listdir(out))

@@ -579,3 +579,42 @@ def test_bf16_forward_full_rounds_equal_split_tail(api):
     m = batch["mask"].to(DEV)
     assert rel_err(f[m], ref["frames"].to_tensor_7()[m]) < TOL_BF16
     assert rel_err(t[m], ref["torsions"][m]) < TOL_BF16
+
+
+def test_bf16_forward_training_gradients_vs_oracle_autograd(api):
+    """Mixed-precision training step: tensor-core (bf16 operand) forward that saves the softmax statistics, fp32 backward
+    that recomputes the pairs.  Gradients against the oracle's fp32 autograd, per tensor relative to its largest entry."""
+    g = torch.Generator().manual_seed(14)
+    B = 6
+    batch = orc.synthetic_batch(B, (5, 14), (20, 60), P_pad=80, seed=43)
+    params = orc.random_params(seed=19)
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    true = orc.gen_noise([B, 16], g)
+    pred = orc.model_forward(p_ref, orc.batch_to_frames(batch), 30, 100)
+    orc.get_loss(true, pred, batch["mask"], batch["torsions_mask"])["total loss"].mean().backward()
+    model = make_model(api, params, 100)
+    model.precision = "bf16"
+    gb = gpu_batch(batch)
+    out = model(gb, 30)
+    true_g = {"frames": api.Rigid(api.Rotation(quats=true["frames"]["quats"].to(DEV), normalize_quats=False), true["frames"]["trans"].to(DEV)),
+              "torsions": true["torsions"].to(DEV)}
+    api.DMO.get_loss(true_g, out, gb["mask"], gb["torsions_mask"])["total loss"].mean().backward()
+    # gate: bf16 tolerance (1e-2 of north_star, x3 for the chain forward -> loss -> backward) relative to the tensor's largest
+    # entry, plus an absolute floor for tensors whose true gradient is zero by symmetry (attention_mlp.2.bias: the softmax is
+    # shift-invariant, the reference's own value there is rounding noise)
+    bad, worst = [], 0.0
+    for k, p in model.named_parameters():
+        if k.startswith("gnn2.feature_mlp"):
+            assert p.grad is None
+            continue
+        ref = p_ref[k].grad
+        err = float((p.grad.cpu() - ref).abs().max())
+        scale = float(ref.abs().max())
+        worst = max(worst, err)
+        # attention_mlp.2.bias: sum over a row of dlogit = sum_k w_k dL/dw_k - c_i, where c_i comes from the tensor-core
+        # forward's saved aggregates and dL/dw_k from the fp32 recomputation: a bf16-sized residue instead of an exact zero
+        floor = 5e-3 if k.endswith("attention_mlp.2.bias") else 2e-4
+        if err > 3e-2 * scale + floor:
+            bad.append((k, err, scale))
+    assert not bad, bad
+    assert worst > 0.0      # the bf16 forward really ran
