@@ -219,6 +219,12 @@ def main():
         run_reference(args)
         return
 
+    # stdout carries exactly one line, the JSON: anything libraries print there (NCCL's version banner at communicator
+    # creation, for one) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch.distributed as dist
     from oracle import egnn_oracle as orc
     from pmhc_diffusion_model_b200 import _lib
@@ -393,7 +399,7 @@ def main():
                "sample": f"one trajectory of {CPU_SAMPLE_B} complexes x T={T_STEPS} (same shapes), {secs:.1f} s, oracle/egnn_oracle.py on torch CPU fp32"}
 
     if rank == 0:
-        print(json.dumps({
+        line = json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if tc else "f32", "data": "synthetic",
@@ -411,7 +417,9 @@ def main():
             "other_precision": other,
             "train": train,
             "io": io,
-        }))
+        })
+        sys.stdout.flush()
+        os.write(json_fd, (line + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

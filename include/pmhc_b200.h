@@ -171,6 +171,17 @@ int pmhc_atom14(const float *frames, const float *torsions, const int64_t *aatyp
                 const float *default_frames, const int32_t *group_idx, const float *lit_positions,
                 const uint8_t *atom_mask, float *positions, uint8_t *exists, void *stream);
 
+/* Host-side text of one complex in the fixed PDB columns, as tools/pdb.py:206-209 gets it from BioPython's PDBIO: chain P =
+ * the peptide's atoms in the order the reference adds them (N, CA, C, CB, side chain, O [, OXT]; pdb.py:112-174), chain M = the
+ * protein's existing atom14 slots (pdb.py:177-204), serial numbers from 1, a TER record per chain, END.  HOST pointers.
+ *   pep_*: one peptide: aatype [16], mask [16], positions [16,15,3], exists [16,15] (pmhc_atom14 layout)
+ *   prot_*: aatype [n_prot], positions [n_prot,14,3], exists [n_prot,14]
+ *   atom_fields [21,15,4] chars, elements [21,15] chars, res3 [21,3] chars per (residue type, atom slot), not terminated
+ * Returns the bytes written to `out`, or -(bytes needed) when out_cap is too small. */
+int64_t pmhc_format_pdb_host(const int64_t *pep_aatype, const uint8_t *pep_mask, const float *pep_pos, const uint8_t *pep_exists,
+                             int64_t n_prot, const int64_t *prot_aatype, const float *prot_pos, const uint8_t *prot_exists,
+                             const char *atom_fields, const char *elements, const char *res3, char *out, int64_t out_cap);
+
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches claim). */
 int64_t pmhc_launch_count(void);
 

@@ -23,7 +23,7 @@ EXPORTS = (
     "pmhc_last_error", "pmhc_check_device", "pmhc_param_offset", "pmhc_param_numel", "pmhc_workspace_bytes",
     "pmhc_saved_floats", "pmhc_model_forward", "pmhc_model_forward_ex", "pmhc_model_backward", "pmhc_gen_noise", "pmhc_noise_from_randoms",
     "pmhc_add_noise", "pmhc_remove_noise", "pmhc_loss", "pmhc_sample", "pmhc_adam_step", "pmhc_launch_count",
-    "pmhc_profile_enable", "pmhc_profile_read", "pmhc_frames4x4_to_tensor7", "pmhc_atom14",
+    "pmhc_profile_enable", "pmhc_profile_read", "pmhc_frames4x4_to_tensor7", "pmhc_atom14", "pmhc_format_pdb_host",
 )
 
 
@@ -91,6 +91,8 @@ def load() -> ctypes.CDLL:
     lib.pmhc_frames4x4_to_tensor7.argtypes = [vp, i64, vp, vp]
     lib.pmhc_atom14.restype = c_int
     lib.pmhc_atom14.argtypes = [vp, vp, vp, vp, c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.pmhc_format_pdb_host.restype = i64
+    lib.pmhc_format_pdb_host.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, c_char_p, c_char_p, c_char_p, vp, i64]
     _lib = lib
     return lib
 

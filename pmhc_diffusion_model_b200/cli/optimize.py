@@ -29,6 +29,8 @@ arg_parser.add_argument("--num-workers", "-w", type=int, help="accepted for comp
 arg_parser.add_argument("--lr", type=float, help="learning rate", default=0.001)
 arg_parser.add_argument("--precision", choices=["fp32", "bf16"], default="fp32", help="arithmetic of the denoiser forward")
 arg_parser.add_argument("--seed", type=int, default=None, help="seed of the batch order, noise steps and noise")
+arg_parser.add_argument("--checkpoint", default=None, help="full training state (weights, Adam, random streams, epoch): written "
+                        "after every epoch and resumed from when the file exists")
 
 
 def main(argv=None) -> None:
@@ -59,9 +61,21 @@ def main(argv=None) -> None:
     trainer = DataParallelTrainer(dm, seed=args.seed if args.seed is not None else 0)
 
     train_dataset = MhcpDataset(args.train_hdf5, device)
+    if args.seed is not None:
+        import random
+        random.seed(args.seed)
+        torch.manual_seed(args.seed)
     order = torch.Generator().manual_seed(args.seed if args.seed is not None else torch.seed() % (1 << 31))
+    first_epoch = 0
+    if args.checkpoint and os.path.isfile(args.checkpoint):
+        ckpt = torch.load(args.checkpoint, map_location=device, weights_only=False)
+        dm.load_state_dict(ckpt["trainer"])
+        order.set_state(ckpt["order"])
+        trainer.step_index = int(ckpt["step_index"])
+        first_epoch = int(ckpt["epoch"]) + 1
+        _log.info(f"resumed from {args.checkpoint} at epoch {first_epoch}")
     metrics_path = args.output_model.replace(".pth", ".csv")
-    for epoch_index in range(args.epoch_count):
+    for epoch_index in range(first_epoch, args.epoch_count):
         _log.debug(f"starting epoch {epoch_index}")
         metrics = MetricsRecord()
         for i, batch in enumerate(train_dataset.batches(args.batch_size, device, shuffle=True, generator=order)):
@@ -76,6 +90,9 @@ def main(argv=None) -> None:
             torch.save(model.state_dict(), args.output_model)
             _log.debug(f"saved {args.output_model}")
             metrics.save(metrics_path, epoch_index)
+            if args.checkpoint:
+                torch.save({"trainer": dm.state_dict(), "order": order.get_state(), "step_index": trainer.step_index, "epoch": epoch_index},
+                           args.checkpoint)
     if world > 1:
         dist.destroy_process_group()
 

@@ -8,6 +8,9 @@
 //                                 atom14_pos, backbone O from the neighbouring N, terminal O / OXT from the psi frame)
 //
 // Both are HBM-bound elementwise kernels: one thread per residue, every input read once, every output written once.
+#include <math.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "pmhc_math.cuh"
 
@@ -250,4 +253,88 @@ extern "C" int pmhc_atom14(const float* frames, const float* torsions, const int
     atom14_kernel<<<grid_for(n, 64), 64, 0, (cudaStream_t)stream>>>(frames, torsions, aatype, mask, n, tb, positions, exists);
     PMHC_CHECK_LAUNCH("pmhc_atom14");
     return 0;
+}
+
+// Host-side text formatting of one complex in the fixed PDB columns (what tools/pdb.py:206-209 gets from BioPython's PDBIO):
+// chain P = peptide atoms in the order the reference adds them (N, CA, C, CB, side chain, O [, OXT], pdb.py:112-174), chain M =
+// the protein's existing atom14 slots (pdb.py:177-204), serial numbers from 1 running through one TER record per chain, END.
+// All pointers are HOST pointers.  atom_fields [21][15][4] / elements [21][15] / res3 [21][3]: the padded atom-name column,
+// element letter and residue name per (residue type, atom slot).  Returns the number of bytes written, or -(bytes needed)
+// when `out` is too small.
+extern "C" int64_t pmhc_format_pdb_host(const int64_t* pep_aatype, const uint8_t* pep_mask, const float* pep_pos, const uint8_t* pep_exists,
+                                        int64_t n_prot, const int64_t* prot_aatype, const float* prot_pos, const uint8_t* prot_exists,
+                                        const char* atom_fields, const char* elements, const char* res3, char* out, int64_t out_cap) {
+    static const int order[15] = {0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 3, 14};
+    const int64_t max_lines = 16 * 15 + n_prot * 14 + 3;
+    if (out_cap < max_lines * 96 + 1) return -(max_lines * 96 + 1);
+    char* w = out;
+    int serial = 0;
+    // "%8.3f" without printf (glibc's float formatting is ~0.3 us a number): x * 1000 rounded half-to-even is exact for float
+    // inputs in the PDB range (a float's distance from a decimal tie is either 0 or >> double rounding error), so the digits
+    // are the ones printf gives.  A line with a number that does not fit its column goes through snprintf whole (and comes
+    // out wider than 80, as it does from PDBIO).
+    auto fits = [](float x) { const double v = (double)x; return v > -999.9994 && v < 9999.9994; };   // false for NaN too
+    auto f83 = [](char* d, float x) {
+        const double v = (double)x;
+        long long m = (long long)nearbyint(fabs(v) * 1000.0);
+        char buf[8];
+        int p = 7;
+        for (int k = 0; k < 3; ++k) { buf[p--] = (char)('0' + m % 10); m /= 10; }
+        buf[p--] = '.';
+        do { buf[p--] = (char)('0' + m % 10); m /= 10; } while (m > 0);
+        if (signbit(v)) buf[p--] = '-';      // printf keeps the sign of -0.0 and of -0.0004 -> "-0.000"
+        while (p >= 0) buf[p--] = ' ';
+        memcpy(d, buf, 8);
+    };
+    auto atom = [&](int aa, int slot, char chain, int resseq, const float* p) {
+        ++serial;
+        // columns: 1-6 record, 7-11 serial, 13-16 name, 18-20 residue, 22 chain, 23-26 number, 31-54 x y z, 55-60 occupancy,
+        // 61-66 B factor, 77-78 element
+        int n = snprintf(w, 82, "ATOM  %5d %.4s %.3s %c%4d    ", serial, atom_fields + (aa * 15 + slot) * 4, res3 + aa * 3, chain, resseq);
+        if (n != 30 || !fits(p[0]) || !fits(p[1]) || !fits(p[2])) {   // something beyond its column: let printf lay the line out
+            w += snprintf(w, 96, "ATOM  %5d %.4s %.3s %c%4d    %8.3f%8.3f%8.3f%6.2f%6.2f          %2c  \n", serial, atom_fields + (aa * 15 + slot) * 4,
+                          res3 + aa * 3, chain, resseq, (double)p[0], (double)p[1], (double)p[2], 1.0, 0.0, elements[aa * 15 + slot]);
+            return;
+        }
+        f83(w + 30, p[0]);
+        f83(w + 38, p[1]);
+        f83(w + 46, p[2]);
+        memcpy(w + 54, "  1.00  0.00           ", 23);
+        w[77] = elements[aa * 15 + slot];
+        w[78] = ' ';
+        w[79] = ' ';
+        w[80] = '\n';
+        w += 81;
+    };
+    auto ter = [&](int aa, char chain, int resseq) {
+        ++serial;
+        const int n = snprintf(w, 82, "TER   %5d      %.3s %c%4d", serial, res3 + aa * 3, chain, resseq);
+        memset(w + n, ' ', 80 - n);
+        w[80] = '\n';
+        w += 81;
+    };
+    int last_aa = -1, last_seq = 0;
+    for (int i = 0; i < 16; ++i) {
+        if (!pep_mask[i]) continue;
+        const int aa = pep_aatype[i] < 0 || pep_aatype[i] > 20 ? 20 : (int)pep_aatype[i];
+        for (int k = 0; k < 15; ++k) {
+            const int a = order[k];
+            if (pep_exists[i * 15 + a]) atom(aa, a, 'P', i + 1, pep_pos + (i * 15 + a) * 3);
+        }
+        last_aa = aa;
+        last_seq = i + 1;
+    }
+    if (last_aa >= 0) ter(last_aa, 'P', last_seq);
+    last_aa = -1;
+    for (int64_t i = 0; i < n_prot; ++i) {
+        const int aa = prot_aatype[i] < 0 || prot_aatype[i] > 20 ? 20 : (int)prot_aatype[i];
+        for (int a = 0; a < 14; ++a)
+            if (prot_exists[i * 14 + a]) atom(aa, a, 'M', (int)i + 1, prot_pos + (i * 14 + a) * 3);
+        last_aa = aa;
+        last_seq = (int)i + 1;
+    }
+    if (last_aa >= 0) ter(last_aa, 'M', last_seq);
+    memcpy(w, "END   \n", 7);
+    w += 7;
+    return (int64_t)(w - out);
 }

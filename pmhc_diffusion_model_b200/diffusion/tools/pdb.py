@@ -98,9 +98,36 @@ def _ter_line(serial: int, res3: str, chain: str, resseq: int) -> str:
     return f"TER   {serial:5d}      {res3:>3s} {chain}{resseq:4d}".ljust(80) + "\n"
 
 
+def _text_tables() -> Tuple[bytes, bytes, bytes]:
+    t = _host_tables()
+    if "c_fields" not in t:
+        t["c_fields"] = "".join(f for row in t["atom_field"] for f in row).encode()
+        t["c_elements"] = "".join((a[0] if a else " ") for row in t["atom_names"] for a in row).encode()
+        t["c_res3"] = "".join(t["names3"]).encode()
+    return t["c_fields"], t["c_elements"], t["c_res3"]
+
+
 def format_pdb(pep_aatype: numpy.ndarray, pep_mask: numpy.ndarray, pep_pos: numpy.ndarray, pep_exists: numpy.ndarray,
                prot_aatype: numpy.ndarray, prot_pos: numpy.ndarray, prot_exists: numpy.ndarray) -> str:
-    """The file text of one complex from host arrays (peptide [16,...], protein [M,...])."""
+    """The file text of one complex from host arrays (peptide [16,...], protein [M,...]), formatted by the library's host
+    routine `pmhc_format_pdb_host` (per-atom Python string formatting caps at ~200 files/s)."""
+    import ctypes
+    fields, elements, res3 = _text_tables()
+    c = lambda a, dt: numpy.ascontiguousarray(a, dtype=dt)
+    pa, pm, pp, pe = c(pep_aatype, numpy.int64), c(pep_mask, numpy.uint8), c(pep_pos, numpy.float32), c(pep_exists, numpy.uint8)
+    ra, rp, re_ = c(prot_aatype, numpy.int64), c(prot_pos, numpy.float32), c(prot_exists, numpy.uint8)
+    cap = (16 * 15 + ra.shape[0] * 14 + 3) * 96 + 1
+    out = ctypes.create_string_buffer(cap)
+    n = _lib.load().pmhc_format_pdb_host(pa.ctypes.data, pm.ctypes.data, pp.ctypes.data, pe.ctypes.data, ra.shape[0], ra.ctypes.data,
+                                         rp.ctypes.data, re_.ctypes.data, fields, elements, res3, ctypes.addressof(out), cap)
+    if n < 0:
+        raise RuntimeError("pmhc_format_pdb_host: output buffer too small")
+    return out.raw[:n].decode()
+
+
+def format_pdb_python(pep_aatype: numpy.ndarray, pep_mask: numpy.ndarray, pep_pos: numpy.ndarray, pep_exists: numpy.ndarray,
+                      prot_aatype: numpy.ndarray, prot_pos: numpy.ndarray, prot_exists: numpy.ndarray) -> str:
+    """The same text built line by line in Python: the readable statement of the layout (tests compare the two)."""
     t = _host_tables()
     lines: List[str] = []
     serial = 0

@@ -185,6 +185,9 @@ def test_pdb_text_layout(golden):
     prot = golden["protein"]
     text = pdbio.format_pdb(aatype.numpy(), mask.numpy(), pos[0].numpy(), exists[0].numpy(), prot["protein_aatype"][b].numpy(),
                             prot["protein_atom14_positions"][b].numpy(), prot["protein_atom14_exists"][b].numpy().astype(bool))
+    # the library's host-side formatter and the line-by-line Python statement of the layout give the same bytes
+    assert text == pdbio.format_pdb_python(aatype.numpy(), mask.numpy(), pos[0].numpy(), exists[0].numpy(), prot["protein_aatype"][b].numpy(),
+                                           prot["protein_atom14_positions"][b].numpy(), prot["protein_atom14_exists"][b].numpy().astype(bool))
     lines = text.splitlines()
     assert lines[-1] == "END   " and all(len(l) == 80 for l in lines[:-1])
     atoms = [l for l in lines if l.startswith("ATOM")]
@@ -199,3 +202,27 @@ def test_pdb_text_layout(golden):
     ters = [l for l in lines if l.startswith("TER")]
     assert len(ters) == 2 and ters[0][21] == "P" and ters[1][21] == "M"
     assert atoms[0][12:16] == " N  " and any(l[12:16] == " CA " for l in atoms)
+
+
+def test_pdb_number_formatting_matches_printf():
+    """The host formatter writes "%8.3f" digits itself: ties (half-to-even on the exact value), negative zero, values that
+    round to zero, column overflow and non-finite values must come out as Python's / printf's formatting does."""
+    t = pdbio._host_tables()
+    rng = numpy.random.default_rng(1)
+    aa = rng.integers(0, 20, 16)
+    mask = numpy.arange(16) < 9
+    ex = numpy.concatenate([numpy.asarray(t["atom_mask"])[aa], numpy.zeros((16, 1), numpy.uint8)], 1).astype(bool)
+    ex[:, 3], ex[8, 14] = True, True
+    paa = rng.integers(0, 21, 40)
+    pex = numpy.asarray(t["atom_mask"])[paa].astype(bool)
+    ppos = (rng.standard_normal((40, 14, 3)) * 30).astype("f4")
+    ppos[0, 0] = [0.0625, -0.0625, 0.1875]
+    ppos[1, 0] = [-0.0004, 0.0005, -1e-9]
+    ppos[2, 0] = [9999.9, -999.9, 123456.7]
+    ppos[3, 0] = [2.5, -3.0005, 0.9995]
+    ppos[4, 0] = [0.0, -0.0, 1234.5675]
+    ppos[5, 0] = [float("nan"), float("inf"), -999.9995]
+    for scale in (0.01, 1.0, 100.0, 3000.0):
+        pos = (rng.standard_normal((16, 15, 3)) * scale).astype("f4")
+        args = (aa, mask, pos, ex, paa, ppos * (scale if scale < 1000 else 1.0), pex)
+        assert pdbio.format_pdb(*args) == pdbio.format_pdb_python(*args)
