@@ -109,12 +109,13 @@ class ClockSampler:
 
 
 def synthetic(B, seed, P_pad=P_PAD, pocket_n=POCKET_N, L=PEPTIDE_LEN):
-    from oracle import egnn_oracle as orc  # input generator only (seeded synthetic SwiftMHC-shaped complexes)
-    return orc.synthetic_batch(B, L, pocket_n, P_pad=P_pad, seed=seed)
+    from pmhc_diffusion_model_b200.synthetic import synthetic_batch   # seeded synthetic SwiftMHC-shaped complexes
+    return synthetic_batch(B, L, pocket_n, P_pad=P_pad, seed=seed)
 
 
 def cpu_trajectory_rate(params, threads, B=CPU_SAMPLE_B, T=T_STEPS, repeats=1):
-    """Reference path on the host cores: oracle.sample() = the reference's DiffusionModelOptimizer.sample restated."""
+    """Reference path on the host cores: oracle.sample() = the reference's DiffusionModelOptimizer.sample restated.
+    (The one place, with run_reference below, where bench.py executes oracle/: as the measured CPU baseline.)"""
     from oracle import egnn_oracle as orc
     torch.set_num_threads(threads)
     batch = orc.batch_to_frames(synthetic(B, seed=4242))
@@ -178,9 +179,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import egnn_oracle as orc
+    from pmhc_diffusion_model_b200.synthetic import random_params
     threads = os.cpu_count() or 1
-    params = orc.random_params(seed=0)
+    params = random_params(seed=0)
     for _ in range(args.warmup):
         cpu_trajectory_rate(params, threads, B=2, T=5)
     t0 = time.perf_counter()
@@ -226,8 +227,8 @@ def main():
     os.dup2(2, 1)
 
     import torch.distributed as dist
-    from oracle import egnn_oracle as orc
     from pmhc_diffusion_model_b200 import _lib
+    from pmhc_diffusion_model_b200.synthetic import random_params
     from pmhc_diffusion_model_b200.diffusion.model import Model
     from pmhc_diffusion_model_b200.diffusion.optimizer import DiffusionModelOptimizer
 
@@ -256,7 +257,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    params = orc.random_params(seed=0)        # random-init weights of the reference architecture
+    params = random_params(seed=0)            # random-init weights of the reference architecture
     model = Model(16, 22, T_STEPS)
     model.load_state_dict(params, strict=True)
     model = model.to(dev)
@@ -267,10 +268,10 @@ def main():
 
     host = synthetic(B, seed=1000 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
-    g = torch.Generator().manual_seed(7 + rank)
-    start = orc.gen_noise([B, 16], g)
-    host["frames"] = torch.cat((start["frames"]["quats"], start["frames"]["trans"]), -1).pin_memory()   # z_T (test.py:71-74)
-    host["torsions"] = start["torsions"].pin_memory()
+    torch.manual_seed(7 + rank)
+    start = dm.gen_noise([B, 16], dev)                                                   # z_T (test.py:71-74)
+    host["frames"] = start["frames"].to_tensor_7().cpu().pin_memory()
+    host["torsions"] = start["torsions"].cpu().pin_memory()
     keys = ("frames", "torsions", "features", "mask", "pocket_frames", "pocket_features", "pocket_mask")
     resident = {k: host[k].to(dev) for k in keys}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2

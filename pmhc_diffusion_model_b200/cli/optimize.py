@@ -53,6 +53,10 @@ def main(argv=None) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
+    if args.seed is not None:      # before the model is built: the initial weights come from torch's generator too
+        import random
+        random.seed(args.seed)
+        torch.manual_seed(args.seed)
     model = Model(16, 22, args.T).to(device=device)
     if os.path.isfile(args.output_model):
         model.load_state_dict(torch.load(args.output_model, map_location=device), strict=True)
@@ -61,16 +65,12 @@ def main(argv=None) -> None:
     trainer = DataParallelTrainer(dm, seed=args.seed if args.seed is not None else 0)
 
     train_dataset = MhcpDataset(args.train_hdf5, device)
-    if args.seed is not None:
-        import random
-        random.seed(args.seed)
-        torch.manual_seed(args.seed)
     order = torch.Generator().manual_seed(args.seed if args.seed is not None else torch.seed() % (1 << 31))
     first_epoch = 0
     if args.checkpoint and os.path.isfile(args.checkpoint):
         ckpt = torch.load(args.checkpoint, map_location=device, weights_only=False)
         dm.load_state_dict(ckpt["trainer"])
-        order.set_state(ckpt["order"])
+        order.set_state(ckpt["order"].cpu())
         trainer.step_index = int(ckpt["step_index"])
         first_epoch = int(ckpt["epoch"]) + 1
         _log.info(f"resumed from {args.checkpoint} at epoch {first_epoch}")

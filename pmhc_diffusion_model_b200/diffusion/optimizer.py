@@ -262,7 +262,7 @@ class DiffusionModelOptimizer:
 
     # ---- full training state (the reference only saves model.state_dict(), optimize.py:75-80) -----------
     def state_dict(self) -> Dict:
-        """Everything a bit-exact resume needs: weights, Adam moments and step count, and the two host random streams the
+        """Everything a resume needs to continue the same run: weights, Adam moments and step count, and the two host random streams the
         training step draws from (Python's `random` for t, optimizer.py:197; torch's CPU generator for the noise keys)."""
         return {"model": self.model.state_dict(), "optimizer": self.optimizer.state_dict(), "noise_step_count": self.noise_step_count,
                 "python_random": random.getstate(), "torch_rng": torch.get_rng_state()}
@@ -273,7 +273,7 @@ class DiffusionModelOptimizer:
         self.model.load_state_dict(state["model"], strict=True)
         self.optimizer.load_state_dict(state["optimizer"])
         random.setstate(state["python_random"])
-        torch.set_rng_state(state["torch_rng"])
+        torch.set_rng_state(state["torch_rng"].cpu())       # (a checkpoint loaded with map_location=cuda moves it)
 
     # ---- sampling -------------------------------------------------------------------------------------------
     def sample(self, batch: Dict[str, Union[torch.Tensor, Rigid]], noise_tape: Optional[torch.Tensor] = None,

@@ -1,6 +1,6 @@
 import sys, os, torch
 sys.path.insert(0, '/root/repo')
-from oracle import egnn_oracle as orc
+from pmhc_diffusion_model_b200 import synthetic as orc
 from pmhc_diffusion_model_b200.diffusion.model import Model
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 dev = torch.device("cuda:0")

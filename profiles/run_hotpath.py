@@ -11,7 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle import egnn_oracle as orc  # noqa: E402  (synthetic inputs + random weights only)
+from pmhc_diffusion_model_b200 import synthetic as orc
 from pmhc_diffusion_model_b200.diffusion.model import Model  # noqa: E402
 from pmhc_diffusion_model_b200.diffusion.optimizer import DiffusionModelOptimizer  # noqa: E402
 

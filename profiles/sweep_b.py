@@ -4,7 +4,7 @@ launch (prologue, tail) from the per-round cost.   python profiles/sweep_b.py [B
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import egnn_oracle as orc
+from pmhc_diffusion_model_b200 import synthetic as orc
 from pmhc_diffusion_model_b200 import _lib
 from pmhc_diffusion_model_b200.diffusion.model import Model
 

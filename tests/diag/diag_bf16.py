@@ -1,6 +1,6 @@
 """Per-component error of the bf16 tensor-core forward against the CPU oracle (development aid)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import egnn_oracle as orc
 from pmhc_diffusion_model_b200.diffusion.model import Model

@@ -1,5 +1,5 @@
 import sys, os, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 from tests.helpers import load_case
 from pmhc_diffusion_model_b200.diffusion.model import Model
 from pmhc_diffusion_model_b200.diffusion.optimizer import DiffusionModelOptimizer
