@@ -170,44 +170,42 @@ __device__ __forceinline__ void axpy64(float (&acc)[kHid], const float* __restri
 }
 
 // tile[n][k] += sum_p bufN[n][p] * bufK[k][p] over the 128 columns of the pass: register-tiled 64x64x128 GEMM.
-// Thread t owns k in {t&15 + 16a}, n in {t>>4 + 8b}; its 32 sums live contiguously in the tile-owner layout.
+// Thread t owns k in {t&15 + 16a}, n in {t>>4 + 16b}, a, b < 4; its 16 sums live contiguously in the tile-owner layout.
 __device__ __forceinline__ void coop_outer(const float* __restrict__ bufN, const float* __restrict__ bufK,
                                            float* __restrict__ tile) {
     const int tid = threadIdx.x, kk = tid & 15, nn = tid >> 4;
-    float acc[4][8];
+    float acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0f;
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
 #pragma unroll 2
     for (int p4 = 0; p4 < 32; ++p4) {
-        float4 kv[4], nv[8];
+        float4 kv[4], nv[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) kv[a] = *reinterpret_cast<const float4*>(bufK + (kk + 16 * a) * kLdc + 4 * p4);
 #pragma unroll
-        for (int b = 0; b < 8; ++b) nv[b] = *reinterpret_cast<const float4*>(bufN + (nn + 8 * b) * kLdc + 4 * p4);
+        for (int b = 0; b < 4; ++b) nv[b] = *reinterpret_cast<const float4*>(bufN + (nn + 16 * b) * kLdc + 4 * p4);
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
+            for (int b = 0; b < 4; ++b) {
                 acc[a][b] = fmaf(kv[a].x, nv[b].x, acc[a][b]);
                 acc[a][b] = fmaf(kv[a].y, nv[b].y, acc[a][b]);
                 acc[a][b] = fmaf(kv[a].z, nv[b].z, acc[a][b]);
                 acc[a][b] = fmaf(kv[a].w, nv[b].w, acc[a][b]);
             }
     }
-    float4* dst = reinterpret_cast<float4*>(tile + tid * 32);
+    float4* dst = reinterpret_cast<float4*>(tile + tid * 16);
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float4 v = dst[a * 2 + h];
-            v.x += acc[a][4 * h + 0];
-            v.y += acc[a][4 * h + 1];
-            v.z += acc[a][4 * h + 2];
-            v.w += acc[a][4 * h + 3];
-            dst[a * 2 + h] = v;
-        }
+    for (int a = 0; a < 4; ++a) {
+        float4 v = dst[a];
+        v.x += acc[a][0];
+        v.y += acc[a][1];
+        v.z += acc[a][2];
+        v.w += acc[a][3];
+        dst[a] = v;
+    }
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
@@ -266,21 +264,41 @@ __device__ __forceinline__ void atomic_add_quat(float* p, const Quat& q) {
     atomicAdd(p + 0, q.w); atomicAdd(p + 1, q.x); atomicAdd(p + 2, q.y); atomicAdd(p + 3, q.z);
 }
 
-template <int LAYER>
-__device__ __forceinline__ void compute_m1(float (&m1)[kHid], const float* S, const BwdMap& M, const float* __restrict__ params,
+// Two threads per pair: threads p and p + 128 (warps w and w + 4) own column p of the pass.  Each computes the half of
+// every 64-wide result whose index lies in its half h (hidden units n in [32h, 32h + 32) on the way forward, input features
+// k in the same range on the way back), so the long GEMV chains are split without partial sums to exchange; the cheap
+// per-pair geometry and the 64 x (1..7) second layers are computed by both.  The halves meet at a 64-thread named barrier.
+__device__ __forceinline__ void pair_sync(int warp4) { asm volatile("bar.sync %0, 64;" ::"r"(1 + warp4) : "memory"); }
+
+// acc[kk] += wrow[32 h + kk] * a, kk < 32
+__device__ __forceinline__ void axpy32(float (&acc)[32], const float* __restrict__ wrow_half, float a) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow_half);
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+        float4 w = w4[k4];
+        acc[4 * k4 + 0] = fmaf(w.x, a, acc[4 * k4 + 0]);
+        acc[4 * k4 + 1] = fmaf(w.y, a, acc[4 * k4 + 1]);
+        acc[4 * k4 + 2] = fmaf(w.z, a, acc[4 * k4 + 2]);
+        acc[4 * k4 + 3] = fmaf(w.w, a, acc[4 * k4 + 3]);
+    }
+}
+
+// m1[k] = relu(A_i[k] + A_j[k] + W_e[k]) for k in [k0, k0 + NK)
+template <int LAYER, int NK>
+__device__ __forceinline__ void compute_m1(float (&m1)[NK], int k0, const float* S, const BwdMap& M, const float* __restrict__ params,
                                            const float* __restrict__ ajt, int Kpad, int i, int j) {
     constexpr int H = layer_H(LAYER);
     constexpr int ld1 = 2 * H + kEdge;
-    const float* ai = S + M.f.Ai + i * kLdN;
+    const float* ai = S + M.f.Ai + i * kLdN + k0;
     const bool pep = (j >= 0 && j < kN);
-    const float* we = params + param_offset(LAYER, MSG0_W) + 2 * H + (pep ? (kN - 1 + i - j) : 0);
-    // issue all 64 L2 loads of the A_j^T column before the first use (see message_stage in egnn_forward.cu)
-    float aj[kHid];
-    const float* ajc = ajt + (j >= 0 ? j : 0);
+    const float* we = params + param_offset(LAYER, MSG0_W) + 2 * H + (pep ? (kN - 1 + i - j) : 0) + (size_t)k0 * ld1;
+    // issue all L2 loads of the A_j^T column before the first use (see message_stage in egnn_forward.cu)
+    float aj[NK];
+    const float* ajc = ajt + (j >= 0 ? j : 0) + (size_t)k0 * Kpad;
 #pragma unroll
-    for (int k = 0; k < kHid; ++k) aj[k] = __ldcg(ajc + k * Kpad);
+    for (int k = 0; k < NK; ++k) aj[k] = __ldcg(ajc + k * Kpad);
 #pragma unroll
-    for (int k = 0; k < kHid; ++k) {
+    for (int k = 0; k < NK; ++k) {
         float v = ai[k];
         if (j >= 0) v += aj[k];
         if (pep) v += __ldg(we + k * ld1);
@@ -298,6 +316,10 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
     constexpr bool IN_GRADS = (LAYER == 1);
     const LayerArgs& a = g.a;
     const int tid = threadIdx.x;
+    const int p = tid & (kBwdPairs - 1);          // this thread's pair column
+    const int half = tid >> 7, n0 = 32 * half;    // its half of every 64-wide result
+    const int warp4 = (tid >> 5) & 3;
+    const bool owner = half == 0;                 // per-pair side effects (atomics, the small dout / extras columns) happen once
     const int i = pr.i, j = pr.j;
     const bool act = pr.active;
     const bool pep = (j >= 0 && j < kN);
@@ -308,24 +330,24 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
     const int Kpad = a.Kpad;
     // offsets of this layer's tensors inside `direct` (relative to the layer's first parameter)
     constexpr int base = param_offset(LAYER, 0);
-    float dm[kHid];
-
-    {   // ---- recompute the message: m1 (registers) -> m (BufA column) ----
-        float m1[kHid];
-        compute_m1<LAYER>(m1, S, M, a.params, ajt, Kpad, i, j);
-        if (HEADS) {
-#pragma unroll 2
-            for (int n = 0; n < kHid; ++n)
-                bufA[n * kLdc + tid] = S[M.f.PkMisc + 4 * n + 3] + dot64(S + M.W2 + n * kHid, m1);
-        }
-    }
+    float dm[32];                                  // dL / d message[n0 + kk]
 
     if (HEADS) {
+        {   // ---- recompute the message: m1 (registers) -> m (BufA column), my half of the outputs ----
+            float m1[kHid];
+            compute_m1<LAYER, kHid>(m1, 0, S, M, a.params, ajt, Kpad, i, j);
+#pragma unroll 2
+            for (int nn = 0; nn < 32; ++nn) {
+                const int n = n0 + nn;
+                bufA[n * kLdc + p] = S[M.f.PkMisc + 4 * n + 3] + dot64(S + M.W2 + n * kHid, m1);
+            }
+        }
+        pair_sync(warp4);
         float m[kHid];
 #pragma unroll
-        for (int k = 0; k < kHid; ++k) m[k] = bufA[k * kLdc + tid];
+        for (int k = 0; k < kHid; ++k) m[k] = bufA[k * kLdc + p];
 #pragma unroll
-        for (int k = 0; k < kHid; ++k) dm[k] = 0.0f;
+        for (int k = 0; k < 32; ++k) dm[k] = 0.0f;
 
         const float* rg = S + M.RowG + i * 16;
         const float lse = rg[15], c_i = rg[14];
@@ -343,16 +365,23 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
             const Quat qinvj = qinv(qj);
             const Quat v = qmul(qi, qj);
             const Quat lq = qmul(qinvj, v);
-            float pre[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) pre[c] = S[M.f.Scal + SC_ROT2B + c];
 #pragma unroll 2
-            for (int n = 0; n < kHid; ++n) {
+            for (int nn = 0; nn < 32; ++nn) {
+                const int n = n0 + nn;
                 const float4 wq = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n);
                 float s = S[M.f.PkMisc + 4 * n + 2] + wq.x * lq.w + wq.y * lq.x + wq.z * lq.y + wq.w * lq.z;
                 s += dot64(S + M.Wh + HD_ROT * 4096 + n * kHid, m);
-                const float h = fmaxf(s, 0.0f);
-                bufB[n * kLdc + tid] = h;
+                bufB[n * kLdc + p] = fmaxf(s, 0.0f);
+            }
+            pair_sync(warp4);
+            float pre[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pre[c] = S[M.f.Scal + SC_ROT2B + c];
+            unsigned long long on = 0ull;
+#pragma unroll 4
+            for (int n = 0; n < kHid; ++n) {
+                const float h = bufB[n * kLdc + p];
+                on |= (unsigned long long)(h > 0.0f) << n;
                 const float4 w2 = *reinterpret_cast<const float4*>(S + M.f.PkRot2 + 4 * n);
                 pre[0] = fmaf(w2.x, h, pre[0]); pre[1] = fmaf(w2.y, h, pre[1]);
                 pre[2] = fmaf(w2.z, h, pre[2]); pre[3] = fmaf(w2.w, h, pre[3]);
@@ -367,26 +396,27 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
             const Quat ddl = qmul_grad_a(du, qinvj);      // u = dl * qinvj
             float dp2[4] = {ddl.w * dl.w * (1.0f - dl.w), ddl.x * dl.x * (1.0f - dl.x), ddl.y * dl.y * (1.0f - dl.y),
                             ddl.z * dl.z * (1.0f - dl.z)};
+            if (owner) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) sDout[c * kLdc + tid] = dp2[c];
-            sEx[0 * kLdc + tid] = lq.w; sEx[1 * kLdc + tid] = lq.x; sEx[2 * kLdc + tid] = lq.y; sEx[3 * kLdc + tid] = lq.z;
+                for (int c = 0; c < 4; ++c) sDout[c * kLdc + p] = dp2[c];
+                sEx[0 * kLdc + p] = lq.w; sEx[1 * kLdc + p] = lq.x; sEx[2 * kLdc + p] = lq.y; sEx[3 * kLdc + p] = lq.z;
+            }
             __syncthreads();
             coop_dwo(bufB, sDout, 4, direct + (param_offset(LAYER, ROT2_W) - base), direct + (param_offset(LAYER, ROT2_B) - base));
             __syncthreads();
             float dlq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 2
             for (int n = 0; n < kHid; ++n) {
-                const float h = bufB[n * kLdc + tid];
                 const float4 w2 = *reinterpret_cast<const float4*>(S + M.f.PkRot2 + 4 * n);
                 float dp = w2.x * dp2[0] + w2.y * dp2[1] + w2.z * dp2[2] + w2.w * dp2[3];
-                dp = h > 0.0f ? dp : 0.0f;
-                bufB[n * kLdc + tid] = dp;
-                axpy64(dm, S + M.Wh + HD_ROT * 4096 + n * kHid, dp);
+                dp = ((on >> n) & 1ull) ? dp : 0.0f;
+                if ((n >> 5) == half) bufB[n * kLdc + p] = dp;
+                axpy32(dm, S + M.Wh + HD_ROT * 4096 + n * kHid + n0, dp);
                 const float4 wq = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n);
                 dlq[0] = fmaf(wq.x, dp, dlq[0]); dlq[1] = fmaf(wq.y, dp, dlq[1]);
                 dlq[2] = fmaf(wq.z, dp, dlq[2]); dlq[3] = fmaf(wq.w, dp, dlq[3]);
             }
-            if (IN_GRADS && act) {
+            if (IN_GRADS && act && owner) {
                 const Quat dlqq{dlq[0], dlq[1], dlq[2], dlq[3]};
                 Quat dqinv = qmul_grad_a(dlqq, v);             // lq = qinvj * v
                 const Quat dv = qmul_grad_b(qinvj, dlqq);
@@ -407,14 +437,21 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
 
         // ================= torsion head (model.py:257-263) =================
         {
+#pragma unroll 2
+            for (int nn = 0; nn < 32; ++nn) {
+                const int n = n0 + nn;
+                const float s = S[M.f.Tt + i * kHid + n] + dot64(S + M.Wh + HD_TOR * 4096 + n * kHid, m);
+                bufB[n * kLdc + p] = fmaxf(s, 0.0f);
+            }
+            pair_sync(warp4);
             float da[PMHC_NTORS];
 #pragma unroll
             for (int c = 0; c < PMHC_NTORS; ++c) da[c] = S[M.f.Scal + SC_TOR2B + c];
-#pragma unroll 2
+            unsigned long long on = 0ull;
+#pragma unroll 4
             for (int n = 0; n < kHid; ++n) {
-                float s = S[M.f.Tt + i * kHid + n] + dot64(S + M.Wh + HD_TOR * 4096 + n * kHid, m);
-                const float h = fmaxf(s, 0.0f);
-                bufB[n * kLdc + tid] = h;
+                const float h = bufB[n * kLdc + p];
+                on |= (unsigned long long)(h > 0.0f) << n;
                 const float4 w0 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n);
                 const float4 w1 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n + 4);
                 da[0] = fmaf(w0.x, h, da[0]); da[1] = fmaf(w0.y, h, da[1]); da[2] = fmaf(w0.z, h, da[2]);
@@ -426,20 +463,19 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
             for (int c = 0; c < PMHC_NTORS; ++c) {
                 dLdw = fmaf(rg[4 + c], da[c], dLdw);
                 dda[c] = w * rg[4 + c];
-                sDout[c * kLdc + tid] = dda[c];
+                if (owner) sDout[c * kLdc + p] = dda[c];
             }
             __syncthreads();
             coop_dwo(bufB, sDout, PMHC_NTORS, direct + (param_offset(LAYER, TOR2_W) - base), direct + (param_offset(LAYER, TOR2_B) - base));
             __syncthreads();
 #pragma unroll 2
             for (int n = 0; n < kHid; ++n) {
-                const float h = bufB[n * kLdc + tid];
                 const float4 w0 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n);
                 const float4 w1 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n + 4);
                 float dp = w0.x * dda[0] + w0.y * dda[1] + w0.z * dda[2] + w0.w * dda[3] + w1.x * dda[4] + w1.y * dda[5] + w1.z * dda[6];
-                dp = h > 0.0f ? dp : 0.0f;
-                bufB[n * kLdc + tid] = dp;
-                axpy64(dm, S + M.Wh + HD_TOR * 4096 + n * kHid, dp);
+                dp = ((on >> n) & 1ull) ? dp : 0.0f;
+                if ((n >> 5) == half) bufB[n * kLdc + p] = dp;
+                axpy32(dm, S + M.Wh + HD_TOR * 4096 + n * kHid + n0, dp);
             }
             __syncthreads();
             coop_outer(bufB, bufA, tiles + T_TOR * 4096);
@@ -449,19 +485,26 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
 
         // ================= translation head (model.py:325-331) =================
         {
-            float sc = S[M.f.Scal + SC_TRN2B];
 #pragma unroll 2
+            for (int nn = 0; nn < 32; ++nn) {
+                const int n = n0 + nn;
+                const float s = S[M.f.PkMisc + 4 * n + 0] + dot64(S + M.Wh + HD_TRN * 4096 + n * kHid, m);
+                bufB[n * kLdc + p] = fmaxf(s, 0.0f);
+            }
+            pair_sync(warp4);
+            float sc = S[M.f.Scal + SC_TRN2B];
+            unsigned long long on = 0ull;
+#pragma unroll 4
             for (int n = 0; n < kHid; ++n) {
-                float s = S[M.f.PkMisc + 4 * n + 0] + dot64(S + M.Wh + HD_TRN * 4096 + n * kHid, m);
-                const float h = fmaxf(s, 0.0f);
-                bufB[n * kLdc + tid] = h;
+                const float h = bufB[n * kLdc + p];
+                on |= (unsigned long long)(h > 0.0f) << n;
                 sc = fmaf(S[M.f.PkMisc + 4 * n + 1], h, sc);
             }
             const float dXr = rg[11] * rx + rg[12] * ry + rg[13] * rz;
             dLdw = fmaf(sc, dXr, dLdw);
             const float ds = w * dXr;
-            sDout[tid] = ds;
-            if (IN_GRADS && act) {
+            if (owner) sDout[p] = ds;
+            if (IN_GRADS && act && owner) {
                 const float f = w * sc;
                 atomicAdd(S + M.dX + i * 3 + 0, f * rg[11]); atomicAdd(S + M.dX + i * 3 + 1, f * rg[12]); atomicAdd(S + M.dX + i * 3 + 2, f * rg[13]);
                 if (pep) {
@@ -473,10 +516,9 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
             __syncthreads();
 #pragma unroll 2
             for (int n = 0; n < kHid; ++n) {
-                const float h = bufB[n * kLdc + tid];
-                const float dp = h > 0.0f ? S[M.f.PkMisc + 4 * n + 1] * ds : 0.0f;
-                bufB[n * kLdc + tid] = dp;
-                axpy64(dm, S + M.Wh + HD_TRN * 4096 + n * kHid, dp);
+                const float dp = ((on >> n) & 1ull) ? S[M.f.PkMisc + 4 * n + 1] * ds : 0.0f;
+                if ((n >> 5) == half) bufB[n * kLdc + p] = dp;
+                axpy32(dm, S + M.Wh + HD_TRN * 4096 + n * kHid + n0, dp);
             }
             __syncthreads();
             coop_outer(bufB, bufA, tiles + T_TRN * 4096);
@@ -490,34 +532,40 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
             const float dotq = qdot(qi, qj);
             const float qd = dotq * dotq;
 #pragma unroll 2
-            for (int n = 0; n < kHid; ++n) {
+            for (int nn = 0; nn < 32; ++nn) {
+                const int n = n0 + nn;
                 const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
-                float s = (pk.z + dot64(S + M.Wh + HD_ATT * 4096 + n * kHid, m)) + fmaf(pk.y, qd, pk.x * -d2);  // same order as the forward
-                bufB[n * kLdc + tid] = fmaxf(s, 0.0f);
+                const float s = (pk.z + dot64(S + M.Wh + HD_ATT * 4096 + n * kHid, m)) + fmaf(pk.y, qd, pk.x * -d2);  // same order as the forward
+                bufB[n * kLdc + p] = fmaxf(s, 0.0f);
             }
+            pair_sync(warp4);
+            unsigned long long on = 0ull;
+#pragma unroll 4
+            for (int n = 0; n < kHid; ++n) on |= (unsigned long long)(bufB[n * kLdc + p] > 0.0f) << n;
             // softmax backward with the saved row statistics.  A fully saturated row (w == 1 exactly, every other
             // weight underflowed) has g - sum_k w_k g_k == 0 exactly in the reference's autograd; here c_i comes from
             // the forward's aggregates, so the same difference would be rounding noise (~1e-7 |g|) that the d2 input
             // of attention_mlp.0 (thousands of A^2) then amplifies — define it as the exact zero it is.
             const float dlogit = (w == 1.0f) ? 0.0f : w * (dLdw - c_i);
-            sDout[tid] = dlogit;
-            sEx[0 * kLdc + tid] = -d2;
-            sEx[1 * kLdc + tid] = qd;
+            if (owner) {
+                sDout[p] = dlogit;
+                sEx[0 * kLdc + p] = -d2;
+                sEx[1 * kLdc + p] = qd;
+            }
             __syncthreads();
             coop_dwo(bufB, sDout, 1, direct + (param_offset(LAYER, ATT2_W) - base), direct + (param_offset(LAYER, ATT2_B) - base));
             __syncthreads();
             float gd = 0.0f, gq = 0.0f;
 #pragma unroll 2
             for (int n = 0; n < kHid; ++n) {
-                const float h = bufB[n * kLdc + tid];
                 const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
-                const float dp = h > 0.0f ? pk.w * dlogit : 0.0f;
-                bufB[n * kLdc + tid] = dp;
-                axpy64(dm, S + M.Wh + HD_ATT * 4096 + n * kHid, dp);
+                const float dp = ((on >> n) & 1ull) ? pk.w * dlogit : 0.0f;
+                if ((n >> 5) == half) bufB[n * kLdc + p] = dp;
+                axpy32(dm, S + M.Wh + HD_ATT * 4096 + n * kHid + n0, dp);
                 gd = fmaf(pk.x, dp, gd);
                 gq = fmaf(pk.y, dp, gq);
             }
-            if (IN_GRADS && act) {
+            if (IN_GRADS && act && owner) {
                 const float f = -gd * 2.0f;                 // d(-d2) = gd
                 atomicAdd(S + M.dX + i * 3 + 0, f * rx); atomicAdd(S + M.dX + i * 3 + 1, f * ry); atomicAdd(S + M.dX + i * 3 + 2, f * rz);
                 const float fq = gq * 2.0f * dotq;
@@ -535,46 +583,48 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
         }
         if (LAYER == 0) {
 #pragma unroll
-            for (int k = 0; k < kHid; ++k) dm[k] += S[M.dMsum + i * kHid + k];
+            for (int k = 0; k < 32; ++k) dm[k] += S[M.dMsum + i * kHid + n0 + k];
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < kHid; ++k) dm[k] = mult * S[M.dMsum + i * kHid + k];
+        for (int k = 0; k < 32; ++k) dm[k] = mult * S[M.dMsum + i * kHid + n0 + k];
     }
 
     // ---- message MLP backward: dW2 += dm (x) m1, dm1 = relu'(.) W2^T dm, then the per-node reductions ----
-#pragma unroll
-    for (int k = 0; k < kHid; ++k) bufB[k * kLdc + tid] = act ? dm[k] : 0.0f;
-    float dm1[kHid];
+    float dm1[32];
     {
-        float m1[kHid];
-        compute_m1<LAYER>(m1, S, M, a.params, ajt, Kpad, i, j);
+        float m1h[32];
+        compute_m1<LAYER, 32>(m1h, n0, S, M, a.params, ajt, Kpad, i, j);
 #pragma unroll
-        for (int k = 0; k < kHid; ++k) bufA[k * kLdc + tid] = m1[k];
-    }
+        for (int k = 0; k < 32; ++k) {
+            bufB[(n0 + k) * kLdc + p] = act ? dm[k] : 0.0f;
+            bufA[(n0 + k) * kLdc + p] = m1h[k];
+        }
+        pair_sync(warp4);
 #pragma unroll
-    for (int k = 0; k < kHid; ++k) dm1[k] = 0.0f;
+        for (int k = 0; k < 32; ++k) dm1[k] = 0.0f;
 #pragma unroll 2
-    for (int n = 0; n < kHid; ++n) axpy64(dm1, S + M.W2 + n * kHid, bufB[n * kLdc + tid]);
+        for (int n = 0; n < kHid; ++n) axpy32(dm1, S + M.W2 + n * kHid + n0, bufB[n * kLdc + p]);
 #pragma unroll
-    for (int k = 0; k < kHid; ++k) dm1[k] = bufA[k * kLdc + tid] > 0.0f ? dm1[k] : 0.0f;
+        for (int k = 0; k < 32; ++k) dm1[k] = m1h[k] > 0.0f ? dm1[k] : 0.0f;
+    }
     __syncthreads();
     coop_outer(bufB, bufA, tiles + T_W2 * 4096);
     coop_bias_extras(bufB, sEx, 0, direct + (param_offset(LAYER, MSG2_B) - base), nullptr, 0);
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kHid; ++k) bufB[k * kLdc + tid] = dm1[k];
+    for (int k = 0; k < 32; ++k) bufB[(n0 + k) * kLdc + p] = dm1[k];
     if (act && pep) {
-        float* dj = S + M.dAjPep + j * kLdN;
-        float* de = S + M.dWe + (kN - 1 + i - j) * kLdN;
+        float* dj = S + M.dAjPep + j * kLdN + n0;
+        float* de = S + M.dWe + (kN - 1 + i - j) * kLdN + n0;
 #pragma unroll 8
-        for (int k = 0; k < kHid; ++k) {
+        for (int k = 0; k < 32; ++k) {
             atomicAdd(dj + k, dm1[k]);
             atomicAdd(de + k, dm1[k]);
         }
     } else if (act && !HEADS && j >= kN) {
         // masked pocket slot with non-zero features (rare): straight to the A_j^T gradient scratch
-        for (int k = 0; k < kHid; ++k) atomicAdd(dajt + k * Kpad + j, dm1[k]);
+        for (int k = 0; k < 32; ++k) atomicAdd(dajt + (n0 + k) * Kpad + j, dm1[k]);
     }
     __syncthreads();
     accumulate_rows(bufB, S + M.dAi, kLdN, I, L, Wr, pass_base, npass);
@@ -742,10 +792,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
 
         // ---------------- attention-carrying pairs ----------------
         const int total = L > 0 ? L * W : 0;
-        for (int pass_base = 0; pass_base < total; pass_base += kBwdThreads) {
-            const int npass = min(kBwdThreads, total - pass_base);
-            const bool act = tid < npass;
-            const PairRef pr = decode_full_pair(I, act ? pass_base + tid : pass_base, W, L, 0, act);
+        const int pcol = tid & (kBwdPairs - 1);      // two threads (tid, tid + 128) per pair column
+        for (int pass_base = 0; pass_base < total; pass_base += kBwdPairs) {
+            const int npass = min(kBwdPairs, total - pass_base);
+            const bool act = pcol < npass;
+            const PairRef pr = decode_full_pair(I, act ? pass_base + pcol : pass_base, W, L, 0, act);
             pair_pass<LAYER, true>(S, M, g, pr, 1.0f, b, ajt, dajt, tiles, direct, I, L, W, pass_base, npass, ci.nv, L - 1);
         }
         // ---------------- layer 1: message-only pairs (self, masked peptide / pocket slots) ----------------
@@ -753,10 +804,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
             const int npx = kN - L;
             const int W2 = 1 + npx + ci.nx + (ci.c0 > 0 ? 1 : 0);
             const int total2 = L * W2;
-            for (int pass_base = 0; pass_base < total2; pass_base += kBwdThreads) {
-                const int npass = min(kBwdThreads, total2 - pass_base);
-                const bool act = tid < npass;
-                const int gp = act ? pass_base + tid : pass_base;
+            for (int pass_base = 0; pass_base < total2; pass_base += kBwdPairs) {
+                const int npass = min(kBwdPairs, total2 - pass_base);
+                const bool act = pcol < npass;
+                const int gp = act ? pass_base + pcol : pass_base;
                 const int rl = gp / W2, e = gp - rl * W2;
                 PairRef pr;
                 pr.i = I[IN_ROWS + rl];
@@ -838,8 +889,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
     __syncthreads();
     for (int idx = tid; idx < kTileFloats; idx += kBwdThreads) {
         int T = idx >> 12, r = idx & 4095;
-        int t = r >> 5, e = r & 31;
-        int k = (t & 15) + 16 * (e >> 3), n = (t >> 4) + 8 * (e & 7);
+        int t = r >> 4, e = r & 15;
+        int k = (t & 15) + 16 * (e >> 2), n = (t >> 4) + 16 * (e & 3);
         int off, ld;
         switch (T) {
             case T_W2: off = param_offset(LAYER, MSG2_W); ld = 64; break;
