@@ -292,17 +292,23 @@ __device__ __forceinline__ void compute_m1(float (&m1)[NK], int k0, const float*
     const float* ai = S + M.f.Ai + i * kLdN + k0;
     const bool pep = (j >= 0 && j < kN);
     const float* we = params + param_offset(LAYER, MSG0_W) + 2 * H + (pep ? (kN - 1 + i - j) : 0) + (size_t)k0 * ld1;
-    // issue all L2 loads of the A_j^T column before the first use (see message_stage in egnn_forward.cu)
-    float aj[NK];
+    // 16 features at a time: all their L2 loads (the A_j^T column, the relative-position column of peptide pairs) are in
+    // flight before the first use
     const float* ajc = ajt + (j >= 0 ? j : 0) + (size_t)k0 * Kpad;
 #pragma unroll
-    for (int k = 0; k < NK; ++k) aj[k] = __ldcg(ajc + k * Kpad);
+    for (int kb = 0; kb < NK; kb += 16) {
+        float aj[16], wr[16];
 #pragma unroll
-    for (int k = 0; k < NK; ++k) {
-        float v = ai[k];
-        if (j >= 0) v += aj[k];
-        if (pep) v += __ldg(we + k * ld1);
-        m1[k] = fmaxf(v, 0.0f);
+        for (int k = 0; k < 16; ++k) aj[k] = __ldcg(ajc + (kb + k) * Kpad);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) wr[k] = pep ? __ldg(we + (kb + k) * ld1) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float v = ai[kb + k];
+            if (j >= 0) v += aj[k];
+            if (pep) v += wr[k];
+            m1[kb + k] = fmaxf(v, 0.0f);
+        }
     }
 }
 
@@ -836,6 +842,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
                     if (cc < PMHC_NFEAT) {
                         const float* pf = a.pocket_feat + (size_t)b * P * PMHC_NFEAT + cc;
                         const float* dj = dajt + k * Kpad + kN;
+#pragma unroll 8
                         for (int p = 0; p < P; ++p) acc = fmaf(__ldcg(dj + p), __ldg(pf + p * PMHC_NFEAT), acc);
                     }
                 } else {
