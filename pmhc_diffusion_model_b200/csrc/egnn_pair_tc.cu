@@ -35,7 +35,11 @@ constexpr int kEngines = 2;
 constexpr int kEngThreads = 128;                 // compute threads of one engine (one per pair row / TMEM lane)
 constexpr int kComputeThreads = kEngines * kEngThreads;
 constexpr int kThreads = kComputeThreads + 128;  // + one warpgroup: warp 8 / 9 issue the MMAs of engine 0 / 1, two warps idle
-constexpr int kRegsCompute = 232, kRegsIssue = 40;   // setmaxnreg budgets (256 * 232 + 128 * 40 <= 64 K registers)
+// setmaxnreg budgets.  An increase only succeeds out of the registers the CTA was LAUNCHED with (384 threads x the 168 ptxas
+// allots under __launch_bounds__(384, 1) = 64 512): 256 * 232 + 128 * 40 = 64 512 uses exactly that pool; a larger sum makes
+// the increase wait for ever.
+constexpr int kRegsCompute = 232, kRegsIssue = 40;
+static_assert(kComputeThreads * kRegsCompute + 128 * kRegsIssue <= kThreads * 168, "setmaxnreg budgets exceed the launch pool");
 constexpr int kTile = 128;
 constexpr int kEngCols = 256;                 // TMEM columns per engine
 // TMEM columns of one engine, relative to its base
