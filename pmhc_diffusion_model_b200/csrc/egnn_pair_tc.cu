@@ -71,11 +71,13 @@ struct PairArgs {
     float* ssum_out;                 // layer 1: [B,16,64] sum_j m1_ij (before message_mlp.2), zero for padded rows
     float* rowstat;                  // training only
     float* logit_out;                // training only: [B,16,Kpad]
+    const int* order;                // [B] complexes sorted by pair count, largest first (work item -> complex); nullable
     int cap_pairs;                   // pairs buffered per row group
     int aj_rows;                     // rows of A_j kept in shared memory: 16 (peptide only) or 16 + P
 };
 
-// Work of one engine.  Complexes are dealt round-robin over the E = 2 * gridDim.x engines; when the last round is only
+// Work of one engine.  Complexes — taken in the order of `order`, largest first, so that a round holds complexes of
+// similar size when peptide lengths and pocket sizes are mixed — are dealt round-robin over the E = 2 * gridDim.x engines; when the last round is only
 // partly filled (rem < E complexes left), each of its complexes is split by peptide rows into `parts` pieces handled by
 // different engines, so the tail of the launch costs a fraction of a complex instead of a whole one.  Engine slots are
 // ordered "first engine of every CTA, then the second", so a thin tail spreads over the SMs.
@@ -83,23 +85,25 @@ constexpr int kMaxParts = 4;
 struct Work {
     int b, part, parts;
 };
-__device__ __forceinline__ bool get_work(int k, int cta, int eng, int ctas, int B, Work& w) {
+__device__ __forceinline__ bool get_work(int k, int cta, int eng, int ctas, int B, const int* __restrict__ order, Work& w) {
     const int E = ctas * kEngines;
     const int full = B / E, rem = B - full * E;
+    int item;
     if (k < full) {
-        w.b = k * E + cta * kEngines + eng;
+        item = k * E + cta * kEngines + eng;
         w.part = 0;
         w.parts = 1;
-        return true;
+    } else {
+        if (k > full || rem == 0) return false;
+        int S = E / rem;
+        S = S > kMaxParts ? kMaxParts : S;
+        const int slot = eng * ctas + cta;
+        if (slot >= rem * S) return false;
+        item = full * E + slot / S;
+        w.part = slot - (slot / S) * S;
+        w.parts = S;
     }
-    if (k > full || rem == 0) return false;
-    int S = E / rem;
-    S = S > kMaxParts ? kMaxParts : S;
-    const int slot = eng * ctas + cta;
-    if (slot >= rem * S) return false;
-    w.b = full * E + slot / S;
-    w.part = slot - (slot / S) * S;
-    w.parts = S;
+    w.b = order != nullptr ? __ldg(order + item) : item;
     return true;
 }
 // real peptide rows [beg, end) of a part
@@ -745,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
                      bars + 4 * eng, 0u, tc::smem_u32(smem), tc::smem_u32(smem + M.cta_bytes + eng * M.eng_bytes), 0u};
             const int* I = E.ints();
             Work wk;
-            for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.B, wk); ++k) {
+            for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.B, a.order, wk); ++k) {
                 E.sync_all();   // the compute threads have set the complex up
                 ComplexInfo ci;
                 ci.L = I[IN_POCKET + a.Kpad + 0];
@@ -802,7 +806,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
         PMHC_TS();
 
         Work wk;
-        for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.B, wk); ++k) {
+        for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.B, a.order, wk); ++k) {
             const int b = wk.b;
             PMHC_TS();
             const ComplexInfo ci = setup_engine(E, b, LAYER == 0);
@@ -987,6 +991,54 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
     tc::fence_before_thread_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// order_kernel — once per batch / trajectory: complexes sorted by their number of attention-carrying pairs
+// L (L - 1 + valid pocket slots), largest first (a counting sort by one CTA; equal keys keep their order, so the result is
+// deterministic).  The pair kernels deal work items in this order: with mixed peptide lengths and pocket sizes every round
+// then holds complexes of similar size, and the small ones end up in the row-split tail.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kOrderBins = kN * (kN - 1 + kMaxP) + 1;
+__global__ void __launch_bounds__(1024) order_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ pocket_mask, int B, int P,
+                                                     int* __restrict__ keys, int* __restrict__ order) {
+    extern __shared__ int bins[];      // [kOrderBins] counts, then starting offsets (descending key)
+    __shared__ int carry;
+    const int tid = threadIdx.x;
+    for (int k = tid; k < kOrderBins; k += blockDim.x) bins[k] = 0;
+    __syncthreads();
+    for (int b = tid; b < B; b += blockDim.x) {
+        int L = 0, nv = 0;
+        for (int i = 0; i < kN; ++i) L += mask[(size_t)b * kN + i] != 0;
+        for (int j = 0; j < P; ++j) nv += pocket_mask[(size_t)b * P + j] != 0;
+        const int key = L * (L - 1 + nv);
+        keys[b] = key;
+        atomicAdd(&bins[key], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {                    // exclusive scan from the largest key down (7 921 bins: microseconds, once per trajectory)
+        int run = 0;
+        for (int k = kOrderBins - 1; k >= 0; --k) {
+            const int c = bins[k];
+            bins[k] = run;
+            run += c;
+        }
+        carry = run;
+    }
+    __syncthreads();
+    if (B <= 4096) {
+        // stable placement: complex b goes after the complexes with the same key and a smaller index (O(B) per complex)
+        for (int b = tid; b < B; b += blockDim.x) {
+            const int key = keys[b];
+            int before = 0;
+            for (int c = 0; c < b; ++c) before += keys[c] == key;
+            order[bins[key] + before] = b;
+        }
+    } else {
+        // very large batches: first come, first placed within a key (only the schedule depends on it, not the results)
+        for (int b = tid; b < B; b += blockDim.x) order[atomicAdd(&bins[keys[b]], 1)] = b;
+    }
+    (void)carry;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1289,6 +1341,8 @@ struct Tc2Workspace {
     uint8_t* cls;              // [B,cls_stride]
     uint8_t* wimage;           // [2][image_bytes]
     uint8_t* nm_image;         // node_mid operand tiles
+    int* order;                // [B] work order of the pair kernels
+    int* keys;                 // [B] scratch of order_kernel
     int cls_stride, image_bytes;
     size_t bytes;
 };
@@ -1306,6 +1360,8 @@ Tc2Workspace carve_tc2(void* base, int B, int P) {
     w.cls = (uint8_t*)take((size_t)B * w.cls_stride);
     w.wimage = (uint8_t*)take((size_t)2 * w.image_bytes);
     w.nm_image = (uint8_t*)take((size_t)tc2::NM_BAR);
+    w.order = (int*)take((size_t)B * sizeof(int));
+    w.keys = (int*)take((size_t)B * sizeof(int));
     w.bytes = o;
     return w;
 }
@@ -1371,6 +1427,8 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
         tc2::node_pre_kernel<<<B, 128, smem, stream>>>(params, bt->features, bt->pocket_features, bt->pocket_mask, P, w.cls_stride,
                                                        w.pk_cache, w.cls, w.aij1);
         PMHC_CHECK_LAUNCH("node_pre");
+        tc2::order_kernel<<<1, 1024, tc2::kOrderBins * sizeof(int), stream>>>(bt->mask, bt->pocket_mask, B, P, w.keys, w.order);
+        PMHC_CHECK_LAUNCH("order");
     }
     tc2::PairArgs a{};
     a.B = B; a.P = P; a.Kpad = pad_k(P);
@@ -1378,6 +1436,7 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
     a.frames_in = bt->frames; a.tors_in = bt->torsions; a.mask = bt->mask;
     a.pocket_frames = bt->pocket_frames; a.pocket_cls = w.cls; a.cls_stride = w.cls_stride; a.pk_cache = w.pk_cache;
     a.aij = w.aij1; a.wimage = w.wimage;
+    a.order = w.order;
     a.dbg = g_tc2_dbg;
     a.frames_out = frames1; a.tors_out = tors1; a.ssum_out = w.ssum;
     a.rowstat = rowstat1; a.logit_out = logits1;
