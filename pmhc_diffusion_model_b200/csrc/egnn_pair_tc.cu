@@ -118,8 +118,8 @@ struct Map {
     int total_bytes;
 };
 // Misc words: [0,16) second-layer biases (fp32) in D3 order; [16,80) layer 1: time column of message_mlp.0 as bf16x2
-// (A_i part | A_j part)
-constexpr int MISC_B2ND = 0, MISC_TIME = 16, MISC_FLOATS = 80;
+// (A_i part | A_j part); [80,144) attention_mlp.2.weight in fp32 (the attention logit is finished on the CUDA cores)
+constexpr int MISC_B2ND = 0, MISC_TIME = 16, MISC_ATT2 = 80, MISC_FLOATS = 144;
 
 __host__ __device__ inline Map make_map(int Kpad, int cap_pairs, int aj_rows) {
     Map m;
@@ -246,6 +246,7 @@ __device__ inline void build_weight_image(uint8_t* smem, const Map& M, const flo
         else if (tid == 12) v = params[param_offset(L, TRN2_B)];
         misc[MISC_B2ND + tid] = v;
     }
+    for (int n = tid; n < 64; n += kThreads) misc[MISC_ATT2 + n] = params[param_offset(L, ATT2_W) + n];
     if (LAYER == 0) {
         for (int w = tid; w < 64; w += kThreads) {
             const int k = 2 * (w & 31), col = w < 32 ? PMHC_NFEAT : H + PMHC_NFEAT;
@@ -404,21 +405,13 @@ __device__ __forceinline__ void mma_head(const Engine& E, uint32_t cta, uint32_t
     for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + dst, tm + TM_A2 + 8 * s, db + 2 * s, id, s > 0);
     tc::mma_bf16_ts(tm + dst, tm + (h < 2 ? TM_XA : TM_XB), dx, id, 1);
 }
-// second layer of head h on its packed hidden units: D3 (+)= A3 . W3_h^T  (W3 blocks: 0 att hi, 1 rot, 2 tor, 3 trn, 4 att lo)
-__device__ __forceinline__ void mma_second(const Engine& E, uint32_t cta, uint32_t tm, int h, int src) {
+// second layer of head h (1 rotation, 2 torsion, 3 translation) on its packed hidden units: D3 (+)= A3 . W3_h^T.  The
+// attention head's second layer (64 -> 1) is a dot product on the CUDA cores, in fp32 (attention_logit below).
+__device__ __forceinline__ void mma_second(const Engine& E, uint32_t cta, uint32_t tm, int h, int src, bool first) {
     constexpr uint32_t id = tc::idesc_bf16_f32(128, 16);
     const uint32_t w3 = cta + E.M.W3b;
-    if (h == 0) {   // attention: hi.W hi + lo.W hi + hi.W lo
 #pragma unroll
-        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + src + 8 * s, tc::smem_desc_sw128(w3) + 2 * s, id, s > 0);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + src + 32 + 8 * s, tc::smem_desc_sw128(w3) + 2 * s, id, 1);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + src + 8 * s, tc::smem_desc_sw128(w3 + 4 * 2048) + 2 * s, id, 1);
-    } else {
-#pragma unroll
-        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + src + 8 * s, tc::smem_desc_sw128(w3 + h * 2048) + 2 * s, id, 1);
-    }
+    for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + TM_D3, tm + src + 8 * s, tc::smem_desc_sw128(w3 + h * 2048) + 2 * s, id, (first && s == 0) ? 0u : 1u);
 }
 
 // extras of the (attention, rotation) half for this pair
@@ -481,29 +474,35 @@ __device__ __forceinline__ void epilogue2(const Engine& E, int buf) {
     }
     tc::tmem_st32(E.tmem + E.lane_base + buf, pk);
 }
-// attention head: its hidden units see -d2 and reach 1e2..1e3, so they go to the second layer as hi + lo
-// (hi = relu(x) truncated to bf16 by a byte permute, lo = bf16(relu(x) - hi): ~16 mantissa bits): 64 columns in place
-__device__ __forceinline__ void epilogue2_att(const Engine& E, int buf) {
+// attention head: logit = attention_mlp.2 . relu(hidden) + bias (model.py:241-243) straight from the fp32 accumulators.  The
+// hidden units see -d2 and reach 1e2..1e3, so a bf16 second layer would need a hi + lo split of both operands (three MMAs
+// and a 64-column repack); 64 FMAs per pair on the CUDA cores are cheaper than that repack, exact in fp32, and take one MMA
+// round trip out of the tile.  The buffer is free for the next head as soon as the loads have landed.
+__device__ __forceinline__ float attention_logit(const Engine& E, int buf) {
     uint32_t v0[32], v1[32];
     tc::tmem_ld32_nowait(E.tmem + E.lane_base + buf, v0);
     tc::tmem_ld32_nowait(E.tmem + E.lane_base + buf + 32, v1);
+    const float4* w = reinterpret_cast<const float4*>(E.smem + E.M.Misc) + MISC_ATT2 / 4;
     tc::tmem_wait_ld();
-    uint32_t pk[32], pl[32];
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        const uint32_t* v = c < 16 ? v0 : v1;
-        const float x0 = fmaxf(__uint_as_float(v[2 * (c & 15)]), 0.0f), x1 = fmaxf(__uint_as_float(v[2 * (c & 15) + 1]), 0.0f);
-        const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
-        pk[c] = __byte_perm(u0, u1, 0x7632);
-        pl[c] = tc::pack_bf16x2(x0 - __uint_as_float(u0 & 0xFFFF0000u), x1 - __uint_as_float(u1 & 0xFFFF0000u));
+    for (int c = 0; c < 8; ++c) {
+        const float4 a = w[c], b = w[8 + c];
+        s0 = fmaf(a.x, fmaxf(__uint_as_float(v0[4 * c + 0]), 0.0f), s0);
+        s1 = fmaf(a.y, fmaxf(__uint_as_float(v0[4 * c + 1]), 0.0f), s1);
+        s2 = fmaf(a.z, fmaxf(__uint_as_float(v0[4 * c + 2]), 0.0f), s2);
+        s3 = fmaf(a.w, fmaxf(__uint_as_float(v0[4 * c + 3]), 0.0f), s3);
+        s0 = fmaf(b.x, fmaxf(__uint_as_float(v1[4 * c + 0]), 0.0f), s0);
+        s1 = fmaf(b.y, fmaxf(__uint_as_float(v1[4 * c + 1]), 0.0f), s1);
+        s2 = fmaf(b.z, fmaxf(__uint_as_float(v1[4 * c + 2]), 0.0f), s2);
+        s3 = fmaf(b.w, fmaxf(__uint_as_float(v1[4 * c + 3]), 0.0f), s3);
     }
-    tc::tmem_st32(E.tmem + E.lane_base + buf, pk);
-    tc::tmem_st32(E.tmem + E.lane_base + buf + 32, pl);
+    return (s0 + s1) + (s2 + s3);
 }
 
 // D3 -> per-pair outputs: logit, global delta quaternion, delta angles, scale * (x_i - x_j)   (model.py:243-331)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ void epilogue3(const Engine& E, const PairRef& pr, int slot, float* __restrict__ lsave) {
+__device__ __forceinline__ void epilogue3(const Engine& E, const PairRef& pr, int slot, float* __restrict__ lsave, float att) {
     float o[16];
     tc::tmem_ld16(E.tmem + E.lane_base + TM_D3, o);
     const float4* b2nd = reinterpret_cast<const float4*>(E.smem + E.M.Misc) + MISC_B2ND / 4;
@@ -519,7 +518,7 @@ __device__ __forceinline__ void epilogue3(const Engine& E, const PairRef& pr, in
     const float sc = o[12] + b3.x;
     if (pr.active) {
         float* out = reinterpret_cast<float*>(E.es + E.M.Out) + slot * kOutPerPair;
-        const float logit = o[0] + b0.x;
+        const float logit = att + b0.x;
         out[0] = logit;
         out[1] = dg.w; out[2] = dg.x; out[3] = dg.y; out[4] = dg.z;
         out[5] = o[5] + b1.y; out[6] = o[6] + b1.z; out[7] = o[7] + b1.w;
@@ -769,22 +768,18 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
                             mma_head(E, cta, tm, 1, TM_Y); E.commit(BY);
                             mma_head(E, cta, tm, 2, TM_Z); E.commit(BZ);
                         });
-                        E.serve([&] {
+                        E.serve([&] {   // the compute threads have read the attention hidden units out of X: X is free
                             const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
-                            mma_second(E, cta, tm, 0, TM_X); E.commit(BX);
-                        });
-                        E.serve([&] {   // the compute threads have seen the attention second layer complete: X is free
-                            const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
-                            mma_second(E, cta, tm, 1, TM_Y);
+                            mma_second(E, cta, tm, 1, TM_Y, true);
                             mma_head(E, cta, tm, 3, TM_X); E.commit(BX);
                         });
                         E.serve([&] {
                             const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
-                            mma_second(E, cta, tm, 2, TM_Z); E.commit(BZ);
+                            mma_second(E, cta, tm, 2, TM_Z, false); E.commit(BZ);
                         });
                         E.serve([&] {
                             const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
-                            mma_second(E, cta, tm, 3, TM_X); E.commit(BM);
+                            mma_second(E, cta, tm, 3, TM_X, false); E.commit(BM);
                         });
                     }
                 }
@@ -910,13 +905,11 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
                     PMHC_TS();   // 4 next tile staged
                     E.wait(BX);
                     PMHC_TS();   // 5 attention hidden ready
-                    epilogue2_att(E, TM_X);
-                    E.request();           // attention second layer
+                    const float att = attention_logit(E, TM_X);   // second layer on the CUDA cores; X is free once read
                     PMHC_TS();   // 6
                     E.wait(BY);
                     PMHC_TS();   // 7 rotation hidden ready
                     epilogue2(E, TM_Y);
-                    E.wait(BX);            // attention second layer done: X is free
                     E.request();           // rotation second layer, translation -> X
                     PMHC_TS();   // 8
                     E.wait(BZ);
@@ -931,7 +924,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
                     PMHC_TS();   // 11
                     E.wait(BM);
                     PMHC_TS();   // 12 second layers done
-                    epilogue3(E, pr, slot, lsave);
+                    epilogue3(E, pr, slot, lsave, att);
                     PMHC_TS();   // 13
                     pr = nxt;
                     slot = nslot;
