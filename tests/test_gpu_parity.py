@@ -618,3 +618,45 @@ def test_bf16_forward_training_gradients_vs_oracle_autograd(api):
             bad.append((k, err, scale))
     assert not bad, bad
     assert worst > 0.0      # the bf16 forward really ran
+
+
+def test_bf16_forward_mixed_sizes_and_large_batch_schedule(api):
+    """The pair kernels deal complexes largest-first (order_kernel: stable counting sort up to 4 096 complexes, first come
+    first placed above).  Every complex must be processed exactly once and its rows must not depend on the schedule:
+    a 4 500-complex batch of mixed sizes equals the same complexes run in slices, bitwise."""
+    B = 4500
+    batch = orc.synthetic_batch(B, (1, 16), (0, 24), P_pad=24, seed=97)
+    model = make_model(api, orc.random_params(seed=21), 100)
+    model.precision = "bf16"
+    gb = gpu_batch(batch)
+    with torch.no_grad():
+        full = model(dict(gb), 60)
+        f, t = full["frames"].to_tensor_7(), full["torsions"]
+        assert torch.isfinite(f).all() and torch.isfinite(t).all()
+        for s in (0, 1234, 4096, 4490):
+            part = model({k: v[s:s + 10] for k, v in gb.items()}, 60)
+            assert torch.equal(f[s:s + 10], part["frames"].to_tensor_7()) and torch.equal(t[s:s + 10], part["torsions"])
+        model.precision = "fp32"
+        ref = model({k: v[:300] for k, v in gb.items()}, 60)
+    m = batch["mask"][:300].to(DEV)
+    sel = m & ((m.sum(-1, keepdim=True) - 1 + gb["pocket_mask"][:300].sum(-1, keepdim=True)) > 0)
+    assert rel_err(f[:300][sel], ref["frames"].to_tensor_7()[sel]) < TOL_BF16
+    assert rel_err(t[:300][sel], ref["torsions"][sel]) < TOL_BF16
+
+
+def test_bf16_forward_largest_pocket(api):
+    """pocket_maxlen = 480 (the largest the kernels accept): the tensor-core layer still fits (neighbour projections stay in
+    L2 instead of shared memory) and agrees with the fp32 path."""
+    batch = orc.synthetic_batch(3, (8, 15), (400, 480), P_pad=480, seed=98)
+    model = make_model(api, orc.random_params(seed=22), 100)
+    gb = gpu_batch(batch)
+    with torch.no_grad():
+        model.precision = "bf16"
+        out = model(dict(gb), 17)
+        model.precision = "fp32"
+        ref = model(dict(gb), 17)
+    m = batch["mask"].to(DEV)
+    assert rel_err(out["frames"].to_tensor_7()[m], ref["frames"].to_tensor_7()[m]) < TOL_BF16
+    assert rel_err(out["torsions"][m], ref["torsions"][m]) < TOL_BF16
+    with pytest.raises(RuntimeError, match="pocket_maxlen"):
+        model({k: (torch.cat((v, v), 1) if k.startswith("pocket") else v) for k, v in gb.items()}, 17)
