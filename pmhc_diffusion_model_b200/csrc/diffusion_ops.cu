@@ -34,15 +34,23 @@ __device__ __forceinline__ void write_noise(float* fr, float* tors, float n0, fl
 // One residue's noise from the counter-based stream: counter = global residue index, 4 Philox blocks (a: the three
 // normals, b: Shoemake coordinates + torsion 0, c: torsions 1..4, d: torsions 5, 6).  Split by output part so that the
 // per-residue kernels and the 8-lanes-per-residue fused reverse step run the very same arithmetic.
-__device__ __forceinline__ void philox_frame_noise(uint64_t seed, uint64_t ctr, float* fr) {
-    Philox4 a = philox4x32_10(ctr, 0, seed), b = philox4x32_10(ctr, 1, seed);
+__device__ __forceinline__ void philox_translation_noise(uint64_t seed, uint64_t ctr, float* x) {
+    Philox4 a = philox4x32_10(ctr, 0, seed);
     // Box-Muller on (a0,a1) and (a2,a3)
     float r0 = sqrtf(-2.0f * logf(u32_to_unit(a.v[0]))), r1 = sqrtf(-2.0f * logf(u32_to_unit(a.v[2])));
     float s0, c0, s1, c1;
     sincosf(kTwoPi * u32_to_unit(a.v[1]), &s0, &c0);
     sincosf(kTwoPi * u32_to_unit(a.v[3]), &s1, &c1);
-    Quat q = shoemake(u32_to_unit(b.v[0]), u32_to_unit(b.v[1]), u32_to_unit(b.v[2]));
-    store_frame(fr, q, (r0 * c0) * 5.0f, (r0 * s0) * 5.0f, (r1 * c1) * 5.0f);
+    x[0] = (r0 * c0) * 5.0f; x[1] = (r0 * s0) * 5.0f; x[2] = (r1 * c1) * 5.0f;
+}
+__device__ __forceinline__ Quat philox_rotation_noise(uint64_t seed, uint64_t ctr) {
+    Philox4 b = philox4x32_10(ctr, 1, seed);
+    return shoemake(u32_to_unit(b.v[0]), u32_to_unit(b.v[1]), u32_to_unit(b.v[2]));
+}
+__device__ __forceinline__ void philox_frame_noise(uint64_t seed, uint64_t ctr, float* fr) {
+    float x[3];
+    philox_translation_noise(seed, ctr, x);
+    store_frame(fr, philox_rotation_noise(seed, ctr), x[0], x[1], x[2]);
 }
 __device__ __forceinline__ SinCos philox_torsion_noise(uint64_t seed, uint64_t ctr, int c) {
     uint32_t u;
@@ -107,14 +115,21 @@ struct ReverseCoef {
     float beta_t, beta_s, alpha_ts, var_ts, denom, sigma_t2s;
 };
 
+__device__ __forceinline__ Quat reverse_step_rotation(const Quat& z, const Quat& p, const Quat& x, const ReverseCoef& k,
+                                                       const float* sign_ref) {
+    Quat undo = qinv(qpartial(p, k.beta_t));
+    Quat q = qunit(qmul(qpartial(x, k.beta_s), qmul(undo, z)));
+    return align_sign(q, sign_ref);
+}
+__device__ __forceinline__ float reverse_step_coordinate(float z, float p, float x, const ReverseCoef& k) {
+    return z / k.alpha_ts - (p * k.var_ts) / k.denom + k.sigma_t2s * x;
+}
 __device__ __forceinline__ void reverse_step_frame(const float* zf, const float* pf, const float* xf, const ReverseCoef& k,
                                                    const float* sign_ref, float* of) {
-    Quat undo = qinv(qpartial(load_quat(pf), k.beta_t));
-    Quat q = qunit(qmul(qpartial(load_quat(xf), k.beta_s), qmul(undo, load_quat(zf))));
-    q = align_sign(q, sign_ref);
-    float px = zf[4] / k.alpha_ts - (pf[4] * k.var_ts) / k.denom + k.sigma_t2s * xf[4];
-    float py = zf[5] / k.alpha_ts - (pf[5] * k.var_ts) / k.denom + k.sigma_t2s * xf[5];
-    float pz = zf[6] / k.alpha_ts - (pf[6] * k.var_ts) / k.denom + k.sigma_t2s * xf[6];
+    Quat q = reverse_step_rotation(load_quat(zf), load_quat(pf), load_quat(xf), k, sign_ref);
+    float px = reverse_step_coordinate(zf[4], pf[4], xf[4], k);
+    float py = reverse_step_coordinate(zf[5], pf[5], xf[5], k);
+    float pz = reverse_step_coordinate(zf[6], pf[6], xf[6], k);
     store_frame(of, q, px, py, pz);
 }
 __device__ __forceinline__ SinCos reverse_step_torsion(const SinCos& z, const SinCos& p, const SinCos& x, const ReverseCoef& k) {
@@ -147,22 +162,33 @@ __global__ void remove_noise_kernel(const float* zf, const float* zt, const floa
 }
 
 // Fused noise draw + reverse step of the sampling loop: the step's fresh noise (optimizer.py:151) never leaves
-// registers.  Eight lanes per residue (lane 0: the frame, lanes 1..7: one torsion each) so the long scalar chains
-// (Philox, acos, sincos) of a residue run side by side.  Bit-identical to gen_noise_kernel followed by remove_noise_kernel.
-__global__ void __launch_bounds__(128) reverse_step_philox_kernel(const float* zf, const float* zt, const float* __restrict__ pf,
-                                                                  const float* __restrict__ pt, uint64_t seed, uint64_t first, ReverseCoef k,
-                                                                  int64_t n, const float* __restrict__ sign_ref, float* of, float* ot) {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t r = gid >> 3;
-    const int l = (int)(gid & 7);
+// registers.  The kernel is a latency chain (Philox, Box-Muller, Shoemake, acos, sincos), not a throughput problem, and
+// divergent roles inside a warp would run one after the other — so a CTA of nine warps takes 32 residues and gives every
+// warp ONE role: warp 0 the rotations, warp 1 the translations, warps 2..8 one torsion each.  Bit-identical to
+// gen_noise_kernel followed by remove_noise_kernel.
+constexpr int kRevThreads = 9 * 32;
+__global__ void __launch_bounds__(kRevThreads) reverse_step_philox_kernel(const float* zf, const float* zt, const float* __restrict__ pf,
+                                                                          const float* __restrict__ pt, uint64_t seed, uint64_t first,
+                                                                          ReverseCoef k, int64_t n, const float* __restrict__ sign_ref,
+                                                                          float* of, float* ot) {
+    const int role = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
     if (r >= n) return;
     const uint64_t ctr = first + (uint64_t)r;
-    if (l == 0) {
-        float xf[7];
-        philox_frame_noise(seed, ctr, xf);
-        reverse_step_frame(zf + r * 7, pf + r * 7, xf, k, sign_ref ? sign_ref + r * 4 : nullptr, of + r * 7);
+    if (role == 0) {
+        const Quat q = reverse_step_rotation(load_quat(zf + r * 7), load_quat(pf + r * 7), philox_rotation_noise(seed, ctr), k,
+                                             sign_ref ? sign_ref + r * 4 : nullptr);
+        float* o = of + r * 7;
+        o[0] = q.w; o[1] = q.x; o[2] = q.y; o[3] = q.z;
+    } else if (role == 1) {
+        float x[3];
+        philox_translation_noise(seed, ctr, x);
+        const float z4 = zf[r * 7 + 4], z5 = zf[r * 7 + 5], z6 = zf[r * 7 + 6];      // (of may alias zf)
+        of[r * 7 + 4] = reverse_step_coordinate(z4, pf[r * 7 + 4], x[0], k);
+        of[r * 7 + 5] = reverse_step_coordinate(z5, pf[r * 7 + 5], x[1], k);
+        of[r * 7 + 6] = reverse_step_coordinate(z6, pf[r * 7 + 6], x[2], k);
     } else {
-        const int c = l - 1;
+        const int c = role - 2;
         const SinCos x = philox_torsion_noise(seed, ctr, c);
         const SinCos o = reverse_step_torsion(SinCos{zt[r * 14 + 2 * c], zt[r * 14 + 2 * c + 1]},
                                               SinCos{pt[r * 14 + 2 * c], pt[r * 14 + 2 * c + 1]}, x, k);
@@ -324,7 +350,7 @@ int launch_reverse_step_philox(const float* zf, const float* zt, const float* pf
     PMHC_REQUIRE(beta_t > 0.0 && beta_t < 1.0 && beta_s >= 0.0 && beta_s < beta_t,
                  "reverse step: need 0 <= beta_s < beta_t < 1 (got %f, %f)", beta_s, beta_t);
     ReverseCoef k = reverse_coef(beta_t, beta_s);
-    reverse_step_philox_kernel<<<grid_for(n * 8, 128), 128, 0, stream>>>(zf, zt, pf, pt, seed, first, k, n, sign_ref, of, ot);
+    reverse_step_philox_kernel<<<grid_for(n, 32), kRevThreads, 0, stream>>>(zf, zt, pf, pt, seed, first, k, n, sign_ref, of, ot);
     PMHC_CHECK_LAUNCH("reverse_step_philox");
     return 0;
 }
