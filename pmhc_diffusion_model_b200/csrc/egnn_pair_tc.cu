@@ -1185,7 +1185,8 @@ __global__ void __launch_bounds__(128, 1) node_mid_kernel(NodeMidArgs a) {
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.image);
         uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (int idx = tid; idx < NM_BAR / 16; idx += 128) dst[idx] = __ldg(src + idx);
+        for (int idx = tid; idx < NM_BAR / 16; idx += 128) tc::cp_async_16(dst + idx, src + idx);   // all pieces in flight at once
+        tc::cp_async_wait_all();
     }
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
