@@ -15,10 +15,10 @@
 
 namespace pmhc {
 
-constexpr int kFwdThreads = 256;     // forward: 8 warps (two per scheduler hide LDS / L2 / instruction-fetch latency), one CTA per SM
+constexpr int kFwdThreads = 512;     // forward: 16 warps = two threads per pair column (each owns half of every 64-wide result), one CTA per SM
 constexpr int kBwdThreads = 256;     // backward: 8 warps = two threads per pair column (each owns half of every 64-wide result)
 constexpr int kBwdPairs = 128;       //   of a 128-pair pass: two [64][128] column tiles are all that fits next to the weights
-constexpr int kPassPairs = 256;      // pairs per forward pass (one per thread)
+constexpr int kPassPairs = 256;      // pairs per forward pass (two threads each)
 constexpr int kScrLd = kPassPairs + 1;  // odd row stride -> conflict-free column access
 constexpr int kCapPairs = 512;       // pairs whose head outputs are buffered before the row softmax
 constexpr int kOutPerPair = 15;      // logit, global delta quat (4), delta angles (7), scale * (x_i - x_j) (3)

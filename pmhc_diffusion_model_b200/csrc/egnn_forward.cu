@@ -15,143 +15,173 @@ namespace pmhc {
 // ahead of the FMAs (which spilled the 2 x 64 accumulators); placed every 8 units.
 #define PMHC_SCHED_FENCE(n) do { if (((n) & 7) == 7) asm volatile("" ::: "memory"); } while (0)
 
-// message MLP for the thread's PPT pairs: scr[:, col] <- m = W2 relu(A_i + A_j + W_e) + b2  (model.py:183-226)
-template <int PPT>
-__device__ __forceinline__ void message_stage(float* S, const SmemMap& M, const float* __restrict__ ajt, int Kpad,
-                                              const PairRef (&pr)[PPT], const int (&col)[PPT]) {
+// Two threads per pair: threads p and p + 256 (warps w and w + 8) own column p of the pass.  Each computes the half of every
+// 64-wide result whose index lies in its half h (n in [32h, 32h + 32)); every output is still produced by ONE thread with the
+// same k order as before, and the 64-term second-layer sums are continued by the second thread from the first thread's
+// partial — so the results are bit-identical to the one-thread-per-pair form, at twice the warps per scheduler.
+__device__ __forceinline__ void pair_sync8(int warp8) { asm volatile("bar.sync %0, 64;" ::"r"(1 + warp8) : "memory"); }
+
+// acc[nn] += sum_k WT[k*ldw + n0 + nn] * scr[k*kScrLd + col]  for k in [0,64), nn in [0,32)
+__device__ __forceinline__ void gemv32(float (&acc)[32], const float* __restrict__ WT, int ldw, const float* __restrict__ scr, int col) {
+#pragma unroll 2
+    for (int k = 0; k < kHid; ++k) {
+        const float av = scr[k * kScrLd + col];
+        const float4* w4 = reinterpret_cast<const float4*>(WT + k * ldw);
+#pragma unroll
+        for (int n4 = 0; n4 < 8; ++n4) {
+            const float4 w = w4[n4];
+            acc[4 * n4 + 0] = fmaf(w.x, av, acc[4 * n4 + 0]);
+            acc[4 * n4 + 1] = fmaf(w.y, av, acc[4 * n4 + 1]);
+            acc[4 * n4 + 2] = fmaf(w.z, av, acc[4 * n4 + 2]);
+            acc[4 * n4 + 3] = fmaf(w.w, av, acc[4 * n4 + 3]);
+        }
+    }
+}
+
+// message MLP of the thread's pair: scr[:, col] <- m = W2 relu(A_i + A_j + W_e) + b2  (model.py:183-226)
+__device__ __forceinline__ void message_stage(float* S, const SmemMap& M, const float* __restrict__ ajt, int Kpad, const PairRef& pr,
+                                              int col, int half, int warp8) {
     float* scr = S + M.Scr;
-#pragma unroll
-    for (int u = 0; u < PPT; ++u) {
-        const int i = pr[u].i, j = pr[u].j;
-        const float* ai = S + M.Ai + i * kLdN;
+    const int n0 = 32 * half;
+    {
+        const int i = pr.i, j = pr.j;
+        const float* ai = S + M.Ai + i * kLdN + n0;
         const bool pep = (j >= 0 && j < kN);
-        const float* we = S + M.We + (pep ? (kN - 1 + i - j) : 0) * kLdN;
-        // all 64 L2 loads of the A_j^T column are issued before the first use (__ldcg is an ordered asm: mixed
-        // with its consumer it serialises into 64 dependent L2 round trips, 26 % of the kernel in the first profile)
-        float aj[kHid];
-        const float* ajc = ajt + (j >= 0 ? j : 0);
+        const float* we = S + M.We + (pep ? (kN - 1 + i - j) : 0) * kLdN + n0;
+        // all L2 loads of the A_j^T column are issued before the first use (__ldcg is an ordered asm: mixed
+        // with its consumer it serialises into dependent L2 round trips, 26 % of the kernel in the first profile)
+        float aj[32];
+        const float* ajc = ajt + (j >= 0 ? j : 0) + (size_t)n0 * Kpad;
 #pragma unroll
-        for (int k = 0; k < kHid; ++k) aj[k] = __ldcg(ajc + k * Kpad);
+        for (int k = 0; k < 32; ++k) aj[k] = __ldcg(ajc + k * Kpad);
 #pragma unroll
-        for (int k = 0; k < kHid; ++k) {
+        for (int k = 0; k < 32; ++k) {
             float v = ai[k];
             if (j >= 0) v += aj[k];
             if (pep) v += we[k];
-            scr[k * kScrLd + col[u]] = fmaxf(v, 0.0f);
+            scr[(n0 + k) * kScrLd + col] = fmaxf(v, 0.0f);
         }
     }
-    float acc[PPT][kHid];
+    pair_sync8(warp8);          // m1 complete
+    float acc[32];
 #pragma unroll
-    for (int u = 0; u < PPT; ++u)
+    for (int n = 0; n < 32; ++n) acc[n] = S[M.PkMisc + 4 * (n0 + n) + 3];
+    gemv32(acc, S + M.W2T + n0, kHid, scr, col);
+    pair_sync8(warp8);          // both halves have read m1: the column may be overwritten with m
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) acc[u][n] = S[M.PkMisc + 4 * n + 3];
-    gemv64<PPT>(acc, S + M.W2T, kHid, scr, col);
-#pragma unroll
-    for (int u = 0; u < PPT; ++u)
-#pragma unroll
-        for (int n = 0; n < kHid; ++n) scr[n * kScrLd + col[u]] = acc[u][n];
+    for (int n = 0; n < 32; ++n) scr[(n0 + n) * kScrLd + col] = acc[n];
+    pair_sync8(warp8);          // m complete
 }
 
-// the four heads of one pair; writes kOutPerPair floats  (model.py:228-333)
-template <int PPT>
-__device__ __forceinline__ void heads_stage(float* S, const SmemMap& M, const PairRef (&pr)[PPT], const int (&col)[PPT],
-                                            const int (&oslot)[PPT], float* __restrict__ logit_save, int Kpad) {
+// the four heads of one pair; writes kOutPerPair floats  (model.py:228-333).  The first half seeds each 64-term second-layer
+// sum with the bias and its 32 terms and parks it in the pair's output slot; the second half continues it and finishes the head.
+__device__ __forceinline__ void heads_stage(float* S, const SmemMap& M, const PairRef& pr, int col, int oslot, int half, int warp8,
+                                            float* __restrict__ logit_save, int Kpad) {
     const float* scr = S + M.Scr;
-    float acc[PPT][kHid];
+    const int n0 = 32 * half;
+    float* out = S + M.Out + oslot * kOutPerPair;
+    const bool act = pr.active;
+    float acc[32];
     // ---- attention logit (model.py:238-242) ----
     // The distance / orientation inputs (-d2 reaches thousands of A^2) are added AFTER the 64-term message
     // contraction: one rounding at that magnitude instead of 64 keeps the logit within a few ulp of a blocked
     // CPU summation (logits of the shipped weights reach 2.5e3, where one fp32 ulp is already 2.4e-4).
-    float ex_d2[PPT], ex_qd[PPT];
+    const float* qi_ = S + M.Q + pr.i * 4;
+    const float* qj_ = S + M.Q + pr.j * 4;
+    const float* xi = S + M.X + pr.i * 3;
+    const float* xj = S + M.X + pr.j * 3;
+    const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+    const float ex_d2 = dx * dx + dy * dy + dz * dz;
+    const float dotq = qi_[0] * qj_[0] + qi_[1] * qj_[1] + qi_[2] * qj_[2] + qi_[3] * qj_[3];
+    const float ex_qd = dotq * dotq;
 #pragma unroll
-    for (int u = 0; u < PPT; ++u) {
-        const float* qi = S + M.Q + pr[u].i * 4;
-        const float* qj = S + M.Q + pr[u].j * 4;
-        const float* xi = S + M.X + pr[u].i * 3;
-        const float* xj = S + M.X + pr[u].j * 3;
-        float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
-        ex_d2[u] = dx * dx + dy * dy + dz * dz;
-        float dot = qi[0] * qj[0] + qi[1] * qj[1] + qi[2] * qj[2] + qi[3] * qj[3];
-        ex_qd[u] = dot * dot;
-#pragma unroll
-        for (int n = 0; n < kHid; ++n) acc[u][n] = S[M.PkAtt + 4 * n + 2];
+    for (int n = 0; n < 32; ++n) acc[n] = S[M.PkAtt + 4 * (n0 + n) + 2];
+    gemv32(acc, S + M.WhT + n0, 256, scr, col);
+    float logit = S[M.Scal + SC_ATT2B];
+    if (half == 1) {
+        pair_sync8(warp8);
+        logit = out[0];
     }
-    gemv64<PPT>(acc, S + M.WhT, 256, scr, col);
 #pragma unroll
-    for (int u = 0; u < PPT; ++u) {
-        float logit = S[M.Scal + SC_ATT2B];
-#pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            const float4 pk = *reinterpret_cast<const float4*>(S + M.PkAtt + 4 * n);
-            const float h = acc[u][n] + fmaf(pk.y, ex_qd[u], pk.x * -ex_d2[u]);
-            logit = fmaf(pk.w, fmaxf(h, 0.0f), logit);
-            PMHC_SCHED_FENCE(n);
-        }
-        if (pr[u].active) {
-            S[M.Out + oslot[u] * kOutPerPair] = logit;
-            if (logit_save != nullptr) logit_save[pr[u].i * Kpad + pr[u].j] = logit;
-        }
+    for (int n = 0; n < 32; ++n) {
+        const float4 pk = *reinterpret_cast<const float4*>(S + M.PkAtt + 4 * (n0 + n));
+        const float h = acc[n] + fmaf(pk.y, ex_qd, pk.x * -ex_d2);
+        logit = fmaf(pk.w, fmaxf(h, 0.0f), logit);
+        PMHC_SCHED_FENCE(n);
     }
+    if (act) {
+        out[0] = logit;
+        if (half == 1 && logit_save != nullptr) logit_save[pr.i * Kpad + pr.j] = logit;
+    }
+    if (half == 0) pair_sync8(warp8);
     // ---- rotation: local frame -> MLP -> sigmoid -> back to the global frame (model.py:283-296) ----
+    const Quat qi{qi_[0], qi_[1], qi_[2], qi_[3]}, qj{qj_[0], qj_[1], qj_[2], qj_[3]};
+    {
+        const Quat lq = qmul(qinv(qj), qmul(qi, qj));
 #pragma unroll
-    for (int u = 0; u < PPT; ++u) {
-        const float* a = S + M.Q + pr[u].i * 4;
-        const float* b = S + M.Q + pr[u].j * 4;
-        Quat qi{a[0], a[1], a[2], a[3]}, qj{b[0], b[1], b[2], b[3]};
-        Quat lq = qmul(qinv(qj), qmul(qi, qj));
-#pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            const float4 wq = *reinterpret_cast<const float4*>(S + M.PkRotQ + 4 * n);
-            float v = S[M.PkMisc + 4 * n + 2];
+        for (int n = 0; n < 32; ++n) {
+            const float4 wq = *reinterpret_cast<const float4*>(S + M.PkRotQ + 4 * (n0 + n));
+            float v = S[M.PkMisc + 4 * (n0 + n) + 2];
             v = fmaf(wq.x, lq.w, v);
             v = fmaf(wq.y, lq.x, v);
             v = fmaf(wq.z, lq.y, v);
             v = fmaf(wq.w, lq.z, v);
-            acc[u][n] = v;
+            acc[n] = v;
             PMHC_SCHED_FENCE(n);
         }
     }
-    gemv64<PPT>(acc, S + M.WhT + 64, 256, scr, col);
-#pragma unroll
-    for (int u = 0; u < PPT; ++u) {
+    gemv32(acc, S + M.WhT + 64 + n0, 256, scr, col);
+    {
         float pre[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) pre[c] = S[M.Scal + SC_ROT2B + c];
+        if (half == 1) {
+            pair_sync8(warp8);
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            float h = fmaxf(acc[u][n], 0.0f);
-            const float4 w = *reinterpret_cast<const float4*>(S + M.PkRot2 + 4 * n);
+            for (int c = 0; c < 4; ++c) pre[c] = out[1 + c];
+        }
+#pragma unroll
+        for (int n = 0; n < 32; ++n) {
+            const float h = fmaxf(acc[n], 0.0f);
+            const float4 w = *reinterpret_cast<const float4*>(S + M.PkRot2 + 4 * (n0 + n));
             pre[0] = fmaf(w.x, h, pre[0]);
             pre[1] = fmaf(w.y, h, pre[1]);
             pre[2] = fmaf(w.z, h, pre[2]);
             pre[3] = fmaf(w.w, h, pre[3]);
             PMHC_SCHED_FENCE(n);
         }
-        const float* b = S + M.Q + pr[u].j * 4;
-        Quat qj{b[0], b[1], b[2], b[3]};
-        Quat dl{sigmoidf(pre[0]), sigmoidf(pre[1]), sigmoidf(pre[2]), sigmoidf(pre[3])};  // never normalised (T5)
-        Quat dg = qmul(qj, qmul(dl, qinv(qj)));
-        if (pr[u].active) {
-            float* o = S + M.Out + oslot[u] * kOutPerPair + 1;
-            o[0] = dg.w; o[1] = dg.x; o[2] = dg.y; o[3] = dg.z;
+        if (half == 0) {
+            if (act) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) out[1 + c] = pre[c];
+            }
+            pair_sync8(warp8);
+        } else {
+            const Quat dl{sigmoidf(pre[0]), sigmoidf(pre[1]), sigmoidf(pre[2]), sigmoidf(pre[3])};  // never normalised (T5)
+            const Quat dg = qmul(qj, qmul(dl, qinv(qj)));
+            if (act) {
+                out[1] = dg.w; out[2] = dg.x; out[3] = dg.y; out[4] = dg.z;
+            }
         }
     }
     // ---- torsion angle increments (model.py:257-260) ----
 #pragma unroll
-    for (int u = 0; u < PPT; ++u)
-#pragma unroll
-        for (int n = 0; n < kHid; ++n) acc[u][n] = S[M.Tt + pr[u].i * kHid + n];
-    gemv64<PPT>(acc, S + M.WhT + 128, 256, scr, col);
-#pragma unroll
-    for (int u = 0; u < PPT; ++u) {
+    for (int n = 0; n < 32; ++n) acc[n] = S[M.Tt + pr.i * kHid + n0 + n];
+    gemv32(acc, S + M.WhT + 128 + n0, 256, scr, col);
+    {
         float da[PMHC_NTORS];
 #pragma unroll
         for (int c = 0; c < PMHC_NTORS; ++c) da[c] = S[M.Scal + SC_TOR2B + c];
+        if (half == 1) {
+            pair_sync8(warp8);
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            float h = fmaxf(acc[u][n], 0.0f);
-            const float4 w0 = *reinterpret_cast<const float4*>(S + M.PkTor2 + 8 * n);
-            const float4 w1 = *reinterpret_cast<const float4*>(S + M.PkTor2 + 8 * n + 4);
+            for (int c = 0; c < PMHC_NTORS; ++c) da[c] = out[5 + c];
+        }
+#pragma unroll
+        for (int n = 0; n < 32; ++n) {
+            const float h = fmaxf(acc[n], 0.0f);
+            const float4 w0 = *reinterpret_cast<const float4*>(S + M.PkTor2 + 8 * (n0 + n));
+            const float4 w1 = *reinterpret_cast<const float4*>(S + M.PkTor2 + 8 * (n0 + n) + 4);
             da[0] = fmaf(w0.x, h, da[0]);
             da[1] = fmaf(w0.y, h, da[1]);
             da[2] = fmaf(w0.z, h, da[2]);
@@ -161,30 +191,31 @@ __device__ __forceinline__ void heads_stage(float* S, const SmemMap& M, const Pa
             da[6] = fmaf(w1.z, h, da[6]);
             PMHC_SCHED_FENCE(n);
         }
-        if (pr[u].active) {
-            float* o = S + M.Out + oslot[u] * kOutPerPair + 5;
+        if (act) {
 #pragma unroll
-            for (int c = 0; c < PMHC_NTORS; ++c) o[c] = da[c];
+            for (int c = 0; c < PMHC_NTORS; ++c) out[5 + c] = da[c];
         }
+        if (half == 0) pair_sync8(warp8);
     }
     // ---- translation scale (model.py:325-331) ----
 #pragma unroll
-    for (int u = 0; u < PPT; ++u)
+    for (int n = 0; n < 32; ++n) acc[n] = S[M.PkMisc + 4 * (n0 + n) + 0];
+    gemv32(acc, S + M.WhT + 192 + n0, 256, scr, col);
+    {
+        float sc = S[M.Scal + SC_TRN2B];
+        if (half == 1) {
+            pair_sync8(warp8);
+            sc = out[12];
+        }
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) acc[u][n] = S[M.PkMisc + 4 * n + 0];
-    gemv64<PPT>(acc, S + M.WhT + 192, 256, scr, col);
-#pragma unroll
-    for (int u = 0; u < PPT; ++u) {
-        float s = S[M.Scal + SC_TRN2B];
-#pragma unroll
-        for (int n = 0; n < kHid; ++n) s = fmaf(S[M.PkMisc + 4 * n + 1], fmaxf(acc[u][n], 0.0f), s);
-        if (pr[u].active) {
-            const float* xi = S + M.X + pr[u].i * 3;
-            const float* xj = S + M.X + pr[u].j * 3;
-            float* o = S + M.Out + oslot[u] * kOutPerPair + 12;
-            o[0] = s * (xi[0] - xj[0]);
-            o[1] = s * (xi[1] - xj[1]);
-            o[2] = s * (xi[2] - xj[2]);
+        for (int n = 0; n < 32; ++n) sc = fmaf(S[M.PkMisc + 4 * (n0 + n) + 1], fmaxf(acc[n], 0.0f), sc);
+        if (half == 0) {
+            if (act) out[12] = sc;
+            pair_sync8(warp8);
+        } else if (act) {
+            out[12] = sc * dx;
+            out[13] = sc * dy;
+            out[14] = sc * dz;
         }
     }
 }
@@ -211,7 +242,8 @@ template <int LAYER>
 __global__ void __launch_bounds__(kFwdThreads, 1) egnn_layer_forward_kernel(LayerArgs a) {
     extern __shared__ __align__(16) float S[];
     const SmemMap M = make_smem_map(a.Kpad);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int pcol = tid & (kPassPairs - 1), half = tid >> 8, warp8 = warp & 7;   // two threads (tid, tid + 256) per pair column
     int* I = reinterpret_cast<int*>(S + M.Ints);
     float* ajt = a.ajt_ws + (size_t)blockIdx.x * kHid * a.Kpad;
 
@@ -239,15 +271,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) egnn_layer_forward_kernel(Laye
             const int gpairs = nrows * W;
             for (int pass_base = 0; pass_base < gpairs; pass_base += kPassPairs) {
                 const int npass = min(kPassPairs, gpairs - pass_base);
-                if (warp * 32 < npass) {  // warps past the end of a short last pass have nothing to do
-                    PairRef pr[1];
-                    int col[1] = {tid}, oslot[1];
-                    const bool act = tid < npass;
-                    const int gp = act ? pass_base + tid : pass_base;
-                    pr[0] = decode_full_pair(I, gp, W, L, row0, act);
-                    oslot[0] = gp;
-                    message_stage<1>(S, M, ajt, a.Kpad, pr, col);
-                    heads_stage<1>(S, M, pr, col, oslot, lsave, a.Kpad);
+                if (warp8 * 32 < npass) {  // warp pairs past the end of a short last pass have nothing to do
+                    const bool act = pcol < npass;
+                    const int gp = act ? pass_base + pcol : pass_base;
+                    const PairRef pr = decode_full_pair(I, gp, W, L, row0, act);
+                    message_stage(S, M, ajt, a.Kpad, pr, pcol, half, warp8);
+                    heads_stage(S, M, pr, pcol, gp, half, warp8, lsave, a.Kpad);
                 }
                 if (LAYER == 0) {
                     __syncthreads();
@@ -266,21 +295,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) egnn_layer_forward_kernel(Laye
             const int npx = kN - L;                          // masked peptide slots
             const int W2 = 1 + npx + ci.nx + (ci.c0 > 0 ? 1 : 0);
             const int total = L * W2;
-            for (int pass_base = 0; pass_base < total; pass_base += kFwdThreads) {
-                const int npass = min(kFwdThreads, total - pass_base);
-                if (warp * 32 < npass) {
-                    PairRef pr[1];
-                    int col[1] = {tid};
-                    bool act = tid < npass;
-                    int gp = act ? pass_base + tid : pass_base;
-                    int rl = gp / W2, e = gp - rl * W2;
-                    pr[0].i = I[IN_ROWS + rl];
-                    pr[0].active = act;
-                    if (e == 0) pr[0].j = pr[0].i;
-                    else if (e <= npx) pr[0].j = I[IN_PEPX + e - 1];
-                    else if (e <= npx + ci.nx) pr[0].j = I[IN_POCKET + a.Kpad - 1 - (e - npx - 1)];
-                    else pr[0].j = -1;
-                    message_stage<1>(S, M, ajt, a.Kpad, pr, col);
+            for (int pass_base = 0; pass_base < total; pass_base += kPassPairs) {
+                const int npass = min(kPassPairs, total - pass_base);
+                if (warp8 * 32 < npass) {
+                    PairRef pr;
+                    const bool act = pcol < npass;
+                    const int gp = act ? pass_base + pcol : pass_base;
+                    const int rl = gp / W2, e = gp - rl * W2;
+                    pr.i = I[IN_ROWS + rl];
+                    pr.active = act;
+                    if (e == 0) pr.j = pr.i;
+                    else if (e <= npx) pr.j = I[IN_PEPX + e - 1];
+                    else if (e <= npx + ci.nx) pr.j = I[IN_POCKET + a.Kpad - 1 - (e - npx - 1)];
+                    else pr.j = -1;
+                    message_stage(S, M, ajt, a.Kpad, pr, pcol, half, warp8);
                 }
                 __syncthreads();
                 accumulate_msum(S, M, I, 0, L, W2, pass_base, npass, ci.c0 > 0 ? W2 - 1 : -1, (float)ci.c0);
