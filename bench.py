@@ -407,7 +407,7 @@ def main():
             "config": {"workload": "sampling T=100, 1000 complexes/GPU, 9-mer peptide, M=180 protein / 60 pocket residues padded to 80 (BASELINE configs[1])",
                        "complexes_per_gpu": B, "T": T_STEPS, "P_pad": P_PAD, "l2": "flushed between steps (256 MiB memset)",
                        "weights": "random init, reference architecture (79 195 params)",
-                       "precision": args.precision + (" (tcgen05 bf16 operands / fp32 accumulate for the two dense contractions; parity gate 1e-2)"
+                       "precision": args.precision + (" (tcgen05: bf16 operands / fp32 accumulate for every per-pair contraction; parity gate 1e-2)"
                                                       if tc else " (FFMA; parity gate 1e-4)")},
             "clocks": clocks.summary(),
             "e2e": {"value": world * B * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
