@@ -660,3 +660,37 @@ def test_bf16_forward_largest_pocket(api):
     assert rel_err(out["torsions"][m], ref["torsions"][m]) < TOL_BF16
     with pytest.raises(RuntimeError, match="pocket_maxlen"):
         model({k: (torch.cat((v, v), 1) if k.startswith("pocket") else v) for k, v in gb.items()}, 17)
+
+
+def test_c_abi_error_behaviour(api):
+    """Errors come back as a non-zero return + text (raised as RuntimeError / ValueError by the Python layer), never as a
+    crash or a silent fallback: too small workspace, null batch, bad precision, reverse step outside the schedule, wrong shapes."""
+    import ctypes
+    lib = api.lib.load()
+    batch = orc.synthetic_batch(2, 9, 20, P_pad=32, seed=1)
+    model = make_model(api, orc.random_params(seed=1), 10)
+    gb = gpu_batch(batch)
+    desc, keep = api.lib.make_batch(gb["frames"], gb["torsions"], gb["features"], gb["mask"], gb["pocket_frames"], gb["pocket_features"], gb["pocket_mask"])
+    flat = model._flat_params()
+    out_f = torch.empty(2, 16, 7, device=DEV)
+    out_t = torch.empty(2, 16, 7, 2, device=DEV)
+    ws = torch.empty(lib.pmhc_workspace_bytes(2, 32), dtype=torch.uint8, device=DEV)
+    s = api.lib.stream_ptr(torch.device(DEV))
+    args = (flat.data_ptr(), ctypes.byref(desc), 0.5, out_f.data_ptr(), out_t.data_ptr(), None, ws.data_ptr())
+    assert lib.pmhc_model_forward_ex(*args, ws.numel(), s, 0) == 0
+    assert lib.pmhc_model_forward_ex(*args, 16, s, 0) != 0 and b"workspace" in lib.pmhc_last_error()
+    assert lib.pmhc_model_forward_ex(*args, ws.numel(), s, 7) != 0 and b"precision" in lib.pmhc_last_error()
+    assert lib.pmhc_model_forward_ex(flat.data_ptr(), None, 0.5, out_f.data_ptr(), out_t.data_ptr(), None, ws.data_ptr(), ws.numel(), s, 0) != 0
+    assert lib.pmhc_remove_noise(out_f.data_ptr(), out_t.data_ptr(), out_f.data_ptr(), out_t.data_ptr(), out_f.data_ptr(), out_t.data_ptr(),
+                                 0.2, 0.5, 32, None, out_f.data_ptr(), out_t.data_ptr(), s) != 0          # beta_s > beta_t
+    with pytest.raises(RuntimeError, match="failed"):
+        api.lib.check(lib.pmhc_model_forward_ex(*args, 16, s, 0), "pmhc_model_forward")
+    with pytest.raises(ValueError):
+        model({**gb, "features": gb["features"][..., :20]}, 3)                  # 20 features instead of 22
+    with pytest.raises(ValueError):
+        model.precision = "fp16"
+        model(gb, 3)
+    model.precision = "fp32"
+    torch.cuda.synchronize()
+    out = model(gb, 3)                                                            # the library is still usable after the errors
+    assert torch.isfinite(out["frames"].to_tensor_7()).all()

@@ -226,3 +226,60 @@ def test_pdb_number_formatting_matches_printf():
         pos = (rng.standard_normal((16, 15, 3)) * scale).astype("f4")
         args = (aa, mask, pos, ex, paa, ppos * (scale if scale < 1000 else 1.0), pex)
         assert pdbio.format_pdb(*args) == pdbio.format_pdb_python(*args)
+
+
+def test_hdf5_random_trees_round_trip(tmp_path):
+    """Property test: any tree of nested groups with numeric / bool datasets of random shape written by the writer reads
+    back identically (names incl. non-ASCII-free punctuation, empty groups, scalars-as-1-element arrays, group sizes
+    around the symbol-node / B-tree fan-out boundaries 8 and 256)."""
+    from hypothesis import given, settings, strategies as st
+    dtypes = ["<f4", "<f8", "<i8", "<i4", "<i2", "|i1", "|u1", "<u2", "<u4", "bool"]
+    names = st.text(alphabet="abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789_-. ", min_size=1, max_size=24).filter(
+        lambda n: n.strip("/ ") == n and n not in (".", ".."))
+
+    @st.composite
+    def arrays(draw):
+        dt = numpy.dtype(draw(st.sampled_from(dtypes)))
+        shape = tuple(draw(st.lists(st.integers(0, 5), min_size=1, max_size=3)))
+        n = int(numpy.prod(shape))
+        seed = draw(st.integers(0, 2 ** 31 - 1))
+        rng = numpy.random.default_rng(seed)
+        if dt == numpy.dtype("bool"):
+            return rng.random(n).reshape(shape) > 0.5
+        if dt.kind == "f":
+            return rng.standard_normal(n).astype(dt).reshape(shape)
+        info = numpy.iinfo(dt)
+        return rng.integers(info.min, info.max, n, dtype=dt, endpoint=True).reshape(shape)
+
+    def trees(depth):
+        leaf = arrays()
+        if depth == 0:
+            return st.dictionaries(names, leaf, max_size=4)
+        return st.dictionaries(names, st.one_of(leaf, trees(depth - 1)), max_size=5)
+
+    counter = {"n": 0}
+
+    @settings(max_examples=40, deadline=None)
+    @given(trees(2), st.sampled_from([0, 7, 8, 9, 17, 255, 256, 257]))
+    def check(tree, extra):
+        tree = dict(tree)
+        for k in range(extra):        # pad the root group to sizes around the fan-out boundaries
+            tree.setdefault(f"pad{k:04d}", numpy.arange(k % 3, dtype="<i4"))
+        counter["n"] += 1
+        path = str(tmp_path / f"r{counter['n']}.h5")
+        hdf5_lite.write_file(path, tree)
+
+        def compare(node, ref):
+            assert sorted(node.keys()) == sorted(ref.keys())
+            for k, v in ref.items():
+                if isinstance(v, dict):
+                    compare(node[k], v)
+                else:
+                    got = node[k][:]
+                    assert got.dtype == v.dtype and got.shape == v.shape and numpy.array_equal(got, v), k
+
+        with hdf5_lite.File(path) as f:
+            compare(f, tree)
+        os.remove(path)
+
+    check()
