@@ -92,6 +92,14 @@ int pmhc_model_backward(const float *params, const PmhcBatch *batch_host, float 
                         const float *saved, const float *d_out_frames, const float *d_out_torsions,
                         float *flat_grad, void *workspace, size_t workspace_bytes, void *stream,
                         void *layer2_done_event);
+/* Same with an explicit PMHC_PRECISION_* mode (pmhc_model_backward == PMHC_PRECISION_FP32).  PMHC_PRECISION_BF16 selects the
+ * tensor-core backward: every 64-wide contraction of the pair recomputation, the input gradients and the weight-gradient
+ * outer products as TF32 MMAs with fp32 accumulation (operands rounded to tf32, i.e. more mantissa than the bf16 forward);
+ * second layers, geometry, softmax backward and all reductions stay fp32.  Gradient gate: the 1e-2 class. */
+int pmhc_model_backward_ex(const float *params, const PmhcBatch *batch_host, float t_over_T,
+                           const float *saved, const float *d_out_frames, const float *d_out_torsions,
+                           float *flat_grad, void *workspace, size_t workspace_bytes, void *stream,
+                           void *layer2_done_event, int precision);
 /* layer2_done_event (nullable cudaEvent_t): recorded on `stream` as soon as the gnn2.* half of flat_grad is final
  * (the gnn1.* half follows), so a data-parallel caller can start all-reducing it on a second stream while the
  * layer-1 backward kernel is still running. */

@@ -21,7 +21,7 @@ PRECISIONS = {"fp32": 0, "bf16": 1}  # PMHC_PRECISION_*
 
 EXPORTS = (
     "pmhc_last_error", "pmhc_check_device", "pmhc_param_offset", "pmhc_param_numel", "pmhc_workspace_bytes",
-    "pmhc_saved_floats", "pmhc_model_forward", "pmhc_model_forward_ex", "pmhc_model_backward", "pmhc_gen_noise", "pmhc_noise_from_randoms",
+    "pmhc_saved_floats", "pmhc_model_forward", "pmhc_model_forward_ex", "pmhc_model_backward", "pmhc_model_backward_ex", "pmhc_gen_noise", "pmhc_noise_from_randoms",
     "pmhc_add_noise", "pmhc_remove_noise", "pmhc_loss", "pmhc_sample", "pmhc_adam_step", "pmhc_launch_count",
     "pmhc_profile_enable", "pmhc_profile_read", "pmhc_frames4x4_to_tensor7", "pmhc_atom14", "pmhc_format_pdb_host",
 )
@@ -67,6 +67,8 @@ def load() -> ctypes.CDLL:
     lib.pmhc_model_forward_ex.argtypes = [vp, POINTER(PmhcBatch), f32, vp, vp, vp, vp, c_size_t, vp, c_int]
     lib.pmhc_model_backward.restype = c_int
     lib.pmhc_model_backward.argtypes = [vp, POINTER(PmhcBatch), f32, vp, vp, vp, vp, vp, c_size_t, vp, vp]
+    lib.pmhc_model_backward_ex.restype = c_int
+    lib.pmhc_model_backward_ex.argtypes = [vp, POINTER(PmhcBatch), f32, vp, vp, vp, vp, vp, c_size_t, vp, vp, c_int]
     lib.pmhc_gen_noise.restype = c_int
     lib.pmhc_gen_noise.argtypes = [u64, u64, i64, vp, vp, vp]
     lib.pmhc_noise_from_randoms.restype = c_int

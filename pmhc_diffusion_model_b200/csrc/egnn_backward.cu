@@ -15,6 +15,11 @@
 namespace pmhc {
 
 constexpr int kLdc = 132;                     // column-tile row stride (floats): 16-byte aligned rows
+constexpr int kLdt = 136;                     // same in tensor-core mode: 8 g + t is a conflict-free bank pattern for MMA fragments
+// tensor-core mode: second-layer weights as swizzled [c][n] row images (rotation 4 rows, torsion 8 (7 used), translation 1,
+// attention 1) and the extra-input columns of the first layers as [e][n] images (rotation: local quaternion 4, attention: 2)
+constexpr int kW3Rot = 0, kW3Tor = 4 * kHid, kW3Trn = 12 * kHid, kW3Att = 13 * kHid, kW3Floats = 14 * kHid;
+constexpr int kWxRot = 0, kWxAtt = 4 * kHid, kWxFloats = 6 * kHid;
 constexpr int kTileFloats = 5 * kHid * kHid;  // tile-owner-layout partials of the five 64x64 matrices
 enum { T_W2 = 0, T_ATT = 1, T_ROT = 2, T_TOR = 3, T_TRN = 4 };
 enum { HD_ATT = 0, HD_ROT = 1, HD_TOR = 2, HD_TRN = 3 };
@@ -39,28 +44,38 @@ struct BwdArgs {
 struct BwdMap {
     SmemMap f;  // the fields setup_complex() uses (Scr, Ai, Tt, Msum, H, Tors, Q, X, Ints) and the packs
     int W2, Wh, BufA, BufB, Dout, Ex;
+    int W3i, Wx, Dx;            // tensor-core mode: second-layer weight images, extra-input weight images, per-pair extras gradients
     int dAi, dAjPep, dWe, dTt, dMsum, RowG, dQ, dX, dTors, grads_end;
     int total_floats;
 };
 
-__host__ __device__ inline BwdMap make_bwd_map(int Kpad) {
+__host__ __device__ inline BwdMap make_bwd_map(int Kpad, bool tc = false) {
     BwdMap m;
     int o = 0;
+    const int ldc = tc ? kLdt : kLdc;
     m.W2 = o;       o += kHid * kHid;        // message_mlp.2.weight as stored: [n][k]
     m.Wh = o;       o += 4 * kHid * kHid;    // head first layers, message columns only: [head][n][k]
     m.f.W2T = m.f.WhT = m.f.We = -1;
     m.f.PkAtt = o;  o += 4 * kHid;
     m.f.PkRotQ = o; o += 4 * kHid;
-    m.f.PkRot2 = o; o += 4 * kHid;
     m.f.PkMisc = o; o += 4 * kHid;
-    m.f.PkTor2 = o; o += 8 * kHid;
+    m.W3i = m.Wx = m.Dx = -1;
+    if (tc) {
+        m.f.PkRot2 = m.f.PkTor2 = -1;
+        m.W3i = o;  o += kW3Floats;
+        m.Wx = o;   o += kWxFloats;
+    } else {
+        m.f.PkRot2 = o; o += 4 * kHid;
+        m.f.PkTor2 = o; o += 8 * kHid;
+    }
     m.f.Scal = o;   o += 16;
-    m.BufA = o;     o += kHid * kLdc;
-    m.BufB = o;     o += kHid * kLdc;
+    m.BufA = o;     o += kHid * ldc;
+    m.BufB = o;     o += kHid * ldc;
     m.f.Scr = m.BufA;                         // setup_complex stages pocket features in BufA..BufB
     m.f.Out = -1;
-    m.Dout = o;     o += 8 * kLdc;
-    m.Ex = o;       o += 6 * kLdc;
+    m.Dout = o;     o += 8 * ldc;
+    m.Ex = o;       o += (tc ? 10 : 6) * ldc;   // tensor-core mode: the per-pair geometry tile (8 MMA rows + 2 fp32 rows)
+    if (tc) { m.Dx = o; o += 6 * ldc; }          // dL / d (local quaternion (4), -d2, qdot2) per pair column
     m.f.Ai = o;     o += kN * kLdN;
     o = (o + 3) & ~3;
     m.f.Tt = o;     o += kN * kHid;
@@ -88,7 +103,17 @@ __host__ __device__ inline BwdMap make_bwd_map(int Kpad) {
     return m;
 }
 
-template <int LAYER>
+// tensor-core mode: the five 64 x 64 matrices are stored tf32-rounded with an XOR swizzle of the column index, so that both
+// A[m][k] = W[m][k] (forward) and A[m][k] = W[k][m] (input gradients) fragment loads of mma.m16n8k8 are bank-conflict free
+// without padding: element (n, k) lives at n * 64 + (k ^ (((n & 3) << 3) | (n & 4))).
+__device__ __forceinline__ int wswz(int n, int k) { return n * 64 + (k ^ (((n & 3) << 3) | (n & 4))); }
+__device__ __forceinline__ float tf32r(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+template <int LAYER, bool TC = false>
 __device__ inline void stage_layer_weights_bwd(float* S, const BwdMap& M, const float* __restrict__ params) {
     constexpr int L = LAYER;
     const int tid = threadIdx.x;
@@ -98,24 +123,30 @@ __device__ inline void stage_layer_weights_bwd(float* S, const BwdMap& M, const 
     const float* tor0 = params + param_offset(L, TOR0_W);
     const float* trn0 = params + param_offset(L, TRN0_W);
     for (int idx = tid; idx < kHid * kHid; idx += kBwdThreads) {
-        S[M.W2 + idx] = msg2[idx];
-        S[M.Wh + HD_TRN * 4096 + idx] = trn0[idx];
+        if (TC) {
+            const int o = wswz(idx >> 6, idx & 63);
+            S[M.W2 + o] = tf32r(msg2[idx]);
+            S[M.Wh + HD_TRN * 4096 + o] = tf32r(trn0[idx]);
+        } else {
+            S[M.W2 + idx] = msg2[idx];
+            S[M.Wh + HD_TRN * 4096 + idx] = trn0[idx];
+        }
     }
     for (int idx = tid; idx < kHid * 66; idx += kBwdThreads) {
         int n = idx / 66, k = idx - n * 66;
         float v = att0[idx];
-        if (k < 64) S[M.Wh + HD_ATT * 4096 + n * 64 + k] = v;
+        if (k < 64) S[M.Wh + HD_ATT * 4096 + (TC ? wswz(n, k) : n * 64 + k)] = TC ? tf32r(v) : v;
         else S[M.f.PkAtt + 4 * n + (k - 64)] = v;
     }
     for (int idx = tid; idx < kHid * 68; idx += kBwdThreads) {
         int n = idx / 68, k = idx - n * 68;
         float v = rot0[idx];
-        if (k < 64) S[M.Wh + HD_ROT * 4096 + n * 64 + k] = v;
+        if (k < 64) S[M.Wh + HD_ROT * 4096 + (TC ? wswz(n, k) : n * 64 + k)] = TC ? tf32r(v) : v;
         else S[M.f.PkRotQ + 4 * n + (k - 64)] = v;
     }
     for (int idx = tid; idx < kHid * 78; idx += kBwdThreads) {
         int n = idx / 78, k = idx - n * 78;
-        if (k < 64) S[M.Wh + HD_TOR * 4096 + n * 64 + k] = tor0[idx];
+        if (k < 64) S[M.Wh + HD_TOR * 4096 + (TC ? wswz(n, k) : n * 64 + k)] = TC ? tf32r(tor0[idx]) : tor0[idx];
     }
     for (int n = tid; n < kHid; n += kBwdThreads) {
         S[M.f.PkAtt + 4 * n + 2] = params[param_offset(L, ATT0_B) + n];
@@ -124,15 +155,24 @@ __device__ inline void stage_layer_weights_bwd(float* S, const BwdMap& M, const 
         S[M.f.PkMisc + 4 * n + 1] = params[param_offset(L, TRN2_W) + n];
         S[M.f.PkMisc + 4 * n + 2] = params[param_offset(L, ROT0_B) + n];
         S[M.f.PkMisc + 4 * n + 3] = params[param_offset(L, MSG2_B) + n];
-        S[M.f.PkTor2 + 8 * n + 7] = 0.0f;
+        if (!TC) S[M.f.PkTor2 + 8 * n + 7] = 0.0f;
+        if (TC) {
+            S[M.W3i + kW3Tor + wswz(7, n)] = 0.0f;
+            S[M.W3i + kW3Trn + wswz(0, n)] = tf32r(params[param_offset(L, TRN2_W) + n]);
+            S[M.W3i + kW3Att + wswz(0, n)] = tf32r(params[param_offset(L, ATT2_W) + n]);
+            for (int e = 0; e < 4; ++e) S[M.Wx + kWxRot + wswz(e, n)] = tf32r(rot0[n * 68 + 64 + e]);
+            for (int e = 0; e < 2; ++e) S[M.Wx + kWxAtt + wswz(e, n)] = tf32r(att0[n * 66 + 64 + e]);
+        }
     }
     for (int idx = tid; idx < 4 * kHid; idx += kBwdThreads) {
         int c = idx >> 6, n = idx & 63;
-        S[M.f.PkRot2 + 4 * n + c] = params[param_offset(L, ROT2_W) + idx];
+        if (TC) S[M.W3i + kW3Rot + wswz(c, n)] = tf32r(params[param_offset(L, ROT2_W) + idx]);
+        else S[M.f.PkRot2 + 4 * n + c] = params[param_offset(L, ROT2_W) + idx];
     }
     for (int idx = tid; idx < PMHC_NTORS * kHid; idx += kBwdThreads) {
         int c = idx >> 6, n = idx & 63;
-        S[M.f.PkTor2 + 8 * n + c] = params[param_offset(L, TOR2_W) + idx];
+        if (TC) S[M.W3i + kW3Tor + wswz(c, n)] = tf32r(params[param_offset(L, TOR2_W) + idx]);
+        else S[M.f.PkTor2 + 8 * n + c] = params[param_offset(L, TOR2_W) + idx];
     }
     if (tid == 0) {
         S[M.f.Scal + SC_ATT2B] = params[param_offset(L, ATT2_B)];
@@ -211,6 +251,7 @@ __device__ __forceinline__ void coop_outer(const float* __restrict__ bufN, const
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
 // second-layer weights of a head: dWo[c][n] += sum_p dout[c][p] * hid[n][p], dbo[c] += sum_p dout[c][p]
+template <int LD = kLdc>
 __device__ __forceinline__ void coop_dwo(const float* __restrict__ hid, const float* __restrict__ dout, int C,
                                          float* __restrict__ dwo, float* __restrict__ dbo) {
     for (int idx = threadIdx.x; idx < C * kHid + C; idx += kBwdThreads) {
@@ -218,13 +259,13 @@ __device__ __forceinline__ void coop_dwo(const float* __restrict__ hid, const fl
         if (idx < C * kHid) {
             int c = idx >> 6, n = idx & 63;
             for (int p4 = 0; p4 < 32; ++p4)
-                sum += dot4(*reinterpret_cast<const float4*>(hid + n * kLdc + 4 * p4),
-                            *reinterpret_cast<const float4*>(dout + c * kLdc + 4 * p4));
+                sum += dot4(*reinterpret_cast<const float4*>(hid + n * LD + 4 * p4),
+                            *reinterpret_cast<const float4*>(dout + c * LD + 4 * p4));
             dwo[idx] += sum;
         } else {
             int c = idx - C * kHid;
             for (int p4 = 0; p4 < 32; ++p4) {
-                float4 v = *reinterpret_cast<const float4*>(dout + c * kLdc + 4 * p4);
+                float4 v = *reinterpret_cast<const float4*>(dout + c * LD + 4 * p4);
                 sum += (v.x + v.y) + (v.z + v.w);
             }
             dbo[c] += sum;
@@ -248,6 +289,7 @@ __device__ __forceinline__ void coop_bias_extras(const float* __restrict__ dpre,
 }
 
 // dst[row(rl)][n] += sum over the pass's pairs of row rl of buf[n][col]
+template <int LD = kLdc>
 __device__ __forceinline__ void accumulate_rows(const float* __restrict__ buf, float* __restrict__ dst, int ld,
                                                 const int* I, int L, int Wr, int pass_base, int npass) {
     for (int idx = threadIdx.x; idx < L * kHid; idx += kBwdThreads) {
@@ -255,7 +297,7 @@ __device__ __forceinline__ void accumulate_rows(const float* __restrict__ buf, f
         int lo = max(rl * Wr, pass_base), hi = min((rl + 1) * Wr, pass_base + npass);
         if (hi <= lo) continue;
         float sum = 0.0f;
-        for (int gp = lo; gp < hi; ++gp) sum += buf[n * kLdc + (gp - pass_base)];
+        for (int gp = lo; gp < hi; ++gp) sum += buf[n * LD + (gp - pass_base)];
         dst[I[IN_ROWS + rl] * ld + n] += sum;
     }
 }
@@ -650,11 +692,643 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
     __syncthreads();
 }
 
-template <int LAYER>
+// =====================================================================================================================
+// Tensor-core mode (PMHC_PRECISION_BF16 training): every 64-wide contraction of the pass — the forward recomputation
+// (message layer 2, the four head hidden layers), the input gradients (W_h^T dpre, W2^T dm) and the weight-gradient outer
+// products — runs as a CTA-level TF32 GEMM on the warp-level tensor-core path (mma.sync.m16n8k8, fp32 accumulate) over
+// the same [feature][pair] column tiles; the per-pair second layers, geometry and softmax backward stay fp32 scalar code.
+// Operands are rounded to tf32 (cvt.rna) once where they are written; gate: the 1e-2 class of the tensor-core forward.
+// =====================================================================================================================
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// acc[mt][nt] += A (64 x 64) * X (64 x this warp's 16 pair columns).  A[m][k] = W[m][k] (TRANS = false) or W[k][m] (true),
+// W swizzled (wswz); X a [64][kLdt] column tile.  Fragment (mt, nt) element e: row 16 mt + g + 8 (e >> 1),
+// pair column 16 warp + 8 nt + 2 t + (e & 1), g = lane >> 2, t = lane & 3.
+template <bool TRANS>
+__device__ __forceinline__ void gemm64_tf32(const float* __restrict__ W, const float* __restrict__ X, float (&acc)[4][2][4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const uint32_t* Wu = reinterpret_cast<const uint32_t*>(W);
+    const uint32_t* xb = reinterpret_cast<const uint32_t*>(X) + 16 * warp + g + t * kLdt;
+    // non-transposed: index = (16 mt + g + 8 h) * 64 + ((t | sw) ^ (8 ks + 4 c)), sw = ((g & 3) << 3) | (g & 4)
+    // transposed:     index = (8 ks + t + 4 c) * 64 + ((g | t << 3) ^ ((16 mt + 8 h) ^ 4 c))
+    const int base = TRANS ? t * 64 : g * 64;
+    const int x = TRANS ? (g | (t << 3)) : (t | ((g & 3) << 3) | (g & 4));
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        uint32_t b[2][2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            b[nt][0] = xb[(8 * ks) * kLdt + 8 * nt];
+            b[nt][1] = xb[(8 * ks + 4) * kLdt + 8 * nt];
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            uint32_t a[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int h = e & 1, c = e >> 1;   // a0: (g, t) a1: (g + 8, t) a2: (g, t + 4) a3: (g + 8, t + 4)
+                a[e] = TRANS ? Wu[base + (8 * ks + 4 * c) * 64 + (x ^ ((16 * mt + 8 * h) ^ (4 * c)))]
+                             : Wu[base + (16 * mt + 8 * h) * 64 + (x ^ (8 * ks + 4 * c))];
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], a[0], a[1], a[2], a[3], b[nt][0], b[nt][1]);
+        }
+    }
+}
+
+// Weight-gradient outer products of one pass: tile[n][k] += sum_p Bn[n][p] Bk[k][p] over the 128 pair columns, plus the
+// same rows against the 8-row geometry tile (lq 0..3, -d2, qdot2, 1, 0): columns [e0, e0 + ne) of that product go to the
+// "extra input" weights xw[n * ldw + e - e0], column 6 (the ones row) to the first-layer bias xb[n].
+// Warp w owns rows n in [16 (w >> 1), +16) and columns k in [32 (w & 1), +32); its 16 sums per thread sit contiguously in
+// the tile-owner layout (tile + 16 tid); the even warps also own the extras of their rows.
+__device__ __forceinline__ void outer_tf32(const float* __restrict__ Bn, const float* __restrict__ Bk, const float* __restrict__ Geo,
+                                           float* __restrict__ tile, float* __restrict__ xw, int ldw, int e0, int ne,
+                                           float* __restrict__ xb) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int mt = warp >> 1, kh = warp & 1;
+    const uint32_t* an = reinterpret_cast<const uint32_t*>(Bn) + (16 * mt + g) * kLdt + t;
+    const uint32_t* bk = reinterpret_cast<const uint32_t*>(Bk) + (32 * kh + g) * kLdt + t;
+    const uint32_t* ge = reinterpret_cast<const uint32_t*>(Geo) + g * kLdt + t;
+    float acc[4][4], accx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float4* dst = reinterpret_cast<float4*>(tile + tid * 16);
+    // the running sums come from L2: start from them, so the round trip hides under the MMAs
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const float4 v = __ldcg(dst + nt);
+        acc[nt][0] = v.x; acc[nt][1] = v.y; acc[nt][2] = v.z; acc[nt][3] = v.w;
+    }
+#pragma unroll 4
+    for (int ks = 0; ks < 16; ++ks) {
+        const uint32_t a0 = an[8 * ks], a1 = an[8 * kLdt + 8 * ks], a2 = an[8 * ks + 4], a3 = an[8 * kLdt + 8 * ks + 4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], a0, a1, a2, a3, bk[(8 * nt) * kLdt + 8 * ks], bk[(8 * nt) * kLdt + 8 * ks + 4]);
+        if (kh == 0) mma_tf32(accx, a0, a1, a2, a3, ge[8 * ks], ge[8 * ks + 4]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) dst[nt] = make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
+    if (kh == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int n = 16 * mt + g + 8 * (e >> 1), col = 2 * t + (e & 1);
+            if (xw != nullptr && col >= e0 && col < e0 + ne) xw[n * ldw + (col - e0)] += accx[e];
+            if (xb != nullptr && col == 6) xb[n] += accx[e];
+        }
+    }
+}
+// (n, k) of element e of thread tid in the tensor-core tile-owner layout
+__device__ __forceinline__ void tc_tile_coord(int tid, int e, int& n, int& k) {
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int nt = e >> 2, r = e & 3;
+    n = 16 * (warp >> 1) + g + 8 * (r >> 1);
+    k = 32 * (warp & 1) + 8 * nt + 2 * t + (r & 1);
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[4][2][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.0f;
+}
+
+enum { GEO_LQ = 0, GEO_D2 = 4, GEO_QD = 5, GEO_ONE = 6, GEO_ZERO = 7, GEO_D2F = 8, GEO_QDF = 9 };
+
+// out rows: acc2[nt] = sum_n Wimg[c][n] X[n][.] for the C (<= 8) rows c = g of a swizzled row image, over this warp's 16 pair
+// columns: element e < 2 of acc2[nt] is (row g, column 16 warp + 8 nt + 2 t + e); the m16 tile's rows g + 8 are zero.
+__device__ __forceinline__ void rows8_tf32(const float* __restrict__ Wimg, int C, const float* __restrict__ X, float (&acc2)[2][4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const uint32_t* wu = reinterpret_cast<const uint32_t*>(Wimg) + g * 64;
+    const uint32_t* xb = reinterpret_cast<const uint32_t*>(X) + 16 * warp + g + t * kLdt;
+    const bool rowok = g < C;
+    const int x = t | ((g & 3) << 3) | (g & 4);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc2[nt][e] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t a0 = rowok ? wu[x ^ (8 * ks)] : 0u, a2 = rowok ? wu[x ^ (8 * ks + 4)] : 0u;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) mma_tf32(acc2[nt], a0, 0u, a2, 0u, xb[(8 * ks) * kLdt + 8 * nt], xb[(8 * ks + 4) * kLdt + 8 * nt]);
+    }
+}
+// acc[mt][nt] = sum_{c < C} Wimg[c][16 mt + .] D[c][.]: the hidden-layer gradient before the relu mask (one k-step, c = t, t + 4)
+__device__ __forceinline__ void cols8_tf32(const float* __restrict__ Wimg, int C, const float* __restrict__ D, float (&acc)[4][2][4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const uint32_t* wu = reinterpret_cast<const uint32_t*>(Wimg);
+    const uint32_t* du = reinterpret_cast<const uint32_t*>(D) + 16 * warp + g;
+    const bool lo = t < C, hi = t + 4 < C;
+    uint32_t b[2][2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+        b[nt][0] = lo ? du[t * kLdt + 8 * nt] : 0u;
+        b[nt][1] = hi ? du[(t + 4) * kLdt + 8 * nt] : 0u;
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        // row c = t: swizzle ((t & 3) << 3) | (t & 4) = t << 3; row t + 4: (t << 3) | 4
+        const uint32_t a0 = lo ? wu[t * 64 + ((16 * mt + g) ^ (t << 3))] : 0u;
+        const uint32_t a1 = lo ? wu[t * 64 + ((16 * mt + g + 8) ^ (t << 3))] : 0u;
+        const uint32_t a2 = hi ? wu[(t + 4) * 64 + ((16 * mt + g) ^ ((t << 3) | 4))] : 0u;
+        const uint32_t a3 = hi ? wu[(t + 4) * 64 + ((16 * mt + g + 8) ^ ((t << 3) | 4))] : 0u;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.0f;
+            mma_tf32(acc[mt][nt], a0, a1, a2, a3, b[nt][0], b[nt][1]);
+        }
+    }
+}
+// second-layer weight gradients: dwo[c * 64 + n] += sum_p D[c][p] Hid[n][p], dbo[c] += sum_p D[c][p] over the 128 pair columns;
+// warp w owns the hidden units n in [8 w, 8 w + 8), warp 0 also the bias (a B operand of ones)
+__device__ __forceinline__ void dwo_tf32(const float* __restrict__ D, int C, const float* __restrict__ Hid,
+                                         float* __restrict__ dwo, float* __restrict__ dbo) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const bool rowok = g < C;
+    const uint32_t* du = reinterpret_cast<const uint32_t*>(D) + g * kLdt + t;
+    const uint32_t* hu = reinterpret_cast<const uint32_t*>(Hid) + (8 * warp + g) * kLdt + t;
+    float* dst = dwo + g * 64 + 8 * warp + 2 * t;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, accb[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (rowok) { acc[0] = __ldcg(dst); acc[1] = __ldcg(dst + 1); }
+    const uint32_t one = __float_as_uint(1.0f);
+#pragma unroll 4
+    for (int ks = 0; ks < 16; ++ks) {
+        const uint32_t a0 = rowok ? du[8 * ks] : 0u, a2 = rowok ? du[8 * ks + 4] : 0u;
+        mma_tf32(acc, a0, 0u, a2, 0u, hu[8 * ks], hu[8 * ks + 4]);
+        if (warp == 0) mma_tf32(accb, a0, 0u, a2, 0u, one, one);
+    }
+    if (rowok) { dst[0] = acc[0]; dst[1] = acc[1]; }
+    if (warp == 0 && rowok && t == 0) dbo[g] += accb[0];
+}
+
+// One pass of up to 128 pairs, tensor-core mode.  Same contract as pair_pass.  Per head: hidden layer (GEMM) -> second
+// layer (MMA, own columns) | barrier | per-pair geometry and output gradients (threads 0..127, one per pair) | barrier |
+// second-layer weight gradients (MMA) | barrier | hidden-layer gradient (MMA + relu mask, in place), input gradient GEMM
+// into the running dL/dm fragments, extras gradients | barrier | first-layer weight-gradient outer products | barrier.
+template <int LAYER, bool HEADS>
+__device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const BwdArgs& g, const PairRef pr, float mult,
+                                             int b, const float* __restrict__ ajt, float* __restrict__ dajt,
+                                             float* __restrict__ tiles, float* __restrict__ direct, const int* I,
+                                             int L, int Wr, int pass_base, int npass, int n_pocket_cols, int pocket_e0) {
+    constexpr bool IN_GRADS = (LAYER == 1);
+    const LayerArgs& a = g.a;
+    const int tid = threadIdx.x;
+    const int p = tid & (kBwdPairs - 1);          // this thread's pair column in the per-pair stages
+    const int half = tid >> 7, n0 = 32 * half;
+    const bool owner = half == 0;
+    const int lane = tid & 31, warp = tid >> 5, fg = lane >> 2, ft = lane & 3;   // fragment coordinates in the GEMM stages
+    const int i = pr.i, j = pr.j;
+    const bool act = pr.active;
+    const bool pep = (j >= 0 && j < kN);
+    float* bufA = S + M.BufA;
+    float* bufB = S + M.BufB;
+    float* sDout = S + M.Dout;
+    float* sGeo = S + M.Ex;
+    float* sDx = S + M.Dx;
+    int* sPI = reinterpret_cast<int*>(sDout + 7 * kLdt);   // row node of every pair column of the pass
+    const float* W2s = S + M.W2;
+    const float* Whs = S + M.Wh;
+    const float* W3s = S + M.W3i;
+    const float* Wxs = S + M.Wx;
+    const int Kpad = a.Kpad;
+    constexpr int base = param_offset(LAYER, 0);
+    float acc[4][2][4], o2[2][4];
+
+    // store the valid rows (g < C) of a rows8 result into a [.][kLdt] tile at this warp's columns
+    auto store_rows = [&](float* dst, int C) {
+        if (fg < C) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+                *reinterpret_cast<float2*>(dst + fg * kLdt + 16 * warp + 8 * nt + 2 * ft) = make_float2(o2[nt][0], o2[nt][1]);
+        }
+    };
+    // hidden-layer gradient: acc (before the mask) -> relu mask from the hidden activations in BufB -> BufB in place (own columns)
+    auto mask_store_dpre = [&]() {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n = 16 * mt + fg + 8 * h;
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    float2* q = reinterpret_cast<float2*>(bufB + n * kLdt + 16 * warp + 8 * nt + 2 * ft);
+                    const float2 hv = *q;
+                    *q = make_float2(hv.x > 0.0f ? tf32r(acc[mt][nt][2 * h]) : 0.0f, hv.y > 0.0f ? tf32r(acc[mt][nt][2 * h + 1]) : 0.0f);
+                }
+            }
+    };
+
+    if (owner) {
+        sPI[p] = i;
+        sGeo[GEO_ONE * kLdt + p] = 1.0f;
+        sGeo[GEO_ZERO * kLdt + p] = 0.0f;
+    }
+    if (HEADS) {
+        const float* rg = S + M.RowG + i * 16;
+        const float lse = rg[15], c_i = rg[14];
+        const float logit = g.logits[((size_t)b * kN + i) * Kpad + j];
+        const float w = act ? expf(logit - lse) : 0.0f;
+        const float* pqi = S + M.f.Q + i * 4;
+        const float* pqj = S + M.f.Q + j * 4;
+        const Quat qi{pqi[0], pqi[1], pqi[2], pqi[3]}, qj{pqj[0], pqj[1], pqj[2], pqj[3]};
+        const float rx = S[M.f.X + i * 3] - S[M.f.X + j * 3], ry = S[M.f.X + i * 3 + 1] - S[M.f.X + j * 3 + 1],
+                    rz = S[M.f.X + i * 3 + 2] - S[M.f.X + j * 3 + 2];
+        const Quat qinvj = qinv(qj);
+        const Quat v = qmul(qi, qj);
+        const Quat lq = qmul(qinvj, v);
+        const float d2 = rx * rx + ry * ry + rz * rz;
+        const float dotq = qdot(qi, qj);
+        const float qd = dotq * dotq;
+        float dLdw = 0.0f;
+        float gi[7] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // layer 2: this pair's share of dL / d (q_i, x_i), summed per row below
+        Quat dqj_part{0.0f, 0.0f, 0.0f, 0.0f}, dqinv_part{0.0f, 0.0f, 0.0f, 0.0f};   // rotation head: the input-gradient terms that do not wait for dlq
+        {   // ---- m1 (my half of its features) -> BufB; the pair's geometry row -> sGeo ----
+            float m1h[32];
+            compute_m1<LAYER, 32>(m1h, n0, S, M, a.params, ajt, Kpad, i, j);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) bufB[(n0 + k) * kLdt + p] = tf32r(m1h[k]);
+            if (owner) {
+                sGeo[(GEO_LQ + 0) * kLdt + p] = tf32r(lq.w); sGeo[(GEO_LQ + 1) * kLdt + p] = tf32r(lq.x);
+                sGeo[(GEO_LQ + 2) * kLdt + p] = tf32r(lq.y); sGeo[(GEO_LQ + 3) * kLdt + p] = tf32r(lq.z);
+                sGeo[GEO_D2 * kLdt + p] = tf32r(-d2); sGeo[GEO_QD * kLdt + p] = tf32r(qd);
+                sGeo[GEO_D2F * kLdt + p] = -d2;       sGeo[GEO_QDF * kLdt + p] = qd;
+            }
+        }
+        __syncthreads();
+        // ---- message = W2 m1 + b2 -> BufA ----
+        zero_acc(acc);
+        gemm64_tf32<false>(W2s, bufB, acc);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n = 16 * mt + fg + 8 * h;
+                const float b2 = S[M.f.PkMisc + 4 * n + 3];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int pc = 16 * warp + 8 * nt + 2 * ft;
+                    *reinterpret_cast<float2*>(bufA + n * kLdt + pc) =
+                        make_float2(tf32r(acc[mt][nt][2 * h] + b2), tf32r(acc[mt][nt][2 * h + 1] + b2));
+                }
+            }
+        __syncthreads();
+        float dm[4][2][4];                         // dL / d message, fragment layout (row = feature, column = pair)
+        zero_acc(dm);
+
+        // ================= rotation head (model.py:283-296) =================
+        {
+            zero_acc(acc);
+            gemm64_tf32<false>(Whs + HD_ROT * 4096, bufA, acc);
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = 16 * mt + fg + 8 * h;
+                    const float4 wq = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n);
+                    const float bias = S[M.f.PkMisc + 4 * n + 2];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const int pc = 16 * warp + 8 * nt + 2 * ft;
+                        float o[2];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const float* ge = sGeo + pc + c;
+                            const float s = acc[mt][nt][2 * h + c] + bias + wq.x * ge[0] + wq.y * ge[kLdt] + wq.z * ge[2 * kLdt] + wq.w * ge[3 * kLdt];
+                            o[c] = tf32r(fmaxf(s, 0.0f));
+                        }
+                        *reinterpret_cast<float2*>(bufB + n * kLdt + pc) = make_float2(o[0], o[1]);
+                    }
+                }
+            __syncwarp();
+            rows8_tf32(W3s + kW3Rot, 4, bufB, o2);
+            store_rows(sDout, 4);
+            __syncthreads();
+            Quat ddg{0.0f, 0.0f, 0.0f, 0.0f}, u{1.0f, 0.0f, 0.0f, 0.0f};
+            if (owner) {
+                const Quat dl{sigmoidf(sDout[0 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 0]), sigmoidf(sDout[1 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 1]),
+                              sigmoidf(sDout[2 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 2]), sigmoidf(sDout[3 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 3])};
+                u = qmul(dl, qinvj);
+                const Quat dg = qmul(qj, u);
+                const Quat dG{rg[0], rg[1], rg[2], rg[3]};
+                dLdw += qdot(dG, dg);
+                ddg = qscale(dG, w);
+                const Quat du = qmul_grad_b(qj, ddg);         // dg = qj * u
+                const Quat ddl = qmul_grad_a(du, qinvj);      // u = dl * qinvj
+                sDout[0 * kLdt + p] = tf32r(ddl.w * dl.w * (1.0f - dl.w));
+                sDout[1 * kLdt + p] = tf32r(ddl.x * dl.x * (1.0f - dl.x));
+                sDout[2 * kLdt + p] = tf32r(ddl.y * dl.y * (1.0f - dl.y));
+                sDout[3 * kLdt + p] = tf32r(ddl.z * dl.z * (1.0f - dl.z));
+                if (IN_GRADS) {
+                    dqj_part = qmul_grad_a(ddg, u);            // dg = qj * u
+                    dqinv_part = qmul_grad_b(dl, du);          // u = dl * qinvj
+                }
+            }
+            __syncthreads();
+            dwo_tf32(sDout, 4, bufB, direct + (param_offset(LAYER, ROT2_W) - base), direct + (param_offset(LAYER, ROT2_B) - base));
+            __syncthreads();
+            cols8_tf32(W3s + kW3Rot, 4, sDout, acc);
+            mask_store_dpre();
+            __syncwarp();
+            gemm64_tf32<true>(Whs + HD_ROT * 4096, bufB, dm);
+            if (IN_GRADS) {
+                rows8_tf32(Wxs + kWxRot, 4, bufB, o2);     // dL / d local quaternion
+                store_rows(sDx, 4);
+            }
+            __syncthreads();
+            outer_tf32(bufB, bufA, sGeo, tiles + T_ROT * 4096, direct + (param_offset(LAYER, ROT0_W) - base) + 64, 68, GEO_LQ, 4,
+                       direct + (param_offset(LAYER, ROT0_B) - base));
+            __syncthreads();
+        }
+
+        // ================= torsion head (model.py:257-263) =================
+        {
+            zero_acc(acc);
+            gemm64_tf32<false>(Whs + HD_TOR * 4096, bufA, acc);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int pc = 16 * warp + 8 * nt + 2 * ft + c;
+                    const float* tt = S + M.f.Tt + sPI[pc] * kHid;
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int n = 16 * mt + fg + 8 * h;
+                            bufB[n * kLdt + pc] = tf32r(fmaxf(acc[mt][nt][2 * h + c] + tt[n], 0.0f));
+                        }
+                }
+            __syncwarp();
+            rows8_tf32(W3s + kW3Tor, PMHC_NTORS, bufB, o2);
+            store_rows(sDout, PMHC_NTORS);
+            __syncthreads();
+            if (owner) {
+                if (IN_GRADS && act) {
+                    // rotation head, second part: dL / d local quaternion arrived (sDx rows 0..3)
+                    const Quat dlqq{sDx[0 * kLdt + p], sDx[1 * kLdt + p], sDx[2 * kLdt + p], sDx[3 * kLdt + p]};
+                    const Quat dqinv = qadd(qmul_grad_a(dlqq, v), dqinv_part);   // lq = qinvj * v
+                    const Quat dv = qmul_grad_b(qinvj, dlqq);
+                    const Quat dqi = qmul_grad_a(dv, qj);                         // v = qi * qj
+                    Quat dqj = qadd(qmul_grad_b(qi, dv), dqj_part);
+                    dqj = qadd(dqj, qinv_grad(qj, dqinv));
+                    gi[0] += dqi.w; gi[1] += dqi.x; gi[2] += dqi.y; gi[3] += dqi.z;
+                    if (pep) atomic_add_quat(S + M.dQ + j * 4, dqj);
+                }
+#pragma unroll
+                for (int c = 0; c < PMHC_NTORS; ++c) {
+                    const float da = sDout[c * kLdt + p] + S[M.f.Scal + SC_TOR2B + c];
+                    dLdw = fmaf(rg[4 + c], da, dLdw);
+                    sDout[c * kLdt + p] = tf32r(w * rg[4 + c]);
+                }
+            }
+            __syncthreads();
+            dwo_tf32(sDout, PMHC_NTORS, bufB, direct + (param_offset(LAYER, TOR2_W) - base), direct + (param_offset(LAYER, TOR2_B) - base));
+            __syncthreads();
+            cols8_tf32(W3s + kW3Tor, PMHC_NTORS, sDout, acc);
+            mask_store_dpre();
+            __syncwarp();
+            gemm64_tf32<true>(Whs + HD_TOR * 4096, bufB, dm);
+            __syncthreads();
+            outer_tf32(bufB, bufA, sGeo, tiles + T_TOR * 4096, nullptr, 0, 0, 0, nullptr);
+            accumulate_rows<kLdt>(bufB, S + M.dTt, kHid, I, L, Wr, pass_base, npass);
+            __syncthreads();
+        }
+
+        // ================= translation head (model.py:325-331) =================
+        {
+            zero_acc(acc);
+            gemm64_tf32<false>(Whs + HD_TRN * 4096, bufA, acc);
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = 16 * mt + fg + 8 * h;
+                    const float bias = S[M.f.PkMisc + 4 * n + 0];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const int pc = 16 * warp + 8 * nt + 2 * ft;
+                        *reinterpret_cast<float2*>(bufB + n * kLdt + pc) =
+                            make_float2(tf32r(fmaxf(acc[mt][nt][2 * h] + bias, 0.0f)), tf32r(fmaxf(acc[mt][nt][2 * h + 1] + bias, 0.0f)));
+                    }
+                }
+            __syncwarp();
+            rows8_tf32(W3s + kW3Trn, 1, bufB, o2);
+            store_rows(sDout, 1);
+            __syncthreads();
+            if (owner) {
+                const float sc = sDout[p] + S[M.f.Scal + SC_TRN2B];
+                const float dXr = rg[11] * rx + rg[12] * ry + rg[13] * rz;
+                dLdw = fmaf(sc, dXr, dLdw);
+                sDout[p] = tf32r(w * dXr);
+                if (IN_GRADS && act) {
+                    const float f = w * sc;
+                    gi[4] += f * rg[11]; gi[5] += f * rg[12]; gi[6] += f * rg[13];
+                    if (pep) {
+                        atomicAdd(S + M.dX + j * 3 + 0, -f * rg[11]); atomicAdd(S + M.dX + j * 3 + 1, -f * rg[12]); atomicAdd(S + M.dX + j * 3 + 2, -f * rg[13]);
+                    }
+                }
+            }
+            __syncthreads();
+            dwo_tf32(sDout, 1, bufB, direct + (param_offset(LAYER, TRN2_W) - base), direct + (param_offset(LAYER, TRN2_B) - base));
+            __syncthreads();
+            cols8_tf32(W3s + kW3Trn, 1, sDout, acc);
+            mask_store_dpre();
+            __syncwarp();
+            gemm64_tf32<true>(Whs + HD_TRN * 4096, bufB, dm);
+            __syncthreads();
+            outer_tf32(bufB, bufA, sGeo, tiles + T_TRN * 4096, nullptr, 0, 0, 0, direct + (param_offset(LAYER, TRN0_B) - base));
+            __syncthreads();
+        }
+
+        // ================= attention head (model.py:238-243) =================
+        {
+            zero_acc(acc);
+            gemm64_tf32<false>(Whs + HD_ATT * 4096, bufA, acc);
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = 16 * mt + fg + 8 * h;
+                    const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const int pc = 16 * warp + 8 * nt + 2 * ft;
+                        float o[2];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const float s = (pk.z + acc[mt][nt][2 * h + c]) + fmaf(pk.y, sGeo[GEO_QDF * kLdt + pc + c], pk.x * sGeo[GEO_D2F * kLdt + pc + c]);
+                            o[c] = tf32r(fmaxf(s, 0.0f));
+                        }
+                        *reinterpret_cast<float2*>(bufB + n * kLdt + pc) = make_float2(o[0], o[1]);
+                    }
+                }
+            // softmax backward with the saved row statistics (see pair_pass for the saturated-row rule); the logit itself was
+            // saved by the forward, so the head's second layer is not recomputed
+            if (owner) sDout[p] = tf32r((w == 1.0f) ? 0.0f : w * (dLdw - c_i));
+            __syncthreads();
+            dwo_tf32(sDout, 1, bufB, direct + (param_offset(LAYER, ATT2_W) - base), direct + (param_offset(LAYER, ATT2_B) - base));
+            __syncthreads();
+            cols8_tf32(W3s + kW3Att, 1, sDout, acc);
+            mask_store_dpre();
+            __syncwarp();
+            gemm64_tf32<true>(Whs + HD_ATT * 4096, bufB, dm);
+            if (IN_GRADS) {
+                rows8_tf32(Wxs + kWxAtt, 2, bufB, o2);     // dL / d (-d2), dL / d qdot2
+                store_rows(sDx + 4 * kLdt, 2);
+            }
+            __syncthreads();
+            outer_tf32(bufB, bufA, sGeo, tiles + T_ATT * 4096, direct + (param_offset(LAYER, ATT0_W) - base) + 64, 66, GEO_D2, 2,
+                       direct + (param_offset(LAYER, ATT0_B) - base));
+            __syncthreads();
+        }
+        if (IN_GRADS && owner) {
+            if (act) {
+                const float gd = sDx[4 * kLdt + p], gq = sDx[5 * kLdt + p];
+                const float f = -gd * 2.0f;                 // d(-d2) = gd
+                gi[4] += f * rx; gi[5] += f * ry; gi[6] += f * rz;
+                const float fq = gq * 2.0f * dotq;
+                gi[0] += fq * qj.w; gi[1] += fq * qj.x; gi[2] += fq * qj.y; gi[3] += fq * qj.z;
+                if (pep) {
+                    atomicAdd(S + M.dX + j * 3 + 0, -f * rx); atomicAdd(S + M.dX + j * 3 + 1, -f * ry); atomicAdd(S + M.dX + j * 3 + 2, -f * rz);
+                    atomic_add_quat(S + M.dQ + j * 4, qscale(qi, fq));
+                }
+            }
+            // the i side of the input gradients: one column per pair, reduced per row after the next barrier (every pair of
+            // a row adds to the same q_i / x_i: shared-memory atomics would serialise a whole row)
+#pragma unroll
+            for (int c = 0; c < 7; ++c) sDout[c * kLdt + p] = act ? gi[c] : 0.0f;
+        }
+        // ---- dm (+ the message-sum gradient of layer 1) -> BufB, inactive columns zero ----
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int pc = 16 * warp + 8 * nt + 2 * ft + c;
+                const bool on_col = pc < npass;
+                const float* dms = S + M.dMsum + sPI[pc] * kHid;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int n = 16 * mt + fg + 8 * h;
+                        float v = dm[mt][nt][2 * h + c];
+                        if (LAYER == 0) v += dms[n];
+                        bufB[n * kLdt + pc] = on_col ? tf32r(v) : 0.0f;
+                    }
+            }
+    } else {
+        if (owner) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) sGeo[r * kLdt + p] = 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) bufB[(n0 + k) * kLdt + p] = act ? tf32r(mult * S[M.dMsum + i * kHid + n0 + k]) : 0.0f;
+    }
+
+    // ---- message MLP backward: dW2 += dm (x) m1, dm1 = relu'(.) W2^T dm, then the per-node reductions ----
+    {
+        float m1h[32];
+        compute_m1<LAYER, 32>(m1h, n0, S, M, a.params, ajt, Kpad, i, j);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) bufA[(n0 + k) * kLdt + p] = tf32r(m1h[k]);
+    }
+    __syncthreads();
+    if (HEADS && IN_GRADS) {
+        for (int idx = tid; idx < L * 7; idx += kBwdThreads) {
+            const int rl = idx / 7, c = idx - rl * 7;
+            const int lo = max(rl * Wr, pass_base), hi = min((rl + 1) * Wr, pass_base + npass);
+            float sum = 0.0f;
+            for (int gp = lo; gp < hi; ++gp) sum += sDout[c * kLdt + (gp - pass_base)];
+            const int ri = I[IN_ROWS + rl];
+            if (hi > lo) {
+                if (c < 4) S[M.dQ + ri * 4 + c] += sum;
+                else S[M.dX + ri * 3 + (c - 4)] += sum;
+            }
+        }
+    }
+    zero_acc(acc);
+    gemm64_tf32<true>(W2s, bufB, acc);
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 16 * mt + fg + 8 * h;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int pc = 16 * warp + 8 * nt + 2 * ft;
+                const float2 m1v = *reinterpret_cast<const float2*>(bufA + k * kLdt + pc);
+                if (!(m1v.x > 0.0f)) acc[mt][nt][2 * h] = 0.0f;
+                if (!(m1v.y > 0.0f)) acc[mt][nt][2 * h + 1] = 0.0f;
+            }
+        }
+    outer_tf32(bufB, bufA, sGeo, tiles + T_W2 * 4096, nullptr, 0, 0, 0, direct + (param_offset(LAYER, MSG2_B) - base));
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 16 * mt + fg + 8 * h;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int pc = 16 * warp + 8 * nt + 2 * ft;
+                *reinterpret_cast<float2*>(bufB + k * kLdt + pc) = make_float2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]);
+            }
+        }
+    __syncthreads();
+    if (act && pep) {
+        float* dj = S + M.dAjPep + j * kLdN + n0;
+        float* de = S + M.dWe + (kN - 1 + i - j) * kLdN + n0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float v = bufB[(n0 + k) * kLdt + p];
+            atomicAdd(dj + k, v);
+            atomicAdd(de + k, v);
+        }
+    } else if (act && !HEADS && j >= kN) {
+        // masked pocket slot with non-zero features (rare): straight to the A_j^T gradient scratch
+        for (int k = 0; k < 32; ++k) atomicAdd(dajt + (n0 + k) * Kpad + j, bufB[(n0 + k) * kLdt + p]);
+    }
+    accumulate_rows<kLdt>(bufB, S + M.dAi, kLdN, I, L, Wr, pass_base, npass);
+    if (HEADS) {
+        // dA_j^T[k][j] += sum over rows of dm1 for the valid pocket columns of this pass
+        const int rl_lo = pass_base / Wr, rl_hi = (pass_base + npass - 1) / Wr;
+        const int n_items = n_pocket_cols * kHid;
+        for (int idx0 = tid; idx0 < n_items; idx0 += 4 * kBwdThreads) {   // four L2 read-modify-writes in flight per thread
+            float old[4];
+            int addr[4], kk[4], ee[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = idx0 + u * kBwdThreads;
+                kk[u] = idx / n_pocket_cols;
+                ee[u] = idx - kk[u] * n_pocket_cols;
+                addr[u] = idx < n_items ? kk[u] * Kpad + I[IN_POCKET + ee[u]] : -1;
+                old[u] = addr[u] >= 0 ? __ldcg(dajt + addr[u]) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (addr[u] < 0) continue;
+                float sum = 0.0f;
+                for (int rl = rl_lo; rl <= rl_hi; ++rl) {
+                    const int col = rl * Wr + pocket_e0 + ee[u] - pass_base;
+                    if (col >= 0 && col < npass) sum += bufB[kk[u] * kLdt + col];
+                }
+                dajt[addr[u]] = old[u] + sum;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int LAYER, bool TC>
 __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(BwdArgs g) {
     extern __shared__ __align__(16) float S[];
     const LayerArgs& a = g.a;
-    const BwdMap M = make_bwd_map(a.Kpad);
+    const BwdMap M = make_bwd_map(a.Kpad, TC);
     constexpr bool IN_GRADS = (LAYER == 1);
     constexpr int H = layer_H(LAYER);
     constexpr int ld1 = 2 * H + kEdge;
@@ -669,7 +1343,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
     float* direct = tiles + kTileFloats;
 
     for (int idx = tid; idx < kTileFloats + layer_numel; idx += kBwdThreads) tiles[idx] = 0.0f;
-    stage_layer_weights_bwd<LAYER>(S, M, a.params);
+    stage_layer_weights_bwd<LAYER, TC>(S, M, a.params);
     __syncthreads();
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
@@ -803,7 +1477,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
             const int npass = min(kBwdPairs, total - pass_base);
             const bool act = pcol < npass;
             const PairRef pr = decode_full_pair(I, act ? pass_base + pcol : pass_base, W, L, 0, act);
-            pair_pass<LAYER, true>(S, M, g, pr, 1.0f, b, ajt, dajt, tiles, direct, I, L, W, pass_base, npass, ci.nv, L - 1);
+            if (TC) pair_pass_tc<LAYER, true>(S, M, g, pr, 1.0f, b, ajt, dajt, tiles, direct, I, L, W, pass_base, npass, ci.nv, L - 1);
+            else pair_pass<LAYER, true>(S, M, g, pr, 1.0f, b, ajt, dajt, tiles, direct, I, L, W, pass_base, npass, ci.nv, L - 1);
         }
         // ---------------- layer 1: message-only pairs (self, masked peptide / pocket slots) ----------------
         if (LAYER == 0 && L > 0) {
@@ -823,13 +1498,46 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
                 else if (e <= npx) pr.j = I[IN_PEPX + e - 1];
                 else if (e <= npx + ci.nx) pr.j = I[IN_POCKET + Kpad - 1 - (e - npx - 1)];
                 else { pr.j = -1; mult = (float)ci.c0; }
-                pair_pass<LAYER, false>(S, M, g, pr, mult, b, ajt, dajt, tiles, direct, I, L, W2, pass_base, npass, 0, 0);
+                if (TC) pair_pass_tc<LAYER, false>(S, M, g, pr, mult, b, ajt, dajt, tiles, direct, I, L, W2, pass_base, npass, 0, 0);
+                else pair_pass<LAYER, false>(S, M, g, pr, mult, b, ajt, dajt, tiles, direct, I, L, W2, pass_base, npass, 0, 0);
             }
         }
         __syncthreads();
 
         // ---------------- node level: message_mlp.0, torsion_mlp.0[:, 64:78] and biases; input gradients ----------------
         {
+            // neighbour-feature columns fed by the pocket (cc < 22): sum_j dA_j[k] h_j[cc] over the peptide, then over the
+            // pocket slots in ascending order; the pocket's dA_j^T (L2) and features are staged through shared memory in
+            // chunks of 128 slots so the 80..480-term chains run from shared memory instead of one L2 round trip per term
+            constexpr int ldc = TC ? kLdt : kLdc;
+            float* scr = S + M.Dout;                 // [64][22] running sums (Dout + Ex are free outside the passes)
+            float* stA = S + M.BufA;                 // [64][ldc] dA_j^T chunk
+            float* stB = S + M.BufB;                 // [128][22] pocket features chunk
+            for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += kBwdThreads) {
+                const int k = idx / PMHC_NFEAT, cc = idx - k * PMHC_NFEAT;
+                float acc = 0.0f;
+                for (int j = 0; j < kN; ++j) acc = fmaf(S[M.dAjPep + j * kLdN + k], S[M.f.H + j * kLdN + cc], acc);
+                scr[idx] = acc;
+            }
+            for (int p0 = 0; p0 < P; p0 += 128) {
+                const int n = min(128, P - p0);
+                __syncthreads();
+                for (int idx = tid; idx < kHid * n; idx += kBwdThreads) {
+                    const int k = idx / n, pp = idx - k * n;
+                    stA[k * ldc + pp] = __ldcg(dajt + k * Kpad + kN + p0 + pp);
+                }
+                const float* pf = a.pocket_feat + ((size_t)b * P + p0) * PMHC_NFEAT;
+                for (int idx = tid; idx < n * PMHC_NFEAT; idx += kBwdThreads) stB[idx] = __ldg(pf + idx);
+                __syncthreads();
+                for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += kBwdThreads) {
+                    const int k = idx / PMHC_NFEAT, cc = idx - k * PMHC_NFEAT;
+                    float acc = scr[idx];
+#pragma unroll 8
+                    for (int pp = 0; pp < n; ++pp) acc = fmaf(stA[k * ldc + pp], stB[pp * PMHC_NFEAT + cc], acc);
+                    scr[idx] = acc;
+                }
+            }
+            __syncthreads();
             float* dW1 = direct + (param_offset(LAYER, MSG0_W) - base);
             for (int idx = tid; idx < kHid * ld1; idx += kBwdThreads) {
                 int k = idx / ld1, c = idx - k * ld1;
@@ -838,12 +1546,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
                     for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dAi + i * kLdN + k], S[M.f.H + i * kLdN + c], acc);
                 } else if (c < 2 * H) {
                     int cc = c - H;
-                    for (int j = 0; j < kN; ++j) acc = fmaf(S[M.dAjPep + j * kLdN + k], S[M.f.H + j * kLdN + cc], acc);
                     if (cc < PMHC_NFEAT) {
-                        const float* pf = a.pocket_feat + (size_t)b * P * PMHC_NFEAT + cc;
-                        const float* dj = dajt + k * Kpad + kN;
-#pragma unroll 8
-                        for (int p = 0; p < P; ++p) acc = fmaf(__ldcg(dj + p), __ldg(pf + p * PMHC_NFEAT), acc);
+                        acc = scr[k * PMHC_NFEAT + cc];
+                    } else {
+                        for (int j = 0; j < kN; ++j) acc = fmaf(S[M.dAjPep + j * kLdN + k], S[M.f.H + j * kLdN + cc], acc);
                     }
                 } else {
                     acc = S[M.dWe + (c - 2 * H) * kLdN + k];
@@ -898,6 +1604,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
         int T = idx >> 12, r = idx & 4095;
         int t = r >> 4, e = r & 15;
         int k = (t & 15) + 16 * (e >> 2), n = (t >> 4) + 16 * (e & 3);
+        if (TC) tc_tile_coord(t, e, n, k);
         int off, ld;
         switch (T) {
             case T_W2: off = param_offset(LAYER, MSG2_W); ld = 64; break;
@@ -944,22 +1651,22 @@ BwdWorkspace carve_bwd_workspace(void* wsbase, size_t fwd_bytes, int B, int P) {
     return w;
 }
 
-template <int LAYER>
+template <int LAYER, bool TC>
 int launch_layer_backward(const BwdArgs& g, int n_cta, float* grad, cudaStream_t stream) {
     static bool configured = false;
     int max_smem = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const BwdMap M = make_bwd_map(g.a.Kpad);
+    const BwdMap M = make_bwd_map(g.a.Kpad, TC);
     size_t smem = (size_t)M.total_floats * sizeof(float);
     PMHC_REQUIRE((int)smem <= max_smem, "EGNN backward needs %zu B of shared memory (P=%d), device allows %d", smem, g.a.P, max_smem);
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(egnn_layer_backward_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaError_t e = cudaFuncSetAttribute(egnn_layer_backward_kernel<LAYER, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(backward): %s", cudaGetErrorString(e));
         configured = true;
     }
     if (profile_enabled()) profile_mark(PROF_BWD, stream, true);
-    egnn_layer_backward_kernel<LAYER><<<n_cta, kBwdThreads, smem, stream>>>(g);
+    egnn_layer_backward_kernel<LAYER, TC><<<n_cta, kBwdThreads, smem, stream>>>(g);
     if (profile_enabled()) profile_mark(PROF_BWD, stream, false);
     PMHC_CHECK_LAUNCH("egnn_layer_backward");
     constexpr int base = param_offset(LAYER, 0);
@@ -979,10 +1686,13 @@ extern "C" size_t pmhc_workspace_bytes(int B, int P) {
     return carve_bwd_workspace(nullptr, forward_workspace_bytes(B, P), B, P).bytes;
 }
 
-extern "C" int pmhc_model_backward(const float* params, const PmhcBatch* bt, float t_over_T, const float* saved,
-                                   const float* d_out_frames, const float* d_out_torsions, float* flat_grad,
-                                   void* workspace, size_t workspace_bytes, void* stream_, void* layer2_done_event) {
+extern "C" int pmhc_model_backward_ex(const float* params, const PmhcBatch* bt, float t_over_T, const float* saved,
+                                      const float* d_out_frames, const float* d_out_torsions, float* flat_grad,
+                                      void* workspace, size_t workspace_bytes, void* stream_, void* layer2_done_event,
+                                      int precision) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    PMHC_REQUIRE(precision == PMHC_PRECISION_FP32 || precision == PMHC_PRECISION_BF16, "pmhc_model_backward: unknown precision %d", precision);
+    const bool tc = precision == PMHC_PRECISION_BF16;
     PMHC_REQUIRE(device_props() == 0, "no CUDA device");
     PMHC_REQUIRE(bt != nullptr && bt->B > 0, "pmhc_model_backward: empty batch");
     PMHC_REQUIRE(bt->P >= 1 && bt->P <= kMaxP, "pmhc_model_backward: pocket_maxlen %d outside [1, %d]", bt->P, kMaxP);
@@ -1007,7 +1717,7 @@ extern "C" int pmhc_model_backward(const float* params, const PmhcBatch* bt, flo
     g.rowstat = sv.rowstat2; g.logits = sv.logits2; g.msum = nullptr; g.feat_post = nullptr;
     g.d_frames_out = d_out_frames; g.d_tors_out = d_out_torsions; g.d_feat_out = nullptr;
     g.d_frames_in = w.d_frames1; g.d_tors_in = w.d_tors1; g.d_feat_in = w.d_feat1;
-    int rc = launch_layer_backward<1>(g, n_cta, flat_grad, stream);
+    int rc = tc ? launch_layer_backward<1, true>(g, n_cta, flat_grad, stream) : launch_layer_backward<1, false>(g, n_cta, flat_grad, stream);
     if (rc != 0) return rc;
     if (layer2_done_event != nullptr) cudaEventRecord((cudaEvent_t)layer2_done_event, stream);
     // layer 1
@@ -1015,5 +1725,12 @@ extern "C" int pmhc_model_backward(const float* params, const PmhcBatch* bt, flo
     g.rowstat = sv.rowstat1; g.logits = sv.logits1; g.msum = sv.msum1; g.feat_post = sv.feat1;
     g.d_frames_out = w.d_frames1; g.d_tors_out = w.d_tors1; g.d_feat_out = w.d_feat1;
     g.d_frames_in = nullptr; g.d_tors_in = nullptr; g.d_feat_in = nullptr;
-    return launch_layer_backward<0>(g, n_cta, flat_grad, stream);
+    return tc ? launch_layer_backward<0, true>(g, n_cta, flat_grad, stream) : launch_layer_backward<0, false>(g, n_cta, flat_grad, stream);
+}
+
+extern "C" int pmhc_model_backward(const float* params, const PmhcBatch* bt, float t_over_T, const float* saved,
+                                   const float* d_out_frames, const float* d_out_torsions, float* flat_grad,
+                                   void* workspace, size_t workspace_bytes, void* stream_, void* layer2_done_event) {
+    return pmhc_model_backward_ex(params, bt, t_over_T, saved, d_out_frames, d_out_torsions, flat_grad, workspace, workspace_bytes,
+                                  stream_, layer2_done_event, PMHC_PRECISION_FP32);
 }

@@ -100,9 +100,10 @@ class _DenoiserFn(torch.autograd.Function):
         ws_bytes = lib.pmhc_workspace_bytes(B, desc.P)
         ws = _lib.workspace(dev, ws_bytes)
         with torch.cuda.device(dev):
-            _lib.check(lib.pmhc_model_backward(flat.data_ptr(), ctypes.byref(desc), ctx.t_over_T, ctx.saved_buf.data_ptr(),
-                                               d_frames.data_ptr(), d_tors.data_ptr(), grad.data_ptr(), ws.data_ptr(),
-                                               ws_bytes, _lib.stream_ptr(dev), None), "pmhc_model_backward")
+            _lib.check(lib.pmhc_model_backward_ex(flat.data_ptr(), ctypes.byref(desc), ctx.t_over_T, ctx.saved_buf.data_ptr(),
+                                                  d_frames.data_ptr(), d_tors.data_ptr(), grad.data_ptr(), ws.data_ptr(),
+                                                  ws_bytes, _lib.stream_ptr(dev), None, model.backward_precision_code()),
+                       "pmhc_model_backward")
         grads = model._split_flat(grad)
         return (None,) * 9 + tuple(grads)
 
@@ -133,6 +134,9 @@ class Model(torch.nn.Module):
         # arithmetic of the two dense per-pair contractions: "fp32" (FFMA, <= 1e-4 parity) or "bf16" (tcgen05 tensor
         # cores, bf16 operands / fp32 accumulate, <= 1e-2); everything else is fp32 in both modes
         self.precision = "fp32"
+        # arithmetic of the backward's contractions: None = follow `precision` ("bf16" -> TF32 tensor-core backward, same
+        # 1e-2 class as the tensor-core forward), or "fp32" / "bf16" to choose it independently of the forward
+        self.backward_precision = None
         self._flat = None
         self._flat_generation = 0
         self._flatten()
@@ -185,6 +189,13 @@ class Model(torch.nn.Module):
             return _lib.PRECISIONS[self.precision]
         except KeyError:
             raise ValueError(f"Model.precision must be one of {sorted(_lib.PRECISIONS)}, got {self.precision!r}") from None
+
+    def backward_precision_code(self) -> int:
+        mode = self.precision if self.backward_precision is None else self.backward_precision
+        try:
+            return _lib.PRECISIONS[mode]
+        except KeyError:
+            raise ValueError(f"Model.backward_precision must be None or one of {sorted(_lib.PRECISIONS)}, got {mode!r}") from None
 
     # ---- forward -----------------------------------------------------------------------------------------
     def forward(self, batch: Dict[str, Union[torch.Tensor, Rigid]], t: int) -> Dict[str, Union[Rigid, torch.Tensor]]:

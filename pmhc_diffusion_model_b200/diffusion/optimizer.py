@@ -232,9 +232,9 @@ class DiffusionModelOptimizer:
             _lib.check(lib.pmhc_loss(true_f.data_ptr(), true_t.data_ptr(), pred_f.data_ptr(), pred_t.data_ptr(),
                                      _lib.u8c(batch["mask"]).data_ptr(), _lib.u8c(batch["torsions_mask"]).data_ptr(), B,
                                      1.0 / B, losses.data_ptr(), d_f.data_ptr(), d_t.data_ptr(), stream), "pmhc_loss")
-            _lib.check(lib.pmhc_model_backward(flat.data_ptr(), ctypes.byref(desc), t_over_T, saved.data_ptr(), d_f.data_ptr(),
-                                               d_t.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes, stream,
-                                               self.layer2_event_handle()), "pmhc_model_backward")
+            _lib.check(lib.pmhc_model_backward_ex(flat.data_ptr(), ctypes.byref(desc), t_over_T, saved.data_ptr(), d_f.data_ptr(),
+                                                  d_t.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes, stream,
+                                                  self.layer2_event_handle(), model.backward_precision_code()), "pmhc_model_backward")
 
         loss_dict = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
         if metrics is not None:

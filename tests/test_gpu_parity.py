@@ -323,6 +323,67 @@ def test_parameter_gradients_edge_shapes_vs_oracle_autograd(api):
         assert rel_err(p.grad.cpu(), p_ref[k].grad) < TOL, (k, rel_err(p.grad.cpu(), p_ref[k].grad))
 
 
+@pytest.mark.parametrize("B,L,Pn,P_pad,seed", [(5, (2, 16), (3, 50), 50, 41), (7, (8, 15), (40, 180), 192, 77), (3, (9, 9), (60, 60), 80, 5)])
+def test_tf32_backward_gradients_vs_oracle_autograd(api, B, L, Pn, P_pad, seed):
+    """Tensor-core backward on its own (fp32 forward, backward_precision = "bf16"): the forward recomputation, the input
+    gradients and the weight-gradient outer products run as TF32 MMAs.  Ragged peptides, dirty padding (message-only pairs
+    with their own features), several passes per complex.
+
+    Gates (tf32 operands carry 11 significant bits, so every recomputed activation is off by ~5e-4 relative):
+      * every tensor: max error <= 2e-2 of its largest entry (measured 1e-4 .. 1.1e-2) ...
+      * ... except the three tensors whose gradient is a small residual of cancelling per-pair terms, gated at 0.3 of the
+        largest entry (measured up to 0.2): rotation_mlp.0.{weight,bias} (neighbour rotations point everywhere: a ~100:1
+        cancelling sum) and attention_mlp.0.bias (softmax gradients of a row sum to zero; dlogit = w (dL/dw - c_i) takes c_i
+        from the forward's saved aggregates and dL/dw from the recomputation, so operand rounding leaves a residue);
+        attention_mlp.2.bias is exactly zero by that symmetry and gets an absolute 5e-3.  The bf16 forward has the same
+        property (mixed-precision test below);
+      * the whole flat gradient: cosine with the oracle's >= 0.99999 and relative L2 error <= 2e-3;
+      * the result must differ from the FFMA backward's (the tensor-core kernels really ran)."""
+    g = torch.Generator().manual_seed(seed)
+    batch = orc.synthetic_batch(B, L, Pn, P_pad=P_pad, seed=seed)
+    batch["pocket_features"][:, ::5] += torch.rand(B, batch["pocket_features"][:, ::5].shape[1], 22, generator=g)
+    params = orc.random_params(seed=9)
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    true = orc.gen_noise([B, 16], g)
+    pred = orc.model_forward(p_ref, orc.batch_to_frames(batch), 30, 100)
+    orc.get_loss(true, pred, batch["mask"], batch["torsions_mask"])["total loss"].mean().backward()
+    true_g = {"frames": api.Rigid(api.Rotation(quats=true["frames"]["quats"].to(DEV), normalize_quats=False), true["frames"]["trans"].to(DEV)),
+              "torsions": true["torsions"].to(DEV)}
+    grads = {}
+    for mode in ("fp32", "bf16"):
+        model = make_model(api, params, 100)
+        model.backward_precision = mode
+        gb = gpu_batch(batch)
+        out = model(gb, 30)
+        api.DMO.get_loss(true_g, out, gb["mask"], gb["torsions_mask"])["total loss"].mean().backward()
+        grads[mode] = {k: (None if p.grad is None else p.grad.cpu()) for k, p in model.named_parameters()}
+    bad, differs, flat_got, flat_ref = [], False, [], []
+    for k, ref in p_ref.items():
+        if k.startswith("gnn2.feature_mlp"):
+            assert grads["bf16"][k] is None
+            continue
+        got = grads["bf16"][k]
+        err = float((got - ref.grad).abs().max())
+        scale = float(ref.grad.abs().max())
+        if k.endswith("attention_mlp.2.bias"):
+            ok = err <= 5e-3
+        elif k.endswith(("rotation_mlp.0.weight", "rotation_mlp.0.bias", "attention_mlp.0.bias")):
+            ok = err <= 0.3 * scale
+        else:
+            ok = err <= 2e-2 * scale
+        if not ok:
+            bad.append((k, err, scale))
+        differs = differs or not torch.equal(got, grads["fp32"][k])
+        flat_got.append(got.flatten())
+        flat_ref.append(ref.grad.flatten())
+    assert not bad, bad
+    fg, fr = torch.cat(flat_got).double(), torch.cat(flat_ref).double()
+    cos = float(fg @ fr / (fg.norm() * fr.norm()))
+    rel = float((fg - fr).norm() / fr.norm())
+    assert cos >= 0.99999 and rel <= 2e-3, (cos, rel)
+    assert differs, "the tensor-core backward returned the FFMA backward's bits: it did not run"
+
+
 def test_optimize_steps_match_reference_fixture(api):
     """Two genuine reference optimize() calls (Adam, lr 1e-3) replayed through DiffusionModelOptimizer.optimize."""
     case = load_case("optimize_shipped_p80.pt")
