@@ -377,14 +377,33 @@ def main():
             return t
 
         tms = time_training()
-        tmodel.precision = "bf16"       # tensor-core forward (saves the softmax statistics), fp32 backward
+        tmodel.precision, tmodel.backward_precision = "bf16", "fp32"   # tensor-core forward (saves the softmax statistics), FFMA backward
         tms_bf16 = time_training()
+        tmodel.backward_precision = None                                # ... and the TF32 tensor-core backward: the "bf16" training mode
+        lib.pmhc_profile_enable(1)
+        tms_tc = time_training()
+        tprof_ms = (ctypes.c_double * 2)()
+        tprof_n = (ctypes.c_int64 * 2)()
+        lib.pmhc_profile_read(tprof_ms, tprof_n)
+        lib.pmhc_profile_enable(0)
         tmodel.precision = "fp32"
+        # backward roofline (tensor pipe): 3 x 43.4 kFLOP per real pair per layer (recomputation + input gradients + weight
+        # gradients), both layers' kernels averaged; pairs as in the forward count
+        bwd_us = tprof_ms[1] / max(tprof_n[1], 1) * 1e3
+        bwd_flops = TRAIN_B * 3.0 * 0.5 * forward_flops_per_complex()
         train = {"metric": "train complexes/s", "value": world * TRAIN_B * n_train / (tms / 1e3), "unit": UNIT,
                  "ms_per_step": tms / n_train, "global_batch": world * TRAIN_B, "steps": n_train,
                  "config": "B=256/GPU, 9-mer, pocket 60/80, fp32, noise+forward+loss+backward+Adam per step",
                  "bf16_forward": {"value": world * TRAIN_B * n_train / (tms_bf16 / 1e3), "ms_per_step": tms_bf16 / n_train,
-                                  "config": "same step with the tensor-core (bf16 operand) forward, fp32 backward"}}
+                                  "config": "same step with the tensor-core (bf16 operand) forward, fp32 FFMA backward"},
+                 "bf16": {"value": world * TRAIN_B * n_train / (tms_tc / 1e3), "ms_per_step": tms_tc / n_train,
+                          "config": "same step in the bf16 training mode: tcgen05 bf16 forward + TF32 tensor-core backward (gradient gate 1e-2 class)",
+                          "backward_kernel_us": bwd_us,
+                          "backward_roofline": {"bound": "tensor", "achieved": bwd_flops / (bwd_us * 1e-6) / 1e12,
+                                                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                                "frac": bwd_flops / (bwd_us * 1e-6) / 1e12 / peaks["bf16_tflops"],
+                                                "note": "algorithmic 3 x 43.4 kFLOP per pair per layer; TF32 mma.sync (legacy tensor path), "
+                                                        "judged against the measured bf16 peak"}}}
 
     # ---------------- loader / writer rows, rank 0 at N = 1 ----------------
     io = None

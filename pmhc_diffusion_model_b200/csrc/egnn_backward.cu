@@ -44,6 +44,7 @@ struct BwdArgs {
 struct BwdMap {
     SmemMap f;  // the fields setup_complex() uses (Scr, Ai, Tt, Msum, H, Tors, Q, X, Ints) and the packs
     int W2, Wh, BufA, BufB, Dout, Ex;
+    int Pl;
     int W3i, Wx, Dx;            // tensor-core mode: second-layer weight images, extra-input weight images, per-pair extras gradients
     int dAi, dAjPep, dWe, dTt, dMsum, RowG, dQ, dX, dTors, grads_end;
     int total_floats;
@@ -76,6 +77,8 @@ __host__ __device__ inline BwdMap make_bwd_map(int Kpad, bool tc = false) {
     m.Dout = o;     o += 8 * ldc;
     m.Ex = o;       o += (tc ? 10 : 6) * ldc;   // tensor-core mode: the per-pair geometry tile (8 MMA rows + 2 fp32 rows)
     if (tc) { m.Dx = o; o += 6 * ldc; }          // dL / d (local quaternion (4), -d2, qdot2) per pair column
+    m.Pl = -1;
+    if (tc) { m.Pl = o; o += kBwdPairs + 4; }    // list of the pass's peptide-neighbour pair columns (+ its length)
     m.f.Ai = o;     o += kN * kLdN;
     o = (o + 3) & ~3;
     m.f.Tt = o;     o += kN * kHid;
@@ -107,6 +110,10 @@ __host__ __device__ inline BwdMap make_bwd_map(int Kpad, bool tc = false) {
 // A[m][k] = W[m][k] (forward) and A[m][k] = W[k][m] (input gradients) fragment loads of mma.m16n8k8 are bank-conflict free
 // without padding: element (n, k) lives at n * 64 + (k ^ (((n & 3) << 3) | (n & 4))).
 __device__ __forceinline__ int wswz(int n, int k) { return n * 64 + (k ^ (((n & 3) << 3) | (n & 4))); }
+// The five 64 x 64 matrices additionally store column k at position kperm(k) inside its block of 8 — MMA k-slots (t, t + 4) of a
+// k-step sit next to each other — so the forward fragments (a0, a2) are one 64-bit load.
+__device__ __forceinline__ int kperm(int k) { return (k & ~7) | ((k & 3) << 1) | ((k >> 2) & 1); }
+__device__ __forceinline__ int wswzp(int n, int k) { return wswz(n, kperm(k)); }
 __device__ __forceinline__ float tf32r(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -122,9 +129,10 @@ __device__ inline void stage_layer_weights_bwd(float* S, const BwdMap& M, const 
     const float* rot0 = params + param_offset(L, ROT0_W);
     const float* tor0 = params + param_offset(L, TOR0_W);
     const float* trn0 = params + param_offset(L, TRN0_W);
+#pragma unroll 8
     for (int idx = tid; idx < kHid * kHid; idx += kBwdThreads) {
         if (TC) {
-            const int o = wswz(idx >> 6, idx & 63);
+            const int o = wswzp(idx >> 6, idx & 63);
             S[M.W2 + o] = tf32r(msg2[idx]);
             S[M.Wh + HD_TRN * 4096 + o] = tf32r(trn0[idx]);
         } else {
@@ -132,21 +140,24 @@ __device__ inline void stage_layer_weights_bwd(float* S, const BwdMap& M, const 
             S[M.Wh + HD_TRN * 4096 + idx] = trn0[idx];
         }
     }
+#pragma unroll 8
     for (int idx = tid; idx < kHid * 66; idx += kBwdThreads) {
         int n = idx / 66, k = idx - n * 66;
         float v = att0[idx];
-        if (k < 64) S[M.Wh + HD_ATT * 4096 + (TC ? wswz(n, k) : n * 64 + k)] = TC ? tf32r(v) : v;
+        if (k < 64) S[M.Wh + HD_ATT * 4096 + (TC ? wswzp(n, k) : n * 64 + k)] = TC ? tf32r(v) : v;
         else S[M.f.PkAtt + 4 * n + (k - 64)] = v;
     }
+#pragma unroll 8
     for (int idx = tid; idx < kHid * 68; idx += kBwdThreads) {
         int n = idx / 68, k = idx - n * 68;
         float v = rot0[idx];
-        if (k < 64) S[M.Wh + HD_ROT * 4096 + (TC ? wswz(n, k) : n * 64 + k)] = TC ? tf32r(v) : v;
+        if (k < 64) S[M.Wh + HD_ROT * 4096 + (TC ? wswzp(n, k) : n * 64 + k)] = TC ? tf32r(v) : v;
         else S[M.f.PkRotQ + 4 * n + (k - 64)] = v;
     }
+#pragma unroll 8
     for (int idx = tid; idx < kHid * 78; idx += kBwdThreads) {
         int n = idx / 78, k = idx - n * 78;
-        if (k < 64) S[M.Wh + HD_TOR * 4096 + (TC ? wswz(n, k) : n * 64 + k)] = TC ? tf32r(tor0[idx]) : tor0[idx];
+        if (k < 64) S[M.Wh + HD_TOR * 4096 + (TC ? wswzp(n, k) : n * 64 + k)] = TC ? tf32r(tor0[idx]) : tor0[idx];
     }
     for (int n = tid; n < kHid; n += kBwdThreads) {
         S[M.f.PkAtt + 4 * n + 2] = params[param_offset(L, ATT0_B) + n];
@@ -713,10 +724,12 @@ __device__ __forceinline__ void gemm64_tf32(const float* __restrict__ W, const f
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const uint32_t* Wu = reinterpret_cast<const uint32_t*>(W);
     const uint32_t* xb = reinterpret_cast<const uint32_t*>(X) + 16 * warp + g + t * kLdt;
-    // non-transposed: index = (16 mt + g + 8 h) * 64 + ((t | sw) ^ (8 ks + 4 c)), sw = ((g & 3) << 3) | (g & 4)
-    // transposed:     index = (8 ks + t + 4 c) * 64 + ((g | t << 3) ^ ((16 mt + 8 h) ^ 4 c))
+    // non-transposed: (a0, a2) of row n = 16 mt + g + 8 h are the adjacent stored columns 8 ks + 2 t, + 1 (kperm):
+    //                 index = n * 64 + (((2 t) ^ sw) ^ 8 ks), sw = ((g & 3) << 3) | (g & 4)
+    // transposed:     A[m][k] = W[k][m], stored at k * 64 + (kperm(m) ^ swz(k)) with k = 8 ks + t + 4 c, m = 16 mt + g + 8 h:
+    //                 index = (8 ks + t + 4 c) * 64 + ((pg | t << 3) ^ ((16 mt + 8 h) ^ 4 c)), pg = 2 (g & 3) + (g >> 2)
     const int base = TRANS ? t * 64 : g * 64;
-    const int x = TRANS ? (g | (t << 3)) : (t | ((g & 3) << 3) | (g & 4));
+    const int x = TRANS ? ((2 * (g & 3) + (g >> 2)) | (t << 3)) : ((2 * t) ^ (((g & 3) << 3) | (g & 4)));
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
         uint32_t b[2][2];
@@ -728,11 +741,16 @@ __device__ __forceinline__ void gemm64_tf32(const float* __restrict__ W, const f
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
             uint32_t a[4];
+            if (TRANS) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int h = e & 1, c = e >> 1;   // a0: (g, t) a1: (g + 8, t) a2: (g, t + 4) a3: (g + 8, t + 4)
-                a[e] = TRANS ? Wu[base + (8 * ks + 4 * c) * 64 + (x ^ ((16 * mt + 8 * h) ^ (4 * c)))]
-                             : Wu[base + (16 * mt + 8 * h) * 64 + (x ^ (8 * ks + 4 * c))];
+                for (int e = 0; e < 4; ++e) {
+                    const int h = e & 1, c = e >> 1;   // a0: (g, t) a1: (g + 8, t) a2: (g, t + 4) a3: (g + 8, t + 4)
+                    a[e] = Wu[base + (8 * ks + 4 * c) * 64 + (x ^ ((16 * mt + 8 * h) ^ (4 * c)))];
+                }
+            } else {
+                const uint2 lo = *reinterpret_cast<const uint2*>(Wu + base + (16 * mt) * 64 + (x ^ (8 * ks)));
+                const uint2 hi = *reinterpret_cast<const uint2*>(Wu + base + (16 * mt + 8) * 64 + (x ^ (8 * ks)));
+                a[0] = lo.x; a[2] = lo.y; a[1] = hi.x; a[3] = hi.y;
             }
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], a[0], a[1], a[2], a[3], b[nt][0], b[nt][1]);
@@ -750,26 +768,36 @@ __device__ __forceinline__ void outer_tf32(const float* __restrict__ Bn, const f
                                            float* __restrict__ xb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int mt = warp >> 1, kh = warp & 1;
-    const uint32_t* an = reinterpret_cast<const uint32_t*>(Bn) + (16 * mt + g) * kLdt + t;
-    const uint32_t* bk = reinterpret_cast<const uint32_t*>(Bk) + (32 * kh + g) * kLdt + t;
-    const uint32_t* ge = reinterpret_cast<const uint32_t*>(Geo) + g * kLdt + t;
+    // the K index (pair column) of a k-step is permuted — MMA slots (t, t + 4) hold pair columns (2 t, 2 t + 1) in both operands —
+    // so every fragment pair is one 64-bit shared load
+    const uint2* an = reinterpret_cast<const uint2*>(Bn + (16 * mt + g) * kLdt) + t;
+    const uint2* bk = reinterpret_cast<const uint2*>(Bk + (32 * kh + g) * kLdt) + t;
+    const uint2* ge = reinterpret_cast<const uint2*>(Geo + g * kLdt) + t;
     float acc[4][4], accx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float4* dst = reinterpret_cast<float4*>(tile + tid * 16);
-    // the running sums come from L2: start from them, so the round trip hides under the MMAs
+    // the running sums come from L2: the loads are issued first and consumed after the MMAs, so the round trip hides under them
+    float4 old[4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-        const float4 v = __ldcg(dst + nt);
-        acc[nt][0] = v.x; acc[nt][1] = v.y; acc[nt][2] = v.z; acc[nt][3] = v.w;
+        old[nt] = __ldcg(dst + nt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
     }
 #pragma unroll 4
     for (int ks = 0; ks < 16; ++ks) {
-        const uint32_t a0 = an[8 * ks], a1 = an[8 * kLdt + 8 * ks], a2 = an[8 * ks + 4], a3 = an[8 * kLdt + 8 * ks + 4];
+        const uint2 a02 = an[4 * ks], a13 = an[4 * kLdt + 4 * ks];     // rows g and g + 8 (8 rows = 4 kLdt uint2)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], a0, a1, a2, a3, bk[(8 * nt) * kLdt + 8 * ks], bk[(8 * nt) * kLdt + 8 * ks + 4]);
-        if (kh == 0) mma_tf32(accx, a0, a1, a2, a3, ge[8 * ks], ge[8 * ks + 4]);
+        for (int nt = 0; nt < 4; ++nt) {
+            const uint2 bb = bk[(4 * nt) * kLdt + 4 * ks];               // row + 8 nt
+            mma_tf32(acc[nt], a02.x, a13.x, a02.y, a13.y, bb.x, bb.y);
+        }
+        if (kh == 0) {
+            const uint2 gg = ge[4 * ks];
+            mma_tf32(accx, a02.x, a13.x, a02.y, a13.y, gg.x, gg.y);
+        }
     }
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) dst[nt] = make_float4(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]);
+    for (int nt = 0; nt < 4; ++nt) dst[nt] = make_float4(old[nt].x + acc[nt][0], old[nt].y + acc[nt][1], old[nt].z + acc[nt][2], old[nt].w + acc[nt][3]);
     if (kh == 0) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -923,11 +951,17 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
             }
     };
 
+    int* sPl = reinterpret_cast<int*>(S + M.Pl);           // [0]: count, [4 + slot]: column | j << 8 | relative position << 16
     if (owner) {
         sPI[p] = i;
         sGeo[GEO_ONE * kLdt + p] = 1.0f;
         sGeo[GEO_ZERO * kLdt + p] = 0.0f;
     }
+    if (tid == 0) sPl[0] = 0;      // (every reader of the previous pass's list is behind that pass's last barrier)
+    // called behind the pass's first barrier; the list is read behind a later one
+    auto list_peptide_columns = [&]() {
+        if (owner && act && pep) sPl[4 + atomicAdd(sPl, 1)] = p | (j << 8) | ((kN - 1 + i - j) << 16);
+    };
     if (HEADS) {
         const float* rg = S + M.RowG + i * 16;
         const float lse = rg[15], c_i = rg[14];
@@ -960,6 +994,7 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
             }
         }
         __syncthreads();
+        list_peptide_columns();
         // ---- message = W2 m1 + b2 -> BufA ----
         zero_acc(acc);
         gemm64_tf32<false>(W2s, bufB, acc);
@@ -1238,6 +1273,7 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
         for (int k = 0; k < 32; ++k) bufA[(n0 + k) * kLdt + p] = tf32r(m1h[k]);
     }
     __syncthreads();
+    if (!HEADS) list_peptide_columns();
     if (HEADS && IN_GRADS) {
         for (int idx = tid; idx < L * 7; idx += kBwdThreads) {
             const int rl = idx / 7, c = idx - rl * 7;
@@ -1280,16 +1316,16 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
             }
         }
     __syncthreads();
-    if (act && pep) {
-        float* dj = S + M.dAjPep + j * kLdN + n0;
-        float* de = S + M.dWe + (kN - 1 + i - j) * kLdN + n0;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const float v = bufB[(n0 + k) * kLdt + p];
-            atomicAdd(dj + k, v);
-            atomicAdd(de + k, v);
+    {   // peptide neighbours: dA_j[j] and dW_e[rel] get the column; the few such columns are spread over all threads
+        const int n_pl = sPl[0];
+        for (int idx = tid; idx < n_pl * kHid; idx += kBwdThreads) {
+            const int e = sPl[4 + (idx >> 6)], k = idx & 63;
+            const float v = bufB[k * kLdt + (e & 255)];
+            atomicAdd(S + M.dAjPep + ((e >> 8) & 255) * kLdN + k, v);
+            atomicAdd(S + M.dWe + (e >> 16) * kLdN + k, v);
         }
-    } else if (act && !HEADS && j >= kN) {
+    }
+    if (act && !HEADS && j >= kN) {
         // masked pocket slot with non-zero features (rare): straight to the A_j^T gradient scratch
         for (int k = 0; k < 32; ++k) atomicAdd(dajt + (n0 + k) * Kpad + j, bufB[(n0 + k) * kLdt + p]);
     }
@@ -1541,6 +1577,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
             float* dW1 = direct + (param_offset(LAYER, MSG0_W) - base);
             for (int idx = tid; idx < kHid * ld1; idx += kBwdThreads) {
                 int k = idx / ld1, c = idx - k * ld1;
+                const float old = __ldcg(dW1 + idx);     // the L2 round trip of the running sum hides under the products below
                 float acc = 0.0f;
                 if (c < H) {
                     for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dAi + i * kLdN + k], S[M.f.H + i * kLdN + c], acc);
@@ -1554,7 +1591,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
                 } else {
                     acc = S[M.dWe + (c - 2 * H) * kLdN + k];
                 }
-                dW1[idx] += acc;
+                dW1[idx] = old + acc;
             }
             for (int k = tid; k < kHid; k += kBwdThreads) {
                 float acc = 0.0f, acct = 0.0f;
@@ -1600,21 +1637,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
 
     // ---------------- fold the tile-owner partials into the parameter layout of this CTA's `direct` region ----------------
     __syncthreads();
-    for (int idx = tid; idx < kTileFloats; idx += kBwdThreads) {
-        int T = idx >> 12, r = idx & 4095;
-        int t = r >> 4, e = r & 15;
-        int k = (t & 15) + 16 * (e >> 2), n = (t >> 4) + 16 * (e & 3);
-        if (TC) tc_tile_coord(t, e, n, k);
-        int off, ld;
-        switch (T) {
-            case T_W2: off = param_offset(LAYER, MSG2_W); ld = 64; break;
-            case T_ATT: off = param_offset(LAYER, ATT0_W); ld = 66; break;
-            case T_ROT: off = param_offset(LAYER, ROT0_W); ld = 68; break;
-            case T_TOR: off = param_offset(LAYER, TOR0_W); ld = 78; break;
-            default: off = param_offset(LAYER, TRN0_W); ld = 64; break;
+    // (these first-layer weight columns of `direct` are written only here, and `direct` starts at zero: plain stores; the 16 L2
+    // loads of a thread per matrix are all in flight together)
+    auto fold = [&](int T, int off, int ld) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(tiles + T * 4096 + tid + u * kBwdThreads);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int r = tid + u * kBwdThreads;
+            const int t = r >> 4, e = r & 15;
+            int k = (t & 15) + 16 * (e >> 2), n = (t >> 4) + 16 * (e & 3);
+            if (TC) tc_tile_coord(t, e, n, k);
+            direct[(off - base) + n * ld + k] = v[u];
         }
-        direct[(off - base) + n * ld + k] += tiles[idx];
-    }
+    };
+    fold(T_W2, param_offset(LAYER, MSG2_W), 64);
+    fold(T_ATT, param_offset(LAYER, ATT0_W), 66);
+    fold(T_ROT, param_offset(LAYER, ROT0_W), 68);
+    fold(T_TOR, param_offset(LAYER, TOR0_W), 78);
+    fold(T_TRN, param_offset(LAYER, TRN0_W), 64);
 }
 
 // grad[p] += sum over CTAs of direct[cta][p]
