@@ -1015,210 +1015,139 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
         float dm[4][2][4];                         // dL / d message, fragment layout (row = feature, column = pair)
         zero_acc(dm);
 
-        // ================= rotation head (model.py:283-296) =================
-        {
+        // ================= the four heads: one runtime loop (rotation, torsion, translation, attention last — its gradient
+        // needs dL/dw from the other three), so the GEMM / outer-product code exists once per kernel and stays in the
+        // instruction cache; the per-head pieces are the epilogue of the hidden layer and the per-pair geometry =================
+        Quat ddg{0.0f, 0.0f, 0.0f, 0.0f}, u{1.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+            const int head = (it + 1) & 3;                         // HD_ROT, HD_TOR, HD_TRN, HD_ATT
+            int C, w3o, dwo_w, dwo_b, xw_off = -1, ldw = 0, e0 = 0, ne = 0, xb_off = -1;
+            if (head == HD_ROT)      { C = 4; w3o = kW3Rot; dwo_w = param_offset(LAYER, ROT2_W); dwo_b = param_offset(LAYER, ROT2_B);
+                                       xw_off = param_offset(LAYER, ROT0_W) + 64; ldw = 68; e0 = GEO_LQ; ne = 4; xb_off = param_offset(LAYER, ROT0_B); }
+            else if (head == HD_TOR) { C = PMHC_NTORS; w3o = kW3Tor; dwo_w = param_offset(LAYER, TOR2_W); dwo_b = param_offset(LAYER, TOR2_B); }
+            else if (head == HD_TRN) { C = 1; w3o = kW3Trn; dwo_w = param_offset(LAYER, TRN2_W); dwo_b = param_offset(LAYER, TRN2_B);
+                                       xb_off = param_offset(LAYER, TRN0_B); }
+            else                     { C = 1; w3o = kW3Att; dwo_w = param_offset(LAYER, ATT2_W); dwo_b = param_offset(LAYER, ATT2_B);
+                                       xw_off = param_offset(LAYER, ATT0_W) + 64; ldw = 66; e0 = GEO_D2; ne = 2; xb_off = param_offset(LAYER, ATT0_B); }
+            const float* Wh = Whs + head * 4096;
+
+            // ---- hidden layer: relu(W_h m + per-head extras) -> BufB (own columns) ----
             zero_acc(acc);
-            gemm64_tf32<false>(Whs + HD_ROT * 4096, bufA, acc);
+            gemm64_tf32<false>(Wh, bufA, acc);
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int n = 16 * mt + fg + 8 * h;
-                    const float4 wq = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n);
-                    const float bias = S[M.f.PkMisc + 4 * n + 2];
+                    // per-unit extras: rotation W_q (4) + bias; attention w_d, w_q, bias; translation bias; torsion T_t[i] per column
+                    float4 wx = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    float bias = 0.0f;
+                    if (head == HD_ROT) { wx = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n); bias = S[M.f.PkMisc + 4 * n + 2]; }
+                    else if (head == HD_ATT) { wx = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n); }
+                    else if (head == HD_TRN) { bias = S[M.f.PkMisc + 4 * n + 0]; }
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt) {
                         const int pc = 16 * warp + 8 * nt + 2 * ft;
                         float o[2];
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
-                            const float* ge = sGeo + pc + c;
-                            const float s = acc[mt][nt][2 * h + c] + bias + wq.x * ge[0] + wq.y * ge[kLdt] + wq.z * ge[2 * kLdt] + wq.w * ge[3 * kLdt];
+                            const float av = acc[mt][nt][2 * h + c];
+                            float s;
+                            if (head == HD_ROT) {
+                                const float* ge = sGeo + pc + c;
+                                s = av + bias + wx.x * ge[0] + wx.y * ge[kLdt] + wx.z * ge[2 * kLdt] + wx.w * ge[3 * kLdt];
+                            } else if (head == HD_ATT) {
+                                s = (wx.z + av) + fmaf(wx.y, sGeo[GEO_QDF * kLdt + pc + c], wx.x * sGeo[GEO_D2F * kLdt + pc + c]);
+                            } else if (head == HD_TOR) {
+                                s = av + S[M.f.Tt + sPI[pc + c] * kHid + n];
+                            } else {
+                                s = av + bias;
+                            }
                             o[c] = tf32r(fmaxf(s, 0.0f));
                         }
                         *reinterpret_cast<float2*>(bufB + n * kLdt + pc) = make_float2(o[0], o[1]);
                     }
                 }
-            __syncwarp();
-            rows8_tf32(W3s + kW3Rot, 4, bufB, o2);
-            store_rows(sDout, 4);
-            __syncthreads();
-            Quat ddg{0.0f, 0.0f, 0.0f, 0.0f}, u{1.0f, 0.0f, 0.0f, 0.0f};
-            if (owner) {
-                const Quat dl{sigmoidf(sDout[0 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 0]), sigmoidf(sDout[1 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 1]),
-                              sigmoidf(sDout[2 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 2]), sigmoidf(sDout[3 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 3])};
-                u = qmul(dl, qinvj);
-                const Quat dg = qmul(qj, u);
-                const Quat dG{rg[0], rg[1], rg[2], rg[3]};
-                dLdw += qdot(dG, dg);
-                ddg = qscale(dG, w);
-                const Quat du = qmul_grad_b(qj, ddg);         // dg = qj * u
-                const Quat ddl = qmul_grad_a(du, qinvj);      // u = dl * qinvj
-                sDout[0 * kLdt + p] = tf32r(ddl.w * dl.w * (1.0f - dl.w));
-                sDout[1 * kLdt + p] = tf32r(ddl.x * dl.x * (1.0f - dl.x));
-                sDout[2 * kLdt + p] = tf32r(ddl.y * dl.y * (1.0f - dl.y));
-                sDout[3 * kLdt + p] = tf32r(ddl.z * dl.z * (1.0f - dl.z));
-                if (IN_GRADS) {
-                    dqj_part = qmul_grad_a(ddg, u);            // dg = qj * u
-                    dqinv_part = qmul_grad_b(dl, du);          // u = dl * qinvj
-                }
+            if (head != HD_ATT) {
+                // second layer on the warp's own columns (the attention logit was saved by the forward)
+                __syncwarp();
+                rows8_tf32(W3s + w3o, C, bufB, o2);
+                store_rows(sDout, C);
             }
             __syncthreads();
-            dwo_tf32(sDout, 4, bufB, direct + (param_offset(LAYER, ROT2_W) - base), direct + (param_offset(LAYER, ROT2_B) - base));
-            __syncthreads();
-            cols8_tf32(W3s + kW3Rot, 4, sDout, acc);
-            mask_store_dpre();
-            __syncwarp();
-            gemm64_tf32<true>(Whs + HD_ROT * 4096, bufB, dm);
-            if (IN_GRADS) {
-                rows8_tf32(Wxs + kWxRot, 4, bufB, o2);     // dL / d local quaternion
-                store_rows(sDx, 4);
-            }
-            __syncthreads();
-            outer_tf32(bufB, bufA, sGeo, tiles + T_ROT * 4096, direct + (param_offset(LAYER, ROT0_W) - base) + 64, 68, GEO_LQ, 4,
-                       direct + (param_offset(LAYER, ROT0_B) - base));
-            __syncthreads();
-        }
 
-        // ================= torsion head (model.py:257-263) =================
-        {
-            zero_acc(acc);
-            gemm64_tf32<false>(Whs + HD_TOR * 4096, bufA, acc);
+            // ---- per pair: head outputs -> geometry -> dL / d outputs (one thread per pair) ----
+            if (owner) {
+                if (head == HD_ROT) {
+                    const Quat dl{sigmoidf(sDout[0 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 0]), sigmoidf(sDout[1 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 1]),
+                                  sigmoidf(sDout[2 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 2]), sigmoidf(sDout[3 * kLdt + p] + S[M.f.Scal + SC_ROT2B + 3])};
+                    u = qmul(dl, qinvj);
+                    const Quat dg = qmul(qj, u);
+                    const Quat dG{rg[0], rg[1], rg[2], rg[3]};
+                    dLdw += qdot(dG, dg);
+                    ddg = qscale(dG, w);
+                    const Quat du = qmul_grad_b(qj, ddg);         // dg = qj * u
+                    const Quat ddl = qmul_grad_a(du, qinvj);      // u = dl * qinvj
+                    sDout[0 * kLdt + p] = tf32r(ddl.w * dl.w * (1.0f - dl.w));
+                    sDout[1 * kLdt + p] = tf32r(ddl.x * dl.x * (1.0f - dl.x));
+                    sDout[2 * kLdt + p] = tf32r(ddl.y * dl.y * (1.0f - dl.y));
+                    sDout[3 * kLdt + p] = tf32r(ddl.z * dl.z * (1.0f - dl.z));
+                    if (IN_GRADS) {
+                        dqj_part = qmul_grad_a(ddg, u);            // dg = qj * u
+                        dqinv_part = qmul_grad_b(dl, du);          // u = dl * qinvj
+                    }
+                } else if (head == HD_TOR) {
+                    if (IN_GRADS && act) {
+                        // rotation head, second part: dL / d local quaternion arrived (sDx rows 0..3)
+                        const Quat dlqq{sDx[0 * kLdt + p], sDx[1 * kLdt + p], sDx[2 * kLdt + p], sDx[3 * kLdt + p]};
+                        const Quat dqinv = qadd(qmul_grad_a(dlqq, v), dqinv_part);   // lq = qinvj * v
+                        const Quat dv = qmul_grad_b(qinvj, dlqq);
+                        const Quat dqi = qmul_grad_a(dv, qj);                         // v = qi * qj
+                        Quat dqj = qadd(qmul_grad_b(qi, dv), dqj_part);
+                        dqj = qadd(dqj, qinv_grad(qj, dqinv));
+                        gi[0] += dqi.w; gi[1] += dqi.x; gi[2] += dqi.y; gi[3] += dqi.z;
+                        if (pep) atomic_add_quat(S + M.dQ + j * 4, dqj);
+                    }
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int pc = 16 * warp + 8 * nt + 2 * ft + c;
-                    const float* tt = S + M.f.Tt + sPI[pc] * kHid;
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int n = 16 * mt + fg + 8 * h;
-                            bufB[n * kLdt + pc] = tf32r(fmaxf(acc[mt][nt][2 * h + c] + tt[n], 0.0f));
+                    for (int c = 0; c < PMHC_NTORS; ++c) {
+                        const float da = sDout[c * kLdt + p] + S[M.f.Scal + SC_TOR2B + c];
+                        dLdw = fmaf(rg[4 + c], da, dLdw);
+                        sDout[c * kLdt + p] = tf32r(w * rg[4 + c]);
+                    }
+                } else if (head == HD_TRN) {
+                    const float sc = sDout[p] + S[M.f.Scal + SC_TRN2B];
+                    const float dXr = rg[11] * rx + rg[12] * ry + rg[13] * rz;
+                    dLdw = fmaf(sc, dXr, dLdw);
+                    sDout[p] = tf32r(w * dXr);
+                    if (IN_GRADS && act) {
+                        const float f = w * sc;
+                        gi[4] += f * rg[11]; gi[5] += f * rg[12]; gi[6] += f * rg[13];
+                        if (pep) {
+                            atomicAdd(S + M.dX + j * 3 + 0, -f * rg[11]); atomicAdd(S + M.dX + j * 3 + 1, -f * rg[12]); atomicAdd(S + M.dX + j * 3 + 2, -f * rg[13]);
                         }
-                }
-            __syncwarp();
-            rows8_tf32(W3s + kW3Tor, PMHC_NTORS, bufB, o2);
-            store_rows(sDout, PMHC_NTORS);
-            __syncthreads();
-            if (owner) {
-                if (IN_GRADS && act) {
-                    // rotation head, second part: dL / d local quaternion arrived (sDx rows 0..3)
-                    const Quat dlqq{sDx[0 * kLdt + p], sDx[1 * kLdt + p], sDx[2 * kLdt + p], sDx[3 * kLdt + p]};
-                    const Quat dqinv = qadd(qmul_grad_a(dlqq, v), dqinv_part);   // lq = qinvj * v
-                    const Quat dv = qmul_grad_b(qinvj, dlqq);
-                    const Quat dqi = qmul_grad_a(dv, qj);                         // v = qi * qj
-                    Quat dqj = qadd(qmul_grad_b(qi, dv), dqj_part);
-                    dqj = qadd(dqj, qinv_grad(qj, dqinv));
-                    gi[0] += dqi.w; gi[1] += dqi.x; gi[2] += dqi.y; gi[3] += dqi.z;
-                    if (pep) atomic_add_quat(S + M.dQ + j * 4, dqj);
-                }
-#pragma unroll
-                for (int c = 0; c < PMHC_NTORS; ++c) {
-                    const float da = sDout[c * kLdt + p] + S[M.f.Scal + SC_TOR2B + c];
-                    dLdw = fmaf(rg[4 + c], da, dLdw);
-                    sDout[c * kLdt + p] = tf32r(w * rg[4 + c]);
+                    }
+                } else {
+                    // softmax backward with the saved row statistics (see pair_pass for the saturated-row rule)
+                    sDout[p] = tf32r((w == 1.0f) ? 0.0f : w * (dLdw - c_i));
                 }
             }
             __syncthreads();
-            dwo_tf32(sDout, PMHC_NTORS, bufB, direct + (param_offset(LAYER, TOR2_W) - base), direct + (param_offset(LAYER, TOR2_B) - base));
+            dwo_tf32(sDout, C, bufB, direct + (dwo_w - base), direct + (dwo_b - base));
             __syncthreads();
-            cols8_tf32(W3s + kW3Tor, PMHC_NTORS, sDout, acc);
+            cols8_tf32(W3s + w3o, C, sDout, acc);
             mask_store_dpre();
             __syncwarp();
-            gemm64_tf32<true>(Whs + HD_TOR * 4096, bufB, dm);
-            __syncthreads();
-            outer_tf32(bufB, bufA, sGeo, tiles + T_TOR * 4096, nullptr, 0, 0, 0, nullptr);
-            accumulate_rows<kLdt>(bufB, S + M.dTt, kHid, I, L, Wr, pass_base, npass);
-            __syncthreads();
-        }
-
-        // ================= translation head (model.py:325-331) =================
-        {
-            zero_acc(acc);
-            gemm64_tf32<false>(Whs + HD_TRN * 4096, bufA, acc);
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int n = 16 * mt + fg + 8 * h;
-                    const float bias = S[M.f.PkMisc + 4 * n + 0];
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
-                        const int pc = 16 * warp + 8 * nt + 2 * ft;
-                        *reinterpret_cast<float2*>(bufB + n * kLdt + pc) =
-                            make_float2(tf32r(fmaxf(acc[mt][nt][2 * h] + bias, 0.0f)), tf32r(fmaxf(acc[mt][nt][2 * h + 1] + bias, 0.0f)));
-                    }
-                }
-            __syncwarp();
-            rows8_tf32(W3s + kW3Trn, 1, bufB, o2);
-            store_rows(sDout, 1);
-            __syncthreads();
-            if (owner) {
-                const float sc = sDout[p] + S[M.f.Scal + SC_TRN2B];
-                const float dXr = rg[11] * rx + rg[12] * ry + rg[13] * rz;
-                dLdw = fmaf(sc, dXr, dLdw);
-                sDout[p] = tf32r(w * dXr);
-                if (IN_GRADS && act) {
-                    const float f = w * sc;
-                    gi[4] += f * rg[11]; gi[5] += f * rg[12]; gi[6] += f * rg[13];
-                    if (pep) {
-                        atomicAdd(S + M.dX + j * 3 + 0, -f * rg[11]); atomicAdd(S + M.dX + j * 3 + 1, -f * rg[12]); atomicAdd(S + M.dX + j * 3 + 2, -f * rg[13]);
-                    }
-                }
+            gemm64_tf32<true>(Wh, bufB, dm);
+            if (IN_GRADS && (head == HD_ROT || head == HD_ATT)) {
+                // dL / d local quaternion (rotation: sDx rows 0..3) or dL / d (-d2, qdot2) (attention: rows 4, 5)
+                rows8_tf32(Wxs + (head == HD_ROT ? kWxRot : kWxAtt), head == HD_ROT ? 4 : 2, bufB, o2);
+                store_rows(sDx + (head == HD_ROT ? 0 : 4 * kLdt), head == HD_ROT ? 4 : 2);
             }
             __syncthreads();
-            dwo_tf32(sDout, 1, bufB, direct + (param_offset(LAYER, TRN2_W) - base), direct + (param_offset(LAYER, TRN2_B) - base));
-            __syncthreads();
-            cols8_tf32(W3s + kW3Trn, 1, sDout, acc);
-            mask_store_dpre();
-            __syncwarp();
-            gemm64_tf32<true>(Whs + HD_TRN * 4096, bufB, dm);
-            __syncthreads();
-            outer_tf32(bufB, bufA, sGeo, tiles + T_TRN * 4096, nullptr, 0, 0, 0, direct + (param_offset(LAYER, TRN0_B) - base));
-            __syncthreads();
-        }
-
-        // ================= attention head (model.py:238-243) =================
-        {
-            zero_acc(acc);
-            gemm64_tf32<false>(Whs + HD_ATT * 4096, bufA, acc);
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int n = 16 * mt + fg + 8 * h;
-                    const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
-                        const int pc = 16 * warp + 8 * nt + 2 * ft;
-                        float o[2];
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const float s = (pk.z + acc[mt][nt][2 * h + c]) + fmaf(pk.y, sGeo[GEO_QDF * kLdt + pc + c], pk.x * sGeo[GEO_D2F * kLdt + pc + c]);
-                            o[c] = tf32r(fmaxf(s, 0.0f));
-                        }
-                        *reinterpret_cast<float2*>(bufB + n * kLdt + pc) = make_float2(o[0], o[1]);
-                    }
-                }
-            // softmax backward with the saved row statistics (see pair_pass for the saturated-row rule); the logit itself was
-            // saved by the forward, so the head's second layer is not recomputed
-            if (owner) sDout[p] = tf32r((w == 1.0f) ? 0.0f : w * (dLdw - c_i));
-            __syncthreads();
-            dwo_tf32(sDout, 1, bufB, direct + (param_offset(LAYER, ATT2_W) - base), direct + (param_offset(LAYER, ATT2_B) - base));
-            __syncthreads();
-            cols8_tf32(W3s + kW3Att, 1, sDout, acc);
-            mask_store_dpre();
-            __syncwarp();
-            gemm64_tf32<true>(Whs + HD_ATT * 4096, bufB, dm);
-            if (IN_GRADS) {
-                rows8_tf32(Wxs + kWxAtt, 2, bufB, o2);     // dL / d (-d2), dL / d qdot2
-                store_rows(sDx + 4 * kLdt, 2);
-            }
-            __syncthreads();
-            outer_tf32(bufB, bufA, sGeo, tiles + T_ATT * 4096, direct + (param_offset(LAYER, ATT0_W) - base) + 64, 66, GEO_D2, 2,
-                       direct + (param_offset(LAYER, ATT0_B) - base));
+            outer_tf32(bufB, bufA, sGeo, tiles + (head + 1) * 4096, xw_off >= 0 ? direct + (xw_off - base) : nullptr, ldw, e0, ne,
+                       xb_off >= 0 ? direct + (xb_off - base) : nullptr);
+            if (head == HD_TOR) accumulate_rows<kLdt>(bufB, S + M.dTt, kHid, I, L, Wr, pass_base, npass);
             __syncthreads();
         }
         if (IN_GRADS && owner) {
