@@ -716,6 +716,19 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// L2 loads the compiler must not sink to their use: issued where written (volatile), so their round trip overlaps the
+// barrier / MMA work in between
+__device__ __forceinline__ float4 ldcg_early4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldcg_early(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // acc[mt][nt] += A (64 x 64) * X (64 x this warp's 16 pair columns).  A[m][k] = W[m][k] (TRANS = false) or W[k][m] (true),
 // W swizzled (wswz); X a [64][kLdt] column tile.  Fragment (mt, nt) element e: row 16 mt + g + 8 (e >> 1),
 // pair column 16 warp + 8 nt + 2 t + (e & 1), g = lane >> 2, t = lane & 3.
@@ -764,8 +777,8 @@ __device__ __forceinline__ void gemm64_tf32(const float* __restrict__ W, const f
 // Warp w owns rows n in [16 (w >> 1), +16) and columns k in [32 (w & 1), +32); its 16 sums per thread sit contiguously in
 // the tile-owner layout (tile + 16 tid); the even warps also own the extras of their rows.
 __device__ __forceinline__ void outer_tf32(const float* __restrict__ Bn, const float* __restrict__ Bk, const float* __restrict__ Geo,
-                                           float* __restrict__ tile, float* __restrict__ xw, int ldw, int e0, int ne,
-                                           float* __restrict__ xb) {
+                                           float* __restrict__ tile, const float4 (&old)[4], float* __restrict__ xw, int ldw,
+                                           int e0, int ne, float* __restrict__ xb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int mt = warp >> 1, kh = warp & 1;
     // the K index (pair column) of a k-step is permuted — MMA slots (t, t + 4) hold pair columns (2 t, 2 t + 1) in both operands —
@@ -775,14 +788,11 @@ __device__ __forceinline__ void outer_tf32(const float* __restrict__ Bn, const f
     const uint2* ge = reinterpret_cast<const uint2*>(Geo + g * kLdt) + t;
     float acc[4][4], accx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float4* dst = reinterpret_cast<float4*>(tile + tid * 16);
-    // the running sums come from L2: the loads are issued first and consumed after the MMAs, so the round trip hides under them
-    float4 old[4];
+    // the running sums come from L2: `old` was loaded by the caller ahead of the barrier before this call (outer_prefetch)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        old[nt] = __ldcg(dst + nt);
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
-    }
 #pragma unroll 4
     for (int ks = 0; ks < 16; ++ks) {
         const uint2 a02 = an[4 * ks], a13 = an[4 * kLdt + 4 * ks];     // rows g and g + 8 (8 rows = 4 kLdt uint2)
@@ -806,6 +816,10 @@ __device__ __forceinline__ void outer_tf32(const float* __restrict__ Bn, const f
             if (xb != nullptr && col == 6) xb[n] += accx[e];
         }
     }
+}
+__device__ __forceinline__ void outer_prefetch(const float* __restrict__ tile, float4 (&old)[4]) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) old[nt] = ldcg_early4(tile + threadIdx.x * 16 + 4 * nt);
 }
 // (n, k) of element e of thread tid in the tensor-core tile-owner layout
 __device__ __forceinline__ void tc_tile_coord(int tid, int e, int& n, int& k) {
@@ -875,14 +889,13 @@ __device__ __forceinline__ void cols8_tf32(const float* __restrict__ Wimg, int C
 // second-layer weight gradients: dwo[c * 64 + n] += sum_p D[c][p] Hid[n][p], dbo[c] += sum_p D[c][p] over the 128 pair columns;
 // warp w owns the hidden units n in [8 w, 8 w + 8), warp 0 also the bias (a B operand of ones)
 __device__ __forceinline__ void dwo_tf32(const float* __restrict__ D, int C, const float* __restrict__ Hid,
-                                         float* __restrict__ dwo, float* __restrict__ dbo) {
+                                         float* __restrict__ dwo, float* __restrict__ dbo, float old0, float old1) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const bool rowok = g < C;
     const uint32_t* du = reinterpret_cast<const uint32_t*>(D) + g * kLdt + t;
     const uint32_t* hu = reinterpret_cast<const uint32_t*>(Hid) + (8 * warp + g) * kLdt + t;
     float* dst = dwo + g * 64 + 8 * warp + 2 * t;
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, accb[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (rowok) { acc[0] = __ldcg(dst); acc[1] = __ldcg(dst + 1); }
     const uint32_t one = __float_as_uint(1.0f);
 #pragma unroll 4
     for (int ks = 0; ks < 16; ++ks) {
@@ -890,7 +903,7 @@ __device__ __forceinline__ void dwo_tf32(const float* __restrict__ D, int C, con
         mma_tf32(acc, a0, 0u, a2, 0u, hu[8 * ks], hu[8 * ks + 4]);
         if (warp == 0) mma_tf32(accb, a0, 0u, a2, 0u, one, one);
     }
-    if (rowok) { dst[0] = acc[0]; dst[1] = acc[1]; }
+    if (rowok) { dst[0] = old0 + acc[0]; dst[1] = old1 + acc[1]; }
     if (warp == 0 && rowok && t == 0) dbo[g] += accb[0];
 }
 
@@ -1031,6 +1044,13 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
             else                     { C = 1; w3o = kW3Att; dwo_w = param_offset(LAYER, ATT2_W); dwo_b = param_offset(LAYER, ATT2_B);
                                        xw_off = param_offset(LAYER, ATT0_W) + 64; ldw = 66; e0 = GEO_D2; ne = 2; xb_off = param_offset(LAYER, ATT0_B); }
             const float* Wh = Whs + head * 4096;
+            // this thread's two running second-layer weight-gradient sums (L2): loaded now, used four phases later
+            float dwo_old0 = 0.0f, dwo_old1 = 0.0f;
+            if (fg < C) {
+                const float* q = direct + (dwo_w - base) + fg * 64 + 8 * warp + 2 * ft;
+                dwo_old0 = ldcg_early(q);
+                dwo_old1 = ldcg_early(q + 1);
+            }
 
             // ---- hidden layer: relu(W_h m + per-head extras) -> BufB (own columns) ----
             zero_acc(acc);
@@ -1133,7 +1153,7 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
                 }
             }
             __syncthreads();
-            dwo_tf32(sDout, C, bufB, direct + (dwo_w - base), direct + (dwo_b - base));
+            dwo_tf32(sDout, C, bufB, direct + (dwo_w - base), direct + (dwo_b - base), dwo_old0, dwo_old1);
             __syncthreads();
             cols8_tf32(W3s + w3o, C, sDout, acc);
             mask_store_dpre();
@@ -1144,8 +1164,10 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
                 rows8_tf32(Wxs + (head == HD_ROT ? kWxRot : kWxAtt), head == HD_ROT ? 4 : 2, bufB, o2);
                 store_rows(sDx + (head == HD_ROT ? 0 : 4 * kLdt), head == HD_ROT ? 4 : 2);
             }
+            float4 told[4];
+            outer_prefetch(tiles + (head + 1) * 4096, told);
             __syncthreads();
-            outer_tf32(bufB, bufA, sGeo, tiles + (head + 1) * 4096, xw_off >= 0 ? direct + (xw_off - base) : nullptr, ldw, e0, ne,
+            outer_tf32(bufB, bufA, sGeo, tiles + (head + 1) * 4096, told, xw_off >= 0 ? direct + (xw_off - base) : nullptr, ldw, e0, ne,
                        xb_off >= 0 ? direct + (xb_off - base) : nullptr);
             if (head == HD_TOR) accumulate_rows<kLdt>(bufB, S + M.dTt, kHid, I, L, Wr, pass_base, npass);
             __syncthreads();
@@ -1201,6 +1223,8 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
 #pragma unroll
         for (int k = 0; k < 32; ++k) bufA[(n0 + k) * kLdt + p] = tf32r(m1h[k]);
     }
+    float4 told[4];
+    outer_prefetch(tiles + T_W2 * 4096, told);
     __syncthreads();
     if (!HEADS) list_peptide_columns();
     if (HEADS && IN_GRADS) {
@@ -1231,7 +1255,7 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
                 if (!(m1v.y > 0.0f)) acc[mt][nt][2 * h + 1] = 0.0f;
             }
         }
-    outer_tf32(bufB, bufA, sGeo, tiles + T_W2 * 4096, nullptr, 0, 0, 0, direct + (param_offset(LAYER, MSG2_B) - base));
+    outer_tf32(bufB, bufA, sGeo, tiles + T_W2 * 4096, told, nullptr, 0, 0, 0, direct + (param_offset(LAYER, MSG2_B) - base));
     __syncthreads();
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
