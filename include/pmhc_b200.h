@@ -159,7 +159,7 @@ int pmhc_sample(const float *params, const PmhcBatch *batch_host, float *frames,
 /* Adam update over the flat buffers — replaces torch.optim.Adam.step (optimizer.py:33, 224), default
  * betas/eps unless given; `skip` ranges (gnn2.feature_mlp) are left untouched like grad=None params. */
 int pmhc_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n,
-                   float lr, float beta1, float beta2, float eps, int step, void *stream);
+                   double lr, double beta1, double beta2, double eps, int step, void *stream);
 
 /* Loader side — replaces the per-entry Rigid.from_tensor_4x4(...).to_tensor_7() of MhcpDataset.get_entry
  * (diffusion/data.py:107, :115; RU:1004-1034 + rot_to_quat RU:184-216): n homogeneous 4x4 matrices (row-major,

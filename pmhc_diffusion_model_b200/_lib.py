@@ -82,7 +82,7 @@ def load() -> ctypes.CDLL:
     lib.pmhc_sample.restype = c_int
     lib.pmhc_sample.argtypes = [vp, POINTER(PmhcBatch), vp, vp, c_int, c_double, c_double, u64, u64, vp, vp, vp, vp, c_size_t, vp, c_int]
     lib.pmhc_adam_step.restype = c_int
-    lib.pmhc_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, c_int, vp]
+    lib.pmhc_adam_step.argtypes = [vp, vp, vp, vp, i64, c_double, c_double, c_double, c_double, c_int, vp]
     lib.pmhc_launch_count.restype = i64
     lib.pmhc_launch_count.argtypes = []
     lib.pmhc_profile_enable.restype = None

@@ -269,13 +269,13 @@ __global__ void loss_kernel(const float* __restrict__ tf, const float* __restric
 
 // torch.optim.Adam single-tensor update (no amsgrad, no weight decay) over the flat buffers.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, int64_t n, float b1, float b2, float eps, float step_size,
-                            float bc2_sqrt) {
+                            float* __restrict__ v, int64_t n, float one_minus_b1, float b2, float one_minus_b2, float eps,
+                            float step_size, float bc2_sqrt) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float gi = g[i];
-    float mi = m[i] + (gi - m[i]) * (1.0f - b1);
-    float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+    float mi = m[i] + (gi - m[i]) * one_minus_b1;
+    float vi = v[i] * b2 + one_minus_b2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
     float denom = sqrtf(vi) / bc2_sqrt + eps;
@@ -374,13 +374,14 @@ extern "C" int pmhc_loss(const float* tf, const float* tt, const float* pf, cons
     return 0;
 }
 
-extern "C" int pmhc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
-                              float eps, int step, void* stream) {
+extern "C" int pmhc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2,
+                              double eps, int step, void* stream) {
     if (n <= 0) return 0;
     PMHC_REQUIRE(step >= 1, "pmhc_adam_step: step counts from 1");
-    double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
-    adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, b1, b2, eps, (float)(lr / bc1),
-                                                                   (float)sqrt(bc2));
+    // the scalars are formed in double and rounded once, as torch does with its Python-float hyperparameters
+    double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
+    adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2),
+                                                                   (float)eps, (float)(lr / bc1), (float)sqrt(bc2));
     PMHC_CHECK_LAUNCH("pmhc_adam_step");
     return 0;
 }

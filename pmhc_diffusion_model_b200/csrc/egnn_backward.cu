@@ -1424,8 +1424,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
                 float acc = 0.0f;
                 if (idx < kHid * kHid) {
                     int n2 = idx >> 6, n = idx & 63;
+                    const float old = __ldcg(direct + (param_offset(0, FEAT2_W) - base) + idx);   // L2 round trip under the products
                     for (int r = 0; r < L; ++r) acc = fmaf(dO[r * kLdN + n2], hid[r * kLdN + n], acc);
-                    direct[(param_offset(0, FEAT2_W) - base) + idx] += acc;
+                    direct[(param_offset(0, FEAT2_W) - base) + idx] = old + acc;
                 } else {
                     int n2 = idx - kHid * kHid;
                     for (int r = 0; r < L; ++r) acc += dO[r * kLdN + n2];
@@ -1438,12 +1439,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
                 float acc = 0.0f;
                 if (idx < kHid * ldf) {
                     int n = idx / ldf, c = idx - n * ldf;
+                    const float old = __ldcg(direct + (param_offset(0, FEAT0_W) - base) + idx);
                     for (int r = 0; r < L; ++r) {
                         int i = I[IN_ROWS + r];
                         float x = c < kH1 ? S[M.f.H + i * kLdN + c] : S[M.f.Msum + i * kHid + (c - kH1)];
                         acc = fmaf(dhid[r * kLdN + n], x, acc);
                     }
-                    direct[(param_offset(0, FEAT0_W) - base) + idx] += acc;
+                    direct[(param_offset(0, FEAT0_W) - base) + idx] = old + acc;
                 } else {
                     int n = idx - kHid * ldf;
                     for (int r = 0; r < L; ++r) acc += dhid[r * kLdN + n];

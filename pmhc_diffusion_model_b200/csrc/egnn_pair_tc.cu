@@ -994,10 +994,16 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair_tc_kernel(PairArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kOrderBins = kN * (kN - 1 + kMaxP) + 1;
 __global__ void __launch_bounds__(1024) order_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ pocket_mask, int B, int P,
-                                                     int* __restrict__ keys, int* __restrict__ order) {
+                                                     int n_engines, int* __restrict__ keys, int* __restrict__ order) {
     extern __shared__ int bins[];      // [kOrderBins] counts, then starting offsets (descending key)
     __shared__ int carry;
     const int tid = threadIdx.x;
+    if (B <= n_engines) {
+        // a single round: every complex has an engine to itself whatever the order (the usual training batch), and the
+        // serial scan below (30 us) would be a visible part of a training step
+        for (int b = tid; b < B; b += blockDim.x) order[b] = b;
+        return;
+    }
     for (int k = tid; k < kOrderBins; k += blockDim.x) bins[k] = 0;
     __syncthreads();
     for (int b = tid; b < B; b += blockDim.x) {
@@ -1421,7 +1427,7 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
         tc2::node_pre_kernel<<<B, 128, smem, stream>>>(params, bt->features, bt->pocket_features, bt->pocket_mask, P, w.cls_stride,
                                                        w.pk_cache, w.cls, w.aij1);
         PMHC_CHECK_LAUNCH("node_pre");
-        tc2::order_kernel<<<1, 1024, tc2::kOrderBins * sizeof(int), stream>>>(bt->mask, bt->pocket_mask, B, P, w.keys, w.order);
+        tc2::order_kernel<<<1, 1024, tc2::kOrderBins * sizeof(int), stream>>>(bt->mask, bt->pocket_mask, B, P, 2 * num_sms(), w.keys, w.order);
         PMHC_CHECK_LAUNCH("order");
     }
     tc2::PairArgs a{};

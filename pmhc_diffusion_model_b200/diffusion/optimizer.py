@@ -73,12 +73,96 @@ class _LossFn(torch.autograd.Function):
         return None, None, d_f * g0[:, None, None], d_t * g0[:, None, None, None], None, None
 
 
+
+class FlatAdam(torch.optim.Adam):
+    """`torch.optim.Adam` (what optimizer.py:33 builds) whose step over the model's flat parameter buffer is one fused kernel
+    (`pmhc_adam_step`, the same single-tensor update arithmetic) instead of torch's 21 multi-tensor launches.  It stays a
+    `torch.optim.Adam`: `param_groups`, `state` (per parameter `step`, `exp_avg`, `exp_avg_sq` — the moments are views into two
+    flat buffers), `state_dict()` / `load_state_dict()` and `zero_grad()` behave as before, and parameters whose `.grad` is None
+    (gnn2.feature_mlp) get no state and no update, as in torch."""
+
+    def __init__(self, model, lr: float):
+        super().__init__(model.parameters(), lr=lr)
+        self._model = model
+        self._m = self._v = None
+        self._generation = -1
+
+    def _link(self, flat: torch.Tensor) -> None:
+        """(Re)build the flat moment buffers for the model's current flat parameter buffer, keeping whatever state exists."""
+        m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+        off = 0
+        for p in self._model.parameters():
+            n = p.numel()
+            st = self.state.get(p)
+            if st:
+                m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                st["exp_avg"], st["exp_avg_sq"] = m[off:off + n].view(p.shape), v[off:off + n].view(p.shape)
+            off += n
+        self._m, self._v, self._generation = m, v, self._model._flat_generation
+
+    def load_state_dict(self, state_dict) -> None:
+        super().load_state_dict(state_dict)
+        self._generation = -1          # the loaded moments are fresh tensors: copied into the flat buffers at the next step
+
+    @torch.no_grad()
+    def step(self, closure=None, flat_grad: Optional[torch.Tensor] = None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        group = self.param_groups[0]
+        if (len(self.param_groups) != 1 or group["weight_decay"] != 0 or group["amsgrad"] or group["maximize"]
+                or group.get("capturable") or group.get("differentiable")):
+            raise RuntimeError("FlatAdam implements plain Adam (one group, no weight decay / amsgrad / maximize), as optimizer.py:33 uses it")
+        lib = _lib.load()
+        model = self._model
+        flat = model._flat_params()
+        if self._generation != model._flat_generation or self._m is None:
+            self._link(flat)
+        params = list(model.parameters())
+        if flat_grad is None:        # plain .step(): gather the .grad tensors (None -> that parameter is skipped)
+            flat_grad = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32) for p in params])
+        flat_grad = _lib.f32c(flat_grad)
+        # contiguous runs of parameters that carry a gradient; all of them share one step count, as in torch when they are
+        # always stepped together (a parameter that gets its first gradient later starts its own count: one run per count)
+        spans, steps, off = [], [], 0
+        for p in params:
+            n = p.numel()
+            if p.grad is not None:
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = self._m[off:off + n].view(p.shape)
+                    st["exp_avg_sq"] = self._v[off:off + n].view(p.shape)
+                spans.append((off, off + n))
+                steps.append(st["step"])
+            off += n
+        runs = []
+        if steps:
+            torch._foreach_add_(steps, 1.0)
+            for (lo, hi), k in zip(spans, torch.stack(steps).tolist()):
+                k = int(k)
+                if runs and runs[-1][1] == lo and runs[-1][2] == k:
+                    runs[-1][1] = hi
+                else:
+                    runs.append([lo, hi, k])
+        b1, b2 = group["betas"]
+        dev = flat.device
+        with torch.cuda.device(dev):
+            for lo, hi, k in runs:
+                _lib.check(lib.pmhc_adam_step(flat.data_ptr() + 4 * lo, flat_grad.data_ptr() + 4 * lo, self._m.data_ptr() + 4 * lo,
+                                              self._v.data_ptr() + 4 * lo, hi - lo, float(group["lr"]), float(b1), float(b2),
+                                              float(group["eps"]), k, _lib.stream_ptr(dev)), "pmhc_adam_step")
+        return loss
+
+
 class DiffusionModelOptimizer:
 
     def __init__(self, noise_step_count: int, model: torch.nn.Module, lr: float):
         self.noise_step_count = noise_step_count
         self.model = model
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr)  # optimizer.py:33
+        self.optimizer = FlatAdam(self.model, lr)  # optimizer.py:33: torch.optim.Adam, stepped by one fused kernel
         self.beta_min = 0.0
         self.beta_max = 0.8
         # parity hooks (tests only): reference z_t quaternions to align the q / -q sign with (SURVEY.md T2)
@@ -245,7 +329,7 @@ class DiffusionModelOptimizer:
         for p, g in zip(model.parameters(), model._split_flat(grad)):
             p.grad = g
         self.grad_hook(grad)
-        self.optimizer.step()
+        self.optimizer.step(flat_grad=grad)
 
     def grad_hook(self, flat_grad: torch.Tensor) -> None:
         """Called with the flat gradient before the Adam step; data-parallel wrappers all-reduce here."""

@@ -323,7 +323,8 @@ def test_parameter_gradients_edge_shapes_vs_oracle_autograd(api):
         assert rel_err(p.grad.cpu(), p_ref[k].grad) < TOL, (k, rel_err(p.grad.cpu(), p_ref[k].grad))
 
 
-@pytest.mark.parametrize("B,L,Pn,P_pad,seed", [(5, (2, 16), (3, 50), 50, 41), (7, (8, 15), (40, 180), 192, 77), (3, (9, 9), (60, 60), 80, 5)])
+@pytest.mark.parametrize("B,L,Pn,P_pad,seed", [(5, (2, 16), (3, 50), 50, 41), (7, (8, 15), (40, 180), 192, 77), (3, (9, 9), (60, 60), 80, 5),
+                                              (2, (8, 15), (150, 400), 400, 13)])
 def test_tf32_backward_gradients_vs_oracle_autograd(api, B, L, Pn, P_pad, seed):
     """Tensor-core backward on its own (fp32 forward, backward_precision = "bf16"): the forward recomputation, the input
     gradients and the weight-gradient outer products run as TF32 MMAs.  Ragged peptides, dirty padding (message-only pairs
@@ -382,6 +383,66 @@ def test_tf32_backward_gradients_vs_oracle_autograd(api, B, L, Pn, P_pad, seed):
     rel = float((fg - fr).norm() / fr.norm())
     assert cos >= 0.99999 and rel <= 2e-3, (cos, rel)
     assert differs, "the tensor-core backward returned the FFMA backward's bits: it did not run"
+
+
+def test_tf32_backward_refuses_pockets_beyond_its_shared_memory(api):
+    """The tensor-core backward keeps more per-pass tiles in shared memory than the FFMA one: pockets up to 432 slots fit
+    (FFMA mode: 480).  Beyond that the call fails with the shared-memory message — it does not switch mode silently."""
+    batch = orc.synthetic_batch(1, 9, 100, P_pad=480, seed=2)
+    model = make_model(api, orc.random_params(seed=1), 100)
+    model.backward_precision = "bf16"
+    out = model(gpu_batch(batch), 10)
+    with pytest.raises(RuntimeError, match="shared memory"):
+        out["torsions"].sum().backward()
+    model.backward_precision = "fp32"
+    out = model(gpu_batch(batch), 10)
+    out["torsions"].sum().backward()
+    assert all(p.grad is not None for k, p in model.named_parameters() if not k.startswith("gnn2.feature_mlp"))
+
+
+def test_flat_adam_matches_torch_adam_and_exchanges_state(api):
+    """DiffusionModelOptimizer.optimizer is a torch.optim.Adam whose step is one fused kernel over the flat parameter buffer
+    (two launches: gnn2.feature_mlp, which never gets a gradient, splits the buffer).  Same update as torch's multi-tensor
+    Adam on identical gradients (rounding-level: torch forms the update with different operation order), parameters without a
+    gradient untouched and stateless, and the state dict loads into a plain torch Adam and back."""
+    params = orc.random_params(seed=21)
+    model = make_model(api, params, 100)
+    ref = make_model(api, params, 100)
+    dm = api.DMO(100, model, 1e-3)
+    assert isinstance(dm.optimizer, torch.optim.Adam)
+    plain = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for step in range(3):
+        flat_grad = torch.randn(model._flat_params().numel(), generator=g).to(DEV) * 10.0 ** (step - 2)
+        for m, opt in ((model, dm.optimizer), (ref, plain)):
+            for p, gr in zip(m.parameters(), m._split_flat(flat_grad)):
+                p.grad = None if gr is None else gr.clone()
+        dm.optimizer.step(flat_grad=flat_grad)
+        plain.step()
+    for (k, a), b in zip(model.named_parameters(), ref.parameters()):
+        assert float((a - b).detach().abs().max()) <= 2e-7 + 1e-6 * float(b.detach().abs().max()), k
+        if k.startswith("gnn2.feature_mlp"):
+            assert torch.equal(a.cpu(), params[k]) and len(dm.optimizer.state[a]) == 0, k
+        else:
+            st, sr = dm.optimizer.state[a], plain.state[b]
+            assert float(st["step"]) == 3.0
+            assert float((st["exp_avg"] - sr["exp_avg"]).abs().max()) <= 1e-6 * float(sr["exp_avg"].abs().max()) + 1e-12, k
+            assert float((st["exp_avg_sq"] - sr["exp_avg_sq"]).abs().max()) <= 1e-6 * float(sr["exp_avg_sq"].abs().max()) + 1e-12, k
+    # plain .step() (gradients gathered from .grad) takes the same path
+    before = model._flat_params().clone()
+    dm.optimizer.step()
+    assert not torch.equal(before, model._flat_params())
+    # state exchange with a plain torch Adam, both ways; a loaded state keeps stepping
+    plain2 = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    plain2.load_state_dict(dm.optimizer.state_dict())
+    dm2 = api.DMO(100, make_model(api, params, 100), 1e-3)
+    dm2.optimizer.load_state_dict(plain.state_dict())
+    for p, gr in zip(dm2.model.parameters(), dm2.model._split_flat(flat_grad)):
+        p.grad = gr
+    dm2.optimizer.step(flat_grad=flat_grad)
+    first = next(p for k, p in dm2.model.named_parameters() if not k.startswith("gnn2.feature_mlp"))
+    assert float(dm2.optimizer.state[first]["step"]) == 4.0
+    assert dm2.optimizer.state[first]["exp_avg"].data_ptr() == dm2.optimizer._m.data_ptr()
 
 
 def test_optimize_steps_match_reference_fixture(api):
