@@ -418,6 +418,9 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
         const float rx = S[M.f.X + i * 3] - S[M.f.X + j * 3], ry = S[M.f.X + i * 3 + 1] - S[M.f.X + j * 3 + 1],
                     rz = S[M.f.X + i * 3 + 2] - S[M.f.X + j * 3 + 2];
         float dLdw = 0.0f;
+        // layer 2: this pair's share of dL / d (q_i, x_i); every pair of a row adds to the same node, so the shares go through
+        // one column per pair and a row reduction below instead of shared-memory atomics that serialise a whole row
+        float gi[7] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
 
         // ================= rotation head (model.py:283-296) =================
         {
@@ -484,7 +487,7 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
                 dqj = qadd(dqj, qmul_grad_a(ddg, u));          // dg = qj * u
                 dqinv = qadd(dqinv, qmul_grad_b(dl, du));      // u = dl * qinvj
                 dqj = qadd(dqj, qinv_grad(qj, dqinv));
-                atomic_add_quat(S + M.dQ + i * 4, dqi);
+                gi[0] += dqi.w; gi[1] += dqi.x; gi[2] += dqi.y; gi[3] += dqi.z;
                 if (pep) atomic_add_quat(S + M.dQ + j * 4, dqj);
             }
             __syncthreads();
@@ -565,7 +568,7 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
             if (owner) sDout[p] = ds;
             if (IN_GRADS && act && owner) {
                 const float f = w * sc;
-                atomicAdd(S + M.dX + i * 3 + 0, f * rg[11]); atomicAdd(S + M.dX + i * 3 + 1, f * rg[12]); atomicAdd(S + M.dX + i * 3 + 2, f * rg[13]);
+                gi[4] += f * rg[11]; gi[5] += f * rg[12]; gi[6] += f * rg[13];
                 if (pep) {
                     atomicAdd(S + M.dX + j * 3 + 0, -f * rg[11]); atomicAdd(S + M.dX + j * 3 + 1, -f * rg[12]); atomicAdd(S + M.dX + j * 3 + 2, -f * rg[13]);
                 }
@@ -626,9 +629,9 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
             }
             if (IN_GRADS && act && owner) {
                 const float f = -gd * 2.0f;                 // d(-d2) = gd
-                atomicAdd(S + M.dX + i * 3 + 0, f * rx); atomicAdd(S + M.dX + i * 3 + 1, f * ry); atomicAdd(S + M.dX + i * 3 + 2, f * rz);
+                gi[4] += f * rx; gi[5] += f * ry; gi[6] += f * rz;
                 const float fq = gq * 2.0f * dotq;
-                atomic_add_quat(S + M.dQ + i * 4, qscale(qj, fq));
+                gi[0] += fq * qj.w; gi[1] += fq * qj.x; gi[2] += fq * qj.y; gi[3] += fq * qj.z;
                 if (pep) {
                     atomicAdd(S + M.dX + j * 3 + 0, -f * rx); atomicAdd(S + M.dX + j * 3 + 1, -f * ry); atomicAdd(S + M.dX + j * 3 + 2, -f * rz);
                     atomic_add_quat(S + M.dQ + j * 4, qscale(qi, fq));
@@ -643,6 +646,10 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
         if (LAYER == 0) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) dm[k] += S[M.dMsum + i * kHid + n0 + k];
+        }
+        if (IN_GRADS && owner) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) sDout[c * kLdc + p] = act ? gi[c] : 0.0f;     // (Dout is free behind the last head's barrier)
         }
     } else {
 #pragma unroll
@@ -668,6 +675,19 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
         for (int k = 0; k < 32; ++k) dm1[k] = m1h[k] > 0.0f ? dm1[k] : 0.0f;
     }
     __syncthreads();
+    if (HEADS && IN_GRADS) {
+        for (int idx = tid; idx < L * 7; idx += kBwdThreads) {
+            const int rl = idx / 7, c = idx - rl * 7;
+            const int lo = max(rl * Wr, pass_base), hi = min((rl + 1) * Wr, pass_base + npass);
+            float sum = 0.0f;
+            for (int gp = lo; gp < hi; ++gp) sum += sDout[c * kLdc + (gp - pass_base)];
+            const int ri = I[IN_ROWS + rl];
+            if (hi > lo) {
+                if (c < 4) S[M.dQ + ri * 4 + c] += sum;
+                else S[M.dX + ri * 3 + (c - 4)] += sum;
+            }
+        }
+    }
     coop_outer(bufB, bufA, tiles + T_W2 * 4096);
     coop_bias_extras(bufB, sEx, 0, direct + (param_offset(LAYER, MSG2_B) - base), nullptr, 0);
     __syncthreads();
