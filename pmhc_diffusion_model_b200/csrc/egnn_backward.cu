@@ -220,11 +220,28 @@ __device__ __forceinline__ void axpy64(float (&acc)[kHid], const float* __restri
     }
 }
 
+// L2 loads the compiler must not sink to their use: issued where written (volatile), so their round trip overlaps the
+// barrier / MMA work in between
+__device__ __forceinline__ float4 ldcg_early4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldcg_early(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // tile[n][k] += sum_p bufN[n][p] * bufK[k][p] over the 128 columns of the pass: register-tiled 64x64x128 GEMM.
 // Thread t owns k in {t&15 + 16a}, n in {t>>4 + 16b}, a, b < 4; its 16 sums live contiguously in the tile-owner layout.
 __device__ __forceinline__ void coop_outer(const float* __restrict__ bufN, const float* __restrict__ bufK,
                                            float* __restrict__ tile) {
     const int tid = threadIdx.x, kk = tid & 15, nn = tid >> 4;
+    // the running sums (L2) are loaded first and consumed after the products, so their round trip hides under them
+    float4 old[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) old[a] = ldcg_early4(tile + tid * 16 + 4 * a);
     float acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -250,7 +267,7 @@ __device__ __forceinline__ void coop_outer(const float* __restrict__ bufN, const
     float4* dst = reinterpret_cast<float4*>(tile + tid * 16);
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        float4 v = dst[a];
+        float4 v = old[a];
         v.x += acc[a][0];
         v.y += acc[a][1];
         v.z += acc[a][2];
@@ -710,14 +727,28 @@ __device__ __forceinline__ void pair_pass(float* S, const BwdMap& M, const BwdAr
     if (HEADS) {
         // dA_j^T[k][j] += sum over rows of dm1 for the valid pocket columns of this pass
         const int rl_lo = pass_base / Wr, rl_hi = (pass_base + npass - 1) / Wr;
-        for (int idx = tid; idx < n_pocket_cols * kHid; idx += kBwdThreads) {
-            int k = idx / n_pocket_cols, ep = idx - k * n_pocket_cols;
-            float sum = 0.0f;
-            for (int rl = rl_lo; rl <= rl_hi; ++rl) {
-                int col = rl * Wr + pocket_e0 + ep - pass_base;
-                if (col >= 0 && col < npass) sum += bufB[k * kLdc + col];
+        const int n_items = n_pocket_cols * kHid;
+        for (int idx0 = tid; idx0 < n_items; idx0 += 4 * kBwdThreads) {   // four L2 read-modify-writes in flight per thread
+            float old[4];
+            int addr[4], kk[4], ee[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = idx0 + u * kBwdThreads;
+                kk[u] = idx / n_pocket_cols;
+                ee[u] = idx - kk[u] * n_pocket_cols;
+                addr[u] = idx < n_items ? kk[u] * Kpad + I[IN_POCKET + ee[u]] : -1;
+                old[u] = addr[u] >= 0 ? __ldcg(dajt + addr[u]) : 0.0f;
             }
-            dajt[k * Kpad + I[IN_POCKET + ep]] += sum;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (addr[u] < 0) continue;
+                float sum = 0.0f;
+                for (int rl = rl_lo; rl <= rl_hi; ++rl) {
+                    const int col = rl * Wr + pocket_e0 + ee[u] - pass_base;
+                    if (col >= 0 && col < npass) sum += bufB[kk[u] * kLdc + col];
+                }
+                dajt[addr[u]] = old[u] + sum;
+            }
         }
     }
     __syncthreads();
@@ -734,19 +765,6 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-// L2 loads the compiler must not sink to their use: issued where written (volatile), so their round trip overlaps the
-// barrier / MMA work in between
-__device__ __forceinline__ float4 ldcg_early4(const float* p) {
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ldcg_early(const float* p) {
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
 }
 
 // acc[mt][nt] += A (64 x 64) * X (64 x this warp's 16 pair columns).  A[m][k] = W[m][k] (TRANS = false) or W[k][m] (true),
