@@ -1658,7 +1658,15 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int st
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= numel) return;
     float acc = 0.0f;
-    for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * stride + kTileFloats + p];
+    // 16 L2 loads in flight, added in CTA order (the fixed order that makes the result independent of timing)
+    for (int c0 = 0; c0 < n_cta; c0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = c0 + u < n_cta ? __ldcg(partial + (size_t)(c0 + u) * stride + kTileFloats + p) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+            if (c0 + u < n_cta) acc += v[u];
+    }
     grad[p] += acc;
 }
 
