@@ -37,6 +37,13 @@ extern "C" {
  *   BF16: tcgen05 tensor cores, bf16 operands, fp32 accumulation in TMEM (<= 1e-2); everything else stays fp32. */
 #define PMHC_PRECISION_FP32 0
 #define PMHC_PRECISION_BF16 1
+/*   TC32: tcgen05 tensor cores with every operand written as two fp16 terms (x = hi + lo, ~22 bits) and every contraction as
+ *         hi.hi + lo.hi + hi.lo with fp32 accumulation in TMEM: fp32-class results (gate: the FP32 mode's own, max(1e-4, 2 x the
+ *         reference's fp32 noise floor)) — the tensor-core mode that holds on the reference's shipped model.pth;
+ *   FP16: the same pipeline with single fp16 terms (11 bits; 1e-2 class on well-conditioned weights).
+ * Both are forward modes; pmhc_model_backward_ex takes FP32 or BF16. */
+#define PMHC_PRECISION_TC32 2
+#define PMHC_PRECISION_FP16 3
 
 /* One batch of complexes in the dataset's padded layout (data.py:105-117, model.py:384-390). */
 typedef struct {

@@ -17,7 +17,8 @@ NTORS = 7       # PMHC_NTORS
 HID = 64        # PMHC_HID
 NPARAM = 79195  # PMHC_NPARAM
 ROWSTAT = 16    # PMHC_ROWSTAT
-PRECISIONS = {"fp32": 0, "bf16": 1}  # PMHC_PRECISION_*
+PRECISIONS = {"fp32": 0, "bf16": 1, "tc32": 2, "fp16": 3}  # PMHC_PRECISION_*
+BACKWARD_OF = {"fp32": "fp32", "bf16": "bf16", "tc32": "fp32", "fp16": "bf16"}  # default backward arithmetic of a forward mode
 
 EXPORTS = (
     "pmhc_last_error", "pmhc_check_device", "pmhc_param_offset", "pmhc_param_numel", "pmhc_workspace_bytes",

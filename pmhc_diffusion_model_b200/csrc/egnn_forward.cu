@@ -388,10 +388,12 @@ int pad_k(int P) { return ((kN + P + 31) / 32) * 32; }
 // workspace layout: [ajt scratch: num_sms * 64 * Kpad] [frames1: B*16*7] [tors1: B*16*14] [feat1: B*16*64]
 struct Workspace {
     float *ajt, *frames1, *tors1, *feat1;
-    void* tc2;          // buffers of the tensor-core path (carve_tc2)
+    void* tc2;          // buffers of the second-generation tensor-core path (carve_tc2)
+    void* tc3;          // buffers of the fp16-term tensor-core path (carve_tc3)
     size_t bytes;
 };
 size_t tc2_workspace_bytes(int B, int P);
+size_t tc3_workspace_bytes(int B, int P);
 Workspace carve_workspace(void* base, int B, int P) {
     Workspace w;
     size_t o = 0;
@@ -403,6 +405,8 @@ Workspace carve_workspace(void* base, int B, int P) {
     w.feat1 = p + o;   o += (size_t)B * kN * kHid;
     o = (o + 63) & ~(size_t)63;   // 256-byte aligned
     w.tc2 = p + o;     o += (tc2_workspace_bytes(B, P) + 3) / 4;
+    o = (o + 63) & ~(size_t)63;
+    w.tc3 = p + o;     o += (tc3_workspace_bytes(B, P) + 3) / 4;
     w.bytes = o * sizeof(float);
     return w;
 }
@@ -461,6 +465,9 @@ namespace pmhc {
 int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float* frames1, float* tors1, float* out_frames,
                 float* out_torsions, float* feat1_out, float* msum_out, float* rowstat1, float* rowstat2, float* logits1,
                 float* logits2, void* tc2_ws, cudaStream_t stream, bool reuse_pocket_cache);
+int forward_tc3(int terms, const float* params, const PmhcBatch* bt, float t_over_T, float* frames1, float* tors1, float* out_frames,
+                float* out_torsions, float* feat1_out, float* msum_out, float* rowstat1, float* rowstat2, float* logits1, float* logits2,
+                void* ws, cudaStream_t stream, bool reuse_pocket_cache);
 
 int model_forward_impl(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames, float* out_torsions,
                        float* saved, void* workspace, size_t workspace_bytes, cudaStream_t stream, int precision,
@@ -486,7 +493,7 @@ extern "C" int pmhc_model_forward_ex(const float* params, const PmhcBatch* bt, f
 int pmhc::model_forward_impl(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames,
                              float* out_torsions, float* saved, void* workspace, size_t workspace_bytes,
                              cudaStream_t stream, int precision, bool reuse_pocket_cache) {
-    PMHC_REQUIRE(precision == PMHC_PRECISION_FP32 || precision == PMHC_PRECISION_BF16, "unknown precision mode %d", precision);
+    PMHC_REQUIRE(precision >= PMHC_PRECISION_FP32 && precision <= PMHC_PRECISION_FP16, "unknown precision mode %d", precision);
     const bool use_tc = precision == PMHC_PRECISION_BF16;
     PMHC_REQUIRE(device_props() == 0, "no CUDA device");
     PMHC_REQUIRE(bt != nullptr && bt->B > 0, "pmhc_model_forward: empty batch");
@@ -502,6 +509,9 @@ int pmhc::model_forward_impl(const float* params, const PmhcBatch* bt, float t_o
     float* feat1 = saved ? sv.feat1 : w.feat1;
     float* msum1 = sv.msum1;
 
+    if (precision == PMHC_PRECISION_TC32 || precision == PMHC_PRECISION_FP16)
+        return forward_tc3(precision == PMHC_PRECISION_TC32 ? 2 : 1, params, bt, t_over_T, frames1, tors1, out_frames, out_torsions,
+                           saved ? feat1 : nullptr, msum1, rowstat1, rowstat2, sv.logits1, sv.logits2, w.tc3, stream, reuse_pocket_cache);
     if (use_tc)
         return forward_tc2(params, bt, t_over_T, frames1, tors1, out_frames, out_torsions, saved ? feat1 : nullptr, msum1,
                            rowstat1, rowstat2, sv.logits1, sv.logits2, w.tc2, stream, reuse_pocket_cache);

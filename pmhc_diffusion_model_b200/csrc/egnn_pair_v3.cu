@@ -1,0 +1,1441 @@
+// egnn_pair_v3.cu — fused EGNN layer forward on tcgen05, third generation: fp32-class results from fp16 hi/lo operand splits.
+//
+// Why: with the reference's shipped weights (model.pth) the attention logits reach 2.5e3 and every single-term 16-bit operand
+// format (bf16: 8 bits, fp16: 11 bits) moves the outputs by 1e-2 .. 3e-1 (tests/diag/emulate_split.py).  Writing every operand
+// as x = hi + lo (two fp16 terms, ~22 bits) and every contraction as hi.hi + lo.hi + hi.lo (three MMAs, fp32 accumulation in
+// tensor memory) brings the layer to the fp32 reference's own noise floor (7.7e-6 against float64 on the shipped fixture).
+//
+// What changed against the second generation (egnn_pair_tc.cu), all of it from that kernel's ncu profile:
+//   * message_mlp.2 is folded into the heads once per trajectory (W_h W2, W_h b2): the per-pair message is never formed, so
+//     the first MMA, its TMEM round trip and its epilogue are gone; the four heads contract m1 = relu(A_i + A_j + W_e) directly
+//     (model.py:183-226, :242, :260, :291, :325);
+//   * an engine is TWO groups of 128 threads over the same 128 pair rows (TMEM lanes): group A owns the attention and rotation
+//     heads, group B the torsion and translation heads — half the dependent chain per thread, 16 compute warps per SM;
+//   * the row softmax is streaming: per tile a row maximum, then exp-weighted partial sums merged into a 1 KB per-complex
+//     state (no buffer of all the complex's pair outputs, no row groups, any pocket size at constant shared memory);
+//   * attention and translation second layers (64 -> 1) are fp32 dot products straight from the accumulators; rotation and
+//     torsion second layers are MMAs on the hi/lo-split hidden units;
+//   * geometry inputs, all first-layer biases and the per-row torsion term ride in the contraction as extra K columns
+//     (bf16 three-term splits for -d2 and (q.q)^2, fp16 two-term for the local quaternion, a one-hot row selector against a
+//     per-complex [64 x 16] tile for W_t tors_i + b);
+//   * operand images and the per-complex node projections are staged by TMA bulk copies (cp.async.bulk + mbarrier tx bytes).
+//
+// TERMS = 2 is the fp32-class mode (PMHC_PRECISION_TC32); TERMS = 1 runs the same pipeline with single fp16 terms.
+#include <cuda_fp16.h>
+
+#include "egnn_common.cuh"
+#include "tcgen05.cuh"
+
+namespace pmhc {
+namespace tc3 {
+
+constexpr int kMaxEngines = 2;
+constexpr int kGrp = 128;                       // threads of one group = pair rows of a tile = TMEM lanes
+constexpr int kEngThreads = 2 * kGrp;           // group A (attention, rotation) + group B (torsion, translation)
+constexpr int kComputeThreads = kMaxEngines * kEngThreads;
+constexpr int kThreads = kComputeThreads + 128;  // + one warpgroup: warps 16 / 17 issue the MMAs of engine 0 / 1
+// setmaxnreg budgets out of the launch pool (640 threads x the 96 registers ptxas allots under __launch_bounds__(640, 1))
+constexpr int kRegsCompute = 104, kRegsIssue = 40, kLaunchRegs = 96;
+static_assert(kComputeThreads * kRegsCompute + 128 * kRegsIssue <= kThreads * kLaunchRegs, "setmaxnreg budgets exceed the launch pool");
+constexpr int kTile = 128;
+constexpr int kEngCols = 256;                   // TMEM columns per engine
+// TMEM columns of one engine: three 64-column head buffers, three 8-column extras blocks (16 K elements each), the two
+// second-layer outputs; layer 1's per-tile message column sums share the second-layer columns (read before those are issued)
+constexpr int TM_X = 0, TM_Y = 64, TM_Z = 128, TM_EXA = 192, TM_EXR = 200, TM_EXO = 208, TM_D3R = 216, TM_D3T = 232, TM_SUM = 216;
+// mbarriers of one engine: each of the first six completes exactly once per pair tile
+enum { B_ATT = 0, B_TOR, B_ROT, B_TRN, B_D3T, B_D3R, B_SUM, B_LOAD, kBars };
+constexpr uint32_t kTileBars = 0x3Fu;
+// named barriers of one engine
+enum { NB_REQ_ALL = 0, NB_REQ_A2, NB_REQ_B3, NB_REQ_A4, NB_ENG, NB_ENG_ALL, kNamed };
+
+struct PairArgs {
+    int B, P, Kpad, n_eng;
+    float t_over_T;
+    const float* params;             // flat parameter buffer (torsion_mlp.0's torsion columns are read per complex)
+    const float* frames_in;          // [B,16,7]
+    const float* tors_in;            // [B,16,14]
+    const uint8_t* mask;             // [B,16]
+    const float* pocket_frames;      // [B,P,7]
+    const uint8_t* pocket_cls;       // [B,cls_stride]
+    int cls_stride;
+    const float* pk32;               // [B,2,P,64] pocket rows of A_j per layer, fp32
+    const float* aij;                // [B,2,16,64] A_i + b1 | A_j of this layer's peptide nodes, fp32, rows chunk-swizzled
+    const uint8_t* wimage;           // this layer's operand image (weight_image3_kernel)
+    float* frames_out;               // [B,16,7]
+    float* tors_out;                 // [B,16,14]
+    float* ssum_out;                 // layer 1: [B,16,64] sum_j m1_ij, zero for padded rows
+    float* rowstat;                  // training only
+    float* logit_out;                // training only: [B,16,Kpad]
+    const int* order;                // [B] complexes by decreasing pair count (nullable)
+};
+
+// ---- work of one engine: complexes dealt round-robin over the engines, a partly filled last round split by peptide rows ----
+constexpr int kMaxParts = 4;
+struct Work {
+    int b, part, parts;
+};
+__device__ __forceinline__ bool get_work(int k, int cta, int eng, int ctas, int n_eng, int B, const int* __restrict__ order, Work& w) {
+    const int E = ctas * n_eng;
+    const int full = B / E, rem = B - full * E;
+    int item;
+    if (k < full) {
+        item = k * E + cta * n_eng + eng;
+        w.part = 0;
+        w.parts = 1;
+    } else {
+        if (k > full || rem == 0) return false;
+        int S = E / rem;
+        S = S > kMaxParts ? kMaxParts : S;
+        const int slot = eng * ctas + cta;
+        if (slot >= rem * S) return false;
+        item = full * E + slot / S;
+        w.part = slot - (slot / S) * S;
+        w.parts = S;
+    }
+    w.b = order != nullptr ? __ldg(order + item) : item;
+    return true;
+}
+__device__ __forceinline__ void part_rows(const Work& w, int L, int& beg, int& end) {
+    beg = (L * w.part) / w.parts;
+    end = (L * (w.part + 1)) / w.parts;
+}
+
+// ---- shared memory ----
+struct Map {
+    int WF, W3, WXA, WXR, WXT, WE, MISC, image_bytes, BAR, TPTR, cta_bytes;                                 // CTA-shared
+    int A1, SEL, TT, OUT, LG, ST, MROW, MTILE, AI, AJS, Q, X, TORS, INTS, CLS, eng_bytes;                     // per engine
+    int total_bytes;
+};
+// MISC floats
+constexpr int MS_ATT2 = 0, MS_TRN2 = 64, MS_B2ND = 128, MS_TCONST = 144, MS_TIME_I = 208, MS_TIME_J = 272, MS_FLOATS = 336;
+// B2ND: [0] attention_mlp.2.bias, [1,5) rotation_mlp.2.bias, [5,12) torsion_mlp.2.bias, [12] translation_mlp.2.bias
+
+template <int TERMS>
+__host__ __device__ inline Map make_map(int Kpad, bool layer1) {
+    Map m;
+    int o = 0;
+    m.WF = o;   o += 4 * TERMS * 8192;     // folded head weights [64 n][64 k] fp16 SW128, (head, term)
+    m.W3 = o;   o += 2 * TERMS * 2048;     // second layers [16 n][64 k] fp16 SW128: (rotation | torsion, term)
+    m.WXA = o;  o += 2048;                 // attention extras [64 n][16 k] bf16, K-major core matrices
+    m.WXR = o;  o += 2048;                 // rotation extras, fp16
+    m.WXT = o;  o += TERMS * 2048;         // translation bias against the one-hot block, fp16 terms
+    m.WE = o;   o += 8192;                 // message_mlp.0 edge columns, fp32 [31][64], chunk-swizzled rows
+    m.MISC = o; o += MS_FLOATS * 4;
+    m.image_bytes = o;                     // [0, image_bytes) is built by weight_image3_kernel
+    m.BAR = o;  o += (kMaxEngines * kBars + 1) * 8;
+    m.TPTR = o; o += 16;
+    o = (o + 1023) & ~1023;
+    m.cta_bytes = o;
+    int e = 0;
+    m.A1 = e;    e += TERMS * 16384;       // pair tile(s): m1 hi [, lo], [128 pairs][64 k] fp16 SW128
+    m.SEL = e;   e += layer1 ? 4096 : 0;   // column-sum selector [32 n][64 k] fp16 SW128
+    m.TT = e;    e += TERMS * 2048;        // per-complex torsion term [64 n][16 rows] fp16 terms
+    m.OUT = e;   e += kTile * kOutPerPair * 4;
+    m.LG = e;    e += kTile * 4;
+    m.ST = e;    e += kN * 16 * 4;
+    m.MROW = e;  e += 2 * kN * 4;
+    m.MTILE = e; e += 2 * kN * 4;
+    m.AI = e;    e += kN * 256;
+    m.AJS = e;   e += kN * 256;
+    m.Q = e;     e += Kpad * 16;
+    m.X = e;     e += Kpad * 16;
+    m.TORS = e;  e += 1024;
+    m.INTS = e;  e += (Kpad + 64) * 4;
+    m.CLS = e;   e += Kpad + 32;
+    e = (e + 1023) & ~1023;
+    m.eng_bytes = e;
+    m.total_bytes = m.cta_bytes + kMaxEngines * m.eng_bytes;   // (the host sizes the launch for the engines it runs)
+    return m;
+}
+
+// no-swizzle K-major [rows n][16 k] 16-bit operand: 8-row groups 256 B apart, the two K halves 128 B apart
+__host__ __device__ inline int kmaj16_offset(int n, int k) { return (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2; }
+// fp32 [rows][64] with the 16-byte chunks of a row XOR-swizzled by the row: lanes reading different rows hit different banks
+__host__ __device__ inline int swz64(int row, int k) { return row * 64 + ((((k >> 2) ^ (row & 7)) & 15) << 2) + (k & 3); }
+
+__device__ __forceinline__ uint16_t f16_bits(float x) { return __half_as_ushort(__float2half_rn(x)); }
+__device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// operand image of one layer (Map offsets [0, image_bytes)), once per trajectory / training step
+// ---------------------------------------------------------------------------------------------------------------
+template <int LAYER, int TERMS>
+__global__ void __launch_bounds__(256) weight_image3_kernel(const float* __restrict__ params, uint8_t* __restrict__ img) {
+    constexpr int L = LAYER;
+    constexpr int H = layer_H(L);
+    constexpr int ld1 = 2 * H + kEdge;
+    const Map M = make_map<TERMS>(32, L == 0);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const float* msg0 = params + param_offset(L, MSG0_W);
+    const float* msg2 = params + param_offset(L, MSG2_W);
+    const float* msg2b = params + param_offset(L, MSG2_B);
+    // head order: 0 attention, 1 rotation, 2 torsion, 3 translation
+    const float* head[4] = {params + param_offset(L, ATT0_W), params + param_offset(L, ROT0_W),
+                            params + param_offset(L, TOR0_W), params + param_offset(L, TRN0_W)};
+    const float* headb[4] = {params + param_offset(L, ATT0_B), params + param_offset(L, ROT0_B),
+                             params + param_offset(L, TOR0_B), params + param_offset(L, TRN0_B)};
+    const int ldh[4] = {66, 68, 78, 64};
+    auto put_split_f16 = [&](int base, int stride, uint32_t off, float v) {
+        const float h = __half2float(__float2half_rn(v));
+        *reinterpret_cast<uint16_t*>(img + base + off) = f16_bits(v);
+        if (TERMS > 1) *reinterpret_cast<uint16_t*>(img + base + stride + off) = f16_bits(v - h);
+    };
+    // folded first layers: Wf_h[n][k] = sum_m W_h[n][m] W2[m][k]
+    for (int idx = tid; idx < 4 * 64 * 64; idx += nthr) {
+        const int h = idx >> 12, n = (idx >> 6) & 63, k = idx & 63;
+        const float* w = head[h] + n * ldh[h];
+        double acc = 0.0;
+        for (int m = 0; m < 64; ++m) acc += (double)w[m] * (double)msg2[m * 64 + k];
+        put_split_f16(M.WF + h * TERMS * 8192, 8192, tc::sw128_offset(n, k), (float)acc);
+    }
+    for (int idx = tid; idx < 2 * 16 * 64; idx += nthr) {
+        const int hh = idx >> 10, n = (idx >> 6) & 15, k = idx & 63;
+        float v = 0.0f;
+        if (hh == 0 && n < 4) v = params[param_offset(L, ROT2_W) + n * 64 + k];
+        if (hh == 1 && n < PMHC_NTORS) v = params[param_offset(L, TOR2_W) + n * 64 + k];
+        put_split_f16(M.W3 + hh * TERMS * 2048, 2048, tc::sw128_offset(n, k), v);
+    }
+    for (int idx = tid; idx < 4 * 64; idx += nthr) {
+        const int h = idx >> 6, n = idx & 63;
+        const float* w = head[h] + n * ldh[h];
+        double bacc = (double)headb[h][n];
+        for (int m = 0; m < 64; ++m) bacc += (double)w[m] * (double)msg2b[m];   // message bias folded in: W_h b2
+        const float bias = (float)bacc;
+        if (h == 0) {
+            // attention extras, bf16 three-term splits.  Pair side: [dh dh dm dh dm dl | qh qh qm qh qm ql | 1 1 1 0]
+            float s[2][3];
+            for (int q = 0; q < 2; ++q) {
+                float r = w[64 + q];
+                for (int t = 0; t < 3; ++t) { s[q][t] = tc::bf16_round(r); r -= s[q][t]; }
+            }
+            float bs[3];
+            { float r = bias; for (int t = 0; t < 3; ++t) { bs[t] = tc::bf16_round(r); r -= bs[t]; } }
+            const float x[16] = {s[0][0], s[0][1], s[0][0], s[0][2], s[0][1], s[0][0], s[1][0], s[1][1], s[1][0], s[1][2], s[1][1], s[1][0],
+                                 bs[0], bs[1], bs[2], 0.0f};
+            for (int k = 0; k < 16; ++k) *reinterpret_cast<uint16_t*>(img + M.WXA + kmaj16_offset(n, k)) = bf16_bits(x[k]);
+        } else if (h == 1) {
+            // rotation extras, fp16 two-term splits.  Pair side: [l0h l0h l0l | l1h l1h l1l | l2h l2h l2l | l3h l3h l3l | 1 1 0 0]
+            float x[16];
+            for (int c = 0; c < 4; ++c) {
+                const float v = w[64 + c], vh = __half2float(__float2half_rn(v));
+                x[3 * c] = vh; x[3 * c + 1] = v - vh; x[3 * c + 2] = vh;
+            }
+            const float bh = __half2float(__float2half_rn(bias));
+            x[12] = bh; x[13] = bias - bh; x[14] = 0.0f; x[15] = 0.0f;
+            for (int k = 0; k < 16; ++k) *reinterpret_cast<uint16_t*>(img + M.WXR + kmaj16_offset(n, k)) = f16_bits(x[k]);
+        } else if (h == 2) {
+            reinterpret_cast<float*>(img + M.MISC)[MS_TCONST + n] = bias;     // joins W_t tors_i per complex
+        } else {
+            const float bh = __half2float(__float2half_rn(bias));
+            for (int k = 0; k < 16; ++k) {
+                *reinterpret_cast<uint16_t*>(img + M.WXT + kmaj16_offset(n, k)) = f16_bits(bias);
+                if (TERMS > 1) *reinterpret_cast<uint16_t*>(img + M.WXT + 2048 + kmaj16_offset(n, k)) = f16_bits(bias - bh);
+            }
+        }
+    }
+    float* we = reinterpret_cast<float*>(img + M.WE);
+    for (int idx = tid; idx < 32 * 64; idx += nthr) {
+        const int r = idx >> 6, k = idx & 63;
+        we[swz64(r, k)] = r < kEdge ? msg0[k * ld1 + 2 * H + r] : 0.0f;
+    }
+    float* misc = reinterpret_cast<float*>(img + M.MISC);
+    for (int n = tid; n < 64; n += nthr) {
+        misc[MS_ATT2 + n] = params[param_offset(L, ATT2_W) + n];
+        misc[MS_TRN2 + n] = params[param_offset(L, TRN2_W) + n];
+        misc[MS_TIME_I + n] = L == 0 ? msg0[n * ld1 + PMHC_NFEAT] : 0.0f;
+        misc[MS_TIME_J + n] = L == 0 ? msg0[n * ld1 + H + PMHC_NFEAT] : 0.0f;
+    }
+    if (tid < 16) {
+        float v = 0.0f;
+        if (tid == 0) v = params[param_offset(L, ATT2_B)];
+        else if (tid <= 4) v = params[param_offset(L, ROT2_B) + tid - 1];
+        else if (tid <= 11) v = params[param_offset(L, TOR2_B) + tid - 5];
+        else if (tid == 12) v = params[param_offset(L, TRN2_B)];
+        misc[MS_B2ND + tid] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one engine
+// ---------------------------------------------------------------------------------------------------------------
+struct Engine {
+    uint8_t* smem;      // CTA block (operand image)
+    uint8_t* es;        // engine block
+    const Map& M;
+    const PairArgs& a;
+    int eng, grp, r;    // engine, group (0 = A, 1 = B), pair row of the tile = TMEM lane
+    int et;             // thread within the engine (issuing warp: 256)
+    uint32_t tmem;      // engine's TMEM base
+    uint32_t lane_base; // (32 * warp-in-group) << 16
+    uint64_t* bar;      // this engine's mbarriers
+    uint32_t phase;     // bit k: parity of the next completion of mbarrier k
+    uint32_t smem_u, es_u;
+
+    static __device__ __forceinline__ uint32_t opaque(uint32_t x) {
+        uint32_t v;
+        asm volatile("mov.u32 %0, %1;" : "=r"(v) : "r"(x));
+        return v;
+    }
+    __device__ __forceinline__ int nb(int k) const { return 1 + kNamed * eng + k; }
+    __device__ __forceinline__ void sync_eng() const { tc::named_bar_sync(nb(NB_ENG), kEngThreads); }
+    __device__ __forceinline__ void sync_all() const { tc::named_bar_sync(nb(NB_ENG_ALL), kEngThreads + 32); }
+    __device__ __forceinline__ void wait(int k) {
+        tc::mbar_wait(bar + k, (phase >> k) & 1u);
+        phase ^= 1u << k;
+        tc::fence_after_thread_sync();
+    }
+    // compute threads: operand writes (TMEM and / or shared memory) are done -> ask the issuing warp for the next MMA batch
+    __device__ __forceinline__ void request(int k, int nthreads) const {
+        tc::tmem_wait_st();
+        tc::fence_before_thread_sync();
+        asm volatile("bar.arrive %0, %1;" ::"r"(nb(k)), "r"(nthreads + 32) : "memory");
+    }
+    template <class F>
+    __device__ __forceinline__ void serve(int k, int nthreads, F&& f) const {
+        tc::named_bar_sync(nb(k), nthreads + 32);
+        tc::fence_after_thread_sync();
+        if (tc::elect_one()) f();
+        __syncwarp();
+    }
+    __device__ __forceinline__ void commit(int k) const { tc::mma_commit(bar + k); }
+    __device__ __forceinline__ const int* ints() const { return reinterpret_cast<const int*>(es + M.INTS); }
+};
+
+// order-preserving float <-> int (for the shared-memory atomicMax of a row's tile maximum)
+__device__ __forceinline__ int enc_max(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float dec_max(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+constexpr int kEncNegInf = (int)0x807FFFFF;   // enc_max(-inf)
+
+// ---- staging: this thread's 32 features of m1 = relu(A_i + A_j + W_e) -> the pair tile(s) ----
+template <int LAYER, int TERMS>
+__device__ __forceinline__ void stage_half(const Engine& E, const PairRef& pr, int b) {
+    const int r = E.r, g = E.grp, i = pr.i, j = pr.j;
+    const float4* ai = reinterpret_cast<const float4*>(E.es + E.M.AI) + i * 16;
+    float4 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = ai[(8 * g + c) ^ (i & 7)];
+    if (j >= kN) {
+        const float4* src = reinterpret_cast<const float4*>(E.a.pk32 + (((size_t)b * 2 + LAYER) * E.a.P + (j - kN)) * kHid) + 8 * g;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 w = __ldg(src + c);
+            v[c].x += w.x; v[c].y += w.y; v[c].z += w.z; v[c].w += w.w;
+        }
+    } else if (j >= 0) {
+        const float4* aj = reinterpret_cast<const float4*>(E.es + E.M.AJS) + j * 16;
+        const int rel = kN - 1 + i - j;
+        const float4* we = reinterpret_cast<const float4*>(E.smem + E.M.WE) + rel * 16;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 w = aj[(8 * g + c) ^ (j & 7)];
+            const float4 e = we[(8 * g + c) ^ (rel & 7)];
+            v[c].x += w.x + e.x; v[c].y += w.y + e.y; v[c].z += w.z + e.z; v[c].w += w.w + e.w;
+        }
+    }
+    uint8_t* row = E.es + E.M.A1 + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {          // 16-byte chunks 4g + cc of the row: features 32 g + 8 cc ..
+        const float4 p = v[2 * cc], q = v[2 * cc + 1];
+        const float x0 = fmaxf(p.x, 0.0f), x1 = fmaxf(p.y, 0.0f), x2 = fmaxf(p.z, 0.0f), x3 = fmaxf(p.w, 0.0f);
+        const float x4 = fmaxf(q.x, 0.0f), x5 = fmaxf(q.y, 0.0f), x6 = fmaxf(q.z, 0.0f), x7 = fmaxf(q.w, 0.0f);
+        uint4 hi, lo;
+        if (TERMS > 1) {
+            tc::split_f16x2(x0, x1, hi.x, lo.x); tc::split_f16x2(x2, x3, hi.y, lo.y);
+            tc::split_f16x2(x4, x5, hi.z, lo.z); tc::split_f16x2(x6, x7, hi.w, lo.w);
+        } else {
+            hi.x = tc::pack_f16x2(x0, x1); hi.y = tc::pack_f16x2(x2, x3); hi.z = tc::pack_f16x2(x4, x5); hi.w = tc::pack_f16x2(x6, x7);
+        }
+        const int off = ((4 * g + cc) ^ (r & 7)) << 4;
+        *reinterpret_cast<uint4*>(row + off) = hi;
+        if (TERMS > 1) *reinterpret_cast<uint4*>(row + 16384 + off) = lo;
+    }
+}
+
+// layer 1: this pair's entry of the column-sum selector, Sel[16 * (r / 64) + i][r % 64] = multiplicity (group A writes it)
+__device__ __forceinline__ void write_sel(const Engine& E, const PairRef& pr, float mult) {
+    if (pr.active) {
+        const int r = E.r;
+        *reinterpret_cast<uint16_t*>(E.es + E.M.SEL + tc::sw128_offset(16 * (r >> 6) + pr.i, r & 63)) = f16_bits(mult);
+    }
+}
+
+// ---- extras blocks in tensor memory (A operand, 16 K elements = 8 columns) ----
+// attention: -d2 and (q_i.q_j)^2 as bf16 three-term splits, 1.0 for the bias terms (model.py:238-242)
+__device__ __forceinline__ void attention_extras(const Engine& E, const PairRef& pr) {
+    const float4* Q = reinterpret_cast<const float4*>(E.es + E.M.Q);
+    const float4* X = reinterpret_cast<const float4*>(E.es + E.M.X);
+    const float4 qi = Q[pr.i], qj = Q[pr.j < 0 ? pr.i : pr.j], xi = X[pr.i], xj = X[pr.j < 0 ? pr.i : pr.j];
+    const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+    const float nd2 = -(rx * rx + ry * ry + rz * rz);
+    const float dq = qi.x * qj.x + qi.y * qj.y + qi.z * qj.z + qi.w * qj.w;
+    const float qd = dq * dq;
+    const float dh = tc::bf16_round(nd2), d1 = nd2 - dh, dm = tc::bf16_round(d1), dl = d1 - dm;
+    const float qh = tc::bf16_round(qd), q1 = qd - qh, qm = tc::bf16_round(q1), ql = q1 - qm;
+    uint32_t x[8];
+    x[0] = tc::pack_bf16x2(dh, dh); x[1] = tc::pack_bf16x2(dm, dh); x[2] = tc::pack_bf16x2(dm, dl);
+    x[3] = tc::pack_bf16x2(qh, qh); x[4] = tc::pack_bf16x2(qm, qh); x[5] = tc::pack_bf16x2(qm, ql);
+    x[6] = 0x3F803F80u;             // (1, 1)
+    x[7] = 0x00003F80u;             // (1, 0)
+    tc::tmem_st8(E.tmem + E.lane_base + TM_EXA, x);
+}
+// rotation: the local quaternion q_j^-1 (q_i q_j) as fp16 two-term splits (model.py:283-291); and the one-hot row selector
+__device__ __forceinline__ void rotation_extras(const Engine& E, const PairRef& pr) {
+    const float4* Q = reinterpret_cast<const float4*>(E.es + E.M.Q);
+    const float4 qi4 = Q[pr.i], qj4 = Q[pr.j < 0 ? pr.i : pr.j];
+    const Quat qi{qi4.x, qi4.y, qi4.z, qi4.w}, qj{qj4.x, qj4.y, qj4.z, qj4.w};
+    const float in2 = 1.0f / qdot(qj, qj);
+    const Quat lq = qmul(Quat{qj.w * in2, -qj.x * in2, -qj.y * in2, -qj.z * in2}, qmul(qi, qj));
+    const float l[4] = {lq.w, lq.x, lq.y, lq.z};
+    float h[4], lo[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { h[c] = tc::f16_round(l[c]); lo[c] = l[c] - h[c]; }
+    uint32_t x[8];
+    x[0] = tc::pack_f16x2(h[0], h[0]); x[1] = tc::pack_f16x2(lo[0], h[1]); x[2] = tc::pack_f16x2(h[1], lo[1]);
+    x[3] = tc::pack_f16x2(h[2], h[2]); x[4] = tc::pack_f16x2(lo[2], h[3]); x[5] = tc::pack_f16x2(h[3], lo[3]);
+    x[6] = 0x3C003C00u;             // (1, 1) in fp16
+    x[7] = 0u;
+    tc::tmem_st8(E.tmem + E.lane_base + TM_EXR, x);
+    uint32_t o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = (pr.i >> 1) == c ? ((pr.i & 1) ? 0x3C000000u : 0x00003C00u) : 0u;
+    tc::tmem_st8(E.tmem + E.lane_base + TM_EXO, o);
+}
+
+// ---- fp32 second layer 64 -> 1 straight from the accumulators: w . relu(hidden) ----
+__device__ __forceinline__ float dot_relu64(const Engine& E, int buf, int misc_off) {
+    const float4* w = reinterpret_cast<const float4*>(E.smem + E.M.MISC) + misc_off / 4;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tc::tmem_ld32_nowait(E.tmem + E.lane_base + buf + 32 * half, v);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 a = w[8 * half + c];
+            s0 = fmaf(a.x, fmaxf(__uint_as_float(v[4 * c + 0]), 0.0f), s0);
+            s1 = fmaf(a.y, fmaxf(__uint_as_float(v[4 * c + 1]), 0.0f), s1);
+            s2 = fmaf(a.z, fmaxf(__uint_as_float(v[4 * c + 2]), 0.0f), s2);
+            s3 = fmaf(a.w, fmaxf(__uint_as_float(v[4 * c + 3]), 0.0f), s3);
+        }
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+// ---- hidden units of one head (64 fp32 columns) -> relu -> fp16 terms, in place.  Elements [32 h, 32 h + 32) of the hi term go
+// to columns [32 h, 32 h + 16), of the lo term to [32 h + 16, 32 h + 32): K step s of the hi term sits at column 8 s + 16 (s >> 1).
+template <int TERMS>
+__device__ __forceinline__ void convert_hidden(const Engine& E, int buf) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tc::tmem_ld32_nowait(E.tmem + E.lane_base + buf + 32 * half, v);
+        tc::tmem_wait_ld();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float x0 = fmaxf(__uint_as_float(v[2 * c]), 0.0f), x1 = fmaxf(__uint_as_float(v[2 * c + 1]), 0.0f);
+            if (TERMS > 1) tc::split_f16x2(x0, x1, hi[c], lo[c]);
+            else hi[c] = tc::pack_f16x2(x0, x1);
+        }
+        tc::tmem_st16(E.tmem + E.lane_base + buf + 32 * half, hi);
+        if (TERMS > 1) tc::tmem_st16(E.tmem + E.lane_base + buf + 32 * half + 16, lo);
+    }
+}
+__device__ __forceinline__ constexpr int hid_col(int s) { return 8 * s + 16 * (s >> 1); }
+
+// ---- MMA batches (one elected lane of the issuing warp) ----
+template <int TERMS>
+__device__ __forceinline__ void mma_head_main(const Engine& E, uint32_t cta, uint32_t esu, uint32_t tm, int h, int dst) {
+    constexpr uint32_t id = tc::idesc_f16_f32(128, 64);
+    const uint64_t a_hi = tc::smem_desc_sw128(esu + E.M.A1);
+    const uint64_t w_hi = tc::smem_desc_sw128(cta + E.M.WF + h * TERMS * 8192);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) tc::mma_bf16(tm + dst, a_hi + 2 * s, w_hi + 2 * s, id, s > 0);
+    if (TERMS > 1) {
+        const uint64_t a_lo = tc::smem_desc_sw128(esu + E.M.A1 + 16384);
+        const uint64_t w_lo = tc::smem_desc_sw128(cta + E.M.WF + h * TERMS * 8192 + 8192);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tc::mma_bf16(tm + dst, a_lo + 2 * s, w_hi + 2 * s, id, 1);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tc::mma_bf16(tm + dst, a_hi + 2 * s, w_lo + 2 * s, id, 1);
+    }
+}
+// K = 16 block from tensor memory against a K-major [64 n][16 k] shared-memory operand
+__device__ __forceinline__ void mma_extras(uint32_t tm_d, uint32_t tm_a, uint32_t b_addr, uint32_t idesc) {
+    tc::mma_bf16_ts(tm_d, tm_a, tc::smem_desc(b_addr, 128, 256, 0), idesc, 1);
+}
+// second layer of the rotation (hh = 0) / torsion (hh = 1) head on the converted hidden units in `src`
+template <int TERMS>
+__device__ __forceinline__ void mma_second(const Engine& E, uint32_t cta, uint32_t tm, int hh, int src, int dst) {
+    constexpr uint32_t id = tc::idesc_f16_f32(128, 16);
+    const uint64_t w_hi = tc::smem_desc_sw128(cta + E.M.W3 + hh * TERMS * 2048);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + dst, tm + src + hid_col(s), w_hi + 2 * s, id, s > 0);
+    if (TERMS > 1) {
+        const uint64_t w_lo = tc::smem_desc_sw128(cta + E.M.W3 + hh * TERMS * 2048 + 2048);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + dst, tm + src + hid_col(s) + 16, w_hi + 2 * s, id, 1);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tc::mma_bf16_ts(tm + dst, tm + src + hid_col(s), w_lo + 2 * s, id, 1);
+    }
+}
+// layer 1: message column sums of the tile, D[64 h + f][16 h + i] = sum over the pairs of tile half h in row i of m1[pair][f]
+template <int TERMS>
+__device__ __forceinline__ void mma_sums(const Engine& E, uint32_t esu, uint32_t tm) {
+    constexpr uint32_t id = tc::idesc_f16_f32_major(128, 32, 1, 0);
+    const uint64_t db = tc::smem_desc_sw128(esu + E.M.SEL);
+#pragma unroll
+    for (int u = 0; u < TERMS; ++u)
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            tc::mma_bf16(tm + TM_SUM, tc::smem_desc(esu + E.M.A1 + u * 16384 + s * 2048, 8192, 1024, 2), db + 2 * s, id, (u | s) > 0);
+}
+
+// per-complex work list, identically derived by the compute threads and the issuing warp
+struct Plan {
+    int L, W, rbeg, rend, G, ntiles, msg_w, msg_tiles;
+};
+__device__ __forceinline__ Plan make_plan(const ComplexInfo& ci, const Work& wk, bool layer1) {
+    Plan p;
+    p.L = ci.L;
+    p.W = (ci.L - 1) + ci.nv;
+    part_rows(wk, ci.L, p.rbeg, p.rend);
+    p.G = (p.rend - p.rbeg) * p.W;
+    p.ntiles = (p.G + kTile - 1) / kTile;
+    // message-only pairs (model.py:151 sums over ALL slots): self, masked peptide slots, masked pocket slots with their own
+    // features, one shared message for the c0 zero-feature masked pocket slots (multiplicity <= 1024 stays exact in fp16)
+    const int nshared = ci.c0 > 1024 ? 2 : (ci.c0 > 0 ? 1 : 0);
+    p.msg_w = 1 + (kN - ci.L) + ci.nx + nshared;
+    p.msg_tiles = layer1 ? ((p.rend - p.rbeg) * p.msg_w + kTile - 1) / kTile : 0;
+    return p;
+}
+
+// ---- per-complex set-up by the engine's 256 threads ----
+template <int LAYER, int TERMS>
+__device__ inline ComplexInfo setup_engine(Engine& E, int b) {
+    const PairArgs& a = E.a;
+    const Map& M = E.M;
+    const int et = E.et, lane = et & 31;
+    const int P = a.P, K = kN + P, Kpad = a.Kpad;
+    int* I = reinterpret_cast<int*>(E.es + M.INTS);
+    float* Q = reinterpret_cast<float*>(E.es + M.Q);
+    float* X = reinterpret_cast<float*>(E.es + M.X);
+    float* Tors = reinterpret_cast<float*>(E.es + M.TORS);
+    uint8_t* Cls = E.es + M.CLS;
+    if (et == 0) {
+        tc::fence_proxy_async_smem();   // the previous complex's generic-proxy accesses of these arrays come first
+        // contiguous per-complex arrays by TMA bulk copies: A_i | A_j rows (8 KB), torsions, peptide mask, pocket slot classes
+        const uint32_t bytes = 2 * kN * 256 + kN * 14 * 4 + 16 + (uint32_t)a.cls_stride;
+        tc::mbar_expect_tx(E.bar + B_LOAD, bytes);
+        tc::bulk_g2s(E.es + M.AI, a.aij + (size_t)b * 2 * kN * 64, kN * 256, E.bar + B_LOAD);
+        tc::bulk_g2s(E.es + M.AJS, a.aij + (size_t)b * 2 * kN * 64 + kN * 64, kN * 256, E.bar + B_LOAD);
+        tc::bulk_g2s(Tors, a.tors_in + (size_t)b * kN * 14, kN * 14 * 4, E.bar + B_LOAD);
+        tc::bulk_g2s(Cls, a.mask + (size_t)b * kN, 16, E.bar + B_LOAD);
+        tc::bulk_g2s(Cls + 16, a.pocket_cls + (size_t)b * a.cls_stride, (uint32_t)a.cls_stride, E.bar + B_LOAD);
+    }
+    for (int idx = et; idx < K * 7; idx += kEngThreads) {
+        const int j = idx / 7, c = idx - j * 7;
+        const float* f = (j < kN) ? a.frames_in + ((size_t)b * kN + j) * 7 + c : a.pocket_frames + ((size_t)b * P + (j - kN)) * 7 + c;
+        tc::cp_async_4(c < 4 ? Q + 4 * j + c : X + 4 * j + (c - 4), f);
+    }
+    if (et < kN * 16) reinterpret_cast<float*>(E.es + M.ST)[et] = 0.0f;
+    if (et < kN) {
+        reinterpret_cast<float*>(E.es + M.MROW)[et] = -INFINITY;
+        reinterpret_cast<int*>(E.es + M.MTILE)[et] = kEncNegInf;
+        reinterpret_cast<int*>(E.es + M.MTILE)[kN + et] = kEncNegInf;
+    }
+    if (LAYER == 0) reinterpret_cast<uint4*>(E.es + M.SEL)[et] = make_uint4(0u, 0u, 0u, 0u);
+    tc::cp_async_wait_all();
+    E.wait(B_LOAD);
+    E.sync_eng();
+    if (LAYER == 0) {
+        // time feature (model.py:394): A_i += (t/T) w_ti, A_j += (t/T) w_tj on the 16 peptide rows
+        const float* misc = reinterpret_cast<const float*>(E.smem + M.MISC);
+        float* ai = reinterpret_cast<float*>(E.es + M.AI);
+        float* aj = reinterpret_cast<float*>(E.es + M.AJS);
+        for (int idx = et; idx < kN * 64; idx += kEngThreads) {
+            const int i = idx >> 6, k = idx & 63;
+            ai[swz64(i, k)] = fmaf(a.t_over_T, misc[MS_TIME_I + k], ai[swz64(i, k)]);
+            aj[swz64(i, k)] = fmaf(a.t_over_T, misc[MS_TIME_J + k], aj[swz64(i, k)]);
+        }
+    }
+    {   // torsion term of the torsion head, per peptide row: T[i][n] = b[n] + W_t[n, 64:78] . tors_i (model.py:260), fp16 terms
+        const float* tor0 = a.params + param_offset(LAYER, TOR0_W);
+        const float* tconst = reinterpret_cast<const float*>(E.smem + M.MISC) + MS_TCONST;
+        const int i = et >> 4, n0 = (et & 15) * 4;
+        const float* t = Tors + i * 14;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int n = n0 + u;
+            const float* w = tor0 + n * 78 + 64;
+            float acc = tconst[n];
+#pragma unroll
+            for (int c = 0; c < 14; ++c) acc = fmaf(__ldg(w + c), t[c], acc);
+            const float h = tc::f16_round(acc);
+            *reinterpret_cast<uint16_t*>(E.es + M.TT + kmaj16_offset(n, i)) = f16_bits(acc);
+            if (TERMS > 1) *reinterpret_cast<uint16_t*>(E.es + M.TT + 2048 + kmaj16_offset(n, i)) = f16_bits(acc - h);
+        }
+    }
+    if ((et >> 5) == 0) {
+        const bool real = lane < kN && Cls[lane] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, real);
+        const int pos = __popc(bal & ((1u << lane) - 1u));
+        const int Lr = __popc(bal);
+        if (lane < kN) {
+            if (real) I[IN_ROWS + pos] = lane;
+            else I[IN_PEPX + (lane - pos)] = lane;
+        }
+        int nv = 0, nx = 0, c0 = 0;
+        for (int base = 0; base < P; base += 32) {
+            const int j = base + lane;
+            const int cls = j < P ? (int)Cls[16 + j] : 3;
+            const unsigned bv = __ballot_sync(0xffffffffu, cls == 0);
+            const unsigned bx = __ballot_sync(0xffffffffu, cls == 2);
+            const unsigned bz = __ballot_sync(0xffffffffu, cls == 1);
+            if (cls == 0) I[IN_POCKET + nv + __popc(bv & ((1u << lane) - 1u))] = kN + j;
+            if (cls == 2) I[IN_POCKET + Kpad - 1 - (nx + __popc(bx & ((1u << lane) - 1u)))] = kN + j;
+            nv += __popc(bv);
+            nx += __popc(bx);
+            c0 += __popc(bz);
+        }
+        if (lane == 0) {
+            I[IN_POCKET + Kpad + 0] = Lr;
+            I[IN_POCKET + Kpad + 1] = nv;
+            I[IN_POCKET + Kpad + 2] = nx;
+            I[IN_POCKET + Kpad + 3] = c0;
+        }
+    }
+    tc::fence_proxy_async_smem();   // the torsion-term tile (and the cleared selector) are MMA operands
+    E.sync_all();                   // + the issuing warp, which reads the lists' counts
+    ComplexInfo ci;
+    ci.L = I[IN_POCKET + Kpad + 0];
+    ci.nv = I[IN_POCKET + Kpad + 1];
+    ci.nx = I[IN_POCKET + Kpad + 2];
+    ci.c0 = I[IN_POCKET + Kpad + 3];
+    return ci;
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+template <int LAYER, int TERMS>
+__global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const Map M = make_map<TERMS>(a.Kpad, LAYER == 0);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + M.BAR);
+    uint64_t* wbar = bars + kMaxEngines * kBars;
+
+    if (warp == 0) tc::tmem_alloc(reinterpret_cast<uint32_t*>(smem + M.TPTR), 512);
+    if (tid == 32) {
+        for (int k = 0; k <= kMaxEngines * kBars; ++k) tc::mbar_init(bars + k, 1);
+        tc::mbar_fence_init();
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    if (tid == 0) {
+        // the layer's operand image: TMA bulk copies, 16 KB pieces, one transaction count
+        tc::mbar_expect_tx(wbar, (uint32_t)M.image_bytes);
+        for (int off = 0; off < M.image_bytes; off += 16384) {
+            const int n = M.image_bytes - off < 16384 ? M.image_bytes - off : 16384;
+            tc::bulk_g2s(smem + off, a.wimage + off, (uint32_t)n, wbar);
+        }
+    }
+    tc::mbar_wait(wbar, 0);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + M.TPTR);
+
+    if (tid >= kComputeThreads) {
+        // =============================== MMA issue: warp 16 -> engine 0, warp 17 -> engine 1 ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
+        const int eng = warp - kComputeThreads / 32;
+        if (eng < a.n_eng) {
+            uint8_t* es = smem + M.cta_bytes + eng * M.eng_bytes;
+            Engine E{smem, es, M, a, eng, 0, 0, kEngThreads, tmem_base + (uint32_t)(eng * kEngCols), 0u, bars + kBars * eng, 0u,
+                     tc::smem_u32(smem), tc::smem_u32(es)};
+            const int* I = E.ints();
+            constexpr uint32_t idf = tc::idesc_f16_f32(128, 64), idb = tc::idesc_bf16_f32(128, 64);
+            Work wk;
+            for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.n_eng, a.B, a.order, wk); ++k) {
+                E.sync_all();   // the compute threads have set the complex up
+                ComplexInfo ci;
+                ci.L = I[IN_POCKET + a.Kpad + 0];
+                ci.nv = I[IN_POCKET + a.Kpad + 1];
+                ci.nx = I[IN_POCKET + a.Kpad + 2];
+                ci.c0 = I[IN_POCKET + a.Kpad + 3];
+                const Plan pl = make_plan(ci, wk, LAYER == 0);
+                for (int t = 0; t < pl.ntiles; ++t) {
+                    E.serve(NB_REQ_ALL, kEngThreads, [&] {
+                        const uint32_t cta = Engine::opaque(E.smem_u), esu = Engine::opaque(E.es_u), tm = Engine::opaque(E.tmem);
+                        if (LAYER == 0) mma_sums<TERMS>(E, esu, tm);
+                        mma_head_main<TERMS>(E, cta, esu, tm, 0, TM_X);
+                        mma_extras(tm + TM_X, tm + TM_EXA, cta + M.WXA, idb);
+                        E.commit(B_ATT);
+                        mma_head_main<TERMS>(E, cta, esu, tm, 2, TM_Z);
+#pragma unroll
+                        for (int u = 0; u < TERMS; ++u) mma_extras(tm + TM_Z, tm + TM_EXO, esu + M.TT + u * 2048, idf);
+                        E.commit(B_TOR);
+                        mma_head_main<TERMS>(E, cta, esu, tm, 1, TM_Y);
+                        mma_extras(tm + TM_Y, tm + TM_EXR, cta + M.WXR, idf);
+                        E.commit(B_ROT);
+                    });
+                    E.serve(NB_REQ_A2, kGrp, [&] {   // group A has read the attention hidden units (and the tile sums): X is free
+                        const uint32_t cta = Engine::opaque(E.smem_u), esu = Engine::opaque(E.es_u), tm = Engine::opaque(E.tmem);
+                        mma_head_main<TERMS>(E, cta, esu, tm, 3, TM_X);
+#pragma unroll
+                        for (int u = 0; u < TERMS; ++u) mma_extras(tm + TM_X, tm + TM_EXO, cta + M.WXT + u * 2048, idf);
+                        E.commit(B_TRN);
+                    });
+                    E.serve(NB_REQ_B3, kGrp, [&] {
+                        const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
+                        mma_second<TERMS>(E, cta, tm, 1, TM_Z, TM_D3T);
+                        E.commit(B_D3T);
+                    });
+                    E.serve(NB_REQ_A4, kGrp, [&] {
+                        const uint32_t cta = Engine::opaque(E.smem_u), tm = Engine::opaque(E.tmem);
+                        mma_second<TERMS>(E, cta, tm, 0, TM_Y, TM_D3R);
+                        E.commit(B_D3R);
+                    });
+                }
+                for (int t = 0; t < pl.msg_tiles; ++t)
+                    E.serve(NB_REQ_ALL, kEngThreads, [&] {
+                        const uint32_t esu = Engine::opaque(E.es_u), tm = Engine::opaque(E.tmem);
+                        mma_sums<TERMS>(E, esu, tm);
+                        E.commit(B_SUM);
+                    });
+            }
+        }
+    } else {
+        // ========================= compute: two threads (group A, group B) per pair row of a tile =========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
+        const int eng = tid >> 8, et = tid & 255;
+        if (eng < a.n_eng) {
+            uint8_t* es = smem + M.cta_bytes + eng * M.eng_bytes;
+            Engine E{smem, es, M, a, eng, et >> 7, et & 127, et, tmem_base + (uint32_t)(eng * kEngCols),
+                     (uint32_t)((warp & 3) * 32) << 16, bars + kBars * eng, 0u, tc::smem_u32(smem), tc::smem_u32(es)};
+            const int* I = E.ints();
+            const bool grpA = E.grp == 0;
+            const int r = E.r;
+            float* Out = reinterpret_cast<float*>(es + M.OUT);
+            float* Lg = reinterpret_cast<float*>(es + M.LG);
+            float* St = reinterpret_cast<float*>(es + M.ST);
+            float* Mrow = reinterpret_cast<float*>(es + M.MROW);
+            int* Mtile = reinterpret_cast<int*>(es + M.MTILE);
+            const float* misc = reinterpret_cast<const float*>(smem + M.MISC);
+            const float4* Q = reinterpret_cast<const float4*>(es + M.Q);
+            const float4* X = reinterpret_cast<const float4*>(es + M.X);
+
+            Work wk;
+            for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.n_eng, a.B, a.order, wk); ++k) {
+                const int b = wk.b;
+                const ComplexInfo ci = setup_engine<LAYER, TERMS>(E, b);
+                const Plan pl = make_plan(ci, wk, LAYER == 0);
+                const int L = pl.L, W = pl.W, G = pl.G;
+                float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
+                if (wk.part == 0) {   // padded rows: pass-through (T4)
+                    for (int idx = et; idx < (kN - L) * 21; idx += kEngThreads) {
+                        const int s = idx / 21, c = idx - s * 21;
+                        const int i = I[IN_PEPX + s];
+                        if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = a.frames_in[((size_t)b * kN + i) * 7 + c];
+                        else a.tors_out[((size_t)b * kN + i) * 14 + (c - 7)] = a.tors_in[((size_t)b * kN + i) * 14 + (c - 7)];
+                    }
+                }
+                // layer 1 (group A): thread 64 h + f holds feature f of the message sums of rows 0..15 over the tile halves h
+                float ssum[kN];
+#pragma unroll
+                for (int i = 0; i < kN; ++i) ssum[i] = 0.0f;
+                auto add_tile_sums = [&] {
+                    float v[16];
+                    tc::tmem_ld16(E.tmem + E.lane_base + TM_SUM + 16 * (r >> 6), v);
+#pragma unroll
+                    for (int i = 0; i < kN; ++i) ssum[i] += v[i];
+                };
+
+                // pair g of the part = (row rl = g / W, entry e = g % W): peptide neighbours first, then the valid pocket slots
+                const int adv_q = W > 0 ? kTile / W : 0, adv_r = W > 0 ? kTile - adv_q * W : 0;
+                int cur_rl = W > 0 ? r / W : 0, cur_e = W > 0 ? r - cur_rl * W : 0;
+                int par = 0;   // tile parity: which copy of Mrow / Mtile is current
+                for (int t = 0; t < pl.ntiles; ++t) {
+                    const int g0 = t * kTile;
+                    PairRef pr;
+                    pr.active = g0 + r < G;
+                    int rl = cur_rl, e = cur_e;
+                    if (!pr.active) { rl = (G - 1) / W; e = (G - 1) - rl * W; }   // idle lanes of the last tile repeat its last pair
+                    cur_rl += adv_q;
+                    cur_e += adv_r;
+                    if (cur_e >= W) { cur_e -= W; ++cur_rl; }
+                    const int rr = pl.rbeg + rl;
+                    pr.i = I[IN_ROWS + rr];
+                    pr.j = e < L - 1 ? I[IN_ROWS + (e < rr ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
+
+                    stage_half<LAYER, TERMS>(E, pr, b);
+                    if (grpA) {
+                        if (LAYER == 0) write_sel(E, pr, 1.0f);
+                        attention_extras(E, pr);
+                    } else {
+                        rotation_extras(E, pr);
+                    }
+                    tc::fence_proxy_async_smem();
+                    E.request(NB_REQ_ALL, kEngThreads);
+
+                    float o[10];        // group A: logit, global delta quaternion; group B: delta angles, scale (x_i - x_j)
+                    if (grpA) {
+                        E.wait(B_ATT);
+                        if (LAYER == 0) {
+                            write_sel(E, pr, 0.0f);
+                            add_tile_sums();
+                        }
+                        const float logit = dot_relu64(E, TM_X, MS_ATT2) + misc[MS_B2ND + 0];   // model.py:241-243
+                        E.request(NB_REQ_A2, kGrp);
+                        E.wait(B_ROT);
+                        convert_hidden<TERMS>(E, TM_Y);
+                        E.request(NB_REQ_A4, kGrp);
+                        o[0] = logit;
+                        if (pr.active) {
+                            Lg[r] = logit;
+                            atomicMax(Mtile + par * kN + rl, enc_max(logit));
+                            if (lsave != nullptr) lsave[pr.i * a.Kpad + pr.j] = logit;
+                        }
+                        E.wait(B_D3R);
+                        float d[4];
+                        tc::tmem_ld4(E.tmem + E.lane_base + TM_D3R, d);
+                        const float4 qj4 = Q[pr.j];
+                        const Quat qj{qj4.x, qj4.y, qj4.z, qj4.w};
+                        const float in2 = __fdividef(1.0f, qdot(qj, qj));
+                        const Quat qinvj{qj.w * in2, -qj.x * in2, -qj.y * in2, -qj.z * in2};
+                        const Quat dl{fast_sigmoid(d[0] + misc[MS_B2ND + 1]), fast_sigmoid(d[1] + misc[MS_B2ND + 2]),
+                                      fast_sigmoid(d[2] + misc[MS_B2ND + 3]), fast_sigmoid(d[3] + misc[MS_B2ND + 4])};   // never normalised (T5)
+                        const Quat dg = qmul(qj, qmul(dl, qinvj));                                  // model.py:296
+                        o[1] = dg.w; o[2] = dg.x; o[3] = dg.y; o[4] = dg.z;
+                        E.phase ^= (1u << B_TOR) | (1u << B_TRN) | (1u << B_D3T);   // completions this group does not wait for
+                    } else {
+                        E.wait(B_TOR);
+                        convert_hidden<TERMS>(E, TM_Z);
+                        E.request(NB_REQ_B3, kGrp);
+                        E.wait(B_TRN);
+                        const float sc = dot_relu64(E, TM_X, MS_TRN2) + misc[MS_B2ND + 12];       // model.py:325-327
+                        tc::fence_before_thread_sync();
+                        E.wait(B_D3T);
+                        float d[8];
+                        tc::tmem_ld8(E.tmem + E.lane_base + TM_D3T, d);
+#pragma unroll
+                        for (int c = 0; c < PMHC_NTORS; ++c) o[c] = d[c] + misc[MS_B2ND + 5 + c];
+                        const float4 xi = X[pr.i], xj = X[pr.j];
+                        o[7] = sc * (xi.x - xj.x); o[8] = sc * (xi.y - xj.y); o[9] = sc * (xi.z - xj.z);   // model.py:331
+                        E.phase ^= (1u << B_ATT) | (1u << B_ROT) | (1u << B_D3R);
+                    }
+                    tc::fence_before_thread_sync();
+                    E.sync_eng();       // every row's tile maximum and every logit are in shared memory
+                    {
+                        const float m_new = fmaxf(Mrow[par * kN + rl], dec_max(Mtile[par * kN + rl]));
+                        const float p = pr.active ? __expf(Lg[r] - m_new) : 0.0f;
+                        float* out = Out + r * kOutPerPair;
+                        if (grpA) {
+                            out[0] = p;
+                            out[1] = p * o[1]; out[2] = p * o[2]; out[3] = p * o[3]; out[4] = p * o[4];
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 10; ++c) out[5 + c] = p * o[c];
+                        }
+                    }
+                    E.sync_eng();       // the tile's weighted outputs are in shared memory
+                    {
+                        // column c of the running sums: 16 lanes walk each row segment of the tile, then the state is rescaled and updated
+                        const int c = et >> 4, k16 = et & 15;
+                        const int rl0 = g0 / W, g1 = (g0 + kTile < G ? g0 + kTile : G) - 1, rl1 = g1 / W;
+                        for (int s = rl0; s <= rl1; ++s) {
+                            const int lo = (s * W > g0 ? s * W : g0) - g0, hi = ((s + 1) * W - 1 < g1 ? (s + 1) * W - 1 : g1) - g0;
+                            float acc = 0.0f;
+                            if (c < kOutPerPair)
+                                for (int p = lo + k16; p <= hi; p += 16) acc += Out[p * kOutPerPair + c];
+#pragma unroll
+                            for (int sh = 8; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+                            if (k16 == 0 && c < kOutPerPair) {
+                                const float m_old = Mrow[par * kN + s];
+                                const float m_new = fmaxf(m_old, dec_max(Mtile[par * kN + s]));
+                                const float f = m_old == -INFINITY ? 0.0f : __expf(m_old - m_new);
+                                St[s * 16 + c] = fmaf(St[s * 16 + c], f, acc);
+                            }
+                        }
+                        if (et < kN) {
+                            Mrow[(par ^ 1) * kN + et] = fmaxf(Mrow[par * kN + et], dec_max(Mtile[par * kN + et]));
+                            Mtile[(par ^ 1) * kN + et] = kEncNegInf;   // free since the previous tile; used by the next one
+                        }
+                    }
+                    par ^= 1;
+                    // (the next tile's request barrier orders these reads before the next writes of Out / Lg / Mtile)
+                }
+                E.sync_eng();
+                {
+                    // finished rows: normalise the running sums and apply the updates (model.py:263-269, 300-310, 331)
+                    const int rl = et >> 4, l16 = et & 15;
+                    if (rl < pl.rend - pl.rbeg) {
+                        const int i = I[IN_ROWS + pl.rbeg + rl];
+                        const float* st = St + rl * 16;
+                        const float se = st[0];
+                        const float inv = W > 0 ? 1.0f / se : 0.0f;
+                        const size_t node = (size_t)b * kN + i;
+                        if (l16 == 0) {
+                            const float4 qi = Q[i], xi = X[i];
+                            const Quat Gq{st[1] * inv, st[2] * inv, st[3] * inv, st[4] * inv};
+                            const Quat gq = W > 0 ? qnormalize(Gq) : Quat{1.0f, 0.0f, 0.0f, 0.0f};   // model.py:301-306
+                            const Quat qo = qunit(qmul(gq, Quat{qi.x, qi.y, qi.z, qi.w}));          // model.py:310, :181
+                            float* fo = a.frames_out + node * 7;
+                            fo[0] = qo.w; fo[1] = qo.x; fo[2] = qo.y; fo[3] = qo.z;
+                            fo[4] = xi.x + st[12] * inv; fo[5] = xi.y + st[13] * inv; fo[6] = xi.z + st[14] * inv;
+                            if (a.rowstat != nullptr) {
+                                float* rs = a.rowstat + node * PMHC_ROWSTAT;
+                                rs[0] = W > 0 ? Mrow[par * kN + rl] + logf(se) : 0.0f;
+#pragma unroll
+                                for (int c = 0; c < 14; ++c) rs[1 + c] = st[1 + c] * inv;
+                                rs[15] = 0.0f;
+                            }
+                        } else if (l16 <= PMHC_NTORS) {
+                            // torsions' = (sin dA, cos dA) (x) torsions (model.py:263-269)
+                            const int tq = l16 - 1;
+                            float sn, cs;
+                            sincosf(st[5 + tq] * inv, &sn, &cs);
+                            const float* tt = reinterpret_cast<const float*>(es + M.TORS) + i * 14 + 2 * tq;
+                            const SinCos so = scmul(SinCos{sn, cs}, SinCos{tt[0], tt[1]});
+                            a.tors_out[node * 14 + 2 * tq] = so.s;
+                            a.tors_out[node * 14 + 2 * tq + 1] = so.c;
+                        }
+                    }
+                }
+
+                if (LAYER == 0) {
+                    const int npx = kN - L, W2 = pl.msg_w, total = (pl.rend - pl.rbeg) * W2;
+                    for (int tile_base = 0; tile_base < total; tile_base += kTile) {
+                        const int gp0 = tile_base + r;
+                        const bool act = gp0 < total;
+                        const int gp = act ? gp0 : tile_base;
+                        const int rl = gp / W2, e = gp - rl * W2;
+                        PairRef pr;
+                        pr.i = I[IN_ROWS + pl.rbeg + rl];
+                        pr.active = act;
+                        float mult = 1.0f;
+                        if (e == 0) pr.j = pr.i;
+                        else if (e <= npx) pr.j = I[IN_PEPX + e - 1];
+                        else if (e <= npx + ci.nx) pr.j = I[IN_POCKET + a.Kpad - 1 - (e - npx - 1)];
+                        else {
+                            pr.j = -1;
+                            const int which = e - (npx + ci.nx + 1);
+                            mult = (float)(which == 0 ? min(ci.c0, 1024) : ci.c0 - 1024);
+                        }
+                        stage_half<LAYER, TERMS>(E, pr, b);
+                        if (grpA) write_sel(E, pr, mult);
+                        tc::fence_proxy_async_smem();
+                        E.request(NB_REQ_ALL, kEngThreads);
+                        E.wait(B_SUM);
+                        if (grpA) {
+                            write_sel(E, pr, 0.0f);
+                            add_tile_sums();
+                        }
+                        tc::fence_before_thread_sync();
+                        E.sync_eng();   // both groups are past the tile before its operands are rewritten
+                    }
+                    // thread 64 h + f holds the sums of tile half h: add the two halves through shared memory (the pair tile is free)
+                    float* scr = reinterpret_cast<float*>(es + M.A1);
+                    if (grpA) {
+#pragma unroll
+                        for (int i = 0; i < kN; ++i) scr[((r >> 6) * kN + i) * 64 + (r & 63)] = ssum[i];
+                    }
+                    E.sync_eng();
+                    for (int idx = et; idx < (pl.rend - pl.rbeg) * kHid; idx += kEngThreads) {
+                        const int o2 = I[IN_ROWS + pl.rbeg + (idx >> 6)] * kHid + (idx & 63);
+                        a.ssum_out[(size_t)b * kN * kHid + o2] = scr[o2] + scr[kN * kHid + o2];
+                    }
+                    if (wk.part == 0)
+                        for (int idx = et; idx < npx * kHid; idx += kEngThreads)
+                            a.ssum_out[(size_t)b * kN * kHid + I[IN_PEPX + (idx >> 6)] * kHid + (idx & 63)] = 0.0f;
+                }
+                E.sync_eng();
+            }
+        }
+    }
+
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// order3_kernel — complexes sorted by their number of attention-carrying pairs, largest first (counting sort, one CTA)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kOrderBins = kN * (kN - 1 + kMaxP) + 1;
+__global__ void __launch_bounds__(1024) order3_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ pocket_mask, int B, int P,
+                                                      int n_engines, int* __restrict__ keys, int* __restrict__ order) {
+    extern __shared__ int bins[];
+    const int tid = threadIdx.x;
+    if (B <= n_engines) {
+        for (int b = tid; b < B; b += blockDim.x) order[b] = b;
+        return;
+    }
+    for (int k = tid; k < kOrderBins; k += blockDim.x) bins[k] = 0;
+    __syncthreads();
+    for (int b = tid; b < B; b += blockDim.x) {
+        int L = 0, nv = 0;
+        for (int i = 0; i < kN; ++i) L += mask[(size_t)b * kN + i] != 0;
+        for (int j = 0; j < P; ++j) nv += pocket_mask[(size_t)b * P + j] != 0;
+        const int key = L * (L - 1 + nv);
+        keys[b] = key;
+        atomicAdd(&bins[key], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int k = kOrderBins - 1; k >= 0; --k) {
+            const int c = bins[k];
+            bins[k] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    if (B <= 4096) {
+        for (int b = tid; b < B; b += blockDim.x) {   // stable: equal keys keep their order
+            const int key = keys[b];
+            int before = 0;
+            for (int c = 0; c < b; ++c) before += keys[c] == key;
+            order[bins[key] + before] = b;
+        }
+    } else {
+        for (int b = tid; b < B; b += blockDim.x) order[atomicAdd(&bins[keys[b]], 1)] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// node_pre3_kernel — step-invariant first-layer projections in fp32, once per batch / trajectory (model.py:401, 411-412):
+//   pk32[b][l][p][k] = W1_l[k, H_l : H_l + 22] . pocket_features[b][p]
+//   cls[b][p]        = 0 valid, 1 masked + all-zero features (one shared message), 2 masked + non-zero features
+//   aij1[b][0][i][k] = b1 + W1_0[k, 0:22] . features[b][i]      (A_i of layer 1 without the time term)
+//   aij1[b][1][i][k] =      W1_0[k, 23:45] . features[b][i]     (rows chunk-swizzled: swz64)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) node_pre3_kernel(const float* __restrict__ params, const float* __restrict__ feat,
+                                                        const float* __restrict__ pocket_feat, const uint8_t* __restrict__ pocket_mask,
+                                                        int P, int cls_stride, float* __restrict__ pk32, uint8_t* __restrict__ cls,
+                                                        float* __restrict__ aij1) {
+    extern __shared__ __align__(16) float sp[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    constexpr int FS = 23;
+    float* pf = sp;                                   // [P][23]
+    float* w = pf + ((P * FS + 3) & ~3);              // [2][64][23] pocket blocks of both layers
+    float* nf = w + 2 * kHid * FS;                    // [16][23] peptide features
+    float* wp = nf + kN * FS + 1;                     // [128][23] layer-1 A_i | A_j blocks
+    for (int idx = tid; idx < P * PMHC_NFEAT; idx += blockDim.x) {
+        const int j = idx / PMHC_NFEAT, c = idx - j * PMHC_NFEAT;
+        pf[j * FS + c] = pocket_feat[(size_t)b * P * PMHC_NFEAT + idx];
+    }
+    for (int idx = tid; idx < 2 * kHid * PMHC_NFEAT; idx += blockDim.x) {
+        const int l = idx / (kHid * PMHC_NFEAT), r = idx - l * kHid * PMHC_NFEAT;
+        const int k = r / PMHC_NFEAT, c = r - k * PMHC_NFEAT;
+        const int H = l == 0 ? kH1 : kH2, ld1 = 2 * H + kEdge;
+        w[(l * kHid + k) * FS + c] = params[param_offset(l, MSG0_W) + k * ld1 + H + c];
+    }
+    for (int idx = tid; idx < kN * PMHC_NFEAT; idx += blockDim.x) {
+        const int i = idx / PMHC_NFEAT, c = idx - i * PMHC_NFEAT;
+        nf[i * FS + c] = feat[(size_t)b * kN * PMHC_NFEAT + idx];
+    }
+    for (int idx = tid; idx < 128 * PMHC_NFEAT; idx += blockDim.x) {
+        const int k = idx / PMHC_NFEAT, c = idx - k * PMHC_NFEAT;
+        constexpr int ld1 = 2 * kH1 + kEdge;
+        wp[k * FS + c] = params[param_offset(0, MSG0_W) + (k & 63) * ld1 + (k < 64 ? 0 : kH1) + c];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 2 * P * (kHid / 4); idx += blockDim.x) {
+        const int l = idx / (P * 16), r = idx - l * P * 16;
+        const int p = r >> 4, k0 = (r & 15) * 4;
+        const float* h = pf + p * FS;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int c = 0; c < PMHC_NFEAT; ++c) {
+            const float hv = h[c];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmaf(w[(l * kHid + k0 + u) * FS + c], hv, acc[u]);
+        }
+        *reinterpret_cast<float4*>(pk32 + (((size_t)b * 2 + l) * P + p) * kHid + k0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+    for (int j = tid; j < P; j += blockDim.x) {
+        uint8_t c = 0;
+        if (pocket_mask[(size_t)b * P + j] == 0) {
+            bool nz = false;
+            for (int q = 0; q < PMHC_NFEAT; ++q) nz |= (pf[j * FS + q] != 0.0f);
+            c = nz ? 2 : 1;
+        }
+        cls[(size_t)b * cls_stride + j] = c;
+    }
+    for (int j = P + tid; j < cls_stride; j += blockDim.x) cls[(size_t)b * cls_stride + j] = 3;
+    for (int idx = tid; idx < kN * 128; idx += blockDim.x) {
+        const int i = idx >> 7, k = idx & 127;
+        float acc = k < 64 ? params[param_offset(0, MSG0_B) + k] : 0.0f;
+#pragma unroll
+        for (int c = 0; c < PMHC_NFEAT; ++c) acc = fmaf(wp[k * FS + c], nf[i * FS + c], acc);
+        aij1[(size_t)b * 2 * kN * 64 + (k >> 6) * kN * 64 + swz64(i, k & 63)] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// node_mid3_kernel — between the layers, 128 nodes (8 complexes) per CTA, four chained tensor-core GEMMs with the A operand
+// in tensor memory (thread = node = TMEM lane), every operand as fp16 hi / lo terms (three MMAs per contraction):
+//   Msum = S . W2^T + (16 + P) b2                  (S = sum_j m1_ij from layer 1)
+//   hid  = relu([Msum | h | t/T] . W_f0^T + b)     (feature_mlp.0, model.py:151)
+//   o1   = relu(hid . W_f2^T + b)                  (feature_mlp.2 and the ReLU of model.py:407)
+//   [A_i | A_j] = o1 . [W1_i ; W1_j]^T (+ b1)      (layer 2's message_mlp.0 peptide blocks) -> fp32, rows chunk-swizzled
+// ---------------------------------------------------------------------------------------------------------------
+struct NodeMid3Args {
+    const uint8_t* image;
+    int B, P;
+    float t_over_T;
+    const float* ssum;        // [B,16,64]
+    const float* feat;        // [B,16,22]
+    const uint8_t* mask;      // [B,16]
+    float* aij2;              // [B,2,16,64]
+    float* feat1_out;         // nullable: [B,16,64] relu(o1)   (saved for the backward pass)
+    float* msum_out;          // nullable: [B,16,64]
+};
+template <int TERMS>
+struct Nm3 {
+    static constexpr int W2 = 0, WF0A = W2 + TERMS * 8192, WF0B = WF0A + TERMS * 8192, WF2 = WF0B + TERMS * 8192, W1 = WF2 + TERMS * 8192,
+                         BIAS = W1 + TERMS * 16384, BAR = BIAS + 1280, TPTR = BAR + 16, BYTES = TPTR + 16 + 1024;
+};
+
+template <int TERMS>
+__global__ void __launch_bounds__(256) node_mid3_image_kernel(const float* __restrict__ params, int P, uint8_t* __restrict__ img) {
+    using N = Nm3<TERMS>;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const float* msg2 = params + param_offset(0, MSG2_W);
+    const float* f0w = params + param_offset(0, FEAT0_W);   // [64][23 + 64]: columns 0..22 node features (+time), 23.. message sum
+    const float* f2w = params + param_offset(0, FEAT2_W);
+    const float* w1 = params + param_offset(1, MSG0_W);     // [64][2*64 + 31]
+    constexpr int ldf = kH1 + kHid, ld1 = 2 * kH2 + kEdge;
+    auto put = [&](int base, int stride, uint32_t off, float v) {
+        const float h = __half2float(__float2half_rn(v));
+        *reinterpret_cast<uint16_t*>(img + base + off) = f16_bits(v);
+        if (TERMS > 1) *reinterpret_cast<uint16_t*>(img + base + stride + off) = f16_bits(v - h);
+    };
+    for (int idx = tid; idx < 64 * 64; idx += nthr) {
+        const int n = idx >> 6, k = idx & 63;
+        const uint32_t off = tc::sw128_offset(n, k);
+        put(N::W2, 8192, off, msg2[n * 64 + k]);
+        put(N::WF2, 8192, off, f2w[n * 64 + k]);
+        put(N::WF0A, 8192, off, f0w[n * ldf + kH1 + k]);                       // K block 0: the 64 message-sum columns
+        put(N::WF0B, 8192, off, k < kH1 ? f0w[n * ldf + k] : 0.0f);            // K block 1: 22 features, t/T, zeros
+    }
+    for (int idx = tid; idx < 128 * 64; idx += nthr) {
+        const int n = idx >> 6, k = idx & 63;
+        put(N::W1, 16384, tc::sw128_offset(n, k), w1[(n & 63) * ld1 + (n < 64 ? 0 : kH2) + k]);
+    }
+    float* bias = reinterpret_cast<float*>(img + N::BIAS);   // [0,64) b2 * (16 + P) | f0b | f2b | b1(layer 2) | 64 zeros
+    if (tid < 64) {
+        bias[tid] = params[param_offset(0, MSG2_B) + tid] * (float)(kN + P);
+        bias[64 + tid] = params[param_offset(0, FEAT0_B) + tid];
+        bias[128 + tid] = params[param_offset(0, FEAT2_B) + tid];
+        bias[192 + tid] = params[param_offset(1, MSG0_B) + tid];
+        bias[256 + tid] = 0.0f;
+    }
+}
+
+template <int TERMS>
+__global__ void __launch_bounds__(128, 1) node_mid3_kernel(NodeMid3Args a) {
+    using N = Nm3<TERMS>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + N::BAR);
+    uint64_t* wbar = bar + 1;
+    const float* bias = reinterpret_cast<const float*>(smem + N::BIAS);
+    if (warp == 0) tc::tmem_alloc(reinterpret_cast<uint32_t*>(smem + N::TPTR), 512);
+    if (tid == 32) {
+        tc::mbar_init(bar, 1);
+        tc::mbar_init(wbar, 1);
+        tc::mbar_fence_init();
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    if (tid == 0) {
+        tc::mbar_expect_tx(wbar, (uint32_t)N::BAR);
+        for (int off = 0; off < N::BAR; off += 16384) {
+            const int n = N::BAR - off < 16384 ? N::BAR - off : 16384;
+            tc::bulk_g2s(smem + off, a.image + off, (uint32_t)n, wbar);
+        }
+    }
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + N::TPTR);
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t phase = 0;
+    // TMEM columns: S hi [0,32) lo [32,64) | D1 [64,128) | Msum hi [128,160) lo [160,192) | feat hi [192,208) lo [208,224) | D2 [224,288)
+    //               | hid hi [288,320) lo [320,352) | D3 [352,416) | o1 hi [416,448) lo [448,480) | D4 [0,128)
+    const int64_t node = (int64_t)blockIdx.x * 128 + tid;
+    const bool in = node < (int64_t)a.B * kN;
+    const bool real = in && a.mask[node] != 0;
+
+    auto store_split = [&](int col_hi, int col_lo, const float (&v)[64]) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            if (TERMS > 1) tc::split_f16x2(v[2 * c], v[2 * c + 1], hi[c], lo[c]);
+            else hi[c] = tc::pack_f16x2(v[2 * c], v[2 * c + 1]);
+        }
+        tc::tmem_st32(tmem + lane_base + col_hi, hi);
+        if (TERMS > 1) tc::tmem_st32(tmem + lane_base + col_lo, lo);
+    };
+    float v[64];
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.ssum + (in ? node : 0) * kHid);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float4 x = in ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+        }
+        store_split(0, 32, v);
+        uint32_t hf[16], lf[16];
+        const float* f = a.feat + (in ? node : 0) * PMHC_NFEAT;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float x0 = 2 * c < PMHC_NFEAT ? (in ? f[2 * c] : 0.0f) : (2 * c == PMHC_NFEAT ? a.t_over_T : 0.0f);
+            const float x1 = 2 * c + 1 < PMHC_NFEAT ? (in ? f[2 * c + 1] : 0.0f) : (2 * c + 1 == PMHC_NFEAT ? a.t_over_T : 0.0f);
+            if (TERMS > 1) tc::split_f16x2(x0, x1, hf[c], lf[c]);
+            else { hf[c] = tc::pack_f16x2(x0, x1); lf[c] = 0u; }
+        }
+        tc::tmem_st16(tmem + lane_base + 192, hf);
+        if (TERMS > 1) tc::tmem_st16(tmem + lane_base + 208, lf);
+    }
+    tc::mbar_wait(wbar, 0);
+    auto issue = [&](auto&& f) {
+        tc::tmem_wait_st();
+        tc::fence_before_thread_sync();
+        __syncthreads();
+        if (warp == 0) {
+            if (tc::elect_one()) {
+                tc::fence_after_thread_sync();
+                f();
+                tc::mma_commit(bar);
+            }
+            __syncwarp();
+        }
+        tc::mbar_wait(bar, phase);
+        phase ^= 1;
+        tc::fence_after_thread_sync();
+    };
+    // D = A . W^T over `ksteps` K steps of 16, A terms at columns a_hi / a_lo, W terms at w / w + wstride
+    auto gemm = [&](uint32_t d, int a_hi, int a_lo, int w, int wstride, int ksteps, uint32_t id, bool first) {
+        const uint64_t w_hi = tc::smem_desc_sw128(tc::smem_u32(smem + w));
+        for (int s = 0; s < ksteps; ++s) tc::mma_bf16_ts(tmem + d, tmem + a_hi + 8 * s, w_hi + 2 * s, id, (first && s == 0) ? 0u : 1u);
+        if (TERMS > 1) {
+            const uint64_t w_lo = tc::smem_desc_sw128(tc::smem_u32(smem + w + wstride));
+            for (int s = 0; s < ksteps; ++s) tc::mma_bf16_ts(tmem + d, tmem + a_lo + 8 * s, w_hi + 2 * s, id, 1u);
+            for (int s = 0; s < ksteps; ++s) tc::mma_bf16_ts(tmem + d, tmem + a_hi + 8 * s, w_lo + 2 * s, id, 1u);
+        }
+    };
+    constexpr uint32_t id64 = tc::idesc_f16_f32(128, 64), id128 = tc::idesc_f16_f32(128, 128);
+    auto load64 = [&](int col, const float* bv, bool relu, float (&out)[64]) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t x[32];
+            tc::tmem_ld32_nowait(tmem + lane_base + col + 32 * half, x);
+            tc::tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float y = __uint_as_float(x[c]) + bv[32 * half + c];
+                out[32 * half + c] = relu ? fmaxf(y, 0.0f) : y;
+            }
+        }
+    };
+    auto store_global = [&](float* dst, const float (&x)[64], bool keep) {
+        if (dst == nullptr || !in) return;
+        float4* d4 = reinterpret_cast<float4*>(dst + node * kHid);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            d4[c] = keep ? make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    };
+    issue([&] { gemm(64, 0, 32, N::W2, 8192, 4, id64, true); });                       // G1: Msum
+    load64(64, bias + 0, false, v);
+    store_global(a.msum_out, v, real);
+    store_split(128, 160, v);
+    issue([&] {                                                                         // G2: feature_mlp.0
+        gemm(224, 128, 160, N::WF0A, 8192, 4, id64, true);
+        gemm(224, 192, 208, N::WF0B, 8192, 2, id64, false);
+    });
+    load64(224, bias + 64, true, v);
+    store_split(288, 320, v);
+    issue([&] { gemm(352, 288, 320, N::WF2, 8192, 4, id64, true); });                  // G3: feature_mlp.2 (+ the ReLU between the layers)
+    load64(352, bias + 128, true, v);
+    store_global(a.feat1_out, v, real);
+    store_split(416, 448, v);
+    issue([&] { gemm(0, 416, 448, N::W1, 16384, 4, id128, true); });                   // G4: layer 2's A_i | A_j
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        load64(64 * half, bias + (half == 0 ? 192 : 256), false, v);
+        if (in) {
+            const int i = (int)(node & (kN - 1));
+            float4* dst = reinterpret_cast<float4*>(a.aij2 + (node >> 4) * 2 * kN * 64 + half * kN * 64 + i * 64);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) dst[c ^ (i & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc3
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct Tc3Workspace {
+    float* pk32;        // [B,2,P,64]
+    float* ssum;        // [B,16,64]
+    float* aij1;        // [B,2,16,64]
+    float* aij2;        // [B,2,16,64]
+    uint8_t* cls;       // [B,cls_stride]
+    uint8_t* wimage;    // [2][image_stride]
+    uint8_t* nm_image;
+    int* order;
+    int* keys;
+    int cls_stride, image_stride;
+    size_t bytes;
+};
+static Tc3Workspace carve_tc3(void* base, int B, int P) {
+    Tc3Workspace w;
+    uint8_t* p = (uint8_t*)base;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t at = o; o += (n + 255) & ~(size_t)255; return p + at; };
+    w.cls_stride = (P + 15) & ~15;
+    w.image_stride = (tc3::make_map<2>(32, true).image_bytes + 255) & ~255;
+    w.pk32 = (float*)take((size_t)B * 2 * P * kHid * 4);
+    w.ssum = (float*)take((size_t)B * kN * kHid * 4);
+    w.aij1 = (float*)take((size_t)B * 2 * kN * 64 * 4);
+    w.aij2 = (float*)take((size_t)B * 2 * kN * 64 * 4);
+    w.cls = (uint8_t*)take((size_t)B * w.cls_stride);
+    w.wimage = (uint8_t*)take((size_t)2 * w.image_stride);
+    w.nm_image = (uint8_t*)take((size_t)tc3::Nm3<2>::BAR);
+    w.order = (int*)take((size_t)B * sizeof(int));
+    w.keys = (int*)take((size_t)B * sizeof(int));
+    w.bytes = o;
+    return w;
+}
+size_t tc3_workspace_bytes(int B, int P) { return carve_tc3(nullptr, B, P).bytes; }
+
+// per-device launch configuration (opt-in shared memory is a per-device function attribute)
+struct Tc3Device {
+    bool configured = false;
+    int max_smem = 0, sms = 0;
+};
+static Tc3Device g_tc3_dev[64];
+
+template <class K>
+static int tc3_set_smem(K kernel, int bytes, const char* what) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+template <int TERMS>
+static int tc3_configure(Tc3Device& d, int dev) {
+    cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    int rc;
+    if ((rc = tc3_set_smem(tc3::egnn_pair3_kernel<0, TERMS>, d.max_smem, "pair3<0>")) != 0) return rc;
+    if ((rc = tc3_set_smem(tc3::egnn_pair3_kernel<1, TERMS>, d.max_smem, "pair3<1>")) != 0) return rc;
+    if ((rc = tc3_set_smem(tc3::node_mid3_kernel<TERMS>, tc3::Nm3<TERMS>::BYTES, "node_mid3")) != 0) return rc;
+    if ((rc = tc3_set_smem(tc3::node_pre3_kernel, 96 * 1024, "node_pre3")) != 0) return rc;
+    // the register budgets of the pair kernel's setmaxnreg come out of the launch pool: check what ptxas allotted
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, tc3::egnn_pair3_kernel<0, TERMS>);
+    PMHC_REQUIRE(fa.numRegs * tc3::kThreads >= tc3::kComputeThreads * tc3::kRegsCompute + 128 * tc3::kRegsIssue,
+                 "pair3 kernel was compiled with %d registers per thread: the setmaxnreg budgets do not fit", fa.numRegs);
+    cudaFuncGetAttributes(&fa, tc3::egnn_pair3_kernel<1, TERMS>);
+    PMHC_REQUIRE(fa.numRegs * tc3::kThreads >= tc3::kComputeThreads * tc3::kRegsCompute + 128 * tc3::kRegsIssue,
+                 "pair3 kernel was compiled with %d registers per thread: the setmaxnreg budgets do not fit", fa.numRegs);
+    return 0;
+}
+
+template <int LAYER, int TERMS>
+static int launch_pair3(tc3::PairArgs& a, const Tc3Device& d, cudaStream_t stream) {
+    const tc3::Map M = tc3::make_map<TERMS>(a.Kpad, LAYER == 0);
+    int n_eng = tc3::kMaxEngines;
+    while (n_eng > 0 && (size_t)M.cta_bytes + (size_t)n_eng * M.eng_bytes + 1024 > (size_t)d.max_smem) --n_eng;
+    PMHC_REQUIRE(n_eng > 0, "EGNN tensor-core layer does not fit in shared memory (P=%d, device allows %d B)", a.P, d.max_smem);
+    a.n_eng = n_eng;
+    const size_t smem = (size_t)M.cta_bytes + (size_t)n_eng * M.eng_bytes + 1024;
+    const int want = (a.B + n_eng - 1) / n_eng;
+    const int grid = want < d.sms ? want : d.sms;
+    if (profile_enabled()) profile_mark(PROF_FWD, stream, true);
+    tc3::egnn_pair3_kernel<LAYER, TERMS><<<grid, tc3::kThreads, smem, stream>>>(a);
+    if (profile_enabled()) profile_mark(PROF_FWD, stream, false);
+    PMHC_CHECK_LAUNCH("egnn_pair3");
+    return 0;
+}
+
+// Denoiser forward on tcgen05 with fp16 operand terms: [node_pre3] -> pair3<0> -> node_mid3 -> pair3<1>.
+template <int TERMS>
+static int forward_tc3_impl(const float* params, const PmhcBatch* bt, float t_over_T, float* frames1, float* tors1, float* out_frames,
+                            float* out_torsions, float* feat1_out, float* msum_out, float* rowstat1, float* rowstat2, float* logits1,
+                            float* logits2, void* ws, cudaStream_t stream, bool reuse_pocket_cache) {
+    const int B = bt->B, P = bt->P;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    PMHC_REQUIRE(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+    Tc3Device& d = g_tc3_dev[dev * 1 + 0];
+    static bool configured[64][3] = {};
+    if (!configured[dev][TERMS]) {
+        int rc = tc3_configure<TERMS>(d, dev);
+        if (rc != 0) return rc;
+        configured[dev][TERMS] = true;
+    }
+    Tc3Workspace w = carve_tc3(ws, B, P);
+    if (!reuse_pocket_cache) {
+        tc3::weight_image3_kernel<0, TERMS><<<16, 256, 0, stream>>>(params, w.wimage);
+        PMHC_CHECK_LAUNCH("weight_image3");
+        tc3::weight_image3_kernel<1, TERMS><<<16, 256, 0, stream>>>(params, w.wimage + w.image_stride);
+        PMHC_CHECK_LAUNCH("weight_image3");
+        tc3::node_mid3_image_kernel<TERMS><<<16, 256, 0, stream>>>(params, P, w.nm_image);
+        PMHC_CHECK_LAUNCH("node_mid3_image");
+        const size_t smem = (size_t)(((P * 23 + 3) & ~3) + 2 * kHid * 23 + kN * 23 + 1 + 128 * 23) * sizeof(float);
+        tc3::node_pre3_kernel<<<B, 128, smem, stream>>>(params, bt->features, bt->pocket_features, bt->pocket_mask, P, w.cls_stride,
+                                                         w.pk32, w.cls, w.aij1);
+        PMHC_CHECK_LAUNCH("node_pre3");
+        tc3::order3_kernel<<<1, 1024, tc3::kOrderBins * sizeof(int), stream>>>(bt->mask, bt->pocket_mask, B, P, tc3::kMaxEngines * d.sms,
+                                                                              w.keys, w.order);
+        PMHC_CHECK_LAUNCH("order3");
+    }
+    tc3::PairArgs a{};
+    a.B = B; a.P = P; a.Kpad = pad_k(P);
+    a.t_over_T = t_over_T;
+    a.params = params;
+    a.frames_in = bt->frames; a.tors_in = bt->torsions; a.mask = bt->mask;
+    a.pocket_frames = bt->pocket_frames; a.pocket_cls = w.cls; a.cls_stride = w.cls_stride; a.pk32 = w.pk32;
+    a.aij = w.aij1; a.wimage = w.wimage;
+    a.order = w.order;
+    a.frames_out = frames1; a.tors_out = tors1; a.ssum_out = w.ssum;
+    a.rowstat = rowstat1; a.logit_out = logits1;
+    int rc = launch_pair3<0, TERMS>(a, d, stream);
+    if (rc != 0) return rc;
+    {
+        tc3::NodeMid3Args n{w.nm_image, B, P, t_over_T, w.ssum, bt->features, bt->mask, w.aij2, feat1_out, msum_out};
+        const int grid = (B * kN + 127) / 128;
+        tc3::node_mid3_kernel<TERMS><<<grid, 128, tc3::Nm3<TERMS>::BYTES, stream>>>(n);
+        PMHC_CHECK_LAUNCH("node_mid3");
+    }
+    a.frames_in = frames1; a.tors_in = tors1;
+    a.aij = w.aij2; a.wimage = w.wimage + w.image_stride;
+    a.frames_out = out_frames; a.tors_out = out_torsions; a.ssum_out = nullptr;
+    a.rowstat = rowstat2; a.logit_out = logits2;
+    return launch_pair3<1, TERMS>(a, d, stream);
+}
+
+int forward_tc3(int terms, const float* params, const PmhcBatch* bt, float t_over_T, float* frames1, float* tors1, float* out_frames,
+                float* out_torsions, float* feat1_out, float* msum_out, float* rowstat1, float* rowstat2, float* logits1, float* logits2,
+                void* ws, cudaStream_t stream, bool reuse_pocket_cache) {
+    if (terms == 2)
+        return forward_tc3_impl<2>(params, bt, t_over_T, frames1, tors1, out_frames, out_torsions, feat1_out, msum_out, rowstat1, rowstat2,
+                                   logits1, logits2, ws, stream, reuse_pocket_cache);
+    return forward_tc3_impl<1>(params, bt, t_over_T, frames1, tors1, out_frames, out_torsions, feat1_out, msum_out, rowstat1, rowstat2,
+                               logits1, logits2, ws, stream, reuse_pocket_cache);
+}
+
+}  // namespace pmhc

@@ -131,8 +131,10 @@ class Model(torch.nn.Module):
         self.gnn2 = EGNNLayer(I, E, 1, M)
         self.act = torch.nn.ReLU()
         self.T = T
-        # arithmetic of the two dense per-pair contractions: "fp32" (FFMA, <= 1e-4 parity) or "bf16" (tcgen05 tensor
-        # cores, bf16 operands / fp32 accumulate, <= 1e-2); everything else is fp32 in both modes
+        # arithmetic of the dense per-pair contractions: "fp32" (FFMA, <= 1e-4 parity), "tc32" (tcgen05 tensor cores, operands as
+        # fp16 hi + lo terms, three MMAs per contraction: fp32-class, holds on the shipped model.pth), "fp16" (same kernels, single
+        # fp16 terms) or "bf16" (second-generation tcgen05 kernels, bf16 operands, <= 1e-2 on well-conditioned weights only);
+        # geometry, softmax and the frame / torsion updates are fp32 in every mode
         self.precision = "fp32"
         # arithmetic of the backward's contractions: None = follow `precision` ("bf16" -> TF32 tensor-core backward, same
         # 1e-2 class as the tensor-core forward), or "fp32" / "bf16" to choose it independently of the forward
@@ -191,11 +193,10 @@ class Model(torch.nn.Module):
             raise ValueError(f"Model.precision must be one of {sorted(_lib.PRECISIONS)}, got {self.precision!r}") from None
 
     def backward_precision_code(self) -> int:
-        mode = self.precision if self.backward_precision is None else self.backward_precision
-        try:
-            return _lib.PRECISIONS[mode]
-        except KeyError:
-            raise ValueError(f"Model.backward_precision must be None or one of {sorted(_lib.PRECISIONS)}, got {mode!r}") from None
+        mode = _lib.BACKWARD_OF.get(self.precision, self.precision) if self.backward_precision is None else self.backward_precision
+        if mode not in ("fp32", "bf16"):
+            raise ValueError(f"Model.backward_precision must be None, 'fp32' or 'bf16', got {mode!r}")
+        return _lib.PRECISIONS[mode]
 
     # ---- forward -----------------------------------------------------------------------------------------
     def forward(self, batch: Dict[str, Union[torch.Tensor, Rigid]], t: int) -> Dict[str, Union[Rigid, torch.Tensor]]:
