@@ -9,7 +9,8 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmhc_b200.so")
+# development: PMHC_B200_LIB points at an alternative build of the same library (A/B experiments on the GPU box)
+LIB_PATH = os.environ.get("PMHC_B200_LIB") or os.path.join(_HERE, "libpmhc_b200.so")
 
 N = 16          # PMHC_N
 NFEAT = 22      # PMHC_NFEAT

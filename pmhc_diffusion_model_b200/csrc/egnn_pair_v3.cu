@@ -107,7 +107,8 @@ struct Map {
     int total_bytes;
 };
 // MISC floats
-constexpr int MS_ATT2 = 0, MS_TRN2 = 64, MS_B2ND = 128, MS_TCONST = 144, MS_TIME_I = 208, MS_TIME_J = 272, MS_FLOATS = 336;
+constexpr int MS_ATT2 = 0, MS_TRN2 = 64, MS_B2ND = 128, MS_TCONST = 144, MS_TIME_I = 208, MS_TIME_J = 272, MS_PKATT = 336, MS_FLOATS = 592;
+// PKATT: per attention hidden unit {w_d, w_q, bias (+ W b2), attention_mlp.2 weight}
 // B2ND: [0] attention_mlp.2.bias, [1,5) rotation_mlp.2.bias, [5,12) torsion_mlp.2.bias, [12] translation_mlp.2.bias
 
 template <int TERMS>
@@ -202,6 +203,8 @@ __global__ void __launch_bounds__(256) weight_image3_kernel(const float* __restr
         for (int m = 0; m < 64; ++m) bacc += (double)w[m] * (double)msg2b[m];   // message bias folded in: W_h b2
         const float bias = (float)bacc;
         if (h == 0) {
+            float* pk = reinterpret_cast<float*>(img + M.MISC) + MS_PKATT + 4 * n;
+            pk[0] = w[64]; pk[1] = w[65]; pk[2] = bias; pk[3] = params[param_offset(L, ATT2_W) + n];
             // attention extras, bf16 three-term splits.  Pair side: [dh dh dm dh dm dl | qh qh qm qh qm ql | 1 1 1 0]
             float s[2][3];
             for (int q = 0; q < 2; ++q) {
@@ -364,7 +367,7 @@ __device__ __forceinline__ void write_sel(const Engine& E, const PairRef& pr, fl
 
 // ---- extras blocks in tensor memory (A operand, 16 K elements = 8 columns) ----
 // attention: -d2 and (q_i.q_j)^2 as bf16 three-term splits, 1.0 for the bias terms (model.py:238-242)
-__device__ __forceinline__ void attention_extras(const Engine& E, const PairRef& pr) {
+__device__ __forceinline__ void attention_extras(const Engine& E, const PairRef& pr, float& nd2_out, float& qd_out) {
     const float4* Q = reinterpret_cast<const float4*>(E.es + E.M.Q);
     const float4* X = reinterpret_cast<const float4*>(E.es + E.M.X);
     const float4 qi = Q[pr.i], qj = Q[pr.j < 0 ? pr.i : pr.j], xi = X[pr.i], xj = X[pr.j < 0 ? pr.i : pr.j];
@@ -372,6 +375,11 @@ __device__ __forceinline__ void attention_extras(const Engine& E, const PairRef&
     const float nd2 = -(rx * rx + ry * ry + rz * rz);
     const float dq = qi.x * qj.x + qi.y * qj.y + qi.z * qj.z + qi.w * qj.w;
     const float qd = dq * dq;
+    nd2_out = nd2;
+    qd_out = qd;
+#ifdef PMHC_V3_ATT_GEO_EPILOGUE
+    return;
+#endif
     const float dh = tc::bf16_round(nd2), d1 = nd2 - dh, dm = tc::bf16_round(d1), dl = d1 - dm;
     const float qh = tc::bf16_round(qd), q1 = qd - qh, qm = tc::bf16_round(q1), ql = q1 - qm;
     uint32_t x[8];
@@ -423,6 +431,28 @@ __device__ __forceinline__ float dot_relu64(const Engine& E, int buf, int misc_o
         }
     }
     return (s0 + s1) + (s2 + s3);
+}
+
+// attention logit with the geometry inputs and the bias added in fp32 after the contraction (model.py:238-243):
+// sum_n att2[n] relu(acc[n] + w_d[n] (-d2) + w_q[n] qdot2 + b[n])
+__device__ __forceinline__ float att_logit_geo(const Engine& E, int buf, float nd2, float qd) {
+    const float4* pk = reinterpret_cast<const float4*>(E.smem + E.M.MISC) + MS_PKATT / 4;
+    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tc::tmem_ld32_nowait(E.tmem + E.lane_base + buf + 32 * half, v);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+            const float4 a = pk[32 * half + c], b = pk[32 * half + c + 1];
+            const float h0 = fmaf(a.x, nd2, fmaf(a.y, qd, a.z + __uint_as_float(v[c])));
+            const float h1 = fmaf(b.x, nd2, fmaf(b.y, qd, b.z + __uint_as_float(v[c + 1])));
+            s0 = fmaf(a.w, fmaxf(h0, 0.0f), s0);
+            s1 = fmaf(b.w, fmaxf(h1, 0.0f), s1);
+        }
+    }
+    return s0 + s1;
 }
 
 // ---- hidden units of one head (64 fp32 columns) -> relu -> fp16 terms, in place.  Elements [32 h, 32 h + 32) of the hi term go
@@ -619,7 +649,13 @@ __device__ inline ComplexInfo setup_engine(Engine& E, int b) {
     return ci;
 }
 
+#ifdef PMHC_V3_PRECISE_MATH
+__device__ __forceinline__ float fast_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float soft_exp(float x) { return expf(x); }
+#else
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float soft_exp(float x) { return __expf(x); }
+#endif
 
 template <int LAYER, int TERMS>
 __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
@@ -673,7 +709,9 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         const uint32_t cta = Engine::opaque(E.smem_u), esu = Engine::opaque(E.es_u), tm = Engine::opaque(E.tmem);
                         if (LAYER == 0) mma_sums<TERMS>(E, esu, tm);
                         mma_head_main<TERMS>(E, cta, esu, tm, 0, TM_X);
+#ifndef PMHC_V3_ATT_GEO_EPILOGUE
                         mma_extras(tm + TM_X, tm + TM_EXA, cta + M.WXA, idb);
+#endif
                         E.commit(B_ATT);
                         mma_head_main<TERMS>(E, cta, esu, tm, 2, TM_Z);
 #pragma unroll
@@ -773,9 +811,10 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     pr.j = e < L - 1 ? I[IN_ROWS + (e < rr ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
 
                     stage_half<LAYER, TERMS>(E, pr, b);
+                    float nd2 = 0.0f, qd = 0.0f;
                     if (grpA) {
                         if (LAYER == 0) write_sel(E, pr, 1.0f);
-                        attention_extras(E, pr);
+                        attention_extras(E, pr, nd2, qd);
                     } else {
                         rotation_extras(E, pr);
                     }
@@ -789,7 +828,11 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                             write_sel(E, pr, 0.0f);
                             add_tile_sums();
                         }
+#ifdef PMHC_V3_ATT_GEO_EPILOGUE
+                        const float logit = att_logit_geo(E, TM_X, nd2, qd) + misc[MS_B2ND + 0];
+#else
                         const float logit = dot_relu64(E, TM_X, MS_ATT2) + misc[MS_B2ND + 0];   // model.py:241-243
+#endif
                         E.request(NB_REQ_A2, kGrp);
                         E.wait(B_ROT);
                         convert_hidden<TERMS>(E, TM_Y);
@@ -832,7 +875,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     E.sync_eng();       // every row's tile maximum and every logit are in shared memory
                     {
                         const float m_new = fmaxf(Mrow[par * kN + rl], dec_max(Mtile[par * kN + rl]));
-                        const float p = pr.active ? __expf(Lg[r] - m_new) : 0.0f;
+                        const float p = pr.active ? soft_exp(Lg[r] - m_new) : 0.0f;
                         float* out = Out + r * kOutPerPair;
                         if (grpA) {
                             out[0] = p;
@@ -857,7 +900,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                             if (k16 == 0 && c < kOutPerPair) {
                                 const float m_old = Mrow[par * kN + s];
                                 const float m_new = fmaxf(m_old, dec_max(Mtile[par * kN + s]));
-                                const float f = m_old == -INFINITY ? 0.0f : __expf(m_old - m_new);
+                                const float f = m_old == -INFINITY ? 0.0f : soft_exp(m_old - m_new);
                                 St[s * 16 + c] = fmaf(St[s * 16 + c], f, acc);
                             }
                         }

@@ -1,37 +1,51 @@
-"""`MetricsRecord` — drop-in for diffusion/tools/metrics.py:8-40.
-
-Same API and CSV format; the per-key sums stay on the device (the reference does a `.item()` host sync per
-key per batch, metrics.py:17) and are read back once, in `mean()`.
+"""`MetricsRecord` — same interface and CSV layout as diffusion/tools/metrics.py:8-40 (`add_batch`, `mean`, `save`;
+header `epoch,<keys...>`, one row per epoch, three decimals), different mechanics: the running totals of all keys live in
+ONE device tensor that a batch is added to with a single stacked reduction, and nothing is read back to the host before
+`mean()` / `save()` (the reference syncs once per key per batch, metrics.py:17).
 """
-import csv
 import os
-from typing import Dict
+from typing import Dict, List, Optional
 
 import torch
 
 
 class MetricsRecord:
     def __init__(self):
-        self._sums = {}
-        self._size = 0
+        self.keys: List[str] = []                    # column order = order of first appearance, as in the reference's dict
+        self.totals: Optional[torch.Tensor] = None   # [len(keys)] running sums on the device of the first batch
+        self.count = 0                               # complexes seen
 
-    def add_batch(self, results: Dict[str, torch.Tensor]):
-        batch_size = 0
-        for key, data in results.items():
-            s = data.detach().sum()
-            self._sums[key] = self._sums[key] + s if key in self._sums else s
-            batch_size = data.shape[0]
-        self._size += batch_size
+    def add_batch(self, results: Dict[str, torch.Tensor]) -> None:
+        names = list(results)
+        if names != self.keys[:len(names)] or len(names) != len(self.keys):
+            self._grow(names, next(iter(results.values())))
+        per_key = torch.stack([results[k].detach().to(self.totals.dtype).sum() for k in self.keys if k in results])
+        if len(names) == len(self.keys):
+            self.totals += per_key
+        else:                                        # a batch that reports only some of the keys
+            index = torch.tensor([self.keys.index(k) for k in names], device=self.totals.device)
+            self.totals.index_add_(0, index, per_key)
+        self.count += int(next(iter(results.values())).shape[0])
+
+    def _grow(self, names: List[str], like: torch.Tensor) -> None:
+        fresh = [k for k in names if k not in self.keys]
+        if not fresh:
+            return
+        extra = torch.zeros(len(fresh), dtype=torch.float64, device=like.device)
+        self.totals = extra if self.totals is None else torch.cat((self.totals, extra))
+        self.keys.extend(fresh)
 
     def mean(self) -> Dict[str, float]:
-        return {key: float(sum_) / self._size for key, sum_ in self._sums.items()}
+        if self.totals is None:
+            return {}
+        values = (self.totals / max(self.count, 1)).tolist()      # the one device -> host read
+        return dict(zip(self.keys, values))
 
-    def save(self, path: str, epoch_number: int):
-        keys = list(self._sums.keys())
-        add_header = not os.path.isfile(path)
-        with open(path, "at") as f:
-            w = csv.writer(f, delimiter=",")
-            if add_header:
-                w.writerow(["epoch"] + keys)
-            m = self.mean()
-            w.writerow([epoch_number] + [round(m[key], 3) for key in keys])
+    def save(self, path: str, epoch_number: int) -> None:
+        means = self.mean()
+        lines = []
+        if not os.path.isfile(path):
+            lines.append(",".join(["epoch"] + self.keys))
+        lines.append(",".join([str(epoch_number)] + [repr(round(means[k], 3)) for k in self.keys]))
+        with open(path, "a", newline="") as out:
+            out.write("\r\n".join(lines) + "\r\n")       # csv.writer's default line terminator, as the reference's file has
