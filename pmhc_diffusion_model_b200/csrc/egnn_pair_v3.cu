@@ -42,9 +42,8 @@ constexpr int kEngCols = 256;                   // TMEM columns per engine
 // TMEM columns of one engine: three 64-column head buffers, three 8-column extras blocks (16 K elements each), the two
 // second-layer outputs; layer 1's per-tile message column sums share the second-layer columns (read before those are issued)
 constexpr int TM_X = 0, TM_Y = 64, TM_Z = 128, TM_EXA = 192, TM_EXR = 200, TM_EXO = 208, TM_D3R = 216, TM_D3T = 232, TM_SUM = 216;
-// mbarriers of one engine: each of the first six completes exactly once per pair tile
-enum { B_ATT = 0, B_TOR, B_ROT, B_TRN, B_D3T, B_D3R, B_SUM, B_LOAD, kBars };
-constexpr uint32_t kTileBars = 0x3Fu;
+// mbarriers of one engine: each of the first four completes exactly once per pair tile
+enum { B_H1 = 0, B_TRN, B_D3T, B_D3R, B_SUM, B_LOAD, kBars };   // B_H1: attention, rotation and torsion hidden layers (one N = 192 contraction)
 // named barriers of one engine
 enum { NB_REQ_ALL = 0, NB_REQ_A2, NB_REQ_B3, NB_REQ_A4, NB_ENG, NB_ENG_ALL, kNamed };
 
@@ -114,7 +113,7 @@ template <int TERMS>
 __host__ __device__ inline Map make_map(int Kpad, bool layer1) {
     Map m;
     int o = 0;
-    m.WF = o;   o += 4 * TERMS * 8192;     // folded head weights [64 n][64 k] fp16 SW128, (head, term)
+    m.WF = o;   o += 4 * TERMS * 8192;     // folded head weights fp16 SW128, per term one [256 n][64 k] tile: rows attention | rotation | torsion | translation
     m.W3 = o;   o += 2 * TERMS * 2048;     // second layers [16 n][64 k] fp16 SW128: (rotation | torsion, term)
     m.WXA = o;  o += 2048;                 // attention extras [64 n][16 k] bf16, K-major core matrices
     m.WXR = o;  o += 2048;                 // rotation extras, fp16
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__(256) weight_image3_kernel(const float* __restr
         const float* w = head[h] + n * ldh[h];
         double acc = 0.0;
         for (int m = 0; m < 64; ++m) acc += (double)w[m] * (double)msg2[m * 64 + k];
-        put_split_f16(M.WF + h * TERMS * 8192, 8192, tc::sw128_offset(n, k), (float)acc);
+        put_split_f16(M.WF + h * 8192, 4 * 8192, tc::sw128_offset(n, k), (float)acc);
     }
     for (int idx = tid; idx < 2 * 16 * 64; idx += nthr) {
         const int hh = idx >> 10, n = (idx >> 6) & 15, k = idx & 63;
@@ -280,7 +279,7 @@ struct Engine {
     __device__ __forceinline__ void sync_eng() const { tc::named_bar_sync(nb(NB_ENG), kEngThreads); }
     __device__ __forceinline__ void sync_all() const { tc::named_bar_sync(nb(NB_ENG_ALL), kEngThreads + 32); }
     __device__ __forceinline__ void wait(int k) {
-        tc::mbar_wait(bar + k, (phase >> k) & 1u);
+        tc::mbar_wait_suspend(bar + k, (phase >> k) & 1u);
         phase ^= 1u << k;
         tc::fence_after_thread_sync();
     }
@@ -310,21 +309,29 @@ __device__ __forceinline__ float dec_max(int i) { return __int_as_float(i >= 0 ?
 constexpr int kEncNegInf = (int)0x807FFFFF;   // enc_max(-inf)
 
 // ---- staging: this thread's 32 features of m1 = relu(A_i + A_j + W_e) -> the pair tile(s) ----
+// load_aj: the pocket neighbour's A_j row from L2 / HBM (issued a phase ahead of its use: the rows of a 1 000-complex batch are
+// 20 MB per layer, so these loads see DRAM latency); peptide neighbours are read from shared memory in finish_stage.
+template <int LAYER>
+__device__ __forceinline__ void load_aj(const Engine& E, const PairRef& pr, int b, float4 (&v)[8]) {
+    if (pr.j >= kN) {
+        const float4* src = reinterpret_cast<const float4*>(E.a.pk32 + (((size_t)b * 2 + LAYER) * E.a.P + (pr.j - kN)) * kHid) + 8 * E.grp;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
 template <int LAYER, int TERMS>
-__device__ __forceinline__ void stage_half(const Engine& E, const PairRef& pr, int b) {
+__device__ __forceinline__ void finish_stage(const Engine& E, const PairRef& pr, float4 (&v)[8]) {
     const int r = E.r, g = E.grp, i = pr.i, j = pr.j;
     const float4* ai = reinterpret_cast<const float4*>(E.es + E.M.AI) + i * 16;
-    float4 v[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) v[c] = ai[(8 * g + c) ^ (i & 7)];
-    if (j >= kN) {
-        const float4* src = reinterpret_cast<const float4*>(E.a.pk32 + (((size_t)b * 2 + LAYER) * E.a.P + (j - kN)) * kHid) + 8 * g;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float4 w = __ldg(src + c);
-            v[c].x += w.x; v[c].y += w.y; v[c].z += w.z; v[c].w += w.w;
-        }
-    } else if (j >= 0) {
+    for (int c = 0; c < 8; ++c) {
+        const float4 w = ai[(8 * g + c) ^ (i & 7)];
+        v[c].x += w.x; v[c].y += w.y; v[c].z += w.z; v[c].w += w.w;
+    }
+    if (j >= 0 && j < kN) {
         const float4* aj = reinterpret_cast<const float4*>(E.es + E.M.AJS) + j * 16;
         const int rel = kN - 1 + i - j;
         const float4* we = reinterpret_cast<const float4*>(E.smem + E.M.WE) + rel * 16;
@@ -453,14 +460,17 @@ __device__ __forceinline__ constexpr int hid_col(int s) { return 8 * s + 16 * (s
 // error of ~1 ulp of the running sum is paid per step.  The two cross products are 2^-11 of the main one: issued FIRST they
 // truncate at that magnitude, and only the four steps of hi.hi (and the extras block after them) truncate at full magnitude
 // — 2.8x less error on the shipped fixtures than hi.hi first, for free.
+// Shape: `nheads` consecutive heads starting at `h0` are ONE contraction of N = 64 nheads columns (head buffers and weight rows
+// are adjacent).  With both operands in shared memory an N = 64 step reads 6 KB for 32 tensor-pipe cycles, 192 B / cycle —
+// more than the 128 B / cycle shared memory delivers; at N = 192 the pair tile is read once for three heads: 10 KB per 96 cycles.
 template <int TERMS>
-__device__ __forceinline__ void mma_head_main(const Engine& E, uint32_t cta, uint32_t esu, uint32_t tm, int h, int dst) {
-    constexpr uint32_t id = tc::idesc_f16_f32(128, 64);
+__device__ __forceinline__ void mma_heads_main(const Engine& E, uint32_t cta, uint32_t esu, uint32_t tm, int h0, int nheads, int dst) {
+    const uint32_t id = tc::idesc_f16_f32(128, 64 * nheads);
     const uint64_t a_hi = tc::smem_desc_sw128(esu + E.M.A1);
-    const uint64_t w_hi = tc::smem_desc_sw128(cta + E.M.WF + h * TERMS * 8192);
+    const uint64_t w_hi = tc::smem_desc_sw128(cta + E.M.WF + h0 * 8192);
     if (TERMS > 1) {
         const uint64_t a_lo = tc::smem_desc_sw128(esu + E.M.A1 + 16384);
-        const uint64_t w_lo = tc::smem_desc_sw128(cta + E.M.WF + h * TERMS * 8192 + 8192);
+        const uint64_t w_lo = tc::smem_desc_sw128(cta + E.M.WF + 4 * 8192 + h0 * 8192);
 #pragma unroll
         for (int s = 0; s < 4; ++s) tc::mma_bf16(tm + dst, a_lo + 2 * s, w_hi + 2 * s, id, s > 0);
 #pragma unroll
@@ -680,20 +690,16 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     E.serve(NB_REQ_ALL, kEngThreads, [&] {
                         const uint32_t cta = Engine::opaque(E.smem_u), esu = Engine::opaque(E.es_u), tm = Engine::opaque(E.tmem);
                         if (LAYER == 0) mma_sums<TERMS>(E, esu, tm);
-                        mma_head_main<TERMS>(E, cta, esu, tm, 0, TM_X);
+                        mma_heads_main<TERMS>(E, cta, esu, tm, 0, 3, TM_X);     // attention -> X, rotation -> Y, torsion -> Z
                         mma_extras(tm + TM_X, tm + TM_EXA, cta + M.WXA, idb);
-                        E.commit(B_ATT);
-                        mma_head_main<TERMS>(E, cta, esu, tm, 2, TM_Z);
+                        mma_extras(tm + TM_Y, tm + TM_EXR, cta + M.WXR, idf);
 #pragma unroll
                         for (int u = 0; u < TERMS; ++u) mma_extras(tm + TM_Z, tm + TM_EXO, esu + M.TT + u * 2048, idf);
-                        E.commit(B_TOR);
-                        mma_head_main<TERMS>(E, cta, esu, tm, 1, TM_Y);
-                        mma_extras(tm + TM_Y, tm + TM_EXR, cta + M.WXR, idf);
-                        E.commit(B_ROT);
+                        E.commit(B_H1);
                     });
                     E.serve(NB_REQ_A2, kGrp, [&] {   // group A has read the attention hidden units (and the tile sums): X is free
                         const uint32_t cta = Engine::opaque(E.smem_u), esu = Engine::opaque(E.es_u), tm = Engine::opaque(E.tmem);
-                        mma_head_main<TERMS>(E, cta, esu, tm, 3, TM_X);
+                        mma_heads_main<TERMS>(E, cta, esu, tm, 3, 1, TM_X);
 #pragma unroll
                         for (int u = 0; u < TERMS; ++u) mma_extras(tm + TM_X, tm + TM_EXO, cta + M.WXT + u * 2048, idf);
                         E.commit(B_TRN);
@@ -766,21 +772,33 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                 // pair g of the part = (row rl = g / W, entry e = g % W): peptide neighbours first, then the valid pocket slots
                 const int adv_q = W > 0 ? kTile / W : 0, adv_r = W > 0 ? kTile - adv_q * W : 0;
                 int cur_rl = W > 0 ? r / W : 0, cur_e = W > 0 ? r - cur_rl * W : 0;
-                int par = 0;   // tile parity: which copy of Mrow / Mtile is current
-                for (int t = 0; t < pl.ntiles; ++t) {
-                    const int g0 = t * kTile;
-                    PairRef pr;
-                    pr.active = g0 + r < G;
+                const int last_rl = W > 0 ? (G - 1) / W : 0, last_e = W > 0 ? (G - 1) - last_rl * W : 0;
+                auto decode = [&](int t, int& rl_out) {     // tile t's pair of this thread; advances the running (row, entry)
+                    PairRef p;
+                    p.active = t * kTile + r < G;
                     int rl = cur_rl, e = cur_e;
-                    if (!pr.active) { rl = (G - 1) / W; e = (G - 1) - rl * W; }   // idle lanes of the last tile repeat its last pair
+                    if (!p.active) { rl = last_rl; e = last_e; }   // idle lanes of the last tile repeat its last pair
                     cur_rl += adv_q;
                     cur_e += adv_r;
                     if (cur_e >= W) { cur_e -= W; ++cur_rl; }
                     const int rr = pl.rbeg + rl;
-                    pr.i = I[IN_ROWS + rr];
-                    pr.j = e < L - 1 ? I[IN_ROWS + (e < rr ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
-
-                    stage_half<LAYER, TERMS>(E, pr, b);
+                    p.i = I[IN_ROWS + rr];
+                    p.j = e < L - 1 ? I[IN_ROWS + (e < rr ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
+                    rl_out = rl;
+                    return p;
+                };
+                int par = 0;             // tile parity: which copy of Mrow / Mtile is current
+                int row0 = 0, off0 = 0;  // the tile starts `off0` pairs into row `row0` of the part (same in every thread)
+                int rl = 0, rl_next = 0;
+                PairRef pr{}, nxt{};
+                float4 aj[8];
+                if (pl.ntiles > 0) {
+                    pr = decode(0, rl);
+                    load_aj<LAYER>(E, pr, b, aj);
+                }
+                for (int t = 0; t < pl.ntiles; ++t) {
+                    const int ntile = G - t * kTile < kTile ? G - t * kTile : kTile;
+                    finish_stage<LAYER, TERMS>(E, pr, aj);
                     if (grpA) {
                         if (LAYER == 0) write_sel(E, pr, 1.0f);
                         attention_extras(E, pr);
@@ -789,25 +807,26 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     }
                     tc::fence_proxy_async_smem();
                     E.request(NB_REQ_ALL, kEngThreads);
+                    const bool more = t + 1 < pl.ntiles;
+                    if (more) nxt = decode(t + 1, rl_next);
 
-                    float o[10];        // group A: logit, global delta quaternion; group B: delta angles, scale (x_i - x_j)
+                    float* out = Out + r * kOutPerPair;
+                    E.wait(B_H1);
                     if (grpA) {
-                        E.wait(B_ATT);
                         if (LAYER == 0) {
                             write_sel(E, pr, 0.0f);
                             add_tile_sums();
                         }
                         const float logit = dot_relu64(E, TM_X, MS_ATT2) + misc[MS_B2ND + 0];   // model.py:241-243
                         E.request(NB_REQ_A2, kGrp);
-                        E.wait(B_ROT);
                         convert_hidden<TERMS>(E, TM_Y);
                         E.request(NB_REQ_A4, kGrp);
-                        o[0] = logit;
                         if (pr.active) {
                             Lg[r] = logit;
                             atomicMax(Mtile + par * kN + rl, enc_max(logit));
                             if (lsave != nullptr) lsave[pr.i * a.Kpad + pr.j] = logit;
                         }
+                        if (more) load_aj<LAYER>(E, nxt, b, aj);     // next tile's neighbour rows: in flight under the tail of this one
                         E.wait(B_D3R);
                         float d[4];
                         tc::tmem_ld4(E.tmem + E.lane_base + TM_D3R, d);
@@ -818,63 +837,59 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         const Quat dl{fast_sigmoid(d[0] + misc[MS_B2ND + 1]), fast_sigmoid(d[1] + misc[MS_B2ND + 2]),
                                       fast_sigmoid(d[2] + misc[MS_B2ND + 3]), fast_sigmoid(d[3] + misc[MS_B2ND + 4])};   // never normalised (T5)
                         const Quat dg = qmul(qj, qmul(dl, qinvj));                                  // model.py:296
-                        o[1] = dg.w; o[2] = dg.x; o[3] = dg.y; o[4] = dg.z;
-                        E.phase ^= (1u << B_TOR) | (1u << B_TRN) | (1u << B_D3T);   // completions this group does not wait for
+                        out[1] = dg.w; out[2] = dg.x; out[3] = dg.y; out[4] = dg.z;
+                        E.phase ^= (1u << B_TRN) | (1u << B_D3T);   // completions this group does not wait for
                     } else {
-                        E.wait(B_TOR);
                         convert_hidden<TERMS>(E, TM_Z);
                         E.request(NB_REQ_B3, kGrp);
                         E.wait(B_TRN);
                         const float sc = dot_relu64(E, TM_X, MS_TRN2) + misc[MS_B2ND + 12];       // model.py:325-327
-                        tc::fence_before_thread_sync();
+                        if (more) load_aj<LAYER>(E, nxt, b, aj);
                         E.wait(B_D3T);
                         float d[8];
                         tc::tmem_ld8(E.tmem + E.lane_base + TM_D3T, d);
 #pragma unroll
-                        for (int c = 0; c < PMHC_NTORS; ++c) o[c] = d[c] + misc[MS_B2ND + 5 + c];
+                        for (int c = 0; c < PMHC_NTORS; ++c) out[5 + c] = d[c] + misc[MS_B2ND + 5 + c];
                         const float4 xi = X[pr.i], xj = X[pr.j];
-                        o[7] = sc * (xi.x - xj.x); o[8] = sc * (xi.y - xj.y); o[9] = sc * (xi.z - xj.z);   // model.py:331
-                        E.phase ^= (1u << B_ATT) | (1u << B_ROT) | (1u << B_D3R);
+                        out[12] = sc * (xi.x - xj.x); out[13] = sc * (xi.y - xj.y); out[14] = sc * (xi.z - xj.z);   // model.py:331
+                        E.phase ^= 1u << B_D3R;
                     }
                     tc::fence_before_thread_sync();
-                    E.sync_eng();       // every row's tile maximum and every logit are in shared memory
+                    E.sync_eng();       // the tile's logits, row maxima and head outputs are in shared memory
                     {
-                        const float m_new = fmaxf(Mrow[par * kN + rl], dec_max(Mtile[par * kN + rl]));
-                        const float p = pr.active ? soft_exp(Lg[r] - m_new) : 0.0f;
-                        float* out = Out + r * kOutPerPair;
-                        if (grpA) {
-                            out[0] = p;
-                            out[1] = p * o[1]; out[2] = p * o[2]; out[3] = p * o[3]; out[4] = p * o[4];
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 10; ++c) out[5 + c] = p * o[c];
-                        }
-                    }
-                    E.sync_eng();       // the tile's weighted outputs are in shared memory
-                    {
-                        // column c of the running sums: 16 lanes walk each row segment of the tile, then the state is rescaled and updated
+                        // streaming softmax: column c of the running sums (0: sum of weights, 1..14: weighted head outputs); 16 lanes
+                        // walk each row segment of the tile, then the row's state is rescaled to the new maximum and updated
                         const int c = et >> 4, k16 = et & 15;
-                        const int rl0 = g0 / W, g1 = (g0 + kTile < G ? g0 + kTile : G) - 1, rl1 = g1 / W;
-                        for (int s = rl0; s <= rl1; ++s) {
-                            const int lo = (s * W > g0 ? s * W : g0) - g0, hi = ((s + 1) * W - 1 < g1 ? (s + 1) * W - 1 : g1) - g0;
+                        int s_row = row0, pos = 0, len = W - off0 < ntile ? W - off0 : ntile;
+                        while (pos < ntile) {
+                            const float m_old = Mrow[par * kN + s_row];
+                            const float m_new = fmaxf(m_old, dec_max(Mtile[par * kN + s_row]));
                             float acc = 0.0f;
                             if (c < kOutPerPair)
-                                for (int p = lo + k16; p <= hi; p += 16) acc += Out[p * kOutPerPair + c];
+                                for (int p = pos + k16; p < pos + len; p += 16) {
+                                    const float wgt = soft_exp(Lg[p] - m_new);
+                                    acc = c == 0 ? acc + wgt : fmaf(wgt, Out[p * kOutPerPair + c], acc);
+                                }
 #pragma unroll
                             for (int sh = 8; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
                             if (k16 == 0 && c < kOutPerPair) {
-                                const float m_old = Mrow[par * kN + s];
-                                const float m_new = fmaxf(m_old, dec_max(Mtile[par * kN + s]));
                                 const float f = m_old == -INFINITY ? 0.0f : soft_exp(m_old - m_new);
-                                St[s * 16 + c] = fmaf(St[s * 16 + c], f, acc);
+                                St[s_row * 16 + c] = fmaf(St[s_row * 16 + c], f, acc);
                             }
+                            pos += len;
+                            ++s_row;
+                            len = W < ntile - pos ? W : ntile - pos;
                         }
                         if (et < kN) {
                             Mrow[(par ^ 1) * kN + et] = fmaxf(Mrow[par * kN + et], dec_max(Mtile[par * kN + et]));
                             Mtile[(par ^ 1) * kN + et] = kEncNegInf;   // free since the previous tile; used by the next one
                         }
+                        off0 += kTile;
+                        while (off0 >= W) { off0 -= W; ++row0; }
                     }
                     par ^= 1;
+                    pr = nxt;
+                    rl = rl_next;
                     // (the next tile's request barrier orders these reads before the next writes of Out / Lg / Mtile)
                 }
                 E.sync_eng();
@@ -934,7 +949,9 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                             const int which = e - (npx + ci.nx + 1);
                             mult = (float)(which == 0 ? min(ci.c0, 1024) : ci.c0 - 1024);
                         }
-                        stage_half<LAYER, TERMS>(E, pr, b);
+                        float4 ajm[8];
+                        load_aj<LAYER>(E, pr, b, ajm);
+                        finish_stage<LAYER, TERMS>(E, pr, ajm);
                         if (grpA) write_sel(E, pr, mult);
                         tc::fence_proxy_async_smem();
                         E.request(NB_REQ_ALL, kEngThreads);

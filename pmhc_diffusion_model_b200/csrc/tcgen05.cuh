@@ -47,6 +47,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// same, parking the warp in the hardware wait (up to `ns` per attempt) instead of spinning on the barrier
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t ns = 20000u) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+            : "memory");
+    } while (!done);
+}
 
 // ---- fences ----
 // generic-proxy writes to shared memory (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
