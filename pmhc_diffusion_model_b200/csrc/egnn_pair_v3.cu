@@ -66,6 +66,7 @@ struct PairArgs {
     float* rowstat;                  // training only
     float* logit_out;                // training only: [B,16,Kpad]
     const int* order;                // [B] complexes by decreasing pair count (nullable)
+    long long* dbg;                  // development: clock64 stamps of CTA 0 / engine 0, lane 0 of group A ([0,256)) and B ([256,512))
 };
 
 // ---- work of one engine: complexes dealt round-robin over the engines, a partly filled last round split by peptide rows ----
@@ -636,6 +637,36 @@ __device__ inline ComplexInfo setup_engine(Engine& E, int b) {
 
 // (exact expf / division measured no different on the reference fixtures: the mode's error floor is the tensor core's
 // truncating fp32 accumulation, see mma_head_main)
+// The next complex of this engine: pull its inputs towards L2 while the current one is being processed (one 128-byte line per
+// thread: A_i | A_j rows, this layer's pocket rows, frames, torsions) — the set-up that follows then waits on L2, not on HBM.
+template <int LAYER>
+__device__ __forceinline__ void prefetch_complex(const Engine& E, int b) {
+    const PairArgs& a = E.a;
+    const int P = a.P;
+    const char* base;
+    int line = E.et;
+    int n = 2 * kN * 256 / 128;
+    if (line < n) base = reinterpret_cast<const char*>(a.aij + (size_t)b * 2 * kN * 64);
+    else {
+        line -= n; n = (P * 256) / 128;
+        if (line < n) base = reinterpret_cast<const char*>(a.pk32 + ((size_t)b * 2 + LAYER) * P * kHid);
+        else {
+            line -= n; n = (P * 28 + 127) / 128;
+            if (line < n) base = reinterpret_cast<const char*>(a.pocket_frames + (size_t)b * P * 7);
+            else {
+                line -= n; n = 4;
+                if (line < n) base = reinterpret_cast<const char*>(a.frames_in + (size_t)b * kN * 7);
+                else {
+                    line -= n; n = 7;
+                    if (line < n) base = reinterpret_cast<const char*>(a.tors_in + (size_t)b * kN * 14);
+                    else return;
+                }
+            }
+        }
+    }
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)line * 128));
+}
+
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float soft_exp(float x) { return __expf(x); }
 
@@ -743,10 +774,20 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
             const float4* Q = reinterpret_cast<const float4*>(es + M.Q);
             const float4* X = reinterpret_cast<const float4*>(es + M.X);
 
+            int ts_n = 0;
+            const bool ts_on = a.dbg != nullptr && blockIdx.x == 0 && eng == 0 && r == 0;
+            long long* ts_buf = a.dbg + (grpA ? 0 : 256);
+#define PMHC_TS(tag) do { if (ts_on && ts_n < 250) { ts_buf[ts_n++] = (clock64() << 8) | (tag); } } while (0)
             Work wk;
             for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.n_eng, a.B, a.order, wk); ++k) {
                 const int b = wk.b;
+                PMHC_TS(1);
                 const ComplexInfo ci = setup_engine<LAYER, TERMS>(E, b);
+                PMHC_TS(2);
+                {
+                    Work wn;
+                    if (get_work(k + 1, blockIdx.x, eng, gridDim.x, a.n_eng, a.B, a.order, wn)) prefetch_complex<LAYER>(E, wn.b);
+                }
                 const Plan pl = make_plan(ci, wk, LAYER == 0);
                 const int L = pl.L, W = pl.W, G = pl.G;
                 float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
@@ -787,31 +828,79 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     rl_out = rl;
                     return p;
                 };
-                int par = 0;             // tile parity: which copy of Mrow / Mtile is current
-                int row0 = 0, off0 = 0;  // the tile starts `off0` pairs into row `row0` of the part (same in every thread)
+                // Software pipeline over the tiles of the part:
+                //   top of iteration t : tile t's operands are staged -> request its first contraction; while the tensor core works, merge
+                //                        tile t - 1's outputs into the running softmax state
+                //   after H1(t)        : head epilogues of tile t; in the shadow of the second-layer contractions each group stages ITS
+                //                        half of tile t + 1 (the pair tile is free once the translation head has read it)
+                int par = 0;             // parity of the tile whose outputs are being produced: its copy of Mrow / Mtile
+                int row0 = 0, off0 = 0;  // the tile being MERGED starts `off0` pairs into row `row0` of the part (same in every thread)
                 int rl = 0, rl_next = 0;
                 PairRef pr{}, nxt{};
-                float4 aj[8];
+                auto stage_tile = [&](const PairRef& p) {
+                    float4 aj[8];
+                    load_aj<LAYER>(E, p, b, aj);
+                    finish_stage<LAYER, TERMS>(E, p, aj);
+                    if (grpA) {
+                        if (LAYER == 0) write_sel(E, p, 1.0f);
+                        attention_extras(E, p);
+                    } else {
+                        rotation_extras(E, p);
+                    }
+                };
+                // streaming softmax: column c of the running sums (0: sum of weights, 1..14: weighted head outputs); 16 lanes walk each
+                // row segment of the tile, then the row's state is rescaled to the new maximum and updated
+                auto merge_tile = [&](int mt, int mpar) {
+                    const int ntile = G - mt * kTile < kTile ? G - mt * kTile : kTile;
+                    const int c = et >> 4, k16 = et & 15;
+                    int s_row = row0, pos = 0, len = W - off0 < ntile ? W - off0 : ntile;
+                    while (pos < ntile) {
+                        const float m_old = Mrow[mpar * kN + s_row];
+                        const float m_new = fmaxf(m_old, dec_max(Mtile[mpar * kN + s_row]));
+                        float acc = 0.0f;
+                        if (c < kOutPerPair)
+                            for (int p = pos + k16; p < pos + len; p += 16) {
+                                const float wgt = soft_exp(Lg[p] - m_new);
+                                acc = c == 0 ? acc + wgt : fmaf(wgt, Out[p * kOutPerPair + c], acc);
+                            }
+#pragma unroll
+                        for (int sh = 8; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+                        if (k16 == 0 && c < kOutPerPair) {
+                            const float f = m_old == -INFINITY ? 0.0f : soft_exp(m_old - m_new);
+                            St[s_row * 16 + c] = fmaf(St[s_row * 16 + c], f, acc);
+                        }
+                        pos += len;
+                        ++s_row;
+                        len = W < ntile - pos ? W : ntile - pos;
+                    }
+                    if (et < kN) {
+                        Mrow[(mpar ^ 1) * kN + et] = fmaxf(Mrow[mpar * kN + et], dec_max(Mtile[mpar * kN + et]));
+                        Mtile[(mpar ^ 1) * kN + et] = kEncNegInf;   // free since the tile before; the next tile's maxima go there
+                    }
+                    off0 += kTile;
+                    while (off0 >= W) { off0 -= W; ++row0; }
+                };
                 if (pl.ntiles > 0) {
                     pr = decode(0, rl);
-                    load_aj<LAYER>(E, pr, b, aj);
+                    stage_tile(pr);
                 }
                 for (int t = 0; t < pl.ntiles; ++t) {
-                    const int ntile = G - t * kTile < kTile ? G - t * kTile : kTile;
-                    finish_stage<LAYER, TERMS>(E, pr, aj);
-                    if (grpA) {
-                        if (LAYER == 0) write_sel(E, pr, 1.0f);
-                        attention_extras(E, pr);
-                    } else {
-                        rotation_extras(E, pr);
-                    }
+                    PMHC_TS(10);
                     tc::fence_proxy_async_smem();
                     E.request(NB_REQ_ALL, kEngThreads);
+                    PMHC_TS(12);
                     const bool more = t + 1 < pl.ntiles;
-                    if (more) nxt = decode(t + 1, rl_next);
-
+                    if (more) {
+                        nxt = decode(t + 1, rl_next);
+                        if (nxt.j >= kN)     // its neighbour row towards L2 now (the rows of a batch are 20 MB per layer: they come from HBM)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk32 + (((size_t)b * 2 + LAYER) * a.P + (nxt.j - kN)) * kHid + 32 * E.grp));
+                    }
+                    if (t > 0) merge_tile(t - 1, par ^ 1);
+                    PMHC_TS(11);
                     float* out = Out + r * kOutPerPair;
                     E.wait(B_H1);
+                    PMHC_TS(13);
+                    E.sync_eng();       // every thread has merged the previous tile: Out / Lg may be rewritten
                     if (grpA) {
                         if (LAYER == 0) {
                             write_sel(E, pr, 0.0f);
@@ -819,15 +908,20 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         }
                         const float logit = dot_relu64(E, TM_X, MS_ATT2) + misc[MS_B2ND + 0];   // model.py:241-243
                         E.request(NB_REQ_A2, kGrp);
+                        PMHC_TS(14);
                         convert_hidden<TERMS>(E, TM_Y);
                         E.request(NB_REQ_A4, kGrp);
+                        PMHC_TS(15);
                         if (pr.active) {
                             Lg[r] = logit;
                             atomicMax(Mtile + par * kN + rl, enc_max(logit));
                             if (lsave != nullptr) lsave[pr.i * a.Kpad + pr.j] = logit;
                         }
-                        if (more) load_aj<LAYER>(E, nxt, b, aj);     // next tile's neighbour rows: in flight under the tail of this one
+                        E.wait(B_TRN);      // the translation head was the last reader of the pair tile
+                        if (more) stage_tile(nxt);
+                        PMHC_TS(17);
                         E.wait(B_D3R);
+                        PMHC_TS(16);
                         float d[4];
                         tc::tmem_ld4(E.tmem + E.lane_base + TM_D3R, d);
                         const float4 qj4 = Q[pr.j];
@@ -838,60 +932,35 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                                       fast_sigmoid(d[2] + misc[MS_B2ND + 3]), fast_sigmoid(d[3] + misc[MS_B2ND + 4])};   // never normalised (T5)
                         const Quat dg = qmul(qj, qmul(dl, qinvj));                                  // model.py:296
                         out[1] = dg.w; out[2] = dg.x; out[3] = dg.y; out[4] = dg.z;
-                        E.phase ^= (1u << B_TRN) | (1u << B_D3T);   // completions this group does not wait for
+                        E.phase ^= 1u << B_D3T;   // completion this group does not wait for
                     } else {
                         convert_hidden<TERMS>(E, TM_Z);
                         E.request(NB_REQ_B3, kGrp);
+                        PMHC_TS(14);
                         E.wait(B_TRN);
+                        PMHC_TS(15);
                         const float sc = dot_relu64(E, TM_X, MS_TRN2) + misc[MS_B2ND + 12];       // model.py:325-327
-                        if (more) load_aj<LAYER>(E, nxt, b, aj);
+                        const float4 xi = X[pr.i], xj = X[pr.j];
+                        out[12] = sc * (xi.x - xj.x); out[13] = sc * (xi.y - xj.y); out[14] = sc * (xi.z - xj.z);   // model.py:331
+                        if (more) stage_tile(nxt);
+                        PMHC_TS(17);
                         E.wait(B_D3T);
+                        PMHC_TS(16);
                         float d[8];
                         tc::tmem_ld8(E.tmem + E.lane_base + TM_D3T, d);
 #pragma unroll
                         for (int c = 0; c < PMHC_NTORS; ++c) out[5 + c] = d[c] + misc[MS_B2ND + 5 + c];
-                        const float4 xi = X[pr.i], xj = X[pr.j];
-                        out[12] = sc * (xi.x - xj.x); out[13] = sc * (xi.y - xj.y); out[14] = sc * (xi.z - xj.z);   // model.py:331
                         E.phase ^= 1u << B_D3R;
                     }
                     tc::fence_before_thread_sync();
-                    E.sync_eng();       // the tile's logits, row maxima and head outputs are in shared memory
-                    {
-                        // streaming softmax: column c of the running sums (0: sum of weights, 1..14: weighted head outputs); 16 lanes
-                        // walk each row segment of the tile, then the row's state is rescaled to the new maximum and updated
-                        const int c = et >> 4, k16 = et & 15;
-                        int s_row = row0, pos = 0, len = W - off0 < ntile ? W - off0 : ntile;
-                        while (pos < ntile) {
-                            const float m_old = Mrow[par * kN + s_row];
-                            const float m_new = fmaxf(m_old, dec_max(Mtile[par * kN + s_row]));
-                            float acc = 0.0f;
-                            if (c < kOutPerPair)
-                                for (int p = pos + k16; p < pos + len; p += 16) {
-                                    const float wgt = soft_exp(Lg[p] - m_new);
-                                    acc = c == 0 ? acc + wgt : fmaf(wgt, Out[p * kOutPerPair + c], acc);
-                                }
-#pragma unroll
-                            for (int sh = 8; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-                            if (k16 == 0 && c < kOutPerPair) {
-                                const float f = m_old == -INFINITY ? 0.0f : soft_exp(m_old - m_new);
-                                St[s_row * 16 + c] = fmaf(St[s_row * 16 + c], f, acc);
-                            }
-                            pos += len;
-                            ++s_row;
-                            len = W < ntile - pos ? W : ntile - pos;
-                        }
-                        if (et < kN) {
-                            Mrow[(par ^ 1) * kN + et] = fmaxf(Mrow[par * kN + et], dec_max(Mtile[par * kN + et]));
-                            Mtile[(par ^ 1) * kN + et] = kEncNegInf;   // free since the previous tile; used by the next one
-                        }
-                        off0 += kTile;
-                        while (off0 >= W) { off0 -= W; ++row0; }
-                    }
+                    PMHC_TS(18);
+                    E.sync_eng();       // the tile's logits, row maxima and head outputs are in shared memory; the next tile is staged
+                    PMHC_TS(19);
                     par ^= 1;
                     pr = nxt;
                     rl = rl_next;
-                    // (the next tile's request barrier orders these reads before the next writes of Out / Lg / Mtile)
                 }
+                if (pl.ntiles > 0) merge_tile(pl.ntiles - 1, par ^ 1);
                 E.sync_eng();
                 {
                     // finished rows: normalise the running sums and apply the updates (model.py:263-269, 300-310, 331)
@@ -979,7 +1048,10 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                             a.ssum_out[(size_t)b * kN * kHid + I[IN_PEPX + (idx >> 6)] * kHid + (idx & 63)] = 0.0f;
                 }
                 E.sync_eng();
+                PMHC_TS(3);
             }
+            if (ts_on) ts_buf[255] = ts_n;
+#undef PMHC_TS
         }
     }
 
@@ -1312,6 +1384,8 @@ __global__ void __launch_bounds__(128, 1) node_mid3_kernel(NodeMid3Args a) {
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+long long* g_tc3_dbg = nullptr;   // development hook (pmhc_debug_set_stamps3)
+
 struct Tc3Workspace {
     float* pk32;        // [B,2,P,64]
     float* ssum;        // [B,16,64]
@@ -1437,6 +1511,7 @@ static int forward_tc3_impl(const float* params, const PmhcBatch* bt, float t_ov
     a.pocket_frames = bt->pocket_frames; a.pocket_cls = w.cls; a.cls_stride = w.cls_stride; a.pk32 = w.pk32;
     a.aij = w.aij1; a.wimage = w.wimage;
     a.order = w.order;
+    a.dbg = g_tc3_dbg;
     a.frames_out = frames1; a.tors_out = tors1; a.ssum_out = w.ssum;
     a.rowstat = rowstat1; a.logit_out = logits1;
     int rc = launch_pair3<0, TERMS>(a, d, stream);
@@ -1449,6 +1524,7 @@ static int forward_tc3_impl(const float* params, const PmhcBatch* bt, float t_ov
     }
     a.frames_in = frames1; a.tors_in = tors1;
     a.aij = w.aij2; a.wimage = w.wimage + w.image_stride;
+    a.dbg = g_tc3_dbg ? g_tc3_dbg + 512 : nullptr;
     a.frames_out = out_frames; a.tors_out = out_torsions; a.ssum_out = nullptr;
     a.rowstat = rowstat2; a.logit_out = logits2;
     return launch_pair3<1, TERMS>(a, d, stream);
@@ -1465,3 +1541,7 @@ int forward_tc3(int terms, const float* params, const PmhcBatch* bt, float t_ove
 }
 
 }  // namespace pmhc
+
+// development hook: device buffer of 1024 int64 receiving (clock64 << 8 | tag) stamps of CTA 0 / engine 0: layer 1 group A [0,256),
+// group B [256,512); layer 2 [512,768), [768,1024); slot 255 of each block = number of stamps
+extern "C" void pmhc_debug_set_stamps3(long long* dev_buf) { pmhc::g_tc3_dbg = dev_buf; }
