@@ -310,29 +310,45 @@ __device__ __forceinline__ float dec_max(int i) { return __int_as_float(i >= 0 ?
 constexpr int kEncNegInf = (int)0x807FFFFF;   // enc_max(-inf)
 
 // ---- staging: this thread's 32 features of m1 = relu(A_i + A_j + W_e) -> the pair tile(s) ----
-// load_aj: the pocket neighbour's A_j row from L2 / HBM (issued a phase ahead of its use: the rows of a 1 000-complex batch are
-// 20 MB per layer, so these loads see DRAM latency); peptide neighbours are read from shared memory in finish_stage.
-template <int LAYER>
-__device__ __forceinline__ void load_aj(const Engine& E, const PairRef& pr, int b, float4 (&v)[8]) {
+// A thread's output — 32 fp16 values per term — occupies four 16-byte chunks of its row in the hi tile and four in the lo tile:
+// 128 bytes (TERMS = 2), exactly the size of its half of the neighbour's fp32 A_j row.  issue_aj copies that half row from
+// global memory (L2 / HBM: the pocket rows of a 1 000-complex batch are 20 MB per layer) STRAIGHT INTO THOSE CHUNKS with
+// cp.async as soon as the pair tile is free; the copy is in flight under the rest of the tile's epilogue, needs no registers,
+// and finish_stage reads it back, adds A_i (and, for peptide neighbours, A_j and the edge term from shared memory), and
+// overwrites the same chunks with the fp16 terms.
+template <int TERMS>
+__device__ __forceinline__ uint8_t* stage_slot(const Engine& E, int k) {
+    const int r = E.r;
+    uint8_t* row = E.es + E.M.A1 + (r >> 3) * 1024 + (r & 7) * 128;
+    if (TERMS > 1) return row + (k >> 2) * 16384 + (((4 * E.grp + (k & 3)) ^ (r & 7)) << 4);
+    // single term: 64 bytes of tile per thread, so only half of the row is parked in the tile (chunks 0..3); see issue_aj
+    return row + (((4 * E.grp + (k & 3)) ^ (r & 7)) << 4);
+}
+template <int LAYER, int TERMS>
+__device__ __forceinline__ void issue_aj(const Engine& E, const PairRef& pr, int b) {
     if (pr.j >= kN) {
         const float4* src = reinterpret_cast<const float4*>(E.a.pk32 + (((size_t)b * 2 + LAYER) * E.a.P + (pr.j - kN)) * kHid) + 8 * E.grp;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c);
-    } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int k = 0; k < (TERMS > 1 ? 8 : 4); ++k) tc::cp_async_16(stage_slot<TERMS>(E, k), src + k);
     }
 }
 template <int LAYER, int TERMS>
-__device__ __forceinline__ void finish_stage(const Engine& E, const PairRef& pr, float4 (&v)[8]) {
+__device__ __forceinline__ void finish_stage(const Engine& E, const PairRef& pr, int b) {
     const int r = E.r, g = E.grp, i = pr.i, j = pr.j;
     const float4* ai = reinterpret_cast<const float4*>(E.es + E.M.AI) + i * 16;
+    float4 v[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float4 w = ai[(8 * g + c) ^ (i & 7)];
-        v[c].x += w.x; v[c].y += w.y; v[c].z += w.z; v[c].w += w.w;
-    }
-    if (j >= 0 && j < kN) {
+    for (int c = 0; c < 8; ++c) v[c] = ai[(8 * g + c) ^ (i & 7)];
+    if (j >= kN) {
+        tc::cp_async_wait_all();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float4 w;
+            if (TERMS > 1 || c < 4) w = *reinterpret_cast<const float4*>(stage_slot<TERMS>(E, c));
+            else w = __ldg(reinterpret_cast<const float4*>(E.a.pk32 + (((size_t)b * 2 + LAYER) * E.a.P + (j - kN)) * kHid) + 8 * g + c);
+            v[c].x += w.x; v[c].y += w.y; v[c].z += w.z; v[c].w += w.w;
+        }
+    } else if (j >= 0) {
         const float4* aj = reinterpret_cast<const float4*>(E.es + E.M.AJS) + j * 16;
         const int rel = kN - 1 + i - j;
         const float4* we = reinterpret_cast<const float4*>(E.smem + E.M.WE) + rel * 16;
@@ -343,7 +359,6 @@ __device__ __forceinline__ void finish_stage(const Engine& E, const PairRef& pr,
             v[c].x += w.x + e.x; v[c].y += w.y + e.y; v[c].z += w.z + e.z; v[c].w += w.w + e.w;
         }
     }
-    uint8_t* row = E.es + E.M.A1 + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {          // 16-byte chunks 4g + cc of the row: features 32 g + 8 cc ..
         const float4 p = v[2 * cc], q = v[2 * cc + 1];
@@ -356,9 +371,8 @@ __device__ __forceinline__ void finish_stage(const Engine& E, const PairRef& pr,
         } else {
             hi.x = tc::pack_f16x2(x0, x1); hi.y = tc::pack_f16x2(x2, x3); hi.z = tc::pack_f16x2(x4, x5); hi.w = tc::pack_f16x2(x6, x7);
         }
-        const int off = ((4 * g + cc) ^ (r & 7)) << 4;
-        *reinterpret_cast<uint4*>(row + off) = hi;
-        if (TERMS > 1) *reinterpret_cast<uint4*>(row + 16384 + off) = lo;
+        *reinterpret_cast<uint4*>(stage_slot<TERMS>(E, cc)) = hi;
+        if (TERMS > 1) *reinterpret_cast<uint4*>(stage_slot<TERMS>(E, 4 + cc)) = lo;
     }
 }
 
@@ -531,8 +545,9 @@ __device__ __forceinline__ Plan make_plan(const ComplexInfo& ci, const Work& wk,
 }
 
 // ---- per-complex set-up by the engine's 256 threads ----
+#define PMHC_TS2(tag) do { if (ts_buf != nullptr && *ts_n < 250) { ts_buf[(*ts_n)++] = (clock64() << 8) | (tag); } } while (0)
 template <int LAYER, int TERMS>
-__device__ inline ComplexInfo setup_engine(Engine& E, int b) {
+__device__ inline ComplexInfo setup_engine(Engine& E, int b, long long* ts_buf, int* ts_n) {
     const PairArgs& a = E.a;
     const Map& M = E.M;
     const int et = E.et, lane = et & 31;
@@ -545,19 +560,29 @@ __device__ inline ComplexInfo setup_engine(Engine& E, int b) {
     if (et == 0) {
         tc::fence_proxy_async_smem();   // the previous complex's generic-proxy accesses of these arrays come first
         // contiguous per-complex arrays by TMA bulk copies: A_i | A_j rows (8 KB), torsions, peptide mask, pocket slot classes
-        const uint32_t bytes = 2 * kN * 256 + kN * 14 * 4 + 16 + (uint32_t)a.cls_stride;
+        const bool raw = (P & 3) == 0 && K * 28 <= kTile * kOutPerPair * 4;
+        const uint32_t bytes = 2 * kN * 256 + kN * 14 * 4 + 16 + (uint32_t)a.cls_stride + (raw ? (uint32_t)K * 28 : 0u);
         tc::mbar_expect_tx(E.bar + B_LOAD, bytes);
+        if (raw) {   // frames as they lie in memory ([slot][7] floats) into the output buffer; de-interleaved below
+            tc::bulk_g2s(E.es + M.OUT, a.frames_in + (size_t)b * kN * 7, kN * 28, E.bar + B_LOAD);
+            tc::bulk_g2s(E.es + M.OUT + kN * 28, a.pocket_frames + (size_t)b * P * 7, (uint32_t)P * 28, E.bar + B_LOAD);
+        }
         tc::bulk_g2s(E.es + M.AI, a.aij + (size_t)b * 2 * kN * 64, kN * 256, E.bar + B_LOAD);
         tc::bulk_g2s(E.es + M.AJS, a.aij + (size_t)b * 2 * kN * 64 + kN * 64, kN * 256, E.bar + B_LOAD);
         tc::bulk_g2s(Tors, a.tors_in + (size_t)b * kN * 14, kN * 14 * 4, E.bar + B_LOAD);
         tc::bulk_g2s(Cls, a.mask + (size_t)b * kN, 16, E.bar + B_LOAD);
         tc::bulk_g2s(Cls + 16, a.pocket_cls + (size_t)b * a.cls_stride, (uint32_t)a.cls_stride, E.bar + B_LOAD);
     }
-    for (int idx = et; idx < K * 7; idx += kEngThreads) {
-        const int j = idx / 7, c = idx - j * 7;
-        const float* f = (j < kN) ? a.frames_in + ((size_t)b * kN + j) * 7 + c : a.pocket_frames + ((size_t)b * P + (j - kN)) * 7 + c;
-        tc::cp_async_4(c < 4 ? Q + 4 * j + c : X + 4 * j + (c - 4), f);
+    PMHC_TS2(21);
+    const bool raw_frames = (P & 3) == 0 && K * 28 <= kTile * kOutPerPair * 4;   // 16-byte aligned rows that fit the (free) output buffer
+    if (!raw_frames) {
+        for (int idx = et; idx < K * 7; idx += kEngThreads) {
+            const int j = idx / 7, c = idx - j * 7;
+            const float* f = (j < kN) ? a.frames_in + ((size_t)b * kN + j) * 7 + c : a.pocket_frames + ((size_t)b * P + (j - kN)) * 7 + c;
+            tc::cp_async_4(c < 4 ? Q + 4 * j + c : X + 4 * j + (c - 4), f);
+        }
     }
+    PMHC_TS2(22);
     if (et < kN * 16) reinterpret_cast<float*>(E.es + M.ST)[et] = 0.0f;
     if (et < kN) {
         reinterpret_cast<float*>(E.es + M.MROW)[et] = -INFINITY;
@@ -566,7 +591,17 @@ __device__ inline ComplexInfo setup_engine(Engine& E, int b) {
     }
     if (LAYER == 0) reinterpret_cast<uint4*>(E.es + M.SEL)[et] = make_uint4(0u, 0u, 0u, 0u);
     tc::cp_async_wait_all();
+    PMHC_TS2(23);
     E.wait(B_LOAD);
+    PMHC_TS2(24);
+    if (raw_frames) {
+        const float* raw = reinterpret_cast<const float*>(E.es + M.OUT);
+        for (int j = et; j < K; j += kEngThreads) {
+            const float* f = raw + 7 * j;
+            *reinterpret_cast<float4*>(Q + 4 * j) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(X + 4 * j) = make_float4(f[4], f[5], f[6], 0.0f);
+        }
+    }
     E.sync_eng();
     if (LAYER == 0) {
         // time feature (model.py:394): A_i += (t/T) w_ti, A_j += (t/T) w_tj on the 16 peptide rows
@@ -579,23 +614,27 @@ __device__ inline ComplexInfo setup_engine(Engine& E, int b) {
             aj[swz64(i, k)] = fmaf(a.t_over_T, misc[MS_TIME_J + k], aj[swz64(i, k)]);
         }
     }
-    {   // torsion term of the torsion head, per peptide row: T[i][n] = b[n] + W_t[n, 64:78] . tors_i (model.py:260), fp16 terms
-        const float* tor0 = a.params + param_offset(LAYER, TOR0_W);
-        const float* tconst = reinterpret_cast<const float*>(E.smem + M.MISC) + MS_TCONST;
-        const int i = et >> 4, n0 = (et & 15) * 4;
-        const float* t = Tors + i * 14;
+    {   // torsion term of the torsion head, per peptide row: T[i][n] = b[n] + W_t[n, 64:78] . tors_i (model.py:260), fp16 terms.
+        // Thread = hidden unit n (its 14 weights in registers, read once), four rows each.
+        const int n = et & 63, i0 = (et >> 6) * 4;
+        const float* w = a.params + param_offset(LAYER, TOR0_W) + n * 78 + 64;
+        float wt[14];
+#pragma unroll
+        for (int c = 0; c < 14; ++c) wt[c] = __ldg(w + c);
+        const float tconst = reinterpret_cast<const float*>(E.smem + M.MISC)[MS_TCONST + n];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int n = n0 + u;
-            const float* w = tor0 + n * 78 + 64;
-            float acc = tconst[n];
+            const int i = i0 + u;
+            const float* t = Tors + i * 14;
+            float acc = tconst;
 #pragma unroll
-            for (int c = 0; c < 14; ++c) acc = fmaf(__ldg(w + c), t[c], acc);
+            for (int c = 0; c < 14; ++c) acc = fmaf(wt[c], t[c], acc);
             const float h = tc::f16_round(acc);
             *reinterpret_cast<uint16_t*>(E.es + M.TT + kmaj16_offset(n, i)) = f16_bits(acc);
             if (TERMS > 1) *reinterpret_cast<uint16_t*>(E.es + M.TT + 2048 + kmaj16_offset(n, i)) = f16_bits(acc - h);
         }
     }
+    PMHC_TS2(25);
     if ((et >> 5) == 0) {
         const bool real = lane < kN && Cls[lane] != 0;
         const unsigned bal = __ballot_sync(0xffffffffu, real);
@@ -625,8 +664,10 @@ __device__ inline ComplexInfo setup_engine(Engine& E, int b) {
             I[IN_POCKET + Kpad + 3] = c0;
         }
     }
+    PMHC_TS2(26);
     tc::fence_proxy_async_smem();   // the torsion-term tile (and the cleared selector) are MMA operands
     E.sync_all();                   // + the issuing warp, which reads the lists' counts
+    PMHC_TS2(27);
     ComplexInfo ci;
     ci.L = I[IN_POCKET + Kpad + 0];
     ci.nv = I[IN_POCKET + Kpad + 1];
@@ -782,7 +823,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
             for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.n_eng, a.B, a.order, wk); ++k) {
                 const int b = wk.b;
                 PMHC_TS(1);
-                const ComplexInfo ci = setup_engine<LAYER, TERMS>(E, b);
+                const ComplexInfo ci = setup_engine<LAYER, TERMS>(E, b, ts_on ? ts_buf : nullptr, &ts_n);
                 PMHC_TS(2);
                 {
                     Work wn;
@@ -795,8 +836,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     for (int idx = et; idx < (kN - L) * 21; idx += kEngThreads) {
                         const int s = idx / 21, c = idx - s * 21;
                         const int i = I[IN_PEPX + s];
-                        if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = a.frames_in[((size_t)b * kN + i) * 7 + c];
-                        else a.tors_out[((size_t)b * kN + i) * 14 + (c - 7)] = a.tors_in[((size_t)b * kN + i) * 14 + (c - 7)];
+                        if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = c < 4 ? reinterpret_cast<const float*>(Q + i)[c] : reinterpret_cast<const float*>(X + i)[c - 4];
+                        else a.tors_out[((size_t)b * kN + i) * 14 + (c - 7)] = reinterpret_cast<const float*>(es + M.TORS)[i * 14 + (c - 7)];
                     }
                 }
                 // layer 1 (group A): thread 64 h + f holds feature f of the message sums of rows 0..15 over the tile halves h
@@ -835,37 +876,45 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                 //                        half of tile t + 1 (the pair tile is free once the translation head has read it)
                 int par = 0;             // parity of the tile whose outputs are being produced: its copy of Mrow / Mtile
                 int row0 = 0, off0 = 0;  // the tile being MERGED starts `off0` pairs into row `row0` of the part (same in every thread)
-                int rl = 0, rl_next = 0;
+                int rl = 0, rl_next = 0, rl_prev = 0;
                 PairRef pr{}, nxt{};
                 auto stage_tile = [&](const PairRef& p) {
-                    float4 aj[8];
-                    load_aj<LAYER>(E, p, b, aj);
-                    finish_stage<LAYER, TERMS>(E, p, aj);
+                    PMHC_TS(31);
+                    finish_stage<LAYER, TERMS>(E, p, b);
+                    PMHC_TS(32);
                     if (grpA) {
                         if (LAYER == 0) write_sel(E, p, 1.0f);
                         attention_extras(E, p);
                     } else {
                         rotation_extras(E, p);
                     }
+                    PMHC_TS(33);
                 };
                 // streaming softmax: column c of the running sums (0: sum of weights, 1..14: weighted head outputs); 16 lanes walk each
                 // row segment of the tile, then the row's state is rescaled to the new maximum and updated
-                auto merge_tile = [&](int mt, int mpar) {
+                auto merge_tile = [&](int mt, int mpar, int my_rl) {
                     const int ntile = G - mt * kTile < kTile ? G - mt * kTile : kTile;
+                    if (grpA) {     // this thread's pair: logit -> softmax weight against its row's new maximum, in place
+                        float wgt = 0.0f;
+                        if (r < ntile) wgt = soft_exp(Lg[r] - fmaxf(Mrow[mpar * kN + my_rl], dec_max(Mtile[mpar * kN + my_rl])));
+                        Lg[r] = wgt;
+                    }
+                    E.sync_eng();
                     const int c = et >> 4, k16 = et & 15;
                     int s_row = row0, pos = 0, len = W - off0 < ntile ? W - off0 : ntile;
                     while (pos < ntile) {
-                        const float m_old = Mrow[mpar * kN + s_row];
-                        const float m_new = fmaxf(m_old, dec_max(Mtile[mpar * kN + s_row]));
                         float acc = 0.0f;
-                        if (c < kOutPerPair)
-                            for (int p = pos + k16; p < pos + len; p += 16) {
-                                const float wgt = soft_exp(Lg[p] - m_new);
-                                acc = c == 0 ? acc + wgt : fmaf(wgt, Out[p * kOutPerPair + c], acc);
-                            }
+                        if (c == 0) {
+                            for (int p = pos + k16; p < pos + len; p += 16) acc += Lg[p];
+                        } else if (c < kOutPerPair) {
+#pragma unroll 4
+                            for (int p = pos + k16; p < pos + len; p += 16) acc = fmaf(Lg[p], Out[p * kOutPerPair + c], acc);
+                        }
 #pragma unroll
                         for (int sh = 8; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
                         if (k16 == 0 && c < kOutPerPair) {
+                            const float m_old = Mrow[mpar * kN + s_row];
+                            const float m_new = fmaxf(m_old, dec_max(Mtile[mpar * kN + s_row]));
                             const float f = m_old == -INFINITY ? 0.0f : soft_exp(m_old - m_new);
                             St[s_row * 16 + c] = fmaf(St[s_row * 16 + c], f, acc);
                         }
@@ -882,6 +931,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                 };
                 if (pl.ntiles > 0) {
                     pr = decode(0, rl);
+                    issue_aj<LAYER, TERMS>(E, pr, b);
                     stage_tile(pr);
                 }
                 for (int t = 0; t < pl.ntiles; ++t) {
@@ -892,10 +942,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     const bool more = t + 1 < pl.ntiles;
                     if (more) {
                         nxt = decode(t + 1, rl_next);
-                        if (nxt.j >= kN)     // its neighbour row towards L2 now (the rows of a batch are 20 MB per layer: they come from HBM)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk32 + (((size_t)b * 2 + LAYER) * a.P + (nxt.j - kN)) * kHid + 32 * E.grp));
                     }
-                    if (t > 0) merge_tile(t - 1, par ^ 1);
+                    if (t > 0) merge_tile(t - 1, par ^ 1, rl_prev);
                     PMHC_TS(11);
                     float* out = Out + r * kOutPerPair;
                     E.wait(B_H1);
@@ -918,7 +966,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                             if (lsave != nullptr) lsave[pr.i * a.Kpad + pr.j] = logit;
                         }
                         E.wait(B_TRN);      // the translation head was the last reader of the pair tile
-                        if (more) stage_tile(nxt);
+                        if (more) issue_aj<LAYER, TERMS>(E, nxt, b);
                         PMHC_TS(17);
                         E.wait(B_D3R);
                         PMHC_TS(16);
@@ -932,6 +980,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                                       fast_sigmoid(d[2] + misc[MS_B2ND + 3]), fast_sigmoid(d[3] + misc[MS_B2ND + 4])};   // never normalised (T5)
                         const Quat dg = qmul(qj, qmul(dl, qinvj));                                  // model.py:296
                         out[1] = dg.w; out[2] = dg.x; out[3] = dg.y; out[4] = dg.z;
+                        if (more) stage_tile(nxt);
                         E.phase ^= 1u << B_D3T;   // completion this group does not wait for
                     } else {
                         convert_hidden<TERMS>(E, TM_Z);
@@ -939,10 +988,10 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         PMHC_TS(14);
                         E.wait(B_TRN);
                         PMHC_TS(15);
+                        if (more) issue_aj<LAYER, TERMS>(E, nxt, b);
                         const float sc = dot_relu64(E, TM_X, MS_TRN2) + misc[MS_B2ND + 12];       // model.py:325-327
                         const float4 xi = X[pr.i], xj = X[pr.j];
                         out[12] = sc * (xi.x - xj.x); out[13] = sc * (xi.y - xj.y); out[14] = sc * (xi.z - xj.z);   // model.py:331
-                        if (more) stage_tile(nxt);
                         PMHC_TS(17);
                         E.wait(B_D3T);
                         PMHC_TS(16);
@@ -950,6 +999,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         tc::tmem_ld8(E.tmem + E.lane_base + TM_D3T, d);
 #pragma unroll
                         for (int c = 0; c < PMHC_NTORS; ++c) out[5 + c] = d[c] + misc[MS_B2ND + 5 + c];
+                        if (more) stage_tile(nxt);
                         E.phase ^= 1u << B_D3R;
                     }
                     tc::fence_before_thread_sync();
@@ -958,9 +1008,10 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     PMHC_TS(19);
                     par ^= 1;
                     pr = nxt;
+                    rl_prev = rl;
                     rl = rl_next;
                 }
-                if (pl.ntiles > 0) merge_tile(pl.ntiles - 1, par ^ 1);
+                if (pl.ntiles > 0) merge_tile(pl.ntiles - 1, par ^ 1, rl_prev);
                 E.sync_eng();
                 {
                     // finished rows: normalise the running sums and apply the updates (model.py:263-269, 300-310, 331)
@@ -1018,9 +1069,8 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                             const int which = e - (npx + ci.nx + 1);
                             mult = (float)(which == 0 ? min(ci.c0, 1024) : ci.c0 - 1024);
                         }
-                        float4 ajm[8];
-                        load_aj<LAYER>(E, pr, b, ajm);
-                        finish_stage<LAYER, TERMS>(E, pr, ajm);
+                        issue_aj<LAYER, TERMS>(E, pr, b);
+                        finish_stage<LAYER, TERMS>(E, pr, b);
                         if (grpA) write_sel(E, pr, mult);
                         tc::fence_proxy_async_smem();
                         E.request(NB_REQ_ALL, kEngThreads);
