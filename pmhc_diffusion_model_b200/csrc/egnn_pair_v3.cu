@@ -317,19 +317,29 @@ constexpr int kEncNegInf = (int)0x807FFFFF;   // enc_max(-inf)
 // and finish_stage reads it back, adds A_i (and, for peptide neighbours, A_j and the edge term from shared memory), and
 // overwrites the same chunks with the fp16 terms.
 template <int TERMS>
-__device__ __forceinline__ uint8_t* stage_slot(const Engine& E, int k) {
-    const int r = E.r;
+__device__ __forceinline__ uint8_t* stage_slot_of(const Engine& E, int r, int k) {
     uint8_t* row = E.es + E.M.A1 + (r >> 3) * 1024 + (r & 7) * 128;
     if (TERMS > 1) return row + (k >> 2) * 16384 + (((4 * E.grp + (k & 3)) ^ (r & 7)) << 4);
-    // single term: 64 bytes of tile per thread, so only half of the row is parked in the tile (chunks 0..3); see issue_aj
+    // single term: 64 bytes of tile per thread, so only half of the half row is parked in the tile (chunks 0..3); see issue_aj
     return row + (((4 * E.grp + (k & 3)) ^ (r & 7)) << 4);
 }
+template <int TERMS>
+__device__ __forceinline__ uint8_t* stage_slot(const Engine& E, int k) { return stage_slot_of<TERMS>(E, E.r, k); }
+// Warp-cooperative and coalesced: 8 lanes copy the 8 chunks of ONE pair's half row (128 contiguous bytes), four pairs per
+// instruction, eight instructions for the warp's 32 pairs.  (One lane per row — each lane fetching its own 128 bytes — touches 32
+// different lines per instruction: 29 shared-memory wavefronts per cp.async instead of 4 and twice the L2 sectors, measured.)
+// Must be called by all 32 lanes of a warp.
 template <int LAYER, int TERMS>
 __device__ __forceinline__ void issue_aj(const Engine& E, const PairRef& pr, int b) {
-    if (pr.j >= kN) {
-        const float4* src = reinterpret_cast<const float4*>(E.a.pk32 + (((size_t)b * 2 + LAYER) * E.a.P + (pr.j - kN)) * kHid) + 8 * E.grp;
+    const int lane = E.r & 31, sub = lane & 7, q = lane >> 3;
 #pragma unroll
-        for (int k = 0; k < (TERMS > 1 ? 8 : 4); ++k) tc::cp_async_16(stage_slot<TERMS>(E, k), src + k);
+    for (int m = 0; m < 8; ++m) {
+        const int T = q + 4 * m;
+        const int jT = __shfl_sync(0xffffffffu, pr.j, T);
+        if (jT >= kN && (TERMS > 1 || sub < 4)) {
+            const float* src = E.a.pk32 + (((size_t)b * 2 + LAYER) * E.a.P + (jT - kN)) * kHid + 32 * E.grp + 4 * sub;
+            tc::cp_async_16(stage_slot_of<TERMS>(E, (E.r & ~31) + T, sub), src);
+        }
     }
 }
 template <int LAYER, int TERMS>
@@ -339,8 +349,9 @@ __device__ __forceinline__ void finish_stage(const Engine& E, const PairRef& pr,
     float4 v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] = ai[(8 * g + c) ^ (i & 7)];
+    tc::cp_async_wait_all();      // this lane's copies (for other lanes' pairs) have landed ...
+    __syncwarp();                 // ... and so have the other lanes' copies for this pair
     if (j >= kN) {
-        tc::cp_async_wait_all();
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float4 w;
@@ -960,9 +971,17 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         convert_hidden<TERMS>(E, TM_Y);
                         E.request(NB_REQ_A4, kGrp);
                         PMHC_TS(15);
+                        {   // the tile maximum of this pair's row: one shared-memory atomic per warp when the warp holds a single row
+                            const int key = pr.active ? rl : -1, key0 = __shfl_sync(0xffffffffu, key, 0);
+                            if (__all_sync(0xffffffffu, key == key0)) {
+                                const int mx = __reduce_max_sync(0xffffffffu, enc_max(logit));
+                                if (key0 >= 0 && (r & 31) == 0) atomicMax(Mtile + par * kN + rl, mx);
+                            } else if (pr.active) {
+                                atomicMax(Mtile + par * kN + rl, enc_max(logit));
+                            }
+                        }
                         if (pr.active) {
                             Lg[r] = logit;
-                            atomicMax(Mtile + par * kN + rl, enc_max(logit));
                             if (lsave != nullptr) lsave[pr.i * a.Kpad + pr.j] = logit;
                         }
                         E.wait(B_TRN);      // the translation head was the last reader of the pair tile
