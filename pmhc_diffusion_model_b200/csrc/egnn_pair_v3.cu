@@ -74,23 +74,33 @@ constexpr int kMaxParts = 4;
 struct Work {
     int b, part, parts;
 };
-__device__ __forceinline__ bool get_work(int k, int cta, int eng, int ctas, int n_eng, int B, const int* __restrict__ order, Work& w) {
-    const int E = ctas * n_eng;
-    const int full = B / E, rem = B - full * E;
+struct Deal {          // per-launch constants of the deal, computed once per thread
+    int E, full, rem, S, slot, first;
+};
+__device__ __forceinline__ Deal make_deal(int cta, int eng, int ctas, int n_eng, int B) {
+    Deal d;
+    d.E = ctas * n_eng;
+    d.full = B / d.E;
+    d.rem = B - d.full * d.E;
+    d.S = d.rem > 0 ? d.E / d.rem : 1;
+    d.S = d.S > kMaxParts ? kMaxParts : d.S;
+    d.slot = eng * ctas + cta;
+    d.first = cta * n_eng + eng;
+    return d;
+}
+__device__ __forceinline__ bool get_work(const Deal& d, int k, const int* __restrict__ order, Work& w) {
     int item;
-    if (k < full) {
-        item = k * E + cta * n_eng + eng;
+    if (k < d.full) {
+        item = k * d.E + d.first;
         w.part = 0;
         w.parts = 1;
     } else {
-        if (k > full || rem == 0) return false;
-        int S = E / rem;
-        S = S > kMaxParts ? kMaxParts : S;
-        const int slot = eng * ctas + cta;
-        if (slot >= rem * S) return false;
-        item = full * E + slot / S;
-        w.part = slot - (slot / S) * S;
-        w.parts = S;
+        if (k > d.full || d.rem == 0) return false;
+        if (d.slot >= d.rem * d.S) return false;
+        const int q = d.slot / d.S;
+        item = d.full * d.E + q;
+        w.part = d.slot - q * d.S;
+        w.parts = d.S;
     }
     w.b = order != nullptr ? __ldg(order + item) : item;
     return true;
@@ -107,7 +117,8 @@ struct Map {
     int total_bytes;
 };
 // MISC floats
-constexpr int MS_ATT2 = 0, MS_TRN2 = 64, MS_B2ND = 128, MS_TCONST = 144, MS_TIME_I = 208, MS_TIME_J = 272, MS_FLOATS = 336;
+constexpr int MS_ATT2 = 0, MS_TRN2 = 64, MS_B2ND = 128, MS_TCONST = 144, MS_TIME_I = 208, MS_TIME_J = 272, MS_WT = 336, MS_FLOATS = 336 + 14 * 64;
+// WT: torsion_mlp.0.weight[:, 64:78] transposed, [14 torsion inputs][64 hidden units]
 // B2ND: [0] attention_mlp.2.bias, [1,5) rotation_mlp.2.bias, [5,12) torsion_mlp.2.bias, [12] translation_mlp.2.bias
 
 template <int TERMS>
@@ -118,7 +129,7 @@ __host__ __device__ inline Map make_map(int Kpad, bool layer1) {
     m.W3 = o;   o += 2 * TERMS * 2048;     // second layers [16 n][64 k] fp16 SW128: (rotation | torsion, term)
     m.WXA = o;  o += 2048;                 // attention extras [64 n][16 k] bf16, K-major core matrices
     m.WXR = o;  o += 2048;                 // rotation extras, fp16
-    m.WXT = o;  o += TERMS * 2048;         // translation bias against the one-hot block, fp16 terms
+    m.WXT = o;  o += 2048;                 // translation bias (hi, lo) against the two 1.0 slots of the rotation extras block, fp16
     m.WE = o;   o += 8192;                 // message_mlp.0 edge columns, fp32 [31][64], chunk-swizzled rows
     m.MISC = o; o += MS_FLOATS * 4;
     m.image_bytes = o;                     // [0, image_bytes) is built by weight_image3_kernel
@@ -227,10 +238,8 @@ __global__ void __launch_bounds__(256) weight_image3_kernel(const float* __restr
             reinterpret_cast<float*>(img + M.MISC)[MS_TCONST + n] = bias;     // joins W_t tors_i per complex
         } else {
             const float bh = __half2float(__float2half_rn(bias));
-            for (int k = 0; k < 16; ++k) {
-                *reinterpret_cast<uint16_t*>(img + M.WXT + kmaj16_offset(n, k)) = f16_bits(bias);
-                if (TERMS > 1) *reinterpret_cast<uint16_t*>(img + M.WXT + 2048 + kmaj16_offset(n, k)) = f16_bits(bias - bh);
-            }
+            for (int k = 0; k < 16; ++k)
+                *reinterpret_cast<uint16_t*>(img + M.WXT + kmaj16_offset(n, k)) = f16_bits(k == 12 ? bias : (k == 13 ? bias - bh : 0.0f));
         }
     }
     float* we = reinterpret_cast<float*>(img + M.WE);
@@ -244,6 +253,7 @@ __global__ void __launch_bounds__(256) weight_image3_kernel(const float* __restr
         misc[MS_TRN2 + n] = params[param_offset(L, TRN2_W) + n];
         misc[MS_TIME_I + n] = L == 0 ? msg0[n * ld1 + PMHC_NFEAT] : 0.0f;
         misc[MS_TIME_J + n] = L == 0 ? msg0[n * ld1 + H + PMHC_NFEAT] : 0.0f;
+        for (int c = 0; c < 14; ++c) misc[MS_WT + c * 64 + n] = head[2][n * 78 + 64 + c];
     }
     if (tid < 16) {
         float v = 0.0f;
@@ -628,10 +638,10 @@ __device__ inline ComplexInfo setup_engine(Engine& E, int b, long long* ts_buf, 
     {   // torsion term of the torsion head, per peptide row: T[i][n] = b[n] + W_t[n, 64:78] . tors_i (model.py:260), fp16 terms.
         // Thread = hidden unit n (its 14 weights in registers, read once), four rows each.
         const int n = et & 63, i0 = (et >> 6) * 4;
-        const float* w = a.params + param_offset(LAYER, TOR0_W) + n * 78 + 64;
+        const float* wtab = reinterpret_cast<const float*>(E.smem + M.MISC) + MS_WT + n;
         float wt[14];
 #pragma unroll
-        for (int c = 0; c < 14; ++c) wt[c] = __ldg(w + c);
+        for (int c = 0; c < 14; ++c) wt[c] = wtab[c * 64];
         const float tconst = reinterpret_cast<const float*>(E.smem + M.MISC)[MS_TCONST + n];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -760,8 +770,9 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                      tc::smem_u32(smem), tc::smem_u32(es)};
             const int* I = E.ints();
             constexpr uint32_t idf = tc::idesc_f16_f32(128, 64), idb = tc::idesc_bf16_f32(128, 64);
+            const Deal deal = make_deal(blockIdx.x, eng, gridDim.x, a.n_eng, a.B);
             Work wk;
-            for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.n_eng, a.B, a.order, wk); ++k) {
+            for (int k = 0; get_work(deal, k, a.order, wk); ++k) {
                 E.sync_all();   // the compute threads have set the complex up
                 ComplexInfo ci;
                 ci.L = I[IN_POCKET + a.Kpad + 0];
@@ -783,8 +794,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     E.serve(NB_REQ_A2, kGrp, [&] {   // group A has read the attention hidden units (and the tile sums): X is free
                         const uint32_t cta = Engine::opaque(E.smem_u), esu = Engine::opaque(E.es_u), tm = Engine::opaque(E.tmem);
                         mma_heads_main<TERMS>(E, cta, esu, tm, 3, 1, TM_X);
-#pragma unroll
-                        for (int u = 0; u < TERMS; ++u) mma_extras(tm + TM_X, tm + TM_EXO, cta + M.WXT + u * 2048, idf);
+                        mma_extras(tm + TM_X, tm + TM_EXR, cta + M.WXT, idf);     // bias through the (1, 1) slots of the rotation block
                         E.commit(B_TRN);
                     });
                     E.serve(NB_REQ_B3, kGrp, [&] {
@@ -830,27 +840,16 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
             const bool ts_on = a.dbg != nullptr && blockIdx.x == 0 && eng == 0 && r == 0;
             long long* ts_buf = a.dbg + (grpA ? 0 : 256);
 #define PMHC_TS(tag) do { if (ts_on && ts_n < 250) { ts_buf[ts_n++] = (clock64() << 8) | (tag); } } while (0)
+            const Deal deal = make_deal(blockIdx.x, eng, gridDim.x, a.n_eng, a.B);
             Work wk;
-            for (int k = 0; get_work(k, blockIdx.x, eng, gridDim.x, a.n_eng, a.B, a.order, wk); ++k) {
+            for (int k = 0; get_work(deal, k, a.order, wk); ++k) {
                 const int b = wk.b;
                 PMHC_TS(1);
                 const ComplexInfo ci = setup_engine<LAYER, TERMS>(E, b, ts_on ? ts_buf : nullptr, &ts_n);
                 PMHC_TS(2);
-                {
-                    Work wn;
-                    if (get_work(k + 1, blockIdx.x, eng, gridDim.x, a.n_eng, a.B, a.order, wn)) prefetch_complex<LAYER>(E, wn.b);
-                }
                 const Plan pl = make_plan(ci, wk, LAYER == 0);
                 const int L = pl.L, W = pl.W, G = pl.G;
                 float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
-                if (wk.part == 0) {   // padded rows: pass-through (T4)
-                    for (int idx = et; idx < (kN - L) * 21; idx += kEngThreads) {
-                        const int s = idx / 21, c = idx - s * 21;
-                        const int i = I[IN_PEPX + s];
-                        if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = c < 4 ? reinterpret_cast<const float*>(Q + i)[c] : reinterpret_cast<const float*>(X + i)[c - 4];
-                        else a.tors_out[((size_t)b * kN + i) * 14 + (c - 7)] = reinterpret_cast<const float*>(es + M.TORS)[i * 14 + (c - 7)];
-                    }
-                }
                 // layer 1 (group A): thread 64 h + f holds feature f of the message sums of rows 0..15 over the tile halves h
                 float ssum[kN];
 #pragma unroll
@@ -910,8 +909,10 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         if (r < ntile) wgt = soft_exp(Lg[r] - fmaxf(Mrow[mpar * kN + my_rl], dec_max(Mtile[mpar * kN + my_rl])));
                         Lg[r] = wgt;
                     }
+                    PMHC_TS(40);
                     E.sync_eng();
                     const int c = et >> 4, k16 = et & 15;
+                    PMHC_TS(41);
                     int s_row = row0, pos = 0, len = W - off0 < ntile ? W - off0 : ntile;
                     while (pos < ntile) {
                         float acc = 0.0f;
@@ -933,18 +934,33 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         ++s_row;
                         len = W < ntile - pos ? W : ntile - pos;
                     }
+                    PMHC_TS(42);
                     if (et < kN) {
                         Mrow[(mpar ^ 1) * kN + et] = fmaxf(Mrow[mpar * kN + et], dec_max(Mtile[mpar * kN + et]));
                         Mtile[(mpar ^ 1) * kN + et] = kEncNegInf;   // free since the tile before; the next tile's maxima go there
                     }
                     off0 += kTile;
                     while (off0 >= W) { off0 -= W; ++row0; }
+                    PMHC_TS(43);
                 };
                 if (pl.ntiles > 0) {
                     pr = decode(0, rl);
-                    issue_aj<LAYER, TERMS>(E, pr, b);
-                    stage_tile(pr);
+                    issue_aj<LAYER, TERMS>(E, pr, b);      // in flight under the rest of the prologue
                 }
+                {
+                    Work wn;
+                    if (get_work(deal, k + 1, a.order, wn)) prefetch_complex<LAYER>(E, wn.b);
+                }
+                if (wk.part == 0) {   // padded rows: pass-through (T4); one warp per padded slot, 21 lanes
+                    const int c = et & 31;
+                    for (int sl = et >> 5; sl < kN - L; sl += kEngThreads / 32) {
+                        const int i = I[IN_PEPX + sl];
+                        if (c < 4) a.frames_out[((size_t)b * kN + i) * 7 + c] = reinterpret_cast<const float*>(Q + i)[c];
+                        else if (c < 7) a.frames_out[((size_t)b * kN + i) * 7 + c] = reinterpret_cast<const float*>(X + i)[c - 4];
+                        else if (c < 21) a.tors_out[((size_t)b * kN + i) * 14 + (c - 7)] = reinterpret_cast<const float*>(es + M.TORS)[i * 14 + (c - 7)];
+                    }
+                }
+                if (pl.ntiles > 0) stage_tile(pr);
                 for (int t = 0; t < pl.ntiles; ++t) {
                     PMHC_TS(10);
                     tc::fence_proxy_async_smem();
@@ -954,6 +970,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     if (more) {
                         nxt = decode(t + 1, rl_next);
                     }
+                    PMHC_TS(39);
                     if (t > 0) merge_tile(t - 1, par ^ 1, rl_prev);
                     PMHC_TS(11);
                     float* out = Out + r * kOutPerPair;
