@@ -12,9 +12,15 @@ independent, each rank samples its own shard, no collective on the data path).
 One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: through the public
 DiffusionModelOptimizer.sample() call with the batch in pinned HOST memory (H2D + D2H inside the timed region);
 `roofline`: the fused EGNN layer-forward kernel timed with CUDA events on its launching stream;
-`cpu_baseline`: the CPU port of the reference path (oracle/) on this box's host cores, bounded sample;
-`train`: the second half of the metric (training complexes/s, B = 256) measured the same way.
-`--impl reference` times that CPU path alone with all host threads (the reference has no GPU path).
+`cpu_baseline`: the UNMODIFIED reference (baseline/_ref, installed by baseline/install_reference.py; the oracle port when that
+install is absent) on this box's host cores, bounded sample;
+`train`: the second half of the metric (training complexes/s, B = 256) measured the same way, with the reference's own
+optimize() timed beside it; `modes`: the other arithmetic modes on the same workload; `configs`: the other BASELINE configs.
+`--impl reference` times the CPU path alone with all host threads (the reference has no GPU path).
+
+Headline mode: precision "tc32" — tcgen05 tensor cores with fp16 hi + lo operand splits (fp32-class: it meets the fp32 parity
+gate on the reference's shipped model.pth, tests/test_gpu_parity.py PARITY_MODES) — on the SHIPPED weights
+(tests/golden/shipped_params.pt), the checkpoint whose attention logits reach 2.5e3.
 """
 import argparse
 import ctypes
@@ -39,6 +45,8 @@ P_PAD = 80
 TRAIN_B = 256
 T_TRAIN = 1000
 CPU_SAMPLE_B = 16          # complexes in one CPU-baseline trajectory (bounded sample)
+CPU_TRAIN_B = 64           # complexes in one CPU-baseline training step (BASELINE configs[0])
+WORKLOAD = "sampling T=100, 1000 complexes/GPU, 9-mer peptide, M=180 protein / 60 pocket residues padded to 80 (BASELINE configs[1])"
 METRIC = "sampled complexes/s (T=100 reverse steps)"
 UNIT = "complexes/s"
 
@@ -47,6 +55,23 @@ UNIT = "complexes/s"
 # message-only pairs of layer 1 (self, padded peptide slots, one shared padded-pocket message) cost 64x64.
 MAC_PER_PAIR = 64 * 64 + 64 * 256 + 64 * 6 + 64 * 13
 MAC_PER_MSG_PAIR = 64 * 64
+
+
+# per forward mode: the fused layer kernel, what it computes in, its parity gate, and its measured DRAM traffic per launch
+# (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at B = 1000, summaries under profiles/)
+KERNELS = {
+    "tc32": {"kernel": "egnn_pair3_kernel<LAYER, 2>", "dtype": "f16x2-split (fp32-class)", "mma_terms": 3, "traffic": 31.1e6,
+             "traffic_source": "profiles/prof_v3_r2_summary.csv",
+             "gate": "max(1e-4, 2 x the reference's fp32 noise floor) on the reference fixtures, shipped weights included",
+             "math": "tcgen05 f16 x f16 -> fp32 (TMEM), every operand as fp16 hi + lo, every contraction as hi.hi + lo.hi + hi.lo; geometry / softmax / updates fp32"},
+    "fp16": {"kernel": "egnn_pair3_kernel<LAYER, 1>", "dtype": "f16", "mma_terms": 1, "traffic": None, "traffic_source": None,
+             "gate": "1e-2 on well-conditioned weights", "math": "tcgen05 f16 x f16 -> fp32 (TMEM), single fp16 terms"},
+    "bf16": {"kernel": "egnn_pair_tc_kernel<LAYER>", "dtype": "bf16", "mma_terms": 1, "traffic": 18.2e6, "traffic_source": "profiles/prof_pair_r1_summary.csv",
+             "gate": "1e-2 on well-conditioned (random-init) weights; NOT met on the shipped model.pth",
+             "math": "tcgen05 bf16 x bf16 -> fp32 (TMEM) for every per-pair contraction, geometry / softmax / updates fp32"},
+    "fp32": {"kernel": "egnn_layer_forward_kernel<LAYER>", "dtype": "f32", "mma_terms": 1, "traffic": 15.1e6, "traffic_source": "profiles/prof_fwd_r1b_summary.csv",
+             "gate": "max(1e-4, 2 x the reference's fp32 noise floor) on the reference fixtures", "math": "fp32 FFMA; tensor-pipe peak is the judged denominator"},
+}
 
 
 def forward_flops_per_complex(L=PEPTIDE_LEN, pocket_n=POCKET_N, n_pad=16):
@@ -65,7 +90,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -75,7 +100,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -113,22 +138,84 @@ def synthetic(B, seed, P_pad=P_PAD, pocket_n=POCKET_N, L=PEPTIDE_LEN):
     return synthetic_batch(B, L, pocket_n, P_pad=P_pad, seed=seed)
 
 
-def cpu_trajectory_rate(params, threads, B=CPU_SAMPLE_B, T=T_STEPS, repeats=1):
-    """Reference path on the host cores: oracle.sample() = the reference's DiffusionModelOptimizer.sample restated.
+def load_weights():
+    """The reference's shipped checkpoint (committed as a fixture: /root/reference does not exist on the GPU box)."""
+    path = os.path.join(ROOT, "tests", "golden", "shipped_params.pt")
+    if os.path.isfile(path):
+        return torch.load(path, map_location="cpu"), "shipped model.pth of the reference (79 195 params)"
+    from pmhc_diffusion_model_b200.synthetic import random_params
+    return random_params(seed=0), "random init, reference architecture (79 195 params)"
+
+
+class CpuReference:
+    """The reference path on the host cores.  kind = "reference": the unmodified reference installed in baseline/_ref, imported
+    through oracle/ref_shim.py (openfold -> the rigid_utils transformers ships); kind = "port": oracle/egnn_oracle.py.
     (The one place, with run_reference below, where bench.py executes oracle/: as the measured CPU baseline.)"""
-    from oracle import egnn_oracle as orc
-    torch.set_num_threads(threads)
-    batch = orc.batch_to_frames(synthetic(B, seed=4242))
-    g = torch.Generator().manual_seed(1)
-    start = orc.gen_noise([B, 16], g)
-    batch["frames"], batch["torsions"] = start["frames"], start["torsions"]
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        orc.sample(params, batch, T, generator=g)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return B / best, best
+
+    def __init__(self, params):
+        self.params = params
+        ref_root = os.path.join(ROOT, "baseline", "_ref")
+        self.kind = "port"
+        if os.path.isfile(os.path.join(ref_root, "diffusion", "optimizer.py")):
+            try:
+                from oracle import ref_shim
+                ref_shim.REFERENCE_ROOT = ref_root
+                self.ref_model, self.ref_opt, _ = ref_shim.load_reference()
+                self.kind = "reference"
+            except Exception as e:  # noqa: BLE001 — e.g. transformers' openfold_utils missing: fall back to the port, and say so
+                print(f"baseline/_ref not importable ({e}); timing the oracle port", file=sys.stderr)
+        from oracle import egnn_oracle as orc
+        self.orc = orc
+
+    def describe(self):
+        return ("unmodified reference (baseline/_ref: diffusion.optimizer.DiffusionModelOptimizer on torch CPU fp32)" if self.kind == "reference"
+                else "oracle/egnn_oracle.py on torch CPU fp32")
+
+    def sample_rate(self, threads, B=CPU_SAMPLE_B, T=T_STEPS):
+        """One trajectory of B complexes: DiffusionModelOptimizer.sample as test.py:60-75 drives it."""
+        torch.set_num_threads(threads)
+        raw = synthetic(B, seed=4242)
+        if self.kind == "reference":
+            model = self.ref_model.Model(16, 22, T)
+            model.load_state_dict(self.params, strict=True)
+            dm = self.ref_opt.DiffusionModelOptimizer(T, model, 0.0)
+            torch.manual_seed(1)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                noise = dm.gen_noise(raw["frames"].shape[:-1], device=torch.device("cpu"))
+                batch = dict(raw)
+                batch["frames"] = noise["frames"].to_tensor_7()
+                batch["torsions"] = noise["torsions"]
+                dm.sample(batch)
+            dt = time.perf_counter() - t0
+        else:
+            orc = self.orc
+            batch = orc.batch_to_frames(raw)
+            g = torch.Generator().manual_seed(1)
+            t0 = time.perf_counter()
+            start = orc.gen_noise([B, 16], g)
+            batch["frames"], batch["torsions"] = start["frames"], start["torsions"]
+            orc.sample(self.params, batch, T, generator=g)
+            dt = time.perf_counter() - t0
+        return B / dt, dt
+
+    def train_rate(self, threads, B=CPU_TRAIN_B, steps=3):
+        """optimize() (optimizer.py:195-224) on B complexes, best of `steps`; reference kind only."""
+        if self.kind != "reference":
+            return None
+        torch.set_num_threads(threads)
+        raw = synthetic(B, seed=4343)
+        model = self.ref_model.Model(16, 22, T_TRAIN)
+        model.load_state_dict(self.params, strict=True)
+        dm = self.ref_opt.DiffusionModelOptimizer(T_TRAIN, model, 1e-3)
+        from diffusion.tools.metrics import MetricsRecord
+        best = None
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            dm.optimize(dict(raw), MetricsRecord())
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return B / best, best
 
 
 def io_leg(dev, dm, n=256):
@@ -174,32 +261,34 @@ def io_leg(dev, dm, n=256):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (it has no GPU path),
-    restated in oracle/ (the reference itself cannot travel to the GPU box), all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path (it has no GPU path): the unmodified
+    reference from baseline/_ref when installed (kind "reference"), else its restatement in oracle/ (kind "port"); all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from pmhc_diffusion_model_b200.synthetic import random_params
     threads = os.cpu_count() or 1
-    params = random_params(seed=0)
-    for _ in range(args.warmup):
-        cpu_trajectory_rate(params, threads, B=2, T=5)
+    params, weights = load_weights()
+    cpu = CpuReference(params)
+    for _ in range(min(args.warmup, 1)):
+        cpu.sample_rate(threads, B=2, T=5)
     t0 = time.perf_counter()
     done = 0
     for _ in range(args.steps):
-        cpu_trajectory_rate(params, threads)
+        cpu.sample_rate(threads)
         done += CPU_SAMPLE_B
     dt = time.perf_counter() - t0
     value = done / dt
-    sample = f"{CPU_SAMPLE_B} complexes x T={T_STEPS} per step (9-mer, pocket 60 padded to {P_PAD}), fp32, torch CPU"
+    train = cpu.train_rate(threads)
+    sample = f"{CPU_SAMPLE_B} complexes x T={T_STEPS} per step (9-mer, pocket 60 padded to {P_PAD}), fp32, {cpu.describe()}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "sampling T=100, 9-mer peptide, M=180 protein / 60 pocket residues padded to 80 (BASELINE configs[1], bounded sample)",
-                   "complexes_per_step": CPU_SAMPLE_B},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD + ", bounded sample", "complexes_per_step": CPU_SAMPLE_B, "weights": weights},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "train": None if train is None else {"metric": "train complexes/s", "value": train[0], "unit": UNIT, "ms_per_step": train[1] * 1e3,
+                                             "config": f"optimize() on B={CPU_TRAIN_B} (BASELINE configs[0] shape), best of 3, {threads} threads"},
     }))
 
 
@@ -213,8 +302,9 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-io", action="store_true", help="skip the HDF5 loader / PDB writer leg")
-    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
-                    help="arithmetic of the denoiser's two dense contractions in the sampling legs (see include/pmhc_b200.h)")
+    ap.add_argument("--no-modes", action="store_true", help="skip the other arithmetic modes and the other BASELINE configs")
+    ap.add_argument("--precision", default="tc32", choices=["fp32", "tc32", "fp16", "bf16"],
+                    help="arithmetic of the denoiser's dense per-pair contractions in the headline legs (see include/pmhc_b200.h)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -228,7 +318,6 @@ def main():
 
     import torch.distributed as dist
     from pmhc_diffusion_model_b200 import _lib
-    from pmhc_diffusion_model_b200.synthetic import random_params
     from pmhc_diffusion_model_b200.diffusion.model import Model
     from pmhc_diffusion_model_b200.diffusion.optimizer import DiffusionModelOptimizer
 
@@ -257,7 +346,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    params = random_params(seed=0)            # random-init weights of the reference architecture
+    params, weights_note = load_weights()
     model = Model(16, 22, T_STEPS)
     model.load_state_dict(params, strict=True)
     model = model.to(dev)
@@ -266,19 +355,24 @@ def main():
     dm.sample_seed = 2024
     dm.sample_first_complex = rank * B        # Philox stream per global complex index: result independent of N
 
-    host = synthetic(B, seed=1000 + rank)
-    host = {k: v.pin_memory() for k, v in host.items()}
-    torch.manual_seed(7 + rank)
-    start = dm.gen_noise([B, 16], dev)                                                   # z_T (test.py:71-74)
-    host["frames"] = start["frames"].to_tensor_7().cpu().pin_memory()
-    host["torsions"] = start["torsions"].cpu().pin_memory()
     keys = ("frames", "torsions", "features", "mask", "pocket_frames", "pocket_features", "pocket_mask")
-    resident = {k: host[k].to(dev) for k in keys}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def sample_resident():
+    def make_inputs(batch_host, seed):
+        host = {k: v.pin_memory() for k, v in batch_host.items() if isinstance(v, torch.Tensor)}
+        torch.manual_seed(seed)
+        n = host["frames"].shape[0]
+        start = dm.gen_noise([n, 16], dev)                                               # z_T (test.py:71-74)
+        host["frames"] = start["frames"].to_tensor_7().cpu().pin_memory()
+        host["torsions"] = start["torsions"].cpu().pin_memory()
+        return host, {k: host[k].to(dev) for k in keys}
+
+    host, resident = make_inputs(synthetic(B, seed=1000 + rank), 7 + rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def sample_resident(inputs=None):
         flush.zero_()                          # L2 flush between timed iterations
-        return dm.sample(dict(resident))
+        return dm.sample(dict(resident if inputs is None else inputs))
 
     def sample_e2e():
         flush.zero_()
@@ -286,25 +380,26 @@ def main():
         out = dm.sample(batch)
         return out["frames"].to_tensor_7().cpu(), out["torsions"].cpu()
 
-    # ---------------- value: inputs resident in HBM ----------------
-    for _ in range(W):
-        sample_resident()
-    lib.pmhc_profile_enable(1)
-    barrier()
-    launches0 = lib.pmhc_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    def timed(fn, warm, steps):
+        """`steps` calls of fn between two events on the launching stream, barrier + synchronize on both sides; max over ranks."""
+        for _ in range(warm):
+            fn()
+        barrier()
         e0.record()
-        for _ in range(K):
-            sample_resident()
+        for _ in range(steps):
+            fn()
         e1.record()
         barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---------------- value: inputs resident in HBM (no profiling hooks inside the timed region) ----------------
+    for _ in range(W):
+        sample_resident()
+    barrier()
+    launches0 = lib.pmhc_launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(sample_resident, 0, K)
     launches = lib.pmhc_launch_count() - launches0
-    prof_ms = (ctypes.c_double * 2)()
-    prof_n = (ctypes.c_int64 * 2)()
-    lib.pmhc_profile_read(prof_ms, prof_n)
-    lib.pmhc_profile_enable(0)
     value = world * B * K / (ms / 1e3)
 
     # ---------------- e2e: host buffers through the public API ----------------
@@ -320,34 +415,47 @@ def main():
     d2h = B * 16 * 21 * 4
 
     # ---------------- roofline of the dominant kernel (fused EGNN layer forward) ----------------
+    # the same K steps once more with a CUDA event pair around every layer launch (pmhc_profile_*; kept out of `value`'s timed
+    # region: creating 2 x 200 events per trajectory costs host time there)
+    def kernel_times(fn, steps):
+        lib.pmhc_profile_enable(1)
+        barrier()
+        for _ in range(steps):
+            fn()
+        barrier()
+        pm, pn = (ctypes.c_double * 2)(), (ctypes.c_int64 * 2)()
+        lib.pmhc_profile_read(pm, pn)
+        lib.pmhc_profile_enable(0)
+        return [pm[0], pm[1]], [pn[0], pn[1]]
+
+    prof_ms, prof_n = kernel_times(sample_resident, K)
     peaks = measured_peaks()
     flops_per_launch = forward_flops_per_complex() * B / 2.0       # one layer per launch
     kernel_ms = prof_ms[0] / max(1, prof_n[0])
     achieved = flops_per_launch / (kernel_ms * 1e-3) / 1e12
-    tc = args.precision == "bf16"
+    kinfo = KERNELS[args.precision]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"],
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ (ncu --set full, B = 1000)
-                "traffic": 18.2e6 if tc else 15.1e6, "peak_source": peaks["source"] + " bf16 sustained",
-                "kernel": "egnn_pair_tc_kernel" if tc else "egnn_layer_forward_kernel", "kernel_ms": kernel_ms,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture under profiles/ (B = 1000)
+                "traffic": kinfo["traffic"], "traffic_source": kinfo["traffic_source"], "peak_source": peaks["source"] + " bf16 sustained",
+                "kernel": kinfo["kernel"], "kernel_ms": kernel_ms, "kernel_launches_timed": int(prof_n[0]),
                 "kernel_share_of_step": prof_ms[0] / (ms * 1.0) if world == 1 else None,
-                "math": ("tcgen05 bf16 x bf16 -> fp32 (TMEM) for every per-pair contraction, geometry / softmax / updates fp32" if tc
-                         else "fp32 FFMA (exact-parity mode); tensor-pipe peak is the judged denominator"),
-                "flops_per_launch": flops_per_launch}
+                "math": kinfo["math"], "flops_per_launch": flops_per_launch,
+                "tensor_flops_executed_per_launch": flops_per_launch * kinfo["mma_terms"],
+                "note": "achieved counts ALGORITHMIC flops (43.4 kFLOP per pair per layer); this mode issues "
+                        f"{kinfo['mma_terms']} MMA term(s) per contraction, so the tensor pipe does {kinfo['mma_terms']}x that"}
 
-    # the other precision mode, one short measurement, for the record (same workload, inputs resident)
-    other = None
-    if world == 1:
-        model.precision = "fp32" if tc else "bf16"
-        sample_resident()
-        barrier()
-        e0.record()
-        sample_resident()
-        e1.record()
-        barrier()
-        oms = e0.elapsed_time(e1)
-        other = {"precision": model.precision, "value": B / (oms / 1e3), "unit": UNIT, "ms_per_step": oms,
-                 "parity_gate": "1e-4 (fp32 FFMA, exact-parity mode)" if tc else "1e-2 (bf16 tensor cores)"}
+    # ---------------- the other arithmetic modes on the same workload (inputs resident), for the record ----------------
+    modes = None
+    if world == 1 and not args.no_modes:
+        modes = {}
+        for mode in ("fp32", "tc32", "bf16"):
+            if mode == args.precision:
+                continue
+            model.precision = mode
+            k2 = 1 if mode == "fp32" else 3
+            oms = timed(sample_resident, 1, k2) / k2
+            modes[mode] = {"value": B / (oms / 1e3), "unit": UNIT, "ms_per_step": oms, "parity_gate": KERNELS[mode]["gate"], "kernel": KERNELS[mode]["kernel"]}
         model.precision = args.precision
 
     # ---------------- training throughput (second half of the metric) ----------------
@@ -357,53 +465,61 @@ def main():
         tmodel.load_state_dict(params, strict=True)
         tmodel = tmodel.to(dev)
         tdm = DiffusionModelOptimizer(T_TRAIN, tmodel, 1e-3)
-        tb = {k: v.to(dev) for k, v in synthetic(TRAIN_B, seed=5000 + rank).items()}
         from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer
         trainer = DataParallelTrainer(tdm, seed=0)   # N = 1: plain optimize(); N > 1: shared t + overlapped NCCL all-reduce
         n_train = 20
 
-        def time_training():
-            for _ in range(W):
-                trainer.optimize(dict(tb), None)
-            barrier()
-            e0.record()
-            for _ in range(n_train):
+        def train_leg(tb, precision, backward):
+            tmodel.precision, tmodel.backward_precision = precision, backward
+
+            def step():
                 flush.zero_()
                 trainer.optimize(dict(tb), None)
-            e1.record()
-            barrier()
-            t = max_over_ranks(e0.elapsed_time(e1))
+            t = timed(step, W, n_train)
             tdm.check_nan()
-            return t
+            nb = tb["frames"].shape[0]
+            return {"value": world * nb * n_train / (t / 1e3), "unit": UNIT, "ms_per_step": t / n_train, "global_batch": world * nb}, step
 
-        tms = time_training()
-        tmodel.precision, tmodel.backward_precision = "bf16", "fp32"   # tensor-core forward (saves the softmax statistics), FFMA backward
-        tms_bf16 = time_training()
-        tmodel.backward_precision = None                                # ... and the TF32 tensor-core backward: the "bf16" training mode
-        lib.pmhc_profile_enable(1)
-        tms_tc = time_training()
-        tprof_ms = (ctypes.c_double * 2)()
-        tprof_n = (ctypes.c_int64 * 2)()
-        lib.pmhc_profile_read(tprof_ms, tprof_n)
-        lib.pmhc_profile_enable(0)
-        tmodel.precision = "fp32"
+        tb = {k: v.to(dev) for k, v in synthetic(TRAIN_B, seed=5000 + rank).items()}
+        fp32_leg, _ = train_leg(tb, "fp32", None)
+        tc32_leg, _ = train_leg(tb, "tc32", None)          # tcgen05 hi/lo forward (saves the softmax statistics), fp32 FFMA backward
+        bf16_leg, bf16_step = train_leg(tb, "bf16", None)  # bf16 tcgen05 forward + TF32 tensor-core backward
+        tprof_ms, tprof_n = kernel_times(bf16_step, n_train)
         # backward roofline (tensor pipe): 3 x 43.4 kFLOP per real pair per layer (recomputation + input gradients + weight
         # gradients), both layers' kernels averaged; pairs as in the forward count
         bwd_us = tprof_ms[1] / max(tprof_n[1], 1) * 1e3
         bwd_flops = TRAIN_B * 3.0 * 0.5 * forward_flops_per_complex()
-        train = {"metric": "train complexes/s", "value": world * TRAIN_B * n_train / (tms / 1e3), "unit": UNIT,
-                 "ms_per_step": tms / n_train, "global_batch": world * TRAIN_B, "steps": n_train,
-                 "config": "B=256/GPU, 9-mer, pocket 60/80, fp32, noise+forward+loss+backward+Adam per step",
-                 "bf16_forward": {"value": world * TRAIN_B * n_train / (tms_bf16 / 1e3), "ms_per_step": tms_bf16 / n_train,
-                                  "config": "same step with the tensor-core (bf16 operand) forward, fp32 FFMA backward"},
-                 "bf16": {"value": world * TRAIN_B * n_train / (tms_tc / 1e3), "ms_per_step": tms_tc / n_train,
-                          "config": "same step in the bf16 training mode: tcgen05 bf16 forward + TF32 tensor-core backward (gradient gate 1e-2 class)",
-                          "backward_kernel_us": bwd_us,
-                          "backward_roofline": {"bound": "tensor", "achieved": bwd_flops / (bwd_us * 1e-6) / 1e12,
-                                                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                                                "frac": bwd_flops / (bwd_us * 1e-6) / 1e12 / peaks["bf16_tflops"],
-                                                "note": "algorithmic 3 x 43.4 kFLOP per pair per layer; TF32 mma.sync (legacy tensor path), "
-                                                        "judged against the measured bf16 peak"}}}
+        bf16_leg.update({"config": "bf16 training mode: tcgen05 bf16 forward + TF32 tensor-core backward (gradient gate 1e-2 class)",
+                         "backward_kernel_us": bwd_us,
+                         "backward_roofline": {"bound": "tensor", "achieved": bwd_flops / (bwd_us * 1e-6) / 1e12, "peak": peaks["bf16_tflops"],
+                                               "unit": "TFLOP/s", "frac": bwd_flops / (bwd_us * 1e-6) / 1e12 / peaks["bf16_tflops"],
+                                               "note": "algorithmic 3 x 43.4 kFLOP per pair per layer; TF32 mma.sync (legacy tensor path), "
+                                                       "judged against the measured bf16 peak"}})
+        tc32_leg["config"] = "fp32-class training: tcgen05 hi/lo-split forward + fp32 FFMA backward (gradient gate 1e-4, same as fp32)"
+        train = {"metric": "train complexes/s", **fp32_leg, "steps": n_train,
+                 "config": "B=256/GPU, 9-mer, pocket 60/80, fp32 FFMA forward + backward, noise+forward+loss+backward+Adam per step (BASELINE configs[2], [3] at N=8)",
+                 "tc32": tc32_leg, "bf16": bf16_leg}
+        if world == 1 and not args.no_modes:
+            # BASELINE configs[2] variant B: the whole M = 180 groove as the pocket (padded to 192)
+            tb2 = {k: v.to(dev) for k, v in synthetic(TRAIN_B, seed=6000 + rank, P_pad=192, pocket_n=180).items()}
+            train["full_groove_P192"] = {"fp32": train_leg(tb2, "fp32", None)[0], "tc32": train_leg(tb2, "tc32", None)[0],
+                                         "bf16": train_leg(tb2, "bf16", None)[0]}
+            del tb2
+        tmodel.precision, tmodel.backward_precision = "fp32", None
+
+    # ---------------- BASELINE configs[4]: mixed peptide lengths 8-15, pockets up to 400 slots (class I + II), bounded sample ----------------
+    sweep = None
+    if not args.no_modes:
+        n5 = 2000
+        from pmhc_diffusion_model_b200.synthetic import synthetic_batch
+        h5, r5 = make_inputs(synthetic_batch(n5, (8, 15), (40, 400), P_pad=400, seed=9000 + rank), 99 + rank)
+        dm.sample_first_complex = rank * n5
+        t5 = timed(lambda: sample_resident(r5), 1, 2) / 2
+        dm.sample_first_complex = rank * B
+        sweep = {"value": world * n5 / (t5 / 1e3), "unit": UNIT, "ms_per_step": t5, "complexes_per_gpu": n5,
+                 "config": "BASELINE configs[4] shapes: peptide length uniform 8-15, pocket uniform 40-400 of 400 slots, T=100, "
+                           f"{args.precision}; {n5} complexes per GPU as a bounded sample of the 100k sweep (weak scaling, no collective)"}
+        del h5, r5
 
     # ---------------- loader / writer rows, rank 0 at N = 1 ----------------
     io = None
@@ -414,28 +530,31 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        rate, secs = cpu_trajectory_rate(params, threads)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"one trajectory of {CPU_SAMPLE_B} complexes x T={T_STEPS} (same shapes), {secs:.1f} s, oracle/egnn_oracle.py on torch CPU fp32"}
+        ref = CpuReference(params)
+        rate, secs = ref.sample_rate(threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": ref.kind,
+               "sample": f"one trajectory of {CPU_SAMPLE_B} complexes x T={T_STEPS} (same shapes, same weights), {secs:.1f} s, {ref.describe()}"}
+        tr = ref.train_rate(threads)
+        if tr is not None and train is not None:
+            train["cpu_baseline"] = {"value": tr[0], "unit": UNIT, "cores": threads, "kind": ref.kind,
+                                     "sample": f"optimize() on B={CPU_TRAIN_B} (BASELINE configs[0] shape), best of 3, {tr[1]:.2f} s per step"}
 
     if rank == 0:
         line = json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if tc else "f32", "data": "synthetic",
-            "config": {"workload": "sampling T=100, 1000 complexes/GPU, 9-mer peptide, M=180 protein / 60 pocket residues padded to 80 (BASELINE configs[1])",
-                       "complexes_per_gpu": B, "T": T_STEPS, "P_pad": P_PAD, "l2": "flushed between steps (256 MiB memset)",
-                       "weights": "random init, reference architecture (79 195 params)",
-                       "precision": args.precision + (" (tcgen05: bf16 operands / fp32 accumulate for every per-pair contraction; parity gate 1e-2)"
-                                                      if tc else " (FFMA; parity gate 1e-4)")},
+            "dtype": KERNELS[args.precision]["dtype"], "data": "synthetic",
+            "config": {"workload": WORKLOAD, "complexes_per_gpu": B, "T": T_STEPS, "P_pad": P_PAD, "l2": "flushed between steps (256 MiB memset)",
+                       "weights": weights_note, "precision": f"{args.precision}: {KERNELS[args.precision]['math']}; parity gate {KERNELS[args.precision]['gate']}"},
             "clocks": clocks.summary(),
             "e2e": {"value": world * B * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "other_precision": other,
+            "modes": modes,
             "train": train,
+            "sweep_config5": sweep,
             "io": io,
         })
         sys.stdout.flush()

@@ -167,6 +167,13 @@ int pmhc_sample(const float *params, const PmhcBatch *batch_host, float *frames,
  * betas/eps unless given; `skip` ranges (gnn2.feature_mlp) are left untouched like grad=None params. */
 int pmhc_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n,
                    double lr, double beta1, double beta2, double eps, int step, void *stream);
+/* Same, guarded on the device: when *skip_flag (one byte, nullable) is non-zero nothing is written.  The training step sets
+ * the flag from `total_loss.isnan().any()`: the reference raises RuntimeError("NaN loss") BEFORE backward() and step()
+ * (optimizer.py:217-218), so its weights never see a NaN gradient; here the check stays on the device (no host sync per
+ * step) and the update is skipped instead. */
+int pmhc_adam_step_guarded(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n,
+                           double lr, double beta1, double beta2, double eps, int step,
+                           const uint8_t *skip_flag, void *stream);
 
 /* Loader side — replaces the per-entry Rigid.from_tensor_4x4(...).to_tensor_7() of MhcpDataset.get_entry
  * (diffusion/data.py:107, :115; RU:1004-1034 + rot_to_quat RU:184-216): n homogeneous 4x4 matrices (row-major,

@@ -24,7 +24,7 @@ BACKWARD_OF = {"fp32": "fp32", "bf16": "bf16", "tc32": "fp32", "fp16": "bf16"}  
 EXPORTS = (
     "pmhc_last_error", "pmhc_check_device", "pmhc_param_offset", "pmhc_param_numel", "pmhc_workspace_bytes",
     "pmhc_saved_floats", "pmhc_model_forward", "pmhc_model_forward_ex", "pmhc_model_backward", "pmhc_model_backward_ex", "pmhc_gen_noise", "pmhc_noise_from_randoms",
-    "pmhc_add_noise", "pmhc_remove_noise", "pmhc_loss", "pmhc_sample", "pmhc_adam_step", "pmhc_launch_count",
+    "pmhc_add_noise", "pmhc_remove_noise", "pmhc_loss", "pmhc_sample", "pmhc_adam_step", "pmhc_adam_step_guarded", "pmhc_launch_count",
     "pmhc_profile_enable", "pmhc_profile_read", "pmhc_frames4x4_to_tensor7", "pmhc_atom14", "pmhc_format_pdb_host",
 )
 
@@ -85,6 +85,8 @@ def load() -> ctypes.CDLL:
     lib.pmhc_sample.argtypes = [vp, POINTER(PmhcBatch), vp, vp, c_int, c_double, c_double, u64, u64, vp, vp, vp, vp, c_size_t, vp, c_int]
     lib.pmhc_adam_step.restype = c_int
     lib.pmhc_adam_step.argtypes = [vp, vp, vp, vp, i64, c_double, c_double, c_double, c_double, c_int, vp]
+    lib.pmhc_adam_step_guarded.restype = c_int
+    lib.pmhc_adam_step_guarded.argtypes = [vp, vp, vp, vp, i64, c_double, c_double, c_double, c_double, c_int, vp, vp]
     lib.pmhc_launch_count.restype = i64
     lib.pmhc_launch_count.argtypes = []
     lib.pmhc_profile_enable.restype = None

@@ -5,9 +5,12 @@
 
 writes `<output_model>` (state dict, the reference's 48 keys) every 100 batches and per epoch, and one CSV row of mean
 losses per epoch to `<output_model stem>.csv`.  Differences that do not change results: batches come GPU-resident from
-`MhcpDataset.batches()` (`--num-workers` is accepted and ignored: there are no loader processes), the NaN check is read
-once per epoch instead of once per step (`DiffusionModelOptimizer.check_nan`), `--precision bf16` selects the tensor-core
-forward.  Runs on one GPU; under torchrun each rank trains on its shard of every batch with an NCCL gradient all-reduce.
+`MhcpDataset.batches()` (`--num-workers` is accepted and ignored: there are no loader processes), the NaN flag stays on the
+device (sticky; from the first NaN loss on every Adam update is skipped there) and is read before every save and at the
+end of each epoch instead of once per step (`DiffusionModelOptimizer.check_nan`), `--precision` selects the arithmetic
+(tc32 = tcgen05 forward with fp32-class results + fp32 backward; bf16 = tcgen05 forward + TF32 tensor-core backward).
+Runs on one GPU; under torchrun each rank trains on its contiguous shard of every batch (same batch order, same t, noise drawn
+per GLOBAL complex) with an NCCL gradient all-reduce; a tail batch smaller than the number of ranks is dropped on all ranks.
 """
 import logging
 import os
@@ -27,7 +30,7 @@ arg_parser.add_argument("-T", type=int, help="number of noise steps", default=10
 arg_parser.add_argument("--batch-size", "-b", type=int, help="data batch size", default=64)
 arg_parser.add_argument("--num-workers", "-w", type=int, help="accepted for compatibility; batches are built on the GPU", default=4)
 arg_parser.add_argument("--lr", type=float, help="learning rate", default=0.001)
-arg_parser.add_argument("--precision", choices=["fp32", "bf16"], default="fp32", help="arithmetic of the denoiser: fp32 FFMA (exact parity) or bf16 = tcgen05 forward + TF32 tensor-core backward")
+arg_parser.add_argument("--precision", choices=["fp32", "tc32", "bf16"], default="fp32", help="arithmetic of the denoiser: fp32 FFMA (exact parity), tc32 = tcgen05 forward with fp16 hi/lo operand splits (fp32-class) + fp32 backward, or bf16 = tcgen05 forward + TF32 tensor-core backward")
 arg_parser.add_argument("--seed", type=int, default=None, help="seed of the batch order, noise steps and noise")
 arg_parser.add_argument("--checkpoint", default=None, help="full training state (weights, Adam, random streams, epoch): written "
                         "after every epoch and resumed from when the file exists")
@@ -43,7 +46,7 @@ def main(argv=None) -> None:
     from pmhc_diffusion_model_b200.diffusion.data import MhcpDataset
     from pmhc_diffusion_model_b200.diffusion.model import Model
     from pmhc_diffusion_model_b200.diffusion.optimizer import DiffusionModelOptimizer
-    from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer
+    from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer, shard_batch
     from pmhc_diffusion_model_b200.diffusion.tools.metrics import MetricsRecord
 
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
@@ -65,7 +68,13 @@ def main(argv=None) -> None:
     trainer = DataParallelTrainer(dm, seed=args.seed if args.seed is not None else 0)
 
     train_dataset = MhcpDataset(args.train_hdf5, device)
-    order = torch.Generator().manual_seed(args.seed if args.seed is not None else torch.seed() % (1 << 31))
+    order_seed = args.seed if args.seed is not None else torch.seed() % (1 << 31)
+    if world > 1 and args.seed is None:      # unseeded: rank 0's draw decides, so every rank walks the same permutation
+        box = torch.tensor([order_seed], dtype=torch.int64, device=device)
+        dist.broadcast(box, src=0)
+        order_seed = int(box.item())
+        trainer.seed = order_seed            # ... and the same t / noise keys
+    order = torch.Generator().manual_seed(order_seed)
     first_epoch = 0
     if args.checkpoint and os.path.isfile(args.checkpoint):
         ckpt = torch.load(args.checkpoint, map_location=device, weights_only=False)
@@ -79,12 +88,20 @@ def main(argv=None) -> None:
         _log.debug(f"starting epoch {epoch_index}")
         metrics = MetricsRecord()
         for i, batch in enumerate(train_dataset.batches(args.batch_size, device, shuffle=True, generator=order)):
-            if world > 1:      # every rank draws the same order and takes its slice of the batch
-                batch = {k: (v[rank::world] if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
-            trainer.optimize(batch, metrics)
-            if rank == 0 and i > 0 and i % 100 == 0:
-                torch.save(model.state_dict(), args.output_model)
-                _log.debug(f"saved {args.output_model}")
+            if world > 1:      # every rank draws the same order and takes its contiguous shard of the batch
+                n_global = int(batch["mask"].shape[0])
+                if n_global < world:
+                    _log.debug(f"dropped a tail batch of {n_global} complexes (fewer than {world} ranks)")
+                    continue
+                batch, first = shard_batch(batch, rank, world)
+                trainer.optimize(batch, metrics, global_batch=n_global, first_complex=first)
+            else:
+                trainer.optimize(batch, metrics)
+            if i > 0 and i % 100 == 0:
+                dm.check_nan()         # never overwrite a good model file with the weights of a run that has seen a NaN loss
+                if rank == 0:
+                    torch.save(model.state_dict(), args.output_model)
+                    _log.debug(f"saved {args.output_model}")
         dm.check_nan()
         if rank == 0:
             torch.save(model.state_dict(), args.output_model)

@@ -20,6 +20,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local const float* g_step_t_dev = nullptr;
+const float* step_t_dev() { return g_step_t_dev; }
+void set_step_t_dev(const float* p) { g_step_t_dev = p; }
+
 static bool g_profile = false;
 static std::mutex g_profile_mu;
 static std::vector<cudaEvent_t> g_prof_events[PROF_SLOTS];  // begin, end, begin, end, ...

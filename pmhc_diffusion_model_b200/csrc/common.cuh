@@ -15,6 +15,27 @@ namespace pmhc {
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
 
+// Opt-in kernel attributes (dynamic shared memory size) are per DEVICE: a process that runs the library on a second GPU must set
+// them there too.  One bit per device ordinal; racing first uses at worst set the attribute twice.
+// Step scalars from device memory (graph-replayable training step, pmhc_train_step): while an API call runs with a device
+// scalar block, the launchers hand every kernel `&block->t_over_T`; kernels read it through time_feature() and ignore the
+// by-value copy.  Thread-local, set and cleared inside one API call — no state survives a call.
+const float* step_t_dev();
+void set_step_t_dev(const float* p);
+template <class Args>
+__device__ __forceinline__ float time_feature(const Args& a) { return a.t_dev != nullptr ? __ldg(a.t_dev) : a.t_over_T; }
+
+struct PerDeviceOnce {
+    std::atomic<uint64_t> done{0};
+    static uint64_t bit() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return 1ull << (dev & 63);
+    }
+    bool needed() const { return (done.load(std::memory_order_acquire) & bit()) == 0; }
+    void mark() { done.fetch_or(bit(), std::memory_order_release); }
+};
+
 // Optional per-kernel timing (bench.py's roofline leg): when enabled, the EGNN layer launches are bracketed by
 // CUDA events on the launching stream; pmhc_profile_read() synchronises and sums them.
 enum ProfileSlot { PROF_FWD = 0, PROF_BWD = 1, PROF_SLOTS = 2 };

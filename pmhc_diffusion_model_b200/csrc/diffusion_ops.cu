@@ -270,9 +270,10 @@ __global__ void loss_kernel(const float* __restrict__ tf, const float* __restric
 // torch.optim.Adam single-tensor update (no amsgrad, no weight decay) over the flat buffers.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float one_minus_b1, float b2, float one_minus_b2, float eps,
-                            float step_size, float bc2_sqrt) {
+                            float step_size, float bc2_sqrt, const uint8_t* __restrict__ skip) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (skip != nullptr && *skip != 0) return;   // a non-finite loss was seen: weights and moments stay as they are
     float gi = g[i];
     float mi = m[i] + (gi - m[i]) * one_minus_b1;
     float vi = v[i] * b2 + one_minus_b2 * gi * gi;
@@ -376,12 +377,17 @@ extern "C" int pmhc_loss(const float* tf, const float* tt, const float* pf, cons
 
 extern "C" int pmhc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2,
                               double eps, int step, void* stream) {
+    return pmhc_adam_step_guarded(p, g, m, v, n, lr, b1, b2, eps, step, nullptr, stream);
+}
+
+extern "C" int pmhc_adam_step_guarded(float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2,
+                                      double eps, int step, const uint8_t* skip_flag, void* stream) {
     if (n <= 0) return 0;
     PMHC_REQUIRE(step >= 1, "pmhc_adam_step: step counts from 1");
     // the scalars are formed in double and rounded once, as torch does with its Python-float hyperparameters
     double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
     adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2),
-                                                                   (float)eps, (float)(lr / bc1), (float)sqrt(bc2));
+                                                                   (float)eps, (float)(lr / bc1), (float)sqrt(bc2), skip_flag);
     PMHC_CHECK_LAUNCH("pmhc_adam_step");
     return 0;
 }

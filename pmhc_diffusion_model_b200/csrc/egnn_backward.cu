@@ -1696,17 +1696,17 @@ BwdWorkspace carve_bwd_workspace(void* wsbase, size_t fwd_bytes, int B, int P) {
 
 template <int LAYER, bool TC>
 int launch_layer_backward(const BwdArgs& g, int n_cta, float* grad, cudaStream_t stream) {
-    static bool configured = false;
+    static PerDeviceOnce configured;
     int max_smem = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const BwdMap M = make_bwd_map(g.a.Kpad, TC);
     size_t smem = (size_t)M.total_floats * sizeof(float);
     PMHC_REQUIRE((int)smem <= max_smem, "EGNN backward needs %zu B of shared memory (P=%d), device allows %d", smem, g.a.P, max_smem);
-    if (!configured) {
+    if (configured.needed()) {
         cudaError_t e = cudaFuncSetAttribute(egnn_layer_backward_kernel<LAYER, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(backward): %s", cudaGetErrorString(e));
-        configured = true;
+        configured.mark();
     }
     if (profile_enabled()) profile_mark(PROF_BWD, stream, true);
     egnn_layer_backward_kernel<LAYER, TC><<<n_cta, kBwdThreads, smem, stream>>>(g);
@@ -1750,6 +1750,7 @@ extern "C" int pmhc_model_backward_ex(const float* params, const PmhcBatch* bt, 
     g.a.params = params;
     g.a.B = bt->B; g.a.P = bt->P; g.a.Kpad = pad_k(bt->P);
     g.a.t_over_T = t_over_T;
+    g.a.t_dev = step_t_dev();
     g.a.mask = bt->mask;
     g.a.pocket_frames = bt->pocket_frames; g.a.pocket_feat = bt->pocket_features; g.a.pocket_mask = bt->pocket_mask;
     g.a.ajt_ws = w.ajt;

@@ -29,6 +29,7 @@ struct LayerArgs {
     const float* params;         // flat parameter buffer
     int B, P, Kpad;              // complexes, pocket slots, padded neighbour count (multiple of 32)
     float t_over_T;
+    const float* t_dev;          // nullable: the same scalar in device memory (read instead of t_over_T; graph-replayable steps)
     const float* frames_in;      // [B,16,7]
     const float* tors_in;        // [B,16,14]
     const float* feat_in;        // layer 1: [B,16,22] features; layer 2: [B,16,64] relu(o1)
@@ -212,7 +213,7 @@ __device__ inline ComplexInfo setup_complex(float* S, const SmemMap& M, const La
     for (int idx = tid; idx < kN * kHid; idx += blockDim.x) {
         int i = idx >> 6, c = idx & 63;
         float v;
-        if (L == 0) v = (c < PMHC_NFEAT) ? a.feat_in[((size_t)b * kN + i) * PMHC_NFEAT + c] : (c == PMHC_NFEAT ? a.t_over_T : 0.0f);
+        if (L == 0) v = (c < PMHC_NFEAT) ? a.feat_in[((size_t)b * kN + i) * PMHC_NFEAT + c] : (c == PMHC_NFEAT ? time_feature(a) : 0.0f);
         else v = a.feat_in[((size_t)b * kN + i) * kHid + c];
         S[M.H + i * kLdN + c] = v;
     }
@@ -481,7 +482,7 @@ __device__ inline ComplexInfo setup_complex_cached(float* S, const SmemMap& M, c
     for (int idx = tid; idx < kN * kHid; idx += blockDim.x) {
         int i = idx >> 6, c = idx & 63;
         float v;
-        if (L == 0) v = (c < PMHC_NFEAT) ? a.feat_in[((size_t)b * kN + i) * PMHC_NFEAT + c] : (c == PMHC_NFEAT ? a.t_over_T : 0.0f);
+        if (L == 0) v = (c < PMHC_NFEAT) ? a.feat_in[((size_t)b * kN + i) * PMHC_NFEAT + c] : (c == PMHC_NFEAT ? time_feature(a) : 0.0f);
         else v = a.feat_in[((size_t)b * kN + i) * kHid + c];
         S[M.H + i * kLdN + c] = v;
     }

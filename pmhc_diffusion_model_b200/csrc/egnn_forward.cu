@@ -413,14 +413,14 @@ Workspace carve_workspace(void* base, int B, int P) {
 
 template <int LAYER>
 int launch_layer_forward(const LayerArgs& a, cudaStream_t stream) {
-    static bool configured = false;
+    static PerDeviceOnce configured;
     const SmemMap M = make_smem_map(a.Kpad);
     size_t smem = (size_t)M.total_floats * sizeof(float);
     PMHC_REQUIRE((int)smem <= g_max_smem, "EGNN layer needs %zu B of shared memory (P=%d), device allows %d", smem, a.P, g_max_smem);
-    if (!configured) {
+    if (configured.needed()) {
         cudaError_t e = cudaFuncSetAttribute(egnn_layer_forward_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
         PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(forward): %s", cudaGetErrorString(e));
-        configured = true;
+        configured.mark();
     }
     int grid = a.B < g_num_sms ? a.B : g_num_sms;
     if (profile_enabled()) profile_mark(PROF_FWD, stream, true);
@@ -520,6 +520,7 @@ int pmhc::model_forward_impl(const float* params, const PmhcBatch* bt, float t_o
     a.params = params;
     a.B = bt->B; a.P = bt->P; a.Kpad = pad_k(bt->P);
     a.t_over_T = t_over_T;
+    a.t_dev = step_t_dev();
     a.frames_in = bt->frames; a.tors_in = bt->torsions; a.feat_in = bt->features; a.mask = bt->mask;
     a.pocket_frames = bt->pocket_frames; a.pocket_feat = bt->pocket_features; a.pocket_mask = bt->pocket_mask;
     a.frames_out = frames1; a.tors_out = tors1; a.feat_out = feat1; a.msum_out = msum1; a.rowstat = rowstat1;

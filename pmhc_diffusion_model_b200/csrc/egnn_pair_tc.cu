@@ -56,6 +56,7 @@ constexpr int BM = 0, BX = 1, BY = 2, BZ = 3;
 struct PairArgs {
     int B, P, Kpad;
     float t_over_T;
+    const float* t_dev;              // nullable: t / T in device memory (see time_feature)
     const float* frames_in;          // [B,16,7]
     const float* tors_in;            // [B,16,14]
     const uint8_t* mask;             // [B,16]
@@ -641,7 +642,8 @@ __device__ inline ComplexInfo setup_engine(const Engine& E, int b, bool layer1) 
     if (layer1) {
         // time feature (model.py:394): A_i += (t/T) w_ti, A_j += (t/T) w_tj on the 16 peptide rows, packed bf16x2 FMAs
         const uint32_t* tw = reinterpret_cast<const uint32_t*>(E.smem + M.Misc) + MISC_TIME;
-        const uint32_t t2 = tc::pack_bf16x2(a.t_over_T, a.t_over_T);
+        const float tt = time_feature(a);
+        const uint32_t t2 = tc::pack_bf16x2(tt, tt);
         uint4* ai = reinterpret_cast<uint4*>(E.es + M.Ai);
         uint4* aj = reinterpret_cast<uint4*>(E.es + M.AjS);
         for (int idx = et; idx < kN * 16; idx += kEngThreads) {
@@ -1137,6 +1139,7 @@ struct NodeMidArgs {
     __nv_bfloat16* aij2;      // [B,16,128]
     float* feat1_out;         // nullable: [B,16,64] relu(o1)   (saved for the backward pass)
     float* msum_out;          // nullable: [B,16,64]
+    const float* t_dev;       // nullable: t / T in device memory (see time_feature)
 };
 constexpr int NM_W2 = 0, NM_WF0 = 8192, NM_WF2 = 24576, NM_W1 = 32768, NM_BIAS = 49152, NM_BAR = 50432, NM_TPTR = 50448,
               NM_BYTES = 50464 + 1024;
@@ -1220,10 +1223,11 @@ __global__ void __launch_bounds__(128, 1) node_mid_kernel(NodeMidArgs a) {
         tc::tmem_st32(tmem + lane_base + 32, lo);
         uint32_t hf[16];
         const float* f = a.feat + (in ? node : 0) * PMHC_NFEAT;
-        const float th = tc::bf16_round(a.t_over_T);
+        const float tt = time_feature(a);
+        const float th = tc::bf16_round(tt);
 #pragma unroll
         for (int c = 0; c < 11; ++c) hf[c] = in ? tc::pack_bf16x2(f[2 * c], f[2 * c + 1]) : 0u;
-        hf[11] = tc::pack_bf16x2(th, a.t_over_T - th);
+        hf[11] = tc::pack_bf16x2(th, tt - th);
 #pragma unroll
         for (int c = 12; c < 16; ++c) hf[c] = 0u;
         tc::tmem_st16(tmem + lane_base + 160, hf);
@@ -1369,7 +1373,7 @@ size_t tc2_workspace_bytes(int B, int P) { return carve_tc2(nullptr, B, P).bytes
 
 template <int LAYER>
 static int launch_pair(tc2::PairArgs& a, cudaStream_t stream) {
-    static bool configured = false;
+    static PerDeviceOnce configured;
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -1389,10 +1393,10 @@ static int launch_pair(tc2::PairArgs& a, cudaStream_t stream) {
     a.aj_rows = aj_rows;
     const tc2::Map M = tc2::make_map(a.Kpad, cap, aj_rows);
     const size_t smem = (size_t)M.total_bytes + 1024;
-    if (!configured) {
+    if (configured.needed()) {
         cudaError_t e = cudaFuncSetAttribute(tc2::egnn_pair_tc_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(pair_tc): %s", cudaGetErrorString(e));
-        configured = true;
+        configured.mark();
     }
     const int want = (a.B + tc2::kEngines - 1) / tc2::kEngines;
     const int grid = want < num_sms() ? want : num_sms();
@@ -1418,11 +1422,11 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
         tc2::node_mid_image_kernel<<<8, 256, 0, stream>>>(params, P, w.nm_image);
         PMHC_CHECK_LAUNCH("node_mid_image");
         const size_t smem = (size_t)(((P * 23 + 3) & ~3) + 2 * kHid * 23 + kN * 23 + 1 + 128 * 23) * sizeof(float);
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce configured;
+        if (configured.needed()) {
             cudaError_t e = cudaFuncSetAttribute(tc2::node_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(node_pre): %s", cudaGetErrorString(e));
-            configured = true;
+            configured.mark();
         }
         tc2::node_pre_kernel<<<B, 128, smem, stream>>>(params, bt->features, bt->pocket_features, bt->pocket_mask, P, w.cls_stride,
                                                        w.pk_cache, w.cls, w.aij1);
@@ -1433,6 +1437,7 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
     tc2::PairArgs a{};
     a.B = B; a.P = P; a.Kpad = pad_k(P);
     a.t_over_T = t_over_T;
+    a.t_dev = step_t_dev();
     a.frames_in = bt->frames; a.tors_in = bt->torsions; a.mask = bt->mask;
     a.pocket_frames = bt->pocket_frames; a.pocket_cls = w.cls; a.cls_stride = w.cls_stride; a.pk_cache = w.pk_cache;
     a.aij = w.aij1; a.wimage = w.wimage;
@@ -1443,13 +1448,13 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
     int rc = launch_pair<0>(a, stream);
     if (rc != 0) return rc;
     {
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce configured;
+        if (configured.needed()) {
             cudaError_t e = cudaFuncSetAttribute(tc2::node_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::NM_BYTES);
             PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(node_mid): %s", cudaGetErrorString(e));
-            configured = true;
+            configured.mark();
         }
-        tc2::NodeMidArgs n{w.nm_image, B, P, t_over_T, w.ssum, bt->features, bt->mask, w.aij2, feat1_out, msum_out};
+        tc2::NodeMidArgs n{w.nm_image, B, P, t_over_T, w.ssum, bt->features, bt->mask, w.aij2, feat1_out, msum_out, step_t_dev()};
         const int grid = (B * kN + 127) / 128;
         tc2::node_mid_kernel<<<grid, 128, tc2::NM_BYTES, stream>>>(n);
         PMHC_CHECK_LAUNCH("node_mid");

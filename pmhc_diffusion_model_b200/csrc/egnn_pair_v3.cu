@@ -50,6 +50,7 @@ enum { NB_REQ_ALL = 0, NB_REQ_A2, NB_REQ_B3, NB_REQ_A4, NB_ENG, NB_ENG_ALL, kNam
 struct PairArgs {
     int B, P, Kpad, n_eng;
     float t_over_T;
+    const float* t_dev;              // nullable: t / T in device memory (see time_feature)
     const float* params;             // flat parameter buffer (torsion_mlp.0's torsion columns are read per complex)
     const float* frames_in;          // [B,16,7]
     const float* tors_in;            // [B,16,14]
@@ -547,21 +548,31 @@ __device__ __forceinline__ void mma_sums(const Engine& E, uint32_t esu, uint32_t
 }
 
 // per-complex work list, identically derived by the compute threads and the issuing warp
+// Tiles lie on a GLOBAL grid of the complex's pair stream (pair g = row * W + entry over all real rows): a part that starts at row
+// rbeg (the row-split tail of a launch) begins inside tile G0 / 128 with its leading lanes inactive.  A row's pairs then fall
+// into the same tiles, at the same lanes, whether the complex is processed whole or in parts — with the fixed summation order
+// inside a tile and the tile-by-tile merge this makes every row's result independent of the schedule, bit for bit (sharded
+// sampling == unsharded).  The message-only pairs of layer 1 use the same construction.
 struct Plan {
-    int L, W, rbeg, rend, G, ntiles, msg_w, msg_tiles;
+    int L, W, rbeg, rend, G0, G1, t0, ntiles, msg_w, M0, M1, mt0, msg_tiles;
 };
 __device__ __forceinline__ Plan make_plan(const ComplexInfo& ci, const Work& wk, bool layer1) {
     Plan p;
     p.L = ci.L;
     p.W = (ci.L - 1) + ci.nv;
     part_rows(wk, ci.L, p.rbeg, p.rend);
-    p.G = (p.rend - p.rbeg) * p.W;
-    p.ntiles = (p.G + kTile - 1) / kTile;
+    p.G0 = p.rbeg * p.W;
+    p.G1 = p.rend * p.W;
+    p.t0 = p.G0 / kTile;
+    p.ntiles = p.G1 > p.G0 ? (p.G1 + kTile - 1) / kTile - p.t0 : 0;
     // message-only pairs (model.py:151 sums over ALL slots): self, masked peptide slots, masked pocket slots with their own
     // features, one shared message for the c0 zero-feature masked pocket slots (multiplicity <= 1024 stays exact in fp16)
     const int nshared = ci.c0 > 1024 ? 2 : (ci.c0 > 0 ? 1 : 0);
     p.msg_w = 1 + (kN - ci.L) + ci.nx + nshared;
-    p.msg_tiles = layer1 ? ((p.rend - p.rbeg) * p.msg_w + kTile - 1) / kTile : 0;
+    p.M0 = p.rbeg * p.msg_w;
+    p.M1 = p.rend * p.msg_w;
+    p.mt0 = p.M0 / kTile;
+    p.msg_tiles = layer1 && p.M1 > p.M0 ? (p.M1 + kTile - 1) / kTile - p.mt0 : 0;
     return p;
 }
 
@@ -629,10 +640,11 @@ __device__ inline ComplexInfo setup_engine(Engine& E, int b, long long* ts_buf, 
         const float* misc = reinterpret_cast<const float*>(E.smem + M.MISC);
         float* ai = reinterpret_cast<float*>(E.es + M.AI);
         float* aj = reinterpret_cast<float*>(E.es + M.AJS);
+        const float tt = time_feature(a);
         for (int idx = et; idx < kN * 64; idx += kEngThreads) {
             const int i = idx >> 6, k = idx & 63;
-            ai[swz64(i, k)] = fmaf(a.t_over_T, misc[MS_TIME_I + k], ai[swz64(i, k)]);
-            aj[swz64(i, k)] = fmaf(a.t_over_T, misc[MS_TIME_J + k], aj[swz64(i, k)]);
+            ai[swz64(i, k)] = fmaf(tt, misc[MS_TIME_I + k], ai[swz64(i, k)]);
+            aj[swz64(i, k)] = fmaf(tt, misc[MS_TIME_J + k], aj[swz64(i, k)]);
         }
     }
     {   // torsion term of the torsion head, per peptide row: T[i][n] = b[n] + W_t[n, 64:78] . tors_i (model.py:260), fp16 terms.
@@ -848,7 +860,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                 const ComplexInfo ci = setup_engine<LAYER, TERMS>(E, b, ts_on ? ts_buf : nullptr, &ts_n);
                 PMHC_TS(2);
                 const Plan pl = make_plan(ci, wk, LAYER == 0);
-                const int L = pl.L, W = pl.W, G = pl.G;
+                const int L = pl.L, W = pl.W;
                 float* lsave = a.logit_out ? a.logit_out + (size_t)b * kN * a.Kpad : nullptr;
                 // layer 1 (group A): thread 64 h + f holds feature f of the message sums of rows 0..15 over the tile halves h
                 float ssum[kN];
@@ -861,21 +873,22 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     for (int i = 0; i < kN; ++i) ssum[i] += v[i];
                 };
 
-                // pair g of the part = (row rl = g / W, entry e = g % W): peptide neighbours first, then the valid pocket slots
+                // pair g of the complex = (row rl = g / W, entry e = g % W): peptide neighbours first, then the valid pocket slots
                 const int adv_q = W > 0 ? kTile / W : 0, adv_r = W > 0 ? kTile - adv_q * W : 0;
-                int cur_rl = W > 0 ? r / W : 0, cur_e = W > 0 ? r - cur_rl * W : 0;
-                const int last_rl = W > 0 ? (G - 1) / W : 0, last_e = W > 0 ? (G - 1) - last_rl * W : 0;
+                const int g_first = pl.t0 * kTile + r;
+                int cur_rl = W > 0 ? g_first / W : 0, cur_e = W > 0 ? g_first - cur_rl * W : 0;
                 auto decode = [&](int t, int& rl_out) {     // tile t's pair of this thread; advances the running (row, entry)
                     PairRef p;
-                    p.active = t * kTile + r < G;
+                    const int g = (pl.t0 + t) * kTile + r;
+                    p.active = g >= pl.G0 && g < pl.G1;
                     int rl = cur_rl, e = cur_e;
-                    if (!p.active) { rl = last_rl; e = last_e; }   // idle lanes of the last tile repeat its last pair
+                    if (g < pl.G0) { rl = pl.rbeg; e = 0; }                    // idle lanes repeat the part's first / last pair
+                    if (g >= pl.G1) { rl = pl.rend - 1; e = W - 1; }
                     cur_rl += adv_q;
                     cur_e += adv_r;
                     if (cur_e >= W) { cur_e -= W; ++cur_rl; }
-                    const int rr = pl.rbeg + rl;
-                    p.i = I[IN_ROWS + rr];
-                    p.j = e < L - 1 ? I[IN_ROWS + (e < rr ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
+                    p.i = I[IN_ROWS + rl];
+                    p.j = e < L - 1 ? I[IN_ROWS + (e < rl ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
                     rl_out = rl;
                     return p;
                 };
@@ -885,7 +898,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                 //   after H1(t)        : head epilogues of tile t; in the shadow of the second-layer contractions each group stages ITS
                 //                        half of tile t + 1 (the pair tile is free once the translation head has read it)
                 int par = 0;             // parity of the tile whose outputs are being produced: its copy of Mrow / Mtile
-                int row0 = 0, off0 = 0;  // the tile being MERGED starts `off0` pairs into row `row0` of the part (same in every thread)
+                int row0 = pl.rbeg, off0 = 0;  // the lanes being MERGED start `off0` pairs into row `row0` (same in every thread)
                 int rl = 0, rl_next = 0, rl_prev = 0;
                 PairRef pr{}, nxt{};
                 auto stage_tile = [&](const PairRef& p) {
@@ -903,18 +916,19 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                 // streaming softmax: column c of the running sums (0: sum of weights, 1..14: weighted head outputs); 16 lanes walk each
                 // row segment of the tile, then the row's state is rescaled to the new maximum and updated
                 auto merge_tile = [&](int mt, int mpar, int my_rl) {
-                    const int ntile = G - mt * kTile < kTile ? G - mt * kTile : kTile;
+                    const int tg = (pl.t0 + mt) * kTile;
+                    const int p_lo = pl.G0 > tg ? pl.G0 - tg : 0, p_hi = pl.G1 - tg < kTile ? pl.G1 - tg : kTile;   // the part's lanes of the tile
                     if (grpA) {     // this thread's pair: logit -> softmax weight against its row's new maximum, in place
                         float wgt = 0.0f;
-                        if (r < ntile) wgt = soft_exp(Lg[r] - fmaxf(Mrow[mpar * kN + my_rl], dec_max(Mtile[mpar * kN + my_rl])));
+                        if (r >= p_lo && r < p_hi) wgt = soft_exp(Lg[r] - fmaxf(Mrow[mpar * kN + my_rl], dec_max(Mtile[mpar * kN + my_rl])));
                         Lg[r] = wgt;
                     }
                     PMHC_TS(40);
                     E.sync_eng();
                     const int c = et >> 4, k16 = et & 15;
                     PMHC_TS(41);
-                    int s_row = row0, pos = 0, len = W - off0 < ntile ? W - off0 : ntile;
-                    while (pos < ntile) {
+                    int s_row = row0, pos = p_lo, len = W - off0 < p_hi - p_lo ? W - off0 : p_hi - p_lo;
+                    while (pos < p_hi) {
                         float acc = 0.0f;
                         if (c == 0) {
                             for (int p = pos + k16; p < pos + len; p += 16) acc += Lg[p];
@@ -932,14 +946,14 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         }
                         pos += len;
                         ++s_row;
-                        len = W < ntile - pos ? W : ntile - pos;
+                        len = W < p_hi - pos ? W : p_hi - pos;
                     }
                     PMHC_TS(42);
                     if (et < kN) {
                         Mrow[(mpar ^ 1) * kN + et] = fmaxf(Mrow[mpar * kN + et], dec_max(Mtile[mpar * kN + et]));
                         Mtile[(mpar ^ 1) * kN + et] = kEncNegInf;   // free since the tile before; the next tile's maxima go there
                     }
-                    off0 += kTile;
+                    off0 += p_hi - p_lo;
                     while (off0 >= W) { off0 -= W; ++row0; }
                     PMHC_TS(43);
                 };
@@ -1051,9 +1065,9 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                 E.sync_eng();
                 {
                     // finished rows: normalise the running sums and apply the updates (model.py:263-269, 300-310, 331)
-                    const int rl = et >> 4, l16 = et & 15;
-                    if (rl < pl.rend - pl.rbeg) {
-                        const int i = I[IN_ROWS + pl.rbeg + rl];
+                    const int rl = pl.rbeg + (et >> 4), l16 = et & 15;
+                    if (rl < pl.rend) {
+                        const int i = I[IN_ROWS + rl];
                         const float* st = St + rl * 16;
                         const float se = st[0];
                         const float inv = W > 0 ? 1.0f / se : 0.0f;
@@ -1087,14 +1101,14 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                 }
 
                 if (LAYER == 0) {
-                    const int npx = kN - L, W2 = pl.msg_w, total = (pl.rend - pl.rbeg) * W2;
-                    for (int tile_base = 0; tile_base < total; tile_base += kTile) {
-                        const int gp0 = tile_base + r;
-                        const bool act = gp0 < total;
-                        const int gp = act ? gp0 : tile_base;
+                    const int npx = kN - L, W2 = pl.msg_w;
+                    for (int mt = 0; mt < pl.msg_tiles; ++mt) {
+                        const int gp0 = (pl.mt0 + mt) * kTile + r;
+                        const bool act = gp0 >= pl.M0 && gp0 < pl.M1;
+                        const int gp = gp0 < pl.M0 ? pl.M0 : (gp0 >= pl.M1 ? pl.M1 - 1 : gp0);
                         const int rl = gp / W2, e = gp - rl * W2;
                         PairRef pr;
-                        pr.i = I[IN_ROWS + pl.rbeg + rl];
+                        pr.i = I[IN_ROWS + rl];
                         pr.active = act;
                         float mult = 1.0f;
                         if (e == 0) pr.j = pr.i;
@@ -1278,6 +1292,7 @@ struct NodeMid3Args {
     float* aij2;              // [B,2,16,64]
     float* feat1_out;         // nullable: [B,16,64] relu(o1)   (saved for the backward pass)
     float* msum_out;          // nullable: [B,16,64]
+    const float* t_dev;       // nullable: t / T in device memory (see time_feature)
 };
 template <int TERMS>
 struct Nm3 {
@@ -1378,8 +1393,8 @@ __global__ void __launch_bounds__(128, 1) node_mid3_kernel(NodeMid3Args a) {
         const float* f = a.feat + (in ? node : 0) * PMHC_NFEAT;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-            const float x0 = 2 * c < PMHC_NFEAT ? (in ? f[2 * c] : 0.0f) : (2 * c == PMHC_NFEAT ? a.t_over_T : 0.0f);
-            const float x1 = 2 * c + 1 < PMHC_NFEAT ? (in ? f[2 * c + 1] : 0.0f) : (2 * c + 1 == PMHC_NFEAT ? a.t_over_T : 0.0f);
+            const float x0 = 2 * c < PMHC_NFEAT ? (in ? f[2 * c] : 0.0f) : (2 * c == PMHC_NFEAT ? time_feature(a) : 0.0f);
+            const float x1 = 2 * c + 1 < PMHC_NFEAT ? (in ? f[2 * c + 1] : 0.0f) : (2 * c + 1 == PMHC_NFEAT ? time_feature(a) : 0.0f);
             if (TERMS > 1) tc::split_f16x2(x0, x1, hf[c], lf[c]);
             else { hf[c] = tc::pack_f16x2(x0, x1); lf[c] = 0u; }
         }
@@ -1592,6 +1607,7 @@ static int forward_tc3_impl(const float* params, const PmhcBatch* bt, float t_ov
     tc3::PairArgs a{};
     a.B = B; a.P = P; a.Kpad = pad_k(P);
     a.t_over_T = t_over_T;
+    a.t_dev = step_t_dev();
     a.params = params;
     a.frames_in = bt->frames; a.tors_in = bt->torsions; a.mask = bt->mask;
     a.pocket_frames = bt->pocket_frames; a.pocket_cls = w.cls; a.cls_stride = w.cls_stride; a.pk32 = w.pk32;
@@ -1603,7 +1619,7 @@ static int forward_tc3_impl(const float* params, const PmhcBatch* bt, float t_ov
     int rc = launch_pair3<0, TERMS>(a, d, stream);
     if (rc != 0) return rc;
     {
-        tc3::NodeMid3Args n{w.nm_image, B, P, t_over_T, w.ssum, bt->features, bt->mask, w.aij2, feat1_out, msum_out};
+        tc3::NodeMid3Args n{w.nm_image, B, P, t_over_T, w.ssum, bt->features, bt->mask, w.aij2, feat1_out, msum_out, step_t_dev()};
         const int grid = (B * kN + 127) / 128;
         tc3::node_mid3_kernel<TERMS><<<grid, 128, tc3::Nm3<TERMS>::BYTES, stream>>>(n);
         PMHC_CHECK_LAUNCH("node_mid3");

@@ -63,7 +63,7 @@ class _DenoiserFn(torch.autograd.Function):
     the reference never differentiates w.r.t. the noised inputs, optimizer.py:205-222)."""
 
     @staticmethod
-    def forward(ctx, model, t_over_T, frames7, torsions, features, mask, pocket7, pocket_features, pocket_mask, *params):
+    def forward(ctx, model, grad_mode, t_over_T, frames7, torsions, features, mask, pocket7, pocket_features, pocket_mask, *params):
         lib = _lib.load()
         desc, keep = _lib.make_batch(frames7, torsions, features, mask, pocket7, pocket_features, pocket_mask)
         dev = keep[0].device
@@ -71,7 +71,9 @@ class _DenoiserFn(torch.autograd.Function):
         B, P = desc.B, desc.P
         out_frames = torch.empty(B, _lib.N, 7, device=dev, dtype=torch.float32)
         out_tors = torch.empty(B, _lib.N, _lib.NTORS, 2, device=dev, dtype=torch.float32)
-        need_grad = any(ctx.needs_input_grad[9:])  # (grad mode is always off inside Function.forward)
+        # grad mode is always off inside Function.forward and needs_input_grad ignores torch.no_grad(): the caller's mode is
+        # passed in, so inference does not allocate (or make the kernels fill) the saved-for-backward buffer
+        need_grad = grad_mode and any(ctx.needs_input_grad[10:])
         saved = torch.empty(lib.pmhc_saved_floats(B, P), device=dev, dtype=torch.float32) if need_grad else None
         ws_bytes = lib.pmhc_workspace_bytes(B, P)
         ws = _lib.workspace(dev, ws_bytes)
@@ -105,7 +107,7 @@ class _DenoiserFn(torch.autograd.Function):
                                                   ws_bytes, _lib.stream_ptr(dev), None, model.backward_precision_code()),
                        "pmhc_model_backward")
         grads = model._split_flat(grad)
-        return (None,) * 9 + tuple(grads)
+        return (None,) * 10 + tuple(grads)
 
 
 class Model(torch.nn.Module):
@@ -206,7 +208,7 @@ class Model(torch.nn.Module):
         pocket7 = _as_tensor7(batch["pocket_frames"])
         params = tuple(self.parameters())
         out_frames, out_tors = _DenoiserFn.apply(
-            self, float(t) / float(self.T), frames7, batch["torsions"], batch["features"], batch["mask"],
+            self, torch.is_grad_enabled(), float(t) / float(self.T), frames7, batch["torsions"], batch["features"], batch["mask"],
             pocket7, batch["pocket_features"], batch["pocket_mask"], *params)
         return {
             "frames": Rigid(Rotation(quats=out_frames[..., :4], normalize_quats=False), out_frames[..., 4:]),

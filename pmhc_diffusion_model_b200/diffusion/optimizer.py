@@ -106,7 +106,7 @@ class FlatAdam(torch.optim.Adam):
         self._generation = -1          # the loaded moments are fresh tensors: copied into the flat buffers at the next step
 
     @torch.no_grad()
-    def step(self, closure=None, flat_grad: Optional[torch.Tensor] = None):
+    def step(self, closure=None, flat_grad: Optional[torch.Tensor] = None, skip_flag: Optional[torch.Tensor] = None):
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -151,9 +151,10 @@ class FlatAdam(torch.optim.Adam):
         dev = flat.device
         with torch.cuda.device(dev):
             for lo, hi, k in runs:
-                _lib.check(lib.pmhc_adam_step(flat.data_ptr() + 4 * lo, flat_grad.data_ptr() + 4 * lo, self._m.data_ptr() + 4 * lo,
-                                              self._v.data_ptr() + 4 * lo, hi - lo, float(group["lr"]), float(b1), float(b2),
-                                              float(group["eps"]), k, _lib.stream_ptr(dev)), "pmhc_adam_step")
+                # skip_flag (one device byte): non-zero = a non-finite loss was seen, leave weights and moments untouched
+                _lib.check(lib.pmhc_adam_step_guarded(flat.data_ptr() + 4 * lo, flat_grad.data_ptr() + 4 * lo, self._m.data_ptr() + 4 * lo,
+                                                      self._v.data_ptr() + 4 * lo, hi - lo, float(group["lr"]), float(b1), float(b2),
+                                                      float(group["eps"]), k, _lib.ptr(skip_flag), _lib.stream_ptr(dev)), "pmhc_adam_step")
         return loss
 
 
@@ -199,9 +200,12 @@ class DiffusionModelOptimizer:
 
     # ---- noise --------------------------------------------------------------------------------------------
     @staticmethod
-    def gen_noise(shape: Union[List[int], Tuple[int]], device: torch.device) -> Dict[str, Union[Rigid, torch.Tensor]]:
+    def gen_noise(shape: Union[List[int], Tuple[int]], device: torch.device, key: Optional[int] = None,
+                  first_residue: int = 0) -> Dict[str, Union[Rigid, torch.Tensor]]:
         """optimizer.py:93-108: translation 5*N(0,I), uniform rotation (Shoemake), 7 uniform torsion angles.
-        Philox counter stream instead of torch's generator (statistically identical, not bitwise)."""
+        Philox counter stream instead of torch's generator (statistically identical, not bitwise).  `key` (default: drawn from
+        torch's CPU generator) and `first_residue` select the counter range: residue r of the call uses counter first_residue + r,
+        so shards of one global batch (same key, first_residue = 16 x the shard's first complex) draw what one call would."""
         lib = _lib.load()
         device = torch.device(device)
         if device.type != "cuda":
@@ -213,7 +217,8 @@ class DiffusionModelOptimizer:
         frames = torch.empty(shape + [7], device=device, dtype=torch.float32)
         tors = torch.empty(shape + [_lib.NTORS, 2], device=device, dtype=torch.float32)
         with torch.cuda.device(device):
-            _lib.check(lib.pmhc_gen_noise(_next_noise_key(), 0, n, frames.data_ptr(), tors.data_ptr(), _lib.stream_ptr(device)), "pmhc_gen_noise")
+            _lib.check(lib.pmhc_gen_noise(_next_noise_key() if key is None else int(key), int(first_residue), n, frames.data_ptr(),
+                                          tors.data_ptr(), _lib.stream_ptr(device)), "pmhc_gen_noise")
         return {"frames": _rigid(frames), "torsions": tors}
 
     @staticmethod
@@ -273,10 +278,12 @@ class DiffusionModelOptimizer:
 
     # ---- training step --------------------------------------------------------------------------------------
     def optimize(self, batch: Dict[str, Union[Rigid, torch.Tensor]], metrics: Optional[MetricsRecord] = None,
-                 t: Optional[int] = None, noise: Optional[Dict] = None):
+                 t: Optional[int] = None, noise: Optional[Dict] = None, noise_key: Optional[int] = None,
+                 noise_first_complex: int = 0, loss_scale: Optional[float] = None):
         """One training step (optimizer.py:195-224): draw t and noise, noise the batch, predict, loss, backward,
-        Adam.  `t` / `noise` may be pinned by the caller (parity tests, data-parallel ranks sharing one t).
-        Six fused launches + Adam; no autograd graph is built."""
+        Adam.  `t` / `noise` may be pinned by the caller (parity tests, data-parallel ranks sharing one t); data-parallel ranks
+        also pass the shared Philox key with their shard's first global complex, and loss_scale = 1 / B_global (default 1 / B:
+        total_loss.mean(), optimizer.py:222).  Six fused launches + Adam; no autograd graph is built."""
         lib = _lib.load()
         if t is None:
             t = random.randint(0, self.noise_step_count - 1)  # optimizer.py:197
@@ -290,7 +297,7 @@ class DiffusionModelOptimizer:
         frames7 = _lib.f32c(batch["frames"].to_tensor_7())
         dev = frames7.device
         if noise is None:
-            noise = self.gen_noise(frames7.shape[:-1], dev)
+            noise = self.gen_noise(frames7.shape[:-1], dev, key=noise_key, first_residue=noise_first_complex * _lib.N)
         zt = self.add_noise(batch, noise, t)
 
         desc, keep = _lib.make_batch(zt["frames"].to_tensor_7(), zt["torsions"], batch["features"], batch["mask"],
@@ -315,7 +322,8 @@ class DiffusionModelOptimizer:
             # total_loss.mean().backward() (optimizer.py:222): gradient scale 1/B
             _lib.check(lib.pmhc_loss(true_f.data_ptr(), true_t.data_ptr(), pred_f.data_ptr(), pred_t.data_ptr(),
                                      _lib.u8c(batch["mask"]).data_ptr(), _lib.u8c(batch["torsions_mask"]).data_ptr(), B,
-                                     1.0 / B, losses.data_ptr(), d_f.data_ptr(), d_t.data_ptr(), stream), "pmhc_loss")
+                                     1.0 / B if loss_scale is None else float(loss_scale), losses.data_ptr(), d_f.data_ptr(),
+                                     d_t.data_ptr(), stream), "pmhc_loss")
             _lib.check(lib.pmhc_model_backward_ex(flat.data_ptr(), ctypes.byref(desc), t_over_T, saved.data_ptr(), d_f.data_ptr(),
                                                   d_t.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes, stream,
                                                   self.layer2_event_handle(), model.backward_precision_code()), "pmhc_model_backward")
@@ -324,12 +332,17 @@ class DiffusionModelOptimizer:
         if metrics is not None:
             metrics.add_batch(loss_dict)
         self.last_losses = loss_dict
-        self._nan_flag = losses[0].isnan().any()  # checked lazily: see check_nan()
+        # sticky and checked lazily (check_nan()); from the first NaN loss on, every Adam update is skipped on the device, so the
+        # weights in memory (and whatever gets saved from them) stay the last finite ones — the reference raises before
+        # backward() / step() (optimizer.py:217-218)
+        flag = losses[0].isnan().any().view(1)
+        prev = getattr(self, "_nan_flag", None)
+        self._nan_flag = flag if prev is None or prev.device != flag.device else (prev | flag)
 
         for p, g in zip(model.parameters(), model._split_flat(grad)):
             p.grad = g
         self.grad_hook(grad)
-        self.optimizer.step(flat_grad=grad)
+        self.optimizer.step(flat_grad=grad, skip_flag=self._nan_flag.view(torch.uint8))
 
     def grad_hook(self, flat_grad: torch.Tensor) -> None:
         """Called with the flat gradient before the Adam step; data-parallel wrappers all-reduce here."""
@@ -341,7 +354,7 @@ class DiffusionModelOptimizer:
     def check_nan(self) -> None:
         """The reference raises RuntimeError("NaN loss") inside optimize() (optimizer.py:217-218) at the price of a
         host sync per step; here the flag stays on the device until asked for."""
-        if getattr(self, "_nan_flag", None) is not None and bool(self._nan_flag):
+        if getattr(self, "_nan_flag", None) is not None and bool(self._nan_flag.any()):
             raise RuntimeError("NaN loss")
 
     # ---- full training state (SURVEY.md §8f: the reference only saves model.state_dict(), optimize.py:75-80) -----------

@@ -64,10 +64,15 @@ def noise_gpu(api, n):
 # denoiser forward
 # ------------------------------------------------------------------------------------------------------------
 
+PARITY_MODES = ["fp32", "tc32"]   # both gated at the reference's fp32 tolerance: FFMA, and tcgen05 with fp16 hi + lo operand splits
+
+
+@pytest.mark.parametrize("precision", PARITY_MODES)
 @pytest.mark.parametrize("name", ["fwd_shipped_p80.pt", "fwd_random_p96.pt", "fwd_shipped_p192.pt"])
-def test_forward_matches_reference_fixture(api, name):
+def test_forward_matches_reference_fixture(api, name, precision):
     case = load_case(name)
     model = make_model(api, case["params"], case["T"])
+    model.precision = precision
     with torch.no_grad():
         out = model(gpu_batch(case["batch"]), case["t"])
     m = case["batch"]["mask"]
@@ -84,10 +89,12 @@ def test_forward_matches_reference_fixture(api, name):
     (2, (8, 15), (300, 400), 400, 23),  # class-II sized pocket (several softmax row groups)
     (64, (8, 15), (50, 80), 80, 24),    # more complexes than fit one wave of rows
 ])
-def test_forward_matches_oracle_edge_shapes(api, B, L, Pn, P_pad, seed):
+@pytest.mark.parametrize("precision", PARITY_MODES)
+def test_forward_matches_oracle_edge_shapes(api, B, L, Pn, P_pad, seed, precision):
     batch = orc.synthetic_batch(B, L, Pn, P_pad=P_pad, seed=seed)
     params = orc.random_params(seed=seed)
     model = make_model(api, params, 100)
+    model.precision = precision
     with torch.no_grad():
         out = model(gpu_batch(batch), 42)
         ref = orc.model_forward(params, orc.batch_to_frames(batch), 42, 100)
@@ -101,7 +108,8 @@ def test_forward_matches_oracle_edge_shapes(api, B, L, Pn, P_pad, seed):
     assert torch.isfinite(out["frames"].to_tensor_7()).all() and torch.isfinite(out["torsions"]).all()
 
 
-def test_forward_unordered_masks_and_dirty_padding(api):
+@pytest.mark.parametrize("precision", PARITY_MODES)
+def test_forward_unordered_masks_and_dirty_padding(api, precision):
     """Masks need not be prefixes and padded pocket slots need not carry zero features: the unmasked message
     sum (model.py:151, T3) still sees them."""
     g = torch.Generator().manual_seed(5)
@@ -115,6 +123,7 @@ def test_forward_unordered_masks_and_dirty_padding(api):
         batch[k] = batch[k][:, perm_n]
     params = orc.random_params(seed=8)
     model = make_model(api, params, 100)
+    model.precision = precision
     with torch.no_grad():
         out = model(gpu_batch(batch), 9)
         ref = orc.model_forward(params, orc.batch_to_frames(batch), 9, 100)
@@ -123,10 +132,12 @@ def test_forward_unordered_masks_and_dirty_padding(api):
     assert rel_err(out["torsions"].cpu()[m], ref["torsions"][m]) < TOL
 
 
-def test_forward_batch_split_invariance_full_size(api):
+@pytest.mark.parametrize("precision", PARITY_MODES)
+def test_forward_batch_split_invariance_full_size(api, precision):
     """B = 256 (BASELINE config 3): the batched launch equals two half launches bit for bit."""
     batch = orc.synthetic_batch(256, 9, 60, P_pad=80, seed=77)
     model = make_model(api, orc.random_params(seed=1), 1000)
+    model.precision = precision
     gb = gpu_batch(batch)
     with torch.no_grad():
         full = model(gb, 500)
@@ -271,11 +282,14 @@ def test_loss_gradient_matches_autograd_of_oracle(api):
 # training step: gradients and Adam
 # ------------------------------------------------------------------------------------------------------------
 
+@pytest.mark.parametrize("precision", PARITY_MODES)
 @pytest.mark.parametrize("name", ["train_shipped_p80.pt", "train_random_p80.pt"])
-def test_parameter_gradients_match_reference_fixture(api, name):
-    """All 44 gradient-carrying tensors of loss.mean().backward() (optimizer.py:222), through the autograd bridge."""
+def test_parameter_gradients_match_reference_fixture(api, name, precision):
+    """All 44 gradient-carrying tensors of loss.mean().backward() (optimizer.py:222), through the autograd bridge.
+    precision = "tc32": the tcgen05 forward saves the softmax statistics, the fp32 backward recomputes the pairs."""
     case = load_case(name)
     model = make_model(api, case["params"], case["T"])
+    model.precision = precision
     dm = api.DMO(case["T"], model, 1e-3)
     dm.quat_sign_ref = case["zt_quats"].to(DEV)
     gb = gpu_batch(case["batch"])
@@ -498,6 +512,123 @@ def test_training_step_batch_linearity_full_size(api):
     assert float((full - half).abs().max()) < 1e-5 * max(1.0, float(full.abs().max()))
 
 
+def test_uneven_shards_with_global_loss_scale_sum_to_the_full_batch_gradient(api):
+    """What the data-parallel step relies on (diffusion/parallel.py): shards of unequal size (5 + 4 complexes), each with
+    loss_scale = 1 / B_global and the noise of its GLOBAL complexes (shared Philox key, first = the shard's first complex),
+    give gradients whose plain SUM is the single-process gradient on the concatenated batch."""
+    T, B = 1000, 9
+    batch = orc.synthetic_batch(B, (8, 12), (40, 60), P_pad=80, seed=111)
+    params = orc.random_params(seed=16)
+    gb = gpu_batch(batch)
+    key = 123456789
+
+    def grads(lo, hi, scale):
+        model = make_model(api, params, T)
+        dm = api.DMO(T, model, 0.0)
+        captured = {}
+        dm.grad_hook = lambda g: captured.setdefault("g", g.clone())
+        dm.optimize({k: v[lo:hi] for k, v in gb.items()}, None, t=400, noise_key=key, noise_first_complex=lo, loss_scale=scale)
+        return captured["g"]
+
+    full = grads(0, B, None)
+    parts = grads(0, 5, 1.0 / B) + grads(5, B, 1.0 / B)
+    assert float((full - parts).abs().max()) < 1e-5 * max(1.0, float(full.abs().max()))
+    # the noise itself: shards of one keyed draw are slices of the full draw, bit for bit
+    n_full = api.DMO.gen_noise([B, 16], torch.device(DEV), key=key)
+    n_hi = api.DMO.gen_noise([B - 5, 16], torch.device(DEV), key=key, first_residue=5 * 16)
+    assert torch.equal(n_full["frames"].to_tensor_7()[5:], n_hi["frames"].to_tensor_7())
+    assert torch.equal(n_full["torsions"][5:], n_hi["torsions"])
+
+
+def test_nan_loss_is_sticky_and_never_reaches_the_weights(api):
+    """The reference raises RuntimeError("NaN loss") before backward() / step() (optimizer.py:217-218).  Here the flag stays on
+    the device: from the first NaN loss on every Adam update is skipped (weights and moments keep their last finite values), the
+    flag survives later finite steps, and check_nan() raises."""
+    T = 100
+    batch = orc.synthetic_batch(4, 9, 40, P_pad=48, seed=7)
+    model = make_model(api, orc.random_params(seed=2), T)
+    dm = api.DMO(T, model, 1e-3)
+    gb = gpu_batch(batch)
+    dm.optimize(dict(gb), None, t=40)
+    dm.check_nan()
+    good = model._flat_params().clone()
+    m_good = dm.optimizer._m.clone()
+    bad = dict(gb)
+    bad["frames"] = gb["frames"].clone()
+    bad["frames"][1, 3, 5] = float("nan")       # a translation: reaches the loss through z_t, the distances and the x update
+    dm.optimize(bad, None, t=40)
+    assert torch.equal(model._flat_params(), good) and torch.equal(dm.optimizer._m, m_good)
+    dm.optimize(dict(gb), None, t=41)          # a later finite step does not clear the flag, and does not step either
+    assert torch.equal(model._flat_params(), good)
+    with pytest.raises(RuntimeError, match="NaN loss"):
+        dm.check_nan()
+
+
+def _dp_worker(rank, world, port, params, batch, steps, out):
+    import os
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from pmhc_diffusion_model_b200.diffusion.model import Model
+        from pmhc_diffusion_model_b200.diffusion.optimizer import DiffusionModelOptimizer
+        from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer, shard_batch
+        model = Model(16, 22, 1000)
+        model.load_state_dict(params, strict=True)
+        model = model.to(dev)
+        dm = DiffusionModelOptimizer(1000, model, 1e-3)
+        trainer = DataParallelTrainer(dm, seed=5)
+        n = batch["mask"].shape[0]
+        for _ in range(steps):
+            local, first = shard_batch({k: v.to(dev) for k, v in batch.items()}, rank, world)
+            trainer.optimize(local, None, global_batch=n, first_complex=first)
+        torch.cuda.synchronize(dev)
+        dm.check_nan()
+        out.put((rank, model._flat_params().cpu()))
+    except Exception as e:  # noqa: BLE001 — surfaced in the parent
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_two_gpus_equals_single_process_on_the_global_batch(api):
+    """SURVEY.md §4 (vi) on real GPUs: two ranks (NCCL), uneven shards (6 + 5 complexes), three optimize() steps ==
+    one process stepping on the 11-complex batch with the same t and noise keys."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    import os
+    import torch.multiprocessing as mp
+    from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer, shared_noise_key, shared_noise_step
+    steps, n = 3, 11
+    batch = orc.synthetic_batch(n, (8, 13), (40, 60), P_pad=80, seed=202)
+    params = orc.random_params(seed=31)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, params, batch, steps, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(out.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert all(isinstance(v, torch.Tensor) for v in results.values()), results
+    assert torch.equal(results[0], results[1])                     # ranks stay in lock-step, bit for bit
+    model = make_model(api, params, 1000)
+    dm = api.DMO(1000, model, 1e-3)
+    gb = gpu_batch(batch)
+    for k in range(steps):
+        dm.optimize(dict(gb), None, t=shared_noise_step(1000, k, 5), noise_key=shared_noise_key(k, 5))
+    single = model._flat_params().cpu()
+    d = (results[0] - single).abs()
+    # Adam turns rounding-level gradient differences (different summation split) into at most +-lr moves on near-zero gradients
+    assert float(d.max()) <= 2.2e-3 * steps
+    assert float((d < 2e-5).float().mean()) > 0.95, float((d < 2e-5).float().mean())
+
+
 # ------------------------------------------------------------------------------------------------------------
 # sampling
 # ------------------------------------------------------------------------------------------------------------
@@ -508,12 +639,14 @@ def _tape(case):
     return tape
 
 
-def test_trajectory_teacher_forced_matches_reference(api):
+@pytest.mark.parametrize("precision", PARITY_MODES)
+def test_trajectory_teacher_forced_matches_reference(api, precision):
     """All reverse steps of the T = 100 fixture, each started from the reference's own z_t (see the oracle test
     of the same name for why free-running parity over 100 steps is impossible for ANY implementation)."""
     case = load_case("trajectory_T100_p80.pt")
     T = case["T"]
     model = make_model(api, case["params"], T)
+    model.precision = precision
     dm = api.DMO(T, model, 0.0)
     gb = gpu_batch(case["batch"])
     m = case["batch"]["mask"]
@@ -534,13 +667,15 @@ def test_trajectory_teacher_forced_matches_reference(api):
     assert worst[0] < 5e-3 and worst[1] < 1e-3 and worst[2] < 1e-3, worst
 
 
-def test_sample_free_running_short_horizon_and_validity(api):
+@pytest.mark.parametrize("precision", PARITY_MODES)
+def test_sample_free_running_short_horizon_and_validity(api, precision):
     """pmhc_sample with the reference's noise and sign tapes: per-residue deviation <= 0.05 A over the first 12
     reverse steps (north_star gate; later steps diverge chaotically for any implementation), and a finite, unit-norm
     final structure after all 100."""
     case = load_case("trajectory_T100_p80.pt")
     T = case["T"]
     model = make_model(api, case["params"], T)
+    model.precision = precision
     start = case["start"]
     tape = _tape(case).to(DEV)
     sign = case["zt_quats"][1:].to(DEV)  # z after step k is the input of model call k+1
@@ -578,13 +713,15 @@ def _run_partial(api, dm, gb, tape, sign, steps):
     return zt
 
 
-def test_sample_equals_stepwise_api_and_shards_bitwise(api):
+@pytest.mark.parametrize("precision", PARITY_MODES)
+def test_sample_equals_stepwise_api_and_shards_bitwise(api, precision):
     """pmhc_sample (one call, T fused steps) == the same steps through Model.forward + remove_noise, and sampling
     a batch in two shards gives bit-identical structures (complexes are independent: no communication needed)."""
     T = 20
     B = 12
     batch = orc.synthetic_batch(B, (8, 15), (40, 80), P_pad=80, seed=55)
     model = make_model(api, orc.random_params(seed=5), T)
+    model.precision = precision
     g = torch.Generator().manual_seed(9)
     start = orc.gen_noise([B, 16], g)
     tape = torch.cat([torch.cat((n["frames"]["quats"], n["frames"]["trans"], n["torsions"].reshape(B, 16, 14)), -1)[None]
@@ -608,6 +745,7 @@ def test_sample_equals_stepwise_api_and_shards_bitwise(api):
 # ------------------------------------------------------------------------------------------------------------
 
 TOL_BF16 = 1e-2
+TC_MODES = [("bf16", TOL_BF16), ("tc32", TOL)]   # (tensor-core forward mode, its gate against the fp32 path / oracle)
 
 
 @pytest.mark.parametrize("B,L,Pn,P_pad,seed", [
@@ -655,11 +793,12 @@ def test_bf16_forward_dirty_padding_and_unordered_masks(api):
     assert rel_err(out["torsions"].cpu()[m], ref["torsions"][m]) < TOL_BF16
 
 
-def test_bf16_sample_runs_and_is_shard_invariant(api):
+@pytest.mark.parametrize("mode,tol", TC_MODES)
+def test_tensor_core_sample_runs_and_is_shard_invariant(api, mode, tol):
     T, B = 20, 10
     batch = orc.synthetic_batch(B, 9, 60, P_pad=80, seed=81)
     model = make_model(api, orc.random_params(seed=5), T)
-    model.precision = "bf16"
+    model.precision = mode
     g = torch.Generator().manual_seed(9)
     start = orc.gen_noise([B, 16], g)
     gb = gpu_batch(batch)
@@ -677,14 +816,15 @@ def test_bf16_sample_runs_and_is_shard_invariant(api):
     assert torch.equal(f, torch.cat((lo["frames"].to_tensor_7(), hi["frames"].to_tensor_7())))
 
 
-def test_bf16_forward_full_rounds_equal_split_tail(api):
+@pytest.mark.parametrize("mode,tol", TC_MODES)
+def test_tensor_core_forward_full_rounds_equal_split_tail(api, mode, tol):
     """The pair kernel deals whole complexes round-robin over its 2 x #SM engines and splits the complexes of a partly
     filled last round by peptide rows (egnn_pair_tc.cu: get_work).  B = 700 runs two full rounds + a split tail; the
     same complexes in chunks of 7 run split only.  A row's result must not depend on which way it was scheduled."""
     B = 700
     batch = orc.synthetic_batch(B, (8, 13), (40, 60), P_pad=80, seed=91)
     model = make_model(api, orc.random_params(seed=12), 100)
-    model.precision = "bf16"
+    model.precision = mode
     gb = gpu_batch(batch)
     with torch.no_grad():
         full = model(dict(gb), 33)
@@ -699,8 +839,8 @@ def test_bf16_forward_full_rounds_equal_split_tail(api):
     with torch.no_grad():
         ref = model(dict(gb), 33)
     m = batch["mask"].to(DEV)
-    assert rel_err(f[m], ref["frames"].to_tensor_7()[m]) < TOL_BF16
-    assert rel_err(t[m], ref["torsions"][m]) < TOL_BF16
+    assert rel_err(f[m], ref["frames"].to_tensor_7()[m]) < tol
+    assert rel_err(t[m], ref["torsions"][m]) < tol
 
 
 def test_bf16_forward_training_gradients_vs_oracle_autograd(api):
@@ -742,14 +882,15 @@ def test_bf16_forward_training_gradients_vs_oracle_autograd(api):
     assert worst > 0.0      # the bf16 forward really ran
 
 
-def test_bf16_forward_mixed_sizes_and_large_batch_schedule(api):
+@pytest.mark.parametrize("mode,tol", TC_MODES)
+def test_tensor_core_forward_mixed_sizes_and_large_batch_schedule(api, mode, tol):
     """The pair kernels deal complexes largest-first (order_kernel: stable counting sort up to 4 096 complexes, first come
     first placed above).  Every complex must be processed exactly once and its rows must not depend on the schedule:
     a 4 500-complex batch of mixed sizes equals the same complexes run in slices, bitwise."""
     B = 4500
     batch = orc.synthetic_batch(B, (1, 16), (0, 24), P_pad=24, seed=97)
     model = make_model(api, orc.random_params(seed=21), 100)
-    model.precision = "bf16"
+    model.precision = mode
     gb = gpu_batch(batch)
     with torch.no_grad():
         full = model(dict(gb), 60)
@@ -762,24 +903,25 @@ def test_bf16_forward_mixed_sizes_and_large_batch_schedule(api):
         ref = model({k: v[:300] for k, v in gb.items()}, 60)
     m = batch["mask"][:300].to(DEV)
     sel = m & ((m.sum(-1, keepdim=True) - 1 + gb["pocket_mask"][:300].sum(-1, keepdim=True)) > 0)
-    assert rel_err(f[:300][sel], ref["frames"].to_tensor_7()[sel]) < TOL_BF16
-    assert rel_err(t[:300][sel], ref["torsions"][sel]) < TOL_BF16
+    assert rel_err(f[:300][sel], ref["frames"].to_tensor_7()[sel]) < tol
+    assert rel_err(t[:300][sel], ref["torsions"][sel]) < tol
 
 
-def test_bf16_forward_largest_pocket(api):
+@pytest.mark.parametrize("mode,tol", TC_MODES)
+def test_tensor_core_forward_largest_pocket(api, mode, tol):
     """pocket_maxlen = 480 (the largest the kernels accept): the tensor-core layer still fits (neighbour projections stay in
     L2 instead of shared memory) and agrees with the fp32 path."""
     batch = orc.synthetic_batch(3, (8, 15), (400, 480), P_pad=480, seed=98)
     model = make_model(api, orc.random_params(seed=22), 100)
     gb = gpu_batch(batch)
     with torch.no_grad():
-        model.precision = "bf16"
+        model.precision = mode
         out = model(dict(gb), 17)
         model.precision = "fp32"
         ref = model(dict(gb), 17)
     m = batch["mask"].to(DEV)
-    assert rel_err(out["frames"].to_tensor_7()[m], ref["frames"].to_tensor_7()[m]) < TOL_BF16
-    assert rel_err(out["torsions"][m], ref["torsions"][m]) < TOL_BF16
+    assert rel_err(out["frames"].to_tensor_7()[m], ref["frames"].to_tensor_7()[m]) < tol
+    assert rel_err(out["torsions"][m], ref["torsions"][m]) < tol
     with pytest.raises(RuntimeError, match="pocket_maxlen"):
         model({k: (torch.cat((v, v), 1) if k.startswith("pocket") else v) for k, v in gb.items()}, 17)
 
@@ -810,7 +952,7 @@ def test_c_abi_error_behaviour(api):
     with pytest.raises(ValueError):
         model({**gb, "features": gb["features"][..., :20]}, 3)                  # 20 features instead of 22
     with pytest.raises(ValueError):
-        model.precision = "fp16"
+        model.precision = "int8"
         model(gb, 3)
     model.precision = "fp32"
     torch.cuda.synchronize()

@@ -37,6 +37,27 @@ def test_shared_noise_step_is_rank_independent():
     assert all(0 <= t < 1000 for t in ts) and len(set(ts)) > 10
 
 
+def test_gradient_buckets_skip_the_parameters_that_never_get_a_gradient():
+    """gnn2.feature_mlp.* (8 321 floats, model.py:415) sits at the start of the gnn2 half of the flat buffer and is left out of
+    the all-reduce; the two buckets cover everything else exactly once."""
+    lo, hi = par.unused_gradient_span()
+    assert lo == par.layer_split_offset() and hi - lo == 128 * 64 + 64 + 64 + 1
+
+    class Dm:
+        model = None
+
+        def __init__(self):
+            self.noise_step_count = 10
+    t = par.DataParallelTrainer.__new__(par.DataParallelTrainer)
+    t._split = None
+    flat = torch.arange(79195, dtype=torch.float32)
+    second, first = t._buckets(flat)
+    assert first.numel() + second.numel() + (hi - lo) == 79195
+    assert first.data_ptr() == flat.data_ptr() and int(second[0]) == hi and int(first[-1]) == lo - 1
+    keys = [par.shared_noise_key(k, 3) for k in range(20)]
+    assert keys == [par.shared_noise_key(k, 3) for k in range(20)] and len(set(keys)) == 20 and all(0 <= k < 2 ** 62 for k in keys)
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
