@@ -302,6 +302,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-io", action="store_true", help="skip the HDF5 loader / PDB writer leg")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every launch of a trajectory / training step instead of replaying a CUDA graph")
     ap.add_argument("--no-modes", action="store_true", help="skip the other arithmetic modes and the other BASELINE configs")
     ap.add_argument("--precision", default="tc32", choices=["fp32", "tc32", "fp16", "bf16"],
                     help="arithmetic of the denoiser's dense per-pair contractions in the headline legs (see include/pmhc_b200.h)")
@@ -354,6 +355,7 @@ def main():
     dm = DiffusionModelOptimizer(T_STEPS, model, 0.0)
     dm.sample_seed = 2024
     dm.sample_first_complex = rank * B        # Philox stream per global complex index: result independent of N
+    dm.use_graph = not args.no_graph          # the trajectory's 4 T launches replayed as one CUDA graph (captured in the warm-up)
 
     keys = ("frames", "torsions", "features", "mask", "pocket_frames", "pocket_features", "pocket_mask")
 
@@ -417,7 +419,8 @@ def main():
     # ---------------- roofline of the dominant kernel (fused EGNN layer forward) ----------------
     # the same K steps once more with a CUDA event pair around every layer launch (pmhc_profile_*; kept out of `value`'s timed
     # region: creating 2 x 200 events per trajectory costs host time there)
-    def kernel_times(fn, steps):
+    def kernel_times(fn, steps, owner):
+        graphed, owner.use_graph = owner.use_graph, False      # (events cannot be recorded into a replayed graph: launches enqueued one by one)
         lib.pmhc_profile_enable(1)
         barrier()
         for _ in range(steps):
@@ -426,9 +429,15 @@ def main():
         pm, pn = (ctypes.c_double * 2)(), (ctypes.c_int64 * 2)()
         lib.pmhc_profile_read(pm, pn)
         lib.pmhc_profile_enable(0)
+        owner.use_graph = graphed
         return [pm[0], pm[1]], [pn[0], pn[1]]
 
-    prof_ms, prof_n = kernel_times(sample_resident, K)
+    prof_ms, prof_n = kernel_times(sample_resident, K, dm)
+    eager_ms = None
+    if dm.use_graph and world == 1:
+        dm.use_graph = False
+        eager_ms = timed(sample_resident, 1, K) / K
+        dm.use_graph = True
     peaks = measured_peaks()
     flops_per_launch = forward_flops_per_complex() * B / 2.0       # one layer per launch
     kernel_ms = prof_ms[0] / max(1, prof_n[0])
@@ -465,6 +474,7 @@ def main():
         tmodel.load_state_dict(params, strict=True)
         tmodel = tmodel.to(dev)
         tdm = DiffusionModelOptimizer(T_TRAIN, tmodel, 1e-3)
+        tdm.use_graph = not args.no_graph and world == 1
         from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer
         trainer = DataParallelTrainer(tdm, seed=0)   # N = 1: plain optimize(); N > 1: shared t + overlapped NCCL all-reduce
         n_train = 20
@@ -484,7 +494,7 @@ def main():
         fp32_leg, _ = train_leg(tb, "fp32", None)
         tc32_leg, _ = train_leg(tb, "tc32", None)          # tcgen05 hi/lo forward (saves the softmax statistics), fp32 FFMA backward
         bf16_leg, bf16_step = train_leg(tb, "bf16", None)  # bf16 tcgen05 forward + TF32 tensor-core backward
-        tprof_ms, tprof_n = kernel_times(bf16_step, n_train)
+        tprof_ms, tprof_n = kernel_times(bf16_step, n_train, tdm)
         # backward roofline (tensor pipe): 3 x 43.4 kFLOP per real pair per layer (recomputation + input gradients + weight
         # gradients), both layers' kernels averaged; pairs as in the forward count
         bwd_us = tprof_ms[1] / max(tprof_n[1], 1) * 1e3
@@ -545,6 +555,9 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": KERNELS[args.precision]["dtype"], "data": "synthetic",
             "config": {"workload": WORKLOAD, "complexes_per_gpu": B, "T": T_STEPS, "P_pad": P_PAD, "l2": "flushed between steps (256 MiB memset)",
+                       "launch": ("one CUDA graph per trajectory (captured once per batch shape; seed / shard offset read from device memory)"
+                                  if dm.use_graph else "every launch enqueued by pmhc_sample"),
+                       "eager_ms_per_step": eager_ms,
                        "weights": weights_note, "precision": f"{args.precision}: {KERNELS[args.precision]['math']}; parity gate {KERNELS[args.precision]['gate']}"},
             "clocks": clocks.summary(),
             "e2e": {"value": world * B * K / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

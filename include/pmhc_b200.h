@@ -163,6 +163,14 @@ int pmhc_sample(const float *params, const PmhcBatch *batch_host, float *frames,
                 const float *noise_tape, const float *quat_sign_tape, float *scratch,
                 void *workspace, size_t workspace_bytes, void *stream, int precision);
 
+/* Same trajectory with the Philox (seed, first_complex) pair read from device memory (seed_first_dev: 2 x uint64, nullable):
+ * the call only enqueues kernels, so it can be captured into a CUDA graph once per (batch shape, T, precision) and replayed
+ * with new noise by rewriting those 16 bytes — DiffusionModelOptimizer.sample(graph=True). */
+int pmhc_sample_ex(const float *params, const PmhcBatch *batch_host, float *frames, float *torsions,
+                   int T, double beta_min, double beta_max, uint64_t seed, uint64_t first_complex,
+                   const uint64_t *seed_first_dev, const float *noise_tape, const float *quat_sign_tape,
+                   float *scratch, void *workspace, size_t workspace_bytes, void *stream, int precision);
+
 /* Adam update over the flat buffers — replaces torch.optim.Adam.step (optimizer.py:33, 224), default
  * betas/eps unless given; `skip` ranges (gnn2.feature_mlp) are left untouched like grad=None params. */
 int pmhc_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n,
@@ -174,6 +182,54 @@ int pmhc_adam_step(float *params, const float *grads, float *exp_avg, float *exp
 int pmhc_adam_step_guarded(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n,
                            double lr, double beta1, double beta2, double eps, int step,
                            const uint8_t *skip_flag, void *stream);
+
+/* ---- one training step as two enqueue-only calls — DiffusionModelOptimizer.optimize (optimizer.py:195-224) -------------
+ * pmhc_train_step_grad: [gen_noise] -> add_noise -> denoiser forward -> loss + its gradient -> NaN flag -> flat_grad = 0 ->
+ * denoiser backward; pmhc_train_step_adam: the guarded Adam update of every parameter that carries a gradient.  (Between the
+ * two a data-parallel caller all-reduces flat_grad.)  All per-step scalars live in one 48-byte block: given by value
+ * (scalars_host, always required) and, optionally, in device memory (scalars_dev): then every kernel reads the device copy, and
+ * a CUDA graph captured around the two calls is replayable for any later step — refresh the block, launch the graph. */
+typedef struct {
+    float t_over_T;               /* time feature t / T (model.py:394) */
+    float beta, alpha, sigma;     /* add_noise at step t: beta_t, sqrt(1 - beta_t), sqrt(beta_t) (optimizer.py:81-91, 110-138) */
+    float adam_step_size;         /* lr / (1 - beta1^k) */
+    float adam_bc2_sqrt;          /* sqrt(1 - beta2^k) */
+    float grad_scale;             /* d(mean loss) / d(per-complex loss): 1 / B, or 1 / B_global under data parallelism */
+    float reserved;
+    uint64_t noise_seed;          /* Philox key of this step's noise */
+    uint64_t noise_first_residue; /* counter of the batch's first residue (16 x its first global complex) */
+} PmhcStepScalars;
+/* Fills *out_host for noise step t of T and Adam step k, forming every scalar in double and rounding once (as the reference's
+ * Python floats / torch's Adam do). */
+int pmhc_step_scalars(int t, int T, double beta_min, double beta_max, double lr, double beta1, double beta2,
+                      int adam_step, double grad_scale, uint64_t noise_seed, uint64_t noise_first_residue,
+                      PmhcStepScalars *out_host);
+/* Copies 1..64 bytes from host to device memory through a kernel's launch parameters (captured when the call returns, ordered
+ * on `stream`): how the scalar block above — and pmhc_sample_ex's seed pair — is refreshed before a graph replay. */
+int pmhc_upload_small(const void *src_host, void *dst_dev, int bytes, void *stream);
+typedef struct {                  /* caller-owned device buffers of one step */
+    float *noise_frames;          /* [B,16,7]   epsilon: written when draw_noise != 0, else read */
+    float *noise_torsions;        /* [B,16,7,2] */
+    float *zt_frames;             /* [B,16,7]   noised input (out) */
+    float *zt_torsions;           /* [B,16,7,2] */
+    float *pred_frames;           /* [B,16,7]   predicted noise (out) */
+    float *pred_torsions;         /* [B,16,7,2] */
+    float *d_frames;              /* [B,16,7]   loss gradient (scratch) */
+    float *d_torsions;            /* [B,16,7,2] */
+    float *losses;                /* [5,B]      total, positions, rotations, torsions, rmsd (out) */
+    float *saved;                 /* pmhc_saved_floats(B, P) */
+    float *flat_grad;             /* PMHC_NPARAM, overwritten */
+    uint8_t *nan_flag;            /* nullable, 1 byte, sticky: set when any total loss is NaN */
+} PmhcStepBuffers;
+/* batch->frames / torsions are the CLEAN x_0; quat_sign_ref (nullable, [B*16,4]) as in pmhc_add_noise. */
+int pmhc_train_step_grad(const float *params, const PmhcBatch *batch_host, const uint8_t *torsions_mask,
+                         const PmhcStepScalars *scalars_host, const PmhcStepScalars *scalars_dev,
+                         const PmhcStepBuffers *buffers_host, int draw_noise, const float *quat_sign_ref,
+                         void *workspace, size_t workspace_bytes, void *stream, void *layer2_done_event,
+                         int precision, int backward_precision);
+int pmhc_train_step_adam(float *params, const float *flat_grad, float *exp_avg, float *exp_avg_sq,
+                         double beta1, double beta2, double eps, const PmhcStepScalars *scalars_host,
+                         const PmhcStepScalars *scalars_dev, const uint8_t *nan_flag, void *stream);
 
 /* Loader side — replaces the per-entry Rigid.from_tensor_4x4(...).to_tensor_7() of MhcpDataset.get_entry
  * (diffusion/data.py:107, :115; RU:1004-1034 + rot_to_quat RU:184-216): n homogeneous 4x4 matrices (row-major,

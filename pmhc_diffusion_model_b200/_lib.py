@@ -24,7 +24,8 @@ BACKWARD_OF = {"fp32": "fp32", "bf16": "bf16", "tc32": "fp32", "fp16": "bf16"}  
 EXPORTS = (
     "pmhc_last_error", "pmhc_check_device", "pmhc_param_offset", "pmhc_param_numel", "pmhc_workspace_bytes",
     "pmhc_saved_floats", "pmhc_model_forward", "pmhc_model_forward_ex", "pmhc_model_backward", "pmhc_model_backward_ex", "pmhc_gen_noise", "pmhc_noise_from_randoms",
-    "pmhc_add_noise", "pmhc_remove_noise", "pmhc_loss", "pmhc_sample", "pmhc_adam_step", "pmhc_adam_step_guarded", "pmhc_launch_count",
+    "pmhc_add_noise", "pmhc_remove_noise", "pmhc_loss", "pmhc_sample", "pmhc_sample_ex", "pmhc_adam_step", "pmhc_adam_step_guarded", "pmhc_step_scalars", "pmhc_upload_small",
+    "pmhc_train_step_grad", "pmhc_train_step_adam", "pmhc_launch_count",
     "pmhc_profile_enable", "pmhc_profile_read", "pmhc_frames4x4_to_tensor7", "pmhc_atom14", "pmhc_format_pdb_host",
 )
 
@@ -35,6 +36,19 @@ class PmhcBatch(Structure):
         ("frames", c_void_p), ("torsions", c_void_p), ("features", c_void_p), ("mask", c_void_p),
         ("pocket_frames", c_void_p), ("pocket_features", c_void_p), ("pocket_mask", c_void_p),
     ]
+
+
+class PmhcStepScalars(Structure):
+    _fields_ = [
+        ("t_over_T", c_float), ("beta", c_float), ("alpha", c_float), ("sigma", c_float),
+        ("adam_step_size", c_float), ("adam_bc2_sqrt", c_float), ("grad_scale", c_float), ("reserved", c_float),
+        ("noise_seed", c_uint64), ("noise_first_residue", c_uint64),
+    ]
+
+
+class PmhcStepBuffers(Structure):
+    _fields_ = [(n, c_void_p) for n in ("noise_frames", "noise_torsions", "zt_frames", "zt_torsions", "pred_frames", "pred_torsions",
+                                        "d_frames", "d_torsions", "losses", "saved", "flat_grad", "nan_flag")]
 
 
 _lib = None
@@ -87,6 +101,18 @@ def load() -> ctypes.CDLL:
     lib.pmhc_adam_step.argtypes = [vp, vp, vp, vp, i64, c_double, c_double, c_double, c_double, c_int, vp]
     lib.pmhc_adam_step_guarded.restype = c_int
     lib.pmhc_adam_step_guarded.argtypes = [vp, vp, vp, vp, i64, c_double, c_double, c_double, c_double, c_int, vp, vp]
+    lib.pmhc_sample_ex.restype = c_int
+    lib.pmhc_sample_ex.argtypes = [vp, POINTER(PmhcBatch), vp, vp, c_int, c_double, c_double, u64, u64, vp, vp, vp, vp, vp, c_size_t, vp, c_int]
+    lib.pmhc_step_scalars.restype = c_int
+    lib.pmhc_step_scalars.argtypes = [c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_int, c_double, u64, u64,
+                                      POINTER(PmhcStepScalars)]
+    lib.pmhc_upload_small.restype = c_int
+    lib.pmhc_upload_small.argtypes = [vp, vp, c_int, vp]
+    lib.pmhc_train_step_grad.restype = c_int
+    lib.pmhc_train_step_grad.argtypes = [vp, POINTER(PmhcBatch), vp, POINTER(PmhcStepScalars), vp, POINTER(PmhcStepBuffers), c_int, vp,
+                                         vp, c_size_t, vp, vp, c_int, c_int]
+    lib.pmhc_train_step_adam.restype = c_int
+    lib.pmhc_train_step_adam.argtypes = [vp, vp, vp, vp, c_double, c_double, c_double, POINTER(PmhcStepScalars), vp, vp, vp]
     lib.pmhc_launch_count.restype = i64
     lib.pmhc_launch_count.argtypes = []
     lib.pmhc_profile_enable.restype = None

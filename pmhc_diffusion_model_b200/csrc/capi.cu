@@ -43,7 +43,7 @@ int model_forward_impl(const float* params, const PmhcBatch* bt, float t_over_T,
                        bool reuse_pocket_cache);
 int launch_reverse_step_philox(const float* zf, const float* zt, const float* pf, const float* pt, uint64_t seed,
                                uint64_t first, double beta_t, double beta_s, int64_t n, const float* sign_ref, float* of,
-                               float* ot, cudaStream_t stream);
+                               float* ot, cudaStream_t stream, const uint64_t* seed_first_dev);
 int launch_remove_noise(const float* zf, const float* zt, const float* pf, const float* pt, const float* xf,
                         const float* xt, double beta_t, double beta_s, int64_t n, const float* sign_ref, float* of,
                         float* ot, cudaStream_t stream);
@@ -119,6 +119,16 @@ extern "C" int pmhc_sample(const float* params, const PmhcBatch* bt, float* fram
                            double beta_min, double beta_max, uint64_t seed, uint64_t first_complex,
                            const float* noise_tape, const float* quat_sign_tape, float* scratch, void* workspace,
                            size_t workspace_bytes, void* stream_, int precision) {
+    return pmhc_sample_ex(params, bt, frames, torsions, T, beta_min, beta_max, seed, first_complex, nullptr, noise_tape, quat_sign_tape,
+                          scratch, workspace, workspace_bytes, stream_, precision);
+}
+
+// seed_first_dev (nullable, 2 x uint64 in device memory: seed, first complex): read by the reverse-step kernels instead of
+// the by-value pair, so a CUDA graph captured around this call (400+ launches) replays with whatever the block holds then.
+extern "C" int pmhc_sample_ex(const float* params, const PmhcBatch* bt, float* frames, float* torsions, int T,
+                              double beta_min, double beta_max, uint64_t seed, uint64_t first_complex,
+                              const uint64_t* seed_first_dev, const float* noise_tape, const float* quat_sign_tape,
+                              float* scratch, void* workspace, size_t workspace_bytes, void* stream_, int precision) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PMHC_REQUIRE(bt != nullptr && bt->B > 0 && T > 0, "pmhc_sample: empty batch or T <= 0");
     PMHC_REQUIRE(scratch != nullptr, "pmhc_sample: scratch is required");
@@ -146,8 +156,9 @@ extern "C" int pmhc_sample(const float* params, const PmhcBatch* bt, float* fram
             rc = launch_remove_noise(frames, torsions, pred_f, pred_t, fresh_f, fresh_t, beta_t, beta_s, n, sign, frames, torsions, stream);
         } else {
             // fused draw + reverse step; one Philox stream per (global residue index, step): the key mixes seed and step
-            rc = launch_reverse_step_philox(frames, torsions, pred_f, pred_t, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(k + 1),
-                                            first_complex * kN, beta_t, beta_s, n, sign, frames, torsions, stream);
+            const uint64_t step_key = 0x9E3779B97F4A7C15ull * (uint64_t)(k + 1);
+            rc = launch_reverse_step_philox(frames, torsions, pred_f, pred_t, (seed_first_dev ? 0ull : seed) + step_key,
+                                            first_complex * kN, beta_t, beta_s, n, sign, frames, torsions, stream, seed_first_dev);
         }
         if (rc != 0) return rc;
     }

@@ -2,6 +2,8 @@
 //
 // All HBM-bound, one thread per peptide residue (loss: one half-warp per complex), no shared-memory
 // staging needed: every input element is read once, every output written once.
+#include <string.h>
+
 #include "common.cuh"
 #include "pmhc_math.cuh"
 
@@ -70,10 +72,12 @@ __device__ __forceinline__ void philox_noise(uint64_t seed, uint64_t ctr, float*
     }
 }
 
+// `sc` (nullable): the step's scalars in device memory, read instead of the by-value arguments (graph-replayable steps)
 __global__ void gen_noise_kernel(uint64_t seed, uint64_t first, int64_t n, float* __restrict__ frames,
-                                 float* __restrict__ tors) {
+                                 float* __restrict__ tors, const PmhcStepScalars* __restrict__ sc) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
+    if (sc != nullptr) { seed = sc->noise_seed; first = sc->noise_first_residue; }
     philox_noise(seed, first + (uint64_t)r, frames + r * 7, tors + r * 14);
 }
 
@@ -92,9 +96,10 @@ __global__ void noise_from_randoms_kernel(const float* __restrict__ normal, cons
 __global__ void add_noise_kernel(const float* __restrict__ frames, const float* __restrict__ tors,
                                  const float* __restrict__ nframes, const float* __restrict__ ntors, float beta,
                                  float alpha, float sigma, int64_t n, const float* __restrict__ sign_ref,
-                                 float* __restrict__ oframes, float* __restrict__ otors) {
+                                 float* __restrict__ oframes, float* __restrict__ otors, const PmhcStepScalars* __restrict__ sc) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
+    if (sc != nullptr) { beta = sc->beta; alpha = sc->alpha; sigma = sc->sigma; }
     const float* f = frames + r * 7;
     const float* e = nframes + r * 7;
     Quat q = qunit(qmul(qpartial(load_quat(e), beta), load_quat(f)));
@@ -170,10 +175,12 @@ constexpr int kRevThreads = 9 * 32;
 __global__ void __launch_bounds__(kRevThreads) reverse_step_philox_kernel(const float* zf, const float* zt, const float* __restrict__ pf,
                                                                           const float* __restrict__ pt, uint64_t seed, uint64_t first,
                                                                           ReverseCoef k, int64_t n, const float* __restrict__ sign_ref,
-                                                                          float* of, float* ot) {
+                                                                          float* of, float* ot, const uint64_t* __restrict__ seed_first_dev) {
     const int role = threadIdx.x >> 5;
     const int64_t r = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
     if (r >= n) return;
+    // (seed, first complex) from device memory: `seed` then carries only the per-step key offset (graph-replayable trajectories)
+    if (seed_first_dev != nullptr) { seed += seed_first_dev[0]; first = seed_first_dev[1] * 16; }
     const uint64_t ctr = first + (uint64_t)r;
     if (role == 0) {
         const Quat q = reverse_step_rotation(load_quat(zf + r * 7), load_quat(pf + r * 7), philox_rotation_noise(seed, ctr), k,
@@ -201,7 +208,8 @@ __global__ void __launch_bounds__(kRevThreads) reverse_step_philox_kernel(const 
 __global__ void loss_kernel(const float* __restrict__ tf, const float* __restrict__ tt, const float* __restrict__ pf,
                             const float* __restrict__ pt, const uint8_t* __restrict__ mask,
                             const uint8_t* __restrict__ tmask, int B, float gscale, float* __restrict__ losses,
-                            float* __restrict__ dpf, float* __restrict__ dpt) {
+                            float* __restrict__ dpf, float* __restrict__ dpt, const PmhcStepScalars* __restrict__ sc) {
+    if (sc != nullptr) gscale = sc->grad_scale;
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int b = gid >> 4, i = gid & 15;
     bool live = b < B;
@@ -270,9 +278,10 @@ __global__ void loss_kernel(const float* __restrict__ tf, const float* __restric
 // torch.optim.Adam single-tensor update (no amsgrad, no weight decay) over the flat buffers.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float one_minus_b1, float b2, float one_minus_b2, float eps,
-                            float step_size, float bc2_sqrt, const uint8_t* __restrict__ skip) {
+                            float step_size, float bc2_sqrt, const uint8_t* __restrict__ skip, const PmhcStepScalars* __restrict__ sc) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (sc != nullptr) { step_size = sc->adam_step_size; bc2_sqrt = sc->adam_bc2_sqrt; }
     if (skip != nullptr && *skip != 0) return;   // a non-finite loss was seen: weights and moments stay as they are
     float gi = g[i];
     float mi = m[i] + (gi - m[i]) * one_minus_b1;
@@ -291,7 +300,7 @@ static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + b
 
 extern "C" int pmhc_gen_noise(uint64_t seed, uint64_t first_residue, int64_t n, float* frames, float* tors, void* stream) {
     if (n <= 0) return 0;
-    gen_noise_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(seed, first_residue, n, frames, tors);
+    gen_noise_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(seed, first_residue, n, frames, tors, nullptr);
     PMHC_CHECK_LAUNCH("pmhc_gen_noise");
     return 0;
 }
@@ -311,7 +320,7 @@ extern "C" int pmhc_add_noise(const float* frames, const float* torsions, const 
     PMHC_REQUIRE(beta >= 0.0 && beta <= 1.0, "pmhc_add_noise: beta %f outside [0,1]", beta);
     float alpha = (float)sqrt(1.0 - beta), sigma = (float)sqrt(beta);
     add_noise_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(frames, torsions, nframes, ntors, (float)beta, alpha,
-                                                                          sigma, n, sign_ref, oframes, otors);
+                                                                          sigma, n, sign_ref, oframes, otors, nullptr);
     PMHC_CHECK_LAUNCH("pmhc_add_noise");
     return 0;
 }
@@ -347,11 +356,11 @@ int launch_remove_noise(const float* zf, const float* zt, const float* pf, const
 }
 int launch_reverse_step_philox(const float* zf, const float* zt, const float* pf, const float* pt, uint64_t seed,
                                uint64_t first, double beta_t, double beta_s, int64_t n, const float* sign_ref, float* of,
-                               float* ot, cudaStream_t stream) {
+                               float* ot, cudaStream_t stream, const uint64_t* seed_first_dev) {
     PMHC_REQUIRE(beta_t > 0.0 && beta_t < 1.0 && beta_s >= 0.0 && beta_s < beta_t,
                  "reverse step: need 0 <= beta_s < beta_t < 1 (got %f, %f)", beta_s, beta_t);
     ReverseCoef k = reverse_coef(beta_t, beta_s);
-    reverse_step_philox_kernel<<<grid_for(n, 32), kRevThreads, 0, stream>>>(zf, zt, pf, pt, seed, first, k, n, sign_ref, of, ot);
+    reverse_step_philox_kernel<<<grid_for(n, 32), kRevThreads, 0, stream>>>(zf, zt, pf, pt, seed, first, k, n, sign_ref, of, ot, seed_first_dev);
     PMHC_CHECK_LAUNCH("reverse_step_philox");
     return 0;
 }
@@ -370,7 +379,7 @@ extern "C" int pmhc_loss(const float* tf, const float* tt, const float* pf, cons
     if (B <= 0) return 0;
     PMHC_REQUIRE((dpf == nullptr) == (dpt == nullptr), "pmhc_loss: pass both gradient buffers or neither");
     loss_kernel<<<grid_for((int64_t)B * 16, 128), 128, 0, (cudaStream_t)stream>>>(tf, tt, pf, pt, mask, tmask, B, gscale,
-                                                                                  losses, dpf, dpt);
+                                                                                  losses, dpf, dpt, nullptr);
     PMHC_CHECK_LAUNCH("pmhc_loss");
     return 0;
 }
@@ -387,7 +396,125 @@ extern "C" int pmhc_adam_step_guarded(float* p, const float* g, float* m, float*
     // the scalars are formed in double and rounded once, as torch does with its Python-float hyperparameters
     double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
     adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2),
-                                                                   (float)eps, (float)(lr / bc1), (float)sqrt(bc2), skip_flag);
+                                                                   (float)eps, (float)(lr / bc1), (float)sqrt(bc2), skip_flag, nullptr);
     PMHC_CHECK_LAUNCH("pmhc_adam_step");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One training step as two enqueue-only calls (optimizer.py:195-224).  Every per-step scalar (t / T, the noising coefficients,
+// the Philox key, the loss scale, Adam's bias corrections) comes either by value from `sc_host` or — when `sc_dev` is given —
+// from device memory, so a CUDA graph captured around the calls can be replayed step after step: the caller refreshes the 48-byte
+// block (a host-to-device copy node of the same graph) and launches the graph.
+// ---------------------------------------------------------------------------------------------------------------
+namespace pmhc {
+int model_forward_impl(const float* params, const PmhcBatch* bt, float t_over_T, float* out_frames, float* out_torsions,
+                       float* saved, void* workspace, size_t workspace_bytes, cudaStream_t stream, int precision,
+                       bool reuse_pocket_cache);
+
+__global__ void nan_flag_kernel(const float* __restrict__ total_loss, int B, uint8_t* __restrict__ flag) {
+    bool bad = false;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) bad = bad || isnan(total_loss[b]);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 1;     // sticky: never cleared here
+}
+}  // namespace pmhc
+
+namespace pmhc {
+struct SmallBlock { unsigned char b[64]; };
+__global__ void upload_small_kernel(SmallBlock v, unsigned char* __restrict__ dst, int bytes) {
+    if ((int)threadIdx.x < bytes) dst[threadIdx.x] = v.b[threadIdx.x];
+}
+}  // namespace pmhc
+
+// Up to 64 bytes from host to device memory THROUGH THE LAUNCH PARAMETERS of a one-warp kernel: the bytes are captured when the
+// call returns (no pinned staging buffer whose reuse could race with an earlier, still queued copy) and the write is ordered
+// on `stream` like any kernel — what refreshes the scalar block of a replayed training-step / trajectory graph.
+extern "C" int pmhc_upload_small(const void* src_host, void* dst_dev, int bytes, void* stream) {
+    PMHC_REQUIRE(src_host != nullptr && dst_dev != nullptr && bytes > 0 && bytes <= 64, "pmhc_upload_small: 1..64 bytes");
+    SmallBlock v;
+    memset(v.b, 0, sizeof(v.b));
+    memcpy(v.b, src_host, (size_t)bytes);
+    upload_small_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(v, (unsigned char*)dst_dev, bytes);
+    PMHC_CHECK_LAUNCH("pmhc_upload_small");
+    return 0;
+}
+
+extern "C" int pmhc_step_scalars(int t, int T, double beta_min, double beta_max, double lr, double beta1, double beta2,
+                                 int adam_step, double grad_scale, uint64_t noise_seed, uint64_t noise_first_residue,
+                                 PmhcStepScalars* out_host) {
+    PMHC_REQUIRE(out_host != nullptr && T > 0 && adam_step >= 1, "pmhc_step_scalars: bad arguments");
+    const double beta = beta_min + (beta_max - beta_min) * ((double)t / (double)T);     // linear_schedule, optimizer.py:20-21
+    PMHC_REQUIRE(beta >= 0.0 && beta <= 1.0, "pmhc_step_scalars: beta %f outside [0,1]", beta);
+    out_host->t_over_T = (float)((double)t / (double)T);      // the Python float t / T, rounded once
+    out_host->beta = (float)beta;
+    out_host->alpha = (float)sqrt(1.0 - beta);
+    out_host->sigma = (float)sqrt(beta);
+    out_host->adam_step_size = (float)(lr / (1.0 - pow(beta1, adam_step)));
+    out_host->adam_bc2_sqrt = (float)sqrt(1.0 - pow(beta2, adam_step));
+    out_host->grad_scale = (float)grad_scale;
+    out_host->reserved = 0.0f;
+    out_host->noise_seed = noise_seed;
+    out_host->noise_first_residue = noise_first_residue;
+    return 0;
+}
+
+extern "C" int pmhc_train_step_grad(const float* params, const PmhcBatch* bt, const uint8_t* torsions_mask,
+                                    const PmhcStepScalars* sc_host, const PmhcStepScalars* sc_dev, const PmhcStepBuffers* buf,
+                                    int draw_noise, const float* quat_sign_ref, void* workspace, size_t workspace_bytes,
+                                    void* stream_, void* layer2_done_event, int precision, int backward_precision) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PMHC_REQUIRE(bt != nullptr && bt->B > 0 && sc_host != nullptr && buf != nullptr && torsions_mask != nullptr,
+                 "pmhc_train_step_grad: empty batch or missing arguments");
+    const int B = bt->B;
+    const int64_t n = (int64_t)B * kN;
+    if (draw_noise) {
+        gen_noise_kernel<<<grid_for(n, 128), 128, 0, stream>>>(sc_host->noise_seed, sc_host->noise_first_residue, n, buf->noise_frames,
+                                                                buf->noise_torsions, sc_dev);
+        PMHC_CHECK_LAUNCH("gen_noise");
+    }
+    add_noise_kernel<<<grid_for(n, 128), 128, 0, stream>>>(bt->frames, bt->torsions, buf->noise_frames, buf->noise_torsions, sc_host->beta,
+                                                            sc_host->alpha, sc_host->sigma, n, quat_sign_ref, buf->zt_frames,
+                                                            buf->zt_torsions, sc_dev);
+    PMHC_CHECK_LAUNCH("add_noise");
+    PmhcBatch zt = *bt;
+    zt.frames = buf->zt_frames;
+    zt.torsions = buf->zt_torsions;
+    set_step_t_dev(sc_dev ? &sc_dev->t_over_T : nullptr);
+    int rc = model_forward_impl(params, &zt, sc_host->t_over_T, buf->pred_frames, buf->pred_torsions, buf->saved, workspace,
+                                workspace_bytes, stream, precision, false);
+    if (rc == 0) {
+        loss_kernel<<<grid_for(n, 128), 128, 0, stream>>>(buf->noise_frames, buf->noise_torsions, buf->pred_frames, buf->pred_torsions,
+                                                           bt->mask, torsions_mask, B, sc_host->grad_scale, buf->losses, buf->d_frames,
+                                                           buf->d_torsions, sc_dev);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("loss: %s", cudaGetErrorString(e)); rc = -2; }
+    }
+    if (rc == 0 && buf->nan_flag != nullptr) nan_flag_kernel<<<1, 256, 0, stream>>>(buf->losses, B, buf->nan_flag);
+    if (rc == 0) {
+        cudaError_t e = cudaMemsetAsync(buf->flat_grad, 0, sizeof(float) * PMHC_NPARAM, stream);
+        if (e != cudaSuccess) { set_error("memset(flat_grad): %s", cudaGetErrorString(e)); rc = -2; }
+    }
+    if (rc == 0)
+        rc = pmhc_model_backward_ex(params, &zt, sc_host->t_over_T, buf->saved, buf->d_frames, buf->d_torsions, buf->flat_grad, workspace,
+                                    workspace_bytes, stream_, layer2_done_event, backward_precision);
+    set_step_t_dev(nullptr);
+    return rc;
+}
+
+extern "C" int pmhc_train_step_adam(float* params, const float* flat_grad, float* exp_avg, float* exp_avg_sq, double beta1,
+                                    double beta2, double eps, const PmhcStepScalars* sc_host, const PmhcStepScalars* sc_dev,
+                                    const uint8_t* nan_flag, void* stream) {
+    PMHC_REQUIRE(sc_host != nullptr, "pmhc_train_step_adam: scalars are required");
+    // gnn2.feature_mlp.* (state-dict tensors 24..27) never carries a gradient (model.py:415): no state, no update, as torch's
+    // Adam treats grad = None
+    const int64_t lo = pmhc_param_offset(24), hi = pmhc_param_offset(27) + pmhc_param_numel(27);
+    const int64_t spans[2][2] = {{0, lo}, {hi, PMHC_NPARAM}};
+    for (int k = 0; k < 2; ++k) {
+        const int64_t o = spans[k][0], n = spans[k][1] - o;
+        adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params + o, flat_grad + o, exp_avg + o, exp_avg_sq + o, n,
+                                                                       (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
+                                                                       sc_host->adam_step_size, sc_host->adam_bc2_sqrt, nan_flag, sc_dev);
+        PMHC_CHECK_LAUNCH("adam");
+    }
     return 0;
 }

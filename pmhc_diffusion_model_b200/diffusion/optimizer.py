@@ -158,6 +158,79 @@ class FlatAdam(torch.optim.Adam):
         return loss
 
 
+    # ---- the training step's own path: one pmhc_train_step_adam call over both gradient-carrying runs ------------------------
+    def next_step(self) -> int:
+        """Adam step count of the update about to be made (all gradient-carrying parameters are stepped together)."""
+        for name, p in self._model.named_parameters():
+            if not name.startswith("gnn2.feature_mlp"):
+                st = self.state.get(p)
+                return int(st["step"]) + 1 if st else 1
+        return 1
+
+    def prepare_flat(self) -> None:
+        """Moment buffers linked to the model's current flat buffer and state entries in place (before a step is enqueued)."""
+        model = self._model
+        flat = model._flat_params()
+        if self._generation != model._flat_generation or self._m is None:
+            self._link(flat)
+        off = 0
+        for name, p in model.named_parameters():
+            n = p.numel()
+            if not name.startswith("gnn2.feature_mlp") and len(self.state[p]) == 0:
+                st = self.state[p]
+                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                st["exp_avg"] = self._m[off:off + n].view(p.shape)
+                st["exp_avg_sq"] = self._v[off:off + n].view(p.shape)
+            off += n
+
+    def count_step(self) -> None:
+        steps = [self.state[p]["step"] for name, p in self._model.named_parameters() if not name.startswith("gnn2.feature_mlp")]
+        torch._foreach_add_(steps, 1.0)
+
+    def hyper(self):
+        group = self.param_groups[0]
+        if (len(self.param_groups) != 1 or group["weight_decay"] != 0 or group["amsgrad"] or group["maximize"]
+                or group.get("capturable") or group.get("differentiable")):
+            raise RuntimeError("FlatAdam implements plain Adam (one group, no weight decay / amsgrad / maximize), as optimizer.py:33 uses it")
+        b1, b2 = group["betas"]
+        return float(group["lr"]), float(b1), float(b2), float(group["eps"])
+
+
+class _StepState:
+    """Device buffers of one training step for one batch shape.  Their addresses never change, so a CUDA graph captured around the
+    step's two C calls can be replayed for every later batch of that shape (inputs are copied into `inputs` first)."""
+
+    def __init__(self, B: int, P: int, dev: torch.device, nan_flag: torch.Tensor):
+        lib = _lib.load()
+
+        def f(*shape):
+            return torch.empty(*shape, device=dev, dtype=torch.float32)
+        self.B, self.P, self.dev = B, P, dev
+        self.noise_f, self.noise_t = f(B, _lib.N, 7), f(B, _lib.N, _lib.NTORS, 2)
+        self.zt_f, self.zt_t = f(B, _lib.N, 7), f(B, _lib.N, _lib.NTORS, 2)
+        self.pred_f, self.pred_t = f(B, _lib.N, 7), f(B, _lib.N, _lib.NTORS, 2)
+        self.d_f, self.d_t = f(B, _lib.N, 7), f(B, _lib.N, _lib.NTORS, 2)
+        self.losses = f(5, B)
+        self.saved = f(lib.pmhc_saved_floats(B, P))
+        self.grad = f(_lib.NPARAM)
+        self.buffers = _lib.PmhcStepBuffers(*[t.data_ptr() for t in (self.noise_f, self.noise_t, self.zt_f, self.zt_t, self.pred_f, self.pred_t,
+                                                                      self.d_f, self.d_t, self.losses, self.saved, self.grad, nan_flag)])
+        self.ws_bytes = lib.pmhc_workspace_bytes(B, P)
+        # graph mode only
+        self.inputs = None          # static copies of the eight batch tensors
+        self.scalars_dev = None     # PmhcStepScalars in device memory
+        self.graph = None
+        self.graph_key = None
+
+    def static_inputs(self, tensors):
+        if self.inputs is None:
+            self.inputs = [torch.empty_like(t) for t in tensors]
+            self.scalars_dev = torch.zeros(48, dtype=torch.uint8, device=self.dev)
+        for dst, src in zip(self.inputs, tensors):
+            dst.copy_(src, non_blocking=True)
+        return self.inputs
+
+
 class DiffusionModelOptimizer:
 
     def __init__(self, noise_step_count: int, model: torch.nn.Module, lr: float):
@@ -172,6 +245,12 @@ class DiffusionModelOptimizer:
         # complex independent of how the complexes are split over GPUs
         self.sample_seed: Optional[int] = None
         self.sample_first_complex: int = 0
+        # CUDA graphs: capture the training step (optimize) / the whole trajectory (sample) once per batch shape and replay it;
+        # per-step scalars (t, noise key, Adam bias corrections; the sampling seed) are read from device memory by the kernels
+        self.use_graph: bool = False
+        self._step_states: Dict = {}
+        self._sample_graphs: Dict = {}
+        self._nan_flag: Optional[torch.Tensor] = None
 
     # ---- loss ---------------------------------------------------------------------------------------------
     @staticmethod
@@ -294,55 +373,83 @@ class DiffusionModelOptimizer:
         batch["pocket_frames"] = Rigid.from_tensor_7(_frames7(batch["pocket_frames"]))
 
         model = self.model
-        frames7 = _lib.f32c(batch["frames"].to_tensor_7())
-        dev = frames7.device
-        if noise is None:
-            noise = self.gen_noise(frames7.shape[:-1], dev, key=noise_key, first_residue=noise_first_complex * _lib.N)
-        zt = self.add_noise(batch, noise, t)
-
-        desc, keep = _lib.make_batch(zt["frames"].to_tensor_7(), zt["torsions"], batch["features"], batch["mask"],
+        desc, keep = _lib.make_batch(batch["frames"].to_tensor_7(), batch["torsions"], batch["features"], batch["mask"],
                                      batch["pocket_frames"].to_tensor_7(), batch["pocket_features"], batch["pocket_mask"])
+        tmask = _lib.u8c(batch["torsions_mask"])
         B, P = desc.B, desc.P
+        dev = keep[0].device
+        if self._nan_flag is None or self._nan_flag.device != dev:
+            self._nan_flag = torch.zeros(1, dtype=torch.uint8, device=dev)
+            self._step_states.clear()
+        st = self._step_states.get((B, P))
+        if st is None:
+            if len(self._step_states) >= 4:          # e.g. the tail batch of every epoch: keep the most recent shapes only
+                self._step_states.pop(next(iter(self._step_states)))
+            st = self._step_states[(B, P)] = _StepState(B, P, dev, self._nan_flag)
         flat = model._flat_params()
-        pred_f = torch.empty(B, _lib.N, 7, device=dev, dtype=torch.float32)
-        pred_t = torch.empty(B, _lib.N, _lib.NTORS, 2, device=dev, dtype=torch.float32)
-        saved = torch.empty(lib.pmhc_saved_floats(B, P), device=dev, dtype=torch.float32)
-        ws_bytes = lib.pmhc_workspace_bytes(B, P)
-        ws = _lib.workspace(dev, ws_bytes)
-        t_over_T = float(t) / float(model.T)
-        true_f, true_t = _lib.f32c(_frames7(noise["frames"])), _lib.f32c(noise["torsions"])
-        losses = torch.empty(5, B, device=dev, dtype=torch.float32)
-        d_f, d_t = torch.empty_like(pred_f), torch.empty_like(pred_t)
-        grad = torch.zeros_like(flat)
-        stream = _lib.stream_ptr(dev)
-        with torch.cuda.device(dev):
-            _lib.check(lib.pmhc_model_forward_ex(flat.data_ptr(), ctypes.byref(desc), t_over_T, pred_f.data_ptr(), pred_t.data_ptr(),
-                                                 saved.data_ptr(), ws.data_ptr(), ws_bytes, stream, model.precision_code()),
-                       "pmhc_model_forward")
-            # total_loss.mean().backward() (optimizer.py:222): gradient scale 1/B
-            _lib.check(lib.pmhc_loss(true_f.data_ptr(), true_t.data_ptr(), pred_f.data_ptr(), pred_t.data_ptr(),
-                                     _lib.u8c(batch["mask"]).data_ptr(), _lib.u8c(batch["torsions_mask"]).data_ptr(), B,
-                                     1.0 / B if loss_scale is None else float(loss_scale), losses.data_ptr(), d_f.data_ptr(),
-                                     d_t.data_ptr(), stream), "pmhc_loss")
-            _lib.check(lib.pmhc_model_backward_ex(flat.data_ptr(), ctypes.byref(desc), t_over_T, saved.data_ptr(), d_f.data_ptr(),
-                                                  d_t.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes, stream,
-                                                  self.layer2_event_handle(), model.backward_precision_code()), "pmhc_model_backward")
+        opt = self.optimizer
+        opt.prepare_flat()
+        lr, b1, b2, eps = opt.hyper()
+        key = _next_noise_key() if (noise is None and noise_key is None) else int(noise_key or 0)
+        sc = _lib.PmhcStepScalars()
+        _lib.check(lib.pmhc_step_scalars(int(t), int(model.T), self.beta_min, self.beta_max, lr, b1, b2, opt.next_step(),
+                                         1.0 / B if loss_scale is None else float(loss_scale), key, int(noise_first_complex) * _lib.N,
+                                         ctypes.byref(sc)), "pmhc_step_scalars")
+        if noise is not None:
+            st.noise_f.copy_(_lib.f32c(_frames7(noise["frames"])))
+            st.noise_t.copy_(_lib.f32c(noise["torsions"]))
+        sign = _lib.f32c(self.quat_sign_ref) if self.quat_sign_ref is not None else None
+        ws = _lib.workspace(dev, st.ws_bytes)
+        stream_of = lambda: _lib.stream_ptr(dev)
+        hooked = type(self).grad_hook is not getattr(self.grad_hook, "__func__", None)   # a data-parallel wrapper reduces between the calls
+        # (a graph-captured step cannot record an event another, non-captured stream waits on: no overlap in graph mode)
+        event = None if self.use_graph else self.layer2_event_handle()
+        self.last_step_overlapped = event is not None
 
-        loss_dict = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
+        def enqueue(d, tm, sc_dev, with_adam):
+            _lib.check(lib.pmhc_train_step_grad(flat.data_ptr(), ctypes.byref(d), tm.data_ptr(), ctypes.byref(sc), sc_dev, ctypes.byref(st.buffers),
+                                                0 if noise is not None else 1, _lib.ptr(sign), ws.data_ptr(), st.ws_bytes, stream_of(), event,
+                                                model.precision_code(), model.backward_precision_code()), "pmhc_train_step_grad")
+            if with_adam:
+                _lib.check(lib.pmhc_train_step_adam(flat.data_ptr(), st.grad.data_ptr(), opt._m.data_ptr(), opt._v.data_ptr(), b1, b2, eps,
+                                                    ctypes.byref(sc), sc_dev, self._nan_flag.data_ptr(), stream_of()), "pmhc_train_step_adam")
+
+        with torch.cuda.device(dev):
+            if not self.use_graph:
+                enqueue(desc, tmask, None, not hooked)
+            else:
+                # static copies of the inputs, the scalar block refreshed through a kernel's launch parameters, then one graph launch
+                ins = st.static_inputs(keep + [tmask])
+                gdesc = _lib.PmhcBatch(B, P, *[x.data_ptr() for x in ins[:7]])
+                gkey = (model.precision_code(), model.backward_precision_code(), noise is not None, sign is not None and sign.data_ptr(),
+                        hooked, event, flat.data_ptr(), opt._m.data_ptr(), ws.data_ptr(), lr, b1, b2, eps)
+                if st.graph is None or st.graph_key != gkey:
+                    if st.graph is None:
+                        enqueue(gdesc, ins[7], None, False)          # warm-up outside capture: lazy kernel-attribute set-up happens here
+                    torch.cuda.synchronize(dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        enqueue(gdesc, ins[7], st.scalars_dev.data_ptr(), not hooked)
+                    st.graph, st.graph_key = g, gkey
+                _lib.check(lib.pmhc_upload_small(ctypes.byref(sc), st.scalars_dev.data_ptr(), 48, stream_of()), "pmhc_upload_small")
+                st.graph.replay()
+            if hooked:
+                self.grad_hook(st.grad)
+                _lib.check(lib.pmhc_train_step_adam(flat.data_ptr(), st.grad.data_ptr(), opt._m.data_ptr(), opt._v.data_ptr(), b1, b2, eps,
+                                                    ctypes.byref(sc), None, self._nan_flag.data_ptr(), stream_of()), "pmhc_train_step_adam")
+        opt.count_step()
+
+        # (views of the step's static buffers: valid until the next optimize() call on this batch shape)
+        loss_dict = {k: st.losses[i] for i, k in enumerate(LOSS_KEYS)}
         if metrics is not None:
             metrics.add_batch(loss_dict)
         self.last_losses = loss_dict
-        # sticky and checked lazily (check_nan()); from the first NaN loss on, every Adam update is skipped on the device, so the
-        # weights in memory (and whatever gets saved from them) stay the last finite ones — the reference raises before
-        # backward() / step() (optimizer.py:217-218)
-        flag = losses[0].isnan().any().view(1)
-        prev = getattr(self, "_nan_flag", None)
-        self._nan_flag = flag if prev is None or prev.device != flag.device else (prev | flag)
-
-        for p, g in zip(model.parameters(), model._split_flat(grad)):
+        self.last_prediction = (st.pred_f, st.pred_t)
+        # the NaN flag is sticky and stays on the device (check_nan()); from the first NaN loss on, every Adam update is skipped
+        # there, so the weights in memory (and whatever gets saved from them) stay the last finite ones — the reference raises
+        # before backward() / step() (optimizer.py:217-218)
+        for p, g in zip(model.parameters(), model._split_flat(st.grad)):
             p.grad = g
-        self.grad_hook(grad)
-        self.optimizer.step(flat_grad=grad, skip_flag=self._nan_flag.view(torch.uint8))
 
     def grad_hook(self, flat_grad: torch.Tensor) -> None:
         """Called with the flat gradient before the Adam step; data-parallel wrappers all-reduce here."""
@@ -354,7 +461,7 @@ class DiffusionModelOptimizer:
     def check_nan(self) -> None:
         """The reference raises RuntimeError("NaN loss") inside optimize() (optimizer.py:217-218) at the price of a
         host sync per step; here the flag stays on the device until asked for."""
-        if getattr(self, "_nan_flag", None) is not None and bool(self._nan_flag.any()):
+        if self._nan_flag is not None and bool(self._nan_flag.any()):
             raise RuntimeError("NaN loss")
 
     # ---- full training state (SURVEY.md §8f: the reference only saves model.state_dict(), optimize.py:75-80) -----------
@@ -374,12 +481,16 @@ class DiffusionModelOptimizer:
 
     # ---- sampling -------------------------------------------------------------------------------------------
     def sample(self, batch: Dict[str, Union[torch.Tensor, Rigid]], noise_tape: Optional[torch.Tensor] = None,
-               quat_sign_tape: Optional[torch.Tensor] = None) -> Dict:
+               quat_sign_tape: Optional[torch.Tensor] = None, graph: Optional[bool] = None) -> Dict:
         """optimizer.py:226-252: T sequential reverse steps, all enqueued by one pmhc_sample call.
-        noise_tape [T, B, 16, 21] (tensor_7 + 14 torsion values) and quat_sign_tape [T, B, 16, 4] are parity hooks."""
+        noise_tape [T, B, 16, 21] (tensor_7 + 14 torsion values) and quat_sign_tape [T, B, 16, 4] are parity hooks.
+        graph (default: self.use_graph): replay the trajectory's 4 T + launches as ONE CUDA graph captured once per batch shape;
+        the Philox (seed, first complex) pair is read from device memory, so every replay draws its own noise."""
         lib = _lib.load()
         batch["pocket_frames"] = Rigid.from_tensor_7(_frames7(batch["pocket_frames"]))
         batch["frames"] = Rigid.from_tensor_7(_frames7(batch["frames"]))
+        if (self.use_graph if graph is None else graph) and noise_tape is None and quat_sign_tape is None:
+            return self._sample_graphed(batch)
         frames = _lib.f32c(batch["frames"].to_tensor_7()).clone()
         tors = _lib.f32c(batch["torsions"]).clone()
         desc, keep = _lib.make_batch(frames, tors, batch["features"], batch["mask"], batch["pocket_frames"].to_tensor_7(),
@@ -399,6 +510,51 @@ class DiffusionModelOptimizer:
                                        self.beta_min, self.beta_max, seed, self.sample_first_complex, _lib.ptr(tape), _lib.ptr(sign),
                                        scratch.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(dev),
                                        self.model.precision_code()), "pmhc_sample")
+        result = {k: batch[k] for k in batch}
+        result["frames"] = _rigid(frames)
+        result["torsions"] = tors
+        return result
+
+    def _sample_graphed(self, batch: Dict) -> Dict:
+        lib = _lib.load()
+        desc, keep = _lib.make_batch(batch["frames"].to_tensor_7(), batch["torsions"], batch["features"], batch["mask"],
+                                     batch["pocket_frames"].to_tensor_7(), batch["pocket_features"], batch["pocket_mask"])
+        dev = keep[0].device
+        B, P, T = desc.B, desc.P, self.noise_step_count
+        flat = self.model._flat_params()
+        ws_bytes = lib.pmhc_workspace_bytes(B, P)
+        ws = _lib.workspace(dev, ws_bytes)
+        key = (B, P, T, self.model.precision_code(), dev.index)
+        sg = self._sample_graphs.get(key)
+        valid = (flat.data_ptr(), ws.data_ptr(), self.beta_min, self.beta_max)
+        with torch.cuda.device(dev):
+            if sg is None or sg["valid"] != valid:
+                if sg is None and len(self._sample_graphs) >= 4:
+                    self._sample_graphs.pop(next(iter(self._sample_graphs)))
+                ins = [torch.empty_like(t) for t in keep]
+                scratch = torch.empty(2 * B * _lib.N * 21, device=dev, dtype=torch.float32)
+                seed_dev = torch.zeros(2, dtype=torch.int64, device=dev)
+                gdesc = _lib.PmhcBatch(B, P, *[t.data_ptr() for t in ins])
+
+                def enqueue():
+                    _lib.check(lib.pmhc_sample_ex(flat.data_ptr(), ctypes.byref(gdesc), ins[0].data_ptr(), ins[1].data_ptr(), T, self.beta_min,
+                                                  self.beta_max, 0, 0, seed_dev.data_ptr(), None, None, scratch.data_ptr(), ws.data_ptr(),
+                                                  ws_bytes, _lib.stream_ptr(dev), self.model.precision_code()), "pmhc_sample")
+                for dst, src in zip(ins, keep):
+                    dst.copy_(src)
+                enqueue()                      # once outside capture: lazy kernel-attribute set-up happens here
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    enqueue()
+                sg = self._sample_graphs[key] = {"graph": g, "ins": ins, "scratch": scratch, "seed": seed_dev, "valid": valid, "ws": ws}
+            for dst, src in zip(sg["ins"], keep):
+                dst.copy_(src, non_blocking=True)
+            seed = self.sample_seed if self.sample_seed is not None else _next_noise_key()
+            pair = (ctypes.c_uint64 * 2)(int(seed) & (2 ** 64 - 1), int(self.sample_first_complex))
+            _lib.check(lib.pmhc_upload_small(pair, sg["seed"].data_ptr(), 16, _lib.stream_ptr(dev)), "pmhc_upload_small")
+            sg["graph"].replay()
+            frames, tors = sg["ins"][0].clone(), sg["ins"][1].clone()
         result = {k: batch[k] for k in batch}
         result["frames"] = _rigid(frames)
         result["torsions"] = tors

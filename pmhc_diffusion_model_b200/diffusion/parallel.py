@@ -109,10 +109,10 @@ class DataParallelTrainer:
         self._split = None
         self._event = None
         self._comm = None
-        if self.world > 1:
+        if self.world > 1:      # (a single process keeps the plain step: backward and Adam in one enqueue, graph-capturable as a whole)
             broadcast_parameters(dm.model, 0, group)
-        dm.grad_hook = self._reduce
-        dm.layer2_event_handle = self._event_handle
+            dm.grad_hook = self._reduce
+            dm.layer2_event_handle = self._event_handle
 
     def _event_handle(self):
         if not self.overlap:
@@ -137,7 +137,7 @@ class DataParallelTrainer:
         if self.world <= 1:
             return
         second, first = self._buckets(flat_grad)
-        if not self.overlap or self._event is None:
+        if not self.overlap or self._event is None or not getattr(self.dm, "last_step_overlapped", True):
             allreduce_sum_(second, self.group)
             allreduce_sum_(first, self.group)
             return

@@ -741,6 +741,69 @@ def test_sample_equals_stepwise_api_and_shards_bitwise(api, precision):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# CUDA graphs: the training step and the sampling trajectory captured once per batch shape, scalars read from device memory
+# ------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("precision", ["fp32", "tc32", "bf16"])
+def test_graphed_training_step_equals_eager(api, precision):
+    """use_graph = True replays ONE captured graph for every step; t, the noise key and Adam's bias corrections change per step
+    and are read from the device scalar block.  Same losses (the forward is deterministic: bitwise) and the same weights as
+    the eager path (gradient sums are reproducible to fp32 rounding only, so Adam may differ by a few +-lr on ~zero gradients)."""
+    T, B, lr = 1000, 24, 1e-3
+    batch = orc.synthetic_batch(B, (8, 13), (40, 60), P_pad=80, seed=303)
+    params = orc.random_params(seed=41)
+    gb = gpu_batch(batch)
+    ts, keys = [100, 700, 321, 5], [11, 22, 33, 44]
+    runs = {}
+    for graphed in (False, True):
+        model = make_model(api, params, T)
+        model.precision = precision
+        dm = api.DMO(T, model, lr)
+        dm.use_graph = graphed
+        losses = []
+        for t, k in zip(ts, keys):
+            dm.optimize(dict(gb), None, t=t, noise_key=k)
+            losses.append(dm.last_losses["total loss"].clone())
+        dm.check_nan()
+        runs[graphed] = (losses, model._flat_params().clone(), dm.optimizer.state_dict())
+    assert torch.equal(runs[False][0][0], runs[True][0][0])            # first step: identical weights in, identical losses out
+    for a, b in zip(runs[False][0], runs[True][0]):
+        assert rel_err(b, a) < (2e-3 if precision == "bf16" else 2e-4)
+    assert not torch.equal(runs[True][0][0], runs[True][0][1])         # the steps really differ (t and noise were refreshed)
+    d = (runs[False][1] - runs[True][1]).abs()
+    assert float(d.max()) <= 2.2 * lr * len(ts)
+    assert float((d < 2e-5).float().mean()) > 0.95
+    steps = {float(v["step"]) for v in runs[True][2]["state"].values()}
+    assert steps == {float(len(ts))}
+
+
+@pytest.mark.parametrize("precision", PARITY_MODES)
+def test_graphed_sampling_equals_eager_bitwise(api, precision):
+    """sample(graph=True): the trajectory's 4 T launches replayed as one CUDA graph; the Philox (seed, first complex) pair is
+    read from device memory, so a replay with another seed / shard offset equals the eager call with it, bit for bit."""
+    T, B = 25, 14
+    batch = orc.synthetic_batch(B, (8, 15), (40, 80), P_pad=80, seed=58)
+    model = make_model(api, orc.random_params(seed=7), T)
+    model.precision = precision
+    torch.manual_seed(3)
+    start = api.DMO.gen_noise([B, 16], torch.device(DEV))
+    gb = gpu_batch(batch)
+    gb["frames"] = start["frames"].to_tensor_7()
+    gb["torsions"] = start["torsions"]
+    dm = api.DMO(T, model, 0.0)
+    for seed, first in ((77, 0), (78, 0), (77, 1000)):
+        dm.sample_seed, dm.sample_first_complex = seed, first
+        eager = dm.sample(dict(gb))
+        graphed = dm.sample(dict(gb), graph=True)
+        assert torch.equal(eager["frames"].to_tensor_7(), graphed["frames"].to_tensor_7())
+        assert torch.equal(eager["torsions"], graphed["torsions"])
+    assert len(dm._sample_graphs) == 1                                  # one capture served all three
+    other = dm.sample({k: v[:5] for k, v in gb.items()}, graph=True)    # another batch shape: its own graph
+    dm.sample_first_complex = 1000
+    assert torch.equal(other["frames"].to_tensor_7(), graphed["frames"].to_tensor_7()[:5])
+
+
+# ------------------------------------------------------------------------------------------------------------
 # bf16 tensor-core mode (tcgen05): the two dense contractions in bf16, everything else fp32; gate 1e-2
 # ------------------------------------------------------------------------------------------------------------
 
