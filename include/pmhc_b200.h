@@ -206,6 +206,7 @@ int pmhc_step_scalars(int t, int T, double beta_min, double beta_max, double lr,
                       PmhcStepScalars *out_host);
 /* Copies 1..64 bytes from host to device memory through a kernel's launch parameters (captured when the call returns, ordered
  * on `stream`): how the scalar block above — and pmhc_sample_ex's seed pair — is refreshed before a graph replay. */
+void pmhc_launch_count_add(int64_t n);   /* kernels launched by a replayed CUDA graph (counted at capture) join pmhc_launch_count() */
 int pmhc_upload_small(const void *src_host, void *dst_dev, int bytes, void *stream);
 typedef struct {                  /* caller-owned device buffers of one step */
     float *noise_frames;          /* [B,16,7]   epsilon: written when draw_noise != 0, else read */

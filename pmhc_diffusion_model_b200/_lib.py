@@ -25,7 +25,7 @@ EXPORTS = (
     "pmhc_last_error", "pmhc_check_device", "pmhc_param_offset", "pmhc_param_numel", "pmhc_workspace_bytes",
     "pmhc_saved_floats", "pmhc_model_forward", "pmhc_model_forward_ex", "pmhc_model_backward", "pmhc_model_backward_ex", "pmhc_gen_noise", "pmhc_noise_from_randoms",
     "pmhc_add_noise", "pmhc_remove_noise", "pmhc_loss", "pmhc_sample", "pmhc_sample_ex", "pmhc_adam_step", "pmhc_adam_step_guarded", "pmhc_step_scalars", "pmhc_upload_small",
-    "pmhc_train_step_grad", "pmhc_train_step_adam", "pmhc_launch_count",
+    "pmhc_train_step_grad", "pmhc_train_step_adam", "pmhc_launch_count", "pmhc_launch_count_add",
     "pmhc_profile_enable", "pmhc_profile_read", "pmhc_frames4x4_to_tensor7", "pmhc_atom14", "pmhc_format_pdb_host",
 )
 
@@ -115,6 +115,8 @@ def load() -> ctypes.CDLL:
     lib.pmhc_train_step_adam.argtypes = [vp, vp, vp, vp, c_double, c_double, c_double, POINTER(PmhcStepScalars), vp, vp, vp]
     lib.pmhc_launch_count.restype = i64
     lib.pmhc_launch_count.argtypes = []
+    lib.pmhc_launch_count_add.restype = None
+    lib.pmhc_launch_count_add.argtypes = [i64]
     lib.pmhc_profile_enable.restype = None
     lib.pmhc_profile_enable.argtypes = [c_int]
     lib.pmhc_profile_read.restype = c_int

@@ -65,6 +65,9 @@ extern "C" const char* pmhc_last_error(void) { return g_error; }
 
 extern "C" int64_t pmhc_launch_count(void) { return g_launches.load(); }
 
+// a replayed CUDA graph launches kernels the library never sees: the caller adds the number it counted at capture
+extern "C" void pmhc_launch_count_add(int64_t n) { g_launches.fetch_add(n); }
+
 extern "C" void pmhc_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_profile_mu);
     g_profile = on != 0;

@@ -577,7 +577,13 @@ __device__ __forceinline__ Plan make_plan(const ComplexInfo& ci, const Work& wk,
 }
 
 // ---- per-complex set-up by the engine's 256 threads ----
+// phase stamps (profiles/stamps3.py) cost ~4 % of the kernel's instructions even when switched off at run time: they exist only
+// in builds made with `make EXTRA=-DPMHC_STAMPS`
+#ifdef PMHC_STAMPS
 #define PMHC_TS2(tag) do { if (ts_buf != nullptr && *ts_n < 250) { ts_buf[(*ts_n)++] = (clock64() << 8) | (tag); } } while (0)
+#else
+#define PMHC_TS2(tag) do { } while (0)
+#endif
 template <int LAYER, int TERMS>
 __device__ inline ComplexInfo setup_engine(Engine& E, int b, long long* ts_buf, int* ts_n) {
     const PairArgs& a = E.a;
@@ -851,7 +857,11 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
             int ts_n = 0;
             const bool ts_on = a.dbg != nullptr && blockIdx.x == 0 && eng == 0 && r == 0;
             long long* ts_buf = a.dbg + (grpA ? 0 : 256);
+#ifdef PMHC_STAMPS
 #define PMHC_TS(tag) do { if (ts_on && ts_n < 250) { ts_buf[ts_n++] = (clock64() << 8) | (tag); } } while (0)
+#else
+#define PMHC_TS(tag) do { } while (0)
+#endif
             const Deal deal = make_deal(blockIdx.x, eng, gridDim.x, a.n_eng, a.B);
             Work wk;
             for (int k = 0; get_work(deal, k, a.order, wk); ++k) {

@@ -428,11 +428,13 @@ class DiffusionModelOptimizer:
                         enqueue(gdesc, ins[7], None, False)          # warm-up outside capture: lazy kernel-attribute set-up happens here
                     torch.cuda.synchronize(dev)
                     g = torch.cuda.CUDAGraph()
+                    n0 = lib.pmhc_launch_count()
                     with torch.cuda.graph(g):
                         enqueue(gdesc, ins[7], st.scalars_dev.data_ptr(), not hooked)
-                    st.graph, st.graph_key = g, gkey
+                    st.graph, st.graph_key, st.graph_launches = g, gkey, lib.pmhc_launch_count() - n0
                 _lib.check(lib.pmhc_upload_small(ctypes.byref(sc), st.scalars_dev.data_ptr(), 48, stream_of()), "pmhc_upload_small")
                 st.graph.replay()
+                lib.pmhc_launch_count_add(st.graph_launches)
             if hooked:
                 self.grad_hook(st.grad)
                 _lib.check(lib.pmhc_train_step_adam(flat.data_ptr(), st.grad.data_ptr(), opt._m.data_ptr(), opt._v.data_ptr(), b1, b2, eps,
@@ -545,15 +547,18 @@ class DiffusionModelOptimizer:
                 enqueue()                      # once outside capture: lazy kernel-attribute set-up happens here
                 torch.cuda.synchronize(dev)
                 g = torch.cuda.CUDAGraph()
+                n0 = lib.pmhc_launch_count()
                 with torch.cuda.graph(g):
                     enqueue()
-                sg = self._sample_graphs[key] = {"graph": g, "ins": ins, "scratch": scratch, "seed": seed_dev, "valid": valid, "ws": ws}
+                sg = self._sample_graphs[key] = {"graph": g, "ins": ins, "scratch": scratch, "seed": seed_dev, "valid": valid, "ws": ws,
+                                                 "launches": lib.pmhc_launch_count() - n0}
             for dst, src in zip(sg["ins"], keep):
                 dst.copy_(src, non_blocking=True)
             seed = self.sample_seed if self.sample_seed is not None else _next_noise_key()
             pair = (ctypes.c_uint64 * 2)(int(seed) & (2 ** 64 - 1), int(self.sample_first_complex))
             _lib.check(lib.pmhc_upload_small(pair, sg["seed"].data_ptr(), 16, _lib.stream_ptr(dev)), "pmhc_upload_small")
             sg["graph"].replay()
+            lib.pmhc_launch_count_add(sg["launches"])
             frames, tors = sg["ins"][0].clone(), sg["ins"][1].clone()
         result = {k: batch[k] for k in batch}
         result["frames"] = _rigid(frames)
