@@ -22,6 +22,7 @@
 //
 // TERMS = 2 is the fp32-class mode (PMHC_PRECISION_TC32); TERMS = 1 runs the same pipeline with single fp16 terms.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "egnn_common.cuh"
 #include "tcgen05.cuh"
@@ -923,8 +924,14 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     }
                     PMHC_TS(33);
                 };
-                // streaming softmax: column c of the running sums (0: sum of weights, 1..14: weighted head outputs); 16 lanes walk each
-                // row segment of the tile, then the row's state is rescaled to the new maximum and updated
+                // streaming softmax: column c of the running sums (0: sum of weights, 1..14: weighted head outputs) belongs to a half-warp.
+                // The head outputs lie column-major (Out[c][pair]); lane k of the half-warp takes the 8 consecutive pairs 8k .. 8k + 7
+                // with four 128-bit loads.  With W >= 8 those pairs span at most two rows: the lane forms one partial sum per row, a
+                // butterfly over the 16 lanes adds them up for three rows at a time, and one lane per row rescales the row's state
+                // to its new maximum and adds the sum.  Fixed order throughout (lane-local ascending, then the butterfly): a row's
+                // result depends on the tile grid only.  (W < 8 — hardly any neighbours at all — walks the row segments one by one.)
+                const float invW = W > 0 ? 1.0f / (float)W : 0.0f;
+                auto row_of = [&](int rel) { return __float2int_rd(((float)rel + 0.5f) * invW); };   // rel / W, exact for rel < 2^15
                 auto merge_tile = [&](int mt, int mpar, int my_rl) {
                     const int tg = (pl.t0 + mt) * kTile;
                     const int p_lo = pl.G0 > tg ? pl.G0 - tg : 0, p_hi = pl.G1 - tg < kTile ? pl.G1 - tg : kTile;   // the part's lanes of the tile
@@ -937,26 +944,63 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     E.sync_eng();
                     const int c = et >> 4, k16 = et & 15;
                     PMHC_TS(41);
-                    int s_row = row0, pos = p_lo, len = W - off0 < p_hi - p_lo ? W - off0 : p_hi - p_lo;
-                    while (pos < p_hi) {
-                        float acc = 0.0f;
-                        if (c == 0) {
-                            for (int p = pos + k16; p < pos + len; p += 16) acc += Lg[p];
-                        } else if (c < kOutPerPair) {
-#pragma unroll 4
-                            for (int p = pos + k16; p < pos + len; p += 16) acc = fmaf(Lg[p], Out[p * kOutPerPair + c], acc);
+                    auto update_row = [&](int s_row, float acc) {
+                        const float m_old = Mrow[mpar * kN + s_row];
+                        const float m_new = fmaxf(m_old, dec_max(Mtile[mpar * kN + s_row]));
+                        const float f = m_old == -INFINITY ? 0.0f : soft_exp(m_old - m_new);
+                        St[s_row * 16 + c] = fmaf(St[s_row * 16 + c], f, acc);
+                    };
+                    if (W >= 8) {
+                        // weights of the lanes outside [p_lo, p_hi) are 0 and every Out entry is a finite head output (idle lanes repeat a
+                        // real pair), so the chunk is summed whole
+                        const float4 w0 = reinterpret_cast<const float4*>(Lg)[2 * k16], w1 = reinterpret_cast<const float4*>(Lg)[2 * k16 + 1];
+                        float4 o0 = make_float4(1.0f, 1.0f, 1.0f, 1.0f), o1 = o0;
+                        if (c > 0) {
+                            const float4* col = reinterpret_cast<const float4*>(Out + (c < kOutPerPair ? c : 1) * kTile);
+                            o0 = col[2 * k16];
+                            o1 = col[2 * k16 + 1];
                         }
+                        const int rel0 = off0 + 8 * k16 - p_lo;                  // the chunk's first pair is `rel0` pairs into row `row0`
+                        const int rA = row_of(rel0 > 0 ? rel0 : 0);
+                        const int bnd = (rA + 1) * W - rel0;                      // elements [bnd, 8) lie in the next row
+                        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                        const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+                        float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-                        for (int sh = 8; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-                        if (k16 == 0 && c < kOutPerPair) {
-                            const float m_old = Mrow[mpar * kN + s_row];
-                            const float m_new = fmaxf(m_old, dec_max(Mtile[mpar * kN + s_row]));
-                            const float f = m_old == -INFINITY ? 0.0f : soft_exp(m_old - m_new);
-                            St[s_row * 16 + c] = fmaf(St[s_row * 16 + c], f, acc);
+                        for (int u = 0; u < 8; ++u) {
+                            if (u < bnd) a0 = fmaf(wv[u], ov[u], a0);
+                            else a1 = fmaf(wv[u], ov[u], a1);
                         }
-                        pos += len;
-                        ++s_row;
-                        len = W < p_hi - pos ? W : p_hi - pos;
+                        const int rowA = row0 + rA;
+                        const int last = row0 + row_of(off0 + (p_hi - p_lo) - 1);
+                        for (int R = row0; R <= last; R += 3) {
+                            float v0 = (rowA == R ? a0 : 0.0f) + (rowA + 1 == R ? a1 : 0.0f);
+                            float v1 = (rowA == R + 1 ? a0 : 0.0f) + (rowA == R ? a1 : 0.0f);
+                            float v2 = (rowA == R + 2 ? a0 : 0.0f) + (rowA == R + 1 ? a1 : 0.0f);
+#pragma unroll
+                            for (int sh = 8; sh > 0; sh >>= 1) {
+                                v0 += __shfl_xor_sync(0xffffffffu, v0, sh);
+                                v1 += __shfl_xor_sync(0xffffffffu, v1, sh);
+                                v2 += __shfl_xor_sync(0xffffffffu, v2, sh);
+                            }
+                            if (k16 < 3 && R + k16 <= last && c < kOutPerPair) update_row(R + k16, k16 == 0 ? v0 : (k16 == 1 ? v1 : v2));
+                        }
+                    } else {
+                        int s_row = row0, pos = p_lo, len = W - off0 < p_hi - p_lo ? W - off0 : p_hi - p_lo;
+                        while (pos < p_hi) {
+                            float acc = 0.0f;
+                            if (c == 0) {
+                                for (int p = pos + k16; p < pos + len; p += 16) acc += Lg[p];
+                            } else if (c < kOutPerPair) {
+                                for (int p = pos + k16; p < pos + len; p += 16) acc = fmaf(Lg[p], Out[c * kTile + p], acc);
+                            }
+#pragma unroll
+                            for (int sh = 8; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+                            if (k16 == 0 && c < kOutPerPair) update_row(s_row, acc);
+                            pos += len;
+                            ++s_row;
+                            len = W < p_hi - pos ? W : p_hi - pos;
+                        }
                     }
                     PMHC_TS(42);
                     if (et < kN) {
@@ -997,7 +1041,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                     PMHC_TS(39);
                     if (t > 0) merge_tile(t - 1, par ^ 1, rl_prev);
                     PMHC_TS(11);
-                    float* out = Out + r * kOutPerPair;
+                    float* out = Out + r;          // column-major: output c of this pair at out[c * kTile]
                     E.wait(B_H1);
                     PMHC_TS(13);
                     E.sync_eng();       // every thread has merged the previous tile: Out / Lg may be rewritten
@@ -1039,7 +1083,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         const Quat dl{fast_sigmoid(d[0] + misc[MS_B2ND + 1]), fast_sigmoid(d[1] + misc[MS_B2ND + 2]),
                                       fast_sigmoid(d[2] + misc[MS_B2ND + 3]), fast_sigmoid(d[3] + misc[MS_B2ND + 4])};   // never normalised (T5)
                         const Quat dg = qmul(qj, qmul(dl, qinvj));                                  // model.py:296
-                        out[1] = dg.w; out[2] = dg.x; out[3] = dg.y; out[4] = dg.z;
+                        out[1 * kTile] = dg.w; out[2 * kTile] = dg.x; out[3 * kTile] = dg.y; out[4 * kTile] = dg.z;
                         if (more) stage_tile(nxt);
                         E.phase ^= 1u << B_D3T;   // completion this group does not wait for
                     } else {
@@ -1051,14 +1095,14 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         if (more) issue_aj<LAYER, TERMS>(E, nxt, b);
                         const float sc = dot_relu64(E, TM_X, MS_TRN2) + misc[MS_B2ND + 12];       // model.py:325-327
                         const float4 xi = X[pr.i], xj = X[pr.j];
-                        out[12] = sc * (xi.x - xj.x); out[13] = sc * (xi.y - xj.y); out[14] = sc * (xi.z - xj.z);   // model.py:331
+                        out[12 * kTile] = sc * (xi.x - xj.x); out[13 * kTile] = sc * (xi.y - xj.y); out[14 * kTile] = sc * (xi.z - xj.z);   // model.py:331
                         PMHC_TS(17);
                         E.wait(B_D3T);
                         PMHC_TS(16);
                         float d[8];
                         tc::tmem_ld8(E.tmem + E.lane_base + TM_D3T, d);
 #pragma unroll
-                        for (int c = 0; c < PMHC_NTORS; ++c) out[5 + c] = d[c] + misc[MS_B2ND + 5 + c];
+                        for (int c = 0; c < PMHC_NTORS; ++c) out[(5 + c) * kTile] = d[c] + misc[MS_B2ND + 5 + c];
                         if (more) stage_tile(nxt);
                         E.phase ^= 1u << B_D3R;
                     }
@@ -1569,6 +1613,7 @@ template <int LAYER, int TERMS>
 static int launch_pair3(tc3::PairArgs& a, const Tc3Device& d, cudaStream_t stream) {
     const tc3::Map M = tc3::make_map<TERMS>(a.Kpad, LAYER == 0);
     int n_eng = tc3::kMaxEngines;
+    if (const char* e = getenv("PMHC_TC3_ENGINES")) n_eng = atoi(e) >= 1 && atoi(e) <= tc3::kMaxEngines ? atoi(e) : n_eng;   // development: engines per CTA
     while (n_eng > 0 && (size_t)M.cta_bytes + (size_t)n_eng * M.eng_bytes + 1024 > (size_t)d.max_smem) --n_eng;
     PMHC_REQUIRE(n_eng > 0, "EGNN tensor-core layer does not fit in shared memory (P=%d, device allows %d B)", a.P, d.max_smem);
     a.n_eng = n_eng;
