@@ -664,7 +664,10 @@ def test_trajectory_teacher_forced_matches_reference(api, precision):
             worst[0] = max(worst[0], float((zs["frames"].get_trans().cpu() - case["zt_trans"][k + 1]).norm(dim=-1)[m].max()))
             worst[1] = max(worst[1], float((zs["frames"].get_rots().get_quats().cpu() - case["zt_quats"][k + 1])[m].abs().max()))
             worst[2] = max(worst[2], float((zs["torsions"].cpu() - case["zt_torsions"][k + 1])[m].abs().max()))
-    assert worst[0] < 5e-3 and worst[1] < 1e-3 and worst[2] < 1e-3, worst
+    print(f"teacher-forced T=100 [{precision}]: worst translation {worst[0]:.2e} A, quaternion {worst[1]:.2e}, torsion {worst[2]:.2e}")
+    # gates = the oracle's own against the same fixture (tests/test_oracle.py: 1e-3 A) and half of it on the unit-norm quantities;
+    # measured on B200: 3e-5 A / 1.2e-4 / 1.8e-4 (fp32), 1.5e-5 A / 9e-5 / 1.8e-4 (tc32)
+    assert worst[0] < 1e-3 and worst[1] < 5e-4 and worst[2] < 5e-4, worst
 
 
 @pytest.mark.parametrize("precision", PARITY_MODES)
@@ -689,7 +692,8 @@ def test_sample_free_running_short_horizon_and_validity(api, precision):
             # run only the first `steps` reverse steps: same schedule, truncated tape
             out = _run_partial(api, dm, gb, tape, sign, steps)
             dev = (out["frames"].get_trans().cpu() - case["zt_trans"][steps]).norm(dim=-1)[m]
-            assert float(dev.max()) < 0.05, float(dev.max())
+            print(f"free-running 12 steps [{precision}]: worst per-residue deviation {float(dev.max()):.2e} A")
+            assert float(dev.max()) < 5e-3, float(dev.max())      # north_star asks 0.05 A; measured 2.5e-5 (fp32), 2.8e-4 (tc32)
         else:
             sign_full = torch.cat((sign, sign[-1:]), dim=0)
             out = dm.sample(gb, noise_tape=tape, quat_sign_tape=sign_full)
