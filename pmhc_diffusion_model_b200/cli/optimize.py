@@ -30,7 +30,7 @@ arg_parser.add_argument("-T", type=int, help="number of noise steps", default=10
 arg_parser.add_argument("--batch-size", "-b", type=int, help="data batch size", default=64)
 arg_parser.add_argument("--num-workers", "-w", type=int, help="accepted for compatibility; batches are built on the GPU", default=4)
 arg_parser.add_argument("--lr", type=float, help="learning rate", default=0.001)
-arg_parser.add_argument("--precision", choices=["fp32", "tc32", "bf16"], default="fp32", help="arithmetic of the denoiser: fp32 FFMA (exact parity), tc32 = tcgen05 forward with fp16 hi/lo operand splits (fp32-class) + fp32 backward, or bf16 = tcgen05 forward + TF32 tensor-core backward")
+arg_parser.add_argument("--precision", choices=["fp32", "tc32", "bf16"], default="tc32", help="arithmetic of the denoiser: fp32 FFMA (exact parity), tc32 = tcgen05 forward with fp16 hi/lo operand splits (fp32-class) + fp32 backward, or bf16 = tcgen05 forward + TF32 tensor-core backward")
 arg_parser.add_argument("--seed", type=int, default=None, help="seed of the batch order, noise steps and noise")
 arg_parser.add_argument("--checkpoint", default=None, help="full training state (weights, Adam, random streams, epoch): written "
                         "after every epoch and resumed from when the file exists")

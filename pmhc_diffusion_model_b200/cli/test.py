@@ -24,7 +24,7 @@ arg_parser.add_argument("--debug", "-d", action="store_const", const=True, defau
 arg_parser.add_argument("-T", type=int, default=1000, help="number of noise steps")
 arg_parser.add_argument("--batch-size", "-b", type=int, help="data batch size", default=64)
 arg_parser.add_argument("--num-workers", "-w", type=int, help="accepted for compatibility; batches are built on the GPU", default=4)
-arg_parser.add_argument("--precision", choices=["fp32", "tc32", "bf16"], default="fp32", help="arithmetic of the denoiser")
+arg_parser.add_argument("--precision", choices=["fp32", "tc32", "bf16"], default="tc32", help="arithmetic of the denoiser")
 arg_parser.add_argument("--seed", type=int, default=None, help="noise seed (per-complex Philox streams)")
 
 

@@ -137,7 +137,9 @@ class Model(torch.nn.Module):
         # fp16 hi + lo terms, three MMAs per contraction: fp32-class, holds on the shipped model.pth), "fp16" (same kernels, single
         # fp16 terms) or "bf16" (second-generation tcgen05 kernels, bf16 operands, <= 1e-2 on well-conditioned weights only);
         # geometry, softmax and the frame / torsion updates are fp32 in every mode
-        self.precision = "fp32"
+        # default: "tc32" — the tensor-core mode that meets the FFMA mode's own parity gates on every reference fixture (shipped
+        # model.pth included) at 8x its speed; its backward is the fp32 one
+        self.precision = "tc32"
         # arithmetic of the backward's contractions: None = follow `precision` ("bf16" -> TF32 tensor-core backward, same
         # 1e-2 class as the tensor-core forward), or "fp32" / "bf16" to choose it independently of the forward
         self.backward_precision = None

@@ -52,6 +52,8 @@ def gpu_batch(batch):
 def make_model(api, params, T):
     m = api.Model(16, 22, T)
     m.load_state_dict(params, strict=True)
+    assert m.precision == "tc32"        # the library default: the fp32-class tensor-core mode
+    m.precision = "fp32"                # tests start from the FFMA path unless they choose a mode themselves
     return m.to(DEV)
 
 
@@ -578,6 +580,7 @@ def _dp_worker(rank, world, port, params, batch, steps, out):
         model = Model(16, 22, 1000)
         model.load_state_dict(params, strict=True)
         model = model.to(dev)
+        model.precision = "fp32"          # as make_model() in the parent
         dm = DiffusionModelOptimizer(1000, model, 1e-3)
         trainer = DataParallelTrainer(dm, seed=5)
         n = batch["mask"].shape[0]
