@@ -553,9 +553,9 @@ __device__ __forceinline__ void mma_sums(const Engine& E, uint32_t esu, uint32_t
 // rbeg (the row-split tail of a launch) begins inside tile G0 / 128 with its leading lanes inactive.  A row's pairs then fall
 // into the same tiles, at the same lanes, whether the complex is processed whole or in parts — with the fixed summation order
 // inside a tile and the tile-by-tile merge this makes every row's result independent of the schedule, bit for bit (sharded
-// sampling == unsharded).  The message-only pairs of layer 1 use the same construction.
+// sampling == unsharded).
 struct Plan {
-    int L, W, rbeg, rend, G0, G1, t0, ntiles, msg_w, M0, M1, mt0, msg_tiles;
+    int L, W, rbeg, rend, G0, G1, t0, ntiles;
 };
 __device__ __forceinline__ Plan make_plan(const ComplexInfo& ci, const Work& wk, bool layer1) {
     Plan p;
@@ -566,14 +566,6 @@ __device__ __forceinline__ Plan make_plan(const ComplexInfo& ci, const Work& wk,
     p.G1 = p.rend * p.W;
     p.t0 = p.G0 / kTile;
     p.ntiles = p.G1 > p.G0 ? (p.G1 + kTile - 1) / kTile - p.t0 : 0;
-    // message-only pairs (model.py:151 sums over ALL slots): self, masked peptide slots, masked pocket slots with their own
-    // features, one shared message for the c0 zero-feature masked pocket slots (multiplicity <= 1024 stays exact in fp16)
-    const int nshared = ci.c0 > 1024 ? 2 : (ci.c0 > 0 ? 1 : 0);
-    p.msg_w = 1 + (kN - ci.L) + ci.nx + nshared;
-    p.M0 = p.rbeg * p.msg_w;
-    p.M1 = p.rend * p.msg_w;
-    p.mt0 = p.M0 / kTile;
-    p.msg_tiles = layer1 && p.M1 > p.M0 ? (p.M1 + kTile - 1) / kTile - p.mt0 : 0;
     return p;
 }
 
@@ -827,12 +819,6 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         E.commit(B_D3R);
                     });
                 }
-                for (int t = 0; t < pl.msg_tiles; ++t)
-                    E.serve(NB_REQ_ALL, kEngThreads, [&] {
-                        const uint32_t esu = Engine::opaque(E.es_u), tm = Engine::opaque(E.tmem);
-                        mma_sums<TERMS>(E, esu, tm);
-                        E.commit(B_SUM);
-                    });
             }
         }
     } else {
@@ -1155,37 +1141,7 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                 }
 
                 if (LAYER == 0) {
-                    const int npx = kN - L, W2 = pl.msg_w;
-                    for (int mt = 0; mt < pl.msg_tiles; ++mt) {
-                        const int gp0 = (pl.mt0 + mt) * kTile + r;
-                        const bool act = gp0 >= pl.M0 && gp0 < pl.M1;
-                        const int gp = gp0 < pl.M0 ? pl.M0 : (gp0 >= pl.M1 ? pl.M1 - 1 : gp0);
-                        const int rl = gp / W2, e = gp - rl * W2;
-                        PairRef pr;
-                        pr.i = I[IN_ROWS + rl];
-                        pr.active = act;
-                        float mult = 1.0f;
-                        if (e == 0) pr.j = pr.i;
-                        else if (e <= npx) pr.j = I[IN_PEPX + e - 1];
-                        else if (e <= npx + ci.nx) pr.j = I[IN_POCKET + a.Kpad - 1 - (e - npx - 1)];
-                        else {
-                            pr.j = -1;
-                            const int which = e - (npx + ci.nx + 1);
-                            mult = (float)(which == 0 ? min(ci.c0, 1024) : ci.c0 - 1024);
-                        }
-                        issue_aj<LAYER, TERMS>(E, pr, b);
-                        finish_stage<LAYER, TERMS>(E, pr, b);
-                        if (grpA) write_sel(E, pr, mult);
-                        tc::fence_proxy_async_smem();
-                        E.request(NB_REQ_ALL, kEngThreads);
-                        E.wait(B_SUM);
-                        if (grpA) {
-                            write_sel(E, pr, 0.0f);
-                            add_tile_sums();
-                        }
-                        tc::fence_before_thread_sync();
-                        E.sync_eng();   // both groups are past the tile before its operands are rewritten
-                    }
+                    const int npx = kN - L;
                     // thread 64 h + f holds the sums of tile half h: add the two halves through shared memory (the pair tile is free)
                     float* scr = reinterpret_cast<float*>(es + M.A1);
                     if (grpA) {
@@ -1193,9 +1149,28 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                         for (int i = 0; i < kN; ++i) scr[((r >> 6) * kN + i) * 64 + (r & 63)] = ssum[i];
                     }
                     E.sync_eng();
+                    // + the message-only pairs of the row (model.py:151 sums over ALL slots): self, the padded peptide slots, masked
+                    // pocket slots that carry features of their own, and c0 times the one message all zero-feature masked pocket slots
+                    // share.  81 pairs per complex at the bench shape: summed right here in fp32, (row, feature) per thread, instead
+                    // of a tile pass of their own (staging, selector contraction and an MMA round trip for < 1 tile of pairs).
+                    const float* AiS = reinterpret_cast<const float*>(es + M.AI);
+                    const float* AjS = reinterpret_cast<const float*>(es + M.AJS);
+                    const float* WeS = reinterpret_cast<const float*>(smem + M.WE);
                     for (int idx = et; idx < (pl.rend - pl.rbeg) * kHid; idx += kEngThreads) {
-                        const int o2 = I[IN_ROWS + pl.rbeg + (idx >> 6)] * kHid + (idx & 63);
-                        a.ssum_out[(size_t)b * kN * kHid + o2] = scr[o2] + scr[kN * kHid + o2];
+                        const int i = I[IN_ROWS + pl.rbeg + (idx >> 6)], f = idx & 63;
+                        const float ai = AiS[swz64(i, f)];
+                        float extra = fmaxf(ai + (AjS[swz64(i, f)] + WeS[swz64(kN - 1, f)]), 0.0f);
+                        for (int e = 0; e < npx; ++e) {
+                            const int j = I[IN_PEPX + e];
+                            extra += fmaxf(ai + (AjS[swz64(j, f)] + WeS[swz64(kN - 1 + i - j, f)]), 0.0f);
+                        }
+                        for (int e = 0; e < ci.nx; ++e) {
+                            const int j = I[IN_POCKET + a.Kpad - 1 - e];
+                            extra += fmaxf(ai + __ldg(a.pk32 + ((size_t)b * 2 * a.P + (j - kN)) * kHid + f), 0.0f);
+                        }
+                        if (ci.c0 > 0) extra = fmaf((float)ci.c0, fmaxf(ai, 0.0f), extra);
+                        const int o2 = i * kHid + f;
+                        a.ssum_out[(size_t)b * kN * kHid + o2] = (scr[o2] + scr[kN * kHid + o2]) + extra;
                     }
                     if (wk.part == 0)
                         for (int idx = et; idx < npx * kHid; idx += kEngThreads)
