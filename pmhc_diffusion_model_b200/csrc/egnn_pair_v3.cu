@@ -1055,7 +1055,9 @@ __global__ void __launch_bounds__(kThreads, 1) egnn_pair3_kernel(PairArgs a) {
                             Lg[r] = logit;
                             if (lsave != nullptr) lsave[pr.i * a.Kpad + pr.j] = logit;
                         }
+                        PMHC_TS(51);
                         E.wait(B_TRN);      // the translation head was the last reader of the pair tile
+                        PMHC_TS(50);
                         if (more) issue_aj<LAYER, TERMS>(E, nxt, b);
                         PMHC_TS(17);
                         E.wait(B_D3R);

@@ -31,7 +31,7 @@ with torch.no_grad():
     lib.pmhc_debug_set_stamps3(None)
 st = buf.cpu().tolist()
 names = {1: "complex begin", 2: "setup done", 3: "complex end", 10: "tile begin", 11: "staged", 12: "requested", 13: "H1 ready", 14: "A: att dot + req | B: tor converted + req",
-         15: "A: rot converted + req | B: trn ready", 16: "D3 ready", 17: "B: trn dot done", 18: "outputs written", 21: "setup: bulk issued", 22: "setup: cp.async issued", 23: "setup: cp.async landed", 24: "setup: bulk landed", 25: "setup: torsion term", 26: "setup: lists", 27: "setup: barrier", 30: "stage: begin", 39: "next pair decoded", 40: "merge: weights", 41: "merge: barrier", 42: "merge: sums", 43: "merge: maxima", 31: "stage: loads issued", 32: "stage: tile written", 33: "stage: extras", 19: "engine barrier passed", 20: "softmax merged"}
+         15: "A: rot converted + req | B: trn ready", 16: "D3 ready", 17: "B: trn dot done", 18: "outputs written", 21: "setup: bulk issued", 22: "setup: cp.async issued", 23: "setup: cp.async landed", 24: "setup: bulk landed", 25: "setup: torsion term", 26: "setup: lists", 27: "setup: barrier", 30: "stage: begin", 39: "next pair decoded", 40: "merge: weights", 41: "merge: barrier", 42: "merge: sums", 43: "merge: maxima", 31: "stage: loads issued", 32: "stage: tile written", 33: "stage: extras", 19: "engine barrier passed", 20: "softmax merged", 50: "A: TRN wait passed", 51: "A: row max + logit stored"}
 for layer in range(2):
     for grp in range(2):
         blk = st[layer * 512 + grp * 256: layer * 512 + grp * 256 + 256]

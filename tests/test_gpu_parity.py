@@ -566,7 +566,7 @@ def test_nan_loss_is_sticky_and_never_reaches_the_weights(api):
         dm.check_nan()
 
 
-def _dp_worker(rank, world, port, params, batch, steps, out):
+def _dp_worker(rank, world, port, params, batch, steps, graphed, out):
     import os
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     import torch.distributed as dist
@@ -582,6 +582,7 @@ def _dp_worker(rank, world, port, params, batch, steps, out):
         model = model.to(dev)
         model.precision = "fp32"          # as make_model() in the parent
         dm = DiffusionModelOptimizer(1000, model, 1e-3)
+        dm.use_graph = graphed            # the gradient half of the step as one graph; all-reduce and Adam follow it eagerly
         trainer = DataParallelTrainer(dm, seed=5)
         n = batch["mask"].shape[0]
         for _ in range(steps):
@@ -596,7 +597,8 @@ def _dp_worker(rank, world, port, params, batch, steps, out):
         dist.destroy_process_group()
 
 
-def test_data_parallel_two_gpus_equals_single_process_on_the_global_batch(api):
+@pytest.mark.parametrize("graphed", [False, True])
+def test_data_parallel_two_gpus_equals_single_process_on_the_global_batch(api, graphed):
     """SURVEY.md §4 (vi) on real GPUs: two ranks (NCCL), uneven shards (6 + 5 complexes), three optimize() steps ==
     one process stepping on the 11-complex batch with the same t and noise keys."""
     if torch.cuda.device_count() < 2:
@@ -612,7 +614,7 @@ def test_data_parallel_two_gpus_equals_single_process_on_the_global_batch(api):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, params, batch, steps, out)) for r in range(2)]
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port + int(graphed), params, batch, steps, graphed, out)) for r in range(2)]
     for p in procs:
         p.start()
     results = dict(out.get(timeout=300) for _ in range(2))
