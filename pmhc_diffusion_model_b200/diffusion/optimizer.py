@@ -444,7 +444,10 @@ class DiffusionModelOptimizer:
         # (views of the step's static buffers: valid until the next optimize() call on this batch shape)
         loss_dict = {k: st.losses[i] for i, k in enumerate(LOSS_KEYS)}
         if metrics is not None:
-            metrics.add_batch(loss_dict)
+            if hasattr(metrics, "add_stacked"):
+                metrics.add_stacked(LOSS_KEYS, st.losses)
+            else:
+                metrics.add_batch(loss_dict)
         self.last_losses = loss_dict
         self.last_prediction = (st.pred_f, st.pred_t)
         # the NaN flag is sticky and stays on the device (check_nan()); from the first NaN loss on, every Adam update is skipped

@@ -27,6 +27,17 @@ class MetricsRecord:
             self.totals.index_add_(0, index, per_key)
         self.count += int(next(iter(results.values())).shape[0])
 
+    def add_stacked(self, names, rows: torch.Tensor) -> None:
+        """Same as add_batch for results that already lie stacked as rows [len(names), B] of one tensor (what the fused loss
+        kernel writes): one reduction and one add per batch instead of one reduction per key."""
+        names = list(names)
+        if names != self.keys:
+            if self.keys:                                # mixed use with add_batch: take the general path
+                return self.add_batch({k: rows[i] for i, k in enumerate(names)})
+            self._grow(names, rows)
+        self.totals += rows.detach().sum(dim=1, dtype=self.totals.dtype)
+        self.count += int(rows.shape[1])
+
     def _grow(self, names: List[str], like: torch.Tensor) -> None:
         fresh = [k for k in names if k not in self.keys]
         if not fresh:

@@ -824,6 +824,52 @@ def test_graphed_training_step_equals_eager(api, precision):
     assert steps == {float(len(ts))}
 
 
+def test_graphs_follow_weight_updates_and_a_moved_parameter_buffer(api):
+    """A captured graph holds POINTERS: new weight values (an optimizer step, load_state_dict) are picked up by the next replay —
+    the operand images are rebuilt inside the graph —, and a re-flattened parameter buffer (model.to(), .float(), ...) makes
+    both the training-step graph and the trajectory graph re-capture instead of reading freed memory."""
+    T, B = 10, 6
+    batch = orc.synthetic_batch(B, 9, 40, P_pad=48, seed=61)
+    p1, p2 = orc.random_params(seed=3), orc.random_params(seed=4)
+    gb = gpu_batch(batch)
+    torch.manual_seed(1)
+    start = api.DMO.gen_noise([B, 16], torch.device(DEV))
+    gb["frames"], gb["torsions"] = start["frames"].to_tensor_7(), start["torsions"]
+
+    def eager(params):
+        m = make_model(api, params, T)
+        m.precision = "tc32"
+        d = api.DMO(T, m, 0.0)
+        d.sample_seed = 5
+        return d.sample(dict(gb))["frames"].to_tensor_7()
+
+    model = make_model(api, p1, T)
+    model.precision = "tc32"
+    dm = api.DMO(T, model, 1e-3)
+    dm.sample_seed, dm.use_graph = 5, True
+    assert torch.equal(dm.sample(dict(gb))["frames"].to_tensor_7(), eager(p1))
+    model.load_state_dict(p2, strict=True)                       # same buffer, new values
+    assert torch.equal(dm.sample(dict(gb))["frames"].to_tensor_7(), eager(p2))
+    old_ptr = model._flat_params().data_ptr()
+    model.to(DEV)                                                # _apply re-flattens: a new buffer
+    assert model._flat_params().data_ptr() != old_ptr
+    assert torch.equal(dm.sample(dict(gb))["frames"].to_tensor_7(), eager(p2))
+    # training: two graphed steps, move the buffer, two more — the same as four eager steps on a twin
+    tb = gpu_batch(orc.synthetic_batch(B, 9, 40, P_pad=48, seed=62))
+    twin = make_model(api, p2, T)
+    twin.precision = "tc32"
+    dt = api.DMO(T, twin, 1e-3)
+    for k in range(4):
+        if k == 2:
+            model.to(DEV)
+        dm.optimize(dict(tb), None, t=3 + k, noise_key=70 + k)
+        dt.optimize(dict(tb), None, t=3 + k, noise_key=70 + k)
+        assert rel_err(dm.last_losses["total loss"], dt.last_losses["total loss"]) < 2e-4
+    dm.check_nan()
+    d = (model._flat_params() - twin._flat_params()).abs()
+    assert float(d.max()) <= 2.2e-3 * 4 and float((d < 2e-5).float().mean()) > 0.95
+
+
 @pytest.mark.parametrize("precision", PARITY_MODES)
 def test_graphed_sampling_equals_eager_bitwise(api, precision):
     """sample(graph=True): the trajectory's 4 T launches replayed as one CUDA graph; the Philox (seed, first complex) pair is
