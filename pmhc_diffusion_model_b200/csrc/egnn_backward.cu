@@ -1351,6 +1351,240 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
     __syncthreads();
 }
 
+// Per-complex prologue shared by every backward kernel: the row-level backward of the output normalisation / torsion rotation /
+// translation (RowG), and for layer 1 the node-feature-MLP backward (model.py:151, :407) that produces dL / d(message sum).
+// Every thread of the CTA takes part (NT = blockDim.x); the caller synchronises afterwards.
+template <int LAYER>
+__device__ __forceinline__ void bwd_prologue(float* S, const BwdMap& M, const BwdArgs& g, int b, const int* I, int L, int W,
+                                             float* __restrict__ direct, const int NT) {
+    const LayerArgs& a = g.a;
+    constexpr bool IN_GRADS = (LAYER == 1);
+    constexpr int base = param_offset(LAYER, 0);
+    const int tid = threadIdx.x;
+    // ---------------- row level: output normalisation, q' = g * q_i, torsion rotation, x' = x + Xa ----------------
+    if (tid < L) {
+        const int i = I[IN_ROWS + tid];
+        const size_t node = (size_t)b * kN + i;
+        const float* rs = g.rowstat + node * PMHC_ROWSTAT;
+        const float* dof = g.d_frames_out + node * 7;
+        const float* dot_ = g.d_tors_out + node * 14;
+        const Quat G{rs[1], rs[2], rs[3], rs[4]};
+        const Quat qi{S[M.f.Q + i * 4], S[M.f.Q + i * 4 + 1], S[M.f.Q + i * 4 + 2], S[M.f.Q + i * 4 + 3]};
+        const bool hasnb = W > 0;
+        const Quat gq = hasnb ? qnormalize(G) : Quat{1.0f, 0.0f, 0.0f, 0.0f};
+        const Quat qp = qmul(gq, qi);
+        const Quat dqp = qnormalize_grad(qp, Quat{dof[0], dof[1], dof[2], dof[3]});
+        const Quat dgq = qmul_grad_a(dqp, qi);
+        const Quat dG = hasnb ? qnormalize_grad(G, dgq) : Quat{0.0f, 0.0f, 0.0f, 0.0f};
+        float* rg = S + M.RowG + i * 16;
+        rg[0] = dG.w; rg[1] = dG.x; rg[2] = dG.y; rg[3] = dG.z;
+        float cacc = qdot(dG, G);
+        if (IN_GRADS) {
+            const Quat dqi = qmul_grad_b(gq, dqp);
+            S[M.dQ + i * 4 + 0] += dqi.w; S[M.dQ + i * 4 + 1] += dqi.x; S[M.dQ + i * 4 + 2] += dqi.y; S[M.dQ + i * 4 + 3] += dqi.z;
+        }
+        for (int c = 0; c < PMHC_NTORS; ++c) {
+            float sn, cs;
+            sincosf(rs[5 + c], &sn, &cs);
+            const float ts = S[M.f.Tors + i * 14 + 2 * c], tc = S[M.f.Tors + i * 14 + 2 * c + 1];
+            const float ds_ = dot_[2 * c], dc_ = dot_[2 * c + 1];
+            const float dS = ds_ * tc - dc_ * ts, dC = ds_ * ts + dc_ * tc;
+            const float dDa = dS * cs - dC * sn;
+            rg[4 + c] = dDa;
+            cacc = fmaf(dDa, rs[5 + c], cacc);
+            if (IN_GRADS) {
+                S[M.dTors + i * 14 + 2 * c] += ds_ * cs - dc_ * sn;
+                S[M.dTors + i * 14 + 2 * c + 1] += ds_ * sn + dc_ * cs;
+            }
+        }
+        for (int c = 0; c < 3; ++c) {
+            rg[11 + c] = dof[4 + c];
+            cacc = fmaf(dof[4 + c], rs[12 + c], cacc);
+            if (IN_GRADS) S[M.dX + i * 3 + c] += dof[4 + c];
+        }
+        rg[14] = cacc;
+        rg[15] = rs[0];
+    }
+
+    // ---------------- layer 1: node feature MLP backward (model.py:151, :407) -> dMsum ----------------
+    if (LAYER == 0) {
+        const float* f0w = a.params + param_offset(0, FEAT0_W);
+        const float* f0b = a.params + param_offset(0, FEAT0_B);
+        const float* f2w = a.params + param_offset(0, FEAT2_W);
+        constexpr int ldf = kH1 + kHid;
+        float* hid = S + M.BufA;                 // [16][65] relu(feature_mlp.0(...))
+        float* dO = S + M.BufA + kN * kLdN;      // [16][65] dL/do (after the relu mask)
+        float* dhid = S + M.BufB;                // [16][65]
+        for (int idx = tid; idx < L * kHid; idx += NT) {
+            int r = idx >> 6, n = idx & 63;
+            int i = I[IN_ROWS + r];
+            const float* w = f0w + n * ldf;
+            const float* h = S + M.f.H + i * kLdN;
+            const float* ms = S + M.f.Msum + i * kHid;
+            float acc = f0b[n];
+            for (int c = 0; c < kH1; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
+            for (int c = 0; c < kHid; ++c) acc = fmaf(__ldg(w + kH1 + c), ms[c], acc);
+            hid[r * kLdN + n] = fmaxf(acc, 0.0f);
+            const size_t node = (size_t)b * kN + i;
+            dO[r * kLdN + n] = g.feat_post[node * kHid + n] > 0.0f ? g.d_feat_out[node * kHid + n] : 0.0f;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < L * kHid; idx += NT) {
+            int r = idx >> 6, n = idx & 63;
+            float acc = 0.0f;
+            for (int n2 = 0; n2 < kHid; ++n2) acc = fmaf(__ldg(f2w + n2 * kHid + n), dO[r * kLdN + n2], acc);
+            dhid[r * kLdN + n] = hid[r * kLdN + n] > 0.0f ? acc : 0.0f;
+        }
+        // feature_mlp.2: dW[n2][n] += sum_r dO[r][n2] hid[r][n]; db[n2] += sum_r dO[r][n2]
+        for (int idx = tid; idx < kHid * kHid + kHid; idx += NT) {
+            float acc = 0.0f;
+            if (idx < kHid * kHid) {
+                int n2 = idx >> 6, n = idx & 63;
+                const float old = __ldcg(direct + (param_offset(0, FEAT2_W) - base) + idx);   // L2 round trip under the products
+                for (int r = 0; r < L; ++r) acc = fmaf(dO[r * kLdN + n2], hid[r * kLdN + n], acc);
+                direct[(param_offset(0, FEAT2_W) - base) + idx] = old + acc;
+            } else {
+                int n2 = idx - kHid * kHid;
+                for (int r = 0; r < L; ++r) acc += dO[r * kLdN + n2];
+                direct[(param_offset(0, FEAT2_B) - base) + n2] += acc;
+            }
+        }
+        __syncthreads();
+        // feature_mlp.0: dW[n][c] += sum_r dhid[r][n] cat(h, msum)[r][c]; db[n] += sum_r dhid[r][n]
+        for (int idx = tid; idx < kHid * ldf + kHid; idx += NT) {
+            float acc = 0.0f;
+            if (idx < kHid * ldf) {
+                int n = idx / ldf, c = idx - n * ldf;
+                const float old = __ldcg(direct + (param_offset(0, FEAT0_W) - base) + idx);
+                for (int r = 0; r < L; ++r) {
+                    int i = I[IN_ROWS + r];
+                    float x = c < kH1 ? S[M.f.H + i * kLdN + c] : S[M.f.Msum + i * kHid + (c - kH1)];
+                    acc = fmaf(dhid[r * kLdN + n], x, acc);
+                }
+                direct[(param_offset(0, FEAT0_W) - base) + idx] = old + acc;
+            } else {
+                int n = idx - kHid * ldf;
+                for (int r = 0; r < L; ++r) acc += dhid[r * kLdN + n];
+                direct[(param_offset(0, FEAT0_B) - base) + n] += acc;
+            }
+        }
+        for (int idx = tid; idx < L * kHid; idx += NT) {
+            int r = idx >> 6, k = idx & 63;
+            float acc = 0.0f;
+            for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(f0w + n * ldf + kH1 + k), dhid[r * kLdN + n], acc);
+            S[M.dMsum + I[IN_ROWS + r] * kHid + k] = acc;
+        }
+    }
+}
+
+// Per-complex node level shared by every backward kernel: message_mlp.0, torsion_mlp.0[:, 64:78] and biases from the per-node
+// accumulators; layer 2 also writes the input gradients.  LDC = row stride of the staging tile at M.BufA; TORB = torsion_mlp.0.bias
+// from the per-row sums (false when the caller gets it from its own bias column).
+template <int LAYER, int LDC, bool TORB>
+__device__ __forceinline__ void bwd_node_level(float* S, const BwdMap& M, const BwdArgs& g, int b, const int* I, float* __restrict__ dajt,
+                                               float* __restrict__ direct, const int NT) {
+    const LayerArgs& a = g.a;
+    constexpr bool IN_GRADS = (LAYER == 1);
+    constexpr int H = layer_H(LAYER);
+    constexpr int ld1 = 2 * H + kEdge;
+    constexpr int base = param_offset(LAYER, 0);
+    const int tid = threadIdx.x;
+    const int Kpad = a.Kpad, P = a.P;
+    // ---------------- node level: message_mlp.0, torsion_mlp.0[:, 64:78] and biases; input gradients ----------------
+    {
+        // neighbour-feature columns fed by the pocket (cc < 22): sum_j dA_j[k] h_j[cc] over the peptide, then over the
+        // pocket slots in ascending order; the pocket's dA_j^T (L2) and features are staged through shared memory in
+        // chunks of 128 slots so the 80..480-term chains run from shared memory instead of one L2 round trip per term
+        constexpr int ldc = LDC;
+        float* scr = S + M.Dout;                 // [64][22] running sums (Dout + Ex are free outside the passes)
+        float* stA = S + M.BufA;                 // [64][ldc] dA_j^T chunk
+        float* stB = S + M.BufB;                 // [128][22] pocket features chunk
+        for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += NT) {
+            const int k = idx / PMHC_NFEAT, cc = idx - k * PMHC_NFEAT;
+            float acc = 0.0f;
+            for (int j = 0; j < kN; ++j) acc = fmaf(S[M.dAjPep + j * kLdN + k], S[M.f.H + j * kLdN + cc], acc);
+            scr[idx] = acc;
+        }
+        for (int p0 = 0; p0 < P; p0 += 128) {
+            const int n = min(128, P - p0);
+            __syncthreads();
+            for (int idx = tid; idx < kHid * n; idx += NT) {
+                const int k = idx / n, pp = idx - k * n;
+                stA[k * ldc + pp] = __ldcg(dajt + k * Kpad + kN + p0 + pp);
+            }
+            const float* pf = a.pocket_feat + ((size_t)b * P + p0) * PMHC_NFEAT;
+            for (int idx = tid; idx < n * PMHC_NFEAT; idx += NT) stB[idx] = __ldg(pf + idx);
+            __syncthreads();
+            for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += NT) {
+                const int k = idx / PMHC_NFEAT, cc = idx - k * PMHC_NFEAT;
+                float acc = scr[idx];
+#pragma unroll 8
+                for (int pp = 0; pp < n; ++pp) acc = fmaf(stA[k * ldc + pp], stB[pp * PMHC_NFEAT + cc], acc);
+                scr[idx] = acc;
+            }
+        }
+        __syncthreads();
+        float* dW1 = direct + (param_offset(LAYER, MSG0_W) - base);
+        for (int idx = tid; idx < kHid * ld1; idx += NT) {
+            int k = idx / ld1, c = idx - k * ld1;
+            const float old = __ldcg(dW1 + idx);     // the L2 round trip of the running sum hides under the products below
+            float acc = 0.0f;
+            if (c < H) {
+                for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dAi + i * kLdN + k], S[M.f.H + i * kLdN + c], acc);
+            } else if (c < 2 * H) {
+                int cc = c - H;
+                if (cc < PMHC_NFEAT) {
+                    acc = scr[k * PMHC_NFEAT + cc];
+                } else {
+                    for (int j = 0; j < kN; ++j) acc = fmaf(S[M.dAjPep + j * kLdN + k], S[M.f.H + j * kLdN + cc], acc);
+                }
+            } else {
+                acc = S[M.dWe + (c - 2 * H) * kLdN + k];
+            }
+            dW1[idx] = old + acc;
+        }
+        for (int k = tid; k < kHid; k += NT) {
+            float acc = 0.0f, acct = 0.0f;
+            for (int i = 0; i < kN; ++i) {
+                acc += S[M.dAi + i * kLdN + k];
+                acct += S[M.dTt + i * kHid + k];
+            }
+            direct[(param_offset(LAYER, MSG0_B) - base) + k] += acc;
+            if (TORB) direct[(param_offset(LAYER, TOR0_B) - base) + k] += acct;
+        }
+        for (int idx = tid; idx < kHid * 14; idx += NT) {
+            int n = idx / 14, c = idx - n * 14;
+            float acc = 0.0f;
+            for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dTt + i * kHid + n], S[M.f.Tors + i * 14 + c], acc);
+            direct[(param_offset(LAYER, TOR0_W) - base) + n * 78 + 64 + c] += acc;
+        }
+        if (IN_GRADS) {
+            const float* tor0 = a.params + param_offset(LAYER, TOR0_W);
+            const float* msg0 = a.params + param_offset(LAYER, MSG0_W);
+            for (int idx = tid; idx < kN * 7; idx += NT) {
+                int i = idx / 7, c = idx - i * 7;
+                g.d_frames_in[((size_t)b * kN + i) * 7 + c] = c < 4 ? S[M.dQ + i * 4 + c] : S[M.dX + i * 3 + (c - 4)];
+            }
+            for (int idx = tid; idx < kN * 14; idx += NT) {
+                int i = idx / 14, c = idx - i * 14;
+                float acc = S[M.dTors + idx];
+                for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(tor0 + n * 78 + 64 + c), S[M.dTt + i * kHid + n], acc);
+                g.d_tors_in[(size_t)b * kN * 14 + idx] = acc;
+            }
+            for (int idx = tid; idx < kN * kHid; idx += NT) {
+                int i = idx >> 6, c = idx & 63;
+                float acc = 0.0f;
+                for (int k = 0; k < kHid; ++k) {
+                    acc = fmaf(S[M.dAi + i * kLdN + k], __ldg(msg0 + k * ld1 + c), acc);
+                    acc = fmaf(S[M.dAjPep + i * kLdN + k], __ldg(msg0 + k * ld1 + H + c), acc);
+                }
+                g.d_feat_in[(size_t)b * kN * kHid + idx] = acc;
+            }
+        }
+    }
+}
+
+
 template <int LAYER, bool TC>
 __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(BwdArgs g) {
     extern __shared__ __align__(16) float S[];
@@ -1383,120 +1617,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
             for (int idx = tid; idx < kN * kHid; idx += kBwdThreads) S[M.f.Msum + idx] = g.msum[(size_t)b * kN * kHid + idx];
         __syncthreads();
 
-        // ---------------- row level: output normalisation, q' = g * q_i, torsion rotation, x' = x + Xa ----------------
-        if (tid < L) {
-            const int i = I[IN_ROWS + tid];
-            const size_t node = (size_t)b * kN + i;
-            const float* rs = g.rowstat + node * PMHC_ROWSTAT;
-            const float* dof = g.d_frames_out + node * 7;
-            const float* dot_ = g.d_tors_out + node * 14;
-            const Quat G{rs[1], rs[2], rs[3], rs[4]};
-            const Quat qi{S[M.f.Q + i * 4], S[M.f.Q + i * 4 + 1], S[M.f.Q + i * 4 + 2], S[M.f.Q + i * 4 + 3]};
-            const bool hasnb = W > 0;
-            const Quat gq = hasnb ? qnormalize(G) : Quat{1.0f, 0.0f, 0.0f, 0.0f};
-            const Quat qp = qmul(gq, qi);
-            const Quat dqp = qnormalize_grad(qp, Quat{dof[0], dof[1], dof[2], dof[3]});
-            const Quat dgq = qmul_grad_a(dqp, qi);
-            const Quat dG = hasnb ? qnormalize_grad(G, dgq) : Quat{0.0f, 0.0f, 0.0f, 0.0f};
-            float* rg = S + M.RowG + i * 16;
-            rg[0] = dG.w; rg[1] = dG.x; rg[2] = dG.y; rg[3] = dG.z;
-            float cacc = qdot(dG, G);
-            if (IN_GRADS) {
-                const Quat dqi = qmul_grad_b(gq, dqp);
-                S[M.dQ + i * 4 + 0] += dqi.w; S[M.dQ + i * 4 + 1] += dqi.x; S[M.dQ + i * 4 + 2] += dqi.y; S[M.dQ + i * 4 + 3] += dqi.z;
-            }
-            for (int c = 0; c < PMHC_NTORS; ++c) {
-                float sn, cs;
-                sincosf(rs[5 + c], &sn, &cs);
-                const float ts = S[M.f.Tors + i * 14 + 2 * c], tc = S[M.f.Tors + i * 14 + 2 * c + 1];
-                const float ds_ = dot_[2 * c], dc_ = dot_[2 * c + 1];
-                const float dS = ds_ * tc - dc_ * ts, dC = ds_ * ts + dc_ * tc;
-                const float dDa = dS * cs - dC * sn;
-                rg[4 + c] = dDa;
-                cacc = fmaf(dDa, rs[5 + c], cacc);
-                if (IN_GRADS) {
-                    S[M.dTors + i * 14 + 2 * c] += ds_ * cs - dc_ * sn;
-                    S[M.dTors + i * 14 + 2 * c + 1] += ds_ * sn + dc_ * cs;
-                }
-            }
-            for (int c = 0; c < 3; ++c) {
-                rg[11 + c] = dof[4 + c];
-                cacc = fmaf(dof[4 + c], rs[12 + c], cacc);
-                if (IN_GRADS) S[M.dX + i * 3 + c] += dof[4 + c];
-            }
-            rg[14] = cacc;
-            rg[15] = rs[0];
-        }
-
-        // ---------------- layer 1: node feature MLP backward (model.py:151, :407) -> dMsum ----------------
-        if (LAYER == 0) {
-            const float* f0w = a.params + param_offset(0, FEAT0_W);
-            const float* f0b = a.params + param_offset(0, FEAT0_B);
-            const float* f2w = a.params + param_offset(0, FEAT2_W);
-            constexpr int ldf = kH1 + kHid;
-            float* hid = S + M.BufA;                 // [16][65] relu(feature_mlp.0(...))
-            float* dO = S + M.BufA + kN * kLdN;      // [16][65] dL/do (after the relu mask)
-            float* dhid = S + M.BufB;                // [16][65]
-            for (int idx = tid; idx < L * kHid; idx += kBwdThreads) {
-                int r = idx >> 6, n = idx & 63;
-                int i = I[IN_ROWS + r];
-                const float* w = f0w + n * ldf;
-                const float* h = S + M.f.H + i * kLdN;
-                const float* ms = S + M.f.Msum + i * kHid;
-                float acc = f0b[n];
-                for (int c = 0; c < kH1; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
-                for (int c = 0; c < kHid; ++c) acc = fmaf(__ldg(w + kH1 + c), ms[c], acc);
-                hid[r * kLdN + n] = fmaxf(acc, 0.0f);
-                const size_t node = (size_t)b * kN + i;
-                dO[r * kLdN + n] = g.feat_post[node * kHid + n] > 0.0f ? g.d_feat_out[node * kHid + n] : 0.0f;
-            }
-            __syncthreads();
-            for (int idx = tid; idx < L * kHid; idx += kBwdThreads) {
-                int r = idx >> 6, n = idx & 63;
-                float acc = 0.0f;
-                for (int n2 = 0; n2 < kHid; ++n2) acc = fmaf(__ldg(f2w + n2 * kHid + n), dO[r * kLdN + n2], acc);
-                dhid[r * kLdN + n] = hid[r * kLdN + n] > 0.0f ? acc : 0.0f;
-            }
-            // feature_mlp.2: dW[n2][n] += sum_r dO[r][n2] hid[r][n]; db[n2] += sum_r dO[r][n2]
-            for (int idx = tid; idx < kHid * kHid + kHid; idx += kBwdThreads) {
-                float acc = 0.0f;
-                if (idx < kHid * kHid) {
-                    int n2 = idx >> 6, n = idx & 63;
-                    const float old = __ldcg(direct + (param_offset(0, FEAT2_W) - base) + idx);   // L2 round trip under the products
-                    for (int r = 0; r < L; ++r) acc = fmaf(dO[r * kLdN + n2], hid[r * kLdN + n], acc);
-                    direct[(param_offset(0, FEAT2_W) - base) + idx] = old + acc;
-                } else {
-                    int n2 = idx - kHid * kHid;
-                    for (int r = 0; r < L; ++r) acc += dO[r * kLdN + n2];
-                    direct[(param_offset(0, FEAT2_B) - base) + n2] += acc;
-                }
-            }
-            __syncthreads();
-            // feature_mlp.0: dW[n][c] += sum_r dhid[r][n] cat(h, msum)[r][c]; db[n] += sum_r dhid[r][n]
-            for (int idx = tid; idx < kHid * ldf + kHid; idx += kBwdThreads) {
-                float acc = 0.0f;
-                if (idx < kHid * ldf) {
-                    int n = idx / ldf, c = idx - n * ldf;
-                    const float old = __ldcg(direct + (param_offset(0, FEAT0_W) - base) + idx);
-                    for (int r = 0; r < L; ++r) {
-                        int i = I[IN_ROWS + r];
-                        float x = c < kH1 ? S[M.f.H + i * kLdN + c] : S[M.f.Msum + i * kHid + (c - kH1)];
-                        acc = fmaf(dhid[r * kLdN + n], x, acc);
-                    }
-                    direct[(param_offset(0, FEAT0_W) - base) + idx] = old + acc;
-                } else {
-                    int n = idx - kHid * ldf;
-                    for (int r = 0; r < L; ++r) acc += dhid[r * kLdN + n];
-                    direct[(param_offset(0, FEAT0_B) - base) + n] += acc;
-                }
-            }
-            for (int idx = tid; idx < L * kHid; idx += kBwdThreads) {
-                int r = idx >> 6, k = idx & 63;
-                float acc = 0.0f;
-                for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(f0w + n * ldf + kH1 + k), dhid[r * kLdN + n], acc);
-                S[M.dMsum + I[IN_ROWS + r] * kHid + k] = acc;
-            }
-        }
+        bwd_prologue<LAYER>(S, M, g, b, I, L, W, direct, kBwdThreads);
         __syncthreads();
 
         // ---------------- attention-carrying pairs ----------------
@@ -1533,98 +1654,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) egnn_layer_backward_kernel(Bwd
         }
         __syncthreads();
 
-        // ---------------- node level: message_mlp.0, torsion_mlp.0[:, 64:78] and biases; input gradients ----------------
-        {
-            // neighbour-feature columns fed by the pocket (cc < 22): sum_j dA_j[k] h_j[cc] over the peptide, then over the
-            // pocket slots in ascending order; the pocket's dA_j^T (L2) and features are staged through shared memory in
-            // chunks of 128 slots so the 80..480-term chains run from shared memory instead of one L2 round trip per term
-            constexpr int ldc = TC ? kLdt : kLdc;
-            float* scr = S + M.Dout;                 // [64][22] running sums (Dout + Ex are free outside the passes)
-            float* stA = S + M.BufA;                 // [64][ldc] dA_j^T chunk
-            float* stB = S + M.BufB;                 // [128][22] pocket features chunk
-            for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += kBwdThreads) {
-                const int k = idx / PMHC_NFEAT, cc = idx - k * PMHC_NFEAT;
-                float acc = 0.0f;
-                for (int j = 0; j < kN; ++j) acc = fmaf(S[M.dAjPep + j * kLdN + k], S[M.f.H + j * kLdN + cc], acc);
-                scr[idx] = acc;
-            }
-            for (int p0 = 0; p0 < P; p0 += 128) {
-                const int n = min(128, P - p0);
-                __syncthreads();
-                for (int idx = tid; idx < kHid * n; idx += kBwdThreads) {
-                    const int k = idx / n, pp = idx - k * n;
-                    stA[k * ldc + pp] = __ldcg(dajt + k * Kpad + kN + p0 + pp);
-                }
-                const float* pf = a.pocket_feat + ((size_t)b * P + p0) * PMHC_NFEAT;
-                for (int idx = tid; idx < n * PMHC_NFEAT; idx += kBwdThreads) stB[idx] = __ldg(pf + idx);
-                __syncthreads();
-                for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += kBwdThreads) {
-                    const int k = idx / PMHC_NFEAT, cc = idx - k * PMHC_NFEAT;
-                    float acc = scr[idx];
-#pragma unroll 8
-                    for (int pp = 0; pp < n; ++pp) acc = fmaf(stA[k * ldc + pp], stB[pp * PMHC_NFEAT + cc], acc);
-                    scr[idx] = acc;
-                }
-            }
-            __syncthreads();
-            float* dW1 = direct + (param_offset(LAYER, MSG0_W) - base);
-            for (int idx = tid; idx < kHid * ld1; idx += kBwdThreads) {
-                int k = idx / ld1, c = idx - k * ld1;
-                const float old = __ldcg(dW1 + idx);     // the L2 round trip of the running sum hides under the products below
-                float acc = 0.0f;
-                if (c < H) {
-                    for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dAi + i * kLdN + k], S[M.f.H + i * kLdN + c], acc);
-                } else if (c < 2 * H) {
-                    int cc = c - H;
-                    if (cc < PMHC_NFEAT) {
-                        acc = scr[k * PMHC_NFEAT + cc];
-                    } else {
-                        for (int j = 0; j < kN; ++j) acc = fmaf(S[M.dAjPep + j * kLdN + k], S[M.f.H + j * kLdN + cc], acc);
-                    }
-                } else {
-                    acc = S[M.dWe + (c - 2 * H) * kLdN + k];
-                }
-                dW1[idx] = old + acc;
-            }
-            for (int k = tid; k < kHid; k += kBwdThreads) {
-                float acc = 0.0f, acct = 0.0f;
-                for (int i = 0; i < kN; ++i) {
-                    acc += S[M.dAi + i * kLdN + k];
-                    acct += S[M.dTt + i * kHid + k];
-                }
-                direct[(param_offset(LAYER, MSG0_B) - base) + k] += acc;
-                direct[(param_offset(LAYER, TOR0_B) - base) + k] += acct;
-            }
-            for (int idx = tid; idx < kHid * 14; idx += kBwdThreads) {
-                int n = idx / 14, c = idx - n * 14;
-                float acc = 0.0f;
-                for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dTt + i * kHid + n], S[M.f.Tors + i * 14 + c], acc);
-                direct[(param_offset(LAYER, TOR0_W) - base) + n * 78 + 64 + c] += acc;
-            }
-            if (IN_GRADS) {
-                const float* tor0 = a.params + param_offset(LAYER, TOR0_W);
-                const float* msg0 = a.params + param_offset(LAYER, MSG0_W);
-                for (int idx = tid; idx < kN * 7; idx += kBwdThreads) {
-                    int i = idx / 7, c = idx - i * 7;
-                    g.d_frames_in[((size_t)b * kN + i) * 7 + c] = c < 4 ? S[M.dQ + i * 4 + c] : S[M.dX + i * 3 + (c - 4)];
-                }
-                for (int idx = tid; idx < kN * 14; idx += kBwdThreads) {
-                    int i = idx / 14, c = idx - i * 14;
-                    float acc = S[M.dTors + idx];
-                    for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(tor0 + n * 78 + 64 + c), S[M.dTt + i * kHid + n], acc);
-                    g.d_tors_in[(size_t)b * kN * 14 + idx] = acc;
-                }
-                for (int idx = tid; idx < kN * kHid; idx += kBwdThreads) {
-                    int i = idx >> 6, c = idx & 63;
-                    float acc = 0.0f;
-                    for (int k = 0; k < kHid; ++k) {
-                        acc = fmaf(S[M.dAi + i * kLdN + k], __ldg(msg0 + k * ld1 + c), acc);
-                        acc = fmaf(S[M.dAjPep + i * kLdN + k], __ldg(msg0 + k * ld1 + H + c), acc);
-                    }
-                    g.d_feat_in[(size_t)b * kN * kHid + idx] = acc;
-                }
-            }
-        }
+        bwd_node_level<LAYER, TC ? kLdt : kLdc, true>(S, M, g, b, I, dajt, direct, kBwdThreads);
         __syncthreads();
     }
 
@@ -1670,8 +1700,16 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int st
     grad[p] += acc;
 }
 
+}  // namespace pmhc
+
+#include "egnn_backward_t5.cuh"
+
+namespace pmhc {
+
 struct BwdWorkspace {
     float *ajt, *dajt, *partial, *d_frames1, *d_tors1, *d_feat1;
+    float *red, *scale;      // tcgen05 mode: reduced partials of a layer, the two layers' operand scales
+    uint8_t* wimg;           // tcgen05 mode: folded-weight images of both layers
     int partial_stride;
     size_t bytes;
 };
@@ -1690,6 +1728,10 @@ BwdWorkspace carve_bwd_workspace(void* wsbase, size_t fwd_bytes, int B, int P) {
     w.d_frames1 = p + o; o += (size_t)B * kN * 7;
     w.d_tors1 = p + o;   o += (size_t)B * kN * 14;
     w.d_feat1 = p + o;   o += (size_t)B * kN * kHid;
+    o = (o + 3) & ~(size_t)3;
+    w.red = p + o;       o += ((size_t)max_layer + 3) & ~(size_t)3;
+    w.scale = p + o;     o += 8;
+    w.wimg = reinterpret_cast<uint8_t*>(p + o); o += (2 * kFoldImageBytes + 3) / 4;
     w.bytes = o * sizeof(float);
     return w;
 }
@@ -1719,6 +1761,38 @@ int launch_layer_backward(const BwdArgs& g, int n_cta, float* grad, cudaStream_t
     return 0;
 }
 
+
+template <int LAYER>
+int launch_layer_backward_t5(const BwdArgs& g, const BwdWorkspace& w, int n_cta, float* grad, cudaStream_t stream) {
+    static PerDeviceOnce configured;
+    int max_smem = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const T5Map T = make_t5_map(g.a.Kpad);
+    const size_t smem = (size_t)T.total_bytes;
+    PMHC_REQUIRE((int)smem <= max_smem, "EGNN backward needs %zu B of shared memory (P=%d), device allows %d", smem, g.a.P, max_smem);
+    if (configured.needed()) {
+        cudaError_t e = cudaFuncSetAttribute(egnn_layer_backward_t5_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(backward): %s", cudaGetErrorString(e));
+        configured.mark();
+    }
+    constexpr int base = param_offset(LAYER, 0);
+    constexpr int numel = param_offset(LAYER + 1, 0) - base;
+    float* scale = w.scale + 4 * LAYER;
+    bwd_grad_scale_kernel<<<1, 1024, 0, stream>>>(g.d_frames_out, g.a.B * kN * 7, g.d_tors_out, g.a.B * kN * 14, scale);
+    PMHC_CHECK_LAUNCH("bwd_grad_scale");
+    T5Args x{w.wimg + (size_t)LAYER * kFoldImageBytes, scale};
+    if (profile_enabled()) profile_mark(PROF_BWD, stream, true);
+    egnn_layer_backward_t5_kernel<LAYER><<<n_cta, kT5Threads, smem, stream>>>(g, x);
+    if (profile_enabled()) profile_mark(PROF_BWD, stream, false);
+    PMHC_CHECK_LAUNCH("egnn_layer_backward_t5");
+    reduce_partials_to_kernel<<<(numel + 255) / 256, 256, 0, stream>>>(g.partial, g.partial_stride, n_cta, numel, w.red);
+    PMHC_CHECK_LAUNCH("reduce_partials_to");
+    bwd_unfold_kernel<LAYER><<<(numel + 255) / 256, 256, 0, stream>>>(g.a.params, w.red, grad);
+    PMHC_CHECK_LAUNCH("bwd_unfold");
+    return 0;
+}
+
 size_t forward_workspace_bytes(int B, int P);
 
 }  // namespace pmhc
@@ -1734,8 +1808,10 @@ extern "C" int pmhc_model_backward_ex(const float* params, const PmhcBatch* bt, 
                                       void* workspace, size_t workspace_bytes, void* stream_, void* layer2_done_event,
                                       int precision) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    PMHC_REQUIRE(precision == PMHC_PRECISION_FP32 || precision == PMHC_PRECISION_BF16, "pmhc_model_backward: unknown precision %d", precision);
+    PMHC_REQUIRE(precision == PMHC_PRECISION_FP32 || precision == PMHC_PRECISION_BF16 || precision == PMHC_PRECISION_FP16,
+                 "pmhc_model_backward: unknown precision %d", precision);
     const bool tc = precision == PMHC_PRECISION_BF16;
+    const bool t5 = precision == PMHC_PRECISION_FP16;
     PMHC_REQUIRE(device_props() == 0, "no CUDA device");
     PMHC_REQUIRE(bt != nullptr && bt->B > 0, "pmhc_model_backward: empty batch");
     PMHC_REQUIRE(bt->P >= 1 && bt->P <= kMaxP, "pmhc_model_backward: pocket_maxlen %d outside [1, %d]", bt->P, kMaxP);
@@ -1761,7 +1837,12 @@ extern "C" int pmhc_model_backward_ex(const float* params, const PmhcBatch* bt, 
     g.rowstat = sv.rowstat2; g.logits = sv.logits2; g.msum = nullptr; g.feat_post = nullptr;
     g.d_frames_out = d_out_frames; g.d_tors_out = d_out_torsions; g.d_feat_out = nullptr;
     g.d_frames_in = w.d_frames1; g.d_tors_in = w.d_tors1; g.d_feat_in = w.d_feat1;
-    int rc = tc ? launch_layer_backward<1, true>(g, n_cta, flat_grad, stream) : launch_layer_backward<1, false>(g, n_cta, flat_grad, stream);
+    if (t5) {
+        bwd_fold_weights_kernel<<<8, 256, 0, stream>>>(params, w.wimg);
+        PMHC_CHECK_LAUNCH("bwd_fold_weights");
+    }
+    int rc = t5 ? launch_layer_backward_t5<1>(g, w, n_cta, flat_grad, stream)
+                : tc ? launch_layer_backward<1, true>(g, n_cta, flat_grad, stream) : launch_layer_backward<1, false>(g, n_cta, flat_grad, stream);
     if (rc != 0) return rc;
     if (layer2_done_event != nullptr) cudaEventRecord((cudaEvent_t)layer2_done_event, stream);
     // layer 1
@@ -1769,6 +1850,7 @@ extern "C" int pmhc_model_backward_ex(const float* params, const PmhcBatch* bt, 
     g.rowstat = sv.rowstat1; g.logits = sv.logits1; g.msum = sv.msum1; g.feat_post = sv.feat1;
     g.d_frames_out = w.d_frames1; g.d_tors_out = w.d_tors1; g.d_feat_out = w.d_feat1;
     g.d_frames_in = nullptr; g.d_tors_in = nullptr; g.d_feat_in = nullptr;
+    if (t5) return launch_layer_backward_t5<0>(g, w, n_cta, flat_grad, stream);
     return tc ? launch_layer_backward<0, true>(g, n_cta, flat_grad, stream) : launch_layer_backward<0, false>(g, n_cta, flat_grad, stream);
 }
 

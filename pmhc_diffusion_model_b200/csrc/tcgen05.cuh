@@ -340,5 +340,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
                  : "memory");
 }
 
+
+// ---- tf32 operands (kind::tf32: fp32 words in shared memory, the low 13 mantissa bits ignored; K = 8 per instruction) ----
+// a_format = b_format = 2 (cute::UMMA::F16F32Format::TF32), D fp32; a_mn / b_mn = 1: MN-major shared-memory operand
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// byte offset of fp32 element (row, c) inside one SW128 atom column of 32 floats per row (c < 32): rows of 128 B, 8-row groups
+// 1024 B apart, the 16-byte chunk index XORed with row & 7.  The same bytes serve as a K-major operand (row = M / N index,
+// c = K) and as an MN-major operand (row = K index, c = M / N index).
+__device__ __forceinline__ uint32_t sw128_offset_f32(int row, int c) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((c >> 2) ^ (row & 7)) & 7) << 4) + ((c & 3) << 2));
+}
+
 }  // namespace tc
 }  // namespace pmhc

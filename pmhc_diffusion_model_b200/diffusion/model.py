@@ -198,8 +198,8 @@ class Model(torch.nn.Module):
 
     def backward_precision_code(self) -> int:
         mode = _lib.BACKWARD_OF.get(self.precision, self.precision) if self.backward_precision is None else self.backward_precision
-        if mode not in ("fp32", "bf16"):
-            raise ValueError(f"Model.backward_precision must be None, 'fp32' or 'bf16', got {mode!r}")
+        if mode not in ("fp32", "bf16", "fp16"):
+            raise ValueError(f"Model.backward_precision must be None, 'fp32', 'bf16' (TF32 mma.sync) or 'fp16' (tcgen05), got {mode!r}")
         return _lib.PRECISIONS[mode]
 
     # ---- forward -----------------------------------------------------------------------------------------

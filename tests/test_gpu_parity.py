@@ -339,9 +339,10 @@ def test_parameter_gradients_edge_shapes_vs_oracle_autograd(api):
         assert rel_err(p.grad.cpu(), p_ref[k].grad) < TOL, (k, rel_err(p.grad.cpu(), p_ref[k].grad))
 
 
+@pytest.mark.parametrize("bmode", ["bf16", "fp16"])
 @pytest.mark.parametrize("B,L,Pn,P_pad,seed", [(5, (2, 16), (3, 50), 50, 41), (7, (8, 15), (40, 180), 192, 77), (3, (9, 9), (60, 60), 80, 5),
                                               (2, (8, 15), (150, 400), 400, 13)])
-def test_tf32_backward_gradients_vs_oracle_autograd(api, B, L, Pn, P_pad, seed):
+def test_tf32_backward_gradients_vs_oracle_autograd(api, B, L, Pn, P_pad, seed, bmode):
     """Tensor-core backward on its own (fp32 forward, backward_precision = "bf16"): the forward recomputation, the input
     gradients and the weight-gradient outer products run as TF32 MMAs.  Ragged peptides, dirty padding (message-only pairs
     with their own features), several passes per complex.
@@ -367,7 +368,7 @@ def test_tf32_backward_gradients_vs_oracle_autograd(api, B, L, Pn, P_pad, seed):
     true_g = {"frames": api.Rigid(api.Rotation(quats=true["frames"]["quats"].to(DEV), normalize_quats=False), true["frames"]["trans"].to(DEV)),
               "torsions": true["torsions"].to(DEV)}
     grads = {}
-    for mode in ("fp32", "bf16"):
+    for mode in ("fp32", bmode):
         model = make_model(api, params, 100)
         model.backward_precision = mode
         gb = gpu_batch(batch)
@@ -377,9 +378,9 @@ def test_tf32_backward_gradients_vs_oracle_autograd(api, B, L, Pn, P_pad, seed):
     bad, differs, flat_got, flat_ref = [], False, [], []
     for k, ref in p_ref.items():
         if k.startswith("gnn2.feature_mlp"):
-            assert grads["bf16"][k] is None
+            assert grads[bmode][k] is None
             continue
-        got = grads["bf16"][k]
+        got = grads[bmode][k]
         err = float((got - ref.grad).abs().max())
         scale = float(ref.grad.abs().max())
         if k.endswith("attention_mlp.2.bias"):
