@@ -493,18 +493,29 @@ def main():
         tb = {k: v.to(dev) for k, v in synthetic(TRAIN_B, seed=5000 + rank).items()}
         fp32_leg, _ = train_leg(tb, "fp32", None)
         tc32_leg, _ = train_leg(tb, "tc32", None)          # tcgen05 hi/lo forward (saves the softmax statistics), fp32 FFMA backward
-        bf16_leg, bf16_step = train_leg(tb, "bf16", None)  # bf16 tcgen05 forward + TF32 tensor-core backward
+        bf16_leg, bf16_step = train_leg(tb, "bf16", None)  # bf16 tcgen05 forward + tcgen05 backward (fp16 operand tiles, TMEM accumulators)
         tprof_ms, tprof_n = kernel_times(bf16_step, n_train, tdm)
         # backward roofline (tensor pipe): 3 x 43.4 kFLOP per real pair per layer (recomputation + input gradients + weight
         # gradients), both layers' kernels averaged; pairs as in the forward count
         bwd_us = tprof_ms[1] / max(tprof_n[1], 1) * 1e3
         bwd_flops = TRAIN_B * 3.0 * 0.5 * forward_flops_per_complex()
-        bf16_leg.update({"config": "bf16 training mode: tcgen05 bf16 forward + TF32 tensor-core backward (gradient gate 1e-2 class)",
+        bf16_leg.update({"config": "bf16 training mode: tcgen05 bf16 forward + tcgen05 backward (fp16 operand tiles used K-major and MN-major, "
+                                   "weight-gradient sums resident in tensor memory; gradient gate 1e-2 class)",
+                         "backward_kernel": "egnn_layer_backward_t5_kernel<LAYER>",
                          "backward_kernel_us": bwd_us,
                          "backward_roofline": {"bound": "tensor", "achieved": bwd_flops / (bwd_us * 1e-6) / 1e12, "peak": peaks["bf16_tflops"],
                                                "unit": "TFLOP/s", "frac": bwd_flops / (bwd_us * 1e-6) / 1e12 / peaks["bf16_tflops"],
-                                               "note": "algorithmic 3 x 43.4 kFLOP per pair per layer; TF32 mma.sync (legacy tensor path), "
-                                                       "judged against the measured bf16 peak"}})
+                                               "note": "algorithmic 3 x 43.4 kFLOP per pair per layer (the folded message layer executes fewer); "
+                                                       "tcgen05 kind::f16, judged against the measured bf16 peak"}})
+        if world == 1 and not args.no_modes:
+            legacy_leg, legacy_step = train_leg(tb, "bf16", "bf16")   # the round-1 warp-level TF32 mma.sync backward, for comparison
+            lprof_ms, lprof_n = kernel_times(legacy_step, n_train, tdm)
+            legacy_leg.update({"config": "bf16 tcgen05 forward + warp-level TF32 mma.sync backward (round 1)",
+                               "backward_kernel_us": lprof_ms[1] / max(lprof_n[1], 1) * 1e3})
+            bf16_leg["tf32_mma_backward"] = legacy_leg
+            mixed_leg, _ = train_leg(tb, "tc32", "fp16")
+            mixed_leg["config"] = "tcgen05 hi/lo-split forward (fp32-class outputs and loss) + tcgen05 fp16 backward (1e-2-class gradients)"
+            bf16_leg["tc32_forward"] = mixed_leg
         tc32_leg["config"] = "fp32-class training: tcgen05 hi/lo-split forward + fp32 FFMA backward (gradient gate 1e-4, same as fp32)"
         train = {"metric": "train complexes/s", **fp32_leg, "steps": n_train,
                  "config": "B=256/GPU, 9-mer, pocket 60/80, fp32 FFMA forward + backward, noise+forward+loss+backward+Adam per step (BASELINE configs[2], [3] at N=8)",

@@ -19,7 +19,9 @@ HID = 64        # PMHC_HID
 NPARAM = 79195  # PMHC_NPARAM
 ROWSTAT = 16    # PMHC_ROWSTAT
 PRECISIONS = {"fp32": 0, "bf16": 1, "tc32": 2, "fp16": 3}  # PMHC_PRECISION_*
-BACKWARD_OF = {"fp32": "fp32", "bf16": "bf16", "tc32": "fp32", "fp16": "bf16"}  # default backward arithmetic of a forward mode
+# default backward arithmetic of a forward mode: "fp16" = the tcgen05 backward (fp16 operand tiles, fp32 accumulation in tensor memory),
+# "bf16" = the older warp-level TF32 mma.sync backward (kept selectable through Model.backward_precision for A/B runs)
+BACKWARD_OF = {"fp32": "fp32", "bf16": "fp16", "tc32": "fp32", "fp16": "fp16"}
 
 EXPORTS = (
     "pmhc_last_error", "pmhc_check_device", "pmhc_param_offset", "pmhc_param_numel", "pmhc_workspace_bytes",

@@ -1351,6 +1351,26 @@ __device__ __forceinline__ void pair_pass_tc(float* S, const BwdMap& M, const Bw
     __syncthreads();
 }
 
+#ifdef PMHC_T5_STAMPS
+__device__ long long node_dbg[24];
+#define NSTAMP(k) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { long long now_ = clock64(); node_dbg[k] += now_ - nst_; nst_ = now_; } } while (0)
+#else
+#define NSTAMP(k) do { } while (0)
+#endif
+// dst[idx] += f(idx) for idx < n on the CTA's L2-resident partial: U read-modify-writes of a thread are in flight together (their
+// round trips overlap each other and the products), instead of one L2 latency per element
+template <int U, class F>
+__device__ __forceinline__ void rmw_batched(float* __restrict__ dst, int n, const int NT, F f) {
+    for (int idx0 = threadIdx.x; idx0 < n; idx0 += U * NT) {
+        float old[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) old[u] = idx0 + u * NT < n ? ldcg_early(dst + idx0 + u * NT) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (idx0 + u * NT < n) dst[idx0 + u * NT] = old[u] + f(idx0 + u * NT);
+    }
+}
+
 // Per-complex prologue shared by every backward kernel: the row-level backward of the output normalisation / torsion rotation /
 // translation (RowG), and for layer 1 the node-feature-MLP backward (model.py:151, :407) that produces dL / d(message sum).
 // Every thread of the CTA takes part (NT = blockDim.x); the caller synchronises afterwards.
@@ -1361,6 +1381,9 @@ __device__ __forceinline__ void bwd_prologue(float* S, const BwdMap& M, const Bw
     constexpr bool IN_GRADS = (LAYER == 1);
     constexpr int base = param_offset(LAYER, 0);
     const int tid = threadIdx.x;
+#ifdef PMHC_T5_STAMPS
+    long long nst_ = clock64();
+#endif
     // ---------------- row level: output normalisation, q' = g * q_i, torsion rotation, x' = x + Xa ----------------
     if (tid < L) {
         const int i = I[IN_ROWS + tid];
@@ -1415,63 +1438,80 @@ __device__ __forceinline__ void bwd_prologue(float* S, const BwdMap& M, const Bw
         float* hid = S + M.BufA;                 // [16][65] relu(feature_mlp.0(...))
         float* dO = S + M.BufA + kN * kLdN;      // [16][65] dL/do (after the relu mask)
         float* dhid = S + M.BufB;                // [16][65]
+        // both weight matrices of the feature MLP staged behind those (coalesced copies, many loads in flight): every product
+        // below then reads shared memory instead of walking an L2-latency chain per term
+        NSTAMP(8);
+        float* f0s = S + M.BufA + 2 * kN * kLdN;  // [64][87]
+        float* f2s = S + M.BufB + kN * kLdN;      // [64][64]
+#pragma unroll 8
+        for (int idx = tid; idx < kHid * ldf; idx += NT) f0s[idx] = __ldg(f0w + idx);
+#pragma unroll 8
+        for (int idx = tid; idx < kHid * kHid; idx += NT) f2s[idx] = __ldg(f2w + idx);
+        __syncthreads();
+        NSTAMP(9);
         for (int idx = tid; idx < L * kHid; idx += NT) {
             int r = idx >> 6, n = idx & 63;
             int i = I[IN_ROWS + r];
-            const float* w = f0w + n * ldf;
+            const float* w = f0s + n * ldf;
             const float* h = S + M.f.H + i * kLdN;
             const float* ms = S + M.f.Msum + i * kHid;
             float acc = f0b[n];
-            for (int c = 0; c < kH1; ++c) acc = fmaf(__ldg(w + c), h[c], acc);
-            for (int c = 0; c < kHid; ++c) acc = fmaf(__ldg(w + kH1 + c), ms[c], acc);
+#pragma unroll
+            for (int c = 0; c < kH1; ++c) acc = fmaf(w[c], h[c], acc);
+#pragma unroll 16
+            for (int c = 0; c < kHid; ++c) acc = fmaf(w[kH1 + c], ms[c], acc);
             hid[r * kLdN + n] = fmaxf(acc, 0.0f);
             const size_t node = (size_t)b * kN + i;
             dO[r * kLdN + n] = g.feat_post[node * kHid + n] > 0.0f ? g.d_feat_out[node * kHid + n] : 0.0f;
         }
         __syncthreads();
+        NSTAMP(10);
         for (int idx = tid; idx < L * kHid; idx += NT) {
             int r = idx >> 6, n = idx & 63;
             float acc = 0.0f;
-            for (int n2 = 0; n2 < kHid; ++n2) acc = fmaf(__ldg(f2w + n2 * kHid + n), dO[r * kLdN + n2], acc);
+#pragma unroll 16
+            for (int n2 = 0; n2 < kHid; ++n2) acc = fmaf(f2s[n2 * kHid + n], dO[r * kLdN + n2], acc);
             dhid[r * kLdN + n] = hid[r * kLdN + n] > 0.0f ? acc : 0.0f;
         }
+        NSTAMP(11);
         // feature_mlp.2: dW[n2][n] += sum_r dO[r][n2] hid[r][n]; db[n2] += sum_r dO[r][n2]
-        for (int idx = tid; idx < kHid * kHid + kHid; idx += NT) {
+        static_assert(param_offset(0, FEAT2_B) == param_offset(0, FEAT2_W) + kHid * kHid, "feature_mlp.2 weight and bias are adjacent");
+        rmw_batched<8>(direct + (param_offset(0, FEAT2_W) - base), kHid * kHid + kHid, NT, [&](int idx) {
             float acc = 0.0f;
             if (idx < kHid * kHid) {
-                int n2 = idx >> 6, n = idx & 63;
-                const float old = __ldcg(direct + (param_offset(0, FEAT2_W) - base) + idx);   // L2 round trip under the products
+                const int n2 = idx >> 6, n = idx & 63;
                 for (int r = 0; r < L; ++r) acc = fmaf(dO[r * kLdN + n2], hid[r * kLdN + n], acc);
-                direct[(param_offset(0, FEAT2_W) - base) + idx] = old + acc;
             } else {
-                int n2 = idx - kHid * kHid;
+                const int n2 = idx - kHid * kHid;
                 for (int r = 0; r < L; ++r) acc += dO[r * kLdN + n2];
-                direct[(param_offset(0, FEAT2_B) - base) + n2] += acc;
             }
-        }
+            return acc;
+        });
         __syncthreads();
+        NSTAMP(12);
         // feature_mlp.0: dW[n][c] += sum_r dhid[r][n] cat(h, msum)[r][c]; db[n] += sum_r dhid[r][n]
-        for (int idx = tid; idx < kHid * ldf + kHid; idx += NT) {
+        static_assert(param_offset(0, FEAT0_B) == param_offset(0, FEAT0_W) + kHid * ldf, "feature_mlp.0 weight and bias are adjacent");
+        rmw_batched<8>(direct + (param_offset(0, FEAT0_W) - base), kHid * ldf + kHid, NT, [&](int idx) {
             float acc = 0.0f;
             if (idx < kHid * ldf) {
-                int n = idx / ldf, c = idx - n * ldf;
-                const float old = __ldcg(direct + (param_offset(0, FEAT0_W) - base) + idx);
+                const int n = idx / ldf, c = idx - n * ldf;
                 for (int r = 0; r < L; ++r) {
-                    int i = I[IN_ROWS + r];
-                    float x = c < kH1 ? S[M.f.H + i * kLdN + c] : S[M.f.Msum + i * kHid + (c - kH1)];
+                    const int i = I[IN_ROWS + r];
+                    const float x = c < kH1 ? S[M.f.H + i * kLdN + c] : S[M.f.Msum + i * kHid + (c - kH1)];
                     acc = fmaf(dhid[r * kLdN + n], x, acc);
                 }
-                direct[(param_offset(0, FEAT0_W) - base) + idx] = old + acc;
             } else {
-                int n = idx - kHid * ldf;
+                const int n = idx - kHid * ldf;
                 for (int r = 0; r < L; ++r) acc += dhid[r * kLdN + n];
-                direct[(param_offset(0, FEAT0_B) - base) + n] += acc;
             }
-        }
+            return acc;
+        });
+        NSTAMP(13);
         for (int idx = tid; idx < L * kHid; idx += NT) {
             int r = idx >> 6, k = idx & 63;
             float acc = 0.0f;
-            for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(f0w + n * ldf + kH1 + k), dhid[r * kLdN + n], acc);
+#pragma unroll 16
+            for (int n = 0; n < kHid; ++n) acc = fmaf(f0s[n * ldf + kH1 + k], dhid[r * kLdN + n], acc);
             S[M.dMsum + I[IN_ROWS + r] * kHid + k] = acc;
         }
     }
@@ -1490,6 +1530,9 @@ __device__ __forceinline__ void bwd_node_level(float* S, const BwdMap& M, const 
     constexpr int base = param_offset(LAYER, 0);
     const int tid = threadIdx.x;
     const int Kpad = a.Kpad, P = a.P;
+#ifdef PMHC_T5_STAMPS
+    long long nst_ = clock64();
+#endif
     // ---------------- node level: message_mlp.0, torsion_mlp.0[:, 64:78] and biases; input gradients ----------------
     {
         // neighbour-feature columns fed by the pocket (cc < 22): sum_j dA_j[k] h_j[cc] over the peptide, then over the
@@ -1524,25 +1567,28 @@ __device__ __forceinline__ void bwd_node_level(float* S, const BwdMap& M, const 
             }
         }
         __syncthreads();
+        NSTAMP(0);
         float* dW1 = direct + (param_offset(LAYER, MSG0_W) - base);
-        for (int idx = tid; idx < kHid * ld1; idx += NT) {
-            int k = idx / ld1, c = idx - k * ld1;
-            const float old = __ldcg(dW1 + idx);     // the L2 round trip of the running sum hides under the products below
+        rmw_batched<8>(dW1, kHid * ld1, NT, [&](int idx) {
+            const int k = idx / ld1, c = idx - k * ld1;
             float acc = 0.0f;
             if (c < H) {
+#pragma unroll
                 for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dAi + i * kLdN + k], S[M.f.H + i * kLdN + c], acc);
             } else if (c < 2 * H) {
-                int cc = c - H;
+                const int cc = c - H;
                 if (cc < PMHC_NFEAT) {
                     acc = scr[k * PMHC_NFEAT + cc];
                 } else {
+#pragma unroll
                     for (int j = 0; j < kN; ++j) acc = fmaf(S[M.dAjPep + j * kLdN + k], S[M.f.H + j * kLdN + cc], acc);
                 }
             } else {
                 acc = S[M.dWe + (c - 2 * H) * kLdN + k];
             }
-            dW1[idx] = old + acc;
-        }
+            return acc;
+        });
+        NSTAMP(1);
         for (int k = tid; k < kHid; k += NT) {
             float acc = 0.0f, acct = 0.0f;
             for (int i = 0; i < kN; ++i) {
@@ -1561,6 +1607,25 @@ __device__ __forceinline__ void bwd_node_level(float* S, const BwdMap& M, const 
         if (IN_GRADS) {
             const float* tor0 = a.params + param_offset(LAYER, TOR0_W);
             const float* msg0 = a.params + param_offset(LAYER, MSG0_W);
+            // the node columns of message_mlp.0 and the torsion columns of torsion_mlp.0 staged in the (now free) pass tiles:
+            // coalesced copies with many loads in flight instead of one L2 round trip per term of the products below
+            NSTAMP(2);
+            constexpr int LDQ = 2 * H + 1;
+            float* wq = S + M.BufA;                  // [64][2 H + 1]
+            float* tx = S + M.BufB;                  // [64][15]
+            static_assert(kHid * LDQ <= kHid * kLdc, "message_mlp.0's node columns must fit the staging tile");
+            __syncthreads();
+#pragma unroll 8
+            for (int idx = tid; idx < kHid * 2 * H; idx += NT) {
+                const int k = idx / (2 * H), c = idx - k * (2 * H);
+                wq[k * LDQ + c] = __ldg(msg0 + k * ld1 + c);
+            }
+            for (int idx = tid; idx < kHid * 14; idx += NT) {
+                const int n = idx / 14, c = idx - n * 14;
+                tx[n * 15 + c] = __ldg(tor0 + n * 78 + 64 + c);
+            }
+            __syncthreads();
+            NSTAMP(3);
             for (int idx = tid; idx < kN * 7; idx += NT) {
                 int i = idx / 7, c = idx - i * 7;
                 g.d_frames_in[((size_t)b * kN + i) * 7 + c] = c < 4 ? S[M.dQ + i * 4 + c] : S[M.dX + i * 3 + (c - 4)];
@@ -1568,18 +1633,21 @@ __device__ __forceinline__ void bwd_node_level(float* S, const BwdMap& M, const 
             for (int idx = tid; idx < kN * 14; idx += NT) {
                 int i = idx / 14, c = idx - i * 14;
                 float acc = S[M.dTors + idx];
-                for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(tor0 + n * 78 + 64 + c), S[M.dTt + i * kHid + n], acc);
+#pragma unroll 16
+                for (int n = 0; n < kHid; ++n) acc = fmaf(tx[n * 15 + c], S[M.dTt + i * kHid + n], acc);
                 g.d_tors_in[(size_t)b * kN * 14 + idx] = acc;
             }
             for (int idx = tid; idx < kN * kHid; idx += NT) {
                 int i = idx >> 6, c = idx & 63;
                 float acc = 0.0f;
+#pragma unroll 8
                 for (int k = 0; k < kHid; ++k) {
-                    acc = fmaf(S[M.dAi + i * kLdN + k], __ldg(msg0 + k * ld1 + c), acc);
-                    acc = fmaf(S[M.dAjPep + i * kLdN + k], __ldg(msg0 + k * ld1 + H + c), acc);
+                    acc = fmaf(S[M.dAi + i * kLdN + k], wq[k * LDQ + c], acc);
+                    acc = fmaf(S[M.dAjPep + i * kLdN + k], wq[k * LDQ + H + c], acc);
                 }
                 g.d_feat_in[(size_t)b * kN * kHid + idx] = acc;
             }
+            NSTAMP(4);
         }
     }
 }

@@ -34,14 +34,18 @@ constexpr int kT5Threads = 288;   // 8 compute warps (two threads per pair) + 1 
 constexpr int kT5Compute = 256;
 // operand tiles: byte offsets from the 1024-byte aligned base of dynamic shared memory
 constexpr int T5_M1 = 0, T5_F = 16384, T5_HID = 49152, T5_DPRE = 81920, T5_DX = 114688, T5_TILE_BYTES = 131072;
-constexpr int T5_RED = T5_HID;                       // fp32 [78][132] reduction tile over the (then free) hid / dpre tiles
-constexpr int T5_RED2 = T5_HID + 78 * kLdc * 4;      // message-only passes: fp32 [64][132] tile of mult * m1
+constexpr int T5_RED = T5_HID;                       // fp32 [64][132] tile of dm1 over the (then free) hid / dpre tiles
+constexpr int T5_DM1H = T5_DPRE + 16384;             // the same as an fp16 operand tile (per-row sums on the tensor core)
+constexpr int T5_RED2 = T5_HID + 64 * kLdc * 4;      // message-only passes: fp32 [64][132] tile of mult * m1
+static_assert(T5_RED + 64 * kLdc * 4 <= T5_DM1H, "the fp32 and fp16 dm1 tiles must not overlap");
 static_assert(T5_HID / 4 + 2 * kHid * kLdt + kHid * PMHC_NFEAT + 96 + kN * kHid <= T5_TILE_BYTES / 4, "staging views must fit behind the folded weights");
 static_assert(T5_RED2 + 64 * kLdc * 4 <= T5_TILE_BYTES, "reduction tiles must fit over the hid / dpre / dx tiles");
 // DX tile columns (fp16): second-layer output gradients of head pair A / B, the extra-input block shared by all heads
-constexpr int DX_A = 0 /* rotation 0..3, torsion 8..14 */, DX_B = 16 /* translation 16, attention 24 */, DX_EXT = 32 /* lq 0..3, -d2, qdot2, 1 */;
+// DX_OUT (16): rotation 0..3, translation 4, attention 5, torsion 8..14 — pair A and pair B write the same columns (the other pair's zero);
+// DX_EXT_A (16): lq 0..3, -d2 4, qdot2 5, one 6; DX_EXT_B = the window 8 columns further: zeros 0..7, -d2 8, qdot2 9, one 10; DX_SEL (16): one-hot row
+constexpr int DX_OUT = 0, DX_EXT_A = 16, DX_EXT_B = 24, DX_SEL = 48;
 // tensor memory columns
-constexpr int TM_HID = 0, TM_DM1 = 256, TM_DFA = 320, TM_DFB = 384, TM_DW3A = 448, TM_DW3B = 464, TM_EXTA = 480, TM_EXTB = 496;
+constexpr int TM_HID = 0, TM_DM1 = 256, TM_DFA = 320, TM_DFB = 384, TM_DW3 = 448, TM_EXT = 464, TM_SEL = 480, TM_ROW = 496;
 // image of one layer's folded weights (global memory, written by bwd_fold_weights_kernel): 4 fp16 SW128 tiles [n][k] in the order
 // rotation, torsion, translation, attention, then c_h as [4][64] floats
 constexpr int kFoldImageBytes = 4 * 8192 + 4 * kHid * 4;
@@ -291,12 +295,13 @@ __device__ __forceinline__ void t5_load64(uint32_t taddr, float (&v)[kHid]) {
     for (int c = 0; c < 32; ++c) { v[c] = __uint_as_float(r0[c]); v[32 + c] = __uint_as_float(r1[c]); }
 }
 
-// ---- the MMA-issuing warp: the three batches of one attention-carrying pass (np = running pass count of the CTA) ----
-__device__ __forceinline__ void t5_issue_pass(uint32_t sbase, uint32_t tmem, uint64_t* bars, uint32_t np) {
+// ---- the MMA-issuing warp: the three batches of one attention-carrying pass (np = running pass count of the CTA, q = pass of the complex) ----
+__device__ __forceinline__ void t5_issue_pass(uint32_t sbase, uint32_t tmem, uint64_t* bars, uint32_t np, int q) {
     const uint32_t par = np & 1u;
-    const uint32_t first = np == 0 ? 0u : 1u;     // accumulate flag of the CTA-resident weight-gradient sums
-    uint64_t* rdy = bars;        // [0..2]
-    uint64_t* done = bars + 3;   // [0..2]
+    const uint32_t keep = np == 0 ? 0u : 1u;      // accumulate flag of the CTA-resident weight-gradient sums at their first step
+    const uint32_t keep_c = q == 0 ? 0u : 1u;     // ... of the complex-resident per-row sums
+    uint64_t* rdy = bars;        // [0..3]
+    uint64_t* done = bars + 4;   // [0..3]
     constexpr uint32_t id_hid = tc::idesc_f16_f32(128, 128);
     constexpr uint32_t id_w16 = tc::idesc_f16_f32_major(128, 16, 1, 1);
     constexpr uint32_t id_w64 = tc::idesc_f16_f32_major(128, 64, 1, 1);
@@ -316,26 +321,12 @@ __device__ __forceinline__ void t5_issue_pass(uint32_t sbase, uint32_t tmem, uin
     }
     __syncwarp();
     // batches 1, 2: head pairs (rotation, torsion) and (translation, attention)
-#pragma unroll
+#pragma unroll 1
     for (int pair = 0; pair < 2; ++pair) {
         tc::mbar_wait_suspend(rdy + 1 + pair, par);
         tc::fence_after_thread_sync();
         if (tc::elect_one()) {
-            const uint32_t dx = sbase + T5_DX + (pair == 0 ? DX_A : DX_B) * 2;
-            // weight-gradient sums over the pairs of the pass (K = 128 pairs = 8 steps of 16 rows), A = the two heads' tiles stacked in M
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                tc::mma_bf16(tmem + (pair == 0 ? TM_DW3A : TM_DW3B), tc::smem_desc(sbase + T5_HID + s * 2048, 16384, 1024, 2),
-                             tc::smem_desc(dx + s * 2048, 16384, 1024, 2), id_w16, s > 0 ? 1u : first);
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                tc::mma_bf16(tmem + (pair == 0 ? TM_EXTA : TM_EXTB), tc::smem_desc(sbase + T5_DPRE + s * 2048, 16384, 1024, 2),
-                             tc::smem_desc(sbase + T5_DX + DX_EXT * 2 + s * 2048, 16384, 1024, 2), id_w16, s > 0 ? 1u : first);
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                tc::mma_bf16(tmem + (pair == 0 ? TM_DFA : TM_DFB), tc::smem_desc(sbase + T5_DPRE + s * 2048, 16384, 1024, 2),
-                             tc::smem_desc(sbase + T5_M1 + s * 2048, 16384, 1024, 2), id_w64, s > 0 ? 1u : first);
-            // dm1 += dpre_h F_h: A K-major, B = the folded weight tile read MN-major (K = hidden units, 4 steps of 16 rows)
+            // dm1 += dpre_h F_h first (the compute threads wait for it): A K-major, B = the folded weight tile read MN-major
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint64_t da = tc::smem_desc_sw128(sbase + T5_DPRE + h * 16384);
@@ -344,18 +335,100 @@ __device__ __forceinline__ void t5_issue_pass(uint32_t sbase, uint32_t tmem, uin
                     tc::mma_bf16(tmem + TM_DM1, da + 2 * s, tc::smem_desc(sbase + T5_F + (2 * pair + h) * 8192 + s * 2048, 8192, 1024, 2), id_dm1,
                                  (pair | h | s) > 0);
             }
+            // weight-gradient sums over the pairs of the pass (K = 128 pairs = 8 steps of 16 rows), A = the two heads' tiles stacked in M
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                tc::mma_bf16(tmem + (pair == 0 ? TM_DFA : TM_DFB), tc::smem_desc(sbase + T5_DPRE + s * 2048, 16384, 1024, 2),
+                             tc::smem_desc(sbase + T5_M1 + s * 2048, 16384, 1024, 2), id_w64, s > 0 ? 1u : keep);
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                tc::mma_bf16(tmem + TM_DW3, tc::smem_desc(sbase + T5_HID + s * 2048, 16384, 1024, 2),
+                             tc::smem_desc(sbase + T5_DX + DX_OUT * 2 + s * 2048, 16384, 1024, 2), id_w16, (s > 0 || pair > 0) ? 1u : keep);
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                tc::mma_bf16(tmem + TM_EXT, tc::smem_desc(sbase + T5_DPRE + s * 2048, 16384, 1024, 2),
+                             tc::smem_desc(sbase + T5_DX + (pair == 0 ? DX_EXT_A : DX_EXT_B) * 2 + s * 2048, 16384, 1024, 2), id_w16,
+                             (s > 0 || pair > 0) ? 1u : keep);
+            if (pair == 0) {
+                // per-row sums of the torsion head's hidden-layer gradient (rows 64.. of the stacked tiles) against the row selector
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    tc::mma_bf16(tmem + TM_SEL, tc::smem_desc(sbase + T5_DPRE + s * 2048, 16384, 1024, 2),
+                                 tc::smem_desc(sbase + T5_DX + DX_SEL * 2 + s * 2048, 16384, 1024, 2), id_w16, s > 0 ? 1u : keep_c);
+            }
             tc::mma_commit(done + 1 + pair);
         }
         __syncwarp();
     }
+    // batch 3: per-row sums of m1 (rows 0..63: layer 1's message-sum path) and of dm1 (rows 64..127: dL / dA_i) against the row selector
+    tc::mbar_wait_suspend(rdy + 3, par);
+    tc::fence_after_thread_sync();
+    if (tc::elect_one()) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            tc::mma_bf16(tmem + TM_ROW, tc::smem_desc(sbase + T5_M1 + s * 2048, T5_DM1H - T5_M1, 1024, 2),
+                         tc::smem_desc(sbase + T5_DX + DX_SEL * 2 + s * 2048, 16384, 1024, 2), id_w16, s > 0 ? 1u : keep_c);
+        tc::mma_commit(done + 3);
+    }
+    __syncwarp();
+}
+
+#ifdef PMHC_T5_STAMPS
+__device__ long long t5_dbg[2][16];
+#define T5_PSTAMP(k) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 128)) { long long now_ = clock64(); t5_dbg[threadIdx.x >> 7][k] += now_ - pst_; pst_ = now_; } } while (0)
+#else
+#define T5_PSTAMP(k) do { } while (0)
+#endif
+
+// 16 accumulator columns of the thread's TMEM lane, split in issue and wait so that the next chunk's load runs under the current
+// chunk's arithmetic; the wait takes the registers as in/out operands: no use of them can be scheduled above it
+__device__ __forceinline__ void t5_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void t5_ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+// chunk ch of a head's 64 accumulator columns -> hv, with chunk ch + 1 requested behind it (nx carries the request between calls)
+__device__ __forceinline__ void t5_next16(uint32_t tbase, int ch, uint32_t (&nx)[16], float (&hv)[16]) {
+    t5_ld16_wait(nx);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) hv[e] = __uint_as_float(nx[e]);
+    if (ch < 3) t5_ld16_issue(tbase + 16 * (ch + 1), nx);
+}
+// 16 floats (scaled) -> two 16-byte chunks (2 ch, 2 ch + 1) of row p of a SW128 fp16 tile
+__device__ __forceinline__ void t5_store16(uint8_t* tile, int p, int ch, const float (&v)[16], float scale) {
+    uint8_t* row = tile + (p >> 3) * 1024 + (p & 7) * 128;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        uint4 u;
+        u.x = pack_h2_sat(v[8 * q + 0] * scale, v[8 * q + 1] * scale);
+        u.y = pack_h2_sat(v[8 * q + 2] * scale, v[8 * q + 3] * scale);
+        u.z = pack_h2_sat(v[8 * q + 4] * scale, v[8 * q + 5] * scale);
+        u.w = pack_h2_sat(v[8 * q + 6] * scale, v[8 * q + 7] * scale);
+        *reinterpret_cast<uint4*>(row + (((2 * ch + q) ^ (p & 7)) << 4)) = u;
+    }
 }
 
 // ---- compute threads: one attention-carrying pass of up to 128 pairs ----
+// Two threads per pair, one head each: threads 0..127 rotation then translation, threads 128..255 torsion then attention.  A head is
+// walked in four chunks of 16 hidden units (runtime loops: the pass code stays inside the instruction cache): chunk loop 1 forms the
+// hidden units and the second layer, chunk loop 2 the hidden-layer gradient; only a 64-bit relu mask is kept between them.
 template <int LAYER>
 __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map& T, const BwdArgs& g, const PairRef pr, int b,
-                                              const float* __restrict__ ajt, float* __restrict__ dajt, const int* I, int L, int Wr,
-                                              int pass_base, int npass, int n_pocket_cols, int pocket_e0, uint32_t np, uint32_t tmem,
-                                              float gs, float inv_gs) {
+                                              const float* __restrict__ ajt, float* __restrict__ dajt, const int* I, int L, int rl,
+                                              int e0, int ncols, uint32_t np, uint32_t tmem, float gs, float inv_gs) {
+    // Pairs of a pass are COLUMN-major: pair p = (neighbour column e0 + p / L, peptide row p % L), whole columns only.  A pocket
+    // column's L pairs are then adjacent (its dL / dA_j is complete inside the pass: a plain store), and a row's pairs are L apart
+    // (per-row sums go through the one-hot row selector on the tensor core; shared-memory atomics see at most 4 lanes per row).
     constexpr bool IN_GRADS = (LAYER == 1);
     const BwdMap& M = T.b;
     const LayerArgs& a = g.a;
@@ -371,27 +444,44 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
     const uint32_t par = np & 1u;
     uint64_t* bars = reinterpret_cast<uint64_t*>(S + T.Bars);
     uint64_t* rdy = bars;
-    uint64_t* done = bars + 3;
+    uint64_t* done = bars + 4;
     float* sDl = S + T.Dl;
     float* sB3 = S + T.B3;
     int* sPl = reinterpret_cast<int*>(S + M.Pl);
     const float* cvec = S + T.Cvec;
-
-    // ---- m1 (my half of its features) -> fp16 tile; geometry; the extra-input block ----
+#ifdef PMHC_T5_STAMPS
+    long long pst_ = clock64();
+#endif
+    // ---- m1 (my half of its features) -> fp16 tile; geometry; the extra-input blocks and the row selector ----
     uint32_t m1mask = 0u;
     {
-        float m1h[32];
-        compute_m1<LAYER, 32>(m1h, 32 * half, S, M, a.params, ajt, Kpad, i, j);
+        constexpr int H = layer_H(LAYER);
+        constexpr int ld1 = 2 * H + kEdge;
+        const int k0 = 32 * half;
+        const float* ajc = ajt + (j >= 0 ? j : 0) + (size_t)k0 * Kpad;
+        float aj[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) aj[k] = __ldcg(ajc + k * Kpad);       // 32 L2 loads in flight
+        const float* ai = S + M.f.Ai + i * kLdN + k0;
+        if (pep) {
+            const float* we = a.params + param_offset(LAYER, MSG0_W) + 2 * H + (kN - 1 + i - j) + (size_t)k0 * ld1;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) aj[k] += __ldg(we + k * ld1);
+        }
+        if (np > 0) tc::mbar_wait_suspend(done + 3, (np - 1) & 1u);   // the previous pass's row sums have read the m1 tile and the selector
         uint8_t* row = sb + T5_M1 + (p >> 3) * 1024 + (p & 7) * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+            float m[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                m[e] = fmaxf(ai[8 * q + e] + aj[8 * q + e], 0.0f);
+                m1mask |= (m[e] > 0.0f ? 1u : 0u) << (8 * q + e);
+            }
             uint4 u;
-            u.x = pack_h2_sat(m1h[8 * q + 0], m1h[8 * q + 1]); u.y = pack_h2_sat(m1h[8 * q + 2], m1h[8 * q + 3]);
-            u.z = pack_h2_sat(m1h[8 * q + 4], m1h[8 * q + 5]); u.w = pack_h2_sat(m1h[8 * q + 6], m1h[8 * q + 7]);
+            u.x = pack_h2_sat(m[0], m[1]); u.y = pack_h2_sat(m[2], m[3]); u.z = pack_h2_sat(m[4], m[5]); u.w = pack_h2_sat(m[6], m[7]);
             *reinterpret_cast<uint4*>(row + (((4 * half + q) ^ (p & 7)) << 4)) = u;
         }
-#pragma unroll
-        for (int k = 0; k < 32; ++k) m1mask |= (m1h[k] > 0.0f ? 1u : 0u) << k;
     }
     const float* rg = S + M.RowG + i * 16;
     const float lse = rg[15], c_i = rg[14];
@@ -409,38 +499,61 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
     const float dotq = qdot(qi, qj);
     const float qd = dotq * dotq;
     if (half == 0) {
-        t5_store_chunk(sb + T5_DX, p, 4, lq.w, lq.x, lq.y, lq.z, -d2, qd, 1.0f, 0.0f);
-        t5_store_chunk(sb + T5_DX, p, 5, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
+        // extras block of pair A: lq (0..3), -d2, qdot2, 1 at its columns 0..6; pair B reads a window shifted by 8 columns, so the same
+        // three inputs appear again at columns 16..18 (its columns 8..10) and its columns 0..7 are zero
+        t5_store_chunk(sb + T5_DX, p, DX_EXT_A / 8, lq.w, lq.x, lq.y, lq.z, -d2, qd, 1.0f, 0.0f);
+        t5_store_chunk(sb + T5_DX, p, DX_EXT_A / 8 + 1, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
+        t5_store_chunk(sb + T5_DX, p, DX_EXT_A / 8 + 2, -d2, qd, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
+    } else {
+        // one-hot selector of the pair's peptide row (list position): the per-row sums of a pass are one small MMA
+        const float o = act ? 1.0f : 0.0f;
+        t5_store_chunk(sb + T5_DX, p, DX_SEL / 8, rl == 0 ? o : 0.0f, rl == 1 ? o : 0.0f, rl == 2 ? o : 0.0f, rl == 3 ? o : 0.0f, rl == 4 ? o : 0.0f,
+                       rl == 5 ? o : 0.0f, rl == 6 ? o : 0.0f, rl == 7 ? o : 0.0f);
+        t5_store_chunk(sb + T5_DX, p, DX_SEL / 8 + 1, rl == 8 ? o : 0.0f, rl == 9 ? o : 0.0f, rl == 10 ? o : 0.0f, rl == 11 ? o : 0.0f,
+                       rl == 12 ? o : 0.0f, rl == 13 ? o : 0.0f, rl == 14 ? o : 0.0f, rl == 15 ? o : 0.0f);
     }
     if (tid == 0) sPl[0] = 0;      // (every reader of the previous pass's list is behind that pass's last barrier)
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
     tc::mbar_arrive(rdy + 0);
+    T5_PSTAMP(0);
 
     float gi[7] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // layer 2: this thread's share of dL / d (q_i, x_i)
     float dLdw_own = 0.0f;                                       // torsion thread: its share of dL / dw
-    float hid[kHid];
+    float gd_keep = 0.0f, gq_keep = 0.0f;                        // attention thread: dL / d(-d2), dL / d(qdot2)
+    float hv[16];
+    uint32_t nx[16];
 
     tc::mbar_wait_suspend(done + 0, par);
     tc::fence_after_thread_sync();
+    T5_PSTAMP(1);
 
     // ======================= head pair A: rotation (half 0) | torsion (half 1) =======================
     if (half == 0) {
-        t5_load64(tlane + TM_HID + 0, hid);
         float pre[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) pre[c] = S[M.f.Scal + SC_ROT2B + c];
+        unsigned long long on = 0ull;
+        t5_ld16_issue(tlane + TM_HID, nx);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            t5_next16(tlane + TM_HID, ch, nx, hv);
+            uint32_t bits = 0u;
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            const float4 wq = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n);
-            const float s = hid[n] + cvec[F_ROT * kHid + n] + wq.x * lq.w + wq.y * lq.x + wq.z * lq.y + wq.w * lq.z;
-            const float h = fmaxf(s, 0.0f);
-            hid[n] = h;
-            const float4 w2 = *reinterpret_cast<const float4*>(S + M.f.PkRot2 + 4 * n);
-            pre[0] = fmaf(w2.x, h, pre[0]); pre[1] = fmaf(w2.y, h, pre[1]);
-            pre[2] = fmaf(w2.z, h, pre[2]); pre[3] = fmaf(w2.w, h, pre[3]);
+            for (int e = 0; e < 16; ++e) {
+                const int n = 16 * ch + e;
+                const float4 wq = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n);
+                const float s = hv[e] + cvec[F_ROT * kHid + n] + wq.x * lq.w + wq.y * lq.x + wq.z * lq.y + wq.w * lq.z;
+                const float h = fmaxf(s, 0.0f);
+                hv[e] = h;
+                bits |= (h > 0.0f ? 1u : 0u) << e;
+                const float4 w2 = *reinterpret_cast<const float4*>(S + M.f.PkRot2 + 4 * n);
+                pre[0] = fmaf(w2.x, h, pre[0]); pre[1] = fmaf(w2.y, h, pre[1]);
+                pre[2] = fmaf(w2.z, h, pre[2]); pre[3] = fmaf(w2.w, h, pre[3]);
+            }
+            on |= (unsigned long long)bits << (16 * ch);
+            t5_store16(sb + T5_HID, p, ch, hv, 1.0f);
         }
-        t5_store_row64(sb + T5_HID, p, hid, 1.0f);
         const Quat dl{sigmoidf(pre[0]), sigmoidf(pre[1]), sigmoidf(pre[2]), sigmoidf(pre[3])};
         const Quat u = qmul(dl, qinvj);
         const Quat dg = qmul(qj, u);
@@ -451,21 +564,26 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
         const Quat ddl = qmul_grad_a(du, qinvj);      // u = dl * qinvj
         const float dp2[4] = {ddl.w * dl.w * (1.0f - dl.w), ddl.x * dl.x * (1.0f - dl.x), ddl.y * dl.y * (1.0f - dl.y),
                               ddl.z * dl.z * (1.0f - dl.z)};
-        t5_store_chunk(sb + T5_DX, p, 0, dp2[0] * gs, dp2[1] * gs, dp2[2] * gs, dp2[3] * gs, 0.0f, 0.0f, 0.0f, 0.0f);
+        t5_store_chunk(sb + T5_DX, p, DX_OUT / 8, dp2[0] * gs, dp2[1] * gs, dp2[2] * gs, dp2[3] * gs, 0.0f, 0.0f, 0.0f, 0.0f);
         float dlq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            const uint32_t bits = (uint32_t)(on >> (16 * ch));
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            const float4 w2 = *reinterpret_cast<const float4*>(S + M.f.PkRot2 + 4 * n);
-            float dp = w2.x * dp2[0] + w2.y * dp2[1] + w2.z * dp2[2] + w2.w * dp2[3];
-            dp = hid[n] > 0.0f ? dp : 0.0f;
-            hid[n] = dp;
-            if (IN_GRADS) {
-                const float4 wq = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n);
-                dlq[0] = fmaf(wq.x, dp, dlq[0]); dlq[1] = fmaf(wq.y, dp, dlq[1]);
-                dlq[2] = fmaf(wq.z, dp, dlq[2]); dlq[3] = fmaf(wq.w, dp, dlq[3]);
+            for (int e = 0; e < 16; ++e) {
+                const int n = 16 * ch + e;
+                const float4 w2 = *reinterpret_cast<const float4*>(S + M.f.PkRot2 + 4 * n);
+                float dp = w2.x * dp2[0] + w2.y * dp2[1] + w2.z * dp2[2] + w2.w * dp2[3];
+                dp = ((bits >> e) & 1u) ? dp : 0.0f;
+                hv[e] = dp;
+                if (IN_GRADS) {
+                    const float4 wq = *reinterpret_cast<const float4*>(S + M.f.PkRotQ + 4 * n);
+                    dlq[0] = fmaf(wq.x, dp, dlq[0]); dlq[1] = fmaf(wq.y, dp, dlq[1]);
+                    dlq[2] = fmaf(wq.z, dp, dlq[2]); dlq[3] = fmaf(wq.w, dp, dlq[3]);
+                }
             }
+            t5_store16(sb + T5_DPRE, p, ch, hv, gs);
         }
-        t5_store_row64(sb + T5_DPRE, p, hid, gs);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float sum = warp_sum(dp2[c]);
@@ -484,37 +602,51 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
             if (pep) atomic_add_quat(S + M.dQ + j * 4, dqj);
         }
     } else {
-        t5_load64(tlane + TM_HID + 64, hid);
         float da[PMHC_NTORS];
 #pragma unroll
         for (int c = 0; c < PMHC_NTORS; ++c) da[c] = S[M.f.Scal + SC_TOR2B + c];
         const float* tt = S + M.f.Tt + i * kHid;
+        unsigned long long on = 0ull;
+        t5_ld16_issue(tlane + TM_HID + 64, nx);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            t5_next16(tlane + TM_HID + 64, ch, nx, hv);
+            uint32_t bits = 0u;
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            const float h = fmaxf(hid[n] + tt[n], 0.0f);
-            hid[n] = h;
-            const float4 w0 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n);
-            const float4 w1 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n + 4);
-            da[0] = fmaf(w0.x, h, da[0]); da[1] = fmaf(w0.y, h, da[1]); da[2] = fmaf(w0.z, h, da[2]);
-            da[3] = fmaf(w0.w, h, da[3]); da[4] = fmaf(w1.x, h, da[4]); da[5] = fmaf(w1.y, h, da[5]);
-            da[6] = fmaf(w1.z, h, da[6]);
+            for (int e = 0; e < 16; ++e) {
+                const int n = 16 * ch + e;
+                const float h = fmaxf(hv[e] + tt[n], 0.0f);
+                hv[e] = h;
+                bits |= (h > 0.0f ? 1u : 0u) << e;
+                const float4 w0 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n);
+                const float4 w1 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n + 4);
+                da[0] = fmaf(w0.x, h, da[0]); da[1] = fmaf(w0.y, h, da[1]); da[2] = fmaf(w0.z, h, da[2]);
+                da[3] = fmaf(w0.w, h, da[3]); da[4] = fmaf(w1.x, h, da[4]); da[5] = fmaf(w1.y, h, da[5]);
+                da[6] = fmaf(w1.z, h, da[6]);
+            }
+            on |= (unsigned long long)bits << (16 * ch);
+            t5_store16(sb + T5_HID + 16384, p, ch, hv, 1.0f);
         }
-        t5_store_row64(sb + T5_HID + 16384, p, hid, 1.0f);
         float dda[PMHC_NTORS];
 #pragma unroll
         for (int c = 0; c < PMHC_NTORS; ++c) {
             dLdw_own = fmaf(rg[4 + c], da[c], dLdw_own);
             dda[c] = w * rg[4 + c];
         }
-        t5_store_chunk(sb + T5_DX, p, 1, dda[0] * gs, dda[1] * gs, dda[2] * gs, dda[3] * gs, dda[4] * gs, dda[5] * gs, dda[6] * gs, 0.0f);
+        t5_store_chunk(sb + T5_DX, p, DX_OUT / 8 + 1, dda[0] * gs, dda[1] * gs, dda[2] * gs, dda[3] * gs, dda[4] * gs, dda[5] * gs, dda[6] * gs, 0.0f);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            const uint32_t bits = (uint32_t)(on >> (16 * ch));
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            const float4 w0 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n);
-            const float4 w1 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n + 4);
-            float dp = w0.x * dda[0] + w0.y * dda[1] + w0.z * dda[2] + w0.w * dda[3] + w1.x * dda[4] + w1.y * dda[5] + w1.z * dda[6];
-            hid[n] = hid[n] > 0.0f ? dp : 0.0f;
+            for (int e = 0; e < 16; ++e) {
+                const int n = 16 * ch + e;
+                const float4 w0 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n);
+                const float4 w1 = *reinterpret_cast<const float4*>(S + M.f.PkTor2 + 8 * n + 4);
+                const float dp = w0.x * dda[0] + w0.y * dda[1] + w0.z * dda[2] + w0.w * dda[3] + w1.x * dda[4] + w1.y * dda[5] + w1.z * dda[6];
+                hv[e] = ((bits >> e) & 1u) ? dp : 0.0f;
+            }
+            t5_store16(sb + T5_DPRE + 16384, p, ch, hv, gs);
         }
-        t5_store_row64(sb + T5_DPRE + 16384, p, hid, gs);
 #pragma unroll
         for (int c = 0; c < PMHC_NTORS; ++c) {
             const float sum = warp_sum(dda[c]);
@@ -523,30 +655,21 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
     }
     tc::fence_proxy_async_smem();
     tc::mbar_arrive(rdy + 1);
-    t5_bar_compute();
-    if (half == 0 && act && pep) sPl[4 + atomicAdd(sPl, 1)] = p | (j << 8) | ((kN - 1 + i - j) << 16);   // read behind a later barrier
-    // per-row sums of the torsion head's hidden-layer gradient (dL / dT_t[i]) from its tile (fp16, scaled)
-    for (int idx = tid; idx < L * kHid; idx += kT5Compute) {
-        const int rl = idx >> 6, n = idx & 63;
-        const int lo = max(rl * Wr, pass_base), hi = min((rl + 1) * Wr, pass_base + npass);
-        if (hi <= lo) continue;
-        float sum = 0.0f;
-        for (int gp = lo; gp < hi; ++gp) {
-            const int pp = gp - pass_base;
-            sum += __half2float(*reinterpret_cast<const __half*>(sb + T5_DPRE + 16384 + tc::sw128_offset(pp, n)));
-        }
-        S[M.dTt + I[IN_ROWS + rl] * kHid + n] += sum * inv_gs;
-    }
+    T5_PSTAMP(2);
 
     // ======================= head pair B: translation (half 0) | attention (half 1) =======================
+    // chunk loop 1 touches no tile (pair A's MMAs are still reading them); loop 2 recomputes the hidden units from the accumulators
     if (half == 0) {
-        t5_load64(tlane + TM_HID + 128, hid);
         float sc = S[M.f.Scal + SC_TRN2B];
+        t5_ld16_issue(tlane + TM_HID + 128, nx);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            t5_next16(tlane + TM_HID + 128, ch, nx, hv);
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            const float h = fmaxf(hid[n] + cvec[F_TRN * kHid + n], 0.0f);
-            hid[n] = h;
-            sc = fmaf(S[M.f.PkMisc + 4 * n + 1], h, sc);
+            for (int e = 0; e < 16; ++e) {
+                const int n = 16 * ch + e;
+                sc = fmaf(S[M.f.PkMisc + 4 * n + 1], fmaxf(hv[e] + cvec[F_TRN * kHid + n], 0.0f), sc);
+            }
         }
         const float dXr = rg[11] * rx + rg[12] * ry + rg[13] * rz;
         sDl[kBwdPairs + p] = sc * dXr;
@@ -560,88 +683,151 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
         }
         const float sum = warp_sum(ds);
         if (lane == 0) atomicAdd(sB3 + 11, sum);
-        t5_bar_compute();                       // dL/dw shares published; every read of pair A's torsion tile is done
-        tc::mbar_wait_suspend(done + 1, par);   // pair A's MMAs have read the hid / dpre tiles
-        t5_store_row64(sb + T5_HID, p, hid, 1.0f);
+        T5_PSTAMP(3);
+        t5_bar_compute();                       // dL/dw shares published
+        T5_PSTAMP(4);
+        if (act && pep) sPl[4 + atomicAdd(sPl, 1)] = p | (j << 8) | ((kN - 1 + i - j) << 16);   // read behind a later barrier
+        tc::mbar_wait_suspend(done + 1, par);   // pair A's MMAs have read the hid / dpre tiles and the second-layer block
+        T5_PSTAMP(5);
+        t5_ld16_issue(tlane + TM_HID + 128, nx);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            t5_next16(tlane + TM_HID + 128, ch, nx, hv);
+            float dp[16];
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) hid[n] = hid[n] > 0.0f ? S[M.f.PkMisc + 4 * n + 1] * ds : 0.0f;
-        t5_store_row64(sb + T5_DPRE, p, hid, gs);
-        t5_store_chunk(sb + T5_DX, p, 2, ds * gs, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
-    } else {
-        t5_load64(tlane + TM_HID + 192, hid);
-#pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
-            hid[n] = fmaxf((cvec[F_ATT * kHid + n] + hid[n]) + fmaf(pk.y, qd, pk.x * -d2), 0.0f);
+            for (int e = 0; e < 16; ++e) {
+                const int n = 16 * ch + e;
+                const float h = fmaxf(hv[e] + cvec[F_TRN * kHid + n], 0.0f);
+                hv[e] = h;
+                dp[e] = h > 0.0f ? S[M.f.PkMisc + 4 * n + 1] * ds : 0.0f;
+            }
+            t5_store16(sb + T5_HID, p, ch, hv, 1.0f);
+            t5_store16(sb + T5_DPRE, p, ch, dp, gs);
         }
+        // second-layer block of pair B: rotation's columns 0..3 zero, translation at 4 (attention writes 5 of the same chunk: see below)
+    } else {
+        unsigned long long on = 0ull;
+        t5_ld16_issue(tlane + TM_HID + 192, nx);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            t5_next16(tlane + TM_HID + 192, ch, nx, hv);
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int n = 16 * ch + e;
+                const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
+                const float h = fmaxf((cvec[F_ATT * kHid + n] + hv[e]) + fmaf(pk.y, qd, pk.x * -d2), 0.0f);
+                bits |= (h > 0.0f ? 1u : 0u) << e;
+            }
+            on |= (unsigned long long)bits << (16 * ch);
+        }
+        T5_PSTAMP(3);
         t5_bar_compute();
+        T5_PSTAMP(4);
         const float dLdw = sDl[p] + dLdw_own + sDl[kBwdPairs + p];
         // softmax backward with the saved row statistics; a fully saturated row has dlogit = 0 exactly (see pair_pass)
         const float dlogit = (w == 1.0f) ? 0.0f : w * (dLdw - c_i);
         tc::mbar_wait_suspend(done + 1, par);
-        t5_store_row64(sb + T5_HID + 16384, p, hid, 1.0f);
+        T5_PSTAMP(5);
         float gd = 0.0f, gq = 0.0f;
+        t5_ld16_issue(tlane + TM_HID + 192, nx);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            t5_next16(tlane + TM_HID + 192, ch, nx, hv);
+            const uint32_t bits = (uint32_t)(on >> (16 * ch));
+            float dp[16];
 #pragma unroll
-        for (int n = 0; n < kHid; ++n) {
-            const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
-            const float dp = hid[n] > 0.0f ? pk.w * dlogit : 0.0f;
-            hid[n] = dp;
-            gd = fmaf(pk.x, dp, gd);
-            gq = fmaf(pk.y, dp, gq);
-        }
-        t5_store_row64(sb + T5_DPRE + 16384, p, hid, gs);
-        t5_store_chunk(sb + T5_DX, p, 3, dlogit * gs, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
-        if (IN_GRADS && act) {
-            const float f = -gd * 2.0f;                 // d(-d2) = gd
-            gi[4] += f * rx; gi[5] += f * ry; gi[6] += f * rz;
-            const float fq = gq * 2.0f * dotq;
-            gi[0] += fq * qj.w; gi[1] += fq * qj.x; gi[2] += fq * qj.y; gi[3] += fq * qj.z;
-            if (pep) {
-                atomicAdd(S + M.dX + j * 3 + 0, -f * rx); atomicAdd(S + M.dX + j * 3 + 1, -f * ry); atomicAdd(S + M.dX + j * 3 + 2, -f * rz);
-                atomic_add_quat(S + M.dQ + j * 4, qscale(qi, fq));
+            for (int e = 0; e < 16; ++e) {
+                const int n = 16 * ch + e;
+                const float4 pk = *reinterpret_cast<const float4*>(S + M.f.PkAtt + 4 * n);
+                hv[e] = fmaxf((cvec[F_ATT * kHid + n] + hv[e]) + fmaf(pk.y, qd, pk.x * -d2), 0.0f);
+                dp[e] = ((bits >> e) & 1u) ? pk.w * dlogit : 0.0f;
+                gd = fmaf(pk.x, dp[e], gd);
+                gq = fmaf(pk.y, dp[e], gq);
             }
+            t5_store16(sb + T5_HID + 16384, p, ch, hv, 1.0f);
+            t5_store16(sb + T5_DPRE + 16384, p, ch, dp, gs);
         }
+        // second-layer block of pair B: the translation thread's ds travels through shared memory so that ONE thread writes the chunk
+        {
+            const float dXr = rg[11] * rx + rg[12] * ry + rg[13] * rz;
+            t5_store_chunk(sb + T5_DX, p, DX_OUT / 8, 0.0f, 0.0f, 0.0f, 0.0f, w * dXr * gs, dlogit * gs, 0.0f, 0.0f);
+            t5_store_chunk(sb + T5_DX, p, DX_OUT / 8 + 1, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        gd_keep = gd; gq_keep = gq;
         const float sum = warp_sum(dlogit);
         if (lane == 0) atomicAdd(sB3 + 12, sum);
     }
     tc::fence_proxy_async_smem();
     tc::mbar_arrive(rdy + 2);
+    T5_PSTAMP(6);
+    if (IN_GRADS && act && half == 1) {
+        // attention head's input gradients (under pair B's MMAs)
+        const float f = -gd_keep * 2.0f;                 // d(-d2) = gd
+        gi[4] += f * rx; gi[5] += f * ry; gi[6] += f * rz;
+        const float fq = gq_keep * 2.0f * dotq;
+        gi[0] += fq * qj.w; gi[1] += fq * qj.x; gi[2] += fq * qj.y; gi[3] += fq * qj.z;
+        if (pep) {
+            atomicAdd(S + M.dX + j * 3 + 0, -f * rx); atomicAdd(S + M.dX + j * 3 + 1, -f * ry); atomicAdd(S + M.dX + j * 3 + 2, -f * rz);
+            atomic_add_quat(S + M.dQ + j * 4, qscale(qi, fq));
+        }
+    }
+    if (IN_GRADS) {
+        // this thread's share of dL / d (q_i, x_i): a row's pairs are L lanes apart — for L >= 8 the (at most four) lanes of a warp
+        // that share a row are folded into the first of them before the shared-memory atomics
+        const bool fold = L >= 8;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            float x = act ? gi[c] : 0.0f;
+            if (fold) {
+                const float y = __shfl_down_sync(0xffffffffu, x, L);
+                if (lane + L < 32) x += y;
+                const float z = __shfl_down_sync(0xffffffffu, x, (2 * L) & 31);
+                if (lane + 2 * L < 32) x += z;
+            }
+            gi[c] = x;
+        }
+        if (!fold || lane < L) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) atomicAdd(S + M.dQ + i * 4 + c, gi[c]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) atomicAdd(S + M.dX + i * 3 + c, gi[4 + c]);
+        }
+    }
 
     // ======================= dm1 = (sum_h dpre_h F_h [+ W2^T dMsum_i]) .* relu'(m1) -> reduction tile =======================
     tc::mbar_wait_suspend(done + 2, par);
     tc::fence_after_thread_sync();
+    T5_PSTAMP(7);
     float* red = reinterpret_cast<float*>(sb + T5_RED);
     {
         uint32_t r[32];
         tc::tmem_ld32_nowait(tlane + TM_DM1 + 32 * half, r);
         tc::tmem_wait_ld();
         const float* gv = S + T.G + i * kHid + 32 * half;
+        float x[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-            float x = __uint_as_float(r[k]) * inv_gs;
-            if (LAYER == 0) x += gv[k];
-            red[(32 * half + k) * kLdc + p] = (act && ((m1mask >> k) & 1u)) ? x : 0.0f;
+            float t = __uint_as_float(r[k]) * inv_gs;
+            if (LAYER == 0) t += gv[k];
+            x[k] = (act && ((m1mask >> k) & 1u)) ? t : 0.0f;
+            red[(32 * half + k) * kLdc + p] = x[k];
         }
-        if (IN_GRADS) {
+        uint8_t* row = sb + T5_DM1H + (p >> 3) * 1024 + (p & 7) * 128;
 #pragma unroll
-            for (int c = 0; c < 7; ++c) red[(64 + 7 * half + c) * kLdc + p] = act ? gi[c] : 0.0f;
+        for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_h2_sat(x[8 * q + 0] * gs, x[8 * q + 1] * gs); u.y = pack_h2_sat(x[8 * q + 2] * gs, x[8 * q + 3] * gs);
+            u.z = pack_h2_sat(x[8 * q + 4] * gs, x[8 * q + 5] * gs); u.w = pack_h2_sat(x[8 * q + 6] * gs, x[8 * q + 7] * gs);
+            *reinterpret_cast<uint4*>(row + (((4 * half + q) ^ (p & 7)) << 4)) = u;
         }
     }
+    tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
+    tc::mbar_arrive(rdy + 3);
+    T5_PSTAMP(8);
     t5_bar_compute();
-    if (IN_GRADS) {
-        for (int idx = tid; idx < L * 7; idx += kT5Compute) {
-            const int rl = idx / 7, c = idx - rl * 7;
-            const int lo = max(rl * Wr, pass_base), hi = min((rl + 1) * Wr, pass_base + npass);
-            float sum = 0.0f;
-            for (int gp = lo; gp < hi; ++gp) sum += red[(64 + c) * kLdc + (gp - pass_base)] + red[(71 + c) * kLdc + (gp - pass_base)];
-            const int ri = I[IN_ROWS + rl];
-            if (hi > lo) {
-                if (c < 4) S[M.dQ + ri * 4 + c] += sum;
-                else S[M.dX + ri * 3 + (c - 4)] += sum;
-            }
-        }
-    }
+    T5_PSTAMP(9);
     {   // peptide neighbours: dA_j[j] and dW_e[rel] get the column
         const int n_pl = sPl[0];
         for (int idx = tid; idx < n_pl * kHid; idx += kT5Compute) {
@@ -651,46 +837,21 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
             atomicAdd(S + M.dWe + (e >> 16) * kLdN + k, x);
         }
     }
-    for (int idx = tid; idx < L * kHid; idx += kT5Compute) {
-        const int rl = idx >> 6, n = idx & 63;
-        const int lo = max(rl * Wr, pass_base), hi = min((rl + 1) * Wr, pass_base + npass);
-        if (hi <= lo) continue;
-        float sum = 0.0f, s1 = 0.0f;
-        for (int gp = lo; gp < hi; ++gp) {
-            sum += red[n * kLdc + (gp - pass_base)];
-            if (LAYER == 0) s1 += __half2float(*reinterpret_cast<const __half*>(sb + T5_M1 + tc::sw128_offset(gp - pass_base, n)));
-        }
-        const int ri = I[IN_ROWS + rl];
-        S[M.dAi + ri * kLdN + n] += sum;
-        if (LAYER == 0) S[T.S1 + ri * kHid + n] += s1;
-    }
-    {   // dA_j^T[k][j] += sum over rows of dm1 for the valid pocket columns of this pass
-        const int rl_lo = pass_base / Wr, rl_hi = (pass_base + npass - 1) / Wr;
-        const int n_items = n_pocket_cols * kHid;
-        for (int idx0 = tid; idx0 < n_items; idx0 += 4 * kT5Compute) {   // four L2 read-modify-writes in flight per thread
-            float old[4];
-            int addr[4], kk[4], ee[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = idx0 + u * kT5Compute;
-                kk[u] = idx / n_pocket_cols;
-                ee[u] = idx - kk[u] * n_pocket_cols;
-                addr[u] = idx < n_items ? kk[u] * Kpad + I[IN_POCKET + ee[u]] : -1;
-                old[u] = addr[u] >= 0 ? __ldcg(dajt + addr[u]) : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (addr[u] < 0) continue;
-                float sum = 0.0f;
-                for (int rl = rl_lo; rl <= rl_hi; ++rl) {
-                    const int col = rl * Wr + pocket_e0 + ee[u] - pass_base;
-                    if (col >= 0 && col < npass) sum += red[kk[u] * kLdc + col];
-                }
-                dajt[addr[u]] = old[u] + sum;
-            }
+    T5_PSTAMP(10);
+    {   // pocket columns: dA_j^T[k][j] = the sum over the column's L adjacent pairs — complete inside this pass, a plain store
+        const int c_lo = max(e0, L - 1) - e0;          // first pocket column of the pass (local index)
+        const int npc = ncols - c_lo;
+        for (int idx = tid; idx < npc * kHid; idx += kT5Compute) {
+            const int k = idx / npc, c = c_lo + (idx - k * npc);
+            const float* src = red + k * kLdc + c * L;
+            float sum = 0.0f;
+            for (int r = 0; r < L; ++r) sum += src[r];
+            dajt[k * Kpad + I[IN_POCKET + (e0 + c - (L - 1))]] = sum;
         }
     }
+    T5_PSTAMP(11);
     t5_bar_compute();
+    T5_PSTAMP(12);
 }
 
 // ---- compute threads, layer 1: one pass of message-only pairs (model.py:151: the unmasked message sum) — no contraction at all:
@@ -768,7 +929,7 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     float* dajt = g.dajt_ws + (size_t)blockIdx.x * kHid * Kpad;
     float* direct = g.partial + (size_t)blockIdx.x * g.partial_stride + kTileFloats;
     uint64_t* bars = reinterpret_cast<uint64_t*>(S + T.Bars);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(S + T.Bars + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(S + T.Bars + 24);
     const uint32_t sbase = tc::smem_u32(sb);
 
     for (int idx = tid; idx < layer_numel; idx += kT5Threads) direct[idx] = 0.0f;
@@ -777,8 +938,8 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     if (tid == 0) reinterpret_cast<int*>(S + M.Pl)[0] = 0;
     if (mma_warp) tc::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-        for (int q = 0; q < 3; ++q) { tc::mbar_init(bars + q, kT5Compute); tc::mbar_init(bars + 3 + q, 1); }
-        tc::mbar_init(bars + 6, 1);
+        for (int q = 0; q < 4; ++q) { tc::mbar_init(bars + q, kT5Compute); tc::mbar_init(bars + 4 + q, 1); }
+        tc::mbar_init(bars + 8, 1);
         tc::mbar_fence_init();
     }
     tc::fence_before_thread_sync();
@@ -788,9 +949,17 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     const float gs = __ldg(x.scale), inv_gs = __ldg(x.scale + 1);
     uint32_t np = 0;          // attention-carrying passes of this CTA so far (mbarrier phase, accumulate flag)
     bool image_loaded = false;
+#ifdef PMHC_T5_STAMPS
+    long long st_acc[6] = {0, 0, 0, 0, 0, 0}, st_t = clock64();
+#define T5_STAMP(k) do { long long now_ = clock64(); st_acc[k] += now_ - st_t; st_t = now_; } while (0)
+#else
+#define T5_STAMP(k) do { } while (0)
+#endif
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        T5_STAMP(5);
         const ComplexInfo ci = setup_complex<LAYER>(S, M.f, a, b, ajt);
+        T5_STAMP(0);
         const int L = ci.L;
         const int W = (L - 1) + ci.nv;
         for (int idx = tid; idx < M.grads_end - T.G; idx += kT5Threads) S[T.G + idx] = 0.0f;
@@ -803,22 +972,26 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
         if (LAYER == 0) {
             // G[i][c] = sum_k W2[k][c] dMsum[i][k]: the message-sum gradient behind message_mlp.2, added to every pair of row i
             const float* W2 = a.params + param_offset(LAYER, MSG2_W);
+            float* w2s = S + M.BufA;                   // staged (the prologue's buffers there are done)
+#pragma unroll 8
+            for (int idx = tid; idx < kHid * kHid; idx += kT5Threads) w2s[idx] = __ldg(W2 + idx);
+            __syncthreads();
             for (int idx = tid; idx < kN * kHid; idx += kT5Threads) {
                 const int i = idx >> 6, c = idx & 63;
                 float acc = 0.0f;
-#pragma unroll 8
-                for (int k = 0; k < kHid; ++k) acc = fmaf(__ldg(W2 + k * kHid + c), S[M.dMsum + i * kHid + k], acc);
+#pragma unroll 16
+                for (int k = 0; k < kHid; ++k) acc = fmaf(w2s[k * kHid + c], S[M.dMsum + i * kHid + k], acc);
                 S[T.G + idx] = acc;
             }
         }
         if (!image_loaded) {
             // the folded weights (+ c_h right behind the tiles... c_h is copied separately: it lives behind the pass tiles)
             if (tid == 0) {
-                tc::mbar_expect_tx(bars + 6, kFoldImageBytes);
-                tc::bulk_g2s(sb + T5_F, x.wimg, 4 * 8192, bars + 6);
-                tc::bulk_g2s(S + T.Cvec, x.wimg + 4 * 8192, 4 * kHid * 4, bars + 6);
+                tc::mbar_expect_tx(bars + 8, kFoldImageBytes);
+                tc::bulk_g2s(sb + T5_F, x.wimg, 4 * 8192, bars + 8);
+                tc::bulk_g2s(S + T.Cvec, x.wimg + 4 * 8192, 4 * kHid * 4, bars + 8);
             }
-            tc::mbar_wait_suspend(bars + 6, 0);
+            tc::mbar_wait_suspend(bars + 8, 0);
             image_loaded = true;
         }
         __syncthreads();
@@ -827,20 +1000,27 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
         __syncthreads();
 
         // ---------------- attention-carrying pairs ----------------
-        const int total = L > 0 ? L * W : 0;
-        const int npasses = (total + kBwdPairs - 1) / kBwdPairs;
+        T5_STAMP(1);
+        const int cpp = L > 0 ? kBwdPairs / L : 1;                  // whole neighbour columns per pass
+        const int npasses = L > 0 ? (W + cpp - 1) / cpp : 0;
         if (mma_warp) {
-            for (int q = 0; q < npasses; ++q) t5_issue_pass(sbase, tmem, bars, np + q);
+            for (int q = 0; q < npasses; ++q) t5_issue_pass(sbase, tmem, bars, np + q, q);
         } else {
             const int pcol = tid & (kBwdPairs - 1);
+            const int pc = L > 0 ? pcol / L : 0, prl = L > 0 ? pcol - pc * L : 0;   // this thread's column (local) and peptide row
             for (int q = 0; q < npasses; ++q) {
-                const int pass_base = q * kBwdPairs;
-                const int npass = min(kBwdPairs, total - pass_base);
-                const bool act = pcol < npass;
-                const PairRef pr = decode_full_pair(I, act ? pass_base + pcol : pass_base, W, L, 0, act);
-                t5_heads_pass<LAYER>(sb, S, T, g, pr, b, ajt, dajt, I, L, W, pass_base, npass, ci.nv, L - 1, np + q, tmem, gs, inv_gs);
+                const int e0 = q * cpp;
+                const int ncols = min(cpp, W - e0);
+                PairRef pr;
+                pr.active = pc < ncols;
+                const int e = pr.active ? e0 + pc : e0, rl = pr.active ? prl : 0;
+                pr.i = I[IN_ROWS + rl];
+                pr.j = e < L - 1 ? I[IN_ROWS + (e < rl ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
+                t5_heads_pass<LAYER>(sb, S, T, g, pr, b, ajt, dajt, I, L, rl, e0, ncols, np + q, tmem, gs, inv_gs);
             }
+            if (npasses > 0) tc::mbar_wait_suspend(bars + 4 + 3, (np + npasses - 1) & 1u);   // the last pass's per-row sums
             // ---------------- layer 1: message-only pairs (self, masked peptide / pocket slots) ----------------
+            T5_STAMP(2);
             if (LAYER == 0 && L > 0) {
                 const int npx = kN - L;
                 const int W2 = 1 + npx + ci.nx + (ci.c0 > 0 ? 1 : 0);
@@ -862,20 +1042,43 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
                 }
             }
         }
+        if (npasses > 0 && tid >= 64 && tid < 128) {
+            // dL / dT_t[i][n] = the torsion head's hidden-layer gradient summed over the pairs of row i (TM_SEL rows 64..127)
+            float sel[16], row[16];
+            tc::fence_after_thread_sync();
+            tc::tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + TM_SEL, sel);
+            tc::tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + TM_ROW, row);
+#pragma unroll
+            for (int rl = 0; rl < kN; ++rl)
+                if (rl < L) {
+                    S[M.dTt + I[IN_ROWS + rl] * kHid + (tid - 64)] = sel[rl] * inv_gs;
+                    S[M.dAi + I[IN_ROWS + rl] * kLdN + (tid - 64)] += row[rl] * inv_gs;   // (+=: layer 1's message-only passes add to it)
+                }
+            tc::fence_before_thread_sync();
+        }
+        if (LAYER == 0 && npasses > 0 && tid < 64) {
+            float row[16];
+            tc::fence_after_thread_sync();
+            tc::tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + TM_ROW, row);
+#pragma unroll
+            for (int rl = 0; rl < kN; ++rl)
+                if (rl < L) S[T.S1 + I[IN_ROWS + rl] * kHid + tid] += row[rl];
+            tc::fence_before_thread_sync();
+        }
         np += npasses;
         __syncthreads();
+        T5_STAMP(3);
 
         if (LAYER == 0) {
             // message_mlp.2 through the message sum: dW2[k][c] += sum_i dMsum[i][k] S1[i][c], db2[k] += (16 + P) sum_i dMsum[i][k]
             float* dW2 = direct + (param_offset(LAYER, MSG2_W) - base);
-            for (int idx = tid; idx < kHid * kHid; idx += kT5Threads) {
+            rmw_batched<8>(dW2, kHid * kHid, kT5Threads, [&](int idx) {
                 const int k = idx >> 6, c = idx & 63;
-                const float old = __ldcg(dW2 + idx);
                 float acc = 0.0f;
 #pragma unroll
                 for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dMsum + i * kHid + k], S[T.S1 + i * kHid + c], acc);
-                dW2[idx] = old + acc;
-            }
+                return acc;
+            });
             for (int k = tid; k < kHid; k += kT5Threads) {
                 float acc = 0.0f;
                 for (int r = 0; r < L; ++r) acc += S[M.dMsum + I[IN_ROWS + r] * kHid + k];
@@ -884,6 +1087,7 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
         }
         bwd_node_level<LAYER, kLdt, false>(S, M, g, b, I, dajt, direct, kT5Threads);
         __syncthreads();
+        T5_STAMP(4);
     }
 
     // ---------------- the CTA-resident weight-gradient sums: tensor memory -> this CTA's partial (parameter layout) ----------------
@@ -906,29 +1110,30 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
             tc::tmem_wait_ld();
 #pragma unroll
             for (int k = 0; k < 32; ++k) direct[woff + n * ld + 32 * half + k] = __uint_as_float(v[k]) * inv_gs;
-            if (half == 0) {
+            if (half == 0 && pair == 0) {
+                // rows 0..63: rotation (pair A) and translation (pair B) share the accumulator rows; 64..127: torsion and attention
                 float w3[16], ex[16];
-                tc::tmem_ld16(tlane + (pair == 0 ? TM_DW3A : TM_DW3B), w3);
-                tc::tmem_ld16(tlane + (pair == 0 ? TM_EXTA : TM_EXTB), ex);
-                if (head == F_ROT) {
+                tc::tmem_ld16(tlane + TM_DW3, w3);
+                tc::tmem_ld16(tlane + TM_EXT, ex);
+                if (hsel == 0) {
+                    const int wrot = param_offset(LAYER, ROT0_W) - base;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         direct[(param_offset(LAYER, ROT2_W) - base) + c * kHid + n] = w3[c] * inv_gs;
-                        direct[woff + n * ld + 64 + c] = ex[c] * inv_gs;
+                        direct[wrot + n * 68 + 64 + c] = ex[c] * inv_gs;
                     }
                     direct[(param_offset(LAYER, ROT0_B) - base) + n] = ex[6] * inv_gs;
-                } else if (head == F_TOR) {
+                    direct[(param_offset(LAYER, TRN2_W) - base) + n] = w3[4] * inv_gs;
+                    direct[(param_offset(LAYER, TRN0_B) - base) + n] = ex[10] * inv_gs;
+                } else {
+                    const int watt = param_offset(LAYER, ATT0_W) - base;
 #pragma unroll
                     for (int c = 0; c < PMHC_NTORS; ++c) direct[(param_offset(LAYER, TOR2_W) - base) + c * kHid + n] = w3[8 + c] * inv_gs;
                     direct[(param_offset(LAYER, TOR0_B) - base) + n] = ex[6] * inv_gs;
-                } else if (head == F_TRN) {
-                    direct[(param_offset(LAYER, TRN2_W) - base) + n] = w3[0] * inv_gs;
-                    direct[(param_offset(LAYER, TRN0_B) - base) + n] = ex[6] * inv_gs;
-                } else {
-                    direct[(param_offset(LAYER, ATT2_W) - base) + n] = w3[8] * inv_gs;
-                    direct[woff + n * ld + 64] = ex[4] * inv_gs;
-                    direct[woff + n * ld + 65] = ex[5] * inv_gs;
-                    direct[(param_offset(LAYER, ATT0_B) - base) + n] = ex[6] * inv_gs;
+                    direct[(param_offset(LAYER, ATT2_W) - base) + n] = w3[5] * inv_gs;
+                    direct[watt + n * 66 + 64] = ex[8] * inv_gs;
+                    direct[watt + n * 66 + 65] = ex[9] * inv_gs;
+                    direct[(param_offset(LAYER, ATT0_B) - base) + n] = ex[10] * inv_gs;
                 }
             }
         }
@@ -939,6 +1144,23 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     }
     tc::fence_before_thread_sync();
     __syncthreads();
+    T5_STAMP(5);
+#ifdef PMHC_T5_STAMPS
+    if (blockIdx.x == 0 && tid == 0)
+        for (int hh = 0; hh < 2; ++hh) {
+            printf("t5<%d> thread %d:", LAYER, 128 * hh);
+            for (int k = 0; k < 14; ++k) { printf(" %lld", t5_dbg[hh][k] / (np ? np : 1)); t5_dbg[hh][k] = 0; }
+            printf("\n");
+        }
+    if (blockIdx.x == 0 && tid == 0) {
+        printf("t5<%d> node level:", LAYER);
+        for (int k = 0; k < 16; ++k) { printf(" %lld", node_dbg[k]); node_dbg[k] = 0; }
+        printf("\n");
+    }
+    if (blockIdx.x == 0 && tid == 0)
+        printf("t5<%d> cta0: setup %lld | prologue+G+image %lld | head passes %lld (%u) | message-only %lld | node level %lld | other %lld cycles\n", LAYER,
+               st_acc[0], st_acc[1], st_acc[2], np, st_acc[3], st_acc[4], st_acc[5]);
+#endif
     if (mma_warp) tc::tmem_dealloc(tmem, 512);
 }
 

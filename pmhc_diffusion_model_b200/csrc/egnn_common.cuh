@@ -217,13 +217,15 @@ __device__ inline ComplexInfo setup_complex(float* S, const SmemMap& M, const La
         else v = a.feat_in[((size_t)b * kN + i) * kHid + c];
         S[M.H + i * kLdN + c] = v;
     }
+#pragma unroll 8
     for (int idx = tid; idx < P * PMHC_NFEAT; idx += blockDim.x) {
         int j = idx / PMHC_NFEAT, c = idx - j * PMHC_NFEAT;
-        feat_stage[j * FS + c] = a.pocket_feat[(size_t)b * P * PMHC_NFEAT + idx];
+        feat_stage[j * FS + c] = __ldg(a.pocket_feat + (size_t)b * P * PMHC_NFEAT + idx);
     }
+#pragma unroll 8
     for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += blockDim.x) {
         int k = idx / PMHC_NFEAT, c = idx - k * PMHC_NFEAT;
-        wp[k * FS + c] = msg0[k * ld1 + H + c];
+        wp[k * FS + c] = __ldg(msg0 + k * ld1 + H + c);
     }
     __syncthreads();
 
@@ -286,13 +288,15 @@ __device__ inline ComplexInfo setup_complex(float* S, const SmemMap& M, const La
     }
     __syncthreads();
     // -- phase 2 staging --
+#pragma unroll 8
     for (int idx = tid; idx < kHid * 2 * H; idx += blockDim.x) {
         int k = idx / (2 * H), c = idx - k * (2 * H);
-        wq[k * LDQ + c] = msg0[k * ld1 + c];
+        wq[k * LDQ + c] = __ldg(msg0 + k * ld1 + c);
     }
+#pragma unroll 4
     for (int idx = tid; idx < kHid * 14; idx += blockDim.x) {
         int n = idx / 14, c = idx - n * 14;
-        torx[n * 15 + c] = tor0[n * 78 + 64 + c];
+        torx[n * 15 + c] = __ldg(tor0 + n * 78 + 64 + c);
     }
     for (int n = tid; n < kHid; n += blockDim.x) torx[n * 15 + 14] = tor0b[n];
     __syncthreads();

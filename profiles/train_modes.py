@@ -20,7 +20,7 @@ dm = DiffusionModelOptimizer(1000, model, 1e-3)
 tb = {k: v.to(dev) for k, v in synthetic_batch(B, 9, Pn, P_pad=P_pad, seed=5000).items()}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for fwd, bwd in (("fp32", "fp32"), ("bf16", "fp32"), ("bf16", "bf16"), ("fp32", "bf16")):
+for fwd, bwd in (("fp32", "fp32"), ("bf16", "bf16"), ("bf16", "fp16"), ("tc32", "fp16")):
     model.precision, model.backward_precision = fwd, bwd
     for _ in range(3):
         dm.optimize(dict(tb), None)
