@@ -1371,10 +1371,108 @@ __device__ __forceinline__ void rmw_batched(float* __restrict__ dst, int n, cons
     }
 }
 
+// Layer 1's node feature MLP backward (model.py:151, :407) for one complex: dL / d relu(o1) -> feature_mlp.{0,2} weight gradients
+// (into the CTA's partial) and dL / d(message sum) in S[M.dMsum].  Needs S[M.f.H], S[M.f.Msum] and the row list I[IN_ROWS..].
+__device__ __forceinline__ void bwd_feature_mlp(float* S, const BwdMap& M, const BwdArgs& g, int b, const int* I, int L,
+                                                float* __restrict__ direct, const int NT, const bool weights_staged = false) {
+    const LayerArgs& a = g.a;
+    constexpr int base = param_offset(0, 0);
+    const int tid = threadIdx.x;
+#ifdef PMHC_T5_STAMPS
+    long long nst_ = clock64();
+#endif
+    const float* f0w = a.params + param_offset(0, FEAT0_W);
+    const float* f0b = a.params + param_offset(0, FEAT0_B);
+    const float* f2w = a.params + param_offset(0, FEAT2_W);
+    constexpr int ldf = kH1 + kHid;
+    float* hid = S + M.BufA;                 // [16][65] relu(feature_mlp.0(...))
+    float* dO = S + M.BufA + kN * kLdN;      // [16][65] dL/do (after the relu mask)
+    float* dhid = S + M.BufB;                // [16][65]
+    // both weight matrices of the feature MLP staged behind those (coalesced copies, many loads in flight): every product
+    // below then reads shared memory instead of walking an L2-latency chain per term
+    NSTAMP(8);
+    float* f0s = S + M.BufA + 2 * kN * kLdN;  // [64][87]
+    float* f2s = S + M.BufB + kN * kLdN;      // [64][64]
+    if (!weights_staged) {      // (a caller that keeps BufA / BufB untouched between complexes stages them once)
+#pragma unroll 8
+        for (int idx = tid; idx < kHid * ldf; idx += NT) f0s[idx] = __ldg(f0w + idx);
+#pragma unroll 8
+        for (int idx = tid; idx < kHid * kHid; idx += NT) f2s[idx] = __ldg(f2w + idx);
+    }
+    __syncthreads();
+    NSTAMP(9);
+    for (int idx = tid; idx < L * kHid; idx += NT) {
+        int r = idx >> 6, n = idx & 63;
+        int i = I[IN_ROWS + r];
+        const float* w = f0s + n * ldf;
+        const float* h = S + M.f.H + i * kLdN;
+        const float* ms = S + M.f.Msum + i * kHid;
+        float acc = f0b[n];
+#pragma unroll
+        for (int c = 0; c < kH1; ++c) acc = fmaf(w[c], h[c], acc);
+#pragma unroll 16
+        for (int c = 0; c < kHid; ++c) acc = fmaf(w[kH1 + c], ms[c], acc);
+        hid[r * kLdN + n] = fmaxf(acc, 0.0f);
+        const size_t node = (size_t)b * kN + i;
+        dO[r * kLdN + n] = g.feat_post[node * kHid + n] > 0.0f ? g.d_feat_out[node * kHid + n] : 0.0f;
+    }
+    __syncthreads();
+    NSTAMP(10);
+    for (int idx = tid; idx < L * kHid; idx += NT) {
+        int r = idx >> 6, n = idx & 63;
+        float acc = 0.0f;
+#pragma unroll 16
+        for (int n2 = 0; n2 < kHid; ++n2) acc = fmaf(f2s[n2 * kHid + n], dO[r * kLdN + n2], acc);
+        dhid[r * kLdN + n] = hid[r * kLdN + n] > 0.0f ? acc : 0.0f;
+    }
+    NSTAMP(11);
+    // feature_mlp.2: dW[n2][n] += sum_r dO[r][n2] hid[r][n]; db[n2] += sum_r dO[r][n2]
+    static_assert(param_offset(0, FEAT2_B) == param_offset(0, FEAT2_W) + kHid * kHid, "feature_mlp.2 weight and bias are adjacent");
+    rmw_batched<8>(direct + (param_offset(0, FEAT2_W) - base), kHid * kHid + kHid, NT, [&](int idx) {
+        float acc = 0.0f;
+        if (idx < kHid * kHid) {
+            const int n2 = idx >> 6, n = idx & 63;
+            for (int r = 0; r < L; ++r) acc = fmaf(dO[r * kLdN + n2], hid[r * kLdN + n], acc);
+        } else {
+            const int n2 = idx - kHid * kHid;
+            for (int r = 0; r < L; ++r) acc += dO[r * kLdN + n2];
+        }
+        return acc;
+    });
+    __syncthreads();
+    NSTAMP(12);
+    // feature_mlp.0: dW[n][c] += sum_r dhid[r][n] cat(h, msum)[r][c]; db[n] += sum_r dhid[r][n]
+    static_assert(param_offset(0, FEAT0_B) == param_offset(0, FEAT0_W) + kHid * ldf, "feature_mlp.0 weight and bias are adjacent");
+    rmw_batched<8>(direct + (param_offset(0, FEAT0_W) - base), kHid * ldf + kHid, NT, [&](int idx) {
+        float acc = 0.0f;
+        if (idx < kHid * ldf) {
+            const int n = idx / ldf, c = idx - n * ldf;
+            for (int r = 0; r < L; ++r) {
+                const int i = I[IN_ROWS + r];
+                const float x = c < kH1 ? S[M.f.H + i * kLdN + c] : S[M.f.Msum + i * kHid + (c - kH1)];
+                acc = fmaf(dhid[r * kLdN + n], x, acc);
+            }
+        } else {
+            const int n = idx - kHid * ldf;
+            for (int r = 0; r < L; ++r) acc += dhid[r * kLdN + n];
+        }
+        return acc;
+    });
+    NSTAMP(13);
+    for (int idx = tid; idx < L * kHid; idx += NT) {
+        int r = idx >> 6, k = idx & 63;
+        float acc = 0.0f;
+#pragma unroll 16
+        for (int n = 0; n < kHid; ++n) acc = fmaf(f0s[n * ldf + kH1 + k], dhid[r * kLdN + n], acc);
+        S[M.dMsum + I[IN_ROWS + r] * kHid + k] = acc;
+    }
+
+}
+
 // Per-complex prologue shared by every backward kernel: the row-level backward of the output normalisation / torsion rotation /
 // translation (RowG), and for layer 1 the node-feature-MLP backward (model.py:151, :407) that produces dL / d(message sum).
 // Every thread of the CTA takes part (NT = blockDim.x); the caller synchronises afterwards.
-template <int LAYER>
+template <int LAYER, bool FEAT = true>
 __device__ __forceinline__ void bwd_prologue(float* S, const BwdMap& M, const BwdArgs& g, int b, const int* I, int L, int W,
                                              float* __restrict__ direct, const int NT) {
     const LayerArgs& a = g.a;
@@ -1429,92 +1527,7 @@ __device__ __forceinline__ void bwd_prologue(float* S, const BwdMap& M, const Bw
         rg[15] = rs[0];
     }
 
-    // ---------------- layer 1: node feature MLP backward (model.py:151, :407) -> dMsum ----------------
-    if (LAYER == 0) {
-        const float* f0w = a.params + param_offset(0, FEAT0_W);
-        const float* f0b = a.params + param_offset(0, FEAT0_B);
-        const float* f2w = a.params + param_offset(0, FEAT2_W);
-        constexpr int ldf = kH1 + kHid;
-        float* hid = S + M.BufA;                 // [16][65] relu(feature_mlp.0(...))
-        float* dO = S + M.BufA + kN * kLdN;      // [16][65] dL/do (after the relu mask)
-        float* dhid = S + M.BufB;                // [16][65]
-        // both weight matrices of the feature MLP staged behind those (coalesced copies, many loads in flight): every product
-        // below then reads shared memory instead of walking an L2-latency chain per term
-        NSTAMP(8);
-        float* f0s = S + M.BufA + 2 * kN * kLdN;  // [64][87]
-        float* f2s = S + M.BufB + kN * kLdN;      // [64][64]
-#pragma unroll 8
-        for (int idx = tid; idx < kHid * ldf; idx += NT) f0s[idx] = __ldg(f0w + idx);
-#pragma unroll 8
-        for (int idx = tid; idx < kHid * kHid; idx += NT) f2s[idx] = __ldg(f2w + idx);
-        __syncthreads();
-        NSTAMP(9);
-        for (int idx = tid; idx < L * kHid; idx += NT) {
-            int r = idx >> 6, n = idx & 63;
-            int i = I[IN_ROWS + r];
-            const float* w = f0s + n * ldf;
-            const float* h = S + M.f.H + i * kLdN;
-            const float* ms = S + M.f.Msum + i * kHid;
-            float acc = f0b[n];
-#pragma unroll
-            for (int c = 0; c < kH1; ++c) acc = fmaf(w[c], h[c], acc);
-#pragma unroll 16
-            for (int c = 0; c < kHid; ++c) acc = fmaf(w[kH1 + c], ms[c], acc);
-            hid[r * kLdN + n] = fmaxf(acc, 0.0f);
-            const size_t node = (size_t)b * kN + i;
-            dO[r * kLdN + n] = g.feat_post[node * kHid + n] > 0.0f ? g.d_feat_out[node * kHid + n] : 0.0f;
-        }
-        __syncthreads();
-        NSTAMP(10);
-        for (int idx = tid; idx < L * kHid; idx += NT) {
-            int r = idx >> 6, n = idx & 63;
-            float acc = 0.0f;
-#pragma unroll 16
-            for (int n2 = 0; n2 < kHid; ++n2) acc = fmaf(f2s[n2 * kHid + n], dO[r * kLdN + n2], acc);
-            dhid[r * kLdN + n] = hid[r * kLdN + n] > 0.0f ? acc : 0.0f;
-        }
-        NSTAMP(11);
-        // feature_mlp.2: dW[n2][n] += sum_r dO[r][n2] hid[r][n]; db[n2] += sum_r dO[r][n2]
-        static_assert(param_offset(0, FEAT2_B) == param_offset(0, FEAT2_W) + kHid * kHid, "feature_mlp.2 weight and bias are adjacent");
-        rmw_batched<8>(direct + (param_offset(0, FEAT2_W) - base), kHid * kHid + kHid, NT, [&](int idx) {
-            float acc = 0.0f;
-            if (idx < kHid * kHid) {
-                const int n2 = idx >> 6, n = idx & 63;
-                for (int r = 0; r < L; ++r) acc = fmaf(dO[r * kLdN + n2], hid[r * kLdN + n], acc);
-            } else {
-                const int n2 = idx - kHid * kHid;
-                for (int r = 0; r < L; ++r) acc += dO[r * kLdN + n2];
-            }
-            return acc;
-        });
-        __syncthreads();
-        NSTAMP(12);
-        // feature_mlp.0: dW[n][c] += sum_r dhid[r][n] cat(h, msum)[r][c]; db[n] += sum_r dhid[r][n]
-        static_assert(param_offset(0, FEAT0_B) == param_offset(0, FEAT0_W) + kHid * ldf, "feature_mlp.0 weight and bias are adjacent");
-        rmw_batched<8>(direct + (param_offset(0, FEAT0_W) - base), kHid * ldf + kHid, NT, [&](int idx) {
-            float acc = 0.0f;
-            if (idx < kHid * ldf) {
-                const int n = idx / ldf, c = idx - n * ldf;
-                for (int r = 0; r < L; ++r) {
-                    const int i = I[IN_ROWS + r];
-                    const float x = c < kH1 ? S[M.f.H + i * kLdN + c] : S[M.f.Msum + i * kHid + (c - kH1)];
-                    acc = fmaf(dhid[r * kLdN + n], x, acc);
-                }
-            } else {
-                const int n = idx - kHid * ldf;
-                for (int r = 0; r < L; ++r) acc += dhid[r * kLdN + n];
-            }
-            return acc;
-        });
-        NSTAMP(13);
-        for (int idx = tid; idx < L * kHid; idx += NT) {
-            int r = idx >> 6, k = idx & 63;
-            float acc = 0.0f;
-#pragma unroll 16
-            for (int n = 0; n < kHid; ++n) acc = fmaf(f0s[n * ldf + kH1 + k], dhid[r * kLdN + n], acc);
-            S[M.dMsum + I[IN_ROWS + r] * kHid + k] = acc;
-        }
-    }
+    if (LAYER == 0 && FEAT) bwd_feature_mlp(S, M, g, b, I, L, direct, NT);
 }
 
 // Per-complex node level shared by every backward kernel: message_mlp.0, torsion_mlp.0[:, 64:78] and biases from the per-node
@@ -1777,6 +1790,9 @@ namespace pmhc {
 struct BwdWorkspace {
     float *ajt, *dajt, *partial, *d_frames1, *d_tors1, *d_feat1;
     float *red, *scale;      // tcgen05 mode: reduced partials of a layer, the two layers' operand scales
+    float *ajt_all, *rec_all; // tcgen05 mode: per-complex neighbour projections and records from the setup pre-kernel
+    float* dmsum_g;          // tcgen05 mode, layer 1: dL / d(message sum) and W2^T of it per complex, from the node pre-kernel
+    float *acc, *dajt_all;   // tcgen05 mode: per-complex gradient accumulators and dL / dA_j^T, handed from the pair kernel to the node kernel
     uint8_t* wimg;           // tcgen05 mode: folded-weight images of both layers
     int partial_stride;
     size_t bytes;
@@ -1800,6 +1816,14 @@ BwdWorkspace carve_bwd_workspace(void* wsbase, size_t fwd_bytes, int B, int P) {
     w.red = p + o;       o += ((size_t)max_layer + 3) & ~(size_t)3;
     w.scale = p + o;     o += 8;
     w.wimg = reinterpret_cast<uint8_t*>(p + o); o += (2 * kFoldImageBytes + 3) / 4;
+    o = (o + 3) & ~(size_t)3;
+    w.acc = p + o;       o += (size_t)B * kAccFloats;
+    o = (o + 3) & ~(size_t)3;
+    w.dajt_all = p + o;  o += (size_t)B * kHid * pad_k(P);
+    o = (o + 3) & ~(size_t)3;
+    w.dmsum_g = p + o;   o += (size_t)B * 2 * kN * kHid;
+    w.ajt_all = p + o;   o += (size_t)B * kHid * pad_k(P);
+    w.rec_all = p + o;   o += (size_t)B * t5_record_floats(pad_k(P));
     w.bytes = o * sizeof(float);
     return w;
 }
@@ -1846,15 +1870,50 @@ int launch_layer_backward_t5(const BwdArgs& g, const BwdWorkspace& w, int n_cta,
     }
     constexpr int base = param_offset(LAYER, 0);
     constexpr int numel = param_offset(LAYER + 1, 0) - base;
-    float* scale = w.scale + 4 * LAYER;
-    bwd_grad_scale_kernel<<<1, 1024, 0, stream>>>(g.d_frames_out, g.a.B * kN * 7, g.d_tors_out, g.a.B * kN * 14, scale);
-    PMHC_CHECK_LAUNCH("bwd_grad_scale");
-    T5Args x{w.wimg + (size_t)LAYER * kFoldImageBytes, scale};
+    unsigned* max_bits = reinterpret_cast<unsigned*>(w.scale) + LAYER;      // zeroed by bwd_fold_weights_kernel at the start of the step
+    bwd_grad_max_kernel<<<128, 256, 0, stream>>>(g.d_frames_out, g.a.B * kN * 7, g.d_tors_out, g.a.B * kN * 14, max_bits);
+    PMHC_CHECK_LAUNCH("bwd_grad_max");
+    if (LAYER == 0) {
+        static PerDeviceOnce pre_configured;
+        const PreMap PM = make_pre_map();
+        if (pre_configured.needed()) {
+            cudaError_t e = cudaFuncSetAttribute(bwd_feature_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PM.total_bytes);
+            PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(node pre-kernel): %s", cudaGetErrorString(e));
+            pre_configured.mark();
+        }
+        bwd_feature_pre_kernel<<<n_cta, kPostThreads, PM.total_bytes, stream>>>(g, w.dmsum_g);
+        PMHC_CHECK_LAUNCH("bwd_feature_pre");
+    }
+    {
+        static PerDeviceOnce setup_configured;
+        const SmemMap SM = make_setup_map(g.a.Kpad, g.a.P, layer_H(LAYER));
+        const size_t sbytes = (size_t)SM.total_floats * sizeof(float);
+        PMHC_REQUIRE((int)sbytes <= max_smem, "EGNN backward setup needs %zu B of shared memory (P=%d), device allows %d", sbytes, g.a.P, max_smem);
+        if (setup_configured.needed()) {
+            cudaError_t e = cudaFuncSetAttribute(bwd_setup_pre_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(setup pre-kernel): %s", cudaGetErrorString(e));
+            setup_configured.mark();
+        }
+        bwd_setup_pre_kernel<LAYER><<<g.a.B, 256, sbytes, stream>>>(g.a, w.ajt_all, w.rec_all, w.wimg + (size_t)LAYER * kFoldImageBytes);
+        PMHC_CHECK_LAUNCH("bwd_setup_pre");
+    }
+    T5Args x{w.wimg + (size_t)LAYER * kFoldImageBytes, max_bits, w.acc, w.dajt_all, w.ajt_all, w.rec_all, w.dmsum_g};
     if (profile_enabled()) profile_mark(PROF_BWD, stream, true);
     egnn_layer_backward_t5_kernel<LAYER><<<n_cta, kT5Threads, smem, stream>>>(g, x);
     if (profile_enabled()) profile_mark(PROF_BWD, stream, false);
     PMHC_CHECK_LAUNCH("egnn_layer_backward_t5");
-    reduce_partials_to_kernel<<<(numel + 255) / 256, 256, 0, stream>>>(g.partial, g.partial_stride, n_cta, numel, w.red);
+    {
+        static PerDeviceOnce post_configured;
+        const PostMap PM = make_post_map();
+        if (post_configured.needed()) {
+            cudaError_t e = cudaFuncSetAttribute(bwd_node_post_kernel<LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, PM.total_bytes);
+            PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(node kernel): %s", cudaGetErrorString(e));
+            post_configured.mark();
+        }
+        bwd_node_post_kernel<LAYER><<<n_cta, kPostThreads, PM.total_bytes, stream>>>(g, w.acc, w.dajt_all);
+        PMHC_CHECK_LAUNCH("bwd_node_post");
+    }
+    reduce_partials_to_kernel<<<(numel + 63) / 64, dim3(64, 4), 0, stream>>>(g.partial, g.partial_stride, n_cta, numel, w.red);
     PMHC_CHECK_LAUNCH("reduce_partials_to");
     bwd_unfold_kernel<LAYER><<<(numel + 255) / 256, 256, 0, stream>>>(g.a.params, w.red, grad);
     PMHC_CHECK_LAUNCH("bwd_unfold");
@@ -1906,7 +1965,7 @@ extern "C" int pmhc_model_backward_ex(const float* params, const PmhcBatch* bt, 
     g.d_frames_out = d_out_frames; g.d_tors_out = d_out_torsions; g.d_feat_out = nullptr;
     g.d_frames_in = w.d_frames1; g.d_tors_in = w.d_tors1; g.d_feat_in = w.d_feat1;
     if (t5) {
-        bwd_fold_weights_kernel<<<8, 256, 0, stream>>>(params, w.wimg);
+        bwd_fold_weights_kernel<<<64, 256, 0, stream>>>(params, w.wimg, reinterpret_cast<unsigned*>(w.scale));
         PMHC_CHECK_LAUNCH("bwd_fold_weights");
     }
     int rc = t5 ? launch_layer_backward_t5<1>(g, w, n_cta, flat_grad, stream)

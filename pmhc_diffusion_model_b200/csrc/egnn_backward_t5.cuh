@@ -53,8 +53,60 @@ enum { F_ROT = 0, F_TOR = 1, F_TRN = 2, F_ATT = 3 };
 
 struct T5Map {
     BwdMap b;          // float offsets (shared prologue / node-level code reads these)
-    int Cvec, Dl, B3, G, S1, Bars, total_bytes;
+    int Cvec, Dl, B3, G, S1, Bars, Rec, total_bytes;
 };
+
+// The per-complex record the setup pre-kernel leaves in global memory (A_i with the first-layer bias, T_t with the torsion head's folded
+// constant, torsions, quaternions, translations, row / neighbour lists and counts), laid out as the pair kernel keeps it in shared memory.
+__host__ __device__ inline int t5_layout_record(int o, SmemMap& f, int Kpad) {
+    f.Ai = o;       o += kN * kLdN;
+    f.Tt = o;       o += kN * kHid;
+    f.Tors = o;     o += kN * 2 * PMHC_NTORS;
+    f.Q = o;        o += Kpad * 4;
+    f.X = o;        o += Kpad * 3;
+    f.Ints = o;     o += Kpad + 64;
+    return o;
+}
+__host__ __device__ inline int t5_record_floats(int Kpad) { return kN * kLdN + kN * kHid + kN * 2 * PMHC_NTORS + 8 * Kpad + 64; }
+
+// The per-complex gradient accumulators, laid out identically in the pair kernel and in the node kernel: the pair kernel writes the
+// block [S1, grads_end) to global memory once per complex (kAccFloats floats), the node kernel (bwd_node_post_kernel) loads it back.
+__host__ __device__ inline int t5_layout_accumulators(int o, BwdMap& m, int& S1) {
+    S1 = o;         o += kN * kHid;                     // layer 1: sum over all neighbour slots of m1[i, .]
+    m.dAi = o;      o += kN * kLdN;
+    m.dAjPep = o;   o += kN * kLdN;
+    m.dWe = o;      o += kEdge * kLdN;
+    m.dTt = o;      o += kN * kHid;
+    m.dMsum = o;    o += kN * kHid;
+    m.RowG = o;     o += kN * 16;
+    m.dQ = o;       o += kN * 4;
+    m.dX = o;       o += kN * 3;
+    m.dTors = o;    o += kN * 14;
+    m.grads_end = o;
+    return o;
+}
+constexpr int kAccFloats = kN * kHid + 2 * kN * kLdN + kEdge * kLdN + 2 * kN * kHid + kN * 16 + kN * 4 + kN * 3 + kN * 14;
+
+struct PostMap {
+    BwdMap b;
+    int S1, total_bytes;
+};
+__host__ __device__ inline PostMap make_post_map() {
+    PostMap t;
+    BwdMap& m = t.b;
+    int o = 0;
+    m.W2 = m.Wh = m.W3i = m.Wx = m.Dx = m.Ex = m.Pl = -1;
+    m.BufA = o;     o += kHid * kLdt;                   // staging: pocket dA_j^T chunk, then message_mlp.0's node columns
+    m.BufB = o;     o += kHid * kLdt;                   // staging: pocket feature chunk, then torsion_mlp.0's torsion columns
+    m.Dout = o;     o += kHid * PMHC_NFEAT + 96;
+    m.f.H = o;      o += kN * kLdN;
+    o = (o + 3) & ~3;
+    m.f.Tors = o;   o += kN * 2 * PMHC_NTORS;
+    o = t5_layout_accumulators(o, m, t.S1);
+    m.total_floats = o;
+    t.total_bytes = o * 4;
+    return t;
+}
 
 __host__ __device__ inline T5Map make_t5_map(int Kpad) {
     T5Map t;
@@ -80,29 +132,12 @@ __host__ __device__ inline T5Map make_t5_map(int Kpad) {
     t.B3 = o;       o += 16;                            // second-layer bias gradients of the CTA
     t.Bars = o;     o += 32;                            // mbarriers + the TMEM base address
     m.Pl = o;       o += kBwdPairs + 4;
-    m.f.Ai = o;     o += kN * kLdN;
-    o = (o + 3) & ~3;
-    m.f.Tt = o;     o += kN * kHid;
-    m.f.H = o;      o += kN * kLdN;
-    o = (o + 3) & ~3;
-    m.f.Tors = o;   o += kN * 2 * PMHC_NTORS;
+    m.f.H = -1;
     t.G = o;        o += kN * kHid;                     // layer 1: W2^T dMsum[i]
-    t.S1 = o;       o += kN * kHid;                     // layer 1: sum over all neighbour slots of m1[i, .]
-    m.dAi = o;      o += kN * kLdN;
-    m.dAjPep = o;   o += kN * kLdN;
-    m.dWe = o;      o += kEdge * kLdN;
-    m.dTt = o;      o += kN * kHid;
-    m.dMsum = o;    o += kN * kHid;
-    m.RowG = o;     o += kN * 16;
-    m.dQ = o;       o += kN * 4;
-    m.dX = o;       o += kN * 3;
-    m.dTors = o;    o += kN * 14;
-    m.grads_end = o;
+    o = t5_layout_accumulators(o, m, t.S1);
     o = (o + 3) & ~3;
-    m.f.Q = o;      o += Kpad * 4;
-    m.f.X = o;      o += Kpad * 3;
-    o = (o + 3) & ~3;
-    m.f.Ints = o;   o += Kpad + 64;
+    t.Rec = o;                                          // the complex's record from bwd_setup_pre_kernel: one bulk copy
+    o = t5_layout_record(o, m.f, Kpad);
     m.total_floats = o;
     m.f.total_floats = o;
     t.total_bytes = o * 4 + 1024;                       // + slack for the 1024-byte alignment of the base
@@ -111,19 +146,24 @@ __host__ __device__ inline T5Map make_t5_map(int Kpad) {
 
 struct T5Args {
     const uint8_t* wimg;   // this layer's folded-weight image (kFoldImageBytes)
-    const float* scale;    // device: [0] = s (power of two applied to gradient-like operands), [1] = 1 / s
+    const unsigned* max_bits;   // device: bit pattern of max |upstream gradient| of this launch (bwd_grad_max_kernel)
+    float* acc;            // [B][kAccFloats] per-complex gradient accumulators, consumed by bwd_node_post_kernel
+    float* dajt_all;       // [B][64][Kpad] per-complex dL / dA_j^T
+    const float* ajt_all;  // [B][64][Kpad] neighbour projections A_j^T per complex (bwd_setup_pre_kernel)
+    const float* rec_all;  // [B][t5_record_floats(Kpad)] per-complex records (bwd_setup_pre_kernel)
+    const float* dmsum_g;  // layer 1: [B][2][16][64] dL / d(message sum) and W2^T of it, from bwd_feature_pre_kernel (which also zeroed the partials)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
 // once per step: F_h = W_h[:, :64] W2 (fp16, SW128 tile), c_h = W_h[:, :64] b2 + b_h (the torsion head's bias lives in T_t)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bwd_fold_weights_kernel(const float* __restrict__ params, uint8_t* __restrict__ img_all) {
-    const int layer = blockIdx.x >> 2, head = blockIdx.x & 3;
+__global__ void __launch_bounds__(256) bwd_fold_weights_kernel(const float* __restrict__ params, uint8_t* __restrict__ img_all,
+                                                               unsigned* __restrict__ max_bits) {
+    // grid: 2 layers x 4 heads x 8 blocks of 8 hidden units
+    const int layer = blockIdx.x >> 5, head = (blockIdx.x >> 3) & 3, n0 = (blockIdx.x & 7) * 8;
     __shared__ float sW2[kHid * kHid];
-    __shared__ float sWh[kHid * (kHid + 1)];
-    const int base = layer == 0 ? param_offset(0, 0) : param_offset(1, 0);
+    __shared__ float sWh[8 * kHid];
     auto off = [&](int id) { return layer == 0 ? param_offset(0, id) : param_offset(1, id); };
-    (void)base;
     int wid, bid, ld;
     if (head == F_ROT)      { wid = ROT0_W; bid = ROT0_B; ld = 68; }
     else if (head == F_TOR) { wid = TOR0_W; bid = -1;     ld = 78; }
@@ -132,52 +172,47 @@ __global__ void __launch_bounds__(256) bwd_fold_weights_kernel(const float* __re
     const float* W2 = params + off(MSG2_W);
     const float* b2 = params + off(MSG2_B);
     const float* Wh = params + off(wid);
-    for (int idx = threadIdx.x; idx < kHid * kHid; idx += 256) {
-        sW2[idx] = W2[idx];
-        sWh[(idx >> 6) * (kHid + 1) + (idx & 63)] = Wh[(idx >> 6) * ld + (idx & 63)];
-    }
+    if (blockIdx.x == 0 && threadIdx.x < 8) max_bits[threadIdx.x] = 0u;      // the step's |upstream gradient| maxima start at zero
+#pragma unroll 8
+    for (int idx = threadIdx.x; idx < kHid * kHid; idx += 256) sW2[idx] = __ldg(W2 + idx);
+    for (int idx = threadIdx.x; idx < 8 * kHid; idx += 256) sWh[idx] = __ldg(Wh + (n0 + (idx >> 6)) * ld + (idx & 63));
     __syncthreads();
     uint8_t* img = img_all + (size_t)layer * kFoldImageBytes;
-    for (int idx = threadIdx.x; idx < kHid * kHid; idx += 256) {
-        const int n = idx >> 6, c = idx & 63;
+    for (int idx = threadIdx.x; idx < 8 * kHid; idx += 256) {
+        const int nl = idx >> 6, c = idx & 63;
         float acc = 0.0f;
-#pragma unroll 8
-        for (int k = 0; k < kHid; ++k) acc = fmaf(sWh[n * (kHid + 1) + k], sW2[k * kHid + c], acc);
-        *reinterpret_cast<__half*>(img + head * 8192 + tc::sw128_offset(n, c)) = __float2half_rn(acc);
+#pragma unroll 16
+        for (int k = 0; k < kHid; ++k) acc = fmaf(sWh[nl * kHid + k], sW2[k * kHid + c], acc);
+        *reinterpret_cast<__half*>(img + head * 8192 + tc::sw128_offset(n0 + nl, c)) = __float2half_rn(acc);
     }
-    if (threadIdx.x < kHid) {
-        const int n = threadIdx.x;
+    if (threadIdx.x < 8) {
+        const int n = n0 + threadIdx.x;
         float acc = bid >= 0 ? params[off(bid) + n] : 0.0f;
-        for (int k = 0; k < kHid; ++k) acc = fmaf(sWh[n * (kHid + 1) + k], b2[k], acc);
+        for (int k = 0; k < kHid; ++k) acc = fmaf(sWh[threadIdx.x * kHid + k], __ldg(b2 + k), acc);
         reinterpret_cast<float*>(img + 4 * 8192)[head * kHid + n] = acc;
     }
 }
 
-// s = 2^-floor(log2 max|x|) over the upstream gradients of a layer launch (frames and torsions): the largest gradient-like
-// operand entry then lies within a few binades of 1.  One block.
-__global__ void __launch_bounds__(1024) bwd_grad_scale_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb,
-                                                              float* __restrict__ out) {
-    __shared__ float red[32];
+// max |x| over the upstream gradients of a layer launch (frames and torsions), as the bit pattern of a non-negative float (atomicMax on
+// unsigned orders those like the floats).  The pair kernel turns it into s = 2^-floor(log2 max): the largest gradient-like operand
+// entry then lies within a few binades of 1.
+__global__ void __launch_bounds__(256) bwd_grad_max_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb,
+                                                           unsigned* __restrict__ out_bits) {
     float mx = 0.0f;
-    for (int i = threadIdx.x; i < na; i += 1024) mx = fmaxf(mx, fabsf(a[i]));
-    for (int i = threadIdx.x; i < nb; i += 1024) mx = fmaxf(mx, fabsf(b[i]));
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < na; i += gridDim.x * 256) mx = fmaxf(mx, fabsf(__ldg(a + i)));
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nb; i += gridDim.x * 256) mx = fmaxf(mx, fabsf(__ldg(b + i)));
     mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        mx = warp_max(red[threadIdx.x]);
-        if (threadIdx.x == 0) {
-            float s = 1.0f;
-            if (mx > 0.0f && mx < INFINITY) {
-                int e;
-                frexpf(mx, &e);                 // mx = f 2^e, f in [0.5, 1)
-                e = min(max(-(e - 1), -100), 100);
-                s = ldexpf(1.0f, e);            // s mx in [1, 2)
-            }
-            out[0] = s;
-            out[1] = 1.0f / s;
-        }
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(mx));
+}
+__device__ __forceinline__ float t5_scale_from_max(float mx) {
+    float s = 1.0f;
+    if (mx > 0.0f && mx < INFINITY) {
+        int e;
+        frexpf(mx, &e);                 // mx = f 2^e, f in [0.5, 1)
+        e = min(max(-(e - 1), -100), 100);
+        s = ldexpf(1.0f, e);            // s mx in [1, 2)
     }
+    return s;
 }
 
 // After the fixed-order reduction of the per-CTA partials into `red` (parameter layout of the layer, the head first-layer message
@@ -187,9 +222,13 @@ __global__ void __launch_bounds__(256) bwd_unfold_kernel(const float* __restrict
     constexpr int base = param_offset(LAYER, 0);
     constexpr int numel = param_offset(LAYER + 1, 0) - base;
     const int p = blockIdx.x * 256 + threadIdx.x;
+    // message_mlp.2.weight staged with a padded row (the head products walk it down a column)
+    __shared__ float sW2[kHid * (kHid + 1)];
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < kHid * kHid; idx += 256) sW2[(idx >> 6) * (kHid + 1) + (idx & 63)] = __ldg(params + param_offset(LAYER, MSG2_W) + idx);
+    __syncthreads();
     if (p >= numel) return;
     const int q = p + base;
-    const float* W2 = params + param_offset(LAYER, MSG2_W);
     const float* b2 = params + param_offset(LAYER, MSG2_B);
     constexpr int wid[4] = {ROT0_W, TOR0_W, TRN0_W, ATT0_W};
     constexpr int bid[4] = {ROT0_B, TOR0_B, TRN0_B, ATT0_B};
@@ -205,55 +244,62 @@ __global__ void __launch_bounds__(256) bwd_unfold_kernel(const float* __restrict
                 // dW_h[n][k] = sum_c dF_h[n][c] W2[k][c] + db_h[n] b2[k]
                 const float* dF = red + (o - base) + n * lds[h];
                 float acc = red[param_offset(LAYER, bid[h]) - base + n] * b2[k];
-#pragma unroll 8
-                for (int c = 0; c < kHid; ++c) acc = fmaf(dF[c], __ldg(W2 + k * kHid + c), acc);
+#pragma unroll 16
+                for (int c = 0; c < kHid; ++c) acc = fmaf(__ldg(dF + c), sW2[k * (kHid + 1) + c], acc);
                 v = acc;
             }
             done = true;
         }
     }
     if (!done && q >= param_offset(LAYER, MSG2_W) && q < param_offset(LAYER, MSG2_W) + kHid * kHid) {
-        // dW2[k][c] += sum_h sum_n W_h[n][k] dF_h[n][c]
+        // dW2[k][c] += sum_h sum_n W_h[n][k] dF_h[n][c]: the four heads' chains run interleaved (64 loads in flight per batch of 8 n)
         const int k = (q - param_offset(LAYER, MSG2_W)) >> 6, c = (q - param_offset(LAYER, MSG2_W)) & 63;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const float* Wh = params + param_offset(LAYER, wid[h]);
-            const float* dF = red + (param_offset(LAYER, wid[h]) - base);
-            float acc = 0.0f;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 8
-            for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(Wh + n * lds[h] + k), dF[n * lds[h] + c], acc);
-            v += acc;
+        for (int n = 0; n < kHid; ++n) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                acc[h] = fmaf(__ldg(params + param_offset(LAYER, wid[h]) + n * lds[h] + k), __ldg(red + (param_offset(LAYER, wid[h]) - base) + n * lds[h] + c), acc[h]);
         }
+        v += ((acc[0] + acc[1]) + acc[2]) + acc[3];
         done = true;
     }
     if (!done && q >= param_offset(LAYER, MSG2_B) && q < param_offset(LAYER, MSG2_B) + kHid) {
         const int k = q - param_offset(LAYER, MSG2_B);
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 8
+        for (int n = 0; n < kHid; ++n) {
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const float* Wh = params + param_offset(LAYER, wid[h]);
-            const float* db = red + (param_offset(LAYER, bid[h]) - base);
-            float acc = 0.0f;
-            for (int n = 0; n < kHid; ++n) acc = fmaf(__ldg(Wh + n * lds[h] + k), db[n], acc);
-            v += acc;
+            for (int h = 0; h < 4; ++h)
+                acc[h] = fmaf(__ldg(params + param_offset(LAYER, wid[h]) + n * lds[h] + k), __ldg(red + (param_offset(LAYER, bid[h]) - base) + n), acc[h]);
         }
+        v += ((acc[0] + acc[1]) + acc[2]) + acc[3];
     }
     grad[q] += v;
 }
 
-// partial -> red (plain store): same fixed CTA order as reduce_partials_kernel
-__global__ void reduce_partials_to_kernel(const float* __restrict__ partial, int stride, int n_cta, int numel, float* __restrict__ red) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= numel) return;
+// partial -> red (plain store).  blockDim = (64, 4): the CTA rows are split in four contiguous groups summed by four threads of a
+// parameter, each in ascending CTA order, and the four sums are added in group order — a fixed order, independent of timing.
+__global__ void __launch_bounds__(256) reduce_partials_to_kernel(const float* __restrict__ partial, int stride, int n_cta, int numel,
+                                                                 float* __restrict__ red) {
+    __shared__ float part[4][64];
+    const int p = blockIdx.x * 64 + threadIdx.x;
+    const int per = (n_cta + 3) / 4;
+    const int c_lo = threadIdx.y * per, c_hi = min(n_cta, c_lo + per);
     float acc = 0.0f;
-    for (int c0 = 0; c0 < n_cta; c0 += 16) {
-        float v[16];
+    if (p < numel) {
+        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+            float v[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = c0 + u < n_cta ? __ldcg(partial + (size_t)(c0 + u) * stride + kTileFloats + p) : 0.0f;
+            for (int u = 0; u < 16; ++u) v[u] = c0 + u < c_hi ? __ldcg(partial + (size_t)(c0 + u) * stride + kTileFloats + p) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
-            if (c0 + u < n_cta) acc += v[u];
+            for (int u = 0; u < 16; ++u)
+                if (c0 + u < c_hi) acc += v[u];
+        }
     }
-    red[p] = acc;
+    part[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && p < numel) red[p] = ((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -925,14 +971,13 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     const bool mma_warp = warp == 8;
     const int Kpad = a.Kpad, P = a.P;
     int* I = reinterpret_cast<int*>(S + M.f.Ints);
-    float* ajt = a.ajt_ws + (size_t)blockIdx.x * kHid * Kpad;
-    float* dajt = g.dajt_ws + (size_t)blockIdx.x * kHid * Kpad;
     float* direct = g.partial + (size_t)blockIdx.x * g.partial_stride + kTileFloats;
     uint64_t* bars = reinterpret_cast<uint64_t*>(S + T.Bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(S + T.Bars + 24);
     const uint32_t sbase = tc::smem_u32(sb);
 
-    for (int idx = tid; idx < layer_numel; idx += kT5Threads) direct[idx] = 0.0f;
+    if (LAYER == 1)     // (layer 1's partial rows were zeroed by bwd_feature_pre_kernel, which already added feature_mlp's gradients)
+        for (int idx = tid; idx < layer_numel; idx += kT5Threads) direct[idx] = 0.0f;
     stage_packs<LAYER>(S, M.f, a.params);
     if (tid < 16) S[T.B3 + tid] = 0.0f;
     if (tid == 0) reinterpret_cast<int*>(S + M.Pl)[0] = 0;
@@ -940,14 +985,17 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     if (tid == 0) {
         for (int q = 0; q < 4; ++q) { tc::mbar_init(bars + q, kT5Compute); tc::mbar_init(bars + 4 + q, 1); }
         tc::mbar_init(bars + 8, 1);
+        tc::mbar_init(bars + 9, 1);
         tc::mbar_fence_init();
     }
     tc::fence_before_thread_sync();
     __syncthreads();
     tc::fence_after_thread_sync();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const float gs = __ldg(x.scale), inv_gs = __ldg(x.scale + 1);
+    // gradient-like operands (dout, dpre, dm1) are scaled by the power of two s that brings the largest upstream gradient into [1, 2)
+    const float gs = t5_scale_from_max(__uint_as_float(__ldg(x.max_bits))), inv_gs = 1.0f / gs;
     uint32_t np = 0;          // attention-carrying passes of this CTA so far (mbarrier phase, accumulate flag)
+    uint32_t nrec = 0;        // records loaded so far (mbarrier phase)
     bool image_loaded = false;
 #ifdef PMHC_T5_STAMPS
     long long st_acc[6] = {0, 0, 0, 0, 0, 0}, st_t = clock64();
@@ -958,30 +1006,31 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         T5_STAMP(5);
-        const ComplexInfo ci = setup_complex<LAYER>(S, M.f, a, b, ajt);
+        // the complex's record (projections, geometry, lists) by one TMA bulk copy; its A_j^T stays in global memory (L2)
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)t5_record_floats(Kpad) * 4u;
+            tc::mbar_expect_tx(bars + 9, bytes);
+            tc::bulk_g2s(S + T.Rec, x.rec_all + (size_t)b * t5_record_floats(Kpad), bytes, bars + 9);
+        }
+        tc::mbar_wait_suspend(bars + 9, nrec & 1u);
+        ++nrec;
+        ComplexInfo ci;
+        ci.L = I[IN_POCKET + Kpad + 0]; ci.nv = I[IN_POCKET + Kpad + 1]; ci.nx = I[IN_POCKET + Kpad + 2]; ci.c0 = I[IN_POCKET + Kpad + 3];
+        const float* ajt = x.ajt_all + (size_t)b * kHid * Kpad;
+        float* dajt = x.dajt_all + (size_t)b * kHid * Kpad;
         T5_STAMP(0);
         const int L = ci.L;
         const int W = (L - 1) + ci.nv;
         for (int idx = tid; idx < M.grads_end - T.G; idx += kT5Threads) S[T.G + idx] = 0.0f;
         for (int idx = tid; idx < kHid * Kpad; idx += kT5Threads) dajt[idx] = 0.0f;
-        if (LAYER == 0)
-            for (int idx = tid; idx < kN * kHid; idx += kT5Threads) S[M.f.Msum + idx] = g.msum[(size_t)b * kN * kHid + idx];
         __syncthreads();
-        bwd_prologue<LAYER>(S, M, g, b, I, L, W, direct, kT5Threads);
-        __syncthreads();
+        bwd_prologue<LAYER, false>(S, M, g, b, I, L, W, direct, kT5Threads);
         if (LAYER == 0) {
-            // G[i][c] = sum_k W2[k][c] dMsum[i][k]: the message-sum gradient behind message_mlp.2, added to every pair of row i
-            const float* W2 = a.params + param_offset(LAYER, MSG2_W);
-            float* w2s = S + M.BufA;                   // staged (the prologue's buffers there are done)
-#pragma unroll 8
-            for (int idx = tid; idx < kHid * kHid; idx += kT5Threads) w2s[idx] = __ldg(W2 + idx);
-            __syncthreads();
+            // dL / d(message sum) and G[i] = W2^T dMsum[i] (added to the message gradient of every pair of row i), from the node pre-kernel
+            const float* rec = x.dmsum_g + (size_t)b * 2 * kN * kHid;
             for (int idx = tid; idx < kN * kHid; idx += kT5Threads) {
-                const int i = idx >> 6, c = idx & 63;
-                float acc = 0.0f;
-#pragma unroll 16
-                for (int k = 0; k < kHid; ++k) acc = fmaf(w2s[k * kHid + c], S[M.dMsum + i * kHid + k], acc);
-                S[T.G + idx] = acc;
+                S[M.dMsum + idx] = __ldcg(rec + idx);
+                S[T.G + idx] = __ldcg(rec + kN * kHid + idx);
             }
         }
         if (!image_loaded) {
@@ -995,10 +1044,6 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
             image_loaded = true;
         }
         __syncthreads();
-        // the torsion head's per-row extras carry its folded constant
-        for (int idx = tid; idx < kN * kHid; idx += kT5Threads) S[M.f.Tt + idx] += S[T.Cvec + F_TOR * kHid + (idx & 63)];
-        __syncthreads();
-
         // ---------------- attention-carrying pairs ----------------
         T5_STAMP(1);
         const int cpp = L > 0 ? kBwdPairs / L : 1;                  // whole neighbour columns per pass
@@ -1069,23 +1114,11 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
         __syncthreads();
         T5_STAMP(3);
 
-        if (LAYER == 0) {
-            // message_mlp.2 through the message sum: dW2[k][c] += sum_i dMsum[i][k] S1[i][c], db2[k] += (16 + P) sum_i dMsum[i][k]
-            float* dW2 = direct + (param_offset(LAYER, MSG2_W) - base);
-            rmw_batched<8>(dW2, kHid * kHid, kT5Threads, [&](int idx) {
-                const int k = idx >> 6, c = idx & 63;
-                float acc = 0.0f;
-#pragma unroll
-                for (int i = 0; i < kN; ++i) acc = fmaf(S[M.dMsum + i * kHid + k], S[T.S1 + i * kHid + c], acc);
-                return acc;
-            });
-            for (int k = tid; k < kHid; k += kT5Threads) {
-                float acc = 0.0f;
-                for (int r = 0; r < L; ++r) acc += S[M.dMsum + I[IN_ROWS + r] * kHid + k];
-                direct[(param_offset(LAYER, MSG2_B) - base) + k] += (float)(kN + P) * acc;
-            }
+        // the complex's accumulators leave for the node kernel (message_mlp.0, the torsion columns, biases, layer 2's input gradients)
+        {
+            float* rec = x.acc + (size_t)b * kAccFloats;
+            for (int idx = tid; idx < kAccFloats; idx += kT5Threads) rec[idx] = S[T.S1 + idx];
         }
-        bwd_node_level<LAYER, kLdt, false>(S, M, g, b, I, dajt, direct, kT5Threads);
         __syncthreads();
         T5_STAMP(4);
     }
@@ -1162,6 +1195,163 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
                st_acc[0], st_acc[1], st_acc[2], np, st_acc[3], st_acc[4], st_acc[5]);
 #endif
     if (mma_warp) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Node kernel: everything of a complex that is per NODE, not per pair — message_mlp.0 (its node, pocket and relative-position
+// columns), torsion_mlp.0's torsion columns, the biases, layer 1's message-sum term of message_mlp.2 and layer 2's input gradients —
+// from the accumulators the pair kernel left in global memory.  Same code as the other backward kernels' node level
+// (bwd_node_level), but with 32 warps per SM instead of the pair kernel's 9: these are short shared-memory-bound products.
+// CTA c adds into row c of the per-CTA partials after the pair kernel's CTA c, so the fixed-order reduction is unchanged.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kPostThreads = 1024;
+template <int LAYER>
+__global__ void __launch_bounds__(kPostThreads, 1) bwd_node_post_kernel(BwdArgs g, const float* __restrict__ acc, float* __restrict__ dajt_all) {
+    extern __shared__ __align__(16) float S[];
+    const LayerArgs& a = g.a;
+    const PostMap T = make_post_map();
+    const BwdMap& M = T.b;
+    constexpr int base = param_offset(LAYER, 0);
+    const int tid = threadIdx.x;
+    const int Kpad = a.Kpad, P = a.P;
+    float* direct = g.partial + (size_t)blockIdx.x * g.partial_stride + kTileFloats;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        for (int idx = tid; idx < kN * kHid; idx += kPostThreads) {
+            const int i = idx >> 6, c = idx & 63;
+            float v;
+            if (LAYER == 0) v = (c < PMHC_NFEAT) ? a.feat_in[((size_t)b * kN + i) * PMHC_NFEAT + c] : (c == PMHC_NFEAT ? time_feature(a) : 0.0f);
+            else v = a.feat_in[((size_t)b * kN + i) * kHid + c];
+            S[M.f.H + i * kLdN + c] = v;
+        }
+        for (int idx = tid; idx < kN * 14; idx += kPostThreads) S[M.f.Tors + idx] = a.tors_in[(size_t)b * kN * 14 + idx];
+        const float* rec = acc + (size_t)b * kAccFloats;
+        for (int idx = tid; idx < kAccFloats; idx += kPostThreads) S[T.S1 + idx] = __ldcg(rec + idx);
+        __syncthreads();
+        if (LAYER == 0) {
+            // message_mlp.2 through the message sum: dW2[k][c] += sum_i dMsum[i][k] S1[i][c], db2[k] += (16 + P) sum_i dMsum[i][k]
+            float* dW2 = direct + (param_offset(LAYER, MSG2_W) - base);
+            rmw_batched<4>(dW2, kHid * kHid, kPostThreads, [&](int idx) {
+                const int k = idx >> 6, c = idx & 63;
+                float sum = 0.0f;
+#pragma unroll
+                for (int i = 0; i < kN; ++i) sum = fmaf(S[M.dMsum + i * kHid + k], S[T.S1 + i * kHid + c], sum);
+                return sum;
+            });
+            for (int k = tid; k < kHid; k += kPostThreads) {
+                float sum = 0.0f;
+                for (int i = 0; i < kN; ++i) sum += S[M.dMsum + i * kHid + k];      // (rows that are not real hold zeros)
+                direct[(param_offset(LAYER, MSG2_B) - base) + k] += (float)(kN + P) * sum;
+            }
+        }
+        bwd_node_level<LAYER, kLdt, false>(S, M, g, b, nullptr, dajt_all + (size_t)b * kHid * Kpad, direct, kPostThreads);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Layer 1's node pre-kernel: the node feature MLP backward (model.py:151, :407) of every complex at 32 warps per SM — zeroes the
+// per-CTA partial rows of the layer, adds feature_mlp.{0,2}'s gradients to them, and leaves dL / d(message sum) and W2^T of it in
+// global memory for the pair kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+struct PreMap {
+    BwdMap b;
+    int W2s, G, total_bytes;
+};
+__host__ __device__ inline PreMap make_pre_map() {
+    PreMap t;
+    BwdMap& m = t.b;
+    int o = 0;
+    m.BufA = o;     o += 2 * kN * kLdN + kHid * (kH1 + kHid);     // hid, dO, feature_mlp.0.weight
+    o = (o + 3) & ~3;
+    m.BufB = o;     o += kN * kLdN + kHid * kHid;                 // dhid, feature_mlp.2.weight
+    o = (o + 3) & ~3;
+    m.f.H = o;      o += kN * kLdN;
+    o = (o + 3) & ~3;
+    m.f.Msum = o;   o += kN * kHid;
+    m.dMsum = o;    o += kN * kHid;
+    t.G = o;        o += kN * kHid;
+    t.W2s = o;      o += kHid * kHid;
+    m.f.Ints = o;   o += 64;
+    m.total_floats = o;
+    t.total_bytes = o * 4;
+    return t;
+}
+__global__ void __launch_bounds__(kPostThreads, 1) bwd_feature_pre_kernel(BwdArgs g, float* __restrict__ dmsum_g) {
+    extern __shared__ __align__(16) float S[];
+    const LayerArgs& a = g.a;
+    const PreMap T = make_pre_map();
+    const BwdMap& M = T.b;
+    constexpr int base = param_offset(0, 0);
+    constexpr int layer_numel = param_offset(1, 0) - base;
+    const int tid = threadIdx.x, lane = tid & 31;
+    int* I = reinterpret_cast<int*>(S + M.f.Ints);
+    float* direct = g.partial + (size_t)blockIdx.x * g.partial_stride + kTileFloats;
+    for (int idx = tid; idx < layer_numel; idx += kPostThreads) direct[idx] = 0.0f;
+    const float* W2 = a.params + param_offset(0, MSG2_W);
+    for (int idx = tid; idx < kHid * kHid; idx += kPostThreads) S[T.W2s + idx] = __ldg(W2 + idx);
+    __syncthreads();
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        if (tid < 32) {
+            const bool real = lane < kN && a.mask[(size_t)b * kN + lane] != 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, real);
+            if (real) I[IN_ROWS + __popc(bal & ((1u << lane) - 1u))] = lane;
+            if (lane == 0) I[IN_PEPX] = __popc(bal);
+        }
+        for (int idx = tid; idx < kN * kHid; idx += kPostThreads) {
+            const int i = idx >> 6, c = idx & 63;
+            S[M.f.H + i * kLdN + c] = (c < PMHC_NFEAT) ? a.feat_in[((size_t)b * kN + i) * PMHC_NFEAT + c] : (c == PMHC_NFEAT ? time_feature(a) : 0.0f);
+            S[M.f.Msum + idx] = g.msum[(size_t)b * kN * kHid + idx];
+            S[M.dMsum + idx] = 0.0f;
+        }
+        __syncthreads();
+        const int L = I[IN_PEPX];
+        bwd_feature_mlp(S, M, g, b, I, L, direct, kPostThreads, /*weights_staged=*/b != (int)blockIdx.x);
+        __syncthreads();
+        float* rec = dmsum_g + (size_t)b * 2 * kN * kHid;
+        for (int idx = tid; idx < kN * kHid; idx += kPostThreads) {
+            const int i = idx >> 6, c = idx & 63;
+            float sum = 0.0f;
+#pragma unroll 16
+            for (int k = 0; k < kHid; ++k) sum = fmaf(S[T.W2s + k * kHid + c], S[M.dMsum + i * kHid + k], sum);
+            rec[idx] = S[M.dMsum + idx];
+            rec[kN * kHid + idx] = sum;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Setup pre-kernel: per complex, the per-node projections of message_mlp.0 (A_i with the bias, A_j^T for peptide and pocket slots),
+// T_t = torsion_mlp.0's torsion columns applied to the row's torsions (+ the head's folded constant), geometry and the row /
+// neighbour lists — setup_complex() of the other kernels, run here with one CTA per complex (several per SM) instead of serially
+// inside the persistent pair kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline SmemMap make_setup_map(int Kpad, int P, int H) {
+    SmemMap m;
+    int o = 0;
+    m.W2T = m.WhT = m.We = m.PkAtt = m.PkRotQ = m.PkRot2 = m.PkMisc = m.PkTor2 = m.Scal = m.Out = -1;
+    const int s1 = ((P * 23 + 3) & ~3) + kHid * 23, s2 = kHid * (2 * H + 1) + kHid * 15;
+    m.Scr = o;      o += ((s1 > s2 ? s1 : s2) + 3) & ~3;
+    m.Msum = o;     o += kN * kHid;
+    m.H = o;        o += kN * kLdN;
+    o = (o + 3) & ~3;
+    o = t5_layout_record(o, m, Kpad);
+    m.total_floats = o;
+    return m;
+}
+template <int LAYER>
+__global__ void __launch_bounds__(256) bwd_setup_pre_kernel(LayerArgs a, float* __restrict__ ajt_all, float* __restrict__ rec_all,
+                                                            const uint8_t* __restrict__ wimg) {
+    extern __shared__ __align__(16) float S[];
+    const SmemMap M = make_setup_map(a.Kpad, a.P, layer_H(LAYER));
+    const int b = blockIdx.x;
+    setup_complex<LAYER>(S, M, a, b, ajt_all + (size_t)b * kHid * a.Kpad);
+    const float* cvec_tor = reinterpret_cast<const float*>(wimg + 4 * 8192) + F_TOR * kHid;
+    for (int idx = threadIdx.x; idx < kN * kHid; idx += 256) S[M.Tt + idx] += __ldg(cvec_tor + (idx & 63));
+    __syncthreads();
+    const int n = t5_record_floats(a.Kpad);
+    float* rec = rec_all + (size_t)b * n;
+    for (int idx = threadIdx.x; idx < n; idx += 256) rec[idx] = S[M.Ai + idx];
 }
 
 }  // namespace pmhc
