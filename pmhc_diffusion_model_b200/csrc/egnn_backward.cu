@@ -1894,7 +1894,7 @@ int launch_layer_backward_t5(const BwdArgs& g, const BwdWorkspace& w, int n_cta,
             PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(setup pre-kernel): %s", cudaGetErrorString(e));
             setup_configured.mark();
         }
-        bwd_setup_pre_kernel<LAYER><<<g.a.B, 256, sbytes, stream>>>(g.a, w.ajt_all, w.rec_all, w.wimg + (size_t)LAYER * kFoldImageBytes);
+        bwd_setup_pre_kernel<LAYER><<<g.a.B, kSetupThreads, sbytes, stream>>>(g.a, w.ajt_all, w.rec_all, w.wimg + (size_t)LAYER * kFoldImageBytes);
         PMHC_CHECK_LAUNCH("bwd_setup_pre");
     }
     T5Args x{w.wimg + (size_t)LAYER * kFoldImageBytes, max_bits, w.acc, w.dajt_all, w.ajt_all, w.rec_all, w.dmsum_g};
@@ -1915,7 +1915,7 @@ int launch_layer_backward_t5(const BwdArgs& g, const BwdWorkspace& w, int n_cta,
     }
     reduce_partials_to_kernel<<<(numel + 63) / 64, dim3(64, 4), 0, stream>>>(g.partial, g.partial_stride, n_cta, numel, w.red);
     PMHC_CHECK_LAUNCH("reduce_partials_to");
-    bwd_unfold_kernel<LAYER><<<(numel + 255) / 256, 256, 0, stream>>>(g.a.params, w.red, grad);
+    bwd_unfold_kernel<LAYER><<<(numel + 255) / 256 + 33, 256, 0, stream>>>(g.a.params, w.red, grad);
     PMHC_CHECK_LAUNCH("bwd_unfold");
     return 0;
 }

@@ -217,65 +217,85 @@ __device__ __forceinline__ float t5_scale_from_max(float mx) {
 
 // After the fixed-order reduction of the per-CTA partials into `red` (parameter layout of the layer, the head first-layer message
 // columns holding dF_h): the chain rule through the folded weights, added into the caller's gradient.
+//   dW_h[n][k] = sum_c dF_h[n][c] W2[k][c] + db_h[n] b2[k],   dW2[k][c] += sum_h sum_n W_h[n][k] dF_h[n][c],   db2[k] += sum_h sum_n W_h[n][k] db_h[n]
+// Grid: ceil(numel / 256) pass-through CTAs (every other parameter: grad += red), then 16 CTAs for the head matrices (head x 16 rows),
+// 16 for message_mlp.2.weight (4 rows each) and one for its bias; the products read their operands from shared memory.
 template <int LAYER>
 __global__ void __launch_bounds__(256) bwd_unfold_kernel(const float* __restrict__ params, const float* __restrict__ red, float* __restrict__ grad) {
     constexpr int base = param_offset(LAYER, 0);
     constexpr int numel = param_offset(LAYER + 1, 0) - base;
-    const int p = blockIdx.x * 256 + threadIdx.x;
-    // message_mlp.2.weight staged with a padded row (the head products walk it down a column)
-    __shared__ float sW2[kHid * (kHid + 1)];
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < kHid * kHid; idx += 256) sW2[(idx >> 6) * (kHid + 1) + (idx & 63)] = __ldg(params + param_offset(LAYER, MSG2_W) + idx);
-    __syncthreads();
-    if (p >= numel) return;
-    const int q = p + base;
-    const float* b2 = params + param_offset(LAYER, MSG2_B);
+    constexpr int n_pass = (numel + 255) / 256;
     constexpr int wid[4] = {ROT0_W, TOR0_W, TRN0_W, ATT0_W};
     constexpr int bid[4] = {ROT0_B, TOR0_B, TRN0_B, ATT0_B};
     constexpr int lds[4] = {68, 78, 64, 66};
-    float v = red[p];
-    bool done = false;
+    constexpr int oW2 = param_offset(LAYER, MSG2_W), oB2 = param_offset(LAYER, MSG2_B);
+    __shared__ float sA[kHid * (kHid + 1)];
+    __shared__ float sB[kHid * (kHid + 1)];
+    const int tid = threadIdx.x;
+    if ((int)blockIdx.x < n_pass) {
+        const int p = blockIdx.x * 256 + tid;
+        if (p >= numel) return;
+        const int q = p + base;
+        bool folded = (q >= oW2 && q < oW2 + kHid * kHid) || (q >= oB2 && q < oB2 + kHid);
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-        const int o = param_offset(LAYER, wid[h]);
-        if (!done && q >= o && q < o + kHid * lds[h]) {
-            const int n = (q - o) / lds[h], k = (q - o) - n * lds[h];
-            if (k < kHid) {
-                // dW_h[n][k] = sum_c dF_h[n][c] W2[k][c] + db_h[n] b2[k]
-                const float* dF = red + (o - base) + n * lds[h];
-                float acc = red[param_offset(LAYER, bid[h]) - base + n] * b2[k];
+        for (int h = 0; h < 4; ++h) {
+            const int o = param_offset(LAYER, wid[h]);
+            if (q >= o && q < o + kHid * lds[h] && (q - o) % lds[h] < kHid) folded = true;
+        }
+        if (!folded) grad[q] += red[p];
+        return;
+    }
+    const int job = blockIdx.x - n_pass;
+    if (job < 16) {
+        // head h, rows n0 .. n0 + 15: sA = W2 [k][c] (padded), sB = dF_h rows
+        const int h = job >> 2, n0 = (job & 3) * 16;
+        const int ow = h == 0 ? param_offset(LAYER, ROT0_W) : h == 1 ? param_offset(LAYER, TOR0_W) : h == 2 ? param_offset(LAYER, TRN0_W) : param_offset(LAYER, ATT0_W);
+        const int ob = h == 0 ? param_offset(LAYER, ROT0_B) : h == 1 ? param_offset(LAYER, TOR0_B) : h == 2 ? param_offset(LAYER, TRN0_B) : param_offset(LAYER, ATT0_B);
+        const int ld = h == 0 ? 68 : h == 1 ? 78 : h == 2 ? 64 : 66;
+#pragma unroll 4
+        for (int idx = tid; idx < kHid * kHid; idx += 256) sA[(idx >> 6) * (kHid + 1) + (idx & 63)] = __ldg(params + oW2 + idx);
+        for (int idx = tid; idx < 16 * kHid; idx += 256) sB[(idx >> 6) * (kHid + 1) + (idx & 63)] = __ldcg(red + (ow - base) + (n0 + (idx >> 6)) * ld + (idx & 63));
+        __syncthreads();
+        for (int idx = tid; idx < 16 * kHid; idx += 256) {
+            const int nl = idx >> 6, k = idx & 63;
+            float acc = __ldcg(red + (ob - base) + n0 + nl) * __ldg(params + oB2 + k);
 #pragma unroll 16
-                for (int c = 0; c < kHid; ++c) acc = fmaf(__ldg(dF + c), sW2[k * (kHid + 1) + c], acc);
-                v = acc;
-            }
-            done = true;
+            for (int c = 0; c < kHid; ++c) acc = fmaf(sB[nl * (kHid + 1) + c], sA[k * (kHid + 1) + c], acc);
+            grad[ow + (n0 + nl) * ld + k] += acc;
         }
-    }
-    if (!done && q >= param_offset(LAYER, MSG2_W) && q < param_offset(LAYER, MSG2_W) + kHid * kHid) {
-        // dW2[k][c] += sum_h sum_n W_h[n][k] dF_h[n][c]: the four heads' chains run interleaved (64 loads in flight per batch of 8 n)
-        const int k = (q - param_offset(LAYER, MSG2_W)) >> 6, c = (q - param_offset(LAYER, MSG2_W)) & 63;
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 8
-        for (int n = 0; n < kHid; ++n) {
-#pragma unroll
-            for (int h = 0; h < 4; ++h)
-                acc[h] = fmaf(__ldg(params + param_offset(LAYER, wid[h]) + n * lds[h] + k), __ldg(red + (param_offset(LAYER, wid[h]) - base) + n * lds[h] + c), acc[h]);
+    } else if (job < 32) {
+        // message_mlp.2.weight rows k0 .. k0 + 3: per head, sA = dF_h [n][c], sB = W_h[n][k0 .. k0 + 3]
+        const int k0 = (job - 16) * 4;
+        const int kk = tid >> 6, c = tid & 63;
+        float acc = __ldcg(red + (oW2 - base) + (k0 + kk) * kHid + c);
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+            const int ow = h == 0 ? param_offset(LAYER, ROT0_W) : h == 1 ? param_offset(LAYER, TOR0_W) : h == 2 ? param_offset(LAYER, TRN0_W) : param_offset(LAYER, ATT0_W);
+            const int ld = h == 0 ? 68 : h == 1 ? 78 : h == 2 ? 64 : 66;
+            __syncthreads();
+#pragma unroll 4
+            for (int idx = tid; idx < kHid * kHid; idx += 256) sA[idx] = __ldcg(red + (ow - base) + (idx >> 6) * ld + (idx & 63));
+            sB[tid] = __ldg(params + ow + (tid >> 2) * ld + k0 + (tid & 3));
+            __syncthreads();
+            float part = 0.0f;
+#pragma unroll 16
+            for (int n = 0; n < kHid; ++n) part = fmaf(sB[n * 4 + kk], sA[n * kHid + c], part);
+            acc += part;
         }
-        v += ((acc[0] + acc[1]) + acc[2]) + acc[3];
-        done = true;
+        grad[oW2 + (k0 + kk) * kHid + c] += acc;
+    } else {
+        // message_mlp.2.bias: thread (h, k) forms sum_n W_h[n][k] db_h[n], the four heads are added in order
+        const int h = tid >> 6, k = tid & 63;
+        const int ow = h == 0 ? param_offset(LAYER, ROT0_W) : h == 1 ? param_offset(LAYER, TOR0_W) : h == 2 ? param_offset(LAYER, TRN0_W) : param_offset(LAYER, ATT0_W);
+        const int ob = h == 0 ? param_offset(LAYER, ROT0_B) : h == 1 ? param_offset(LAYER, TOR0_B) : h == 2 ? param_offset(LAYER, TRN0_B) : param_offset(LAYER, ATT0_B);
+        const int ld = h == 0 ? 68 : h == 1 ? 78 : h == 2 ? 64 : 66;
+        float part = 0.0f;
+#pragma unroll 16
+        for (int n = 0; n < kHid; ++n) part = fmaf(__ldg(params + ow + n * ld + k), __ldcg(red + (ob - base) + n), part);
+        sA[tid] = part;
+        __syncthreads();
+        if (tid < kHid) grad[oB2 + tid] += __ldcg(red + (oB2 - base) + tid) + (((sA[tid] + sA[64 + tid]) + sA[128 + tid]) + sA[192 + tid]);
     }
-    if (!done && q >= param_offset(LAYER, MSG2_B) && q < param_offset(LAYER, MSG2_B) + kHid) {
-        const int k = q - param_offset(LAYER, MSG2_B);
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 8
-        for (int n = 0; n < kHid; ++n) {
-#pragma unroll
-            for (int h = 0; h < 4; ++h)
-                acc[h] = fmaf(__ldg(params + param_offset(LAYER, wid[h]) + n * lds[h] + k), __ldg(red + (param_offset(LAYER, bid[h]) - base) + n), acc[h]);
-        }
-        v += ((acc[0] + acc[1]) + acc[2]) + acc[3];
-    }
-    grad[q] += v;
 }
 
 // partial -> red (plain store).  blockDim = (64, 4): the CTA rows are split in four contiguous groups summed by four threads of a
@@ -1339,19 +1359,20 @@ __host__ __device__ inline SmemMap make_setup_map(int Kpad, int P, int H) {
     m.total_floats = o;
     return m;
 }
+constexpr int kSetupThreads = 512;
 template <int LAYER>
-__global__ void __launch_bounds__(256) bwd_setup_pre_kernel(LayerArgs a, float* __restrict__ ajt_all, float* __restrict__ rec_all,
+__global__ void __launch_bounds__(kSetupThreads) bwd_setup_pre_kernel(LayerArgs a, float* __restrict__ ajt_all, float* __restrict__ rec_all,
                                                             const uint8_t* __restrict__ wimg) {
     extern __shared__ __align__(16) float S[];
     const SmemMap M = make_setup_map(a.Kpad, a.P, layer_H(LAYER));
     const int b = blockIdx.x;
     setup_complex<LAYER>(S, M, a, b, ajt_all + (size_t)b * kHid * a.Kpad);
     const float* cvec_tor = reinterpret_cast<const float*>(wimg + 4 * 8192) + F_TOR * kHid;
-    for (int idx = threadIdx.x; idx < kN * kHid; idx += 256) S[M.Tt + idx] += __ldg(cvec_tor + (idx & 63));
+    for (int idx = threadIdx.x; idx < kN * kHid; idx += kSetupThreads) S[M.Tt + idx] += __ldg(cvec_tor + (idx & 63));
     __syncthreads();
     const int n = t5_record_floats(a.Kpad);
     float* rec = rec_all + (size_t)b * n;
-    for (int idx = threadIdx.x; idx < n; idx += 256) rec[idx] = S[M.Ai + idx];
+    for (int idx = threadIdx.x; idx < n; idx += kSetupThreads) rec[idx] = S[M.Ai + idx];
 }
 
 }  // namespace pmhc
