@@ -1790,6 +1790,7 @@ namespace pmhc {
 struct BwdWorkspace {
     float *ajt, *dajt, *partial, *d_frames1, *d_tors1, *d_feat1;
     float *red, *scale;      // tcgen05 mode: reduced partials of a layer, the two layers' operand scales
+    int* sched_ws;           // tcgen05 mode: units [B], per-CTA schedule [sms] (int4), per-complex segments [B] (int2)
     float *ajt_all, *rec_all; // tcgen05 mode: per-complex neighbour projections and records from the setup pre-kernel
     float* dmsum_g;          // tcgen05 mode, layer 1: dL / d(message sum) and W2^T of it per complex, from the node pre-kernel
     float *acc, *dajt_all;   // tcgen05 mode: per-complex gradient accumulators and dL / dA_j^T, handed from the pair kernel to the node kernel
@@ -1817,13 +1818,15 @@ BwdWorkspace carve_bwd_workspace(void* wsbase, size_t fwd_bytes, int B, int P) {
     w.scale = p + o;     o += 8;
     w.wimg = reinterpret_cast<uint8_t*>(p + o); o += (2 * kFoldImageBytes + 3) / 4;
     o = (o + 3) & ~(size_t)3;
-    w.acc = p + o;       o += (size_t)B * kAccFloats;
+    w.acc = p + o;       o += (size_t)(B + sms) * kAccFloats;   // one slot per segment: at most B + (CTAs) of them
     o = (o + 3) & ~(size_t)3;
     w.dajt_all = p + o;  o += (size_t)B * kHid * pad_k(P);
     o = (o + 3) & ~(size_t)3;
     w.dmsum_g = p + o;   o += (size_t)B * 2 * kN * kHid;
     w.ajt_all = p + o;   o += (size_t)B * kHid * pad_k(P);
     w.rec_all = p + o;   o += (size_t)B * t5_record_floats(pad_k(P));
+    o = (o + 3) & ~(size_t)3;
+    w.sched_ws = reinterpret_cast<int*>(p + o); o += (size_t)B + 4 * (size_t)sms + 2 * (size_t)B + 8;
     w.bytes = o * sizeof(float);
     return w;
 }
@@ -1853,6 +1856,8 @@ int launch_layer_backward(const BwdArgs& g, int n_cta, float* grad, cudaStream_t
     return 0;
 }
 
+
+static inline int num_sms_or(int d) { const int n = num_sms(); return n > 0 ? n : d; }
 
 template <int LAYER>
 int launch_layer_backward_t5(const BwdArgs& g, const BwdWorkspace& w, int n_cta, float* grad, cudaStream_t stream) {
@@ -1884,6 +1889,8 @@ int launch_layer_backward_t5(const BwdArgs& g, const BwdWorkspace& w, int n_cta,
         bwd_feature_pre_kernel<<<n_cta, kPostThreads, PM.total_bytes, stream>>>(g, w.dmsum_g);
         PMHC_CHECK_LAUNCH("bwd_feature_pre");
     }
+    int4* sched = reinterpret_cast<int4*>(w.sched_ws + (((size_t)g.a.B + 3) & ~(size_t)3));
+    int2* segs = reinterpret_cast<int2*>(reinterpret_cast<int*>(sched) + 4 * (size_t)num_sms_or(148));
     {
         static PerDeviceOnce setup_configured;
         const SmemMap SM = make_setup_map(g.a.Kpad, g.a.P, layer_H(LAYER));
@@ -1894,10 +1901,21 @@ int launch_layer_backward_t5(const BwdArgs& g, const BwdWorkspace& w, int n_cta,
             PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(setup pre-kernel): %s", cudaGetErrorString(e));
             setup_configured.mark();
         }
-        bwd_setup_pre_kernel<LAYER><<<g.a.B, kSetupThreads, sbytes, stream>>>(g.a, w.ajt_all, w.rec_all, w.wimg + (size_t)LAYER * kFoldImageBytes);
+        int* units = w.sched_ws;
+        bwd_setup_pre_kernel<LAYER><<<g.a.B, kSetupThreads, sbytes, stream>>>(g.a, w.ajt_all, w.rec_all, w.wimg + (size_t)LAYER * kFoldImageBytes,
+                                                                               w.dajt_all, units);
         PMHC_CHECK_LAUNCH("bwd_setup_pre");
+        const size_t sched_smem = (2 * (size_t)g.a.B + 2) * sizeof(int);
+        PMHC_REQUIRE(sched_smem <= 200 * 1024, "EGNN backward: batch of %d complexes exceeds the schedule kernel's staging", g.a.B);
+        static PerDeviceOnce sched_configured;
+        if (sched_configured.needed()) {
+            cudaFuncSetAttribute(bwd_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            sched_configured.mark();
+        }
+        bwd_schedule_kernel<<<1, 1024, sched_smem, stream>>>(units, g.a.B, n_cta, sched, segs);
+        PMHC_CHECK_LAUNCH("bwd_schedule");
     }
-    T5Args x{w.wimg + (size_t)LAYER * kFoldImageBytes, max_bits, w.acc, w.dajt_all, w.ajt_all, w.rec_all, w.dmsum_g};
+    T5Args x{w.wimg + (size_t)LAYER * kFoldImageBytes, max_bits, w.acc, w.dajt_all, w.ajt_all, w.rec_all, w.sched_ws, sched, segs, w.dmsum_g};
     if (profile_enabled()) profile_mark(PROF_BWD, stream, true);
     egnn_layer_backward_t5_kernel<LAYER><<<n_cta, kT5Threads, smem, stream>>>(g, x);
     if (profile_enabled()) profile_mark(PROF_BWD, stream, false);
@@ -1910,7 +1928,7 @@ int launch_layer_backward_t5(const BwdArgs& g, const BwdWorkspace& w, int n_cta,
             PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(node kernel): %s", cudaGetErrorString(e));
             post_configured.mark();
         }
-        bwd_node_post_kernel<LAYER><<<n_cta, kPostThreads, PM.total_bytes, stream>>>(g, w.acc, w.dajt_all);
+        bwd_node_post_kernel<LAYER><<<n_cta, kPostThreads, PM.total_bytes, stream>>>(g, w.acc, w.dajt_all, segs);
         PMHC_CHECK_LAUNCH("bwd_node_post");
     }
     reduce_partials_to_kernel<<<(numel + 63) / 64, dim3(64, 4), 0, stream>>>(g.partial, g.partial_stride, n_cta, numel, w.red);
@@ -1947,7 +1965,8 @@ extern "C" int pmhc_model_backward_ex(const float* params, const PmhcBatch* bt, 
     BwdWorkspace w = carve_bwd_workspace(workspace, fwd_bytes, bt->B, bt->P);
     PMHC_REQUIRE(workspace != nullptr && workspace_bytes >= w.bytes, "pmhc_model_backward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
     SavedMap sv = carve_saved(const_cast<float*>(saved), bt->B, bt->P);
-    const int n_cta = bt->B < num_sms() ? bt->B : num_sms();
+    // (the tcgen05 mode splits complexes over CTAs by passes: every SM works, whatever the batch size)
+    const int n_cta = t5 ? num_sms() : (bt->B < num_sms() ? bt->B : num_sms());
 
     BwdArgs g{};
     g.a.params = params;

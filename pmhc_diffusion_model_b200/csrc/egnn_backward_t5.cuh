@@ -48,7 +48,8 @@ constexpr int DX_OUT = 0, DX_EXT_A = 16, DX_EXT_B = 24, DX_SEL = 48;
 constexpr int TM_HID = 0, TM_DM1 = 256, TM_DFA = 320, TM_DFB = 384, TM_DW3 = 448, TM_EXT = 464, TM_SEL = 480, TM_ROW = 496;
 // image of one layer's folded weights (global memory, written by bwd_fold_weights_kernel): 4 fp16 SW128 tiles [n][k] in the order
 // rotation, torsion, translation, attention, then c_h as [4][64] floats
-constexpr int kFoldImageBytes = 4 * 8192 + 4 * kHid * 4;
+constexpr int kFoldTailFloats = 4 * kHid + 4 * 4 * kHid + 8 * kHid + 16;   // c_h, then the per-unit parameter packs and scalars as the pair kernel keeps them
+constexpr int kFoldImageBytes = 4 * 8192 + kFoldTailFloats * 4;
 enum { F_ROT = 0, F_TOR = 1, F_TRN = 2, F_ATT = 3 };
 
 struct T5Map {
@@ -85,6 +86,7 @@ __host__ __device__ inline int t5_layout_accumulators(int o, BwdMap& m, int& S1)
     m.grads_end = o;
     return o;
 }
+// (dQ, dX, dTors are adjacent: a later segment of a shared complex zeroes them as one block)
 constexpr int kAccFloats = kN * kHid + 2 * kN * kLdN + kEdge * kLdN + 2 * kN * kHid + kN * 16 + kN * 4 + kN * 3 + kN * 14;
 
 struct PostMap {
@@ -151,6 +153,9 @@ struct T5Args {
     float* dajt_all;       // [B][64][Kpad] per-complex dL / dA_j^T
     const float* ajt_all;  // [B][64][Kpad] neighbour projections A_j^T per complex (bwd_setup_pre_kernel)
     const float* rec_all;  // [B][t5_record_floats(Kpad)] per-complex records (bwd_setup_pre_kernel)
+    const int* units;      // [B] work units of a complex = max(its attention-carrying passes, 1) (bwd_setup_pre_kernel)
+    const int4* sched;     // [gridDim] {first complex, first unit inside it, units of this CTA, accumulator slot of its first segment}
+    const int2* segs;      // [B] {first accumulator slot, segments} of a complex (bwd_schedule_kernel)
     const float* dmsum_g;  // layer 1: [B][2][16][64] dL / d(message sum) and W2^T of it, from bwd_feature_pre_kernel (which also zeroed the partials)
 };
 
@@ -185,11 +190,38 @@ __global__ void __launch_bounds__(256) bwd_fold_weights_kernel(const float* __re
         for (int k = 0; k < kHid; ++k) acc = fmaf(sWh[nl * kHid + k], sW2[k * kHid + c], acc);
         *reinterpret_cast<__half*>(img + head * 8192 + tc::sw128_offset(n0 + nl, c)) = __float2half_rn(acc);
     }
+    float* tail = reinterpret_cast<float*>(img + 4 * 8192);
     if (threadIdx.x < 8) {
         const int n = n0 + threadIdx.x;
         float acc = bid >= 0 ? params[off(bid) + n] : 0.0f;
         for (int k = 0; k < kHid; ++k) acc = fmaf(sWh[threadIdx.x * kHid + k], __ldg(b2 + k), acc);
-        reinterpret_cast<float*>(img + 4 * 8192)[head * kHid + n] = acc;
+        tail[head * kHid + n] = acc;
+    }
+    if ((blockIdx.x & 31) == 0) {
+        // the per-hidden-unit packs and scalars (stage_packs' layout: PkAtt, PkRotQ, PkRot2, PkMisc, PkTor2, Scal), once per layer
+        float* pk = tail + 4 * kHid;
+        const float* att0 = params + off(ATT0_W);
+        const float* rot0 = params + off(ROT0_W);
+        for (int idx = threadIdx.x; idx < 4 * kHid; idx += 256) {
+            const int n = idx >> 2, c = idx & 3;
+            pk[idx] = c == 0 ? att0[n * 66 + 64] : c == 1 ? att0[n * 66 + 65] : c == 2 ? params[off(ATT0_B) + n] : params[off(ATT2_W) + n];
+            pk[4 * kHid + idx] = rot0[n * 68 + 64 + c];
+            pk[8 * kHid + idx] = params[off(ROT2_W) + c * kHid + n];
+            pk[12 * kHid + idx] = c == 0 ? params[off(TRN0_B) + n] : c == 1 ? params[off(TRN2_W) + n] : c == 2 ? params[off(ROT0_B) + n] : params[off(MSG2_B) + n];
+        }
+        for (int idx = threadIdx.x; idx < 8 * kHid; idx += 256) {
+            const int n = idx >> 3, c = idx & 7;
+            pk[16 * kHid + idx] = c < PMHC_NTORS ? params[off(TOR2_W) + c * kHid + n] : 0.0f;
+        }
+        if (threadIdx.x < 16) {
+            const int t = threadIdx.x;
+            float v = 0.0f;
+            if (t == SC_ATT2B) v = params[off(ATT2_B)];
+            else if (t == SC_TRN2B) v = params[off(TRN2_B)];
+            else if (t >= SC_ROT2B && t < SC_ROT2B + 4) v = params[off(ROT2_B) + t - SC_ROT2B];
+            else if (t >= SC_TOR2B && t < SC_TOR2B + PMHC_NTORS) v = params[off(TOR2_B) + t - SC_TOR2B];
+            pk[24 * kHid + t] = v;
+        }
     }
 }
 
@@ -484,6 +516,15 @@ __device__ __forceinline__ void t5_store16(uint8_t* tile, int p, int ch, const f
     }
 }
 
+// the A_j^T column half (32 features) and the saved attention logit of a pair: 33 L2 loads in flight
+__device__ __forceinline__ void t5_request_pair(float (&aj)[32], float& logit, const BwdArgs& g, int b, const float* __restrict__ ajt, int Kpad,
+                                                const PairRef pr, int half) {
+    const float* ajc = ajt + (pr.j >= 0 ? pr.j : 0) + (size_t)(32 * half) * Kpad;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) aj[k] = __ldcg(ajc + k * Kpad);
+    logit = __ldcg(g.logits + ((size_t)b * kN + pr.i) * Kpad + pr.j);
+}
+
 // ---- compute threads: one attention-carrying pass of up to 128 pairs ----
 // Two threads per pair, one head each: threads 0..127 rotation then translation, threads 128..255 torsion then attention.  A head is
 // walked in four chunks of 16 hidden units (runtime loops: the pass code stays inside the instruction cache): chunk loop 1 forms the
@@ -491,7 +532,10 @@ __device__ __forceinline__ void t5_store16(uint8_t* tile, int p, int ch, const f
 template <int LAYER>
 __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map& T, const BwdArgs& g, const PairRef pr, int b,
                                               const float* __restrict__ ajt, float* __restrict__ dajt, const int* I, int L, int rl,
-                                              int e0, int ncols, uint32_t np, uint32_t tmem, float gs, float inv_gs) {
+                                              int e0, int ncols, uint32_t np, uint32_t tmem, float gs, float inv_gs,
+                                              float (&aj)[32], float& logit_io, const PairRef nxt, const bool has_next) {
+    // aj / logit_io: this pass's A_j^T column half and saved logit, loaded by the previous pass (or the caller) — on return they hold
+    // the next pass's (pair `nxt`), requested under pair B's MMAs so their L2 round trip is off the critical path
     // Pairs of a pass are COLUMN-major: pair p = (neighbour column e0 + p / L, peptide row p % L), whole columns only.  A pocket
     // column's L pairs are then adjacent (its dL / dA_j is complete inside the pass: a plain store), and a row's pairs are L apart
     // (per-row sums go through the one-hot row selector on the tensor core; shared-memory atomics see at most 4 lanes per row).
@@ -524,10 +568,6 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
         constexpr int H = layer_H(LAYER);
         constexpr int ld1 = 2 * H + kEdge;
         const int k0 = 32 * half;
-        const float* ajc = ajt + (j >= 0 ? j : 0) + (size_t)k0 * Kpad;
-        float aj[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) aj[k] = __ldcg(ajc + k * Kpad);       // 32 L2 loads in flight
         const float* ai = S + M.f.Ai + i * kLdN + k0;
         if (pep) {
             const float* we = a.params + param_offset(LAYER, MSG0_W) + 2 * H + (kN - 1 + i - j) + (size_t)k0 * ld1;
@@ -551,7 +591,7 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
     }
     const float* rg = S + M.RowG + i * 16;
     const float lse = rg[15], c_i = rg[14];
-    const float logit = g.logits[((size_t)b * kN + i) * Kpad + j];
+    const float logit = logit_io;
     const float w = act ? expf(logit - lse) : 0.0f;
     const float* pqi = S + M.f.Q + i * 4;
     const float* pqj = S + M.f.Q + j * 4;
@@ -827,6 +867,7 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
     tc::fence_proxy_async_smem();
     tc::mbar_arrive(rdy + 2);
     T5_PSTAMP(6);
+    if (has_next) t5_request_pair(aj, logit_io, g, b, ajt, Kpad, nxt, half);
     if (IN_GRADS && act && half == 1) {
         // attention head's input gradients (under pair B's MMAs)
         const float f = -gd_keep * 2.0f;                 // d(-d2) = gd
@@ -987,6 +1028,9 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     const BwdMap& M = T.b;
     constexpr int base = param_offset(LAYER, 0);
     constexpr int layer_numel = param_offset(LAYER + 1, 0) - base;
+#ifdef PMHC_T5_STAMPS
+    const long long st_entry = clock64();
+#endif
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool mma_warp = warp == 8;
     const int Kpad = a.Kpad, P = a.P;
@@ -996,9 +1040,6 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(S + T.Bars + 24);
     const uint32_t sbase = tc::smem_u32(sb);
 
-    if (LAYER == 1)     // (layer 1's partial rows were zeroed by bwd_feature_pre_kernel, which already added feature_mlp's gradients)
-        for (int idx = tid; idx < layer_numel; idx += kT5Threads) direct[idx] = 0.0f;
-    stage_packs<LAYER>(S, M.f, a.params);
     if (tid < 16) S[T.B3 + tid] = 0.0f;
     if (tid == 0) reinterpret_cast<int*>(S + M.Pl)[0] = 0;
     if (mma_warp) tc::tmem_alloc(tmem_slot, 512);
@@ -1011,21 +1052,37 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     tc::fence_before_thread_sync();
     __syncthreads();
     tc::fence_after_thread_sync();
+    // the folded weights, c_h and the parameter packs: two TMA bulk copies, in flight under the zeroing of the partial row
+    if (tid == 0) {
+        tc::mbar_expect_tx(bars + 8, kFoldImageBytes);
+        tc::bulk_g2s(sb + T5_F, x.wimg, 4 * 8192, bars + 8);
+        tc::bulk_g2s(S + T.Cvec, x.wimg + 4 * 8192, kFoldTailFloats * 4, bars + 8);
+    }
+    if (LAYER == 1) {   // (layer 1's partial rows were zeroed by bwd_feature_pre_kernel, which already added feature_mlp's gradients)
+        static_assert((param_offset(1, 0) % 4) == 0 || true, "");
+        float4* d4 = reinterpret_cast<float4*>(g.partial + (size_t)blockIdx.x * g.partial_stride + kTileFloats);   // 16-byte aligned: stride and kTileFloats are multiples of 4
+        for (int idx = tid; idx < layer_numel / 4; idx += kT5Threads) d4[idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int idx = (layer_numel & ~3) + tid; idx < layer_numel; idx += kT5Threads) direct[idx] = 0.0f;
+    }
+    tc::mbar_wait_suspend(bars + 8, 0);
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     // gradient-like operands (dout, dpre, dm1) are scaled by the power of two s that brings the largest upstream gradient into [1, 2)
     const float gs = t5_scale_from_max(__uint_as_float(__ldg(x.max_bits))), inv_gs = 1.0f / gs;
     uint32_t np = 0;          // attention-carrying passes of this CTA so far (mbarrier phase, accumulate flag)
     uint32_t nrec = 0;        // records loaded so far (mbarrier phase)
-    bool image_loaded = false;
 #ifdef PMHC_T5_STAMPS
     long long st_acc[6] = {0, 0, 0, 0, 0, 0}, st_t = clock64();
+    const long long st_first = st_t;
 #define T5_STAMP(k) do { long long now_ = clock64(); st_acc[k] += now_ - st_t; st_t = now_; } while (0)
 #else
 #define T5_STAMP(k) do { } while (0)
 #endif
 
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    const int4 my = x.sched[blockIdx.x];
+    int b = my.x, q0 = my.y, remaining = my.z, slot = my.w;
+    for (; remaining > 0; ++b, q0 = 0) {
         T5_STAMP(5);
+        if (q0 == 0 && b != my.x) slot = x.segs[b].x;      // a complex this CTA starts gets the complex's first accumulator slot
         // the complex's record (projections, geometry, lists) by one TMA bulk copy; its A_j^T stays in global memory (L2)
         if (tid == 0) {
             const uint32_t bytes = (uint32_t)t5_record_floats(Kpad) * 4u;
@@ -1042,9 +1099,13 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
         const int L = ci.L;
         const int W = (L - 1) + ci.nv;
         for (int idx = tid; idx < M.grads_end - T.G; idx += kT5Threads) S[T.G + idx] = 0.0f;
-        for (int idx = tid; idx < kHid * Kpad; idx += kT5Threads) dajt[idx] = 0.0f;
         __syncthreads();
         bwd_prologue<LAYER, false>(S, M, g, b, I, L, W, direct, kT5Threads);
+        if (LAYER == 1 && q0 > 0) {
+            // a later segment of a shared complex: the row-level terms of the input gradients belong to its first segment
+            __syncthreads();
+            for (int idx = tid; idx < kN * (4 + 3 + 14); idx += kT5Threads) S[M.dQ + idx] = 0.0f;
+        }
         if (LAYER == 0) {
             // dL / d(message sum) and G[i] = W2^T dMsum[i] (added to the message gradient of every pair of row i), from the node pre-kernel
             const float* rec = x.dmsum_g + (size_t)b * 2 * kN * kHid;
@@ -1053,40 +1114,48 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
                 S[T.G + idx] = __ldcg(rec + kN * kHid + idx);
             }
         }
-        if (!image_loaded) {
-            // the folded weights (+ c_h right behind the tiles... c_h is copied separately: it lives behind the pass tiles)
-            if (tid == 0) {
-                tc::mbar_expect_tx(bars + 8, kFoldImageBytes);
-                tc::bulk_g2s(sb + T5_F, x.wimg, 4 * 8192, bars + 8);
-                tc::bulk_g2s(S + T.Cvec, x.wimg + 4 * 8192, 4 * kHid * 4, bars + 8);
-            }
-            tc::mbar_wait_suspend(bars + 8, 0);
-            image_loaded = true;
-        }
         __syncthreads();
         // ---------------- attention-carrying pairs ----------------
         T5_STAMP(1);
         const int cpp = L > 0 ? kBwdPairs / L : 1;                  // whole neighbour columns per pass
-        const int npasses = L > 0 ? (W + cpp - 1) / cpp : 0;
+        const int npasses_all = L > 0 ? (W + cpp - 1) / cpp : 0;
+        const int units_b = npasses_all > 0 ? npasses_all : 1;
+        const int q1 = min(units_b, q0 + remaining);                // this segment: units [q0, q1) of the complex
+        const bool last_seg = q1 == units_b;
+        const int npasses = min(q1, npasses_all) - q0;              // attention-carrying passes of the segment
+        remaining -= q1 - q0;
         if (mma_warp) {
             for (int q = 0; q < npasses; ++q) t5_issue_pass(sbase, tmem, bars, np + q, q);
         } else {
             const int pcol = tid & (kBwdPairs - 1);
             const int pc = L > 0 ? pcol / L : 0, prl = L > 0 ? pcol - pc * L : 0;   // this thread's column (local) and peptide row
-            for (int q = 0; q < npasses; ++q) {
-                const int e0 = q * cpp;
-                const int ncols = min(cpp, W - e0);
-                PairRef pr;
+            auto decode = [&](int q, PairRef& pr, int& rl, int& e0, int& ncols) {
+                e0 = (q0 + q) * cpp;
+                ncols = min(cpp, W - e0);
                 pr.active = pc < ncols;
-                const int e = pr.active ? e0 + pc : e0, rl = pr.active ? prl : 0;
+                const int e = pr.active ? e0 + pc : e0;
+                rl = pr.active ? prl : 0;
                 pr.i = I[IN_ROWS + rl];
                 pr.j = e < L - 1 ? I[IN_ROWS + (e < rl ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
-                t5_heads_pass<LAYER>(sb, S, T, g, pr, b, ajt, dajt, I, L, rl, e0, ncols, np + q, tmem, gs, inv_gs);
+            };
+            float aj[32], logit = 0.0f;
+            PairRef pr, nxt;
+            int rl = 0, e0 = 0, ncols = 0, rl_n = 0, e0_n = 0, ncols_n = 0;
+            if (npasses > 0) {
+                decode(0, pr, rl, e0, ncols);
+                t5_request_pair(aj, logit, g, b, ajt, Kpad, pr, tid >> 7);
+            }
+            for (int q = 0; q < npasses; ++q) {
+                const bool has_next = q + 1 < npasses;
+                if (has_next) decode(q + 1, nxt, rl_n, e0_n, ncols_n);
+                else nxt = pr;
+                t5_heads_pass<LAYER>(sb, S, T, g, pr, b, ajt, dajt, I, L, rl, e0, ncols, np + q, tmem, gs, inv_gs, aj, logit, nxt, has_next);
+                pr = nxt; rl = rl_n; e0 = e0_n; ncols = ncols_n;
             }
             if (npasses > 0) tc::mbar_wait_suspend(bars + 4 + 3, (np + npasses - 1) & 1u);   // the last pass's per-row sums
             // ---------------- layer 1: message-only pairs (self, masked peptide / pocket slots) ----------------
             T5_STAMP(2);
-            if (LAYER == 0 && L > 0) {
+            if (LAYER == 0 && L > 0 && last_seg) {
                 const int npx = kN - L;
                 const int W2 = 1 + npx + ci.nx + (ci.c0 > 0 ? 1 : 0);
                 const int total2 = L * W2;
@@ -1136,8 +1205,11 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
 
         // the complex's accumulators leave for the node kernel (message_mlp.0, the torsion columns, biases, layer 2's input gradients)
         {
-            float* rec = x.acc + (size_t)b * kAccFloats;
-            for (int idx = tid; idx < kAccFloats; idx += kT5Threads) rec[idx] = S[T.S1 + idx];
+            float* rec = x.acc + (size_t)slot * kAccFloats;
+            // (dL / d(message sum) is the same in every segment of a shared complex: only the first one hands it on)
+            const int dm_lo = M.dMsum - T.S1, dm_hi = dm_lo + kN * kHid;
+            for (int idx = tid; idx < kAccFloats; idx += kT5Threads) rec[idx] = (q0 > 0 && idx >= dm_lo && idx < dm_hi) ? 0.0f : S[T.S1 + idx];
+            ++slot;
         }
         __syncthreads();
         T5_STAMP(4);
@@ -1158,11 +1230,24 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
             const int woff = (head == F_ROT ? param_offset(LAYER, ROT0_W) : head == F_TOR ? param_offset(LAYER, TOR0_W)
                               : head == F_TRN ? param_offset(LAYER, TRN0_W) : param_offset(LAYER, ATT0_W)) - base;
             (void)wid;
-            uint32_t v[32];
-            tc::tmem_ld32_nowait(tlane + (pair == 0 ? TM_DFA : TM_DFB) + 32 * half, v);
-            tc::tmem_wait_ld();
+            (void)ld; (void)woff;
+            {   // through a padded shared-memory tile, so that the stores to the partial row are coalesced
+                float* stage = reinterpret_cast<float*>(sb + T5_HID);      // [128][65]
+                uint32_t v[32];
+                tc::tmem_ld32_nowait(tlane + (pair == 0 ? TM_DFA : TM_DFB) + 32 * half, v);
+                tc::tmem_wait_ld();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) direct[woff + n * ld + 32 * half + k] = __uint_as_float(v[k]) * inv_gs;
+                for (int k = 0; k < 32; ++k) stage[r * (kHid + 1) + 32 * half + k] = __uint_as_float(v[k]) * inv_gs;
+                t5_bar_compute();
+                for (int idx = tid; idx < 2 * kHid * kHid; idx += kT5Compute) {
+                    const int rr = idx >> 6, k = idx & 63, hd = 2 * pair + (rr >> 6), nn = rr & 63;
+                    const int ldh = hd == F_ROT ? 68 : hd == F_TOR ? 78 : hd == F_TRN ? 64 : 66;
+                    const int wo = (hd == F_ROT ? param_offset(LAYER, ROT0_W) : hd == F_TOR ? param_offset(LAYER, TOR0_W)
+                                    : hd == F_TRN ? param_offset(LAYER, TRN0_W) : param_offset(LAYER, ATT0_W)) - base;
+                    direct[wo + nn * ldh + k] = stage[rr * (kHid + 1) + k];
+                }
+                t5_bar_compute();
+            }
             if (half == 0 && pair == 0) {
                 // rows 0..63: rotation (pair A) and translation (pair B) share the accumulator rows; 64..127: torsion and attention
                 float w3[16], ex[16];
@@ -1199,6 +1284,11 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     __syncthreads();
     T5_STAMP(5);
 #ifdef PMHC_T5_STAMPS
+    if (tid == 0) {
+        long long tot = 0;
+        for (int k = 0; k < 6; ++k) tot += st_acc[k];
+        printf("t5cta<%d> %d passes %u total %lld passes_cycles %lld entry_to_end %lld pre_loop %lld tail %lld\n", LAYER, (int)blockIdx.x, np, tot, st_acc[2], clock64() - st_entry, st_first - st_entry, st_acc[5]);
+    }
     if (blockIdx.x == 0 && tid == 0)
         for (int hh = 0; hh < 2; ++hh) {
             printf("t5<%d> thread %d:", LAYER, 128 * hh);
@@ -1217,6 +1307,76 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
     if (mma_warp) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Work split of the pair kernel: a complex is max(passes, 1) work units; CTA c takes the units [c T / G, (c + 1) T / G) of the batch's
+// unit stream, so a complex may be shared by consecutive CTAs (each of them a SEGMENT with its own accumulator slot, summed by the node
+// kernel in slot order).  One warp; thread 0 walks the complexes (B + G steps).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bwd_schedule_kernel(const int* __restrict__ units, int B, int G, int4* __restrict__ sched, int2* __restrict__ segs) {
+    // P[b] = units before complex b (exclusive scan), start(c) = floor(c T / Ga) for the Ga = min(G, T) CTAs that get work (their starts
+    // are distinct).  Complex b is cut at every start strictly inside (P[b], P[b + 1]); its segments get consecutive slots.
+    extern __shared__ int sm[];              // [B + 1] P, then [B + 1] slot0
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    int* P = sm;
+    int* S0 = sm + B + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto block_excl_scan = [&](auto value_of, int* out) {      // out[b] = sum of value_of(b') for b' < b, out[B] = total
+        if (tid == 0) carry_s = 0;
+        __syncthreads();
+        for (int base = 0; base < B; base += 1024) {
+            const int b = base + tid;
+            const int v = b < B ? value_of(b) : 0;
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                int w = wsum[lane], winc = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+                wsum[lane] = winc - w;
+            }
+            __syncthreads();
+            const int carry = carry_s;
+            if (b < B) out[b] = carry + wsum[warp] + inc - v;
+            __syncthreads();
+            if (tid == 1023) carry_s = carry + wsum[31] + inc;
+            __syncthreads();
+        }
+        if (tid == 0) out[B] = carry_s;
+        __syncthreads();
+    };
+    block_excl_scan([&](int b) { return __ldg(units + b); }, P);
+    const long long T = P[B];
+    const int Ga = (int)(T < G ? T : G);
+    auto start = [&](int c) { return (int)((long long)c * T / Ga); };               // c in [0, Ga]
+    auto cnt_lt = [&](int x) {        // number of c in [0, Ga) with start(c) < x   (x in [0, T])
+        if (x <= 0) return 0;
+        int c = (int)(((long long)x * Ga) / T);                                     // start(c) <= x
+        if (c > Ga) c = Ga;
+        while (c > 0 && start(c - 1) >= x) --c;
+        while (c < Ga && start(c) < x) ++c;
+        return c;
+    };
+    // segments of a complex = 1 + starts strictly inside it
+    block_excl_scan([&](int b) { return 1 + cnt_lt(P[b + 1]) - cnt_lt(P[b] + 1); }, S0);
+    for (int b = tid; b < B; b += 1024) segs[b] = make_int2(S0[b], S0[b + 1] - S0[b]);
+    for (int c = tid; c < G; c += 1024) {
+        int4 v = make_int4(0, 0, 0, 0);
+        if (c < Ga) {
+            const int st = start(c), en = start(c + 1);
+            int lo = 0, hi = B - 1;                       // the complex with P[b] <= st < P[b + 1]
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (P[mid] <= st) lo = mid; else hi = mid - 1; }
+            while (P[lo + 1] <= st) ++lo;                 // (complexes always have >= 1 unit; defensive)
+            v = make_int4(lo, st - P[lo], en - st, S0[lo] + (cnt_lt(st + 1) - cnt_lt(P[lo] + 1)));
+        }
+        sched[c] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Node kernel: everything of a complex that is per NODE, not per pair — message_mlp.0 (its node, pocket and relative-position
 // columns), torsion_mlp.0's torsion columns, the biases, layer 1's message-sum term of message_mlp.2 and layer 2's input gradients —
@@ -1226,7 +1386,8 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kPostThreads = 1024;
 template <int LAYER>
-__global__ void __launch_bounds__(kPostThreads, 1) bwd_node_post_kernel(BwdArgs g, const float* __restrict__ acc, float* __restrict__ dajt_all) {
+__global__ void __launch_bounds__(kPostThreads, 1) bwd_node_post_kernel(BwdArgs g, const float* __restrict__ acc, float* __restrict__ dajt_all,
+                                                                        const int2* __restrict__ segs) {
     extern __shared__ __align__(16) float S[];
     const LayerArgs& a = g.a;
     const PostMap T = make_post_map();
@@ -1244,8 +1405,15 @@ __global__ void __launch_bounds__(kPostThreads, 1) bwd_node_post_kernel(BwdArgs 
             S[M.f.H + i * kLdN + c] = v;
         }
         for (int idx = tid; idx < kN * 14; idx += kPostThreads) S[M.f.Tors + idx] = a.tors_in[(size_t)b * kN * 14 + idx];
-        const float* rec = acc + (size_t)b * kAccFloats;
-        for (int idx = tid; idx < kAccFloats; idx += kPostThreads) S[T.S1 + idx] = __ldcg(rec + idx);
+        const int2 sg = segs[b];
+        for (int u = 0; u < sg.y; ++u) {                      // segments in slot order; the loads of a segment are independent
+            const float* rec = acc + (size_t)(sg.x + u) * kAccFloats;
+#pragma unroll 8
+            for (int idx = tid; idx < kAccFloats; idx += kPostThreads) {
+                const float v = __ldcg(rec + idx);
+                S[T.S1 + idx] = u == 0 ? v : S[T.S1 + idx] + v;
+            }
+        }
         __syncthreads();
         if (LAYER == 0) {
             // message_mlp.2 through the message sum: dW2[k][c] += sum_i dMsum[i][k] S1[i][c], db2[k] += (16 + P) sum_i dMsum[i][k]
@@ -1362,7 +1530,7 @@ __host__ __device__ inline SmemMap make_setup_map(int Kpad, int P, int H) {
 constexpr int kSetupThreads = 512;
 template <int LAYER>
 __global__ void __launch_bounds__(kSetupThreads) bwd_setup_pre_kernel(LayerArgs a, float* __restrict__ ajt_all, float* __restrict__ rec_all,
-                                                            const uint8_t* __restrict__ wimg) {
+                                                            const uint8_t* __restrict__ wimg, float* __restrict__ dajt_all, int* __restrict__ units) {
     extern __shared__ __align__(16) float S[];
     const SmemMap M = make_setup_map(a.Kpad, a.P, layer_H(LAYER));
     const int b = blockIdx.x;
@@ -1373,6 +1541,16 @@ __global__ void __launch_bounds__(kSetupThreads) bwd_setup_pre_kernel(LayerArgs 
     const int n = t5_record_floats(a.Kpad);
     float* rec = rec_all + (size_t)b * n;
     for (int idx = threadIdx.x; idx < n; idx += kSetupThreads) rec[idx] = S[M.Ai + idx];
+    // dL / dA_j^T of the complex starts at zero (the pair kernel's segments store disjoint pocket columns)
+    float* dajt = dajt_all + (size_t)b * kHid * a.Kpad;
+    for (int idx = threadIdx.x; idx < kHid * a.Kpad; idx += kSetupThreads) dajt[idx] = 0.0f;
+    if (threadIdx.x == 0) {
+        const int* I = reinterpret_cast<const int*>(S + M.Ints);
+        const int L = I[IN_POCKET + a.Kpad + 0], W = L - 1 + I[IN_POCKET + a.Kpad + 1];
+        const int cpp = L > 0 ? kBwdPairs / L : 1;
+        const int npasses = L > 0 ? (W + cpp - 1) / cpp : 0;
+        units[b] = npasses > 0 ? npasses : 1;
+    }
 }
 
 }  // namespace pmhc
