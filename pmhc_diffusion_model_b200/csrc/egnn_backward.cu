@@ -1533,7 +1533,7 @@ __device__ __forceinline__ void bwd_prologue(float* S, const BwdMap& M, const Bw
 // Per-complex node level shared by every backward kernel: message_mlp.0, torsion_mlp.0[:, 64:78] and biases from the per-node
 // accumulators; layer 2 also writes the input gradients.  LDC = row stride of the staging tile at M.BufA; TORB = torsion_mlp.0.bias
 // from the per-row sums (false when the caller gets it from its own bias column).
-template <int LAYER, int LDC, bool TORB>
+template <int LAYER, int LDC, bool TORB, bool TILED = false>
 __device__ __forceinline__ void bwd_node_level(float* S, const BwdMap& M, const BwdArgs& g, int b, const int* I, float* __restrict__ dajt,
                                                float* __restrict__ direct, const int NT) {
     const LayerArgs& a = g.a;
@@ -1571,17 +1571,81 @@ __device__ __forceinline__ void bwd_node_level(float* S, const BwdMap& M, const 
             const float* pf = a.pocket_feat + ((size_t)b * P + p0) * PMHC_NFEAT;
             for (int idx = tid; idx < n * PMHC_NFEAT; idx += NT) stB[idx] = __ldg(pf + idx);
             __syncthreads();
-            for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += NT) {
-                const int k = idx / PMHC_NFEAT, cc = idx - k * PMHC_NFEAT;
-                float acc = scr[idx];
+            if (TILED) {
+                // register tile of 4 features x 2 pocket-feature columns over a quarter of the chunk's slots (5 shared loads per 8
+                // products instead of 16); the four quarter sums are added in order afterwards
+                float* part = stB + 128 * PMHC_NFEAT;     // [4][64 * 22]
+                for (int item = tid; item < 16 * 11 * 4; item += NT) {
+                    const int cc2 = item % 11, q = (item / 11) & 3, k4 = item / 44;
+                    const int lo = (n * q) >> 2, hi = (n * (q + 1)) >> 2;
+                    float acc[4][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};
+#pragma unroll 4
+                    for (int pp = lo; pp < hi; ++pp) {
+                        const float2 bv = *reinterpret_cast<const float2*>(stB + pp * PMHC_NFEAT + 2 * cc2);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float av = stA[(4 * k4 + u) * ldc + pp];
+                            acc[u][0] = fmaf(av, bv.x, acc[u][0]);
+                            acc[u][1] = fmaf(av, bv.y, acc[u][1]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        part[q * (kHid * PMHC_NFEAT) + (4 * k4 + u) * PMHC_NFEAT + 2 * cc2] = acc[u][0];
+                        part[q * (kHid * PMHC_NFEAT) + (4 * k4 + u) * PMHC_NFEAT + 2 * cc2 + 1] = acc[u][1];
+                    }
+                }
+                __syncthreads();
+                for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += NT)
+                    scr[idx] += ((part[idx] + part[kHid * PMHC_NFEAT + idx]) + part[2 * kHid * PMHC_NFEAT + idx]) + part[3 * kHid * PMHC_NFEAT + idx];
+            } else {
+                for (int idx = tid; idx < kHid * PMHC_NFEAT; idx += NT) {
+                    const int k = idx / PMHC_NFEAT, cc = idx - k * PMHC_NFEAT;
+                    float acc = scr[idx];
 #pragma unroll 8
-                for (int pp = 0; pp < n; ++pp) acc = fmaf(stA[k * ldc + pp], stB[pp * PMHC_NFEAT + cc], acc);
-                scr[idx] = acc;
+                    for (int pp = 0; pp < n; ++pp) acc = fmaf(stA[k * ldc + pp], stB[pp * PMHC_NFEAT + cc], acc);
+                    scr[idx] = acc;
+                }
             }
         }
         __syncthreads();
         NSTAMP(0);
         float* dW1 = direct + (param_offset(LAYER, MSG0_W) - base);
+        if (TILED) {
+            // 4 features per item: the per-node gradients as 16-byte aligned rows (one broadcast 128-bit load feeds four products)
+            float* dAiA = S + M.BufB;                // [16][64]
+            float* dAjA = dAiA + kN * kHid;          // [16][64]
+            for (int idx = tid; idx < kN * kHid; idx += NT) {
+                dAiA[idx] = S[M.dAi + (idx >> 6) * kLdN + (idx & 63)];
+                dAjA[idx] = S[M.dAjPep + (idx >> 6) * kLdN + (idx & 63)];
+            }
+            __syncthreads();
+            for (int item = tid; item < 16 * ld1; item += NT) {
+                const int k4 = item / ld1, c = item - k4 * ld1;
+                float old[4], acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) old[u] = ldcg_early(dW1 + (4 * k4 + u) * ld1 + c);
+                if (c < H || (c < 2 * H && c - H >= PMHC_NFEAT)) {
+                    const float* av = (c < H ? dAiA : dAjA) + 4 * k4;
+                    const float* hv = S + M.f.H + (c < H ? c : c - H);
+#pragma unroll
+                    for (int i = 0; i < kN; ++i) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(av + i * kHid);
+                        const float h = hv[i * kLdN];
+                        acc[0] = fmaf(a4.x, h, acc[0]); acc[1] = fmaf(a4.y, h, acc[1]);
+                        acc[2] = fmaf(a4.z, h, acc[2]); acc[3] = fmaf(a4.w, h, acc[3]);
+                    }
+                } else if (c < 2 * H) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[u] = scr[(4 * k4 + u) * PMHC_NFEAT + (c - H)];
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[u] = S[M.dWe + (c - 2 * H) * kLdN + 4 * k4 + u];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dW1[(4 * k4 + u) * ld1 + c] = old[u] + acc[u];
+            }
+        } else
         rmw_batched<8>(dW1, kHid * ld1, NT, [&](int idx) {
             const int k = idx / ld1, c = idx - k * ld1;
             float acc = 0.0f;
@@ -1650,6 +1714,33 @@ __device__ __forceinline__ void bwd_node_level(float* S, const BwdMap& M, const 
                 for (int n = 0; n < kHid; ++n) acc = fmaf(tx[n * 15 + c], S[M.dTt + i * kHid + n], acc);
                 g.d_tors_in[(size_t)b * kN * 14 + idx] = acc;
             }
+            if (TILED) {
+                // 4 nodes per item: the per-node gradients transposed ([k][16 nodes]) so that one 128-bit load covers four nodes
+                float* dAiT = S + M.BufB + 1024;     // (behind tx)
+                float* dAjT = dAiT + kN * kHid;
+                for (int idx = tid; idx < kN * kHid; idx += NT) {
+                    const int k = idx >> 4, i = idx & 15;
+                    dAiT[idx] = S[M.dAi + i * kLdN + k];
+                    dAjT[idx] = S[M.dAjPep + i * kLdN + k];
+                }
+                __syncthreads();
+                for (int item = tid; item < 4 * kHid; item += NT) {
+                    const int i4 = item >> 6, c = item & 63;
+                    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 8
+                    for (int k = 0; k < kHid; ++k) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(dAiT + k * kN + 4 * i4);
+                        const float4 b4 = *reinterpret_cast<const float4*>(dAjT + k * kN + 4 * i4);
+                        const float w0 = wq[k * LDQ + c], w1 = wq[k * LDQ + H + c];
+                        acc[0] = fmaf(a4.x, w0, acc[0]); acc[0] = fmaf(b4.x, w1, acc[0]);
+                        acc[1] = fmaf(a4.y, w0, acc[1]); acc[1] = fmaf(b4.y, w1, acc[1]);
+                        acc[2] = fmaf(a4.z, w0, acc[2]); acc[2] = fmaf(b4.z, w1, acc[2]);
+                        acc[3] = fmaf(a4.w, w0, acc[3]); acc[3] = fmaf(b4.w, w1, acc[3]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) g.d_feat_in[((size_t)b * kN + 4 * i4 + u) * kHid + c] = acc[u];
+                }
+            } else
             for (int idx = tid; idx < kN * kHid; idx += NT) {
                 int i = idx >> 6, c = idx & 63;
                 float acc = 0.0f;

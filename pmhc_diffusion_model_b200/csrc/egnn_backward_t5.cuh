@@ -1431,7 +1431,7 @@ __global__ void __launch_bounds__(kPostThreads, 1) bwd_node_post_kernel(BwdArgs 
                 direct[(param_offset(LAYER, MSG2_B) - base) + k] += (float)(kN + P) * sum;
             }
         }
-        bwd_node_level<LAYER, kLdt, false>(S, M, g, b, nullptr, dajt_all + (size_t)b * kHid * Kpad, direct, kPostThreads);
+        bwd_node_level<LAYER, kLdt, false, true>(S, M, g, b, nullptr, dajt_all + (size_t)b * kHid * Kpad, direct, kPostThreads);
         __syncthreads();
     }
 }
