@@ -474,7 +474,7 @@ def main():
         tmodel.load_state_dict(params, strict=True)
         tmodel = tmodel.to(dev)
         tdm = DiffusionModelOptimizer(T_TRAIN, tmodel, 1e-3)
-        tdm.use_graph = not args.no_graph and world == 1
+        tdm.use_graph = not args.no_graph      # N > 1: the gradient step is one graph, the two all-reduces and Adam follow it
         from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer
         trainer = DataParallelTrainer(tdm, seed=0)   # N = 1: plain optimize(); N > 1: shared t + overlapped NCCL all-reduce
         n_train = 20

@@ -2057,7 +2057,9 @@ extern "C" int pmhc_model_backward_ex(const float* params, const PmhcBatch* bt, 
     PMHC_REQUIRE(workspace != nullptr && workspace_bytes >= w.bytes, "pmhc_model_backward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
     SavedMap sv = carve_saved(const_cast<float*>(saved), bt->B, bt->P);
     // (the tcgen05 mode splits complexes over CTAs by passes: every SM works, whatever the batch size)
-    const int n_cta = t5 ? num_sms() : (bt->B < num_sms() ? bt->B : num_sms());
+    // (... and when the caller overlaps a collective with the layer-1 launch (layer2_done_event), eight SMs are left to it: a persistent
+    // CTA that cannot become resident next to the collective's CTAs would otherwise run its whole share after everybody else)
+    const int n_cta = t5 ? num_sms() - (layer2_done_event != nullptr && num_sms() > 16 ? 8 : 0) : (bt->B < num_sms() ? bt->B : num_sms());
 
     BwdArgs g{};
     g.a.params = params;

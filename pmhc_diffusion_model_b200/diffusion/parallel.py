@@ -138,8 +138,9 @@ class DataParallelTrainer:
             return
         second, first = self._buckets(flat_grad)
         if not self.overlap or self._event is None or not getattr(self.dm, "last_step_overlapped", True):
-            allreduce_sum_(second, self.group)
-            allreduce_sum_(first, self.group)
+            # nothing to overlap with (e.g. the gradient step was one CUDA-graph replay): ONE latency-bound all-reduce over the whole flat
+            # gradient — the span that never carries a gradient holds zeros and costs less than a second collective's launch
+            allreduce_sum_(flat_grad, self.group)
             return
         main = torch.cuda.current_stream(flat_grad.device)
         comm = self._comm
