@@ -19,9 +19,11 @@
 //     are read back with 1 / s.
 //   * every weight-gradient sum of the CTA stays in tensor memory for the whole launch (dF: two M = 128 accumulators over head pairs
 //     (rotation, torsion) and (translation, attention), dW3 and the extras / bias columns: 16 columns each) and is written to the
-//     CTA's partial once, at the end; a pass needs three MMA batches (hidden layers of all four heads; pair A; pair B) issued by a
-//     dedicated warp, and the 256 compute threads work as two threads per pair, one HEAD each (rotation | torsion, then
-//     translation | attention), each on the full 64-wide hidden vector read from its TMEM lane.
+//     CTA's partial once, at the end; a pass needs three MMA batches (hidden layers of all four heads; pair A; pair B) plus a small one
+//     for the per-row sums, issued by a dedicated warp, and the 256 compute threads work as two threads per pair, one HEAD each
+//     (rotation | torsion, then translation | attention), walking the 64 hidden units of their TMEM lane in chunks of 16.
+//   * passes are COLUMN-major and dealt to the CTAs by pass (bwd_schedule_kernel); everything of a complex that is per node rather
+//     than per pair runs in its own kernels: bwd_setup_pre_kernel, bwd_feature_pre_kernel (layer 1), bwd_node_post_kernel.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -363,19 +365,6 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
-// write 64 floats (scaled) as one fp16 row of a SW128 tile: 8 chunks of 16 bytes at their swizzled positions
-__device__ __forceinline__ void t5_store_row64(uint8_t* tile, int p, const float (&v)[kHid], float scale) {
-    uint8_t* row = tile + (p >> 3) * 1024 + (p & 7) * 128;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        uint4 u;
-        u.x = pack_h2_sat(v[8 * q + 0] * scale, v[8 * q + 1] * scale);
-        u.y = pack_h2_sat(v[8 * q + 2] * scale, v[8 * q + 3] * scale);
-        u.z = pack_h2_sat(v[8 * q + 4] * scale, v[8 * q + 5] * scale);
-        u.w = pack_h2_sat(v[8 * q + 6] * scale, v[8 * q + 7] * scale);
-        *reinterpret_cast<uint4*>(row + ((q ^ (p & 7)) << 4)) = u;
-    }
-}
 // one 16-byte chunk (8 fp16 columns starting at column 8 * chunk) of row p
 __device__ __forceinline__ void t5_store_chunk(uint8_t* tile, int p, int chunk, float v0, float v1, float v2, float v3, float v4, float v5,
                                                float v6, float v7) {
@@ -383,16 +372,6 @@ __device__ __forceinline__ void t5_store_chunk(uint8_t* tile, int p, int chunk, 
     u.x = pack_h2_sat(v0, v1); u.y = pack_h2_sat(v2, v3); u.z = pack_h2_sat(v4, v5); u.w = pack_h2_sat(v6, v7);
     *reinterpret_cast<uint4*>(tile + (p >> 3) * 1024 + (p & 7) * 128 + ((chunk ^ (p & 7)) << 4)) = u;
 }
-// the thread's 64 accumulator columns of TMEM lane (pair) p
-__device__ __forceinline__ void t5_load64(uint32_t taddr, float (&v)[kHid]) {
-    uint32_t r0[32], r1[32];
-    tc::tmem_ld32_nowait(taddr, r0);
-    tc::tmem_ld32_nowait(taddr + 32, r1);
-    tc::tmem_wait_ld();
-#pragma unroll
-    for (int c = 0; c < 32; ++c) { v[c] = __uint_as_float(r0[c]); v[32 + c] = __uint_as_float(r1[c]); }
-}
-
 // ---- the MMA-issuing warp: the three batches of one attention-carrying pass (np = running pass count of the CTA, q = pass of the complex) ----
 __device__ __forceinline__ void t5_issue_pass(uint32_t sbase, uint32_t tmem, uint64_t* bars, uint32_t np, int q) {
     const uint32_t par = np & 1u;
@@ -1059,7 +1038,6 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
         tc::bulk_g2s(S + T.Cvec, x.wimg + 4 * 8192, kFoldTailFloats * 4, bars + 8);
     }
     if (LAYER == 1) {   // (layer 1's partial rows were zeroed by bwd_feature_pre_kernel, which already added feature_mlp's gradients)
-        static_assert((param_offset(1, 0) % 4) == 0 || true, "");
         float4* d4 = reinterpret_cast<float4*>(g.partial + (size_t)blockIdx.x * g.partial_stride + kTileFloats);   // 16-byte aligned: stride and kTileFloats are multiples of 4
         for (int idx = tid; idx < layer_numel / 4; idx += kT5Threads) d4[idx] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         for (int idx = (layer_numel & ~3) + tid; idx < layer_numel; idx += kT5Threads) direct[idx] = 0.0f;
