@@ -403,18 +403,55 @@ def test_tf32_backward_gradients_vs_oracle_autograd(api, B, L, Pn, P_pad, seed, 
 
 
 def test_tf32_backward_refuses_pockets_beyond_its_shared_memory(api):
-    """The tensor-core backward keeps more per-pass tiles in shared memory than the FFMA one: pockets up to 432 slots fit
-    (FFMA mode: 480).  Beyond that the call fails with the shared-memory message — it does not switch mode silently."""
+    """The TF32 mma.sync backward keeps more per-pass tiles in shared memory than the others: pockets up to 432 slots fit
+    (FFMA and tcgen05 modes: 480).  Beyond that the call fails with the shared-memory message — it does not switch mode silently."""
     batch = orc.synthetic_batch(1, 9, 100, P_pad=480, seed=2)
     model = make_model(api, orc.random_params(seed=1), 100)
     model.backward_precision = "bf16"
     out = model(gpu_batch(batch), 10)
     with pytest.raises(RuntimeError, match="shared memory"):
         out["torsions"].sum().backward()
-    model.backward_precision = "fp32"
-    out = model(gpu_batch(batch), 10)
-    out["torsions"].sum().backward()
-    assert all(p.grad is not None for k, p in model.named_parameters() if not k.startswith("gnn2.feature_mlp"))
+    grads = {}
+    for mode in ("fp32", "fp16"):       # the FFMA and the tcgen05 backward take the largest pocket
+        model.zero_grad(set_to_none=True)
+        model.backward_precision = mode
+        out = model(gpu_batch(batch), 10)
+        out["torsions"].sum().backward()
+        assert all(p.grad is not None for k, p in model.named_parameters() if not k.startswith("gnn2.feature_mlp"))
+        grads[mode] = torch.cat([p.grad.flatten() for k, p in model.named_parameters() if p.grad is not None]).double()
+    cos = float(grads["fp16"] @ grads["fp32"] / (grads["fp16"].norm() * grads["fp32"].norm()))
+    assert cos > 0.9999, cos
+
+
+def test_tcgen05_backward_is_linear_in_the_batch_whatever_the_schedule(api):
+    """The tcgen05 backward deals 128-pair passes to the SMs (a complex may be shared by consecutive CTAs, each with its own
+    accumulator slot): the schedule depends on the batch, the gradient must not.  B = 300 mixed complexes against the sum of three
+    unequal parts (7 + 150 + 143 complexes: from 'every complex split over many CTAs' to 'several complexes per CTA'), same noise."""
+    T = 1000
+    batch = orc.synthetic_batch(300, (8, 15), (30, 80), P_pad=80, seed=111)
+    params = orc.random_params(seed=16)
+    gb = gpu_batch(batch)
+    torch.manual_seed(17)
+    noise = api.DMO.gen_noise([300, 16], torch.device(DEV))
+    nf, nt = noise["frames"].to_tensor_7(), noise["torsions"]
+
+    def grads(sl):
+        model = make_model(api, params, T)
+        model.precision, model.backward_precision = "fp32", "fp16"
+        dm = api.DMO(T, model, 0.0)
+        captured = {}
+        dm.grad_hook = lambda g: captured.setdefault("g", g.clone())
+        sub = {k: v[sl] for k, v in gb.items()}
+        dm.optimize(sub, None, t=321, noise={"frames": api.Rigid.from_tensor_7(nf[sl]), "torsions": nt[sl]}, loss_scale=1.0 / 300)
+        return captured["g"]
+
+    full = grads(slice(0, 300))
+    parts = grads(slice(0, 7)) + grads(slice(7, 157)) + grads(slice(157, 300))
+    # (the operand scale 2^-floor(log2 max|upstream gradient|) is taken per call: the parts may round their fp16 operands on another
+    # grid than the whole batch does, so the comparison is at the mode's operand precision, not at fp32 rounding)
+    assert float((full - parts).abs().max()) < 2e-3 * float(full.abs().max())
+    fg, pg = full.double(), parts.double()
+    assert float(fg @ pg / (fg.norm() * pg.norm())) > 0.999999
 
 
 def test_flat_adam_matches_torch_adam_and_exchanges_state(api):
