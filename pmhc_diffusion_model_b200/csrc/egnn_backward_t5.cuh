@@ -35,11 +35,14 @@ namespace pmhc {
 constexpr int kT5Threads = 288;   // 8 compute warps (two threads per pair) + 1 MMA-issuing warp
 constexpr int kT5Compute = 256;
 // operand tiles: byte offsets from the 1024-byte aligned base of dynamic shared memory
-constexpr int T5_M1 = 0, T5_F = 16384, T5_HID = 49152, T5_DPRE = 81920, T5_DX = 114688, T5_TILE_BYTES = 131072;
+constexpr int T5_M1 = 0, T5_M1B = 16384, T5_F = 32768, T5_HID = 65536, T5_DPRE = 98304, T5_DX = 131072, T5_TILE_BYTES = 147456;
+// (two m1 tiles: pass p uses the one of parity p & 1, so the next pass's tile is staged under this pass's last MMA batches)
+__host__ __device__ constexpr int t5_m1_tile(uint32_t np) { return (np & 1u) ? T5_M1B : T5_M1; }
 constexpr int T5_RED = T5_HID;                       // fp32 [64][132] tile of dm1 over the (then free) hid / dpre tiles
 constexpr int T5_DM1H = T5_DPRE + 16384;             // the same as an fp16 operand tile (per-row sums on the tensor core)
 constexpr int T5_RED2 = T5_HID + 64 * kLdc * 4;      // message-only passes: fp32 [64][132] tile of mult * m1
 static_assert(T5_RED + 64 * kLdc * 4 <= T5_DM1H, "the fp32 and fp16 dm1 tiles must not overlap");
+static_assert(T5_DM1H > T5_M1B, "the stacked [m1 | dm1] operand needs the dm1 tile behind both m1 tiles");
 static_assert(T5_HID / 4 + 2 * kHid * kLdt + kHid * PMHC_NFEAT + 96 + kN * kHid <= T5_TILE_BYTES / 4, "staging views must fit behind the folded weights");
 static_assert(T5_RED2 + 64 * kLdc * 4 <= T5_TILE_BYTES, "reduction tiles must fit over the hid / dpre / dx tiles");
 // DX tile columns (fp16): second-layer output gradients of head pair A / B, the extra-input block shared by all heads
@@ -387,7 +390,7 @@ __device__ __forceinline__ void t5_issue_pass(uint32_t sbase, uint32_t tmem, uin
     tc::mbar_wait_suspend(rdy + 0, par);
     tc::fence_after_thread_sync();
     if (tc::elect_one()) {
-        const uint64_t da = tc::smem_desc_sw128(sbase + T5_M1);
+        const uint64_t da = tc::smem_desc_sw128(sbase + t5_m1_tile(np));
 #pragma unroll
         for (int pair = 0; pair < 2; ++pair) {
             const uint64_t db = tc::smem_desc_sw128(sbase + T5_F + pair * 16384);
@@ -416,7 +419,7 @@ __device__ __forceinline__ void t5_issue_pass(uint32_t sbase, uint32_t tmem, uin
 #pragma unroll
             for (int s = 0; s < 8; ++s)
                 tc::mma_bf16(tmem + (pair == 0 ? TM_DFA : TM_DFB), tc::smem_desc(sbase + T5_DPRE + s * 2048, 16384, 1024, 2),
-                             tc::smem_desc(sbase + T5_M1 + s * 2048, 16384, 1024, 2), id_w64, s > 0 ? 1u : keep);
+                             tc::smem_desc(sbase + t5_m1_tile(np) + s * 2048, 16384, 1024, 2), id_w64, s > 0 ? 1u : keep);
 #pragma unroll
             for (int s = 0; s < 8; ++s)
                 tc::mma_bf16(tmem + TM_DW3, tc::smem_desc(sbase + T5_HID + s * 2048, 16384, 1024, 2),
@@ -443,7 +446,7 @@ __device__ __forceinline__ void t5_issue_pass(uint32_t sbase, uint32_t tmem, uin
     if (tc::elect_one()) {
 #pragma unroll
         for (int s = 0; s < 8; ++s)
-            tc::mma_bf16(tmem + TM_ROW, tc::smem_desc(sbase + T5_M1 + s * 2048, T5_DM1H - T5_M1, 1024, 2),
+            tc::mma_bf16(tmem + TM_ROW, tc::smem_desc(sbase + t5_m1_tile(np) + s * 2048, (uint32_t)(T5_DM1H - t5_m1_tile(np)), 1024, 2),
                          tc::smem_desc(sbase + T5_DX + DX_SEL * 2 + s * 2048, 16384, 1024, 2), id_w16, s > 0 ? 1u : keep_c);
         tc::mma_commit(done + 3);
     }
@@ -504,6 +507,36 @@ __device__ __forceinline__ void t5_request_pair(float (&aj)[32], float& logit, c
     logit = __ldcg(g.logits + ((size_t)b * kN + pr.i) * Kpad + pr.j);
 }
 
+// m1 = relu(A_i + A_j + W_e) of pair `pr` (this thread's half of the features) -> fp16 row of the m1 tile of pass np; returns the relu mask
+template <int LAYER>
+__device__ __forceinline__ uint32_t t5_stage_m1(uint8_t* sb, const float* S, const BwdMap& M, const LayerArgs& a, const PairRef pr, int p, int half,
+                                                uint32_t np, float (&aj)[32]) {
+    constexpr int H = layer_H(LAYER);
+    constexpr int ld1 = 2 * H + kEdge;
+    const int k0 = 32 * half;
+    const float* ai = S + M.f.Ai + pr.i * kLdN + k0;
+    if (pr.j >= 0 && pr.j < kN) {
+        const float* we = a.params + param_offset(LAYER, MSG0_W) + 2 * H + (kN - 1 + pr.i - pr.j) + (size_t)k0 * ld1;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) aj[k] += __ldg(we + k * ld1);
+    }
+    uint32_t mask = 0u;
+    uint8_t* row = sb + t5_m1_tile(np) + (p >> 3) * 1024 + (p & 7) * 128;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float m[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            m[e] = fmaxf(ai[8 * q + e] + aj[8 * q + e], 0.0f);
+            mask |= (m[e] > 0.0f ? 1u : 0u) << (8 * q + e);
+        }
+        uint4 u;
+        u.x = pack_h2_sat(m[0], m[1]); u.y = pack_h2_sat(m[2], m[3]); u.z = pack_h2_sat(m[4], m[5]); u.w = pack_h2_sat(m[6], m[7]);
+        *reinterpret_cast<uint4*>(row + (((4 * half + q) ^ (p & 7)) << 4)) = u;
+    }
+    return mask;
+}
+
 // ---- compute threads: one attention-carrying pass of up to 128 pairs ----
 // Two threads per pair, one head each: threads 0..127 rotation then translation, threads 128..255 torsion then attention.  A head is
 // walked in four chunks of 16 hidden units (runtime loops: the pass code stays inside the instruction cache): chunk loop 1 forms the
@@ -512,9 +545,9 @@ template <int LAYER>
 __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map& T, const BwdArgs& g, const PairRef pr, int b,
                                               const float* __restrict__ ajt, float* __restrict__ dajt, const int* I, int L, int rl,
                                               int e0, int ncols, uint32_t np, uint32_t tmem, float gs, float inv_gs,
-                                              float (&aj)[32], float& logit_io, const PairRef nxt, const bool has_next) {
-    // aj / logit_io: this pass's A_j^T column half and saved logit, loaded by the previous pass (or the caller) — on return they hold
-    // the next pass's (pair `nxt`), requested under pair B's MMAs so their L2 round trip is off the critical path
+                                              float (&aj)[32], float& logit_io, const PairRef nxt, const bool has_next, uint2& m1mask_io) {
+    // aj / logit_io: this pass's A_j^T column half and saved logit, loaded by the caller for the first pass of a segment; m1mask_io =
+    // {relu mask of this pass's m1, staged flag}: set by the previous pass when it staged this pass's m1 tile, and set for the next here
     // Pairs of a pass are COLUMN-major: pair p = (neighbour column e0 + p / L, peptide row p % L), whole columns only.  A pocket
     // column's L pairs are then adjacent (its dL / dA_j is complete inside the pass: a plain store), and a row's pairs are L apart
     // (per-row sums go through the one-hot row selector on the tensor core; shared-memory atomics see at most 4 lanes per row).
@@ -541,33 +574,10 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
 #ifdef PMHC_T5_STAMPS
     long long pst_ = clock64();
 #endif
-    // ---- m1 (my half of its features) -> fp16 tile; geometry; the extra-input blocks and the row selector ----
-    uint32_t m1mask = 0u;
-    {
-        constexpr int H = layer_H(LAYER);
-        constexpr int ld1 = 2 * H + kEdge;
-        const int k0 = 32 * half;
-        const float* ai = S + M.f.Ai + i * kLdN + k0;
-        if (pep) {
-            const float* we = a.params + param_offset(LAYER, MSG0_W) + 2 * H + (kN - 1 + i - j) + (size_t)k0 * ld1;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) aj[k] += __ldg(we + k * ld1);
-        }
-        if (np > 0) tc::mbar_wait_suspend(done + 3, (np - 1) & 1u);   // the previous pass's row sums have read the m1 tile and the selector
-        uint8_t* row = sb + T5_M1 + (p >> 3) * 1024 + (p & 7) * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float m[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                m[e] = fmaxf(ai[8 * q + e] + aj[8 * q + e], 0.0f);
-                m1mask |= (m[e] > 0.0f ? 1u : 0u) << (8 * q + e);
-            }
-            uint4 u;
-            u.x = pack_h2_sat(m[0], m[1]); u.y = pack_h2_sat(m[2], m[3]); u.z = pack_h2_sat(m[4], m[5]); u.w = pack_h2_sat(m[6], m[7]);
-            *reinterpret_cast<uint4*>(row + (((4 * half + q) ^ (p & 7)) << 4)) = u;
-        }
-    }
+    // ---- m1 (my half of its features) -> fp16 tile, unless the previous pass staged it already; geometry; extras; row selector ----
+    if (np > 0) tc::mbar_wait_suspend(done + 3, (np - 1) & 1u);   // the previous pass's row sums have read their m1 tile and the selector
+    const bool prestaged = m1mask_io.y != 0u;
+    const uint32_t m1mask = prestaged ? m1mask_io.x : t5_stage_m1<LAYER>(sb, S, M, a, pr, p, half, np, aj);
     const float* rg = S + M.RowG + i * 16;
     const float lse = rg[15], c_i = rg[14];
     const float logit = logit_io;
@@ -600,7 +610,7 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
     if (tid == 0) sPl[0] = 0;      // (every reader of the previous pass's list is behind that pass's last barrier)
     tc::fence_proxy_async_smem();
     tc::fence_before_thread_sync();
-    tc::mbar_arrive(rdy + 0);
+    if (!prestaged) tc::mbar_arrive(rdy + 0);
     T5_PSTAMP(0);
 
     float gi[7] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // layer 2: this thread's share of dL / d (q_i, x_i)
@@ -846,7 +856,18 @@ __device__ __forceinline__ void t5_heads_pass(uint8_t* sb, float* S, const T5Map
     tc::fence_proxy_async_smem();
     tc::mbar_arrive(rdy + 2);
     T5_PSTAMP(6);
-    if (has_next) t5_request_pair(aj, logit_io, g, b, ajt, Kpad, nxt, half);
+    if (has_next) {
+        // the next pass of this segment: its operands from L2, its m1 tile (the other buffer) and its batch-0 signal — all under
+        // pair B's MMAs, so the next pass starts at its hidden-layer wait
+        t5_request_pair(aj, logit_io, g, b, ajt, Kpad, nxt, half);
+        m1mask_io.x = t5_stage_m1<LAYER>(sb, S, M, a, nxt, p, half, np + 1, aj);
+        m1mask_io.y = 1u;
+        tc::fence_proxy_async_smem();
+        tc::fence_before_thread_sync();
+        tc::mbar_arrive(rdy + 0);
+    } else {
+        m1mask_io.y = 0u;
+    }
     if (IN_GRADS && act && half == 1) {
         // attention head's input gradients (under pair B's MMAs)
         const float f = -gd_keep * 2.0f;                 // d(-d2) = gd
@@ -1117,6 +1138,7 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
                 pr.j = e < L - 1 ? I[IN_ROWS + (e < rl ? e : e + 1)] : I[IN_POCKET + (e - (L - 1))];
             };
             float aj[32], logit = 0.0f;
+            uint2 m1state = make_uint2(0u, 0u);
             PairRef pr, nxt;
             int rl = 0, e0 = 0, ncols = 0, rl_n = 0, e0_n = 0, ncols_n = 0;
             if (npasses > 0) {
@@ -1127,7 +1149,7 @@ __global__ void __launch_bounds__(kT5Threads, 1) egnn_layer_backward_t5_kernel(B
                 const bool has_next = q + 1 < npasses;
                 if (has_next) decode(q + 1, nxt, rl_n, e0_n, ncols_n);
                 else nxt = pr;
-                t5_heads_pass<LAYER>(sb, S, T, g, pr, b, ajt, dajt, I, L, rl, e0, ncols, np + q, tmem, gs, inv_gs, aj, logit, nxt, has_next);
+                t5_heads_pass<LAYER>(sb, S, T, g, pr, b, ajt, dajt, I, L, rl, e0, ncols, np + q, tmem, gs, inv_gs, aj, logit, nxt, has_next, m1state);
                 pr = nxt; rl = rl_n; e0 = e0_n; ncols = ncols_n;
             }
             if (npasses > 0) tc::mbar_wait_suspend(bars + 4 + 3, (np + npasses - 1) & 1u);   // the last pass's per-row sums
