@@ -304,6 +304,7 @@ def main():
     ap.add_argument("--no-io", action="store_true", help="skip the HDF5 loader / PDB writer leg")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every launch of a trajectory / training step instead of replaying a CUDA graph")
     ap.add_argument("--no-modes", action="store_true", help="skip the other arithmetic modes and the other BASELINE configs")
+    ap.add_argument("--capture-allreduce", action="store_true", help="N > 1: capture the gradient all-reduce and Adam into the training step's CUDA graph (experimental)")
     ap.add_argument("--precision", default="tc32", choices=["fp32", "tc32", "fp16", "bf16"],
                     help="arithmetic of the denoiser's dense per-pair contractions in the headline legs (see include/pmhc_b200.h)")
     args = ap.parse_args()
@@ -475,6 +476,7 @@ def main():
         tmodel = tmodel.to(dev)
         tdm = DiffusionModelOptimizer(T_TRAIN, tmodel, 1e-3)
         tdm.use_graph = not args.no_graph      # N > 1: the gradient step is one graph, the two all-reduces and Adam follow it
+        tdm.capture_grad_hook = bool(args.capture_allreduce)
         from pmhc_diffusion_model_b200.diffusion.parallel import DataParallelTrainer
         trainer = DataParallelTrainer(tdm, seed=0)   # N = 1: plain optimize(); N > 1: shared t + overlapped NCCL all-reduce
         n_train = 20
@@ -584,6 +586,9 @@ def main():
         sys.stdout.flush()
         os.write(json_fd, (line + "\n").encode())
     if world > 1:
+        if not args.no_train and args.capture_allreduce:
+            tdm._step_states.clear()          # captured graphs hold the communicator: release them before it goes
+            torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
