@@ -1050,7 +1050,7 @@ __global__ void __launch_bounds__(1024) order_kernel(const uint8_t* __restrict__
 //   aij1[b][i][0:64]     = bf16( b1 + W1_0[k, 0:22] . features[b][i] )   (A_i of layer 1 without the time term, which the
 //   aij1[b][i][64:128]   = bf16(      W1_0[k, 23:45] . features[b][i] )   pair kernel adds per step)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) node_pre_kernel(const float* __restrict__ params, const float* __restrict__ feat,
+__global__ void __launch_bounds__(256) node_pre_kernel(const float* __restrict__ params, const float* __restrict__ feat,
                                                        const float* __restrict__ pocket_feat, const uint8_t* __restrict__ pocket_mask,
                                                        int P, int cls_stride, __nv_bfloat16* __restrict__ pk_cache,
                                                        uint8_t* __restrict__ cls, __nv_bfloat16* __restrict__ aij1) {
@@ -1415,11 +1415,11 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
     Tc2Workspace w = carve_tc2(tc2_ws, B, P);
     if (!reuse_pocket_cache) {
         // step-invariant: operand tiles of both layers, pocket projections, static peptide projections
-        tc2::weight_image_kernel<0><<<8, 256, 0, stream>>>(params, w.wimage);
+        tc2::weight_image_kernel<0><<<32, 256, 0, stream>>>(params, w.wimage);
         PMHC_CHECK_LAUNCH("weight_image");
-        tc2::weight_image_kernel<1><<<8, 256, 0, stream>>>(params, w.wimage + w.image_bytes);
+        tc2::weight_image_kernel<1><<<32, 256, 0, stream>>>(params, w.wimage + w.image_bytes);
         PMHC_CHECK_LAUNCH("weight_image");
-        tc2::node_mid_image_kernel<<<8, 256, 0, stream>>>(params, P, w.nm_image);
+        tc2::node_mid_image_kernel<<<32, 256, 0, stream>>>(params, P, w.nm_image);
         PMHC_CHECK_LAUNCH("node_mid_image");
         const size_t smem = (size_t)(((P * 23 + 3) & ~3) + 2 * kHid * 23 + kN * 23 + 1 + 128 * 23) * sizeof(float);
         static PerDeviceOnce configured;
@@ -1428,7 +1428,7 @@ int forward_tc2(const float* params, const PmhcBatch* bt, float t_over_T, float*
             PMHC_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(node_pre): %s", cudaGetErrorString(e));
             configured.mark();
         }
-        tc2::node_pre_kernel<<<B, 128, smem, stream>>>(params, bt->features, bt->pocket_features, bt->pocket_mask, P, w.cls_stride,
+        tc2::node_pre_kernel<<<B, 256, smem, stream>>>(params, bt->features, bt->pocket_features, bt->pocket_mask, P, w.cls_stride,
                                                        w.pk_cache, w.cls, w.aij1);
         PMHC_CHECK_LAUNCH("node_pre");
         tc2::order_kernel<<<1, 1024, tc2::kOrderBins * sizeof(int), stream>>>(bt->mask, bt->pocket_mask, B, P, 2 * num_sms(), w.keys, w.order);
