@@ -15,7 +15,7 @@ from pmhc_diffusion_model_b200.rigid import Rigid, Rotation             # noqa: 
 
 DEV = torch.device("cuda:0")
 CASES = {"small": (3, (9, 9), (60, 60), 80, 5), "ragged": (5, (2, 16), (3, 50), 50, 41), "groove": (7, (8, 15), (40, 180), 192, 77),
-         "big": (2, (8, 15), (150, 400), 400, 13), "one": (1, (9, 9), (60, 60), 80, 5)}
+         "big": (2, (8, 15), (150, 400), 400, 13), "one": (1, (9, 9), (60, 60), 80, 5), "tiny": (6, (1, 3), (1, 5), 8, 21), "nopocket": (4, (2, 16), (0, 1), 8, 22)}
 
 
 def main():

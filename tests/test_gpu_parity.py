@@ -341,7 +341,7 @@ def test_parameter_gradients_edge_shapes_vs_oracle_autograd(api):
 
 @pytest.mark.parametrize("bmode", ["bf16", "fp16"])
 @pytest.mark.parametrize("B,L,Pn,P_pad,seed", [(5, (2, 16), (3, 50), 50, 41), (7, (8, 15), (40, 180), 192, 77), (3, (9, 9), (60, 60), 80, 5),
-                                              (2, (8, 15), (150, 400), 400, 13)])
+                                              (2, (8, 15), (150, 400), 400, 13), (4, (2, 16), (0, 1), 8, 22)])
 def test_tf32_backward_gradients_vs_oracle_autograd(api, B, L, Pn, P_pad, seed, bmode):
     """Tensor-core backward on its own (fp32 forward, backward_precision = "bf16"): the forward recomputation, the input
     gradients and the weight-gradient outer products run as TF32 MMAs.  Ragged peptides, dirty padding (message-only pairs
