@@ -423,6 +423,26 @@ def test_tf32_backward_refuses_pockets_beyond_its_shared_memory(api):
     assert cos > 0.9999, cos
 
 
+def test_tcgen05_backward_is_reproducible_to_fp32_rounding(api):
+    """Eight identical steps (lr 0, same t and noise key): the tcgen05 backward's only unordered sums are shared-memory atomics on
+    per-node accumulators, so run-to-run differences must stay at fp32 rounding — a hazard between its four MMA batches, its tile
+    reuse or its kernels would show up as something larger, sooner or later."""
+    batch = orc.synthetic_batch(150, (8, 15), (30, 180), P_pad=192, seed=71)
+    model = make_model(api, orc.random_params(seed=3), 1000)
+    model.precision, model.backward_precision = "bf16", "fp16"
+    dm = api.DMO(1000, model, 0.0)
+    cap = {}
+    dm.grad_hook = lambda g: cap.__setitem__("g", g.clone())
+    gb = gpu_batch(batch)
+    runs = []
+    for _ in range(8):
+        dm.optimize(dict(gb), None, t=321, noise_key=77)
+        runs.append(cap["g"])
+    assert bool(torch.isfinite(runs[0]).all())
+    scale = float(runs[0].abs().max())
+    assert max(float((g - runs[0]).abs().max()) for g in runs[1:]) < 1e-4 * scale
+
+
 def test_tcgen05_backward_is_linear_in_the_batch_whatever_the_schedule(api):
     """The tcgen05 backward deals 128-pair passes to the SMs (a complex may be shared by consecutive CTAs, each with its own
     accumulator slot): the schedule depends on the batch, the gradient must not.  B = 300 mixed complexes against the sum of three
