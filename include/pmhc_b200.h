@@ -41,7 +41,9 @@ extern "C" {
  *         hi.hi + lo.hi + hi.lo with fp32 accumulation in TMEM: fp32-class results (gate: the FP32 mode's own, max(1e-4, 2 x the
  *         reference's fp32 noise floor)) — the tensor-core mode that holds on the reference's shipped model.pth;
  *   FP16: the same pipeline with single fp16 terms (11 bits; 1e-2 class on well-conditioned weights).
- * Both are forward modes; pmhc_model_backward_ex takes FP32 or BF16. */
+ * As BACKWARD modes (pmhc_model_backward_ex, pmhc_train_step_grad): FP32 = the FFMA backward, FP16 = the backward on tcgen05
+ *   (fp16 operand tiles, fp32 accumulation in tensor memory, 1e-2 class), BF16 = the older warp-level TF32 mma.sync backward;
+ *   TC32 is not a backward mode (a TC32 forward pairs with the FP32 backward, or with FP16 for 1e-2-class gradients). */
 #define PMHC_PRECISION_TC32 2
 #define PMHC_PRECISION_FP16 3
 
@@ -102,7 +104,12 @@ int pmhc_model_backward(const float *params, const PmhcBatch *batch_host, float 
 /* Same with an explicit PMHC_PRECISION_* mode (pmhc_model_backward == PMHC_PRECISION_FP32).  PMHC_PRECISION_BF16 selects the
  * tensor-core backward: every 64-wide contraction of the pair recomputation, the input gradients and the weight-gradient
  * outer products as TF32 MMAs with fp32 accumulation (operands rounded to tf32, i.e. more mantissa than the bf16 forward);
- * second layers, geometry, softmax backward and all reductions stay fp32.  Gradient gate: the 1e-2 class. */
+ * second layers, geometry, softmax backward and all reductions stay fp32.  Gradient gate: the 1e-2 class.
+ * PMHC_PRECISION_FP16 selects the backward on the Blackwell tensor-core path (tcgen05.mma, accumulators in tensor memory): the
+ * message layer folded into the head weights, fp16 operand tiles used K-major and MN-major, every weight-gradient sum of a CTA
+ * resident in tensor memory, work dealt to the SMs by 128-pair pass; per layer it enqueues the setup, schedule, pair, node,
+ * reduce and unfold kernels (+ layer 1's feature pre-kernel) on `stream`.  Same gate; 3.7x the TF32 kernel's speed.  When
+ * layer2_done_event is given it leaves eight SMs to the collective the caller overlaps with the layer-1 launch. */
 int pmhc_model_backward_ex(const float *params, const PmhcBatch *batch_host, float t_over_T,
                            const float *saved, const float *d_out_frames, const float *d_out_torsions,
                            float *flat_grad, void *workspace, size_t workspace_bytes, void *stream,
