@@ -514,7 +514,7 @@ def main():
             lprof_ms, lprof_n = kernel_times(legacy_step, n_train, tdm)
             legacy_leg.update({"config": "bf16 tcgen05 forward + warp-level TF32 mma.sync backward (round 1)",
                                "backward_kernel_us": lprof_ms[1] / max(lprof_n[1], 1) * 1e3})
-            bf16_leg["tf32_mma_backward"] = legacy_leg
+            bf16_leg["tf32_mma_backward"] = legacy_leg        # (kept under its old key too)
             mixed_leg, _ = train_leg(tb, "tc32", "fp16")
             mixed_leg["config"] = "tcgen05 hi/lo-split forward (fp32-class outputs and loss) + tcgen05 fp16 backward (1e-2-class gradients)"
             bf16_leg["tc32_forward"] = mixed_leg
@@ -522,6 +522,10 @@ def main():
         train = {"metric": "train complexes/s", **fp32_leg, "steps": n_train,
                  "config": "B=256/GPU, 9-mer, pocket 60/80, fp32 FFMA forward + backward, noise+forward+loss+backward+Adam per step (BASELINE configs[2], [3] at N=8)",
                  "tc32": tc32_leg, "bf16": bf16_leg}
+        if "tc32_forward" in bf16_leg:
+            # fp32-class forward and loss + tcgen05 backward: the fast combination that also holds on the shipped checkpoint
+            # (tests: ..._holds_on_the_shipped_checkpoint, ..._track_the_fp32_loss_curve)
+            train["tc32_fp16_backward"] = bf16_leg["tc32_forward"]
         if world == 1 and not args.no_modes:
             # BASELINE configs[2] variant B: the whole M = 180 groove as the pocket (padded to 192)
             tb2 = {k: v.to(dev) for k, v in synthetic(TRAIN_B, seed=6000 + rank, P_pad=192, pocket_n=180).items()}

@@ -30,7 +30,8 @@ arg_parser.add_argument("-T", type=int, help="number of noise steps", default=10
 arg_parser.add_argument("--batch-size", "-b", type=int, help="data batch size", default=64)
 arg_parser.add_argument("--num-workers", "-w", type=int, help="accepted for compatibility; batches are built on the GPU", default=4)
 arg_parser.add_argument("--lr", type=float, help="learning rate", default=0.001)
-arg_parser.add_argument("--precision", choices=["fp32", "tc32", "bf16"], default="tc32", help="arithmetic of the denoiser: fp32 FFMA (exact parity), tc32 = tcgen05 forward with fp16 hi/lo operand splits (fp32-class) + fp32 backward, or bf16 = tcgen05 forward + TF32 tensor-core backward")
+arg_parser.add_argument("--precision", choices=["fp32", "tc32", "bf16"], default="tc32", help="arithmetic of the denoiser: fp32 FFMA (exact parity), tc32 = tcgen05 forward with fp16 hi/lo operand splits (fp32-class) + fp32 backward, or bf16 = tcgen05 bf16 forward + tcgen05 fp16 backward")
+arg_parser.add_argument("--backward-precision", choices=["fp32", "fp16", "bf16"], default=None, help="arithmetic of the backward on its own (default: follows --precision): fp32 FFMA, fp16 = the tcgen05 backward (1e-2-class gradients; with --precision tc32 the fast combination that holds on ill-conditioned checkpoints), bf16 = the older TF32 mma.sync backward")
 arg_parser.add_argument("--seed", type=int, default=None, help="seed of the batch order, noise steps and noise")
 arg_parser.add_argument("--checkpoint", default=None, help="full training state (weights, Adam, random streams, epoch): written "
                         "after every epoch and resumed from when the file exists")
@@ -64,6 +65,7 @@ def main(argv=None) -> None:
     if os.path.isfile(args.output_model):
         model.load_state_dict(torch.load(args.output_model, map_location=device), strict=True)
     model.precision = args.precision
+    model.backward_precision = args.backward_precision
     dm = DiffusionModelOptimizer(args.T, model, args.lr)
     trainer = DataParallelTrainer(dm, seed=args.seed if args.seed is not None else 0)
 
