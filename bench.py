@@ -305,6 +305,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="enqueue every launch of a trajectory / training step instead of replaying a CUDA graph")
     ap.add_argument("--no-modes", action="store_true", help="skip the other arithmetic modes and the other BASELINE configs")
     ap.add_argument("--capture-allreduce", action="store_true", help="N > 1: capture the gradient all-reduce and Adam into the training step's CUDA graph (experimental)")
+    ap.add_argument("--metric", default="sample", choices=["sample", "train"],
+                    help="which half of BASELINE.json's metric the JSON line headlines: sampled complexes/s (default; the training record rides along under `train`) "
+                         "or train complexes/s (the line is then the training step: value, e2e, roofline of the backward kernel, cpu_baseline = the reference's optimize())")
     ap.add_argument("--precision", default="tc32", choices=["fp32", "tc32", "fp16", "bf16"],
                     help="arithmetic of the denoiser's dense per-pair contractions in the headline legs (see include/pmhc_b200.h)")
     args = ap.parse_args()
@@ -509,15 +512,38 @@ def main():
                                                "unit": "TFLOP/s", "frac": bwd_flops / (bwd_us * 1e-6) / 1e12 / peaks["bf16_tflops"],
                                                "note": "algorithmic 3 x 43.4 kFLOP per pair per layer (the folded message layer executes fewer); "
                                                        "tcgen05 kind::f16, judged against the measured bf16 peak"}})
+        mixed_leg, mixed_step = train_leg(tb, "tc32", "fp16")
+        mixed_leg["config"] = "tcgen05 hi/lo-split forward (fp32-class outputs and loss) + tcgen05 fp16 backward (1e-2-class gradients)"
+        bf16_leg["tc32_forward"] = mixed_leg
+        train_e2e = None
+        if args.metric == "train":
+            # end to end through the public API: the batch comes from pinned host memory every step, the per-complex losses go back
+            mprof_ms, mprof_n = kernel_times(mixed_step, n_train, tdm)
+            mixed_leg["backward_kernel_us"] = mprof_ms[1] / max(mprof_n[1], 1) * 1e3
+            tmodel.precision, tmodel.backward_precision = "tc32", "fp16"
+            host_tb = {k: v.cpu().pin_memory() for k, v in tb.items()}
+
+            def train_step_e2e():
+                gbt = {k: v.to(dev, non_blocking=True) for k, v in host_tb.items()}
+                trainer.optimize(gbt, None)
+                return tdm.last_losses["total loss"].cpu()
+
+            for _ in range(3):
+                train_step_e2e()
+            barrier()
+            t0e = time.perf_counter()
+            for _ in range(n_train):
+                train_step_e2e()
+            barrier()
+            te = max_over_ranks((time.perf_counter() - t0e) * 1e3)
+            train_e2e = {"value": world * TRAIN_B * n_train / (te / 1e3), "unit": UNIT, "ms_per_step": te / n_train,
+                         "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host_tb.values())), "d2h_bytes_per_step": TRAIN_B * 4}
         if world == 1 and not args.no_modes:
             legacy_leg, legacy_step = train_leg(tb, "bf16", "bf16")   # the round-1 warp-level TF32 mma.sync backward, for comparison
             lprof_ms, lprof_n = kernel_times(legacy_step, n_train, tdm)
             legacy_leg.update({"config": "bf16 tcgen05 forward + warp-level TF32 mma.sync backward (round 1)",
                                "backward_kernel_us": lprof_ms[1] / max(lprof_n[1], 1) * 1e3})
-            bf16_leg["tf32_mma_backward"] = legacy_leg        # (kept under its old key too)
-            mixed_leg, _ = train_leg(tb, "tc32", "fp16")
-            mixed_leg["config"] = "tcgen05 hi/lo-split forward (fp32-class outputs and loss) + tcgen05 fp16 backward (1e-2-class gradients)"
-            bf16_leg["tc32_forward"] = mixed_leg
+            bf16_leg["tf32_mma_backward"] = legacy_leg
         tc32_leg["config"] = "fp32-class training: tcgen05 hi/lo-split forward + fp32 FFMA backward (gradient gate 1e-4, same as fp32)"
         train = {"metric": "train complexes/s", **fp32_leg, "steps": n_train,
                  "config": "B=256/GPU, 9-mer, pocket 60/80, fp32 FFMA forward + backward, noise+forward+loss+backward+Adam per step (BASELINE configs[2], [3] at N=8)",
@@ -566,7 +592,34 @@ def main():
             train["cpu_baseline"] = {"value": tr[0], "unit": UNIT, "cores": threads, "kind": ref.kind,
                                      "sample": f"optimize() on B={CPU_TRAIN_B} (BASELINE configs[0] shape), best of 3, {tr[1]:.2f} s per step"}
 
-    if rank == 0:
+    if rank == 0 and args.metric == "train" and train is not None:
+        leg = train["tc32_fp16_backward"]
+        bus = leg.get("backward_kernel_us")
+        bflops = TRAIN_B * 3.0 * 0.5 * forward_flops_per_complex()
+        line = json.dumps({
+            "metric": "train complexes/s (one optimize() step: noise, forward, loss, backward, Adam)", "value": leg["value"], "unit": UNIT,
+            "n_gpus": world, "steps": train["steps"], "warmup": W, "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16x2-split forward (fp32-class) + f16 tcgen05 backward, fp32 accumulation", "data": "synthetic",
+            "config": {"workload": f"training step, {TRAIN_B} complexes/GPU, 9-mer peptide, M=180 protein / 60 pocket residues padded to 80 (BASELINE configs[2]; [3] at N=8)",
+                       "complexes_per_gpu": TRAIN_B, "P_pad": P_PAD, "l2": "flushed between steps (256 MiB memset)",
+                       "launch": "one CUDA graph per step" + ("" if world == 1 else ", then one NCCL all-reduce of the flat gradient and Adam"),
+                       "weights": weights_note,
+                       "precision": "tc32 forward (parity gate of the fp32 mode on the reference fixtures) + tcgen05 fp16 backward (gradient gates: 2e-2 of each tensor's "
+                                    "largest entry vs the oracle's autograd, flat gradient cosine >= 0.99999; on the shipped checkpoint cosine 0.9999998 vs the fp32 backward)"},
+            "clocks": clocks.summary(),
+            "e2e": train_e2e,
+            "gpu_launches": None,
+            "roofline": None if bus is None else {"bound": "tensor", "achieved": bflops / (bus * 1e-6) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                                  "frac": bflops / (bus * 1e-6) / 1e12 / peaks["bf16_tflops"], "traffic": 12.2e6,
+                                                  "traffic_source": "profiles/prof_t5_r2_summary.csv", "peak_source": peaks["source"] + " bf16 sustained",
+                                                  "kernel": "egnn_layer_backward_t5_kernel<LAYER>", "kernel_ms": bus / 1e3,
+                                                  "note": "algorithmic 3 x 43.4 kFLOP per pair per layer; two launches per step"},
+            "cpu_baseline": train.get("cpu_baseline"),
+            "train": train,
+        })
+        sys.stdout.flush()
+        os.write(json_fd, (line + "\n").encode())
+    elif rank == 0:
         line = json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
