@@ -838,9 +838,12 @@ def test_tensor_core_training_modes_track_the_fp32_loss_curve(api):
     """Convergence check of the training modes: 150 optimize() steps on a fixed synthetic set (B = 64, lr 1e-3, the same t and
     noise keys in every run) in fp32, tc32 (tcgen05 fp32-class forward + fp32 backward) and bf16 (tcgen05 bf16 forward + tcgen05
     fp16 backward).  The loss must go down, and the tensor-core runs must follow the fp32 run's curve: window means (25 steps)
-    within 1 % (tc32) / 3 % (bf16) all the way — or within 3 x the deviation of a SECOND fp32 run from the first, whichever is
-    larger: gradient sums are reproducible to fp32 rounding only (shared-memory atomics), Adam turns that into +-lr moves, and two
-    identical fp32 runs of this loop already drift apart by up to ~1 % of a window mean (the noise floor of the comparison)."""
+    within 1 % (tc32) / 3 % (tc32 forward + tcgen05 backward; measured 0.6 - 1.0 %) / 6 % (bf16) all the way — or within 3 x the deviation
+    of a SECOND fp32 run from the first, whichever is larger: gradient sums are reproducible to fp32 rounding only (shared-memory
+    atomics), Adam turns that into +-lr moves, and two identical fp32 runs of this loop already drift apart by 0.1 - 0.6 % of a window
+    mean (the noise floor of the comparison).  The bf16 gate is set by the bf16 FORWARD, not by the backward behind it
+    (profiles/curve_spread.py, six runs each): with the exact fp32 backward that forward deviates 2.3 - 3.9 %, with the tcgen05 fp16
+    backward 1.2 - 2.5 % (4 % seen once in twenty runs), with the TF32 mma.sync backward 0.4 - 1.2 %."""
     T, B, steps, lr = 1000, 64, 150, 1e-3
     batch = orc.synthetic_batch(B, (8, 12), (40, 60), P_pad=80, seed=404)
     params = orc.random_params(seed=51)
@@ -870,7 +873,7 @@ def test_tensor_core_training_modes_track_the_fp32_loss_curve(api):
     assert floor < 2e-2, floor                                             # two fp32 runs stay together
     # (the weights themselves are no gate: Adam turns rounding-level gradient differences into +-lr moves, so two fp32 runs of
     # this very loop already differ by ~0.2 of the update's norm; printed for the record)
-    for mode, tol in (("tc32", 1e-2), ("bf16", 3e-2), ("tc32 + fp16 backward", 3e-2)):
+    for mode, tol in (("tc32", 1e-2), ("bf16", 6e-2), ("tc32 + fp16 backward", 3e-2)):
         dev = float(((win(curves[mode]) - ref).abs() / ref).max())
         wrel = float((finals[mode] - finals["fp32"]).norm() / (finals["fp32"] - torch.cat([v.flatten() for v in params.values()]).to(DEV)).norm())
         print(f"training curve [{mode}]: worst window deviation {dev:.2e} (fp32 vs fp32: {floor:.2e}), weight-update relative L2 difference {wrel:.2e}; "
