@@ -343,9 +343,11 @@ def test_parameter_gradients_edge_shapes_vs_oracle_autograd(api):
 @pytest.mark.parametrize("B,L,Pn,P_pad,seed", [(5, (2, 16), (3, 50), 50, 41), (7, (8, 15), (40, 180), 192, 77), (3, (9, 9), (60, 60), 80, 5),
                                               (2, (8, 15), (150, 400), 400, 13), (4, (2, 16), (0, 1), 8, 22)])
 def test_tf32_backward_gradients_vs_oracle_autograd(api, B, L, Pn, P_pad, seed, bmode):
-    """Tensor-core backward on its own (fp32 forward, backward_precision = "bf16"): the forward recomputation, the input
-    gradients and the weight-gradient outer products run as TF32 MMAs.  Ragged peptides, dirty padding (message-only pairs
-    with their own features), several passes per complex.
+    """A tensor-core backward on its own (fp32 forward, backward_precision = bmode): "bf16" = the warp-level kernel (forward recomputation,
+    input gradients and weight-gradient outer products as TF32 mma.sync MMAs), "fp16" = the tcgen05 kernel family (folded message layer,
+    fp16 operand tiles, weight-gradient sums in tensor memory, passes dealt over all SMs — at these batch sizes every complex is shared by
+    several CTAs).  Ragged peptides, dirty padding (message-only pairs with their own features), several passes per complex, pockets from
+    (almost) none to 400.
 
     Gates (tf32 operands carry 11 significant bits, so every recomputed activation is off by ~5e-4 relative):
       * every tensor: max error <= 2e-2 of its largest entry (measured 1e-4 .. 1.1e-2) ...
